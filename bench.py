@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""bench.py -- noisy Surface-17 shots/sec on B200 (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): PDD_model importance sampling, fixed-weight error subset
+[0,0,2,1,1] placed uniformly over the two-round slot lists [24,36,48,156,48], s2 protocol
+(calc_log_e_rate_arbitrary_error_model.py:355-457 of the reference): prep cycle, noisy cycle, second
+noisy cycle for shots whose syndrome changed, lookup decode, logical read-out, failure tally.
+A step = one batch of --shots shots per GPU.  Shots shard over ranks with no data-path collective; the
+only exchange is one all-reduce of the counters at the end (inside the timed region).
+
+`value`  : whole-job shots/s, device-timed (CUDA events on the library's launch stream), max over ranks.
+`e2e`    : the same through the reference-shaped Python entry point
+           surface_17_iqt_b200.calc_log_e_rate_arbitrary_error_model.s2_calculate_log_e_rate_error_subset
+           with host inputs and host results, wall-clock around the calls.
+`roofline`: the gate sweep kernel k_layer: algorithmic bytes (2 MiB read + 2 MiB write per shot per sweep;
+           the first sweep of a shot synthesises |0..0> and only writes) / summed CUDA-event kernel time.
+`cpu_baseline` / --impl reference: the oracle port (one CPU sweep per gate, ProjectQ's execution model,
+           python per-gate driver like the reference) on all host cores, bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+MODEL = "PDD_model"
+ESET = [0, 0, 2, 1, 1]
+LOCS2 = [24, 36, 48, 156, 48]
+PROB_LISTS = [[1e-4], [1e-4], [5e-3], [1e-3], [5e-3]]
+SWEEP_BYTES = 2 * (1 << 17) * 16          # read + write of one 2^17 complex128 state
+
+
+def load_tables():
+    from surface_17_iqt_b200 import api
+    return (api.load_lookup_table("correction_table_depolarising.json"),
+            api.load_lookup_table("correction_table_classical_bitflip.json"), api.load_error_models())
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: oracle port, one process per host core
+# ---------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    shots, seed = args
+    import random
+    os.environ["OMP_NUM_THREADS"] = "1"
+    from oracle import s17_oracle as so
+    ct, bt, models = load_tables()
+    orc = so.ShotOracle(models, ct, bt)
+    t0 = time.perf_counter()
+    failed, not0 = so.run_subset(orc, "s2", shots, MODEL, ESET, LOCS2, PROB_LISTS, rnd=random.Random(seed),
+                                 meas_rng=random.Random(seed + 1))
+    return shots, failed, not0, time.perf_counter() - t0
+
+
+def cpu_arm(shots_per_core, cores=None, seed=0):
+    import multiprocessing as mp
+    from oracle import sv
+    sv.lib()          # build liboracle_sv.so before forking if it is missing
+    cores = cores or os.cpu_count() or 1
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, [(shots_per_core, seed + 17 * i) for i in range(cores)])
+    wall = time.perf_counter() - t0
+    shots = sum(r[0] for r in res)
+    return {"shots": shots, "wall_s": wall, "shots_per_s": shots / wall, "cores": cores,
+            "per_core_shots_per_s": sum(r[0] / r[3] for r in res) / cores,
+            "failed": sum(r[1] for r in res), "not0": sum(r[2] for r in res)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_core = max(1, args.ref_shots_per_core)
+    vals = []
+    for _ in range(args.warmup):
+        cpu_arm(max(1, per_core // 4), cores)
+    t_all = time.perf_counter()
+    for k in range(args.steps):
+        vals.append(cpu_arm(per_core, cores, seed=1000 * k))
+    wall = time.perf_counter() - t_all
+    shots = sum(v["shots"] for v in vals)
+    value = shots / sum(v["wall_s"] for v in vals)
+    line = {
+        "impl": "reference", "metric": "noisy Surface-17 shots/sec", "value": value, "unit": "shots/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * wall / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
+        "config": workload_config(per_core * cores, 1, None),
+        "cpu_baseline": {"value": value, "unit": "shots/s", "cores": cores, "kind": "port",
+                         "sample": "{} s2 shots per step on {} processes (oracle port: C sweep per gate, python driver)"
+                         .format(per_core * cores, cores)},
+        "e2e": {"value": value, "unit": "shots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(shots, n_gpus, fusion):
+    return {"workload": "Surface-17 {} s2 importance sampling, subset {} over {} two-round slots, uniform placement"
+            .format(MODEL, ESET, LOCS2), "shots_per_step_per_gpu": shots, "fusion": fusion,
+            "state": "2^17 complex128 per shot resident in HBM", "parallelism": "shots sharded x{}".format(n_gpus),
+            "l2": "per-step working set (shots x 2 MiB) exceeds the 126 MB L2, no flush needed"}
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from surface_17_iqt_b200 import _lib as L
+    from surface_17_iqt_b200 import api
+    import surface_17_iqt_b200.calc_log_e_rate_arbitrary_error_model as drv
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ct, bt, models = load_tables()
+    B = args.shots
+    sim = api.Simulation(MODEL, LOCS2, B, ct, bt, fusion=args.fusion, device=local, error_models=models)
+    sim.backend.set_subset(ESET, LOCS2)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(k):
+        first = (k * world + rank) * B
+        c = sim.backend.run("s2", B, L.NOISE_SUBSET, seed=args.seed, first_shot_id=first)
+        return c, sim.backend.timing()
+
+    for k in range(args.warmup):
+        step(k)
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    span_ms = gate_ms = 0.0
+    sweeps = launches = gate_launches = failed = not0 = 0
+    for k in range(args.steps):
+        c, t = step(args.warmup + k)
+        span_ms += t["span_ms"]
+        gate_ms += t["gate_ms"]
+        sweeps += c.sweeps
+        launches += t["launches"]
+        gate_launches += t["gate_launches"]
+        failed += c.failed
+        not0 += c.not0
+    tot = torch.tensor([failed, not0], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tot)           # the path's only collective: per-subset failure / s2 counts
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    sampler.stop_flag = True
+    # max over ranks of the device-timed span; host wall clock reported beside it
+    times = torch.tensor([span_ms, wall_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    span_ms_max, wall_ms_max = [float(v) for v in times.tolist()]
+    total_shots = B * args.steps * world
+    value = total_shots / (span_ms_max * 1e-3)
+
+    # roofline of the gate sweep on this rank
+    algo_bytes = sweeps * SWEEP_BYTES - (B * args.steps) * (SWEEP_BYTES // 2)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = algo_bytes / (gate_ms * 1e-3) / 1e9 if gate_ms > 0 else 0.0
+
+    # e2e through the reference-shaped entry point: host args in, host tuple out, wall clock
+    sim.close()
+    drv.VERBOSE = False
+    drv.BATCH_SHOTS, drv.FUSION, drv.DEVICE = B, args.fusion, local
+    drv.s2_calculate_log_e_rate_error_subset(B, ct, MODEL, ESET, LOCS2, bt, PROB_LISTS)      # warm: builds the context
+    barrier()
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        r = drv.s2_calculate_log_e_rate_error_subset(B * world, ct, MODEL, ESET, LOCS2, bt, PROB_LISTS)
+    barrier()
+    e2e_s = time.perf_counter() - t1
+    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = B * world * args.steps / float(e2e_t.item())
+    drv.release()
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            cpu = cpu_arm(args.cpu_shots_per_core)
+        line = {
+            "metric": "noisy Surface-17 shots/sec", "value": value, "unit": "shots/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": span_ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128)",
+            "data": "synthetic", "config": workload_config(B, world, args.fusion),
+            "wall_ms_per_step": wall_ms_max / args.steps,
+            "clocks": sampler.summary(),
+            "e2e": {"value": e2e_value, "unit": "shots/s",
+                    "h2d_bytes_per_step": 2048 * 8 + 3 * 4 * len(ESET) + 64, "d2h_bytes_per_step": 64 + 8 * 8,
+                    "api": "s2_calculate_log_e_rate_error_subset(num_runs, ...) -> (rate, not0_rate, failed, not0)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_layer", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                         "traffic": None, "launches": int(gate_launches), "sweeps": int(sweeps),
+                         "sweeps_per_shot": sweeps / (B * args.steps),
+                         "gate_kernel_share_of_step": gate_ms / span_ms if span_ms else None},
+            "counts": {"failed": int(tot[0]), "not0": int(tot[1]), "shots": total_shots},
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = {"value": cpu["shots_per_s"], "unit": "shots/s", "cores": cpu["cores"], "kind": "port",
+                                    "sample": "{} s2 shots of the same workload, {} processes (oracle port)".format(
+                                        cpu["shots"], cpu["cores"])}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--shots", type=int, default=int(os.environ.get("S17_BENCH_SHOTS", "8192")), help="shots per GPU per step")
+    ap.add_argument("--fusion", type=int, default=2)
+    ap.add_argument("--seed", type=int, default=2026)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-shots-per-core", type=int, default=60)
+    ap.add_argument("--ref-shots-per-core", type=int, default=40)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

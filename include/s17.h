@@ -1,0 +1,199 @@
+/*
+ * s17.h -- C ABI of libs17.so, the B200 (sm_100a) batched Surface-17 trajectory backend.
+ *
+ * This is the drop-in boundary for the reference's hot path.  Citations are into the reference
+ * repository (Alexowens94/Surface_17_IQT):
+ *   CS = compiled_surface_code_arbitrary_error_model.py, CL = calc_log_e_rate_arbitrary_error_model.py
+ *
+ * In the reference the boundary is the ProjectQ engine object: `MainEngine(Simulator())`
+ * (CL:63, 221, 299, 392), `eng.allocate_qureg` (CL:302-303), `Gate | qubits` (every gate line of
+ * CS:291-344), `All(Measure) | ancilla; eng.flush(); int(q)` (CS:848-851) -- one pybind call per
+ * gate per shot.  Here the boundary is one call per BATCH of shots: the host compiles the cycle
+ * and the error model once (s17_load_program), then s17_run executes whole shot protocols
+ * (CL:183 single, CL:261 s1, CL:355 s2, CL:33 run-til-fail) on device and returns the counters
+ * those functions return.
+ *
+ * Conventions: every function returns 0 on success, a negative S17_E_* code otherwise;
+ * s17_last_error gives the message.  No C++ types, exceptions or torch types cross the line.  The
+ * caller owns every buffer it passes; the library owns device memory behind the opaque handle.
+ * A context is bound to one CUDA device and is not thread-safe.  All entry points are synchronous.
+ * There is no CPU fallback: s17_create fails if no CUDA device is usable.
+ */
+#ifndef S17_H
+#define S17_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S17_N_QUBITS 17u
+#define S17_DIM (1u << 17)
+#define S17_EV_WORDS 32u       /* per-shot event words per cycle: 24 op words + 7 idle masks + 1 spare */
+#define S17_MASK_WORDS 32u     /* per-shot error-slot bitset (<= 1024 slots over both rounds) */
+#define S17_MAX_LISTS 8u
+#define S17_MAX_OUTCOMES 40u   /* 3 x 8 ancilla + 9 data, padded */
+
+enum { S17_OK = 0, S17_E_ARG = -1, S17_E_CUDA = -2, S17_E_STATE = -3, S17_E_NOMEM = -4 };
+
+/* ---- gate stream ------------------------------------------------------------------------- */
+
+/* micro-ops executed on the 4 register-resident amplitudes of one (data, ancilla) pair */
+enum {
+    S17_U_RY = 1,      /* Ry(sign*pi/2) on the data bit          (CS:315, 339) */
+    S17_U_RXX = 2,     /* Rxx(sign*pi/2) on (data, ancilla)      (CS:294, 323) */
+    S17_U_RX = 3,      /* Rx(sign*pi/2) on the data bit          (CS:304, 333) */
+    S17_U_H = 4,       /* Hadamard on the data bit               (CS:54, 106)  */
+    S17_U_ROT_X = 5,   /* Rx(theta), cos/sin from the parameter table (coherent over-rotation) */
+    S17_U_ROT_Y = 6,   /* Ry(theta) */
+    S17_U_ROT_XX = 7   /* Rxx(theta) */
+};
+
+typedef struct {
+    uint8_t type;       /* S17_U_* */
+    int8_t sign;        /* +1 / -1 for the +-pi/2 forms */
+    uint8_t skippable;  /* 1: not executed when the op's leak predicate holds (CS:293, 322) */
+    uint8_t ev_shift;   /* bit offset of the 6-bit Pauli event field applied AFTER this uop; 255 = none */
+    uint8_t param;      /* index into the (cos, sin) parameter table for S17_U_ROT_* */
+    uint8_t pad[3];
+} s17_uop;
+
+enum { S17_OP_ENT = 0, S17_OP_IDLE = 1 };
+
+/* one entangling operation (x_type_entangling CS:291 / z_type_entangling CS:312), or an idle z-mask */
+typedef struct {
+    uint8_t kind;       /* S17_OP_ENT or S17_OP_IDLE */
+    uint8_t data_bit;   /* state-vector bit of the data qubit (0..8) */
+    uint8_t anc_bit;    /* state-vector bit of the ancilla qubit (9..16) */
+    uint8_t n_uops;
+    uint8_t ev_word;    /* index of this op's per-shot event word */
+    uint8_t pad[3];
+    s17_uop uops[8];
+} s17_op;
+
+/* one sweep over the state: every op's ancilla bit must be one of anc_bits */
+typedef struct {
+    uint8_t n_ops;
+    uint8_t anc_bits[3];   /* ancilla bits staged in shared memory next to the 9 data bits */
+    uint8_t emit_hist;     /* 1: also emit the 256-bin joint ancilla histogram (last sweep of a cycle) */
+    uint8_t pad[3];
+    s17_op ops[8];
+} s17_layer;
+
+/* ---- error-injection program (restates insert_errors / insert_error, CS:127-234) ---------------- */
+
+enum { S17_P_OP_BEGIN = 1, S17_P_ERR = 2, S17_P_OP_END = 3, S17_P_IDLE = 4 };
+enum {
+    S17_ERR_X = 1, S17_ERR_Y = 2, S17_ERR_Z = 3,   /* on qubits[0]            (CS:201-206) */
+    S17_ERR_ZC = 4, S17_ERR_ZT = 5,                /* Z on qubits[0] / [1]    (CS:207-211) */
+    S17_ERR_XX = 6, S17_ERR_ZZ = 7,                /* both qubits             (CS:212-217) */
+    S17_ERR_LEAK_A = 8,                            /* set leak[a]             (CS:218-219, 225-232) */
+    S17_ERR_LEAK_AB = 9,                           /* set leak[a], leak[b]    (CS:220-223) */
+    S17_ERR_DEPOL = 10                             /* uniform 15-way 2q Pauli (CS:237-283) */
+};
+
+typedef struct {
+    uint8_t kind;      /* S17_P_* */
+    uint8_t err;       /* S17_ERR_* */
+    uint8_t list;      /* probability-list id (position in the model's "probabilities") */
+    uint8_t field;     /* event-field bit offset inside the op word (0, 6, 12, 18) */
+    uint16_t slot;     /* slot index inside ONE round of the list */
+    uint8_t a, b;      /* OP_BEGIN: leak predicate indices; ERR leak kinds: indices to set; IDLE: a = qubit */
+    uint8_t word;      /* event word index (op word, or 24 + timestep for IDLE) */
+    uint8_t in_skip;   /* 1: entry sits inside the `if not leaked` block and is not drawn when skipped */
+    uint8_t use_round; /* 1: slot is offset by half the list in the second cycle (CS:191-193); 0 for Idle */
+    uint8_t pad;
+} s17_pinstr;
+
+typedef struct {
+    uint32_t n_lists;
+    uint32_t list_len[S17_MAX_LISTS];   /* total length the caller passes per list (1 or 2 rounds) */
+} s17_lists;
+
+/* ---- run control ------------------------------------------------------------------------------ */
+
+enum { S17_PROTO_SINGLE = 0, S17_PROTO_S1 = 1, S17_PROTO_S2 = 2, S17_PROTO_RTF = 3 };
+enum { S17_NOISE_PROB = 0, S17_NOISE_SUBSET = 1, S17_NOISE_REPLAY = 2 };
+enum { S17_STOP_NONE = 0, S17_STOP_AFTER_PREP = 1, S17_STOP_CYCLE1_GATES = 2, S17_STOP_AFTER_CYCLE1 = 3,
+       S17_STOP_AFTER_CORRECTION = 4 };
+
+typedef struct {
+    uint32_t protocol;        /* S17_PROTO_* */
+    uint32_t noise;           /* S17_NOISE_* */
+    uint64_t first_shot_id;   /* global id of shot 0 of this batch: Philox counter => results independent of sharding */
+    uint64_t n_shots;
+    uint64_t seed;
+    uint32_t logical_state;   /* 0 / 1  (CS:103-104) */
+    uint32_t basis_x;         /* 1: prepare / read out in the X basis (CS:53-54, 105-106) */
+    uint32_t materialize;     /* 1: apply collapse + correction to the stored state (parity mode) */
+    uint32_t stop_stage;      /* S17_STOP_* (parity/debug) */
+    uint32_t stop_layers;     /* with S17_STOP_CYCLE1_GATES: run only this many sweeps of cycle 1 (0 = all) */
+    uint32_t forced;          /* 1: measurement outcomes come from s17_set_replay */
+    uint32_t rtf_runs;        /* S17_PROTO_RTF: number of runs to complete */
+    uint32_t rtf_max_rounds;  /* S17_PROTO_RTF: safety cap on rounds per run (0 = none) */
+} s17_run_args;
+
+typedef struct {
+    uint64_t shots;        /* shots executed */
+    uint64_t failed;       /* failed_count        (CL:330, 433, 251) */
+    uint64_t not0;         /* flipsa_not0_count   (CL:333, 417) */
+    uint64_t counted;      /* shots that reached decode + read-out */
+    uint64_t errors;       /* shots with a forced outcome of zero probability */
+    uint64_t sweeps;       /* (shot, sweep) pairs executed by the gate kernel, for roofline accounting */
+    uint64_t rounds;       /* S17_PROTO_RTF: total rounds simulated */
+    uint64_t spare;
+} s17_counts;
+
+typedef struct {
+    uint8_t quiescent, synd1, synd2, flips_a;  /* bit j = ancilla j */
+    uint8_t ft_syndrome, flags, logical_meas, n_outcomes;
+    uint32_t correction;      /* bits 0-8: X on data i; bits 9-17: Z on data i (CS:901-907) */
+    uint32_t leak;            /* 17 leak flags (CS:286-288) */
+    uint16_t data_meas;       /* after the leak override (CS:61-63) */
+    uint16_t pad;
+    uint8_t outcomes[S17_MAX_OUTCOMES];  /* raw measurement outcomes in program order */
+} s17_record;
+enum { S17_F_NOT0 = 1, S17_F_COUNTED = 2, S17_F_FAIL = 4, S17_F_ERROR = 8, S17_F_SYND2 = 16 };
+
+typedef struct s17_ctx s17_ctx;
+
+/* replaces MainEngine(Simulator()) + allocate_qureg(9)/(8) for a whole batch (CL:299-303) */
+int s17_create(s17_ctx **out, int device, uint64_t max_shots);
+int s17_destroy(s17_ctx *ctx);
+const char *s17_last_error(const s17_ctx *ctx);
+int s17_device_count(void);
+
+/* the compiled cycle: what stabilizer_cycle_error_index (CS:773-845) emits, grouped into sweeps.
+ * `layers` concatenates three sweep lists of n_layers[0..2] entries: the noiseless preparation cycle
+ * (logical_prep, CS:96-123), the first noisy cycle (stab_ind=0) and the second one (stab_ind=1). */
+int s17_load_program(s17_ctx *ctx, const s17_layer *layers, const uint32_t n_layers[3],
+                     const double *params_cos_sin, uint32_t n_params,
+                     const s17_pinstr *plan, uint32_t n_plan, const s17_lists *lists);
+/* decoder tables: lookup (CS:886-892) and return_weight_classical_lookup (CS:895-898) */
+int s17_load_tables(s17_ctx *ctx, const uint32_t *lut256, const uint8_t *classical_weight16);
+/* true-probability mode: the lists instantiate_error_model binds (CS:31-49) */
+int s17_set_slot_probs(s17_ctx *ctx, uint32_t list_id, const double *p, uint32_t len);
+/* fixed-weight mode: generate_error_locations[_non_uniform] (CL:151-181); weights[t] NULL => uniform */
+int s17_set_subset(s17_ctx *ctx, uint32_t n_types, const uint32_t *eset, const uint32_t *n_loc,
+                   const double *const *weights);
+/* replay mode: explicit masks (one byte per slot, lists concatenated) and forced outcomes per shot */
+int s17_set_replay(s17_ctx *ctx, uint64_t n_shots, const uint8_t *masks, uint64_t mask_stride,
+                   const uint8_t *outcomes, uint64_t outcome_stride);
+/* the shot loops of CL:183 / 261 / 355 / 33 */
+int s17_run(s17_ctx *ctx, const s17_run_args *args, s17_counts *out);
+int s17_read_records(s17_ctx *ctx, s17_record *out, uint64_t n);
+int s17_read_masks(s17_ctx *ctx, uint32_t *out /* n x 2 x S17_MASK_WORDS: cycle-1 / cycle-2 record */, uint64_t n);
+/* per-shot event words of the most recent cycle (debug / parity): n x S17_EV_WORDS */
+int s17_read_events(s17_ctx *ctx, uint32_t *out, uint64_t n);
+int s17_read_state(s17_ctx *ctx, uint64_t shot, double *re_im /* 2 * 2^17 doubles */);
+int s17_read_rtf(s17_ctx *ctx, uint32_t *rounds_til_fail, uint32_t *syndrome_b_count, uint64_t n_runs);
+/* device time of the last s17_run, CUDA events on the launch stream (ms): per kernel class, and the span from
+ * the first to the last device operation of the call */
+int s17_last_timing(s17_ctx *ctx, double *gate_ms, double *measure_ms, double *other_ms,
+                    uint64_t *gate_launches, uint64_t *all_launches, double *span_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

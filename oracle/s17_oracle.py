@@ -126,6 +126,7 @@ class ShotOracle:
         self.error_models = error_models
         self.correction_table = correction_table
         self.bitflip_table = bitflip_table
+        self.depol_script = None  # optional {(stab_ind, rxx_ind): k} replaying insert_2q_error's choice
         self.log = None  # optional list receiving ('gate', name, angle, bits) / ('meas', bit, out, p)
 
     # ---- primitive ops ----------------------------------------------------------------
@@ -196,10 +197,12 @@ class ShotOracle:
             elif err == "Lt":
                 leaked[t_ind] = 1
             elif err == "depol":
-                self._insert_2q_error(st, bits, rnd)
+                self._insert_2q_error(st, bits, rnd, key=(stab_ind, rxx_ind))
 
-    def _insert_2q_error(self, st, bits, rnd):
+    def _insert_2q_error(self, st, bits, rnd, key=None):
         r = rnd.random()                                # CS:238
+        if self.depol_script is not None:               # test hook: replay a recorded 15-way choice
+            r = (self.depol_script[key] + 0.5) / 15.0
         for k, pp in enumerate(DEPOL_ORDER):
             lo, hi = k * 1 / 15, (k + 1) * 1 / 15
             if (k == 0 and r < hi) or (k > 0 and lo < r < hi):   # strict compares as in CS:239-283
@@ -209,7 +212,8 @@ class ShotOracle:
                     self._gate(st, pp[1], bits[1:2])
 
     # ---- one stabiliser cycle (CS:773-863) ----------------------------------------------
-    def stabilizer_cycle(self, st, leaked, gates, probs, rnd, meas, stab_ind=0, cooling=False, reset=True):
+    def stabilizer_cycle(self, st, leaked, gates, probs, rnd, meas, stab_ind=0, cooling=False, reset=True,
+                         gates_only=False):
         rx_ind = ry_ind = rxx_ind = 0
         for step, (kind, ops) in enumerate(TIMESTEPS):
             for (d, a, s, c_rx, c_ry1, c_ry2, dl, al) in ops:
@@ -242,6 +246,8 @@ class ShotOracle:
                 for q in range(N_QUBITS):
                     self._insert_errors(st, "Idle", (q,), leaked, gates, probs, rnd,
                                         sc_ind=step * N_QUBITS + q, stab_ind=0)
+        if gates_only:                                  # test hook: state just before All(Measure)
+            return None
         outcomes = [self._measure(st, N_DATA + j, meas) for j in range(N_ANC)]   # CS:848-851
         syndrome = list(outcomes)
         for j in range(N_ANC):                          # CS:854-857

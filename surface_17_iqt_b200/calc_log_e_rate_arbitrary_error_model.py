@@ -1,0 +1,248 @@
+"""Drop-in Monte-Carlo drivers with the reference's names, positional signatures and return values
+(calc_log_e_rate_arbitrary_error_model.py [CL]), executing whole batches of shots on the B200 backend.
+
+    s1_calculate_log_e_rate_error_subset   CL:261-353
+    s2_calculate_log_e_rate_error_subset   CL:355-457
+    calculate_log_e_rate_error_subset      CL:183-259
+    calculate_log_e_rate                   CL:33-148   (run-til-fail)
+    generate_error_locations[_non_uniform] CL:151-181  (host versions, same contract)
+
+Placement and error draws use device Philox streams keyed by (seed, global shot id); the seed of each call
+is taken from Python's global ``random`` (``random.getrandbits(64)``), so ``random.seed(k)`` makes a run
+reproducible just as it does for the reference.  When torch.distributed is initialised the shot range is
+split over the ranks and the counters are all-reduced (distributed.py).
+"""
+import json
+import os
+import random
+import time
+
+import numpy as np
+
+from . import _lib as L
+from . import api, circuit, distributed
+
+# knobs (module-level like the reference's scripts; no CLI)
+BATCH_SHOTS = int(os.environ.get("S17_BATCH", "4096"))    # shots resident per device context (2 MiB each)
+FUSION = int(os.environ.get("S17_FUSION", "2"))           # 0 per gate, 1 per timestep, 2 per two timesteps
+DEVICE = None                                             # None: LOCAL_RANK or 0
+VERBOSE = True                                            # print the reference's summary lines
+
+_SIMS = {}
+LAST_TIMING = {}
+
+
+def _log(*a):
+    if VERBOSE:
+        print(*a)
+
+
+def _device():
+    return int(os.environ.get("LOCAL_RANK", "0")) if DEVICE is None else int(DEVICE)
+
+
+def _simulation(model, list_len, cooling, correction_table, bitflip_table, over_angles=None):
+    key = (model, tuple(list_len), bool(cooling), FUSION, _device(), BATCH_SHOTS,
+           None if over_angles is None else json.dumps(over_angles, sort_keys=True))
+    sim = _SIMS.get(key)
+    if sim is None:
+        for k in list(_SIMS):            # one resident context per device: free the previous program's state
+            if k[4] == _device():
+                _SIMS.pop(k).close()
+        sim = api.Simulation(model, list_len, BATCH_SHOTS, correction_table, bitflip_table, fusion=FUSION,
+                             cooling=cooling, device=_device(), over_angles=over_angles)
+        _SIMS[key] = sim
+    else:
+        sim.backend.load_tables(correction_table, bitflip_table)
+    return sim
+
+
+def release():
+    """Free every cached device context."""
+    for k in list(_SIMS):
+        _SIMS.pop(k).close()
+
+
+def generate_error_locations(num_e, num_e_locations):
+    """CL:151-161 (host version): uniform fixed-weight 0/1 mask.  Raises instead of looping forever if k > L."""
+    if num_e > num_e_locations:
+        raise ValueError("cannot place {} errors on {} locations".format(num_e, num_e_locations))
+    mask = num_e_locations * [0]
+    for ind in random.sample(range(num_e_locations), num_e):
+        mask[ind] = 1
+    return mask
+
+
+def generate_from_distr(probs):
+    """CL:163-169."""
+    r = random.random() * sum(probs)
+    total = 0
+    for i, p in enumerate(probs):
+        total += p
+        if total > r:
+            return i
+    return len(probs) - 1
+
+
+def generate_error_locations_non_uniform(num_e, num_e_locations, probs):
+    """CL:171-181: sequential sampling proportional to probs, rejecting repeats."""
+    if num_e > sum(1 for p in probs if p > 0):
+        raise ValueError("more errors than locations with non-zero weight")
+    mask = num_e_locations * [0]
+    for _ in range(num_e):
+        while True:
+            ind = generate_from_distr(probs)
+            if mask[ind] == 0:
+                mask[ind] = 1
+                break
+    return mask
+
+
+def _run_subset(protocol, num_runs, correction_table, model, eset, locations, bitflip_table, prob_lists, cz_comp,
+                cooling):
+    if cz_comp:
+        raise NotImplementedError("the experimental CZ compilation is outside the accelerated path (SURVEY C-9)")
+    if len(eset) != len(locations) or len(prob_lists) != len(eset):
+        raise ValueError("eset, locations and prob_lists must have one entry per error type")
+    sim = _simulation(model, list(locations), cooling, correction_table, bitflip_table)
+    weights = [None if len(p) == 1 else list(p) for p in prob_lists]     # CL:287: one entry => uniform placement
+    sim.backend.set_subset(eset, locations, weights)
+    seed = random.getrandbits(64)
+    rank, world_size = distributed.world()
+    first, count = distributed.shard_range(num_runs, rank, world_size)
+    failed = not0 = counted = 0
+    gate_ms = span_ms = 0.0
+    sweeps = launches = 0
+    done = 0
+    while done < count:
+        n = min(BATCH_SHOTS, count - done)
+        c = sim.backend.run(protocol, n, L.NOISE_SUBSET, seed=seed, first_shot_id=first + done)
+        if c.errors:
+            raise L.S17Error("{} shots hit a zero-probability outcome".format(c.errors))
+        t = sim.backend.timing()
+        failed, not0, counted = failed + c.failed, not0 + c.not0, counted + c.counted
+        gate_ms, span_ms = gate_ms + t["gate_ms"], span_ms + t["span_ms"]
+        sweeps, launches = sweeps + c.sweeps, launches + t["launches"]
+        done += n
+    failed, not0, counted = distributed.allreduce_counts([failed, not0, counted])
+    LAST_TIMING.update(gate_ms=gate_ms, span_ms=span_ms, sweeps=sweeps, launches=launches, shots=count)
+    return failed, not0, counted
+
+
+def calculate_log_e_rate_error_subset(num_runs, correction_table, model, eset, locations, bitflip_table,
+                                      prob_lists, cz_comp=False):
+    """CL:183-259: single round, always decode flips_a.  Returns failed_count / num_runs."""
+    t_begin = time.perf_counter()
+    if not isinstance(prob_lists[0], list):      # CL:207: a flat list of floats means uniform placement
+        prob_lists = [[p] for p in prob_lists]
+    failed, _, _ = _run_subset("single", num_runs, correction_table, model, eset, locations, bitflip_table,
+                               prob_lists, cz_comp, False)
+    log_e_rate = failed / num_runs
+    _log(log_e_rate)
+    _log('total_time_taken_{}_runs_{}'.format(num_runs, time.perf_counter() - t_begin))
+    return log_e_rate
+
+
+def s1_calculate_log_e_rate_error_subset(num_runs, correction_table, model, eset, locations, bitflip_table,
+                                         prob_lists, cz_comp=False, cooling=False):
+    """CL:261-353.  Returns (failed/(runs-not0) or None, not0/runs, failed_count, flipsa_not0_count)."""
+    t_begin = time.perf_counter()
+    failed_count, flipsa_not0_count, _ = _run_subset("s1", num_runs, correction_table, model, eset, locations,
+                                                     bitflip_table, prob_lists, cz_comp, cooling)
+    try:
+        log_e_rate = failed_count / (num_runs - flipsa_not0_count)
+    except ZeroDivisionError:
+        _log('cant assign error rate, 0 runs ending after first stab, placeholder e rate -1')
+        log_e_rate = None                        # CL:343 (the message says -1, the value is None)
+    flipsa_not0_rate = flipsa_not0_count / num_runs
+    _summary(failed_count, flipsa_not0_count, log_e_rate, flipsa_not0_rate, num_runs, t_begin)
+    return log_e_rate, flipsa_not0_rate, failed_count, flipsa_not0_count
+
+
+def s2_calculate_log_e_rate_error_subset(num_runs, correction_table, model, eset, locations, bitflip_table,
+                                         prob_lists, cz_comp=False, cooling=False):
+    """CL:355-457.  `locations` / masks span two rounds.  Returns (failed/not0 or -1, not0/runs, failed, not0)."""
+    t_begin = time.perf_counter()
+    failed_count, flipsa_not0_count, _ = _run_subset("s2", num_runs, correction_table, model, eset, locations,
+                                                     bitflip_table, prob_lists, cz_comp, cooling)
+    try:
+        log_e_rate = failed_count / flipsa_not0_count
+    except ZeroDivisionError:
+        _log('cant assign error rate, 0 runs ending after first stab, placeholder e rate -1')
+        log_e_rate = -1                          # CL:447
+    flipsa_not0_rate = flipsa_not0_count / num_runs
+    _summary(failed_count, flipsa_not0_count, log_e_rate, flipsa_not0_rate, num_runs, t_begin)
+    return log_e_rate, flipsa_not0_rate, failed_count, flipsa_not0_count
+
+
+def _summary(failed_count, flipsa_not0_count, log_e_rate, flipsa_not0_rate, num_runs, t_begin):
+    _log('counts')
+    _log('failed {} times'.format(failed_count))
+    _log('wouldnt stop at s1 {} '.format(flipsa_not0_count))
+    _log('rates')
+    _log(log_e_rate)
+    _log(flipsa_not0_rate)
+    _log('total_time_taken_{}_runs_{}'.format(num_runs, time.perf_counter() - t_begin))
+
+
+def f(t, A, r):
+    """CL:756."""
+    return A * np.exp(-r * t)
+
+
+def fit_log_e_rate(results, num_bins, include_b=False):
+    """The histogram + exponential fit of plot_log_e_rate_graph (CL:546-565) without the plotting."""
+    from scipy.optimize import curve_fit
+    data = np.array(results['rounds_til_fail_list'], dtype='float64')
+    if include_b:
+        data = data + np.array(results['syndrome_b_measured_list'], dtype='float64')
+    vals, bins = np.histogram(data, bins=num_bins)
+    popt, _pcov = curve_fit(f, bins[:-1], vals.astype('float64'))
+    return popt[1], popt[0], vals, bins
+
+
+def calculate_log_e_rate(num_runs, filename, correction_table, e_model, e_probs, bitflip_table, num_bins=20,
+                         cz_compilation=False, model_name=None, save=True):
+    """CL:33-148: run-til-fail with true Bernoulli noise, JSON dump and exponential fit; returns log_e_rate.
+
+    `e_model` is the model dict returned by instantiate_error_model (or its name), `e_probs` the
+    {name: list} dict.  Deviation (SURVEY C-6): the leak register is reset at the start of every run.
+    """
+    if cz_compilation:
+        raise NotImplementedError("the experimental CZ compilation is outside the accelerated path (SURVEY C-9)")
+    models = api.load_error_models()
+    if isinstance(e_model, str):
+        model_name, e_model = e_model, models[e_model]
+    if model_name is None:
+        model_name = next(k for k, v in models.items() if v == e_model)
+    names = e_model['probabilities']
+    p_set = [list(e_probs[k]) for k in names]
+    need = circuit.list_lengths(e_model)
+    for k, plist, n in zip(names, p_set, need):
+        if len(plist) < n:
+            raise IndexError("probability list {} has {} entries, the cycle indexes {}".format(k, len(plist), n))
+    sim = _simulation(model_name, [len(p) for p in p_set], False, correction_table, bitflip_table)
+    sim.backend.set_slot_probs(p_set)
+    t_begin = time.perf_counter()
+    c = sim.backend.run("rtf", min(BATCH_SHOTS, num_runs), L.NOISE_PROB, seed=random.getrandbits(64),
+                        rtf_runs=num_runs)
+    rounds, syndb = sim.backend.rtf_results(num_runs)
+    total_time_taken = time.perf_counter() - t_begin
+    round_count_list = [int(v) for v in rounds]
+    _log('total time taken {}'.format(total_time_taken))
+    results = {
+        'total_time_taken_{}_runs'.format(num_runs): total_time_taken,
+        'probability_set': e_probs,
+        'rounds_til_fail_list': round_count_list,
+        'syndrome_b_measured_list': [int(v) for v in syndb],
+        'rounds_til_fail_list_X0': [], 'rounds_til_fail_list_X1': [],
+        'rounds_til_fail_list_Z0': round_count_list, 'rounds_til_fail_list_Z1': [],
+        'error_model': e_model,
+    }
+    LAST_TIMING.update(rounds=int(c.rounds), span_ms=sim.backend.timing()["span_ms"])
+    if save:
+        os.makedirs("data", exist_ok=True)
+        with open(os.path.join("data", filename + '.json'), 'w') as file:
+            json.dump(results, file)
+    log_e_rate, _A, _vals, _bins = fit_log_e_rate(results, num_bins)
+    return log_e_rate

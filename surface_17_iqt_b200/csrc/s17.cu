@@ -1,0 +1,1141 @@
+// s17.cu -- libs17.so: hand-written sm_100a kernels + the C ABI declared in include/s17.h.
+//
+// Reference behaviour being replaced (citations: CS = compiled_surface_code_arbitrary_error_model.py,
+// CL = calc_log_e_rate_arbitrary_error_model.py of Alexowens94/Surface_17_IQT):
+//   k_layer    : the Rxx/Rx/Ry gate stream of stabiliser_timestep_1..8 (CS:365-650) plus the Pauli
+//                gates insert_error applies (CS:198-217), ProjectQ's per-gate sweeps fused per layer
+//   k_place    : generate_error_locations / _non_uniform (CL:151-181)
+//   k_plan     : insert_errors / insert_error / insert_2q_error / insert_leakage decision logic
+//                (CS:127-288) and the leak skip predicate (CS:293, 322), one thread per shot
+//   k_measure  : All(Measure) | ancilla, leak override, reset decision (CS:848-862) and the
+//                s1/s2/single/run-til-fail branching (CL:240, 320-333, 415-424, 83-98) + lookup (CS:886)
+//   k_collapse : ProjectQ's collapse + renormalise, and the ancilla reset X gates (CS:859-862)
+//   k_pauli    : apply_correction (CS:901-907)
+//   k_readout  : logical_measurement (CS:52-93) + failure tally (CL:329-330, 433-434)
+// There is NO CPU fallback in this library.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "s17_kernels.cuh"
+
+namespace s17 {
+
+enum { C_FAILED = 0, C_NOT0 = 1, C_COUNTED = 2, C_ERRORS = 3, C_SWEEPS = 4, C_ROUNDS = 5, C_NEXT_RUN = 6, C_ALIVE = 7, C_N = 8 };
+
+// =================================================================================================
+// gate sweep
+// =================================================================================================
+__device__ __forceinline__ int insert0(int x, int pos) { return (x & ((1 << pos) - 1)) | ((x >> pos) << (pos + 1)); }
+
+__global__ void __launch_bounds__(kLayerThreads, 3)
+k_layer(double2 *__restrict__ state, const __grid_constant__ LayerArg A, const uint32_t *__restrict__ ev,
+        const uint8_t *__restrict__ active, double *__restrict__ hist, unsigned long long *__restrict__ counters,
+        int init_basis)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double2 *tile = reinterpret_cast<double2 *>(smem_raw);
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t s_ev[S17_EV_WORDS];
+
+    const int shot = blockIdx.x / kTilesPerShot;
+    const int tile_id = blockIdx.x % kTilesPerShot;
+    if (!active[shot]) return;
+    const int t = threadIdx.x;
+
+    uint32_t base = 0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) base |= ((tile_id >> k) & 1u) << A.other_bits[k];
+    uint32_t run_off[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        uint32_t g = base;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) g |= ((r >> k) & 1u) << A.L.anc_bits[k];
+        run_off[r] = g;
+    }
+    double2 *sbase = state + (size_t)shot * kDim;
+
+    if (t < (int)S17_EV_WORDS) s_ev[t] = ev[(size_t)shot * S17_EV_WORDS + t];
+    if (init_basis < 0) {
+        if (t == 0) {
+            mbar_init(&bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (t == 0) {
+            mbar_expect_tx(&bar, kTile * 16);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) tma_load_1d(tile + r * kRun, sbase + run_off[r], kRunBytes, &bar);
+        }
+        mbar_wait(&bar, 0);
+    } else {
+        // first sweep of a shot: synthesise the computational basis state instead of reading HBM
+#pragma unroll
+        for (int i = 0; i < kTile / kLayerThreads; ++i) tile[t + kLayerThreads * i] = make_double2(0.0, 0.0);
+        __syncthreads();
+        if (tile_id == 0 && t == 0) tile[init_basis] = make_double2(1.0, 0.0);
+        __syncthreads();
+    }
+
+    // how many 1/sqrt(2) factors this shot really picks up in this layer, and which op applies them
+    int nsc = 0, last_ent = -1;
+    for (int o = 0; o < A.L.n_ops; ++o) {
+        const s17_op &op = A.L.ops[o];
+        if (op.kind != S17_OP_ENT) continue;
+        last_ent = o;
+        const uint32_t skip = (s_ev[op.ev_word] >> 24) & 1u;
+        for (int u = 0; u < op.n_uops; ++u) {
+            const s17_uop up = op.uops[u];
+            if (up.type <= S17_U_H && !(up.skippable && skip)) ++nsc;
+        }
+    }
+    const double scale = ldexp((nsc & 1) ? 0.70710678118654752440 : 1.0, -(nsc >> 1));
+
+    for (int o = 0; o < A.L.n_ops; ++o) {
+        const s17_op &op = A.L.ops[o];
+        if (op.kind == S17_OP_IDLE) {
+            // Z on every qubit whose bit is set in the 17-bit idle mask (sympathetic_cooling, CS:762-772)
+            const uint32_t zm = s_ev[op.ev_word];
+            if (zm) {
+                uint32_t lm = zm & 0x1FFu;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) lm |= ((zm >> A.L.anc_bits[k]) & 1u) << (9 + k);
+                const uint32_t c0 = __popc(base & zm) & 1u;
+#pragma unroll 4
+                for (int i = 0; i < kTile / kLayerThreads; ++i) {
+                    const int l = t + kLayerThreads * i;
+                    if ((__popc(l & lm) & 1u) ^ c0) {
+                        double2 v = tile[l];
+                        tile[l] = make_double2(-v.x, -v.y);
+                    }
+                }
+                __syncthreads();
+            }
+            continue;
+        }
+        const uint32_t w = s_ev[op.ev_word];
+        const uint32_t skip = (w >> 24) & 1u;
+        const int lb0 = op.data_bit;
+        int lb1 = 9;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            if (A.L.anc_bits[k] == op.anc_bit) lb1 = 9 + k;
+        const int m0 = 1 << lb0, m1 = 1 << lb1;
+        const bool do_scale = (o == last_ent) && (nsc != 0);
+
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            int idx[2];
+            double2 a[2][4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int item = t + kLayerThreads * (pass * 2 + i);
+                idx[i] = insert0(insert0(item, lb0), lb1);
+                a[i][0] = tile[idx[i]];
+                a[i][1] = tile[idx[i] | m0];
+                a[i][2] = tile[idx[i] | m1];
+                a[i][3] = tile[idx[i] | m0 | m1];
+            }
+            for (int u = 0; u < op.n_uops; ++u) {
+                const s17_uop up = op.uops[u];
+                if (up.skippable && skip) continue;
+                const double sg = (double)up.sign;
+                switch (up.type) {
+                case S17_U_RY:  g_ry(a[0], sg);  g_ry(a[1], sg);  break;
+                case S17_U_RXX: g_rxx(a[0], sg); g_rxx(a[1], sg); break;
+                case S17_U_RX:  g_rx(a[0], sg);  g_rx(a[1], sg);  break;
+                case S17_U_H:   g_h(a[0]);       g_h(a[1]);       break;
+                case S17_U_ROT_X:  { const double2 p = A.prm[up.param]; g_rot_x(a[0], p.x, p.y);  g_rot_x(a[1], p.x, p.y);  } break;
+                case S17_U_ROT_Y:  { const double2 p = A.prm[up.param]; g_rot_y(a[0], p.x, p.y);  g_rot_y(a[1], p.x, p.y);  } break;
+                case S17_U_ROT_XX: { const double2 p = A.prm[up.param]; g_rot_xx(a[0], p.x, p.y); g_rot_xx(a[1], p.x, p.y); } break;
+                default: break;
+                }
+                if (up.ev_shift != 255) {
+                    const uint32_t f = (w >> up.ev_shift) & 63u;
+                    if (f) { g_pauli(a[0], f); g_pauli(a[1], f); }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                if (do_scale) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { a[i][q].x *= scale; a[i][q].y *= scale; }
+                }
+                tile[idx[i]] = a[i][0];
+                tile[idx[i] | m0] = a[i][1];
+                tile[idx[i] | m1] = a[i][2];
+                tile[idx[i] | m0 | m1] = a[i][3];
+            }
+        }
+        __syncthreads();
+    }
+
+    if (A.L.emit_hist) {
+        // joint ancilla histogram: warp w owns run w (one ancilla value, all 512 data amplitudes)
+        const int wid = t >> 5, lane = t & 31;
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < kRun / 32; ++i) {
+            const double2 v = tile[wid * kRun + lane + 32 * i];
+            acc = fma(v.x, v.x, fma(v.y, v.y, acc));
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+        if (lane == 0) {
+            uint32_t g = base;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) g |= ((wid >> k) & 1u) << A.L.anc_bits[k];
+            hist[(size_t)shot * 256 + (g >> 9)] = acc;
+        }
+    }
+
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (t == 0) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) tma_store_1d(sbase + run_off[r], tile + r * kRun, kRunBytes);
+        tma_store_commit_and_wait_read();
+        if (tile_id == 0) atomicAdd(&counters[C_SWEEPS], 1ull);
+    }
+}
+
+// =================================================================================================
+// error placement + per-shot event planning
+// =================================================================================================
+struct NoiseDev {
+    uint32_t n_lists;
+    uint32_t list_len[S17_MAX_LISTS];
+    uint32_t list_off[S17_MAX_LISTS];
+    uint32_t eset[S17_MAX_LISTS];
+    uint32_t weighted[S17_MAX_LISTS];   // 1: cum[] holds running sums of the weights for this list
+};
+
+__device__ __forceinline__ bool mask_get(const uint32_t *m, uint32_t bit) { return (m[bit >> 5] >> (bit & 31)) & 1u; }
+__device__ __forceinline__ void mask_set(uint32_t *m, uint32_t bit) { m[bit >> 5] |= 1u << (bit & 31); }
+
+// generate_error_locations (uniform, rejection) / generate_error_locations_non_uniform (CL:151-181)
+__global__ void k_place(NoiseDev nd, const double *__restrict__ cum, uint32_t *__restrict__ masks, uint64_t seed,
+                        uint64_t first_shot, int n_shots)
+{
+    const int shot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (shot >= n_shots) return;
+    uint32_t m[S17_MASK_WORDS];
+#pragma unroll
+    for (int i = 0; i < (int)S17_MASK_WORDS; ++i) m[i] = 0;
+    Philox rng(seed, first_shot + shot, 1u);
+    for (uint32_t t = 0; t < nd.n_lists; ++t) {
+        const uint32_t L = nd.list_len[t], off = nd.list_off[t];
+        const double total = nd.weighted[t] ? cum[off + L - 1] : 0.0;
+        for (uint32_t e = 0; e < nd.eset[t]; ++e) {
+            for (;;) {
+                uint32_t ind;
+                if (!nd.weighted[t]) {
+                    ind = (uint32_t)(rng.next() * (double)L);
+                    if (ind >= L) ind = L - 1;
+                } else {
+                    const double r = rng.next() * total;      // generate_from_distr: first i with cum[i] > r
+                    uint32_t lo = 0, hi = L - 1;
+                    while (lo < hi) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if (cum[off + mid] > r) hi = mid; else lo = mid + 1;
+                    }
+                    ind = lo;
+                }
+                if (!mask_get(m, off + ind)) { mask_set(m, off + ind); break; }
+            }
+        }
+    }
+    uint32_t *out = masks + (size_t)shot * (2 * S17_MASK_WORDS);
+#pragma unroll
+    for (int i = 0; i < (int)S17_MASK_WORDS; ++i) out[i] = m[i];
+}
+
+struct PlanArgs {
+    int n_instr;
+    int noise;        // S17_NOISE_*
+    int noiseless;    // prep cycle: nothing fires, only the leak skip predicate is evaluated
+    int second;       // 1: second (stab_ind=1) cycle -> use_round slots are offset by len/2 (CS:191-193)
+    int rec_half;     // PROB mode: which half of the mask record receives the fired bits (0/1)
+    uint32_t stream;
+    uint64_t seed, first_shot;
+    int n_shots;
+};
+
+// multiply the 6-bit field (x0 z0 x1 z1 k k) on the left by Pauli `p` (1=X 2=Y 3=Z) on qubit q (0/1)
+__device__ __forceinline__ uint32_t pauli_mul(uint32_t f, int q, int p) {
+    uint32_t x = (f >> (2 * q)) & 1u, z = (f >> (2 * q + 1)) & 1u, k = (f >> 4) & 3u;
+    if (p == 1) { x ^= 1u; }
+    else if (p == 3) { k = (k + 2u * x) & 3u; z ^= 1u; }
+    else { k = (k + 1u + 2u * x) & 3u; x ^= 1u; z ^= 1u; }
+    f &= ~((3u << (2 * q)) | (3u << 4));
+    return f | (x << (2 * q)) | (z << (2 * q + 1)) | (k << 4);
+}
+
+__global__ void k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, NoiseDev nd, const double *__restrict__ probs,
+                       uint32_t *__restrict__ ev, uint32_t *__restrict__ masks, uint32_t *__restrict__ leak,
+                       const uint8_t *__restrict__ active)
+{
+    const int shot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (shot >= pa.n_shots || !active[shot]) return;
+    Philox rng(pa.seed, pa.first_shot + shot, pa.stream);
+    uint32_t lk = leak[shot];
+    uint32_t *evs = ev + (size_t)shot * S17_EV_WORDS;
+    uint32_t *mk = masks + (size_t)shot * (2 * S17_MASK_WORDS);
+    uint32_t *mrec = mk + (pa.rec_half ? S17_MASK_WORDS : 0);
+    for (int i = 24; i < (int)S17_EV_WORDS; ++i) evs[i] = 0;
+    uint32_t w = 0, skip = 0;
+    for (int i = 0; i < pa.n_instr; ++i) {
+        const s17_pinstr in = prog[i];
+        if (in.kind == S17_P_OP_BEGIN) {
+            skip = ((lk >> in.a) | (lk >> in.b)) & 1u;
+            w = skip << 24;
+            continue;
+        }
+        if (in.kind == S17_P_OP_END) { evs[in.word] = w; continue; }
+        // S17_P_ERR / S17_P_IDLE: one Bernoulli draw per entry (CS:198), none inside a skipped Rxx block
+        if (in.in_skip && skip) continue;
+        if (pa.noiseless) continue;
+        const uint32_t L = nd.list_len[in.list];
+        const uint32_t slot = in.slot + ((pa.second && in.use_round) ? (L >> 1) : 0u);
+        bool fire;
+        if (pa.noise == S17_NOISE_PROB) {
+            fire = rng.next() < probs[nd.list_off[in.list] + slot];
+            if (fire) mask_set(mrec, nd.list_off[in.list] + slot);
+        } else {
+            fire = mask_get(mk, nd.list_off[in.list] + slot);
+        }
+        if (!fire) continue;
+        if (in.kind == S17_P_IDLE) { evs[in.word] |= 1u << in.a; continue; }
+        uint32_t f = (w >> in.field) & 63u;
+        switch (in.err) {
+        case S17_ERR_X: f = pauli_mul(f, 0, 1); break;
+        case S17_ERR_Y: f = pauli_mul(f, 0, 2); break;
+        case S17_ERR_Z: f = pauli_mul(f, 0, 3); break;
+        case S17_ERR_ZC: f = pauli_mul(f, 0, 3); break;
+        case S17_ERR_ZT: f = pauli_mul(f, 1, 3); break;
+        case S17_ERR_XX: f = pauli_mul(pauli_mul(f, 0, 1), 1, 1); break;
+        case S17_ERR_ZZ: f = pauli_mul(pauli_mul(f, 0, 3), 1, 3); break;
+        case S17_ERR_LEAK_A: lk |= 1u << in.a; break;
+        case S17_ERR_LEAK_AB: lk |= (1u << in.a) | (1u << in.b); break;
+        case S17_ERR_DEPOL: {
+            // insert_2q_error (CS:237-283): 15 equiprobable non-identity pairs, first letter -> qubits[0]
+            int k = (int)(rng.next() * 15.0);
+            if (k > 14) k = 14;
+            const int code = k + 1, p0 = code >> 2, p1 = code & 3;   // IX,IY,IZ,XI,...,ZZ
+            if (p0) f = pauli_mul(f, 0, p0);
+            if (p1) f = pauli_mul(f, 1, p1);
+        } break;
+        default: break;
+        }
+        w = (w & ~(63u << in.field)) | (f << in.field);
+    }
+    leak[shot] = lk;
+}
+
+// =================================================================================================
+// measurement, collapse, correction, read-out
+// =================================================================================================
+struct MeasArgs {
+    int stage;        // 0 prep, 1 first noisy cycle, 2 second cycle
+    int protocol;
+    int forced;
+    uint32_t stream;
+    uint64_t seed, first_shot;
+    int n_shots;
+};
+
+__global__ void k_measure(MeasArgs ma, const double *__restrict__ hist, const uint8_t *__restrict__ forced,
+                          const uint32_t *__restrict__ lut, uint32_t *__restrict__ leak, uint8_t *__restrict__ active,
+                          uint8_t *__restrict__ ready, ShotAux *__restrict__ aux, s17_record *__restrict__ rec,
+                          unsigned long long *__restrict__ counters)
+{
+    const int shot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (shot >= ma.n_shots || !active[shot]) return;
+    const double *h = hist + (size_t)shot * 256;
+    s17_record r = rec[shot];
+    Philox rng(ma.seed, ma.first_shot + shot, ma.stream);
+    uint32_t a = 0;
+    bool bad = false;
+    // one Measure per ancilla in order (All(Measure) | ancilla, CS:848): conditional on earlier outcomes
+    for (int j = 0; j < 8; ++j) {
+        double p0 = 0.0, p1 = 0.0;
+        const uint32_t lowmask = (1u << j) - 1u;
+        for (uint32_t m = 0; m < 256; ++m) {
+            if ((m & lowmask) != a) continue;
+            if ((m >> j) & 1u) p1 += h[m]; else p0 += h[m];
+        }
+        uint32_t out;
+        if (ma.forced) {
+            out = forced[(size_t)shot * S17_MAX_OUTCOMES + r.n_outcomes] & 1u;
+            if ((out ? p1 : p0) <= 0.0) bad = true;
+        } else {
+            out = (rng.next() * (p0 + p1) < p1) ? 1u : 0u;
+        }
+        if (r.n_outcomes < S17_MAX_OUTCOMES) r.outcomes[r.n_outcomes++] = (uint8_t)out;
+        a |= out << j;
+    }
+    const double pa = h[a];
+    ShotAux ax;
+    ax.scale = pa > 0.0 ? 1.0 / sqrt(pa) : 0.0;
+    ax.anc_outcome = a;
+    ax.collapsed = 0;
+    aux[shot] = ax;
+    // a leaked ancilla always reads 1 and is reset (CS:854-857)
+    uint32_t lk = leak[shot];
+    const uint32_t synd = a | ((lk >> 9) & 0xFFu);
+    lk &= 0x1FFu;
+    leak[shot] = lk;
+    r.leak = lk;
+    if (bad) { r.flags |= S17_F_ERROR; atomicAdd(&counters[C_ERRORS], 1ull); }
+
+    bool decode = false;
+    if (ma.stage == 0) {
+        r.quiescent = (uint8_t)synd;
+    } else if (ma.stage == 1) {
+        r.synd1 = (uint8_t)synd;
+        r.flips_a = r.quiescent ^ (uint8_t)synd;                  // (prev - synd) % 2, CL:240, 320, 415
+        const bool not0 = r.flips_a != 0;
+        if (not0) { r.flags |= S17_F_NOT0; atomicAdd(&counters[C_NOT0], 1ull); }
+        if (ma.protocol == S17_PROTO_SINGLE) decode = true;
+        else if (ma.protocol == S17_PROTO_S1) { decode = !not0; if (not0) active[shot] = 0; }      // CL:321, 332
+        else if (ma.protocol == S17_PROTO_S2) { if (!not0) active[shot] = 0; }                    // CL:416, 437
+        else { decode = !not0; if (!not0) active[shot] = 0; }                                     // CL:86-92
+    } else {
+        r.synd2 = (uint8_t)synd;
+        r.flags |= S17_F_SYND2;
+        decode = true;
+    }
+    if (decode) {
+        r.ft_syndrome = r.quiescent ^ (uint8_t)synd;             // CL:424; equals (flips_a + flips_b) % 2, CL:98
+        r.correction = lut[r.ft_syndrome];
+        r.flags |= S17_F_COUNTED;
+        ready[shot] = 1;
+    }
+    rec[shot] = r;
+}
+
+// ProjectQ collapse + renormalise for the 8 measured ancillas, fused with the reset X gates (CS:859-862):
+// the surviving 512-amplitude block moves to ancilla value 0, everything else becomes zero.
+__global__ void __launch_bounds__(256)
+k_collapse(double2 *__restrict__ state, ShotAux *__restrict__ aux, const uint8_t *__restrict__ flag)
+{
+    const int shot = blockIdx.x / 32, part = blockIdx.x % 32, t = threadIdx.x;
+    if (!flag[shot]) return;
+    const uint32_t a = aux[shot].anc_outcome;
+    const double sc = aux[shot].scale;
+    const int owner = a >> 3;
+    double2 *s = state + (size_t)shot * kDim;
+    double2 keep[2];
+    if (part == owner) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const double2 v = s[a * kRun + t + 256 * i];
+            keep[i] = make_double2(v.x * sc, v.y * sc);
+        }
+    }
+    for (int b = 0; b < 8; ++b) {
+        const int blk = part * 8 + b;
+        if (blk == 0 && part != owner) continue;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) s[blk * kRun + t + 256 * i] = make_double2(0.0, 0.0);
+    }
+    if (part == owner) {
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 2; ++i) s[t + 256 * i] = keep[i];
+        if (t == 0) aux[shot].collapsed = 1;
+    }
+}
+
+// apply_correction (CS:901-907): per data qubit X then Z  =>  out[m] = (-1)^{popc(x&z)} (-1)^{popc((m^x)&z)} in[m^x]
+__global__ void __launch_bounds__(256)
+k_pauli(double2 *__restrict__ state, const s17_record *__restrict__ rec, const uint8_t *__restrict__ flag)
+{
+    const int shot = blockIdx.x / 32, part = blockIdx.x % 32, t = threadIdx.x;
+    if (!flag[shot]) return;
+    const uint32_t c = rec[shot].correction;
+    const uint32_t x = c & 0x1FFu, z = (c >> 9) & 0x1FFu;
+    if (!(x | z)) return;
+    double2 *s = state + (size_t)shot * kDim;
+    const double g = (__popc(x & z) & 1) ? -1.0 : 1.0;
+    if (x == 0) {
+        for (int i = 0; i < kDim / 32 / 256; ++i) {
+            const uint32_t m = part * (kDim / 32) + t + 256 * i;
+            const double sg = (__popc(m & z) & 1) ? -g : g;
+            const double2 v = s[m];
+            s[m] = make_double2(sg * v.x, sg * v.y);
+        }
+        return;
+    }
+    const int p = __ffs(x) - 1;
+    for (int i = 0; i < kDim / 64 / 256; ++i) {
+        const uint32_t n = part * (kDim / 64) + t + 256 * i;
+        const uint32_t m0 = insert0((int)n, p), m1 = m0 ^ x;
+        const double2 v0 = s[m0], v1 = s[m1];
+        const double s0 = (__popc(m1 & z) & 1) ? -g : g;   // out[m0] takes in[m1]
+        const double s1 = (__popc(m0 & z) & 1) ? -g : g;
+        s[m0] = make_double2(s0 * v1.x, s0 * v1.y);
+        s[m1] = make_double2(s1 * v0.x, s1 * v0.y);
+    }
+}
+
+struct ReadArgs {
+    int forced;
+    int folded;        // 1: the X part of the correction is folded into the read-out instead of the state
+    int logical_state;
+    uint32_t stream;
+    uint64_t seed, first_shot;
+    int n_shots;
+};
+
+// logical_measurement (CS:52-93): one warp per shot
+__global__ void __launch_bounds__(128)
+k_readout(ReadArgs ra, const double2 *__restrict__ state, const ShotAux *__restrict__ aux,
+          const uint8_t *__restrict__ forced, const uint8_t *__restrict__ cw16, const uint32_t *__restrict__ leak,
+          const uint8_t *__restrict__ ready, s17_record *__restrict__ rec, unsigned long long *__restrict__ counters)
+{
+    const int shot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (shot >= ra.n_shots || !ready[shot]) return;
+    const ShotAux ax = aux[shot];
+    const uint32_t sel = ax.collapsed ? 0u : ax.anc_outcome;
+    const double sc2 = ax.collapsed ? 1.0 : ax.scale * ax.scale;
+    const uint32_t corr = rec[shot].correction;
+    const uint32_t xc = ra.folded ? (corr & 0x1FFu) : 0u;
+    const double2 *blk = state + (size_t)shot * kDim + (size_t)sel * kRun;
+    double p[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const uint32_t d = lane + 32 * i;
+        const double2 v = blk[d ^ xc];       // probability of reading d from the corrected state
+        p[i] = (v.x * v.x + v.y * v.y) * sc2;
+    }
+    Philox rng(ra.seed, ra.first_shot + shot, ra.stream);
+    uint32_t chosen = 0, nout = rec[shot].n_outcomes;
+    bool bad = false;
+    uint8_t outs[9];
+    for (int j = 0; j < 9; ++j) {
+        double p0 = 0.0, p1 = 0.0;
+        const uint32_t lowmask = (1u << j) - 1u;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const uint32_t d = lane + 32 * i;
+            if ((d & lowmask) != chosen) continue;
+            if ((d >> j) & 1u) p1 += p[i]; else p0 += p[i];
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            p0 += __shfl_xor_sync(0xffffffffu, p0, s);
+            p1 += __shfl_xor_sync(0xffffffffu, p1, s);
+        }
+        uint32_t out;
+        if (ra.forced) {
+            out = forced[(size_t)shot * S17_MAX_OUTCOMES + nout + j] & 1u;
+            if ((out ? p1 : p0) <= 0.0) bad = true;
+        } else {
+            double u = rng.next();
+            u = __shfl_sync(0xffffffffu, u, 0);
+            out = (u * (p0 + p1) < p1) ? 1u : 0u;
+        }
+        outs[j] = (uint8_t)out;
+        chosen |= out << j;
+    }
+    if (lane != 0) return;
+    s17_record r = rec[shot];
+    for (int j = 0; j < 9; ++j)
+        if (r.n_outcomes < S17_MAX_OUTCOMES) r.outcomes[r.n_outcomes++] = outs[j];
+    const uint32_t dm = chosen | (leak[shot] & 0x1FFu);                 // leaked data reads 1 (CS:61-63)
+#define S17_B(i) ((dm >> (i)) & 1u)
+    const uint32_t q = r.quiescent;
+    const uint32_t c0 = (S17_B(0) ^ S17_B(1)) ^ ((q >> 0) & 1u);        // CS:71-77
+    const uint32_t c1 = (S17_B(1) ^ S17_B(2) ^ S17_B(4) ^ S17_B(5)) ^ ((q >> 2) & 1u);
+    const uint32_t c2 = (S17_B(3) ^ S17_B(4) ^ S17_B(6) ^ S17_B(7)) ^ ((q >> 5) & 1u);
+    const uint32_t c3 = (S17_B(7) ^ S17_B(8)) ^ ((q >> 7) & 1u);
+#undef S17_B
+    const uint32_t weight = cw16[c0 | (c1 << 1) | (c2 << 2) | (c3 << 3)];
+    const uint32_t logic = (__popc(dm) + weight) & 1u;                   // CS:86
+    r.data_meas = (uint16_t)dm;
+    r.logical_meas = (uint8_t)logic;
+    atomicAdd(&counters[C_COUNTED], 1ull);
+    if (logic != (uint32_t)ra.logical_state) { r.flags |= S17_F_FAIL; atomicAdd(&counters[C_FAILED], 1ull); }
+    if (bad) { r.flags |= S17_F_ERROR; atomicAdd(&counters[C_ERRORS], 1ull); }
+    rec[shot] = r;
+}
+
+__global__ void k_reset(int n_shots, uint32_t *leak, uint8_t *active, uint8_t *ready, s17_record *rec, uint32_t *masks,
+                        int clear_masks, int keep_leak)
+{
+    const int shot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (shot >= n_shots) return;
+    if (!keep_leak) leak[shot] = 0;
+    active[shot] = 1;
+    ready[shot] = 0;
+    s17_record z;
+    memset(&z, 0, sizeof(z));
+    rec[shot] = z;
+    if (clear_masks)
+        for (int i = 0; i < 2 * (int)S17_MASK_WORDS; ++i) masks[(size_t)shot * 2 * S17_MASK_WORDS + i] = 0;
+}
+
+// run-til-fail bookkeeping (CL:52-127): one slot = one run in flight; a failed run frees its slot for the next run id
+struct RtfSlot { uint32_t run_id, rounds, synd_b, alive; };
+
+__global__ void k_rtf_init(int n_slots, uint32_t total_runs, RtfSlot *slots, unsigned long long *counters)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_slots) return;
+    RtfSlot sl;
+    sl.run_id = (uint32_t)s; sl.rounds = 0; sl.synd_b = 0; sl.alive = (uint32_t)s < total_runs;
+    slots[s] = sl;
+    if (s == 0) { counters[C_NEXT_RUN] = (unsigned long long)min((uint32_t)n_slots, total_runs); }
+}
+
+__global__ void k_rtf_begin_round(int n_slots, const RtfSlot *slots, uint8_t *active, uint8_t *ready, s17_record *rec)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_slots) return;
+    active[s] = (uint8_t)slots[s].alive;
+    ready[s] = 0;
+    s17_record z;
+    memset(&z, 0, sizeof(z));
+    rec[s] = z;
+}
+
+__global__ void k_rtf_end_round(int n_slots, uint32_t total_runs, uint32_t max_rounds, RtfSlot *slots,
+                                const s17_record *rec, uint32_t *leak, uint32_t *rounds_out, uint32_t *syndb_out,
+                                unsigned long long *counters)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_slots) return;
+    RtfSlot sl = slots[s];
+    if (!sl.alive) return;
+    const s17_record r = rec[s];
+    sl.rounds += 1;
+    if (r.flags & S17_F_SYND2) sl.synd_b += 1;
+    atomicAdd(&counters[C_ROUNDS], 1ull);
+    const bool fail = (r.flags & S17_F_FAIL) != 0;
+    if (fail || (max_rounds && sl.rounds >= max_rounds)) {
+        rounds_out[sl.run_id] = sl.rounds;
+        syndb_out[sl.run_id] = sl.synd_b;
+        const unsigned long long nxt = atomicAdd(&counters[C_NEXT_RUN], 1ull);
+        if (nxt < total_runs) { sl.run_id = (uint32_t)nxt; sl.rounds = 0; sl.synd_b = 0; leak[s] = 0; }
+        else { sl.alive = 0; }
+    }
+    if (sl.alive) atomicAdd(&counters[C_ALIVE], 1ull);
+    slots[s] = sl;
+}
+
+}  // namespace s17
+
+// =================================================================================================
+// host side: context + C ABI
+// =================================================================================================
+using namespace s17;
+
+struct TimedLaunch { int cat; cudaEvent_t e0, e1; };
+
+struct s17_ctx {
+    int device = 0;
+    uint64_t max_shots = 0;
+    cudaStream_t stream = nullptr;
+    double2 *state = nullptr;
+    uint32_t *ev = nullptr, *masks = nullptr, *leak = nullptr, *lut = nullptr;
+    uint8_t *active = nullptr, *ready = nullptr, *forced = nullptr, *cw16 = nullptr;
+    double *hist = nullptr, *probs = nullptr, *cum = nullptr;
+    ShotAux *aux = nullptr;
+    s17_record *rec = nullptr;
+    unsigned long long *counters = nullptr;
+    s17_pinstr *plan = nullptr;
+    RtfSlot *rtf_slots = nullptr;
+    uint32_t *rtf_rounds = nullptr, *rtf_syndb = nullptr;
+    uint64_t rtf_capacity = 0;
+    int n_plan = 0;
+    std::vector<LayerArg> layers[3];   // prep, first noisy cycle, second noisy cycle
+    NoiseDev nd{};
+    uint32_t total_slots = 0;
+    bool have_program = false, have_tables = false, have_replay = false;
+    uint64_t last_n = 0;
+    // timing
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    std::vector<TimedLaunch> launches;
+    double t_gate = 0, t_meas = 0, t_other = 0, t_span = 0;
+    uint64_t n_gate = 0, n_all = 0;
+    cudaEvent_t span0 = nullptr, span1 = nullptr;
+    std::string err;
+};
+
+static thread_local std::string g_err;
+
+static int fail(s17_ctx *c, int code, const std::string &msg) {
+    if (c) c->err = msg;
+    g_err = msg;
+    return code;
+}
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+            return fail(ctx, S17_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
+    } while (0)
+
+static cudaEvent_t get_event(s17_ctx *c) {
+    if (c->ev_used == c->ev_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        c->ev_pool.push_back(e);
+    }
+    return c->ev_pool[c->ev_used++];
+}
+enum { CAT_GATE = 0, CAT_MEAS = 1, CAT_OTHER = 2 };
+struct Scope {
+    s17_ctx *c; TimedLaunch tl;
+    Scope(s17_ctx *c_, int cat) : c(c_) { tl.cat = cat; tl.e0 = get_event(c); tl.e1 = get_event(c); cudaEventRecord(tl.e0, c->stream); }
+    ~Scope() { cudaEventRecord(tl.e1, c->stream); c->launches.push_back(tl); }
+};
+
+extern "C" int s17_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+extern "C" const char *s17_last_error(const s17_ctx *ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+extern "C" int s17_create(s17_ctx **out, int device, uint64_t max_shots) {
+    s17_ctx *ctx = nullptr;
+    if (!out || max_shots == 0) return fail(nullptr, S17_E_ARG, "s17_create: bad arguments");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0)
+        return fail(nullptr, S17_E_CUDA, "s17_create: no CUDA device (this library has no CPU fallback)");
+    if (device < 0 || device >= n) return fail(nullptr, S17_E_ARG, "s17_create: device index out of range");
+    ctx = new s17_ctx();
+    ctx->device = device;
+    ctx->max_shots = max_shots;
+    CK(cudaSetDevice(device));
+    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    const size_t B = max_shots;
+    CK(cudaMalloc(&ctx->state, B * kDim * sizeof(double2)));
+    CK(cudaMalloc(&ctx->ev, B * S17_EV_WORDS * 4));
+    CK(cudaMalloc(&ctx->masks, B * 2 * S17_MASK_WORDS * 4));
+    CK(cudaMalloc(&ctx->leak, B * 4));
+    CK(cudaMalloc(&ctx->active, B));
+    CK(cudaMalloc(&ctx->ready, B));
+    CK(cudaMalloc(&ctx->forced, B * S17_MAX_OUTCOMES));
+    CK(cudaMalloc(&ctx->hist, B * 256 * sizeof(double)));
+    CK(cudaMalloc(&ctx->aux, B * sizeof(ShotAux)));
+    CK(cudaMalloc(&ctx->rec, B * sizeof(s17_record)));
+    CK(cudaMalloc(&ctx->counters, C_N * sizeof(unsigned long long)));
+    CK(cudaMalloc(&ctx->lut, 256 * 4));
+    CK(cudaMalloc(&ctx->cw16, 16));
+    CK(cudaMalloc(&ctx->probs, 2048 * sizeof(double)));
+    CK(cudaMalloc(&ctx->cum, 2048 * sizeof(double)));
+    CK(cudaMalloc(&ctx->rtf_slots, B * sizeof(RtfSlot)));
+    CK(cudaMemset(ctx->probs, 0, 2048 * sizeof(double)));
+    CK(cudaMemset(ctx->leak, 0, B * 4));
+    CK(cudaMemset(ctx->ev, 0, B * S17_EV_WORDS * 4));
+    CK(cudaFuncSetAttribute(k_layer, cudaFuncAttributeMaxDynamicSharedMemorySize, kTile * 16));
+    CK(cudaEventCreate(&ctx->span0));
+    CK(cudaEventCreate(&ctx->span1));
+    *out = ctx;
+    return S17_OK;
+}
+
+extern "C" int s17_destroy(s17_ctx *ctx) {
+    if (!ctx) return S17_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    void *ptrs[] = {ctx->state, ctx->ev, ctx->masks, ctx->leak, ctx->active, ctx->ready, ctx->forced, ctx->hist,
+                    ctx->aux, ctx->rec, ctx->counters, ctx->lut, ctx->cw16, ctx->probs, ctx->cum, ctx->plan,
+                    ctx->rtf_slots, ctx->rtf_rounds, ctx->rtf_syndb};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return S17_OK;
+}
+
+static int check_layer(s17_ctx *ctx, const s17_layer &L) {
+    if (L.n_ops > 8) return fail(ctx, S17_E_ARG, "layer has more than 8 ops");
+    for (int k = 0; k < 3; ++k)
+        if (L.anc_bits[k] < 9 || L.anc_bits[k] > 16 || (k && L.anc_bits[k] <= L.anc_bits[k - 1]))
+            return fail(ctx, S17_E_ARG, "layer anc_bits must be 3 ascending ancilla bits in 9..16");
+    for (int o = 0; o < L.n_ops; ++o) {
+        const s17_op &op = L.ops[o];
+        if (op.ev_word >= S17_EV_WORDS) return fail(ctx, S17_E_ARG, "op ev_word out of range");
+        if (op.kind == S17_OP_IDLE) continue;
+        if (op.kind != S17_OP_ENT || op.data_bit > 8 || op.n_uops > 8) return fail(ctx, S17_E_ARG, "bad op");
+        bool ok = false;
+        for (int k = 0; k < 3; ++k) ok |= (L.anc_bits[k] == op.anc_bit);
+        if (!ok) return fail(ctx, S17_E_ARG, "op ancilla bit is not staged by its layer");
+    }
+    return S17_OK;
+}
+
+extern "C" int s17_load_program(s17_ctx *ctx, const s17_layer *layers, const uint32_t n_layers[3], const double *params,
+                                uint32_t n_params, const s17_pinstr *plan, uint32_t n_plan, const s17_lists *lists) {
+    if (!ctx || !layers || !n_layers || !plan || !lists) return fail(ctx, S17_E_ARG, "s17_load_program: bad arguments");
+    if (!n_layers[0] || !n_layers[1] || !n_layers[2]) return fail(ctx, S17_E_ARG, "s17_load_program: empty sweep list");
+    if (lists->n_lists > S17_MAX_LISTS) return fail(ctx, S17_E_ARG, "too many probability lists");
+    CK(cudaSetDevice(ctx->device));
+    const s17_layer *src = layers;
+    for (int c = 0; c < 3; ++c) {
+        ctx->layers[c].clear();
+        for (uint32_t i = 0; i < n_layers[c]; ++i, ++src) {
+            if (int rc = check_layer(ctx, *src)) return rc;
+            LayerArg A;
+            memset(&A, 0, sizeof(A));
+            A.L = *src;
+            int np = 0;
+            for (int o = 0; o < A.L.n_ops; ++o)
+                for (int u = 0; u < A.L.ops[o].n_uops; ++u) {
+                    s17_uop &up = A.L.ops[o].uops[u];
+                    if (up.type >= S17_U_ROT_X) {
+                        if (up.param >= n_params || !params) return fail(ctx, S17_E_ARG, "uop param out of range");
+                        if (np >= 32) return fail(ctx, S17_E_ARG, "too many rotation parameters in one layer");
+                        A.prm[np] = make_double2(params[2 * up.param], params[2 * up.param + 1]);
+                        up.param = (uint8_t)np++;
+                    }
+                }
+            int k = 0;
+            for (int b = 9; b <= 16; ++b) {
+                bool in = false;
+                for (int j = 0; j < 3; ++j) in |= (A.L.anc_bits[j] == b);
+                if (!in) A.other_bits[k++] = (uint8_t)b;
+            }
+            ctx->layers[c].push_back(A);
+        }
+    }
+    if (ctx->plan) { cudaFree(ctx->plan); ctx->plan = nullptr; }
+    CK(cudaMalloc(&ctx->plan, n_plan * sizeof(s17_pinstr)));
+    CK(cudaMemcpy(ctx->plan, plan, n_plan * sizeof(s17_pinstr), cudaMemcpyHostToDevice));
+    ctx->n_plan = (int)n_plan;
+    memset(&ctx->nd, 0, sizeof(ctx->nd));
+    ctx->nd.n_lists = lists->n_lists;
+    uint32_t off = 0;
+    for (uint32_t t = 0; t < lists->n_lists; ++t) {
+        ctx->nd.list_len[t] = lists->list_len[t];
+        ctx->nd.list_off[t] = off;
+        off += lists->list_len[t];
+    }
+    if (off > S17_MASK_WORDS * 32 || off > 2048) return fail(ctx, S17_E_ARG, "too many error slots");
+    ctx->total_slots = off;
+    for (uint32_t i = 0; i < n_plan; ++i) {
+        const s17_pinstr &in = plan[i];
+        if (in.kind == S17_P_ERR || in.kind == S17_P_IDLE) {
+            if (in.list >= lists->n_lists) return fail(ctx, S17_E_ARG, "plan entry names an unknown list");
+            if (in.slot >= lists->list_len[in.list]) return fail(ctx, S17_E_ARG, "plan slot beyond its list (list too short)");
+        }
+        if (in.word >= S17_EV_WORDS) return fail(ctx, S17_E_ARG, "plan word out of range");
+    }
+    CK(cudaMemset(ctx->probs, 0, 2048 * sizeof(double)));
+    ctx->have_program = true;
+    return S17_OK;
+}
+
+extern "C" int s17_load_tables(s17_ctx *ctx, const uint32_t *lut256, const uint8_t *cw16) {
+    if (!ctx || !lut256 || !cw16) return fail(ctx, S17_E_ARG, "s17_load_tables: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy(ctx->lut, lut256, 256 * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->cw16, cw16, 16, cudaMemcpyHostToDevice));
+    ctx->have_tables = true;
+    return S17_OK;
+}
+
+extern "C" int s17_set_slot_probs(s17_ctx *ctx, uint32_t list_id, const double *p, uint32_t len) {
+    if (!ctx || !ctx->have_program || !p) return fail(ctx, S17_E_ARG, "s17_set_slot_probs: bad arguments");
+    if (list_id >= ctx->nd.n_lists || len != ctx->nd.list_len[list_id])
+        return fail(ctx, S17_E_ARG, "make sure you pass enough probabilities to specify the error model");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy(ctx->probs + ctx->nd.list_off[list_id], p, len * sizeof(double), cudaMemcpyHostToDevice));
+    return S17_OK;
+}
+
+extern "C" int s17_set_subset(s17_ctx *ctx, uint32_t n_types, const uint32_t *eset, const uint32_t *n_loc,
+                              const double *const *weights) {
+    if (!ctx || !ctx->have_program || !eset || !n_loc) return fail(ctx, S17_E_ARG, "s17_set_subset: bad arguments");
+    if (n_types != ctx->nd.n_lists)
+        return fail(ctx, S17_E_ARG, "make sure you pass enough probabilities to specify the error model");
+    CK(cudaSetDevice(ctx->device));
+    std::vector<double> cum(2048, 0.0);
+    for (uint32_t t = 0; t < n_types; ++t) {
+        if (n_loc[t] != ctx->nd.list_len[t]) return fail(ctx, S17_E_ARG, "subset locations do not match the program's lists");
+        if (eset[t] > n_loc[t]) return fail(ctx, S17_E_ARG, "more errors than locations (the reference would loop forever)");
+        ctx->nd.eset[t] = eset[t];
+        ctx->nd.weighted[t] = (weights && weights[t]) ? 1u : 0u;
+        if (ctx->nd.weighted[t]) {
+            double tot = 0.0;
+            uint32_t positive = 0;
+            for (uint32_t i = 0; i < n_loc[t]; ++i) {
+                tot += weights[t][i];                      // same running sum as generate_from_distr (CL:165-168)
+                cum[ctx->nd.list_off[t] + i] = tot;
+                positive += weights[t][i] > 0.0;
+            }
+            if (eset[t] > positive) return fail(ctx, S17_E_ARG, "more errors than locations with non-zero weight");
+        }
+    }
+    CK(cudaMemcpy(ctx->cum, cum.data(), 2048 * sizeof(double), cudaMemcpyHostToDevice));
+    return S17_OK;
+}
+
+extern "C" int s17_set_replay(s17_ctx *ctx, uint64_t n, const uint8_t *masks, uint64_t mstride, const uint8_t *outcomes,
+                              uint64_t ostride) {
+    if (!ctx || !ctx->have_program || n > ctx->max_shots) return fail(ctx, S17_E_ARG, "s17_set_replay: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    if (masks) {
+        if (mstride < ctx->total_slots) return fail(ctx, S17_E_ARG, "mask stride shorter than the program's slots");
+        std::vector<uint32_t> bits(n * 2 * S17_MASK_WORDS, 0u);
+        for (uint64_t s = 0; s < n; ++s)
+            for (uint32_t i = 0; i < ctx->total_slots; ++i)
+                if (masks[s * mstride + i]) bits[s * 2 * S17_MASK_WORDS + (i >> 5)] |= 1u << (i & 31);
+        CK(cudaMemcpy(ctx->masks, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice));
+    }
+    if (outcomes) {
+        if (ostride > S17_MAX_OUTCOMES) return fail(ctx, S17_E_ARG, "outcome stride too long");
+        std::vector<uint8_t> o(n * S17_MAX_OUTCOMES, 0);
+        for (uint64_t s = 0; s < n; ++s) memcpy(&o[s * S17_MAX_OUTCOMES], outcomes + s * ostride, ostride);
+        CK(cudaMemcpy(ctx->forced, o.data(), o.size(), cudaMemcpyHostToDevice));
+    }
+    ctx->have_replay = true;
+    return S17_OK;
+}
+
+static inline int blocks_for(uint64_t n, int per) { return (int)((n + per - 1) / per); }
+
+// one stabiliser cycle: plan -> gate sweeps -> ancilla measurement decisions
+static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second, int init_basis, uint32_t max_layers) {
+    const int n = (int)a.n_shots;
+    PlanArgs pa;
+    pa.n_instr = ctx->n_plan;
+    pa.noise = (int)a.noise;
+    pa.noiseless = (stage == 0);
+    pa.second = second;
+    pa.rec_half = (stage == 2) ? 1 : 0;
+    pa.stream = 8u + (uint32_t)stage;
+    pa.seed = a.seed;
+    pa.first_shot = a.first_shot_id;
+    pa.n_shots = n;
+    {
+        Scope s(ctx, CAT_OTHER);
+        k_plan<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(ctx->plan, pa, ctx->nd, ctx->probs, ctx->ev, ctx->masks,
+                                                            ctx->leak, ctx->active);
+    }
+    const std::vector<LayerArg> &Ls = ctx->layers[stage == 0 ? 0 : (second ? 2 : 1)];
+    uint32_t nl = (uint32_t)Ls.size();
+    if (max_layers && max_layers < nl) nl = max_layers;
+    for (uint32_t i = 0; i < nl; ++i) {
+        Scope s(ctx, CAT_GATE);
+        k_layer<<<n * kTilesPerShot, kLayerThreads, kTile * 16, ctx->stream>>>(
+            ctx->state, Ls[i], ctx->ev, ctx->active, ctx->hist, ctx->counters, (i == 0) ? init_basis : -1);
+        ctx->n_gate++;
+    }
+    if (max_layers && max_layers < Ls.size()) return S17_OK;
+    MeasArgs ma;
+    ma.stage = stage;
+    ma.protocol = (int)a.protocol;
+    ma.forced = (int)a.forced;
+    ma.stream = 16u + (uint32_t)stage;
+    ma.seed = a.seed;
+    ma.first_shot = a.first_shot_id;
+    ma.n_shots = n;
+    {
+        Scope s(ctx, CAT_MEAS);
+        k_measure<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(ma, ctx->hist, ctx->forced, ctx->lut, ctx->leak,
+                                                               ctx->active, ctx->ready, ctx->aux, ctx->rec, ctx->counters);
+    }
+    return S17_OK;
+}
+
+static void collapse(s17_ctx *ctx, int n, const uint8_t *flag) {
+    Scope s(ctx, CAT_MEAS);
+    k_collapse<<<n * 32, 256, 0, ctx->stream>>>(ctx->state, ctx->aux, flag);
+}
+
+// one full round for every active slot: prep, cycle A, optional cycle B, decode, read-out
+static int run_round(s17_ctx *ctx, const s17_run_args &a) {
+    const int n = (int)a.n_shots;
+    const int basis_index = a.logical_state ? 0x1FF : 0;     // All(X) | data when state == 1 (CS:103-104)
+    if (int rc = run_cycle(ctx, a, 0, 0, basis_index, 0)) return rc;
+    collapse(ctx, n, ctx->active);
+    if (a.stop_stage == S17_STOP_AFTER_PREP) return S17_OK;
+    if (a.stop_stage == S17_STOP_CYCLE1_GATES) return run_cycle(ctx, a, 1, 0, -1, a.stop_layers ? a.stop_layers : 1000);
+    if (int rc = run_cycle(ctx, a, 1, 0, -1, 0)) return rc;
+    if (a.stop_stage == S17_STOP_AFTER_CYCLE1) {
+        Scope s(ctx, CAT_OTHER);
+        cudaMemsetAsync(ctx->active, 1, n, ctx->stream);
+        collapse(ctx, n, ctx->active);
+        return S17_OK;
+    }
+    if (a.protocol == S17_PROTO_S2 || a.protocol == S17_PROTO_RTF) {
+        collapse(ctx, n, ctx->active);
+        // s2: stab_ind=1 slots (CL:422); run-til-fail: cycle B reuses the stab_ind=0 probabilities (CL:92)
+        if (int rc = run_cycle(ctx, a, 2, a.protocol == S17_PROTO_S2 ? 1 : 0, -1, 0)) return rc;
+    }
+    if (a.materialize) {
+        collapse(ctx, n, ctx->ready);
+        Scope s(ctx, CAT_OTHER);
+        k_pauli<<<n * 32, 256, 0, ctx->stream>>>(ctx->state, ctx->rec, ctx->ready);
+    }
+    ReadArgs ra;
+    ra.forced = (int)a.forced;
+    ra.folded = a.materialize ? 0 : 1;
+    ra.logical_state = (int)a.logical_state;
+    ra.stream = 32u;
+    ra.seed = a.seed;
+    ra.first_shot = a.first_shot_id;
+    ra.n_shots = n;
+    {
+        Scope s(ctx, CAT_MEAS);
+        k_readout<<<blocks_for((uint64_t)n * 32, 128), 128, 0, ctx->stream>>>(ra, ctx->state, ctx->aux, ctx->forced, ctx->cw16,
+                                                                          ctx->leak, ctx->ready, ctx->rec, ctx->counters);
+    }
+    return S17_OK;
+}
+
+static int finish_timing(s17_ctx *ctx) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    for (const TimedLaunch &tl : ctx->launches) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, tl.e0, tl.e1);
+        (tl.cat == CAT_GATE ? ctx->t_gate : tl.cat == CAT_MEAS ? ctx->t_meas : ctx->t_other) += ms;
+    }
+    ctx->n_all += ctx->launches.size();
+    ctx->launches.clear();
+    ctx->ev_used = 0;
+    return S17_OK;
+}
+
+extern "C" int s17_run(s17_ctx *ctx, const s17_run_args *args, s17_counts *out) {
+    if (!ctx || !args || !out) return fail(ctx, S17_E_ARG, "s17_run: bad arguments");
+    if (!ctx->have_program || !ctx->have_tables) return fail(ctx, S17_E_STATE, "s17_run: load the program and tables first");
+    s17_run_args a = *args;
+    if (a.n_shots == 0 || a.n_shots > ctx->max_shots) return fail(ctx, S17_E_ARG, "s17_run: n_shots out of range");
+    if (a.protocol > S17_PROTO_RTF || a.noise > S17_NOISE_REPLAY) return fail(ctx, S17_E_ARG, "s17_run: bad protocol/noise");
+    if (a.basis_x) return fail(ctx, S17_E_ARG, "s17_run: X-basis preparation is not implemented (dead in the reference, CL:274)");
+    if ((a.noise == S17_NOISE_REPLAY || a.forced) && !ctx->have_replay)
+        return fail(ctx, S17_E_STATE, "s17_run: replay requested but s17_set_replay was not called");
+    CK(cudaSetDevice(ctx->device));
+    ctx->t_gate = ctx->t_meas = ctx->t_other = 0;
+    ctx->n_gate = ctx->n_all = 0;
+    ctx->launches.clear();
+    ctx->ev_used = 0;
+    const int n = (int)a.n_shots;
+    CK(cudaEventRecord(ctx->span0, ctx->stream));
+    CK(cudaMemsetAsync(ctx->counters, 0, C_N * sizeof(unsigned long long), ctx->stream));
+    {
+        Scope s(ctx, CAT_OTHER);
+        k_reset<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(n, ctx->leak, ctx->active, ctx->ready, ctx->rec, ctx->masks,
+                                                             a.noise == S17_NOISE_PROB, 0);
+    }
+    if (a.noise == S17_NOISE_SUBSET) {
+        Scope s(ctx, CAT_OTHER);
+        k_place<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(ctx->nd, ctx->cum, ctx->masks, a.seed, a.first_shot_id, n);
+    }
+    uint64_t shots_done = a.n_shots;
+    if (a.protocol != S17_PROTO_RTF) {
+        if (int rc = run_round(ctx, a)) return rc;
+        if (int rc = finish_timing(ctx)) return rc;
+    } else {
+        // run-til-fail (CL:33-148): every slot carries one run; rounds are fresh restarts (CL:70-73) that
+        // share only the leak register (reset per run here; the reference never resets it, CL:49)
+        if (a.rtf_runs == 0) return fail(ctx, S17_E_ARG, "s17_run: rtf_runs must be > 0");
+        if (ctx->rtf_capacity < a.rtf_runs) {
+            if (ctx->rtf_rounds) cudaFree(ctx->rtf_rounds);
+            if (ctx->rtf_syndb) cudaFree(ctx->rtf_syndb);
+            CK(cudaMalloc(&ctx->rtf_rounds, (size_t)a.rtf_runs * 4));
+            CK(cudaMalloc(&ctx->rtf_syndb, (size_t)a.rtf_runs * 4));
+            ctx->rtf_capacity = a.rtf_runs;
+        }
+        CK(cudaMemsetAsync(ctx->rtf_rounds, 0, (size_t)a.rtf_runs * 4, ctx->stream));
+        CK(cudaMemsetAsync(ctx->rtf_syndb, 0, (size_t)a.rtf_runs * 4, ctx->stream));
+        k_rtf_init<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(n, a.rtf_runs, ctx->rtf_slots, ctx->counters);
+        uint64_t round_no = 0;
+        for (;;) {
+            k_rtf_begin_round<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(n, ctx->rtf_slots, ctx->active, ctx->ready, ctx->rec);
+            s17_run_args ar = a;
+            ar.seed = a.seed + 0x9E3779B97F4A7C15ull * (round_no + 1);   // fresh Philox key per round
+            if (int rc = run_round(ctx, ar)) return rc;
+            CK(cudaMemsetAsync(ctx->counters + C_ALIVE, 0, sizeof(unsigned long long), ctx->stream));
+            k_rtf_end_round<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(n, a.rtf_runs, a.rtf_max_rounds, ctx->rtf_slots, ctx->rec,
+                                                                         ctx->leak, ctx->rtf_rounds, ctx->rtf_syndb, ctx->counters);
+            if (int rc = finish_timing(ctx)) return rc;
+            unsigned long long alive = 0;
+            CK(cudaMemcpy(&alive, ctx->counters + C_ALIVE, sizeof(alive), cudaMemcpyDeviceToHost));
+            ++round_no;
+            if (alive == 0) break;
+        }
+    }
+    unsigned long long c[C_N];
+    CK(cudaEventRecord(ctx->span1, ctx->stream));
+    CK(cudaMemcpyAsync(c, ctx->counters, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ctx->span0, ctx->span1));
+        ctx->t_span = ms;
+    }
+    memset(out, 0, sizeof(*out));
+    out->shots = shots_done;
+    out->failed = c[C_FAILED];
+    out->not0 = c[C_NOT0];
+    out->counted = c[C_COUNTED];
+    out->errors = c[C_ERRORS];
+    out->sweeps = c[C_SWEEPS];
+    out->rounds = c[C_ROUNDS];
+    ctx->last_n = a.n_shots;
+    return S17_OK;
+}
+
+extern "C" int s17_read_records(s17_ctx *ctx, s17_record *out, uint64_t n) {
+    if (!ctx || !out || n > ctx->max_shots) return fail(ctx, S17_E_ARG, "s17_read_records: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy(out, ctx->rec, n * sizeof(s17_record), cudaMemcpyDeviceToHost));
+    return S17_OK;
+}
+
+extern "C" int s17_read_events(s17_ctx *ctx, uint32_t *out, uint64_t n) {
+    if (!ctx || !out || n > ctx->max_shots) return fail(ctx, S17_E_ARG, "s17_read_events: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy(out, ctx->ev, n * S17_EV_WORDS * 4, cudaMemcpyDeviceToHost));
+    return S17_OK;
+}
+
+extern "C" int s17_read_masks(s17_ctx *ctx, uint32_t *out, uint64_t n) {
+    if (!ctx || !out || n > ctx->max_shots) return fail(ctx, S17_E_ARG, "s17_read_masks: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy(out, ctx->masks, n * 2 * S17_MASK_WORDS * 4, cudaMemcpyDeviceToHost));
+    return S17_OK;
+}
+
+extern "C" int s17_read_state(s17_ctx *ctx, uint64_t shot, double *re_im) {
+    if (!ctx || !re_im || shot >= ctx->max_shots) return fail(ctx, S17_E_ARG, "s17_read_state: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy(re_im, ctx->state + shot * kDim, kDim * sizeof(double2), cudaMemcpyDeviceToHost));
+    return S17_OK;
+}
+
+extern "C" int s17_read_rtf(s17_ctx *ctx, uint32_t *rounds, uint32_t *syndb, uint64_t n_runs) {
+    if (!ctx || !rounds || n_runs > ctx->rtf_capacity) return fail(ctx, S17_E_ARG, "s17_read_rtf: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy(rounds, ctx->rtf_rounds, n_runs * 4, cudaMemcpyDeviceToHost));
+    if (syndb) CK(cudaMemcpy(syndb, ctx->rtf_syndb, n_runs * 4, cudaMemcpyDeviceToHost));
+    return S17_OK;
+}
+
+extern "C" int s17_last_timing(s17_ctx *ctx, double *gate_ms, double *measure_ms, double *other_ms, uint64_t *gate_launches,
+                               uint64_t *all_launches, double *span_ms) {
+    if (!ctx) return fail(ctx, S17_E_ARG, "s17_last_timing: bad arguments");
+    if (span_ms) *span_ms = ctx->t_span;
+    if (gate_ms) *gate_ms = ctx->t_gate;
+    if (measure_ms) *measure_ms = ctx->t_meas;
+    if (other_ms) *other_ms = ctx->t_other;
+    if (gate_launches) *gate_launches = ctx->n_gate;
+    if (all_launches) *all_launches = ctx->n_all;
+    return S17_OK;
+}

@@ -1,0 +1,123 @@
+"""Host-side logic (no GPU): the compiled cycle equals the reference's traced gate stream, slot
+indexing / list lengths, program structure, table packing and the C-ABI export list."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from surface_17_iqt_b200 import _lib as L
+from surface_17_iqt_b200 import backend, circuit
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _reduce(theta):
+    return round(float(theta) % (4.0 * np.pi), 12)
+
+
+def test_gate_stream_equals_reference_trace(golden):
+    trace = golden("cycle_trace.json")["trace"]
+    mine = circuit.gate_stream()
+    assert len(mine) == len(trace) == 54
+    for (name, angle, bits), (rn, ra, rb) in zip(mine, trace):
+        assert name == rn and list(bits) == rb and abs(_reduce(angle) - ra) < 1e-12
+
+
+def test_list_lengths(error_models):
+    assert circuit.list_lengths(error_models["PDD_model"]) == [12, 18, 24, 78, 24]
+    assert circuit.list_lengths(error_models["Dress_cooling"]) == [12, 18, 24, 78, 24, 119]
+    assert circuit.list_lengths(error_models["PDD_model"], two_rounds=True) == [24, 36, 48, 156, 48]
+    assert circuit.list_lengths(error_models["depolarising_model"]) == [30, 30, 30, 24]
+    assert circuit.list_lengths(error_models["coherent_model"]) == [30, 24, 24]
+
+
+def test_leak_index_quirk_preserved():
+    ops = circuit.build_cycle()
+    op = [o for o in ops if o.timestep == 4][1]
+    assert (op.data, op.ancilla) == (3, 5) and (op.d_leak, op.a_leak) == (1, 11)    # CS:559-561
+    for o in ops:
+        if o is not op:
+            assert (o.d_leak, o.a_leak) == (o.data, 9 + o.ancilla)
+
+
+@pytest.mark.parametrize("fusion,n_layers", [(0, 54), (1, 8), (2, 4)])
+def test_program_shapes(error_models, fusion, n_layers):
+    prog = circuit.compile_program(error_models["PDD_model"], [12, 18, 24, 78, 24], fusion=fusion)
+    assert len(prog.layers[0]) == len(prog.layers[1]) == len(prog.layers[2]) == n_layers
+    n_uops = sum(op.n_uops for lay in prog.layers[0] for op in lay.ops[:lay.n_ops])
+    assert n_uops == 54
+    assert [lay.emit_hist for lay in prog.layers[0]] == [0] * (n_layers - 1) + [1]
+    for lay in prog.layers[0]:
+        for op in lay.ops[:lay.n_ops]:
+            assert op.anc_bit in list(lay.anc_bits)
+    errs = [p for p in prog.plan if p.kind == L.P_ERR]
+    # 12 Rx x 2 + 18 Ry x 2 + 24 Rxx x 4 entries
+    assert len(errs) == 12 * 2 + 18 * 2 + 24 * 4
+    for p in errs:
+        assert p.slot < prog.list_len[p.list]
+
+
+def test_cooling_program(error_models):
+    prog = circuit.compile_program(error_models["PDD_cooling"], [12, 18, 24, 78, 24, 119], fusion=2, cooling=True)
+    idle = [p for p in prog.plan if p.kind == L.P_IDLE]
+    assert len(idle) == 119 and [p.slot for p in idle] == list(range(119))
+    assert all(p.use_round == 0 for p in idle)
+    assert sum(1 for lay in prog.layers[0] for op in lay.ops[:lay.n_ops] if op.kind == L.OP_IDLE) == 7
+    with pytest.raises(KeyError):
+        circuit.compile_program(error_models["PDD_model"], [12, 18, 24, 78, 24], cooling=True)
+    with pytest.raises(ValueError):
+        circuit.compile_program(error_models["PDD_model"], [12, 18, 24, 78])
+
+
+def test_coherent_program(error_models):
+    eps1, eps2 = [0.02] * 30, [0.02] * 24
+    prog = circuit.compile_program(error_models["coherent_model"], [30, 24, 24], fusion=1,
+                                   over_angles={"eps_1q": eps1, "eps_2q": eps2})
+    assert not [u for lay in prog.layers[0] for op in lay.ops[:lay.n_ops] for u in op.uops[:op.n_uops]
+                if u.type >= L.U_ROT_X]              # preparation cycle stays noiseless
+    rot = [u.type for lay in prog.layers[1] for op in lay.ops[:lay.n_ops] for u in op.uops[:op.n_uops]
+           if u.type >= L.U_ROT_X]
+    assert len(rot) == 54
+    assert abs(prog.params[0] - np.cos(0.01)) < 1e-15 and abs(prog.params[1] - np.sin(0.01)) < 1e-15
+
+
+def test_table_packing(correction_table, bitflip_table):
+    lut = backend.pack_correction_table(correction_table)
+    assert lut[0] == 0
+    vec = correction_table["0 0 0 0 0 0 0 1"][0]       # ancilla 7 flipped -> X on data 8
+    assert lut[1 << 7] == sum(v << i for i, v in enumerate(vec)) == 1 << 8
+    cw = backend.pack_bitflip_table(bitflip_table)
+    assert cw[0] == 0 and cw[0b0101] == 2 and cw[0b1000] == 1
+
+
+def test_library_exports_every_declared_symbol():
+    """libs17.so loads without a GPU and exports exactly what include/s17.h declares."""
+    lib_path = os.path.join(REPO, "surface_17_iqt_b200", "libs17.so")
+    if not os.path.exists(lib_path):
+        import __graft_entry__ as g
+        g.build_cuda()
+    header = open(os.path.join(REPO, "include", "s17.h")).read()
+    declared = set(re.findall(r"\b(s17_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(L.EXPORTS)
+    lib = ctypes.CDLL(lib_path)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.s17_device_count() >= 0
+
+
+def test_no_silent_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(L.S17Error):
+        backend.Backend(4)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(REPO, "surface_17_iqt_b200")
+    out = subprocess.run(["grep", "-rIl", "--include=*.py", "--include=*.cu", "--include=*.cuh", "-E",
+                          r"(from|import) +oracle|oracle/", pkg], capture_output=True, text=True).stdout.strip()
+    assert out == "", out

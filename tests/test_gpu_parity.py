@@ -1,0 +1,300 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the golden vectors.
+
+Bars: integer / bit fields (syndromes, corrections, read-outs, pass/fail, leak flags) bit-exact;
+amplitudes within 1e-10 per amplitude (BASELINE.json north_star).
+"""
+import os
+import random
+
+import numpy as np
+import pytest
+
+from oracle import s17_oracle as so
+from oracle import sv
+from surface_17_iqt_b200 import _lib as L
+from surface_17_iqt_b200 import api, circuit
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+AMP_TOL = 1e-10
+FIELDS = ("quiescent", "synd1", "synd2", "flips_a", "ft_syndrome", "correction", "data_meas", "logical_meas",
+          "fail", "not0", "counted", "leaked")
+
+
+def flat(p_set):
+    return [b for lst in p_set for b in lst]
+
+
+def make_sim(models, ct, bt, model, list_len, n, fusion=1, cooling=False, **kw):
+    return api.Simulation(model, list_len, max_shots=n, fusion=fusion, cooling=cooling, correction_table=ct,
+                          bitflip_table=bt, error_models=models, **kw)
+
+
+@pytest.mark.parametrize("fusion", [0, 1, 2])
+def test_golden_replays(error_models, correction_table, bitflip_table, golden, fusion):
+    """Replayed reference trajectories (masks + forced outcomes): every record field bit-exact, and the
+    post-correction state equals the reference's 512-amplitude block within 1e-10."""
+    reps = golden("replays.json")["replays"]
+    blocks = np.load(os.path.join(GOLDEN, "replay_blocks.npz"))["blocks"]
+    groups = {}
+    for r in reps:
+        groups.setdefault((r["model"], r["protocol"], r["cooling"]), []).append(r)
+    for (model, protocol, cooling), rs in groups.items():
+        list_len = [len(x) for x in rs[0]["p_set"]]
+        sim = make_sim(error_models, correction_table, bitflip_table, model, list_len, len(rs), fusion, cooling)
+        sim.backend.set_replay([flat(r["p_set"]) for r in rs], [r["outcomes"] for r in rs])
+        c = sim.backend.run(protocol, len(rs), L.NOISE_REPLAY, forced=True, materialize=True)
+        assert c.errors == 0
+        recs = sim.backend.records(len(rs))
+        for i, r in enumerate(rs):
+            for f in FIELDS:
+                assert recs[i].get(f) == r.get(f), (model, protocol, i, f, recs[i].get(f), r.get(f))
+            if r["block_index"] >= 0:
+                psi = sim.backend.state(i)
+                assert np.max(np.abs(psi[:512] - blocks[r["block_index"]])) < AMP_TOL
+                assert np.sum(np.abs(psi[512:]) ** 2) < 1e-20
+        assert c.failed == sum(r["fail"] for r in rs)
+        assert c.not0 == sum(r["not0"] for r in rs)
+        sim.close()
+
+
+def test_amplitudes_after_every_gate(error_models, correction_table, bitflip_table, golden):
+    """fusion=0 is ProjectQ's execution model (one sweep per gate): compare the full 2^17 state with the
+    oracle after each of the 54 gates of a noiseless cycle."""
+    trace = golden("cycle_trace.json")["trace"]
+    outcomes = [0, 1, 0, 0, 1, 0, 1, 0]
+    sim = make_sim(error_models, correction_table, bitflip_table, "PDD_model", [12, 18, 24, 78, 24], 1, fusion=0)
+    zero = [[0] * n for n in (12, 18, 24, 78, 24)]
+    sim.backend.set_replay([flat(zero)], [outcomes + [0] * 8])
+    orc = so.ShotOracle(error_models, correction_table, bitflip_table)
+    st = sv.StateVector(17)
+    gates = error_models["PDD_model"]["gates"]
+    probs = dict(zip(error_models["PDD_model"]["probabilities"], zero))
+    q = orc.logical_prep(st, "Z", 0, 17 * [0], gates, probs, random.Random(0), so.ForcedMeasure(outcomes))
+    assert list(q) == outcomes
+    sim.backend.run("s1", 1, L.NOISE_REPLAY, forced=True, stop_stage=L.STOP_AFTER_PREP)
+    assert np.max(np.abs(sim.backend.state(0) - st.psi)) < AMP_TOL
+    for k, (name, angle, bits) in enumerate(trace):
+        orc._gate(st, name, bits, angle)
+        sim.backend.run("s1", 1, L.NOISE_REPLAY, forced=True, stop_stage=L.STOP_CYCLE1_GATES, stop_layers=k + 1)
+        err = np.max(np.abs(sim.backend.state(0) - st.psi))
+        assert err < AMP_TOL, (k, name, bits, err)
+    sim.close()
+
+
+@pytest.mark.parametrize("fusion", [1, 2])
+def test_amplitudes_noisy_cycle_before_measurement(error_models, correction_table, bitflip_table, fusion):
+    """Full state after the gates of a noisy cycle (Pauli events of every kind, leak skips, idle Z)."""
+    rng = random.Random(99)
+    for model, cooling in (("PDD_model", False), ("Dress_cooling", True), ("depolarising_model", False)):
+        list_len = circuit.list_lengths(error_models[model])
+        n = 6
+        p_sets, scripts = [], []
+        for _ in range(n):
+            p_set = [[0] * L_ for L_ in list_len]
+            for t, L_ in enumerate(list_len):
+                for i in rng.sample(range(L_), min(L_, 3)):
+                    p_set[t][i] = 1
+            p_sets.append(p_set)
+        outcomes = [[rng.randint(0, 1) if j in (1, 3, 4, 6) else 0 for j in range(8)] for _ in range(n)]
+        sim = make_sim(error_models, correction_table, bitflip_table, model, list_len, n, fusion, cooling)
+        sim.backend.set_replay([flat(p) for p in p_sets], outcomes)
+        sim.backend.run("single", n, L.NOISE_REPLAY, forced=True, stop_stage=L.STOP_CYCLE1_GATES, seed=3)
+        ev = sim.backend.events(n)
+        orc = so.ShotOracle(error_models, correction_table, bitflip_table)
+        gates = error_models[model]["gates"]
+        for i in range(n):
+            if model == "depolarising_model":
+                # the 15-way choice is drawn on device: read it back from the event word of each Rxx
+                script = {}
+                for k in range(24):
+                    f = (int(ev[i, k]) >> 6) & 63
+                    code = {0: 0, 1: 1, 3: 2, 2: 3}   # (x | z<<1) -> I X Y Z
+                    p0, p1 = code[f & 3], code[(f >> 2) & 3]
+                    if p0 or p1:
+                        script[(0, k)] = p0 * 4 + p1 - 1
+                orc.depol_script = script
+            st = sv.StateVector(17)
+            probs = dict(zip(error_models[model]["probabilities"], p_sets[i]))
+            leaked = 17 * [0]
+            orc.logical_prep(st, "Z", 0, leaked, gates, probs, random.Random(0), so.ForcedMeasure(outcomes[i]))
+            orc.stabilizer_cycle(st, leaked, gates, probs, random.Random(0), None, cooling=cooling, gates_only=True)
+            err = np.max(np.abs(sim.backend.state(i) - st.psi))
+            assert err < AMP_TOL, (model, i, err)
+        sim.close()
+
+
+@pytest.mark.parametrize("model,protocol,cooling,eset", [
+    ("PDD_model", "s1", False, [0, 0, 1, 1, 0]),
+    ("PDD_model", "s2", False, [0, 1, 2, 1, 0]),
+    ("Dress_model", "s2", False, [1, 0, 1, 3, 1]),
+    ("Dress_cooling", "s2", True, [0, 0, 1, 2, 0, 3]),
+    ("PDD_cooling", "single", True, [1, 1, 1, 1, 1, 2]),
+])
+def test_sampled_trajectories_replay_bit_exact_in_oracle(error_models, correction_table, bitflip_table, model,
+                                                         protocol, cooling, eset):
+    """Device-sampled shots (Philox placement + outcomes): replaying their masks and outcomes through the
+    oracle reproduces syndromes, corrections, read-outs and pass/fail bit for bit."""
+    per_round = circuit.list_lengths(error_models[model])
+    locs = [2 * x for x in per_round] if protocol == "s2" else per_round
+    n = 48
+    sim = make_sim(error_models, correction_table, bitflip_table, model, locs, n, 2, cooling)
+    sim.backend.set_subset(eset, locs)
+    c = sim.backend.run(protocol, n, L.NOISE_SUBSET, seed=1234, first_shot_id=77)
+    recs, masks = sim.backend.records(n), sim.backend.masks(n)
+    orc = so.ShotOracle(error_models, correction_table, bitflip_table)
+    fails = not0 = 0
+    for i in range(n):
+        p_set = sim.backend.split_mask(masks[i, 0])
+        assert [sum(x) for x in p_set] == eset
+        ref = orc.run_shot(model, p_set, protocol, cooling=cooling, rnd=random.Random(0),
+                           meas=so.ForcedMeasure(recs[i]["outcomes"]))
+        for f in FIELDS:
+            assert recs[i].get(f) == ref.get(f), (i, f, recs[i].get(f), ref.get(f))
+        fails += ref["fail"]
+        not0 += ref["not0"]
+    assert (c.failed, c.not0, c.errors) == (fails, not0, 0)
+    sim.close()
+
+
+def test_true_probability_mode_replays_in_oracle(error_models, correction_table, bitflip_table):
+    """Bernoulli-per-slot noise (run-til-fail style probabilities, high p so that many slots fire)."""
+    model = "PDD_model"
+    locs = circuit.list_lengths(error_models[model])
+    n = 40
+    sim = make_sim(error_models, correction_table, bitflip_table, model, locs, n, 1)
+    sim.backend.set_slot_probs([[0.03] * x for x in locs])
+    c = sim.backend.run("single", n, L.NOISE_PROB, seed=42)
+    recs, masks = sim.backend.records(n), sim.backend.masks(n)
+    assert masks[:, 0].sum() > n          # plenty of events fired
+    orc = so.ShotOracle(error_models, correction_table, bitflip_table)
+    for i in range(n):
+        ref = orc.run_shot(model, sim.backend.split_mask(masks[i, 0]), "single", rnd=random.Random(0),
+                           meas=so.ForcedMeasure(recs[i]["outcomes"]))
+        for f in FIELDS:
+            assert recs[i].get(f) == ref.get(f), (i, f)
+    assert c.failed == sum(r["fail"] for r in recs)
+    sim.close()
+
+
+def test_single_fault_table(error_models, correction_table, bitflip_table, golden):
+    rows = golden("single_fault_pdd.json")["rows"]
+    locs = [24, 36, 48, 156, 48]
+    masks = []
+    for row in rows:
+        p_set = [[0] * x for x in locs]
+        p_set[row["type"]][row["slot"]] = 1
+        masks.append(flat(p_set))
+    sim = make_sim(error_models, correction_table, bitflip_table, "PDD_model", locs, len(rows), 2)
+    sim.backend.set_replay(masks, [r["outcomes"] for r in rows])
+    c = sim.backend.run("s2", len(rows), L.NOISE_REPLAY, forced=True)
+    recs = sim.backend.records(len(rows))
+    for rec, row in zip(recs, rows):
+        assert rec["flips_a"] == row["flips_a"]
+        assert rec.get("ft_syndrome") == row["ft"]
+    assert c.failed == 0 and c.not0 == 156 - 58 and c.errors == 0
+    sim.close()
+
+
+def test_full_size_properties(error_models, correction_table, bitflip_table):
+    """Size-independent properties at a large batch: no noise => no detection, no failure; the counters do
+    not depend on how the shot range is split into batches (Philox counter = global shot id); every
+    single-error subset is corrected (code distance 3)."""
+    locs = [12, 18, 24, 78, 24]
+    n = 2048
+    sim = make_sim(error_models, correction_table, bitflip_table, "PDD_model", locs, n, 2)
+    sim.backend.set_subset([0, 0, 0, 0, 0], locs)
+    c = sim.backend.run("s1", n, L.NOISE_SUBSET, seed=9)
+    assert (c.failed, c.not0, c.counted, c.errors) == (0, 0, n, 0)
+    assert c.sweeps == 2 * 4 * n
+    quiescent = {tuple(r["quiescent"]) for r in sim.backend.records(n)}
+    assert len(quiescent) == 16 and all(q[0] == q[2] == q[5] == q[7] == 0 for q in quiescent)
+
+    sim.backend.set_subset([0, 0, 2, 1, 0], locs)
+    whole = sim.backend.run("s1", n, L.NOISE_SUBSET, seed=11, first_shot_id=0)
+    whole = (whole.failed, whole.not0, whole.counted)
+    parts = [0, 0, 0]
+    for first in range(0, n, n // 4):
+        c = sim.backend.run("s1", n // 4, L.NOISE_SUBSET, seed=11, first_shot_id=first)
+        parts = [parts[0] + c.failed, parts[1] + c.not0, parts[2] + c.counted]
+    assert tuple(parts) == whole
+    for t in range(5):
+        eset = [0] * 5
+        eset[t] = 1
+        sim.backend.set_subset(eset, locs)
+        assert sim.backend.run("s1", n, L.NOISE_SUBSET, seed=t).failed == 0
+    sim.close()
+    locs2 = [2 * x for x in locs]
+    sim = make_sim(error_models, correction_table, bitflip_table, "PDD_model", locs2, n, 2)
+    for t in range(5):
+        eset = [0] * 5
+        eset[t] = 1
+        sim.backend.set_subset(eset, locs2)
+        assert sim.backend.run("s2", n, L.NOISE_SUBSET, seed=t).failed == 0
+    sim.close()
+
+
+def test_statistics_against_oracle_sampling(error_models, correction_table, bitflip_table):
+    """Sampled s2 failure / not0 rates agree with the oracle's own sampling within binomial 3 sigma."""
+    locs = [24, 36, 48, 156, 48]
+    eset = [0, 0, 2, 0, 0]
+    n = 4096
+    sim = make_sim(error_models, correction_table, bitflip_table, "PDD_model", locs, n, 2)
+    sim.backend.set_subset(eset, locs)
+    c = sim.backend.run("s2", n, L.NOISE_SUBSET, seed=5)
+    sim.close()
+    orc = so.ShotOracle(error_models, correction_table, bitflip_table)
+    m = 150
+    failed, not0 = so.run_subset(orc, "s2", m, "PDD_model", eset, locs, [[1]] * 5, rnd=random.Random(8),
+                                 meas_rng=random.Random(9))
+    p_gpu, p_cpu = c.not0 / n, not0 / m
+    p = (c.not0 + not0) / (n + m)
+    assert abs(p_gpu - p_cpu) < 3 * np.sqrt(p * (1 - p) * (1 / n + 1 / m)) + 1e-9
+    f_gpu, f_cpu = c.failed / max(1, c.not0), failed / max(1, not0)
+    f = (c.failed + failed) / max(1, c.not0 + not0)
+    assert abs(f_gpu - f_cpu) < 3 * np.sqrt(f * (1 - f) * (1 / max(1, c.not0) + 1 / max(1, not0))) + 1e-9
+
+
+def test_coherent_overrotation_against_oracle(error_models, correction_table, bitflip_table):
+    """BASELINE config 3 (extension): deterministic over-rotations + stochastic XX, full-state parity."""
+    eps1, eps2 = [0.02] * 30, [0.02] * 24
+    n = 4
+    sim = make_sim(error_models, correction_table, bitflip_table, "coherent_model", [30, 24, 24], n, 1,
+                   over_angles={"eps_1q": eps1, "eps_2q": eps2})
+    masks = []
+    rng = random.Random(4)
+    for _ in range(n):
+        xx = [0] * 24
+        xx[rng.randrange(24)] = 1
+        masks.append([0] * 54 + xx)
+    outcomes = [[0, rng.randint(0, 1), 0, rng.randint(0, 1), rng.randint(0, 1), 0, rng.randint(0, 1), 0] for _ in range(n)]
+    sim.backend.set_replay(masks, outcomes)
+    sim.backend.run("single", n, L.NOISE_REPLAY, forced=True, stop_stage=L.STOP_CYCLE1_GATES)
+    orc = so.ShotOracle(error_models, correction_table, bitflip_table)
+    gates = error_models["coherent_model"]["gates"]
+    for i in range(n):
+        st = sv.StateVector(17)
+        probs = {"eps_1q": eps1, "eps_2q": eps2, "p_XX_ctrl": masks[i][54:]}
+        noiseless = {"eps_1q": [0.0] * 30, "eps_2q": [0.0] * 24, "p_XX_ctrl": [0] * 24}
+        orc.stabilizer_cycle(st, 17 * [0], gates, noiseless, random.Random(0), so.ForcedMeasure(outcomes[i]))
+        orc.stabilizer_cycle(st, 17 * [0], gates, probs, random.Random(0), None, gates_only=True)
+        assert np.max(np.abs(sim.backend.state(i) - st.psi)) < AMP_TOL
+    sim.close()
+
+
+def test_run_til_fail_bookkeeping(error_models, correction_table, bitflip_table):
+    """Run-til-fail (CL:33-148): every run ends with a failure, rounds >= 1, totals consistent."""
+    locs = [12, 18, 24, 78, 24]
+    sim = make_sim(error_models, correction_table, bitflip_table, "PDD_model", locs, 64, 2)
+    p = 0.02
+    sim.backend.set_slot_probs([[p] * 12, [p] * 18, [p] * 24, [0.0] * 78, [0.0] * 24])
+    runs = 200
+    c = sim.backend.run("rtf", 64, L.NOISE_PROB, seed=3, rtf_runs=runs)
+    rounds, syndb = sim.backend.rtf_results(runs)
+    assert (rounds >= 1).all() and int(rounds.sum()) == c.rounds
+    assert c.failed == runs
+    assert (syndb <= rounds).all()
+    mean = rounds.mean()
+    assert 2.0 < mean < 60.0
+    sim.close()
