@@ -83,7 +83,8 @@ typedef struct {
 
 /* ---- error-injection program (restates insert_errors / insert_error, CS:127-234) ---------------- */
 
-enum { S17_P_OP_BEGIN = 1, S17_P_ERR = 2, S17_P_OP_END = 3, S17_P_IDLE = 4 };
+enum { S17_P_OP_BEGIN = 1, S17_P_ERR = 2, S17_P_OP_END = 3, S17_P_IDLE = 4,
+       S17_P_SKIP_TEST = 5 /* evaluate `leaked[a] or leaked[b]` right before the Rxx (CS:293, 322) */ };
 enum {
     S17_ERR_X = 1, S17_ERR_Y = 2, S17_ERR_Z = 3,   /* on qubits[0]            (CS:201-206) */
     S17_ERR_ZC = 4, S17_ERR_ZT = 5,                /* Z on qubits[0] / [1]    (CS:207-211) */
@@ -99,7 +100,7 @@ typedef struct {
     uint8_t list;      /* probability-list id (position in the model's "probabilities") */
     uint8_t field;     /* event-field bit offset inside the op word (0, 6, 12, 18) */
     uint16_t slot;     /* slot index inside ONE round of the list */
-    uint8_t a, b;      /* OP_BEGIN: leak predicate indices; ERR leak kinds: indices to set; IDLE: a = qubit */
+    uint8_t a, b;      /* SKIP_TEST: leak predicate indices; ERR leak kinds: indices to set; IDLE: a = qubit */
     uint8_t word;      /* event word index (op word, or 24 + timestep for IDLE) */
     uint8_t in_skip;   /* 1: entry sits inside the `if not leaked` block and is not drawn when skipped */
     uint8_t use_round; /* 1: slot is offset by half the list in the second cycle (CS:191-193); 0 for Idle */

@@ -15,7 +15,7 @@ MAX_OUTCOMES = 40
 
 U_RY, U_RXX, U_RX, U_H, U_ROT_X, U_ROT_Y, U_ROT_XX = 1, 2, 3, 4, 5, 6, 7
 OP_ENT, OP_IDLE = 0, 1
-P_OP_BEGIN, P_ERR, P_OP_END, P_IDLE = 1, 2, 3, 4
+P_OP_BEGIN, P_ERR, P_OP_END, P_IDLE, P_SKIP_TEST = 1, 2, 3, 4, 5
 (ERR_X, ERR_Y, ERR_Z, ERR_ZC, ERR_ZT, ERR_XX, ERR_ZZ, ERR_LEAK_A, ERR_LEAK_AB, ERR_DEPOL) = range(1, 11)
 PROTO_SINGLE, PROTO_S1, PROTO_S2, PROTO_RTF = 0, 1, 2, 3
 NOISE_PROB, NOISE_SUBSET, NOISE_REPLAY = 0, 1, 2

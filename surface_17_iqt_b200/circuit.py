@@ -206,8 +206,10 @@ def compile_program(model, list_len, fusion=1, cooling=False, over_angles=None) 
 
     for t in range(8):
         for op in (o for o in ops if o.timestep == t):
-            emit(kind=L.P_OP_BEGIN, a=op.d_leak, b=op.a_leak, word=op.index)
+            emit(kind=L.P_OP_BEGIN, word=op.index)
             for pos, gate, _, _, run_ind in gates_of(op):
+                if gate == "Rxx":     # the leak predicate is read here, after any Ry error of this op (CS:322)
+                    emit(kind=L.P_SKIP_TEST, a=op.d_leak, b=op.a_leak, word=op.index)
                 rx_i = op.rx_ind if gate == "Rx" else 0
                 ry_i = run_ind if gate == "Ry" else 0
                 seen_pauli = False

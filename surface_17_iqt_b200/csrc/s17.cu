@@ -291,9 +291,11 @@ __global__ void k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, NoiseDe
     uint32_t w = 0, skip = 0;
     for (int i = 0; i < pa.n_instr; ++i) {
         const s17_pinstr in = prog[i];
-        if (in.kind == S17_P_OP_BEGIN) {
+        if (in.kind == S17_P_OP_BEGIN) { w = 0; skip = 0; continue; }
+        if (in.kind == S17_P_SKIP_TEST) {
+            // evaluated AFTER the errors of a preceding Ry (which may just have leaked the data qubit)
             skip = ((lk >> in.a) | (lk >> in.b)) & 1u;
-            w = skip << 24;
+            w |= skip << 24;
             continue;
         }
         if (in.kind == S17_P_OP_END) { evs[in.word] = w; continue; }
