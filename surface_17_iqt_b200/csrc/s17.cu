@@ -17,11 +17,13 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "s17_kernels.cuh"
+#include "s17_layer2.cuh"
 
 namespace s17 {
 
@@ -30,14 +32,13 @@ enum { C_FAILED = 0, C_NOT0 = 1, C_COUNTED = 2, C_ERRORS = 3, C_SWEEPS = 4, C_RO
 // =================================================================================================
 // gate sweep
 // =================================================================================================
-__device__ __forceinline__ int insert0(int x, int pos) { return (x & ((1 << pos) - 1)) | ((x >> pos) << (pos + 1)); }
 
 __global__ void __launch_bounds__(kLayerThreads, 3)
 k_layer(double2 *__restrict__ state, const __grid_constant__ LayerArg A, const uint32_t *__restrict__ ev,
         const uint8_t *__restrict__ active, double *__restrict__ hist, unsigned long long *__restrict__ counters,
         int init_basis)
 {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     double2 *tile = reinterpret_cast<double2 *>(smem_raw);
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t s_ev[S17_EV_WORDS];
@@ -486,6 +487,34 @@ k_pauli(double2 *__restrict__ state, const s17_record *__restrict__ rec, const u
     }
 }
 
+// ordered list of the shots that still take part in gate sweeps (consumed by k_layer2)
+__global__ void __launch_bounds__(1024)
+k_compact(const uint8_t *__restrict__ active, int n, uint32_t *__restrict__ list, uint32_t *__restrict__ n_act)
+{
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t base_s;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t == 0) base_s = 0;
+    __syncthreads();
+    for (int start = 0; start < n; start += 1024) {
+        const int i = start + t;
+        const bool flag = i < n && active[i];
+        const uint32_t ballot = __ballot_sync(0xffffffffu, flag);
+        if (lane == 0) warp_sums[warp] = __popc(ballot);
+        __syncthreads();
+        uint32_t woff = 0, total = 0;
+        for (int w = 0; w < 32; ++w) {
+            if (w < warp) woff += warp_sums[w];
+            total += warp_sums[w];
+        }
+        if (flag) list[base_s + woff + __popc(ballot & ((1u << lane) - 1u))] = (uint32_t)i;
+        __syncthreads();
+        if (t == 0) base_s += total;
+        __syncthreads();
+    }
+    if (t == 0) *n_act = base_s;
+}
+
 struct ReadArgs {
     int forced;
     int folded;        // 1: the X part of the correction is folded into the read-out instead of the state
@@ -657,6 +686,10 @@ struct s17_ctx {
     uint64_t rtf_capacity = 0;
     int n_plan = 0;
     std::vector<LayerArg> layers[3];   // prep, first noisy cycle, second noisy cycle
+    std::vector<LayerArg2> layers2[3];
+    uint32_t *act_list = nullptr, *n_act = nullptr;
+    int num_sms = 148;
+    bool use_v1 = false;
     NoiseDev nd{};
     uint32_t total_slots = 0;
     bool have_program = false, have_tables = false, have_replay = false;
@@ -741,6 +774,16 @@ extern "C" int s17_create(s17_ctx **out, int device, uint64_t max_shots) {
     CK(cudaMemset(ctx->leak, 0, B * 4));
     CK(cudaMemset(ctx->ev, 0, B * S17_EV_WORDS * 4));
     CK(cudaFuncSetAttribute(k_layer, cudaFuncAttributeMaxDynamicSharedMemorySize, kTile * 16));
+    CK(cudaFuncSetAttribute(k_layer2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kL2Smem));
+    CK(cudaMalloc(&ctx->act_list, B * 4));
+    CK(cudaMalloc(&ctx->n_act, 4));
+    {
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, device));
+        ctx->num_sms = prop.multiProcessorCount;
+        const char *v1 = getenv("S17_LAYER_V1");
+        ctx->use_v1 = v1 && v1[0] == '1';
+    }
     CK(cudaEventCreate(&ctx->span0));
     CK(cudaEventCreate(&ctx->span1));
     *out = ctx;
@@ -753,7 +796,7 @@ extern "C" int s17_destroy(s17_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     void *ptrs[] = {ctx->state, ctx->ev, ctx->masks, ctx->leak, ctx->active, ctx->ready, ctx->forced, ctx->hist,
                     ctx->aux, ctx->rec, ctx->counters, ctx->lut, ctx->cw16, ctx->probs, ctx->cum, ctx->plan,
-                    ctx->rtf_slots, ctx->rtf_rounds, ctx->rtf_syndb};
+                    ctx->rtf_slots, ctx->rtf_rounds, ctx->rtf_syndb, ctx->act_list, ctx->n_act};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
@@ -777,6 +820,78 @@ static int check_layer(s17_ctx *ctx, const s17_layer &L) {
         if (!ok) return fail(ctx, S17_E_ARG, "op ancilla bit is not staged by its layer");
     }
     return S17_OK;
+}
+
+// host-side lowering of one sweep for k_layer2: per-op constants and the pass schedule
+static LayerArg2 make_layer2(const LayerArg &A) {
+    LayerArg2 P;
+    memset(&P, 0, sizeof(P));
+    P.A = A;
+    const s17_layer &L = A.L;
+    for (int o = 0; o < L.n_ops; ++o) {
+        const s17_op &op = L.ops[o];
+        OpC &c = P.oc[o];
+        c.ev_word = op.ev_word;
+        if (op.kind != S17_OP_ENT) continue;
+        c.lb0 = op.data_bit;
+        c.lb1 = 9;
+        for (int k = 0; k < 3; ++k)
+            if (L.anc_bits[k] == op.anc_bit) c.lb1 = (uint8_t)(9 + k);
+        // standard template: [Ry(+) ev0] Rxx(s, skippable, ev6) [Rx(-s) ev12] [Ry(-) ev18]
+        int u = 0;
+        bool ok = true;
+        uint8_t shape = 0;
+        int8_t s = 0;
+        if (u < op.n_uops && op.uops[u].type == S17_U_RY && op.uops[u].sign == 1 && !op.uops[u].skippable &&
+            op.uops[u].ev_shift == 0) { shape |= 1; ++u; }
+        if (u < op.n_uops && op.uops[u].type == S17_U_RXX && op.uops[u].skippable && op.uops[u].ev_shift == 6 &&
+            (op.uops[u].sign == 1 || op.uops[u].sign == -1)) { s = op.uops[u].sign; ++u; } else ok = false;
+        if (ok && u < op.n_uops && op.uops[u].type == S17_U_RX && op.uops[u].sign == -s && !op.uops[u].skippable &&
+            op.uops[u].ev_shift == 12) { shape |= 2; ++u; }
+        if (ok && u < op.n_uops && op.uops[u].type == S17_U_RY && op.uops[u].sign == -1 && !op.uops[u].skippable &&
+            op.uops[u].ev_shift == 18) { shape |= 4; ++u; }
+        if (u != op.n_uops) ok = false;
+        c.generic = ok ? 0 : 1;
+        c.shape = shape;
+        c.s = s;
+        for (int k = 0; k < op.n_uops; ++k)
+            if (op.uops[k].type <= S17_U_H) (op.uops[k].skippable ? c.n_skip : c.n_fixed)++;
+    }
+    // passes: consecutive operations on four distinct bits share one pass; an idle mask closes a run
+    int np = 0, last_gate_pass = -1;
+    std::vector<int> run;
+    auto flush = [&]() {
+        size_t i = 0;
+        while (i < run.size()) {
+            PassC &ps = P.pass[np];
+            ps.idle_word = 255;
+            const OpC &c1 = P.oc[run[i]];
+            if (i + 1 < run.size() && P.oc[run[i + 1]].lb0 != c1.lb0 && P.oc[run[i + 1]].lb1 != c1.lb1) {
+                ps.kind = 1; ps.o1 = (uint8_t)run[i]; ps.o2 = (uint8_t)run[i + 1];
+                i += 2;
+            } else {
+                ps.kind = 0; ps.o1 = (uint8_t)run[i];
+                i += 1;
+            }
+            last_gate_pass = np++;
+        }
+        run.clear();
+    };
+    for (int o = 0; o < L.n_ops; ++o) {
+        if (L.ops[o].kind == S17_OP_ENT) { run.push_back(o); continue; }
+        flush();
+        if (np == 0 || P.pass[np - 1].idle_word != 255) {      // nothing to attach to: idle-only pass
+            P.pass[np].kind = 2;
+            P.pass[np].idle_word = L.ops[o].ev_word;
+            ++np;
+        } else {
+            P.pass[np - 1].idle_word = L.ops[o].ev_word;
+        }
+    }
+    flush();
+    if (last_gate_pass >= 0) P.pass[last_gate_pass].last = 1;
+    P.n_pass = (uint32_t)np;
+    return P;
 }
 
 extern "C" int s17_load_program(s17_ctx *ctx, const s17_layer *layers, const uint32_t n_layers[3], const double *params,
@@ -812,6 +927,8 @@ extern "C" int s17_load_program(s17_ctx *ctx, const s17_layer *layers, const uin
             }
             ctx->layers[c].push_back(A);
         }
+        ctx->layers2[c].clear();
+        for (const LayerArg &A : ctx->layers[c]) ctx->layers2[c].push_back(make_layer2(A));
     }
     if (ctx->plan) { cudaFree(ctx->plan); ctx->plan = nullptr; }
     CK(cudaMalloc(&ctx->plan, n_plan * sizeof(s17_pinstr)));
@@ -927,13 +1044,23 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
         k_plan<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(ctx->plan, pa, ctx->nd, ctx->probs, ctx->ev, ctx->masks,
                                                             ctx->leak, ctx->active);
     }
-    const std::vector<LayerArg> &Ls = ctx->layers[stage == 0 ? 0 : (second ? 2 : 1)];
+    const int which = stage == 0 ? 0 : (second ? 2 : 1);
+    const std::vector<LayerArg> &Ls = ctx->layers[which];
+    const std::vector<LayerArg2> &Ls2 = ctx->layers2[which];
     uint32_t nl = (uint32_t)Ls.size();
     if (max_layers && max_layers < nl) nl = max_layers;
+    if (!ctx->use_v1) {
+        Scope s(ctx, CAT_OTHER);
+        k_compact<<<1, 1024, 0, ctx->stream>>>(ctx->active, n, ctx->act_list, ctx->n_act);
+    }
     for (uint32_t i = 0; i < nl; ++i) {
         Scope s(ctx, CAT_GATE);
-        k_layer<<<n * kTilesPerShot, kLayerThreads, kTile * 16, ctx->stream>>>(
-            ctx->state, Ls[i], ctx->ev, ctx->active, ctx->hist, ctx->counters, (i == 0) ? init_basis : -1);
+        if (ctx->use_v1)
+            k_layer<<<n * kTilesPerShot, kLayerThreads, kTile * 16, ctx->stream>>>(
+                ctx->state, Ls[i], ctx->ev, ctx->active, ctx->hist, ctx->counters, (i == 0) ? init_basis : -1);
+        else
+            k_layer2<<<ctx->num_sms, kL2Threads, kL2Smem, ctx->stream>>>(
+                ctx->state, Ls2[i], ctx->ev, ctx->act_list, ctx->n_act, ctx->hist, ctx->counters, (i == 0) ? init_basis : -1);
         ctx->n_gate++;
     }
     if (max_layers && max_layers < Ls.size()) return S17_OK;

@@ -35,6 +35,8 @@ struct ShotAux {
     uint32_t collapsed;       // 1: state already collapsed + reset to ancilla block 0
 };
 
+__device__ __forceinline__ int insert0(int x, int pos) { return (x & ((1 << pos) - 1)) | ((x >> pos) << (pos + 1)); }
+
 // ------------------------------------------------------------------------------------------------
 // Philox4x32-10, key = seed, counter = (global shot id, stream, block)
 // ------------------------------------------------------------------------------------------------

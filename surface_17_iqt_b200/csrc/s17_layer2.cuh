@@ -1,0 +1,322 @@
+// s17_layer2.cuh -- persistent, warp-specialised gate sweep (the production k_layer).
+//
+// One CTA per SM walks a contiguous range of (shot, tile) items.  Three 64 KiB shared-memory tile
+// buffers form a ring:
+//     loader warp  : TMA bulk loads of tile j+1, j+2 (8 runs x 8 KiB + the shot's 128 B of event words)
+//     8 math warps : tile j -- two entangling operations per pass on 16 register-resident amplitudes
+//     storer warp  : TMA bulk stores of tile j-1, then hands the buffer back to the loader
+// so HBM reads, FP64 math and HBM writes of different tiles overlap inside every SM.
+// Algorithmic traffic per (shot, sweep) is unchanged: 2 MiB read + 2 MiB write.
+#pragma once
+#include "s17_kernels.cuh"
+
+namespace s17 {
+
+constexpr int kMathThreads = 256;
+constexpr int kL2Threads = kMathThreads + 64;      // + loader warp + storer warp
+constexpr int kRing = 3;
+constexpr int kEvBytes = S17_EV_WORDS * 4;
+constexpr size_t kL2Smem = (size_t)kRing * kTile * 16 + kRing * kEvBytes + 3 * kRing * 8 + 64;
+
+struct OpC {                 // per-operation constants precomputed on the host
+    uint8_t lb0, lb1;        // tile-local bit of the data / ancilla qubit
+    uint8_t shape;           // bit0 Ry(+) before, bit1 Rx(-s) after, bit2 Ry(-) after   (standard ops)
+    uint8_t generic;         // 1: interpret the uop list (coherent rotations, H, ...)
+    int8_t s;                // sign of the Rxx angle
+    uint8_t ev_word;
+    uint8_t n_fixed, n_skip; // number of 1/sqrt2 gates always executed / executed unless skipped
+};
+
+struct PassC {
+    uint8_t kind;            // 0: one op on 4 items x 4 amplitudes, 1: two ops on 1 item x 16 amplitudes, 2: idle only
+    uint8_t o1, o2;
+    uint8_t idle_word;       // 255: none; else event word holding a 17-bit Z mask applied after the pass
+    uint8_t last;            // 1: last pass with gates -> applies the deferred scale
+    uint8_t pad[3];
+};
+
+struct LayerArg2 {
+    LayerArg A;
+    OpC oc[8];
+    PassC pass[8];
+    uint32_t n_pass;
+    uint32_t pad;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void math_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kMathThreads) : "memory"); }
+
+// quad accessors: op 1 of a pass owns register bits 0,1; op 2 owns bits 2,3
+template <bool OP2>
+struct Quad {
+    static __device__ __forceinline__ int r(int q, int k) { return OP2 ? (q + 4 * k) : (4 * q + k); }
+};
+
+#define S17_FOR_QUADS(body)                                                                                  \
+    _Pragma("unroll") for (int q = 0; q < 4; ++q) {                                                          \
+        double2 v[4] = {a[Quad<OP2>::r(q, 0)], a[Quad<OP2>::r(q, 1)], a[Quad<OP2>::r(q, 2)], a[Quad<OP2>::r(q, 3)]}; \
+        body;                                                                                                \
+        a[Quad<OP2>::r(q, 0)] = v[0]; a[Quad<OP2>::r(q, 1)] = v[1];                                          \
+        a[Quad<OP2>::r(q, 2)] = v[2]; a[Quad<OP2>::r(q, 3)] = v[3];                                          \
+    }
+
+// the fixed gate template of x_type_entangling / z_type_entangling (CS:291-344)
+template <bool OP2>
+__device__ __forceinline__ void apply_standard(double2 (&a)[16], const OpC c, uint32_t w) {
+    const double s = (double)c.s;
+    const bool skip = (w >> 24) & 1u;
+    const bool ev = (w & 0xFFFFFFu) != 0;
+    if (c.shape & 1) {
+        S17_FOR_QUADS(g_ry(v, 1.0));
+        if (ev && (w & 63u)) { const uint32_t f = w & 63u; S17_FOR_QUADS(g_pauli(v, f)); }
+    }
+    if (!skip) {
+        S17_FOR_QUADS(g_rxx(v, s));
+        if (ev && ((w >> 6) & 63u)) { const uint32_t f = (w >> 6) & 63u; S17_FOR_QUADS(g_pauli(v, f)); }
+    }
+    if (c.shape & 2) {
+        S17_FOR_QUADS(g_rx(v, -s));
+        if (ev && ((w >> 12) & 63u)) { const uint32_t f = (w >> 12) & 63u; S17_FOR_QUADS(g_pauli(v, f)); }
+    }
+    if (c.shape & 4) {
+        S17_FOR_QUADS(g_ry(v, -1.0));
+        if (ev && ((w >> 18) & 63u)) { const uint32_t f = (w >> 18) & 63u; S17_FOR_QUADS(g_pauli(v, f)); }
+    }
+}
+
+// interpreter for operations with non-standard micro-ops (coherent over-rotations, Hadamards)
+template <bool OP2>
+__device__ __forceinline__ void apply_generic(double2 (&a)[16], const s17_op &op, const double2 *prm, uint32_t w) {
+    const bool skip = (w >> 24) & 1u;
+    for (int u = 0; u < op.n_uops; ++u) {
+        const s17_uop up = op.uops[u];
+        if (up.skippable && skip) continue;
+        const double sg = (double)up.sign;
+        const double2 p = prm[up.param & 31];
+        switch (up.type) {
+        case S17_U_RY:     S17_FOR_QUADS(g_ry(v, sg)); break;
+        case S17_U_RXX:    S17_FOR_QUADS(g_rxx(v, sg)); break;
+        case S17_U_RX:     S17_FOR_QUADS(g_rx(v, sg)); break;
+        case S17_U_H:      S17_FOR_QUADS(g_h(v)); break;
+        case S17_U_ROT_X:  S17_FOR_QUADS(g_rot_x(v, p.x, p.y)); break;
+        case S17_U_ROT_Y:  S17_FOR_QUADS(g_rot_y(v, p.x, p.y)); break;
+        case S17_U_ROT_XX: S17_FOR_QUADS(g_rot_xx(v, p.x, p.y)); break;
+        default: break;
+        }
+        if (up.ev_shift != 255) {
+            const uint32_t f = (w >> up.ev_shift) & 63u;
+            if (f) { S17_FOR_QUADS(g_pauli(v, f)); }
+        }
+    }
+}
+
+template <bool OP2>
+__device__ __forceinline__ void apply_op(double2 (&a)[16], const LayerArg2 &P, int o, uint32_t w) {
+    if (P.oc[o].generic) apply_generic<OP2>(a, P.A.L.ops[o], P.A.prm, w);
+    else apply_standard<OP2>(a, P.oc[o], w);
+}
+
+__device__ __forceinline__ void tile_coords(const LayerArg &A, int tile_id, uint32_t &base, uint32_t (&run_off)[8]) {
+    base = 0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) base |= ((tile_id >> k) & 1u) << A.other_bits[k];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        uint32_t g = base;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) g |= ((r >> k) & 1u) << A.L.anc_bits[k];
+        run_off[r] = g;
+    }
+}
+
+__global__ void __launch_bounds__(kL2Threads, 1)
+k_layer2(double2 *__restrict__ state, const __grid_constant__ LayerArg2 P, const uint32_t *__restrict__ ev,
+         const uint32_t *__restrict__ act_list, const uint32_t *__restrict__ n_act_ptr, double *__restrict__ hist,
+         unsigned long long *__restrict__ counters, int init_basis)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    double2 *tiles = reinterpret_cast<double2 *>(smem_raw);
+    uint32_t *evbuf = reinterpret_cast<uint32_t *>(smem_raw + (size_t)kRing * kTile * 16);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kRing * kTile * 16 + kRing * kEvBytes);
+    uint64_t *done = full + kRing;
+    uint64_t *free_ = done + kRing;
+
+    const int t = threadIdx.x;
+    const uint32_t n_items = (*n_act_ptr) * kTilesPerShot;
+    const uint32_t chunk = (n_items + gridDim.x - 1) / gridDim.x;
+    const uint32_t first = blockIdx.x * chunk;
+    const uint32_t last = min(n_items, first + chunk);
+    if (first >= last) return;
+    const uint32_t n_local = last - first;
+
+    if (t == 0) {
+        for (int b = 0; b < kRing; ++b) {
+            mbar_init(&full[b], 1);
+            mbar_init(&done[b], kMathThreads / 32);
+            mbar_init(&free_[b], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int warp = t >> 5, lane = t & 31;
+
+    if (warp == kMathThreads / 32) {
+        // ------------------------------- loader ---------------------------------------------------
+        if (lane == 0) {
+            for (uint32_t j = 0; j < n_local; ++j) {
+                const int b = j % kRing;
+                if (j >= (uint32_t)kRing) mbar_wait(&free_[b], ((j / kRing) - 1) & 1);
+                const uint32_t item = first + j;
+                const uint32_t shot = act_list[item >> 5];
+                uint32_t base, run_off[8];
+                tile_coords(P.A, item & 31, base, run_off);
+                const double2 *sbase = state + (size_t)shot * kDim;
+                double2 *tile = tiles + (size_t)b * kTile;
+                if (init_basis < 0) {
+                    mbar_expect_tx(&full[b], kTile * 16 + kEvBytes);
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) tma_load_1d(tile + r * kRun, sbase + run_off[r], kRunBytes, &full[b]);
+                } else {
+                    mbar_expect_tx(&full[b], kEvBytes);
+                }
+                tma_load_1d(evbuf + b * S17_EV_WORDS, ev + (size_t)shot * S17_EV_WORDS, kEvBytes, &full[b]);
+            }
+        }
+        return;
+    }
+    if (warp == kMathThreads / 32 + 1) {
+        // ------------------------------- storer ---------------------------------------------------
+        if (lane == 0) {
+            for (uint32_t j = 0; j < n_local; ++j) {
+                const int b = j % kRing;
+                mbar_wait(&done[b], (j / kRing) & 1);
+                const uint32_t item = first + j;
+                const uint32_t shot = act_list[item >> 5];
+                uint32_t base, run_off[8];
+                tile_coords(P.A, item & 31, base, run_off);
+                double2 *sbase = state + (size_t)shot * kDim;
+                const double2 *tile = tiles + (size_t)b * kTile;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) tma_store_1d(sbase + run_off[r], tile + r * kRun, kRunBytes);
+                tma_store_commit_and_wait_read();
+                mbar_arrive(&free_[b]);
+                if ((item & 31) == 0) atomicAdd(&counters[4], 1ull);   // C_SWEEPS
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
+        return;
+    }
+
+    // ----------------------------------- math warps ----------------------------------------------
+    for (uint32_t j = 0; j < n_local; ++j) {
+        const int b = j % kRing;
+        double2 *tile = tiles + (size_t)b * kTile;
+        const uint32_t *evw = evbuf + b * S17_EV_WORDS;
+        const uint32_t item = first + j;
+        const int tile_id = item & 31;
+        mbar_wait(&full[b], (j / kRing) & 1);
+        uint32_t base = 0;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) base |= ((tile_id >> k) & 1u) << P.A.other_bits[k];
+
+        if (init_basis >= 0) {
+#pragma unroll
+            for (int i = 0; i < kTile / kMathThreads; ++i) tile[t + kMathThreads * i] = make_double2(0.0, 0.0);
+            math_barrier();
+            if (tile_id == 0 && t == 0) tile[init_basis] = make_double2(1.0, 0.0);
+            math_barrier();
+        }
+
+        // deferred 2^(-n/2): count the 1/sqrt2 gates this shot really executes in this layer
+        int nsc = 0;
+        for (int o = 0; o < P.A.L.n_ops; ++o) {
+            if (P.A.L.ops[o].kind != S17_OP_ENT) continue;
+            const uint32_t skip = (evw[P.oc[o].ev_word] >> 24) & 1u;
+            nsc += P.oc[o].n_fixed + (skip ? 0 : P.oc[o].n_skip);
+        }
+        const double scale = ldexp((nsc & 1) ? 0.70710678118654752440 : 1.0, -(nsc >> 1));
+
+        for (uint32_t p = 0; p < P.n_pass; ++p) {
+            const PassC ps = P.pass[p];
+            double2 a[16];
+            int idx[4];
+            int off[16];
+            if (ps.kind == 1) {
+                const OpC c1 = P.oc[ps.o1], c2 = P.oc[ps.o2];
+                // insert zero bits at the four (distinct) local positions, lowest first
+                int d_lo = min(c1.lb0, c2.lb0), d_hi = max(c1.lb0, c2.lb0);
+                int a_lo = min(c1.lb1, c2.lb1), a_hi = max(c1.lb1, c2.lb1);
+                const int i0 = insert0(insert0(insert0(insert0(t, d_lo), d_hi), a_lo), a_hi);
+                idx[0] = idx[1] = idx[2] = idx[3] = i0;
+                const int m[4] = {1 << c1.lb0, 1 << c1.lb1, 1 << c2.lb0, 1 << c2.lb1};
+#pragma unroll
+                for (int r = 0; r < 16; ++r)
+                    off[r] = i0 | ((r & 1) ? m[0] : 0) | ((r & 2) ? m[1] : 0) | ((r & 4) ? m[2] : 0) | ((r & 8) ? m[3] : 0);
+            } else {
+                const OpC c1 = P.oc[ps.o1];
+                const int lb0 = ps.kind == 0 ? c1.lb0 : 0, lb1 = ps.kind == 0 ? c1.lb1 : 9;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    idx[i] = insert0(insert0(t + kMathThreads * i, lb0), lb1);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) off[4 * i + k] = idx[i] | ((k & 1) ? (1 << lb0) : 0) | ((k & 2) ? (1 << lb1) : 0);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 16; ++r) a[r] = tile[off[r]];
+
+            if (ps.kind == 1) {
+                apply_op<false>(a, P, ps.o1, evw[P.oc[ps.o1].ev_word]);
+                apply_op<true>(a, P, ps.o2, evw[P.oc[ps.o2].ev_word]);
+            } else if (ps.kind == 0) {
+                apply_op<false>(a, P, ps.o1, evw[P.oc[ps.o1].ev_word]);
+            }
+            if (ps.idle_word != 255) {
+                // Z on every qubit whose bit is set in the 17-bit idle mask (sympathetic_cooling, CS:762-772)
+                const uint32_t zm = evw[ps.idle_word];
+                if (zm) {
+                    uint32_t lm = zm & 0x1FFu;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) lm |= ((zm >> P.A.L.anc_bits[k]) & 1u) << (9 + k);
+                    const uint32_t c0 = __popc(base & zm) & 1u;
+#pragma unroll
+                    for (int r = 0; r < 16; ++r)
+                        if ((__popc(off[r] & lm) & 1u) ^ c0) a[r] = make_double2(-a[r].x, -a[r].y);
+                }
+            }
+            if (ps.last && nsc) {
+#pragma unroll
+                for (int r = 0; r < 16; ++r) { a[r].x *= scale; a[r].y *= scale; }
+            }
+#pragma unroll
+            for (int r = 0; r < 16; ++r) tile[off[r]] = a[r];
+            math_barrier();
+        }
+
+        if (P.A.L.emit_hist) {
+            double acc = 0.0;
+#pragma unroll
+            for (int i = 0; i < kRun / 32; ++i) {
+                const double2 v = tile[warp * kRun + lane + 32 * i];
+                acc = fma(v.x, v.x, fma(v.y, v.y, acc));
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+            if (lane == 0) {
+                uint32_t g = base;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) g |= ((warp >> k) & 1u) << P.A.L.anc_bits[k];
+                const uint32_t shot = act_list[item >> 5];
+                hist[(size_t)shot * 256 + (g >> 9)] = acc;
+            }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&done[b]);
+    }
+}
+
+}  // namespace s17
