@@ -46,6 +46,17 @@ struct LayerArg2 {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// mbarrier wait for the single-lane producer warps: back off so the spin does not steal issue slots
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t phase) {
+    uint32_t ok = 0;
+    for (;;) {
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\nselp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+        if (ok) break;
+        __nanosleep(200);
+    }
+}
 __device__ __forceinline__ void math_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kMathThreads) : "memory"); }
 
 // quad accessors: op 1 of a pass owns register bits 0,1; op 2 owns bits 2,3
@@ -112,6 +123,24 @@ __device__ __forceinline__ void apply_generic(double2 (&a)[16], const s17_op &op
     }
 }
 
+// Branch-free form of the same template for shots without Pauli events: an absent (or leak-skipped)
+// gate is executed with coefficient 0, which is the exact identity in the unscaled add/sub form.
+template <bool OP2>
+__device__ __forceinline__ void apply_fast(double2 (&a)[16], double v1, double s, double sx, double v2) {
+    S17_FOR_QUADS(g_ry(v, v1); g_rxx(v, s); g_rx(v, sx); g_ry(v, v2));
+}
+
+struct FastC { double v1, s, sx, v2; };
+__device__ __forceinline__ FastC fast_coeffs(const OpC c, uint32_t w) {
+    FastC f;
+    const double s = (double)c.s;
+    f.v1 = (c.shape & 1) ? 1.0 : 0.0;
+    f.s = ((w >> 24) & 1u) ? 0.0 : s;
+    f.sx = (c.shape & 2) ? -s : 0.0;
+    f.v2 = (c.shape & 4) ? -1.0 : 0.0;
+    return f;
+}
+
 template <bool OP2>
 __device__ __forceinline__ void apply_op(double2 (&a)[16], const LayerArg2 &P, int o, uint32_t w) {
     if (P.oc[o].generic) apply_generic<OP2>(a, P.A.L.ops[o], P.A.prm, w);
@@ -168,7 +197,7 @@ k_layer2(double2 *__restrict__ state, const __grid_constant__ LayerArg2 P, const
         if (lane == 0) {
             for (uint32_t j = 0; j < n_local; ++j) {
                 const int b = j % kRing;
-                if (j >= (uint32_t)kRing) mbar_wait(&free_[b], ((j / kRing) - 1) & 1);
+                if (j >= (uint32_t)kRing) mbar_wait_sleep(&free_[b], ((j / kRing) - 1) & 1);
                 const uint32_t item = first + j;
                 const uint32_t shot = act_list[item >> 5];
                 uint32_t base, run_off[8];
@@ -192,7 +221,7 @@ k_layer2(double2 *__restrict__ state, const __grid_constant__ LayerArg2 P, const
         if (lane == 0) {
             for (uint32_t j = 0; j < n_local; ++j) {
                 const int b = j % kRing;
-                mbar_wait(&done[b], (j / kRing) & 1);
+                mbar_wait_sleep(&done[b], (j / kRing) & 1);
                 const uint32_t item = first + j;
                 const uint32_t shot = act_list[item >> 5];
                 uint32_t base, run_off[8];
@@ -268,31 +297,52 @@ k_layer2(double2 *__restrict__ state, const __grid_constant__ LayerArg2 P, const
 #pragma unroll
             for (int r = 0; r < 16; ++r) a[r] = tile[off[r]];
 
-            if (ps.kind == 1) {
-                apply_op<false>(a, P, ps.o1, evw[P.oc[ps.o1].ev_word]);
-                apply_op<true>(a, P, ps.o2, evw[P.oc[ps.o2].ev_word]);
-            } else if (ps.kind == 0) {
-                apply_op<false>(a, P, ps.o1, evw[P.oc[ps.o1].ev_word]);
-            }
+            uint32_t zm = 0, lm = 0, c0 = 0;
             if (ps.idle_word != 255) {
                 // Z on every qubit whose bit is set in the 17-bit idle mask (sympathetic_cooling, CS:762-772)
-                const uint32_t zm = evw[ps.idle_word];
-                if (zm) {
-                    uint32_t lm = zm & 0x1FFu;
+                zm = evw[ps.idle_word];
+                lm = zm & 0x1FFu;
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) lm |= ((zm >> P.A.L.anc_bits[k]) & 1u) << (9 + k);
-                    const uint32_t c0 = __popc(base & zm) & 1u;
+                for (int k = 0; k < 3; ++k) lm |= ((zm >> P.A.L.anc_bits[k]) & 1u) << (9 + k);
+                c0 = __popc(base & zm) & 1u;
+            }
+            const double sc = ps.last ? scale : 1.0;
+            auto finish = [&](double2 (&x)[16]) {
+                if (zm) {
 #pragma unroll
                     for (int r = 0; r < 16; ++r)
-                        if ((__popc(off[r] & lm) & 1u) ^ c0) a[r] = make_double2(-a[r].x, -a[r].y);
+                        if ((__popc(off[r] & lm) & 1u) ^ c0) x[r] = make_double2(-x[r].x, -x[r].y);
                 }
-            }
-            if (ps.last && nsc) {
 #pragma unroll
-                for (int r = 0; r < 16; ++r) { a[r].x *= scale; a[r].y *= scale; }
+                for (int r = 0; r < 16; ++r) tile[off[r]] = make_double2(x[r].x * sc, x[r].y * sc);
+            };
+            const uint32_t w1 = evw[P.oc[ps.o1].ev_word];
+            const uint32_t w2 = ps.kind == 1 ? evw[P.oc[ps.o2].ev_word] : 0u;
+            const bool fast = !(P.oc[ps.o1].generic | (ps.kind == 1 ? P.oc[ps.o2].generic : 0)) &&
+                              !((w1 | w2) & 0xFFFFFFu);
+            if (ps.kind == 1) {
+                if (fast) {
+                    const FastC f1 = fast_coeffs(P.oc[ps.o1], w1), f2 = fast_coeffs(P.oc[ps.o2], w2);
+                    apply_fast<false>(a, f1.v1, f1.s, f1.sx, f1.v2);
+                    apply_fast<true>(a, f2.v1, f2.s, f2.sx, f2.v2);
+                    finish(a);
+                } else {
+                    apply_op<false>(a, P, ps.o1, w1);
+                    apply_op<true>(a, P, ps.o2, w2);
+                    finish(a);
+                }
+            } else if (ps.kind == 0) {
+                if (fast) {
+                    const FastC f1 = fast_coeffs(P.oc[ps.o1], w1);
+                    apply_fast<false>(a, f1.v1, f1.s, f1.sx, f1.v2);
+                    finish(a);
+                } else {
+                    apply_op<false>(a, P, ps.o1, w1);
+                    finish(a);
+                }
+            } else {
+                finish(a);
             }
-#pragma unroll
-            for (int r = 0; r < 16; ++r) tile[off[r]] = a[r];
             math_barrier();
         }
 
