@@ -3,7 +3,8 @@
 // One CTA per SM walks a contiguous range of (shot, tile) items.  Three 64 KiB shared-memory tile
 // buffers form a ring:
 //     loader warp  : TMA bulk loads of tile j+1, j+2 (8 runs x 8 KiB + the shot's 128 B of event words)
-//     8 math warps : tile j -- two entangling operations per pass on 16 register-resident amplitudes
+//     2 x 4 math warps : tiles j, j+1 -- two entangling operations per pass on 16 register-resident
+//                    amplitudes; the two groups run out of phase (one in its LDS/STS phase, one in FP64)
 //     storer warp  : TMA bulk stores of tile j-1, then hands the buffer back to the loader
 // so HBM reads, FP64 math and HBM writes of different tiles overlap inside every SM.
 // Algorithmic traffic per (shot, sweep) is unchanged: 2 MiB read + 2 MiB write.
@@ -13,6 +14,8 @@
 namespace s17 {
 
 constexpr int kMathThreads = 256;
+constexpr int kGroups = 2;                          // independent math groups, each on its own tile
+constexpr int kGroupThreads = kMathThreads / kGroups;
 constexpr int kL2Threads = kMathThreads + 64;      // + loader warp + storer warp
 constexpr int kRing = 3;
 constexpr int kEvBytes = S17_EV_WORDS * 4;
@@ -57,7 +60,9 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t phase) {
         __nanosleep(200);
     }
 }
-__device__ __forceinline__ void math_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kMathThreads) : "memory"); }
+__device__ __forceinline__ void group_barrier(int grp) {
+    asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kGroupThreads) : "memory");
+}
 
 // quad accessors: op 1 of a pass owns register bits 0,1; op 2 owns bits 2,3
 template <bool OP2>
@@ -183,7 +188,7 @@ k_layer2(double2 *__restrict__ state, const __grid_constant__ LayerArg2 P, const
     if (t == 0) {
         for (int b = 0; b < kRing; ++b) {
             mbar_init(&full[b], 1);
-            mbar_init(&done[b], kMathThreads / 32);
+            mbar_init(&done[b], kGroupThreads / 32);
             mbar_init(&free_[b], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -240,7 +245,12 @@ k_layer2(double2 *__restrict__ state, const __grid_constant__ LayerArg2 P, const
     }
 
     // ----------------------------------- math warps ----------------------------------------------
-    for (uint32_t j = 0; j < n_local; ++j) {
+    // two independent groups of 4 warps: group g owns tiles j = g, g+2, ... so that one group's
+    // shared-memory phase overlaps the other group's FP64 phase
+    const int grp = warp / (kGroupThreads / 32);
+    const int tg = t - grp * kGroupThreads;                  // thread index inside the group
+    const int gw = warp - grp * (kGroupThreads / 32);        // warp index inside the group
+    for (uint32_t j = grp; j < n_local; j += kGroups) {
         const int b = j % kRing;
         double2 *tile = tiles + (size_t)b * kTile;
         const uint32_t *evw = evbuf + b * S17_EV_WORDS;
@@ -252,11 +262,11 @@ k_layer2(double2 *__restrict__ state, const __grid_constant__ LayerArg2 P, const
         for (int k = 0; k < 5; ++k) base |= ((tile_id >> k) & 1u) << P.A.other_bits[k];
 
         if (init_basis >= 0) {
-#pragma unroll
-            for (int i = 0; i < kTile / kMathThreads; ++i) tile[t + kMathThreads * i] = make_double2(0.0, 0.0);
-            math_barrier();
-            if (tile_id == 0 && t == 0) tile[init_basis] = make_double2(1.0, 0.0);
-            math_barrier();
+#pragma unroll 4
+            for (int i = 0; i < kTile / kGroupThreads; ++i) tile[tg + kGroupThreads * i] = make_double2(0.0, 0.0);
+            group_barrier(grp);
+            if (tile_id == 0 && tg == 0) tile[init_basis] = make_double2(1.0, 0.0);
+            group_barrier(grp);
         }
 
         // deferred 2^(-n/2): count the 1/sqrt2 gates this shot really executes in this layer
@@ -270,33 +280,6 @@ k_layer2(double2 *__restrict__ state, const __grid_constant__ LayerArg2 P, const
 
         for (uint32_t p = 0; p < P.n_pass; ++p) {
             const PassC ps = P.pass[p];
-            double2 a[16];
-            int idx[4];
-            int off[16];
-            if (ps.kind == 1) {
-                const OpC c1 = P.oc[ps.o1], c2 = P.oc[ps.o2];
-                // insert zero bits at the four (distinct) local positions, lowest first
-                int d_lo = min(c1.lb0, c2.lb0), d_hi = max(c1.lb0, c2.lb0);
-                int a_lo = min(c1.lb1, c2.lb1), a_hi = max(c1.lb1, c2.lb1);
-                const int i0 = insert0(insert0(insert0(insert0(t, d_lo), d_hi), a_lo), a_hi);
-                idx[0] = idx[1] = idx[2] = idx[3] = i0;
-                const int m[4] = {1 << c1.lb0, 1 << c1.lb1, 1 << c2.lb0, 1 << c2.lb1};
-#pragma unroll
-                for (int r = 0; r < 16; ++r)
-                    off[r] = i0 | ((r & 1) ? m[0] : 0) | ((r & 2) ? m[1] : 0) | ((r & 4) ? m[2] : 0) | ((r & 8) ? m[3] : 0);
-            } else {
-                const OpC c1 = P.oc[ps.o1];
-                const int lb0 = ps.kind == 0 ? c1.lb0 : 0, lb1 = ps.kind == 0 ? c1.lb1 : 9;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    idx[i] = insert0(insert0(t + kMathThreads * i, lb0), lb1);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) off[4 * i + k] = idx[i] | ((k & 1) ? (1 << lb0) : 0) | ((k & 2) ? (1 << lb1) : 0);
-                }
-            }
-#pragma unroll
-            for (int r = 0; r < 16; ++r) a[r] = tile[off[r]];
-
             uint32_t zm = 0, lm = 0, c0 = 0;
             if (ps.idle_word != 255) {
                 // Z on every qubit whose bit is set in the 17-bit idle mask (sympathetic_cooling, CS:762-772)
@@ -307,60 +290,98 @@ k_layer2(double2 *__restrict__ state, const __grid_constant__ LayerArg2 P, const
                 c0 = __popc(base & zm) & 1u;
             }
             const double sc = ps.last ? scale : 1.0;
-            auto finish = [&](double2 (&x)[16]) {
-                if (zm) {
+            const OpC c1 = P.oc[ps.o1], c2 = P.oc[ps.kind == 1 ? ps.o2 : ps.o1];
+            const uint32_t w1 = evw[c1.ev_word];
+            const uint32_t w2 = ps.kind == 1 ? evw[c2.ev_word] : 0u;
+            const bool fast = !(c1.generic | (ps.kind == 1 ? c2.generic : 0)) && !((w1 | w2) & 0xFFFFFFu);
+            const FastC f1 = fast_coeffs(c1, w1), f2 = fast_coeffs(c2, w2);
+            // register r of a thread holds the amplitude at tile offset i0 + (warp-uniform combination of m0..m3)
+            int p0, p1, p2, p3;                                  // zero-bit insert positions, ascending
+            int m0, m1, m2, m3;
+            if (ps.kind == 1) {
+                p0 = min(c1.lb0, c2.lb0); p1 = max(c1.lb0, c2.lb0);
+                p2 = min(c1.lb1, c2.lb1); p3 = max(c1.lb1, c2.lb1);
+                m0 = 1 << c1.lb0; m1 = 1 << c1.lb1; m2 = 1 << c2.lb0; m3 = 1 << c2.lb1;
+            } else {
+                const int lb0 = ps.kind == 0 ? c1.lb0 : 0, lb1 = ps.kind == 0 ? c1.lb1 : 9;
+                p0 = lb0; p1 = lb1; p2 = p3 = 0;
+                m0 = 1 << lb0; m1 = 1 << lb1; m2 = m3 = 0;
+            }
+
+#pragma unroll 1
+            for (int it = 0; it < kTile / 16 / kGroupThreads; ++it) {
+                double2 a[16];
+                int off[16];
+                if (ps.kind == 1) {
+                    const int i0 = insert0(insert0(insert0(insert0(tg + kGroupThreads * it, p0), p1), p2), p3);
 #pragma unroll
                     for (int r = 0; r < 16; ++r)
-                        if ((__popc(off[r] & lm) & 1u) ^ c0) x[r] = make_double2(-x[r].x, -x[r].y);
+                        off[r] = i0 + ((r & 1) ? m0 : 0) + ((r & 2) ? m1 : 0) + ((r & 4) ? m2 : 0) + ((r & 8) ? m3 : 0);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int i0 = insert0(insert0(tg + kGroupThreads * (4 * it + i), p0), p1);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) off[4 * i + k] = i0 + ((k & 1) ? m0 : 0) + ((k & 2) ? m1 : 0);
+                    }
                 }
 #pragma unroll
-                for (int r = 0; r < 16; ++r) tile[off[r]] = make_double2(x[r].x * sc, x[r].y * sc);
-            };
-            const uint32_t w1 = evw[P.oc[ps.o1].ev_word];
-            const uint32_t w2 = ps.kind == 1 ? evw[P.oc[ps.o2].ev_word] : 0u;
-            const bool fast = !(P.oc[ps.o1].generic | (ps.kind == 1 ? P.oc[ps.o2].generic : 0)) &&
-                              !((w1 | w2) & 0xFFFFFFu);
-            if (ps.kind == 1) {
-                if (fast) {
-                    const FastC f1 = fast_coeffs(P.oc[ps.o1], w1), f2 = fast_coeffs(P.oc[ps.o2], w2);
-                    apply_fast<false>(a, f1.v1, f1.s, f1.sx, f1.v2);
-                    apply_fast<true>(a, f2.v1, f2.s, f2.sx, f2.v2);
-                    finish(a);
+                for (int r = 0; r < 16; ++r) a[r] = tile[off[r]];
+
+                auto finish = [&](double2 (&x)[16]) {
+                    if (zm) {
+#pragma unroll
+                        for (int r = 0; r < 16; ++r)
+                            if ((__popc(off[r] & lm) & 1u) ^ c0) x[r] = make_double2(-x[r].x, -x[r].y);
+                    }
+#pragma unroll
+                    for (int r = 0; r < 16; ++r) tile[off[r]] = make_double2(x[r].x * sc, x[r].y * sc);
+                };
+                if (ps.kind == 1) {
+                    if (fast) {
+                        apply_fast<false>(a, f1.v1, f1.s, f1.sx, f1.v2);
+                        apply_fast<true>(a, f2.v1, f2.s, f2.sx, f2.v2);
+                        finish(a);
+                    } else {
+                        apply_op<false>(a, P, ps.o1, w1);
+                        apply_op<true>(a, P, ps.o2, w2);
+                        finish(a);
+                    }
+                } else if (ps.kind == 0) {
+                    if (fast) {
+                        apply_fast<false>(a, f1.v1, f1.s, f1.sx, f1.v2);
+                        finish(a);
+                    } else {
+                        apply_op<false>(a, P, ps.o1, w1);
+                        finish(a);
+                    }
                 } else {
-                    apply_op<false>(a, P, ps.o1, w1);
-                    apply_op<true>(a, P, ps.o2, w2);
                     finish(a);
                 }
-            } else if (ps.kind == 0) {
-                if (fast) {
-                    const FastC f1 = fast_coeffs(P.oc[ps.o1], w1);
-                    apply_fast<false>(a, f1.v1, f1.s, f1.sx, f1.v2);
-                    finish(a);
-                } else {
-                    apply_op<false>(a, P, ps.o1, w1);
-                    finish(a);
-                }
-            } else {
-                finish(a);
             }
-            math_barrier();
+            group_barrier(grp);
         }
 
         if (P.A.L.emit_hist) {
-            double acc = 0.0;
+            // joint ancilla histogram: every warp of the group owns two runs (ancilla values) of the tile
 #pragma unroll
-            for (int i = 0; i < kRun / 32; ++i) {
-                const double2 v = tile[warp * kRun + lane + 32 * i];
-                acc = fma(v.x, v.x, fma(v.y, v.y, acc));
-            }
+            for (int rr = 0; rr < 8 / (kGroupThreads / 32); ++rr) {
+                const int run = gw + (kGroupThreads / 32) * rr;
+                double acc = 0.0;
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-            if (lane == 0) {
-                uint32_t g = base;
+                for (int i = 0; i < kRun / 32; ++i) {
+                    const double2 v = tile[run * kRun + lane + 32 * i];
+                    acc = fma(v.x, v.x, fma(v.y, v.y, acc));
+                }
 #pragma unroll
-                for (int k = 0; k < 3; ++k) g |= ((warp >> k) & 1u) << P.A.L.anc_bits[k];
-                const uint32_t shot = act_list[item >> 5];
-                hist[(size_t)shot * 256 + (g >> 9)] = acc;
+                for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+                if (lane == 0) {
+                    uint32_t g = base;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) g |= ((run >> k) & 1u) << P.A.L.anc_bits[k];
+                    const uint32_t shot = act_list[item >> 5];
+                    hist[(size_t)shot * 256 + (g >> 9)] = acc;
+                }
             }
         }
         fence_proxy_async_smem();
