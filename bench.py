@@ -14,8 +14,9 @@ only exchange is one all-reduce of the counters at the end (inside the timed reg
 `e2e`    : the same through the reference-shaped Python entry point
            surface_17_iqt_b200.calc_log_e_rate_arbitrary_error_model.s2_calculate_log_e_rate_error_subset
            with host inputs and host results, wall-clock around the calls.
-`roofline`: the gate sweep kernel k_layer: algorithmic bytes (2 MiB read + 2 MiB write per shot per sweep;
-           the first sweep of a shot synthesises |0..0> and only writes) / summed CUDA-event kernel time.
+`roofline`: the gate sweep kernel k_layer2: algorithmic bytes = the 8 KiB amplitude runs it really reads and
+           writes (a dense sweep is 2 MiB read + 2 MiB write per shot; regions of the state that are exactly zero
+           after an ancilla reset are skipped unless S17_DENSE=1) / summed CUDA-event kernel time.
 `cpu_baseline` / --impl reference: the oracle port (one CPU sweep per gate, ProjectQ's execution model,
            python per-gate driver like the reference) on all host cores, bounded sample of the same workload.
 """
@@ -186,12 +187,13 @@ def run_gpu(args):
     barrier()
     t0 = time.perf_counter()
     span_ms = gate_ms = 0.0
-    sweeps = launches = gate_launches = failed = not0 = 0
+    sweeps = launches = gate_launches = failed = not0 = sweep_bytes = 0
     for k in range(args.steps):
         c, t = step(args.warmup + k)
         span_ms += t["span_ms"]
         gate_ms += t["gate_ms"]
         sweeps += c.sweeps
+        sweep_bytes += c.sweep_bytes
         launches += t["launches"]
         gate_launches += t["gate_launches"]
         failed += c.failed
@@ -211,7 +213,7 @@ def run_gpu(args):
     value = total_shots / (span_ms_max * 1e-3)
 
     # roofline of the gate sweep on this rank
-    algo_bytes = sweeps * SWEEP_BYTES - (B * args.steps) * (SWEEP_BYTES // 2)
+    algo_bytes = sweep_bytes     # 8 KiB runs really read + written by the gate sweeps (known-zero regions are skipped)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
@@ -256,6 +258,7 @@ def run_gpu(args):
                          "frac": achieved / peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                          "traffic": None, "launches": int(gate_launches), "sweeps": int(sweeps),
                          "sweeps_per_shot": sweeps / (B * args.steps),
+                         "bytes_per_shot": sweep_bytes / (B * args.steps), "dense_bytes_per_sweep": SWEEP_BYTES,
                          "gate_kernel_share_of_step": gate_ms / span_ms if span_ms else None},
             "counts": {"failed": int(tot[0]), "not0": int(tot[1]), "shots": total_shots},
         }

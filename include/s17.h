@@ -141,9 +141,9 @@ typedef struct {
     uint64_t not0;         /* flipsa_not0_count   (CL:333, 417) */
     uint64_t counted;      /* shots that reached decode + read-out */
     uint64_t errors;       /* shots with a forced outcome of zero probability */
-    uint64_t sweeps;       /* (shot, sweep) pairs executed by the gate kernel, for roofline accounting */
+    uint64_t sweeps;       /* (shot, sweep) pairs executed by the gate kernel */
     uint64_t rounds;       /* S17_PROTO_RTF: total rounds simulated */
-    uint64_t spare;
+    uint64_t sweep_bytes;  /* algorithmic HBM bytes the gate sweeps moved (8 KiB runs read + written) */
 } s17_counts;
 
 typedef struct {

@@ -58,7 +58,7 @@ class RunArgs(C.Structure):
 
 class Counts(C.Structure):
     _fields_ = [("shots", C.c_uint64), ("failed", C.c_uint64), ("not0", C.c_uint64), ("counted", C.c_uint64),
-                ("errors", C.c_uint64), ("sweeps", C.c_uint64), ("rounds", C.c_uint64), ("spare", C.c_uint64)]
+                ("errors", C.c_uint64), ("sweeps", C.c_uint64), ("rounds", C.c_uint64), ("sweep_bytes", C.c_uint64)]
 
 
 class Record(C.Structure):

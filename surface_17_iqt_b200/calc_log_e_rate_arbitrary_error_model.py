@@ -112,7 +112,7 @@ def _run_subset(protocol, num_runs, correction_table, model, eset, locations, bi
     first, count = distributed.shard_range(num_runs, rank, world_size)
     failed = not0 = counted = 0
     gate_ms = span_ms = 0.0
-    sweeps = launches = 0
+    sweeps = launches = sweep_bytes = 0
     done = 0
     while done < count:
         n = min(BATCH_SHOTS, count - done)
@@ -123,9 +123,11 @@ def _run_subset(protocol, num_runs, correction_table, model, eset, locations, bi
         failed, not0, counted = failed + c.failed, not0 + c.not0, counted + c.counted
         gate_ms, span_ms = gate_ms + t["gate_ms"], span_ms + t["span_ms"]
         sweeps, launches = sweeps + c.sweeps, launches + t["launches"]
+        sweep_bytes += c.sweep_bytes
         done += n
     failed, not0, counted = distributed.allreduce_counts([failed, not0, counted])
-    LAST_TIMING.update(gate_ms=gate_ms, span_ms=span_ms, sweeps=sweeps, launches=launches, shots=count)
+    LAST_TIMING.update(gate_ms=gate_ms, span_ms=span_ms, sweeps=sweeps, sweep_bytes=sweep_bytes, launches=launches,
+                       shots=count)
     return failed, not0, counted
 
 

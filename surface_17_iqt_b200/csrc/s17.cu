@@ -27,7 +27,8 @@
 
 namespace s17 {
 
-enum { C_FAILED = 0, C_NOT0 = 1, C_COUNTED = 2, C_ERRORS = 3, C_SWEEPS = 4, C_ROUNDS = 5, C_NEXT_RUN = 6, C_ALIVE = 7, C_N = 8 };
+enum { C_FAILED = 0, C_NOT0 = 1, C_COUNTED = 2, C_ERRORS = 3, C_SWEEPS = 4, C_ROUNDS = 5, C_NEXT_RUN = 6, C_ALIVE = 7,
+       C_RUNS_MOVED = 8, C_N = 10 };
 
 // =================================================================================================
 // gate sweep
@@ -686,7 +687,9 @@ struct s17_ctx {
     uint64_t rtf_capacity = 0;
     int n_plan = 0;
     std::vector<LayerArg> layers[3];   // prep, first noisy cycle, second noisy cycle
-    std::vector<LayerArg2> layers2[3];
+    std::vector<LayerArg2> layers2[3], layers2d[3];   // support-aware / dense variants
+    double2 *zero_page = nullptr;
+    bool dense = false;               // option: full-state sweeps + explicit collapse (ProjectQ-equivalent traffic)
     uint32_t *act_list = nullptr, *n_act = nullptr;
     int num_sms = 148;
     bool use_v1 = false;
@@ -777,6 +780,12 @@ extern "C" int s17_create(s17_ctx **out, int device, uint64_t max_shots) {
     CK(cudaFuncSetAttribute(k_layer2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kL2Smem));
     CK(cudaMalloc(&ctx->act_list, B * 4));
     CK(cudaMalloc(&ctx->n_act, 4));
+    CK(cudaMalloc(&ctx->zero_page, kRunBytes));
+    CK(cudaMemset(ctx->zero_page, 0, kRunBytes));
+    {
+        const char *d = getenv("S17_DENSE");
+        ctx->dense = d && d[0] == '1';
+    }
     {
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, device));
@@ -796,7 +805,7 @@ extern "C" int s17_destroy(s17_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     void *ptrs[] = {ctx->state, ctx->ev, ctx->masks, ctx->leak, ctx->active, ctx->ready, ctx->forced, ctx->hist,
                     ctx->aux, ctx->rec, ctx->counters, ctx->lut, ctx->cw16, ctx->probs, ctx->cum, ctx->plan,
-                    ctx->rtf_slots, ctx->rtf_rounds, ctx->rtf_syndb, ctx->act_list, ctx->n_act};
+                    ctx->rtf_slots, ctx->rtf_rounds, ctx->rtf_syndb, ctx->act_list, ctx->n_act, ctx->zero_page};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
@@ -823,10 +832,29 @@ static int check_layer(s17_ctx *ctx, const s17_layer &L) {
 }
 
 // host-side lowering of one sweep for k_layer2: per-op constants and the pass schedule
-static LayerArg2 make_layer2(const LayerArg &A) {
+static LayerArg2 make_layer2(const LayerArg &A, uint32_t support /* ancilla bits possibly non-zero */, bool first, bool dense) {
     LayerArg2 P;
     memset(&P, 0, sizeof(P));
     P.A = A;
+    {
+        int n = 0;
+        for (int tid = 0; tid < 32; ++tid) {
+            bool ok = true;
+            for (int k = 0; k < 5; ++k)
+                if (((tid >> k) & 1) && !dense && !((support >> A.other_bits[k]) & 1u)) ok = false;
+            if (ok) P.tile_ids[n++] = (uint8_t)tid;
+        }
+        int sh = 0;
+        while ((1 << sh) < n) ++sh;
+        P.tile_shift = (uint8_t)sh;
+        for (int r = 0; r < 8; ++r) {
+            bool ok = true;
+            for (int k = 0; k < 3; ++k)
+                if (((r >> k) & 1) && !dense && !((support >> A.L.anc_bits[k]) & 1u)) ok = false;
+            if (ok) P.in_runs |= (uint8_t)(1u << r);
+        }
+        P.first = (first && !dense) ? 1 : 0;
+    }
     const s17_layer &L = A.L;
     for (int o = 0; o < L.n_ops; ++o) {
         const s17_op &op = L.ops[o];
@@ -928,7 +956,14 @@ extern "C" int s17_load_program(s17_ctx *ctx, const s17_layer *layers, const uin
             ctx->layers[c].push_back(A);
         }
         ctx->layers2[c].clear();
-        for (const LayerArg &A : ctx->layers[c]) ctx->layers2[c].push_back(make_layer2(A));
+        ctx->layers2d[c].clear();
+        uint32_t support = 0;
+        for (size_t i = 0; i < ctx->layers[c].size(); ++i) {
+            const LayerArg &A = ctx->layers[c][i];
+            ctx->layers2[c].push_back(make_layer2(A, support, i == 0, false));
+            ctx->layers2d[c].push_back(make_layer2(A, 0x1FE00u, i == 0, true));
+            for (int k = 0; k < 3; ++k) support |= 1u << A.L.anc_bits[k];
+        }
     }
     if (ctx->plan) { cudaFree(ctx->plan); ctx->plan = nullptr; }
     CK(cudaMalloc(&ctx->plan, n_plan * sizeof(s17_pinstr)));
@@ -1027,7 +1062,7 @@ extern "C" int s17_set_replay(s17_ctx *ctx, uint64_t n, const uint8_t *masks, ui
 static inline int blocks_for(uint64_t n, int per) { return (int)((n + per - 1) / per); }
 
 // one stabiliser cycle: plan -> gate sweeps -> ancilla measurement decisions
-static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second, int init_basis, uint32_t max_layers) {
+static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second, int init_basis, uint32_t max_layers, bool dense) {
     const int n = (int)a.n_shots;
     PlanArgs pa;
     pa.n_instr = ctx->n_plan;
@@ -1046,7 +1081,7 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
     }
     const int which = stage == 0 ? 0 : (second ? 2 : 1);
     const std::vector<LayerArg> &Ls = ctx->layers[which];
-    const std::vector<LayerArg2> &Ls2 = ctx->layers2[which];
+    const std::vector<LayerArg2> &Ls2 = dense ? ctx->layers2d[which] : ctx->layers2[which];
     uint32_t nl = (uint32_t)Ls.size();
     if (max_layers && max_layers < nl) nl = max_layers;
     if (!ctx->use_v1) {
@@ -1060,7 +1095,8 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
                 ctx->state, Ls[i], ctx->ev, ctx->active, ctx->hist, ctx->counters, (i == 0) ? init_basis : -1);
         else
             k_layer2<<<ctx->num_sms, kL2Threads, kL2Smem, ctx->stream>>>(
-                ctx->state, Ls2[i], ctx->ev, ctx->act_list, ctx->n_act, ctx->hist, ctx->counters, (i == 0) ? init_basis : -1);
+                ctx->state, Ls2[i], ctx->ev, ctx->act_list, ctx->n_act, ctx->hist, ctx->counters, ctx->aux, ctx->zero_page,
+                (i == 0) ? init_basis : -1);
         ctx->n_gate++;
     }
     if (max_layers && max_layers < Ls.size()) return S17_OK;
@@ -1089,11 +1125,17 @@ static void collapse(s17_ctx *ctx, int n, const uint8_t *flag) {
 static int run_round(s17_ctx *ctx, const s17_run_args &a) {
     const int n = (int)a.n_shots;
     const int basis_index = a.logical_state ? 0x1FF : 0;     // All(X) | data when state == 1 (CS:103-104)
-    if (int rc = run_cycle(ctx, a, 0, 0, basis_index, 0)) return rc;
-    collapse(ctx, n, ctx->active);
+    // dense: every sweep covers the full state and ProjectQ's collapse is materialised after each measurement.
+    // otherwise the collapse + reset is lazy: the next sweep reads the surviving block, scaled, and sweeps only
+    // cover the part of the state that can be non-zero.
+    const bool dense = ctx->dense || ctx->use_v1;
+    const bool explicit_collapse = dense || a.materialize || a.stop_stage != S17_STOP_NONE;
+    if (int rc = run_cycle(ctx, a, 0, 0, basis_index, 0, dense)) return rc;
+    if (explicit_collapse) collapse(ctx, n, ctx->active);
     if (a.stop_stage == S17_STOP_AFTER_PREP) return S17_OK;
-    if (a.stop_stage == S17_STOP_CYCLE1_GATES) return run_cycle(ctx, a, 1, 0, -1, a.stop_layers ? a.stop_layers : 1000);
-    if (int rc = run_cycle(ctx, a, 1, 0, -1, 0)) return rc;
+    if (a.stop_stage == S17_STOP_CYCLE1_GATES)
+        return run_cycle(ctx, a, 1, 0, -1, a.stop_layers ? a.stop_layers : 1000, dense);
+    if (int rc = run_cycle(ctx, a, 1, 0, -1, 0, dense)) return rc;
     if (a.stop_stage == S17_STOP_AFTER_CYCLE1) {
         Scope s(ctx, CAT_OTHER);
         cudaMemsetAsync(ctx->active, 1, n, ctx->stream);
@@ -1101,9 +1143,9 @@ static int run_round(s17_ctx *ctx, const s17_run_args &a) {
         return S17_OK;
     }
     if (a.protocol == S17_PROTO_S2 || a.protocol == S17_PROTO_RTF) {
-        collapse(ctx, n, ctx->active);
+        if (explicit_collapse) collapse(ctx, n, ctx->active);
         // s2: stab_ind=1 slots (CL:422); run-til-fail: cycle B reuses the stab_ind=0 probabilities (CL:92)
-        if (int rc = run_cycle(ctx, a, 2, a.protocol == S17_PROTO_S2 ? 1 : 0, -1, 0)) return rc;
+        if (int rc = run_cycle(ctx, a, 2, a.protocol == S17_PROTO_S2 ? 1 : 0, -1, 0, dense)) return rc;
     }
     if (a.materialize) {
         collapse(ctx, n, ctx->ready);
@@ -1217,6 +1259,7 @@ extern "C" int s17_run(s17_ctx *ctx, const s17_run_args *args, s17_counts *out) 
     out->errors = c[C_ERRORS];
     out->sweeps = c[C_SWEEPS];
     out->rounds = c[C_ROUNDS];
+    out->sweep_bytes = c[C_RUNS_MOVED] * (unsigned long long)kRunBytes;   // algorithmic HBM bytes moved by the gate sweeps
     ctx->last_n = a.n_shots;
     return S17_OK;
 }

@@ -19,7 +19,8 @@ constexpr int kGroupThreads = kMathThreads / kGroups;
 constexpr int kL2Threads = kMathThreads + 64;      // + loader warp + storer warp
 constexpr int kRing = 3;
 constexpr int kEvBytes = S17_EV_WORDS * 4;
-constexpr size_t kL2Smem = (size_t)kRing * kTile * 16 + kRing * kEvBytes + 3 * kRing * 8 + 64;
+constexpr int kAuxBytes = 16;                       // sizeof(ShotAux)
+constexpr size_t kL2Smem = (size_t)kRing * kTile * 16 + kRing * kEvBytes + kRing * kAuxBytes + 3 * kRing * 8 + 64;
 
 struct OpC {                 // per-operation constants precomputed on the host
     uint8_t lb0, lb1;        // tile-local bit of the data / ancilla qubit
@@ -43,7 +44,13 @@ struct LayerArg2 {
     OpC oc[8];
     PassC pass[8];
     uint32_t n_pass;
-    uint32_t pad;
+    // support of the state before this sweep (ancilla bits that may be non-zero): tiles / runs outside it are
+    // known to be exactly zero and are neither read nor written
+    uint8_t tile_shift;      // log2(number of tiles of a shot inside the support)
+    uint8_t in_runs;         // bit r set: run r of a support tile may be non-zero on input
+    uint8_t first;           // 1: first sweep after a measurement -> input is the surviving block (lazy collapse)
+    uint8_t pad0;
+    uint8_t tile_ids[32];
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
@@ -168,17 +175,20 @@ __device__ __forceinline__ void tile_coords(const LayerArg &A, int tile_id, uint
 __global__ void __launch_bounds__(kL2Threads, 1)
 k_layer2(double2 *__restrict__ state, const __grid_constant__ LayerArg2 P, const uint32_t *__restrict__ ev,
          const uint32_t *__restrict__ act_list, const uint32_t *__restrict__ n_act_ptr, double *__restrict__ hist,
-         unsigned long long *__restrict__ counters, int init_basis)
+         unsigned long long *__restrict__ counters, const ShotAux *__restrict__ aux, const double2 *__restrict__ zero_page,
+         int init_basis)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     double2 *tiles = reinterpret_cast<double2 *>(smem_raw);
     uint32_t *evbuf = reinterpret_cast<uint32_t *>(smem_raw + (size_t)kRing * kTile * 16);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kRing * kTile * 16 + kRing * kEvBytes);
+    ShotAux *auxbuf = reinterpret_cast<ShotAux *>(smem_raw + (size_t)kRing * kTile * 16 + kRing * kEvBytes);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kRing * kTile * 16 + kRing * kEvBytes + kRing * kAuxBytes);
     uint64_t *done = full + kRing;
     uint64_t *free_ = done + kRing;
 
     const int t = threadIdx.x;
-    const uint32_t n_items = (*n_act_ptr) * kTilesPerShot;
+    const uint32_t n_items = (*n_act_ptr) << P.tile_shift;
+    const uint32_t tile_mask = (1u << P.tile_shift) - 1u;
     const uint32_t chunk = (n_items + gridDim.x - 1) / gridDim.x;
     const uint32_t first = blockIdx.x * chunk;
     const uint32_t last = min(n_items, first + chunk);
@@ -204,19 +214,31 @@ k_layer2(double2 *__restrict__ state, const __grid_constant__ LayerArg2 P, const
                 const int b = j % kRing;
                 if (j >= (uint32_t)kRing) mbar_wait_sleep(&free_[b], ((j / kRing) - 1) & 1);
                 const uint32_t item = first + j;
-                const uint32_t shot = act_list[item >> 5];
+                const uint32_t shot = act_list[item >> P.tile_shift];
                 uint32_t base, run_off[8];
-                tile_coords(P.A, item & 31, base, run_off);
+                tile_coords(P.A, P.tile_ids[item & tile_mask], base, run_off);
                 const double2 *sbase = state + (size_t)shot * kDim;
                 double2 *tile = tiles + (size_t)b * kTile;
                 if (init_basis < 0) {
-                    mbar_expect_tx(&full[b], kTile * 16 + kEvBytes);
+                    mbar_expect_tx(&full[b], kTile * 16 + kEvBytes + kAuxBytes);
+                    if (P.first) {
+                        // lazy collapse + reset: the only non-zero input is the surviving 512-amplitude block
+                        const ShotAux ax = aux[shot];
+                        const uint32_t blk = ax.collapsed ? 0u : ax.anc_outcome;
+                        tma_load_1d(tile, sbase + (size_t)blk * kRun, kRunBytes, &full[b]);
 #pragma unroll
-                    for (int r = 0; r < 8; ++r) tma_load_1d(tile + r * kRun, sbase + run_off[r], kRunBytes, &full[b]);
+                        for (int r = 1; r < 8; ++r) tma_load_1d(tile + r * kRun, zero_page, kRunBytes, &full[b]);
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < 8; ++r)
+                            tma_load_1d(tile + r * kRun, ((P.in_runs >> r) & 1) ? sbase + run_off[r] : zero_page, kRunBytes,
+                                        &full[b]);
+                    }
                 } else {
-                    mbar_expect_tx(&full[b], kEvBytes);
+                    mbar_expect_tx(&full[b], kEvBytes + kAuxBytes);
                 }
                 tma_load_1d(evbuf + b * S17_EV_WORDS, ev + (size_t)shot * S17_EV_WORDS, kEvBytes, &full[b]);
+                tma_load_1d(auxbuf + b, aux + shot, kAuxBytes, &full[b]);
             }
         }
         return;
@@ -228,17 +250,20 @@ k_layer2(double2 *__restrict__ state, const __grid_constant__ LayerArg2 P, const
                 const int b = j % kRing;
                 mbar_wait_sleep(&done[b], (j / kRing) & 1);
                 const uint32_t item = first + j;
-                const uint32_t shot = act_list[item >> 5];
+                const uint32_t shot = act_list[item >> P.tile_shift];
                 uint32_t base, run_off[8];
-                tile_coords(P.A, item & 31, base, run_off);
+                tile_coords(P.A, P.tile_ids[item & tile_mask], base, run_off);
                 double2 *sbase = state + (size_t)shot * kDim;
                 const double2 *tile = tiles + (size_t)b * kTile;
 #pragma unroll
                 for (int r = 0; r < 8; ++r) tma_store_1d(sbase + run_off[r], tile + r * kRun, kRunBytes);
                 tma_store_commit_and_wait_read();
                 mbar_arrive(&free_[b]);
-                if ((item & 31) == 0) atomicAdd(&counters[4], 1ull);   // C_SWEEPS
             }
+            // roofline accounting: (shot, sweep) pairs and 8 KiB run transfers that really touched HBM
+            const uint32_t in_runs = init_basis >= 0 ? 0u : (P.first ? 1u : (uint32_t)__popc(P.in_runs));
+            atomicAdd(&counters[4], (unsigned long long)((last + tile_mask) >> P.tile_shift) - ((first + tile_mask) >> P.tile_shift));
+            atomicAdd(&counters[8], (unsigned long long)n_local * (in_runs + 8u));   // C_RUNS_MOVED
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         }
         return;
@@ -255,7 +280,7 @@ k_layer2(double2 *__restrict__ state, const __grid_constant__ LayerArg2 P, const
         double2 *tile = tiles + (size_t)b * kTile;
         const uint32_t *evw = evbuf + b * S17_EV_WORDS;
         const uint32_t item = first + j;
-        const int tile_id = item & 31;
+        const int tile_id = P.tile_ids[item & tile_mask];
         mbar_wait(&full[b], (j / kRing) & 1);
         uint32_t base = 0;
 #pragma unroll
@@ -276,7 +301,8 @@ k_layer2(double2 *__restrict__ state, const __grid_constant__ LayerArg2 P, const
             const uint32_t skip = (evw[P.oc[o].ev_word] >> 24) & 1u;
             nsc += P.oc[o].n_fixed + (skip ? 0 : P.oc[o].n_skip);
         }
-        const double scale = ldexp((nsc & 1) ? 0.70710678118654752440 : 1.0, -(nsc >> 1));
+        double scale = ldexp((nsc & 1) ? 0.70710678118654752440 : 1.0, -(nsc >> 1));
+        if (P.first && init_basis < 0 && !auxbuf[b].collapsed) scale *= auxbuf[b].scale;   // renormalisation of the lazy collapse
 
         for (uint32_t p = 0; p < P.n_pass; ++p) {
             const PassC ps = P.pass[p];
@@ -379,7 +405,7 @@ k_layer2(double2 *__restrict__ state, const __grid_constant__ LayerArg2 P, const
                     uint32_t g = base;
 #pragma unroll
                     for (int k = 0; k < 3; ++k) g |= ((run >> k) & 1u) << P.A.L.anc_bits[k];
-                    const uint32_t shot = act_list[item >> 5];
+                    const uint32_t shot = act_list[item >> P.tile_shift];
                     hist[(size_t)shot * 256 + (g >> 9)] = acc;
                 }
             }

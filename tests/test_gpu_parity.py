@@ -31,10 +31,11 @@ def make_sim(models, ct, bt, model, list_len, n, fusion=1, cooling=False, **kw):
                           bitflip_table=bt, error_models=models, **kw)
 
 
-@pytest.mark.parametrize("fusion", [0, 1, 2])
-def test_golden_replays(error_models, correction_table, bitflip_table, golden, fusion):
+@pytest.mark.parametrize("fusion,dense", [(0, "0"), (1, "0"), (2, "0"), (2, "1"), (0, "1")])
+def test_golden_replays(error_models, correction_table, bitflip_table, golden, fusion, dense, monkeypatch):
     """Replayed reference trajectories (masks + forced outcomes): every record field bit-exact, and the
     post-correction state equals the reference's 512-amplitude block within 1e-10."""
+    monkeypatch.setenv("S17_DENSE", dense)     # 1: full-state sweeps + explicit collapse kernels
     reps = golden("replays.json")["replays"]
     blocks = np.load(os.path.join(GOLDEN, "replay_blocks.npz"))["blocks"]
     groups = {}
@@ -56,6 +57,27 @@ def test_golden_replays(error_models, correction_table, bitflip_table, golden, f
                 assert np.sum(np.abs(psi[512:]) ** 2) < 1e-20
         assert c.failed == sum(r["fail"] for r in rs)
         assert c.not0 == sum(r["not0"] for r in rs)
+        sim.close()
+
+
+@pytest.mark.parametrize("dense", ["0", "1"])
+def test_golden_replays_fast_path(error_models, correction_table, bitflip_table, golden, dense, monkeypatch):
+    """Same replays through the production path (lazy collapse, correction folded into the read-out)."""
+    monkeypatch.setenv("S17_DENSE", dense)
+    reps = golden("replays.json")["replays"]
+    groups = {}
+    for r in reps:
+        groups.setdefault((r["model"], r["protocol"], r["cooling"]), []).append(r)
+    for (model, protocol, cooling), rs in groups.items():
+        list_len = [len(x) for x in rs[0]["p_set"]]
+        sim = make_sim(error_models, correction_table, bitflip_table, model, list_len, len(rs), 2, cooling)
+        sim.backend.set_replay([flat(r["p_set"]) for r in rs], [r["outcomes"] for r in rs])
+        c = sim.backend.run(protocol, len(rs), L.NOISE_REPLAY, forced=True)
+        assert c.errors == 0
+        recs = sim.backend.records(len(rs))
+        for i, r in enumerate(rs):
+            for f in FIELDS:
+                assert recs[i].get(f) == r.get(f), (model, protocol, i, f, recs[i].get(f), r.get(f))
         sim.close()
 
 
