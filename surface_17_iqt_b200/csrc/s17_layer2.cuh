@@ -11,9 +11,13 @@
 #pragma once
 #include "s17_kernels.cuh"
 
+#ifndef S17_MATH_THREADS
+#define S17_MATH_THREADS 256
+#endif
+
 namespace s17 {
 
-constexpr int kMathThreads = 256;
+constexpr int kMathThreads = S17_MATH_THREADS;
 constexpr int kGroups = 2;                          // independent math groups, each on its own tile
 constexpr int kGroupThreads = kMathThreads / kGroups;
 constexpr int kL2Threads = kMathThreads + 64;      // + loader warp + storer warp
@@ -143,11 +147,11 @@ __device__ __forceinline__ void apply_fast(double2 (&a)[16], double v1, double s
 }
 
 struct FastC { double v1, s, sx, v2; };
-__device__ __forceinline__ FastC fast_coeffs(const OpC c, uint32_t w) {
+__device__ __forceinline__ FastC fast_coeffs(const OpC c) {
     FastC f;
     const double s = (double)c.s;
     f.v1 = (c.shape & 1) ? 1.0 : 0.0;
-    f.s = ((w >> 24) & 1u) ? 0.0 : s;
+    f.s = s;
     f.sx = (c.shape & 2) ? -s : 0.0;
     f.v2 = (c.shape & 4) ? -1.0 : 0.0;
     return f;
@@ -157,6 +161,75 @@ template <bool OP2>
 __device__ __forceinline__ void apply_op(double2 (&a)[16], const LayerArg2 &P, int o, uint32_t w) {
     if (P.oc[o].generic) apply_generic<OP2>(a, P.A.L.ops[o], P.A.prm, w);
     else apply_standard<OP2>(a, P.oc[o], w);
+}
+
+struct PassGeom { int p0, p1, p2, p3, m0, m1, m2, m3; };
+
+// tile offsets of the 16 amplitudes a thread owns in a pass.  KIND 1: one item, four register bits
+// (op1 data, op1 ancilla, op2 data, op2 ancilla); KIND 0: four items, two register bits each.
+template <int KIND>
+__device__ __forceinline__ void item_offsets(const PassGeom &g, int item, int (&off)[16]) {
+    if (KIND == 1) {
+        const int i0 = insert0(insert0(insert0(insert0(item, g.p0), g.p1), g.p2), g.p3);
+#pragma unroll
+        for (int r = 0; r < 16; ++r)
+            off[r] = i0 + ((r & 1) ? g.m0 : 0) + ((r & 2) ? g.m1 : 0) + ((r & 4) ? g.m2 : 0) + ((r & 8) ? g.m3 : 0);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int i0 = insert0(insert0(4 * item + i, g.p0), g.p1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) off[4 * i + k] = i0 + ((k & 1) ? g.m0 : 0) + ((k & 2) ? g.m1 : 0);
+        }
+    }
+}
+
+template <int KIND>
+__device__ __forceinline__ void fast_item(double2 *tile, const PassGeom &g, int item, const FastC f1, const FastC f2,
+                                          double sc) {
+    double2 a[16];
+    {
+        int off[16];
+        item_offsets<KIND>(g, item, off);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) a[r] = tile[off[r]];
+    }
+    apply_fast<false>(a, f1.v1, f1.s, f1.sx, f1.v2);
+    if (KIND == 1) apply_fast<true>(a, f2.v1, f2.s, f2.sx, f2.v2);
+    {
+        // recompute the offsets instead of keeping 16 address registers live across the FP64 block
+        int item2 = item;
+        asm volatile("" : "+r"(item2));
+        int off[16];
+        item_offsets<KIND>(g, item2, off);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) tile[off[r]] = make_double2(a[r].x * sc, a[r].y * sc);
+    }
+}
+
+// everything else (Pauli events, leak-skipped Rxx, idle Z masks, coherent rotations): rare, kept out of line
+__device__ __noinline__ void slow_item(double2 *tile, const LayerArg2 *Pp, const PassC ps, const PassGeom g, int item,
+                                       uint32_t w1, uint32_t w2, uint32_t zm, uint32_t lm, uint32_t c0, double sc) {
+    const LayerArg2 &P = *Pp;
+    double2 a[16];
+    int off[16];
+    if (ps.kind == 1) item_offsets<1>(g, item, off);
+    else item_offsets<0>(g, item, off);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) a[r] = tile[off[r]];
+    if (ps.kind == 1) {
+        apply_op<false>(a, P, ps.o1, w1);
+        apply_op<true>(a, P, ps.o2, w2);
+    } else if (ps.kind == 0) {
+        apply_op<false>(a, P, ps.o1, w1);
+    }
+    if (zm) {
+#pragma unroll
+        for (int r = 0; r < 16; ++r)
+            if ((__popc(off[r] & lm) & 1u) ^ c0) a[r] = make_double2(-a[r].x, -a[r].y);
+    }
+#pragma unroll
+    for (int r = 0; r < 16; ++r) tile[off[r]] = make_double2(a[r].x * sc, a[r].y * sc);
 }
 
 __device__ __forceinline__ void tile_coords(const LayerArg &A, int tile_id, uint32_t &base, uint32_t (&run_off)[8]) {
@@ -319,71 +392,31 @@ k_layer2(double2 *__restrict__ state, const __grid_constant__ LayerArg2 P, const
             const OpC c1 = P.oc[ps.o1], c2 = P.oc[ps.kind == 1 ? ps.o2 : ps.o1];
             const uint32_t w1 = evw[c1.ev_word];
             const uint32_t w2 = ps.kind == 1 ? evw[c2.ev_word] : 0u;
-            const bool fast = !(c1.generic | (ps.kind == 1 ? c2.generic : 0)) && !((w1 | w2) & 0xFFFFFFu);
-            const FastC f1 = fast_coeffs(c1, w1), f2 = fast_coeffs(c2, w2);
-            // register r of a thread holds the amplitude at tile offset i0 + (warp-uniform combination of m0..m3)
-            int p0, p1, p2, p3;                                  // zero-bit insert positions, ascending
-            int m0, m1, m2, m3;
+            // fast path: standard ops, no Pauli event, no leak skip, no idle mask -> straight-line code whose
+            // coefficients all come from the constant bank
+            const bool fast = ps.kind != 2 && !(c1.generic | (ps.kind == 1 ? c2.generic : 0)) &&
+                              !((w1 | w2) & 0x1FFFFFFu) && zm == 0;
+            PassGeom g;
             if (ps.kind == 1) {
-                p0 = min(c1.lb0, c2.lb0); p1 = max(c1.lb0, c2.lb0);
-                p2 = min(c1.lb1, c2.lb1); p3 = max(c1.lb1, c2.lb1);
-                m0 = 1 << c1.lb0; m1 = 1 << c1.lb1; m2 = 1 << c2.lb0; m3 = 1 << c2.lb1;
+                g.p0 = min(c1.lb0, c2.lb0); g.p1 = max(c1.lb0, c2.lb0);
+                g.p2 = min(c1.lb1, c2.lb1); g.p3 = max(c1.lb1, c2.lb1);
+                g.m0 = 1 << c1.lb0; g.m1 = 1 << c1.lb1; g.m2 = 1 << c2.lb0; g.m3 = 1 << c2.lb1;
             } else {
                 const int lb0 = ps.kind == 0 ? c1.lb0 : 0, lb1 = ps.kind == 0 ? c1.lb1 : 9;
-                p0 = lb0; p1 = lb1; p2 = p3 = 0;
-                m0 = 1 << lb0; m1 = 1 << lb1; m2 = m3 = 0;
+                g.p0 = lb0; g.p1 = lb1; g.p2 = g.p3 = 0;
+                g.m0 = 1 << lb0; g.m1 = 1 << lb1; g.m2 = g.m3 = 0;
             }
-
+            if (fast) {
+                const FastC f1 = fast_coeffs(c1), f2 = fast_coeffs(c2);
 #pragma unroll 1
-            for (int it = 0; it < kTile / 16 / kGroupThreads; ++it) {
-                double2 a[16];
-                int off[16];
-                if (ps.kind == 1) {
-                    const int i0 = insert0(insert0(insert0(insert0(tg + kGroupThreads * it, p0), p1), p2), p3);
-#pragma unroll
-                    for (int r = 0; r < 16; ++r)
-                        off[r] = i0 + ((r & 1) ? m0 : 0) + ((r & 2) ? m1 : 0) + ((r & 4) ? m2 : 0) + ((r & 8) ? m3 : 0);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int i0 = insert0(insert0(tg + kGroupThreads * (4 * it + i), p0), p1);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) off[4 * i + k] = i0 + ((k & 1) ? m0 : 0) + ((k & 2) ? m1 : 0);
-                    }
+                for (int it = 0; it < kTile / 16 / kGroupThreads; ++it) {
+                    if (ps.kind == 1) fast_item<1>(tile, g, tg + kGroupThreads * it, f1, f2, sc);
+                    else fast_item<0>(tile, g, tg + kGroupThreads * it, f1, f2, sc);
                 }
-#pragma unroll
-                for (int r = 0; r < 16; ++r) a[r] = tile[off[r]];
-
-                auto finish = [&](double2 (&x)[16]) {
-                    if (zm) {
-#pragma unroll
-                        for (int r = 0; r < 16; ++r)
-                            if ((__popc(off[r] & lm) & 1u) ^ c0) x[r] = make_double2(-x[r].x, -x[r].y);
-                    }
-#pragma unroll
-                    for (int r = 0; r < 16; ++r) tile[off[r]] = make_double2(x[r].x * sc, x[r].y * sc);
-                };
-                if (ps.kind == 1) {
-                    if (fast) {
-                        apply_fast<false>(a, f1.v1, f1.s, f1.sx, f1.v2);
-                        apply_fast<true>(a, f2.v1, f2.s, f2.sx, f2.v2);
-                        finish(a);
-                    } else {
-                        apply_op<false>(a, P, ps.o1, w1);
-                        apply_op<true>(a, P, ps.o2, w2);
-                        finish(a);
-                    }
-                } else if (ps.kind == 0) {
-                    if (fast) {
-                        apply_fast<false>(a, f1.v1, f1.s, f1.sx, f1.v2);
-                        finish(a);
-                    } else {
-                        apply_op<false>(a, P, ps.o1, w1);
-                        finish(a);
-                    }
-                } else {
-                    finish(a);
-                }
+            } else {
+#pragma unroll 1
+                for (int it = 0; it < kTile / 16 / kGroupThreads; ++it)
+                    slow_item(tile, &P, ps, g, tg + kGroupThreads * it, w1, w2, zm, lm, c0, sc);
             }
             group_barrier(grp);
         }
