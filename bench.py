@@ -254,7 +254,7 @@ def run_gpu(args):
                     "h2d_bytes_per_step": 2048 * 8 + 3 * 4 * len(ESET) + 64, "d2h_bytes_per_step": 64 + 8 * 8,
                     "api": "s2_calculate_log_e_rate_error_subset(num_runs, ...) -> (rate, not0_rate, failed, not0)"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_layer", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_layer4" if args.fusion == 4 else "k_layer2", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                          "traffic": None, "launches": int(gate_launches), "sweeps": int(sweeps),
                          "sweeps_per_shot": sweeps / (B * args.steps),
@@ -278,7 +278,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--shots", type=int, default=int(os.environ.get("S17_BENCH_SHOTS", "8192")), help="shots per GPU per step")
-    ap.add_argument("--fusion", type=int, default=2)
+    ap.add_argument("--fusion", type=int, default=4)
     ap.add_argument("--seed", type=int, default=2026)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-shots-per-core", type=int, default=60)

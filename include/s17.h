@@ -73,12 +73,14 @@ typedef struct {
 } s17_op;
 
 /* one sweep over the state: every op's ancilla bit must be one of anc_bits */
+#define S17_MAX_LAYER_OPS 16u
 typedef struct {
     uint8_t n_ops;
-    uint8_t anc_bits[3];   /* ancilla bits staged in shared memory next to the 9 data bits */
+    uint8_t n_anc;         /* 3: 4096-amplitude tiles (<= 8 ops), 4: 8192-amplitude tiles (<= 16 ops) */
+    uint8_t anc_bits[4];   /* ancilla bits staged in shared memory next to the 9 data bits, ascending */
     uint8_t emit_hist;     /* 1: also emit the 256-bin joint ancilla histogram (last sweep of a cycle) */
-    uint8_t pad[3];
-    s17_op ops[8];
+    uint8_t pad;
+    s17_op ops[S17_MAX_LAYER_OPS];
 } s17_layer;
 
 /* ---- error-injection program (restates insert_errors / insert_error, CS:127-234) ---------------- */

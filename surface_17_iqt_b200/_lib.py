@@ -34,8 +34,8 @@ class Op(C.Structure):
 
 
 class Layer(C.Structure):
-    _fields_ = [("n_ops", C.c_uint8), ("anc_bits", C.c_uint8 * 3), ("emit_hist", C.c_uint8), ("pad", C.c_uint8 * 3),
-                ("ops", Op * 8)]
+    _fields_ = [("n_ops", C.c_uint8), ("n_anc", C.c_uint8), ("anc_bits", C.c_uint8 * 4), ("emit_hist", C.c_uint8),
+                ("pad", C.c_uint8), ("ops", Op * 16)]
 
 
 class PInstr(C.Structure):
@@ -68,7 +68,7 @@ class Record(C.Structure):
                 ("data_meas", C.c_uint16), ("pad", C.c_uint16), ("outcomes", C.c_uint8 * MAX_OUTCOMES)]
 
 
-assert C.sizeof(Uop) == 8 and C.sizeof(Op) == 72 and C.sizeof(Layer) == 584
+assert C.sizeof(Uop) == 8 and C.sizeof(Op) == 72 and C.sizeof(Layer) == 1160
 assert C.sizeof(PInstr) == 12 and C.sizeof(Record) == 60 and C.sizeof(RunArgs) == 64
 
 EXPORTS = ("s17_create", "s17_destroy", "s17_last_error", "s17_device_count", "s17_load_program",

@@ -172,11 +172,11 @@ def compile_program(model, list_len, fusion=1, cooling=False, over_angles=None) 
     """Compile `model` (one entry of error_models.json) for lists of total length `list_len`.
 
     fusion: 0 = one sweep per gate (ProjectQ's execution model), 1 = one sweep per timestep,
-            2 = one sweep per two timesteps.
+            2 = one sweep per two timesteps, 4 = one sweep per four timesteps (8192-amplitude tiles).
     over_angles: {prob_name: [angles]} for the coherent ``*_over`` entries (extension, SURVEY C-10).
     """
-    if fusion not in (0, 1, 2):
-        raise ValueError("fusion must be 0, 1 or 2")
+    if fusion not in (0, 1, 2, 4):
+        raise ValueError("fusion must be 0, 1, 2 or 4")
     names = list(model["probabilities"])
     if len(names) != len(list_len):
         raise ValueError("make sure you pass enough probabilities to specify the error model - see error_model.json")
@@ -301,15 +301,17 @@ def compile_program(model, list_len, fusion=1, cooling=False, over_angles=None) 
     def make_layer(items, anc_bits, emit_hist=False):
         lay = L.Layer()
         anc = sorted(set(anc_bits))
+        n_anc = 4 if len(anc) > 3 else 3
         fill = [b for b in range(N_DATA, N_DATA + N_ANC) if b not in anc]
-        while len(anc) < 3:
+        while len(anc) < n_anc:
             anc.append(fill.pop(0))
         anc.sort()
-        if len(anc) != 3:
-            raise ValueError("a sweep can stage at most 3 ancilla bits")
-        if len(items) > 8:
-            raise ValueError("a sweep holds at most 8 operations")
+        if len(anc) != n_anc:
+            raise ValueError("a sweep can stage at most 4 ancilla bits")
+        if len(items) > (16 if n_anc == 4 else 8):
+            raise ValueError("too many operations in one sweep")
         lay.n_ops = len(items)
+        lay.n_anc = n_anc
         for i, b in enumerate(anc):
             lay.anc_bits[i] = b
         lay.emit_hist = int(emit_hist)

@@ -24,6 +24,7 @@
 
 #include "s17_kernels.cuh"
 #include "s17_layer2.cuh"
+#include "s17_layer4.cuh"
 
 namespace s17 {
 
@@ -778,6 +779,7 @@ extern "C" int s17_create(s17_ctx **out, int device, uint64_t max_shots) {
     CK(cudaMemset(ctx->ev, 0, B * S17_EV_WORDS * 4));
     CK(cudaFuncSetAttribute(k_layer, cudaFuncAttributeMaxDynamicSharedMemorySize, kTile * 16));
     CK(cudaFuncSetAttribute(k_layer2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kL2Smem));
+    CK(cudaFuncSetAttribute(k_layer4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kL4Smem));
     CK(cudaMalloc(&ctx->act_list, B * 4));
     CK(cudaMalloc(&ctx->n_act, 4));
     CK(cudaMalloc(&ctx->zero_page, kRunBytes));
@@ -815,17 +817,18 @@ extern "C" int s17_destroy(s17_ctx *ctx) {
 }
 
 static int check_layer(s17_ctx *ctx, const s17_layer &L) {
-    if (L.n_ops > 8) return fail(ctx, S17_E_ARG, "layer has more than 8 ops");
-    for (int k = 0; k < 3; ++k)
+    if (L.n_anc != 3 && L.n_anc != 4) return fail(ctx, S17_E_ARG, "layer must stage 3 or 4 ancilla bits");
+    if (L.n_ops > (L.n_anc == 4 ? 16 : 8)) return fail(ctx, S17_E_ARG, "too many ops in one layer");
+    for (int k = 0; k < L.n_anc; ++k)
         if (L.anc_bits[k] < 9 || L.anc_bits[k] > 16 || (k && L.anc_bits[k] <= L.anc_bits[k - 1]))
-            return fail(ctx, S17_E_ARG, "layer anc_bits must be 3 ascending ancilla bits in 9..16");
+            return fail(ctx, S17_E_ARG, "layer anc_bits must be ascending ancilla bits in 9..16");
     for (int o = 0; o < L.n_ops; ++o) {
         const s17_op &op = L.ops[o];
         if (op.ev_word >= S17_EV_WORDS) return fail(ctx, S17_E_ARG, "op ev_word out of range");
         if (op.kind == S17_OP_IDLE) continue;
         if (op.kind != S17_OP_ENT || op.data_bit > 8 || op.n_uops > 8) return fail(ctx, S17_E_ARG, "bad op");
         bool ok = false;
-        for (int k = 0; k < 3; ++k) ok |= (L.anc_bits[k] == op.anc_bit);
+        for (int k = 0; k < L.n_anc; ++k) ok |= (L.anc_bits[k] == op.anc_bit);
         if (!ok) return fail(ctx, S17_E_ARG, "op ancilla bit is not staged by its layer");
     }
     return S17_OK;
@@ -836,22 +839,23 @@ static LayerArg2 make_layer2(const LayerArg &A, uint32_t support /* ancilla bits
     LayerArg2 P;
     memset(&P, 0, sizeof(P));
     P.A = A;
+    const int n_anc = A.L.n_anc, n_other = 8 - n_anc;
     {
         int n = 0;
-        for (int tid = 0; tid < 32; ++tid) {
+        for (int tid = 0; tid < (1 << n_other); ++tid) {
             bool ok = true;
-            for (int k = 0; k < 5; ++k)
+            for (int k = 0; k < n_other; ++k)
                 if (((tid >> k) & 1) && !dense && !((support >> A.other_bits[k]) & 1u)) ok = false;
             if (ok) P.tile_ids[n++] = (uint8_t)tid;
         }
         int sh = 0;
         while ((1 << sh) < n) ++sh;
         P.tile_shift = (uint8_t)sh;
-        for (int r = 0; r < 8; ++r) {
+        for (int r = 0; r < (1 << n_anc); ++r) {
             bool ok = true;
-            for (int k = 0; k < 3; ++k)
+            for (int k = 0; k < n_anc; ++k)
                 if (((r >> k) & 1) && !dense && !((support >> A.L.anc_bits[k]) & 1u)) ok = false;
-            if (ok) P.in_runs |= (uint8_t)(1u << r);
+            if (ok) P.in_runs |= (uint16_t)(1u << r);
         }
         P.first = (first && !dense) ? 1 : 0;
     }
@@ -863,7 +867,7 @@ static LayerArg2 make_layer2(const LayerArg &A, uint32_t support /* ancilla bits
         if (op.kind != S17_OP_ENT) continue;
         c.lb0 = op.data_bit;
         c.lb1 = 9;
-        for (int k = 0; k < 3; ++k)
+        for (int k = 0; k < n_anc; ++k)
             if (L.anc_bits[k] == op.anc_bit) c.lb1 = (uint8_t)(9 + k);
         // standard template: [Ry(+) ev0] Rxx(s, skippable, ev6) [Rx(-s) ev12] [Ry(-) ev18]
         int u = 0;
@@ -942,7 +946,7 @@ extern "C" int s17_load_program(s17_ctx *ctx, const s17_layer *layers, const uin
                     s17_uop &up = A.L.ops[o].uops[u];
                     if (up.type >= S17_U_ROT_X) {
                         if (up.param >= n_params || !params) return fail(ctx, S17_E_ARG, "uop param out of range");
-                        if (np >= 32) return fail(ctx, S17_E_ARG, "too many rotation parameters in one layer");
+                        if (np >= 64) return fail(ctx, S17_E_ARG, "too many rotation parameters in one layer");
                         A.prm[np] = make_double2(params[2 * up.param], params[2 * up.param + 1]);
                         up.param = (uint8_t)np++;
                     }
@@ -950,7 +954,7 @@ extern "C" int s17_load_program(s17_ctx *ctx, const s17_layer *layers, const uin
             int k = 0;
             for (int b = 9; b <= 16; ++b) {
                 bool in = false;
-                for (int j = 0; j < 3; ++j) in |= (A.L.anc_bits[j] == b);
+                for (int j = 0; j < A.L.n_anc; ++j) in |= (A.L.anc_bits[j] == b);
                 if (!in) A.other_bits[k++] = (uint8_t)b;
             }
             ctx->layers[c].push_back(A);
@@ -962,7 +966,7 @@ extern "C" int s17_load_program(s17_ctx *ctx, const s17_layer *layers, const uin
             const LayerArg &A = ctx->layers[c][i];
             ctx->layers2[c].push_back(make_layer2(A, support, i == 0, false));
             ctx->layers2d[c].push_back(make_layer2(A, 0x1FE00u, i == 0, true));
-            for (int k = 0; k < 3; ++k) support |= 1u << A.L.anc_bits[k];
+            for (int k = 0; k < A.L.n_anc; ++k) support |= 1u << A.L.anc_bits[k];
         }
     }
     if (ctx->plan) { cudaFree(ctx->plan); ctx->plan = nullptr; }
@@ -1084,13 +1088,17 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
     const std::vector<LayerArg2> &Ls2 = dense ? ctx->layers2d[which] : ctx->layers2[which];
     uint32_t nl = (uint32_t)Ls.size();
     if (max_layers && max_layers < nl) nl = max_layers;
-    if (!ctx->use_v1) {
+    {
         Scope s(ctx, CAT_OTHER);
         k_compact<<<1, 1024, 0, ctx->stream>>>(ctx->active, n, ctx->act_list, ctx->n_act);
     }
     for (uint32_t i = 0; i < nl; ++i) {
         Scope s(ctx, CAT_GATE);
-        if (ctx->use_v1)
+        if (Ls[i].L.n_anc == 4)
+            k_layer4<<<ctx->num_sms, kL4Threads, kL4Smem, ctx->stream>>>(
+                ctx->state, Ls2[i], ctx->ev, ctx->act_list, ctx->n_act, ctx->hist, ctx->counters, ctx->aux,
+                (i == 0) ? init_basis : -1);
+        else if (ctx->use_v1)
             k_layer<<<n * kTilesPerShot, kLayerThreads, kTile * 16, ctx->stream>>>(
                 ctx->state, Ls[i], ctx->ev, ctx->active, ctx->hist, ctx->counters, (i == 0) ? init_basis : -1);
         else

@@ -24,7 +24,7 @@ constexpr int kLayerThreads = 256;
 
 struct LayerArg {
     s17_layer L;
-    double2 prm[32];          // (cos, sin) of theta/2 for S17_U_ROT_* uops, layer-local indices
+    double2 prm[64];          // (cos, sin) of theta/2 for S17_U_ROT_* uops, layer-local indices
     uint8_t other_bits[5];    // the ancilla bits NOT staged in the tile, ascending
     uint8_t pad[3];
 };

@@ -45,15 +45,14 @@ struct PassC {
 
 struct LayerArg2 {
     LayerArg A;
-    OpC oc[8];
-    PassC pass[8];
+    OpC oc[S17_MAX_LAYER_OPS];
+    PassC pass[S17_MAX_LAYER_OPS];
     uint32_t n_pass;
     // support of the state before this sweep (ancilla bits that may be non-zero): tiles / runs outside it are
     // known to be exactly zero and are neither read nor written
     uint8_t tile_shift;      // log2(number of tiles of a shot inside the support)
-    uint8_t in_runs;         // bit r set: run r of a support tile may be non-zero on input
     uint8_t first;           // 1: first sweep after a measurement -> input is the surviving block (lazy collapse)
-    uint8_t pad0;
+    uint16_t in_runs;        // bit r set: run r of a support tile may be non-zero on input
     uint8_t tile_ids[32];
 };
 
@@ -121,7 +120,7 @@ __device__ __forceinline__ void apply_generic(double2 (&a)[16], const s17_op &op
         const s17_uop up = op.uops[u];
         if (up.skippable && skip) continue;
         const double sg = (double)up.sign;
-        const double2 p = prm[up.param & 31];
+        const double2 p = prm[up.param & 63];
         switch (up.type) {
         case S17_U_RY:     S17_FOR_QUADS(g_ry(v, sg)); break;
         case S17_U_RXX:    S17_FOR_QUADS(g_rxx(v, sg)); break;
@@ -163,7 +162,7 @@ __device__ __forceinline__ void apply_op(double2 (&a)[16], const LayerArg2 &P, i
     else apply_standard<OP2>(a, P.oc[o], w);
 }
 
-struct PassGeom { int p0, p1, p2, p3, m0, m1, m2, m3; };
+struct PassGeom { int p0, p1, p2, p3, m0, m1, m2, m3, n; };   // n = thread-items per pass (tile amplitudes / 16)
 
 // tile offsets of the 16 amplitudes a thread owns in a pass.  KIND 1: one item, four register bits
 // (op1 data, op1 ancilla, op2 data, op2 ancilla); KIND 0: four items, two register bits each.
@@ -177,7 +176,7 @@ __device__ __forceinline__ void item_offsets(const PassGeom &g, int item, int (&
     } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int i0 = insert0(insert0(4 * item + i, g.p0), g.p1);
+            const int i0 = insert0(insert0(item + g.n * i, g.p0), g.p1);   // consecutive lanes -> consecutive quads
 #pragma unroll
             for (int k = 0; k < 4; ++k) off[4 * i + k] = i0 + ((k & 1) ? g.m0 : 0) + ((k & 2) ? g.m1 : 0);
         }
@@ -397,6 +396,7 @@ k_layer2(double2 *__restrict__ state, const __grid_constant__ LayerArg2 P, const
             const bool fast = ps.kind != 2 && !(c1.generic | (ps.kind == 1 ? c2.generic : 0)) &&
                               !((w1 | w2) & 0x1FFFFFFu) && zm == 0;
             PassGeom g;
+            g.n = kTile / 16;
             if (ps.kind == 1) {
                 g.p0 = min(c1.lb0, c2.lb0); g.p1 = max(c1.lb0, c2.lb0);
                 g.p2 = min(c1.lb1, c2.lb1); g.p3 = max(c1.lb1, c2.lb1);

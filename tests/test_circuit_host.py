@@ -43,7 +43,7 @@ def test_leak_index_quirk_preserved():
             assert (o.d_leak, o.a_leak) == (o.data, 9 + o.ancilla)
 
 
-@pytest.mark.parametrize("fusion,n_layers", [(0, 54), (1, 8), (2, 4)])
+@pytest.mark.parametrize("fusion,n_layers", [(0, 54), (1, 8), (2, 4), (4, 2)])
 def test_program_shapes(error_models, fusion, n_layers):
     prog = circuit.compile_program(error_models["PDD_model"], [12, 18, 24, 78, 24], fusion=fusion)
     assert len(prog.layers[0]) == len(prog.layers[1]) == len(prog.layers[2]) == n_layers
@@ -52,7 +52,7 @@ def test_program_shapes(error_models, fusion, n_layers):
     assert [lay.emit_hist for lay in prog.layers[0]] == [0] * (n_layers - 1) + [1]
     for lay in prog.layers[0]:
         for op in lay.ops[:lay.n_ops]:
-            assert op.anc_bit in list(lay.anc_bits)
+            assert op.anc_bit in list(lay.anc_bits)[:lay.n_anc]
     errs = [p for p in prog.plan if p.kind == L.P_ERR]
     # 12 Rx x 2 + 18 Ry x 2 + 24 Rxx x 4 entries
     assert len(errs) == 12 * 2 + 18 * 2 + 24 * 4

@@ -31,7 +31,7 @@ def make_sim(models, ct, bt, model, list_len, n, fusion=1, cooling=False, **kw):
                           bitflip_table=bt, error_models=models, **kw)
 
 
-@pytest.mark.parametrize("fusion,dense", [(0, "0"), (1, "0"), (2, "0"), (2, "1"), (0, "1")])
+@pytest.mark.parametrize("fusion,dense", [(0, "0"), (1, "0"), (2, "0"), (4, "0"), (2, "1"), (0, "1"), (4, "1")])
 def test_golden_replays(error_models, correction_table, bitflip_table, golden, fusion, dense, monkeypatch):
     """Replayed reference trajectories (masks + forced outcomes): every record field bit-exact, and the
     post-correction state equals the reference's 512-amplitude block within 1e-10."""
@@ -60,8 +60,8 @@ def test_golden_replays(error_models, correction_table, bitflip_table, golden, f
         sim.close()
 
 
-@pytest.mark.parametrize("dense", ["0", "1"])
-def test_golden_replays_fast_path(error_models, correction_table, bitflip_table, golden, dense, monkeypatch):
+@pytest.mark.parametrize("dense,fusion", [("0", 2), ("1", 2), ("0", 4), ("0", 1)])
+def test_golden_replays_fast_path(error_models, correction_table, bitflip_table, golden, dense, fusion, monkeypatch):
     """Same replays through the production path (lazy collapse, correction folded into the read-out)."""
     monkeypatch.setenv("S17_DENSE", dense)
     reps = golden("replays.json")["replays"]
@@ -70,7 +70,7 @@ def test_golden_replays_fast_path(error_models, correction_table, bitflip_table,
         groups.setdefault((r["model"], r["protocol"], r["cooling"]), []).append(r)
     for (model, protocol, cooling), rs in groups.items():
         list_len = [len(x) for x in rs[0]["p_set"]]
-        sim = make_sim(error_models, correction_table, bitflip_table, model, list_len, len(rs), 2, cooling)
+        sim = make_sim(error_models, correction_table, bitflip_table, model, list_len, len(rs), fusion, cooling)
         sim.backend.set_replay([flat(r["p_set"]) for r in rs], [r["outcomes"] for r in rs])
         c = sim.backend.run(protocol, len(rs), L.NOISE_REPLAY, forced=True)
         assert c.errors == 0
@@ -105,7 +105,7 @@ def test_amplitudes_after_every_gate(error_models, correction_table, bitflip_tab
     sim.close()
 
 
-@pytest.mark.parametrize("fusion", [1, 2])
+@pytest.mark.parametrize("fusion", [1, 2, 4])
 def test_amplitudes_noisy_cycle_before_measurement(error_models, correction_table, bitflip_table, fusion):
     """Full state after the gates of a noisy cycle (Pauli events of every kind, leak skips, idle Z)."""
     rng = random.Random(99)
@@ -154,14 +154,15 @@ def test_amplitudes_noisy_cycle_before_measurement(error_models, correction_tabl
     ("Dress_cooling", "s2", True, [0, 0, 1, 2, 0, 3]),
     ("PDD_cooling", "single", True, [1, 1, 1, 1, 1, 2]),
 ])
+@pytest.mark.parametrize("fusion", [2, 4])
 def test_sampled_trajectories_replay_bit_exact_in_oracle(error_models, correction_table, bitflip_table, model,
-                                                         protocol, cooling, eset):
+                                                         protocol, cooling, eset, fusion):
     """Device-sampled shots (Philox placement + outcomes): replaying their masks and outcomes through the
     oracle reproduces syndromes, corrections, read-outs and pass/fail bit for bit."""
     per_round = circuit.list_lengths(error_models[model])
     locs = [2 * x for x in per_round] if protocol == "s2" else per_round
-    n = 48
-    sim = make_sim(error_models, correction_table, bitflip_table, model, locs, n, 2, cooling)
+    n = 32
+    sim = make_sim(error_models, correction_table, bitflip_table, model, locs, n, fusion, cooling)
     sim.backend.set_subset(eset, locs)
     c = sim.backend.run(protocol, n, L.NOISE_SUBSET, seed=1234, first_shot_id=77)
     recs, masks = sim.backend.records(n), sim.backend.masks(n)
@@ -278,11 +279,12 @@ def test_statistics_against_oracle_sampling(error_models, correction_table, bitf
     assert abs(f_gpu - f_cpu) < 3 * np.sqrt(f * (1 - f) * (1 / max(1, c.not0) + 1 / max(1, not0))) + 1e-9
 
 
-def test_coherent_overrotation_against_oracle(error_models, correction_table, bitflip_table):
+@pytest.mark.parametrize("fusion", [1, 4])
+def test_coherent_overrotation_against_oracle(error_models, correction_table, bitflip_table, fusion):
     """BASELINE config 3 (extension): deterministic over-rotations + stochastic XX, full-state parity."""
     eps1, eps2 = [0.02] * 30, [0.02] * 24
     n = 4
-    sim = make_sim(error_models, correction_table, bitflip_table, "coherent_model", [30, 24, 24], n, 1,
+    sim = make_sim(error_models, correction_table, bitflip_table, "coherent_model", [30, 24, 24], n, fusion,
                    over_angles={"eps_1q": eps1, "eps_2q": eps2})
     masks = []
     rng = random.Random(4)
