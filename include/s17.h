@@ -78,7 +78,9 @@ typedef struct {
     uint8_t n_ops;
     uint8_t n_anc;         /* 3: 4096-amplitude tiles (<= 8 ops), 4: 8192-amplitude tiles (<= 16 ops) */
     uint8_t anc_bits[4];   /* ancilla bits staged in shared memory next to the 9 data bits, ascending */
-    uint8_t emit_hist;     /* 1: also emit the 256-bin joint ancilla histogram (last sweep of a cycle) */
+    uint8_t meas_mask;     /* != 0: after this sweep the ancillas j with bit j set are measured (the sweep also emits the
+                              joint ancilla histogram).  0xFF on the last sweep = All(Measure) | ancilla (CS:848); a
+                              partial mask measures qubits no later gate touches earlier, which commutes */
     uint8_t pad;
     s17_op ops[S17_MAX_LAYER_OPS];
 } s17_layer;
@@ -154,7 +156,7 @@ typedef struct {
     uint32_t correction;      /* bits 0-8: X on data i; bits 9-17: Z on data i (CS:901-907) */
     uint32_t leak;            /* 17 leak flags (CS:286-288) */
     uint16_t data_meas;       /* after the leak override (CS:61-63) */
-    uint16_t pad;
+    uint16_t partial;         /* scratch: outcome bits of a cycle measured so far */
     uint8_t outcomes[S17_MAX_OUTCOMES];  /* raw measurement outcomes in program order */
 } s17_record;
 enum { S17_F_NOT0 = 1, S17_F_COUNTED = 2, S17_F_FAIL = 4, S17_F_ERROR = 8, S17_F_SYND2 = 16 };

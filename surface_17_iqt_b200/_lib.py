@@ -34,7 +34,7 @@ class Op(C.Structure):
 
 
 class Layer(C.Structure):
-    _fields_ = [("n_ops", C.c_uint8), ("n_anc", C.c_uint8), ("anc_bits", C.c_uint8 * 4), ("emit_hist", C.c_uint8),
+    _fields_ = [("n_ops", C.c_uint8), ("n_anc", C.c_uint8), ("anc_bits", C.c_uint8 * 4), ("meas_mask", C.c_uint8),
                 ("pad", C.c_uint8), ("ops", Op * 16)]
 
 
@@ -65,7 +65,7 @@ class Record(C.Structure):
     _fields_ = [("quiescent", C.c_uint8), ("synd1", C.c_uint8), ("synd2", C.c_uint8), ("flips_a", C.c_uint8),
                 ("ft_syndrome", C.c_uint8), ("flags", C.c_uint8), ("logical_meas", C.c_uint8),
                 ("n_outcomes", C.c_uint8), ("correction", C.c_uint32), ("leak", C.c_uint32),
-                ("data_meas", C.c_uint16), ("pad", C.c_uint16), ("outcomes", C.c_uint8 * MAX_OUTCOMES)]
+                ("data_meas", C.c_uint16), ("partial", C.c_uint16), ("outcomes", C.c_uint8 * MAX_OUTCOMES)]
 
 
 assert C.sizeof(Uop) == 8 and C.sizeof(Op) == 72 and C.sizeof(Layer) == 1160

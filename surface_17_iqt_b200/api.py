@@ -30,12 +30,14 @@ class Simulation:
     """Compiles `model` for probability lists of the given total lengths and owns the device context."""
 
     def __init__(self, model, list_len, max_shots, correction_table, bitflip_table, fusion=1, cooling=False,
-                 device=0, error_models=None, over_angles=None):
+                 device=0, error_models=None, over_angles=None, early_measure=None):
         models = error_models if error_models is not None else load_error_models()
         self.model_name = model
         self.model = models[model]
+        if early_measure is None:
+            early_measure = os.environ.get("S17_EARLY", "1") == "1"
         self.program = circuit.compile_program(self.model, list_len, fusion=fusion, cooling=cooling,
-                                               over_angles=over_angles)
+                                               over_angles=over_angles, early_measure=early_measure)
         self.backend = Backend(max_shots, device=device)
         self.backend.load_program(self.program)
         self.backend.load_tables(correction_table, bitflip_table)

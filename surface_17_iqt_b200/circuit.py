@@ -168,12 +168,15 @@ def _uop(type_, sign=0, skippable=0, ev_shift=255, param=0):
     return u
 
 
-def compile_program(model, list_len, fusion=1, cooling=False, over_angles=None) -> Program:
+def compile_program(model, list_len, fusion=1, cooling=False, over_angles=None, early_measure=False) -> Program:
     """Compile `model` (one entry of error_models.json) for lists of total length `list_len`.
 
     fusion: 0 = one sweep per gate (ProjectQ's execution model), 1 = one sweep per timestep,
             2 = one sweep per two timesteps, 4 = one sweep per four timesteps (8192-amplitude tiles).
     over_angles: {prob_name: [angles]} for the coherent ``*_over`` entries (extension, SURVEY C-10).
+    early_measure: measure the four X-type ancillas right after timestep 4 (no later gate touches them, so
+            this commutes with the rest of the cycle: same joint outcome statistics and the same collapsed
+            state up to a global sign) -- the Z-type half of the cycle then runs on a 2^13-amplitude support.
     """
     if fusion not in (0, 1, 2, 4):
         raise ValueError("fusion must be 0, 1, 2 or 4")
@@ -298,7 +301,7 @@ def compile_program(model, list_len, fusion=1, cooling=False, over_angles=None) 
         o.kind, o.ev_word = L.OP_IDLE, 24 + t
         return o
 
-    def make_layer(items, anc_bits, emit_hist=False):
+    def make_layer(items, anc_bits, meas_mask=0):
         lay = L.Layer()
         anc = sorted(set(anc_bits))
         n_anc = 4 if len(anc) > 3 else 3
@@ -314,13 +317,14 @@ def compile_program(model, list_len, fusion=1, cooling=False, over_angles=None) 
         lay.n_anc = n_anc
         for i, b in enumerate(anc):
             lay.anc_bits[i] = b
-        lay.emit_hist = int(emit_hist)
+        lay.meas_mask = int(meas_mask)
         for i, o in enumerate(items):
             lay.ops[i] = o
         return lay
 
     for cycle in (-1, 0, 1):                           # preparation, stab_ind=0, stab_ind=1
         layers = []
+        x_half_end = -1
         if fusion == 0:
             for t in range(8):
                 t_ops = [o for o in ops if o.timestep == t]
@@ -329,6 +333,8 @@ def compile_program(model, list_len, fusion=1, cooling=False, over_angles=None) 
                         layers.append(([make_op(op, cycle, only=pos)], [op.anc_bit]))
                 if cooling and t < 7:
                     layers[-1][0].append(idle_op(t))
+                if t == 3:
+                    x_half_end = len(layers) - 1
         else:
             step = fusion
             for t0 in range(0, 8, step):
@@ -340,5 +346,16 @@ def compile_program(model, list_len, fusion=1, cooling=False, over_angles=None) 
                     if cooling and t < 7:
                         items.append(idle_op(t))
                 layers.append((items, anc))
-        prog.layers.append([make_layer(it, an, emit_hist=(i == len(layers) - 1)) for i, (it, an) in enumerate(layers)])
+                if t0 + step == 4:
+                    x_half_end = len(layers) - 1
+        x_mask = sum(1 << a for a in {o.ancilla for o in ops if o.kind == "x"})          # ancillas 1, 3, 4, 6
+        built = []
+        for i, (it, an) in enumerate(layers):
+            mask = 0
+            if i == len(layers) - 1:
+                mask = (0xFF & ~x_mask) if early_measure else 0xFF
+            elif early_measure and i == x_half_end:
+                mask = x_mask
+            built.append(make_layer(it, an, meas_mask=mask))
+        prog.layers.append(built)
     return prog

@@ -178,7 +178,7 @@ k_layer(double2 *__restrict__ state, const __grid_constant__ LayerArg A, const u
         __syncthreads();
     }
 
-    if (A.L.emit_hist) {
+    if (A.L.meas_mask) {
         // joint ancilla histogram: warp w owns run w (one ancilla value, all 512 data amplitudes)
         const int wid = t >> 5, lane = t & 31;
         double acc = 0.0;
@@ -349,54 +349,87 @@ struct MeasArgs {
     int stage;        // 0 prep, 1 first noisy cycle, 2 second cycle
     int protocol;
     int forced;
+    uint32_t mask;    // ancillas measured by this call (bit j = ancilla j)
+    int final_part;   // 1: completes the cycle's All(Measure) | ancilla
     uint32_t stream;
     uint64_t seed, first_shot;
     int n_shots;
 };
 
-__global__ void k_measure(MeasArgs ma, const double *__restrict__ hist, const uint8_t *__restrict__ forced,
-                          const uint32_t *__restrict__ lut, uint32_t *__restrict__ leak, uint8_t *__restrict__ active,
-                          uint8_t *__restrict__ ready, ShotAux *__restrict__ aux, s17_record *__restrict__ rec,
-                          unsigned long long *__restrict__ counters)
+// one warp per shot: sample the ancillas in `mask` from the joint histogram, then (on the final part of a
+// cycle) apply the leak override and take the protocol's branch
+__global__ void __launch_bounds__(128)
+k_measure(MeasArgs ma, const double *__restrict__ hist, const uint8_t *__restrict__ forced,
+          const uint32_t *__restrict__ lut, uint32_t *__restrict__ leak, uint8_t *__restrict__ active,
+          uint8_t *__restrict__ ready, ShotAux *__restrict__ aux, s17_record *__restrict__ rec,
+          unsigned long long *__restrict__ counters)
 {
-    const int shot = blockIdx.x * blockDim.x + threadIdx.x;
+    const int shot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (shot >= ma.n_shots || !active[shot]) return;
     const double *h = hist + (size_t)shot * 256;
-    s17_record r = rec[shot];
+    // bins outside the measured set are not part of the support (their ancillas are reset to 0)
+    double hv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t m = lane + 32 * i;
+        hv[i] = (m & ~ma.mask) ? 0.0 : h[m];
+    }
+    const uint32_t nout = rec[shot].n_outcomes;
     Philox rng(ma.seed, ma.first_shot + shot, ma.stream);
-    uint32_t a = 0;
+    uint32_t a = 0, seen = 0;
     bool bad = false;
     // one Measure per ancilla in order (All(Measure) | ancilla, CS:848): conditional on earlier outcomes
     for (int j = 0; j < 8; ++j) {
+        if (!((ma.mask >> j) & 1u)) continue;
         double p0 = 0.0, p1 = 0.0;
-        const uint32_t lowmask = (1u << j) - 1u;
-        for (uint32_t m = 0; m < 256; ++m) {
-            if ((m & lowmask) != a) continue;
-            if ((m >> j) & 1u) p1 += h[m]; else p0 += h[m];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t m = lane + 32 * i;
+            if ((m & seen) != a) continue;
+            if ((m >> j) & 1u) p1 += hv[i]; else p0 += hv[i];
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            p0 += __shfl_xor_sync(0xffffffffu, p0, d);
+            p1 += __shfl_xor_sync(0xffffffffu, p1, d);
         }
         uint32_t out;
         if (ma.forced) {
-            out = forced[(size_t)shot * S17_MAX_OUTCOMES + r.n_outcomes] & 1u;
+            out = forced[(size_t)shot * S17_MAX_OUTCOMES + nout + j] & 1u;
             if ((out ? p1 : p0) <= 0.0) bad = true;
         } else {
-            out = (rng.next() * (p0 + p1) < p1) ? 1u : 0u;
+            double u = rng.next();
+            u = __shfl_sync(0xffffffffu, u, 0);
+            out = (u * (p0 + p1) < p1) ? 1u : 0u;
         }
-        if (r.n_outcomes < S17_MAX_OUTCOMES) r.outcomes[r.n_outcomes++] = (uint8_t)out;
         a |= out << j;
+        seen |= 1u << j;
     }
+    if (lane != 0) return;
+    s17_record r = rec[shot];
+    for (int j = 0; j < 8; ++j)
+        if (((ma.mask >> j) & 1u) && nout + j < S17_MAX_OUTCOMES) r.outcomes[nout + j] = (uint8_t)((a >> j) & 1u);
     const double pa = h[a];
     ShotAux ax;
     ax.scale = pa > 0.0 ? 1.0 / sqrt(pa) : 0.0;
-    ax.anc_outcome = a;
+    ax.anc_outcome = a;          // the surviving block; the ancillas measured earlier were already reset to 0
     ax.collapsed = 0;
     aux[shot] = ax;
+    if (bad) { r.flags |= S17_F_ERROR; atomicAdd(&counters[C_ERRORS], 1ull); }
+    const uint32_t all = r.partial | a;
+    if (!ma.final_part) {
+        r.partial = (uint16_t)all;
+        rec[shot] = r;
+        return;
+    }
+    r.partial = 0;
+    r.n_outcomes = (uint8_t)min(nout + 8u, (uint32_t)S17_MAX_OUTCOMES);
     // a leaked ancilla always reads 1 and is reset (CS:854-857)
     uint32_t lk = leak[shot];
-    const uint32_t synd = a | ((lk >> 9) & 0xFFu);
+    const uint32_t synd = all | ((lk >> 9) & 0xFFu);
     lk &= 0x1FFu;
     leak[shot] = lk;
     r.leak = lk;
-    if (bad) { r.flags |= S17_F_ERROR; atomicAdd(&counters[C_ERRORS], 1ull); }
 
     bool decode = false;
     if (ma.stage == 0) {
@@ -962,12 +995,17 @@ extern "C" int s17_load_program(s17_ctx *ctx, const s17_layer *layers, const uin
         ctx->layers2[c].clear();
         ctx->layers2d[c].clear();
         uint32_t support = 0;
+        bool first = true;
         for (size_t i = 0; i < ctx->layers[c].size(); ++i) {
             const LayerArg &A = ctx->layers[c][i];
-            ctx->layers2[c].push_back(make_layer2(A, support, i == 0, false));
-            ctx->layers2d[c].push_back(make_layer2(A, 0x1FE00u, i == 0, true));
+            ctx->layers2[c].push_back(make_layer2(A, support, first, false));
+            ctx->layers2d[c].push_back(make_layer2(A, 0x1FE00u, first, true));
             for (int k = 0; k < A.L.n_anc; ++k) support |= 1u << A.L.anc_bits[k];
+            first = false;
+            if (A.L.meas_mask) { support = 0; first = true; }     // measured + reset: the support collapses again
         }
+        if (ctx->layers[c].empty() || !ctx->layers[c].back().L.meas_mask)
+            return fail(ctx, S17_E_ARG, "the last sweep of a cycle must carry a measurement mask");
     }
     if (ctx->plan) { cudaFree(ctx->plan); ctx->plan = nullptr; }
     CK(cudaMalloc(&ctx->plan, n_plan * sizeof(s17_pinstr)));
@@ -1066,7 +1104,10 @@ extern "C" int s17_set_replay(s17_ctx *ctx, uint64_t n, const uint8_t *masks, ui
 static inline int blocks_for(uint64_t n, int per) { return (int)((n + per - 1) / per); }
 
 // one stabiliser cycle: plan -> gate sweeps -> ancilla measurement decisions
-static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second, int init_basis, uint32_t max_layers, bool dense) {
+static void collapse(s17_ctx *ctx, int n, const uint8_t *flag);
+
+static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second, int init_basis, uint32_t max_layers, bool dense,
+                     bool mid_collapse) {
     const int n = (int)a.n_shots;
     PlanArgs pa;
     pa.n_instr = ctx->n_plan;
@@ -1092,34 +1133,41 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
         Scope s(ctx, CAT_OTHER);
         k_compact<<<1, 1024, 0, ctx->stream>>>(ctx->active, n, ctx->act_list, ctx->n_act);
     }
-    for (uint32_t i = 0; i < nl; ++i) {
-        Scope s(ctx, CAT_GATE);
-        if (Ls[i].L.n_anc == 4)
-            k_layer4<<<ctx->num_sms, kL4Threads, kL4Smem, ctx->stream>>>(
-                ctx->state, Ls2[i], ctx->ev, ctx->act_list, ctx->n_act, ctx->hist, ctx->counters, ctx->aux,
-                (i == 0) ? init_basis : -1);
-        else if (ctx->use_v1)
-            k_layer<<<n * kTilesPerShot, kLayerThreads, kTile * 16, ctx->stream>>>(
-                ctx->state, Ls[i], ctx->ev, ctx->active, ctx->hist, ctx->counters, (i == 0) ? init_basis : -1);
-        else
-            k_layer2<<<ctx->num_sms, kL2Threads, kL2Smem, ctx->stream>>>(
-                ctx->state, Ls2[i], ctx->ev, ctx->act_list, ctx->n_act, ctx->hist, ctx->counters, ctx->aux, ctx->zero_page,
-                (i == 0) ? init_basis : -1);
-        ctx->n_gate++;
-    }
-    if (max_layers && max_layers < Ls.size()) return S17_OK;
     MeasArgs ma;
     ma.stage = stage;
     ma.protocol = (int)a.protocol;
     ma.forced = (int)a.forced;
-    ma.stream = 16u + (uint32_t)stage;
     ma.seed = a.seed;
     ma.first_shot = a.first_shot_id;
     ma.n_shots = n;
-    {
-        Scope s(ctx, CAT_MEAS);
-        k_measure<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(ma, ctx->hist, ctx->forced, ctx->lut, ctx->leak,
-                                                               ctx->active, ctx->ready, ctx->aux, ctx->rec, ctx->counters);
+    for (uint32_t i = 0; i < nl; ++i) {
+        {
+            Scope s(ctx, CAT_GATE);
+            if (Ls[i].L.n_anc == 4)
+                k_layer4<<<ctx->num_sms, kL4Threads, kL4Smem, ctx->stream>>>(
+                    ctx->state, Ls2[i], ctx->ev, ctx->act_list, ctx->n_act, ctx->hist, ctx->counters, ctx->aux,
+                    (i == 0) ? init_basis : -1);
+            else if (ctx->use_v1)
+                k_layer<<<n * kTilesPerShot, kLayerThreads, kTile * 16, ctx->stream>>>(
+                    ctx->state, Ls[i], ctx->ev, ctx->active, ctx->hist, ctx->counters, (i == 0) ? init_basis : -1);
+            else
+                k_layer2<<<ctx->num_sms, kL2Threads, kL2Smem, ctx->stream>>>(
+                    ctx->state, Ls2[i], ctx->ev, ctx->act_list, ctx->n_act, ctx->hist, ctx->counters, ctx->aux,
+                    ctx->zero_page, (i == 0) ? init_basis : -1);
+            ctx->n_gate++;
+        }
+        if (!Ls[i].L.meas_mask) continue;
+        const bool final_part = (i + 1 == Ls.size());
+        ma.mask = Ls[i].L.meas_mask;
+        ma.final_part = final_part ? 1 : 0;
+        ma.stream = 16u + (uint32_t)stage * 4u + (final_part ? 0u : 1u);
+        {
+            Scope s(ctx, CAT_MEAS);
+            k_measure<<<blocks_for((uint64_t)n * 32, 128), 128, 0, ctx->stream>>>(
+                ma, ctx->hist, ctx->forced, ctx->lut, ctx->leak, ctx->active, ctx->ready, ctx->aux, ctx->rec, ctx->counters);
+        }
+        // a partial measurement inside the cycle: materialise its collapse when the caller wants exact states
+        if (!final_part && mid_collapse) collapse(ctx, n, ctx->active);
     }
     return S17_OK;
 }
@@ -1138,12 +1186,12 @@ static int run_round(s17_ctx *ctx, const s17_run_args &a) {
     // cover the part of the state that can be non-zero.
     const bool dense = ctx->dense || ctx->use_v1;
     const bool explicit_collapse = dense || a.materialize || a.stop_stage != S17_STOP_NONE;
-    if (int rc = run_cycle(ctx, a, 0, 0, basis_index, 0, dense)) return rc;
+    if (int rc = run_cycle(ctx, a, 0, 0, basis_index, 0, dense, explicit_collapse)) return rc;
     if (explicit_collapse) collapse(ctx, n, ctx->active);
     if (a.stop_stage == S17_STOP_AFTER_PREP) return S17_OK;
     if (a.stop_stage == S17_STOP_CYCLE1_GATES)
-        return run_cycle(ctx, a, 1, 0, -1, a.stop_layers ? a.stop_layers : 1000, dense);
-    if (int rc = run_cycle(ctx, a, 1, 0, -1, 0, dense)) return rc;
+        return run_cycle(ctx, a, 1, 0, -1, a.stop_layers ? a.stop_layers : 1000, dense, explicit_collapse);
+    if (int rc = run_cycle(ctx, a, 1, 0, -1, 0, dense, explicit_collapse)) return rc;
     if (a.stop_stage == S17_STOP_AFTER_CYCLE1) {
         Scope s(ctx, CAT_OTHER);
         cudaMemsetAsync(ctx->active, 1, n, ctx->stream);
@@ -1153,7 +1201,7 @@ static int run_round(s17_ctx *ctx, const s17_run_args &a) {
     if (a.protocol == S17_PROTO_S2 || a.protocol == S17_PROTO_RTF) {
         if (explicit_collapse) collapse(ctx, n, ctx->active);
         // s2: stab_ind=1 slots (CL:422); run-til-fail: cycle B reuses the stab_ind=0 probabilities (CL:92)
-        if (int rc = run_cycle(ctx, a, 2, a.protocol == S17_PROTO_S2 ? 1 : 0, -1, 0, dense)) return rc;
+        if (int rc = run_cycle(ctx, a, 2, a.protocol == S17_PROTO_S2 ? 1 : 0, -1, 0, dense, explicit_collapse)) return rc;
     }
     if (a.materialize) {
         collapse(ctx, n, ctx->ready);

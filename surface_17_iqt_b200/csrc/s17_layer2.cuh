@@ -421,7 +421,7 @@ k_layer2(double2 *__restrict__ state, const __grid_constant__ LayerArg2 P, const
             group_barrier(grp);
         }
 
-        if (P.A.L.emit_hist) {
+        if (P.A.L.meas_mask) {
             // joint ancilla histogram: every warp of the group owns two runs (ancilla values) of the tile
 #pragma unroll
             for (int rr = 0; rr < 8 / (kGroupThreads / 32); ++rr) {

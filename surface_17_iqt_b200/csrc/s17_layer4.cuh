@@ -182,7 +182,7 @@ k_layer4(double2 *__restrict__ state, const __grid_constant__ LayerArg2 P, const
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
-        if (P.A.L.emit_hist) {
+        if (P.A.L.meas_mask) {
 #pragma unroll
             for (int rr = 0; rr < kRuns4 / (kL4Threads / 32); ++rr) {
                 const int run = warp + (kL4Threads / 32) * rr;

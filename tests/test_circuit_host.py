@@ -49,7 +49,10 @@ def test_program_shapes(error_models, fusion, n_layers):
     assert len(prog.layers[0]) == len(prog.layers[1]) == len(prog.layers[2]) == n_layers
     n_uops = sum(op.n_uops for lay in prog.layers[0] for op in lay.ops[:lay.n_ops])
     assert n_uops == 54
-    assert [lay.emit_hist for lay in prog.layers[0]] == [0] * (n_layers - 1) + [1]
+    assert [lay.meas_mask for lay in prog.layers[0]] == [0] * (n_layers - 1) + [0xFF]
+    early = circuit.compile_program(error_models["PDD_model"], [12, 18, 24, 78, 24], fusion=fusion, early_measure=True)
+    masks = [lay.meas_mask for lay in early.layers[1]]
+    assert [m for m in masks if m] == [0x5A, 0xA5] and masks[-1] == 0xA5
     for lay in prog.layers[0]:
         for op in lay.ops[:lay.n_ops]:
             assert op.anc_bit in list(lay.anc_bits)[:lay.n_anc]
