@@ -24,7 +24,7 @@ from . import api, circuit, distributed
 
 # knobs (module-level like the reference's scripts; no CLI)
 BATCH_SHOTS = int(os.environ.get("S17_BATCH", "4096"))    # shots resident per device context (2 MiB each)
-FUSION = int(os.environ.get("S17_FUSION", "4"))           # timesteps per sweep: 0 = one gate per sweep, 1, 2 or 4
+FUSION = int(os.environ.get("S17_FUSION", "2"))           # timesteps per sweep: 0 = one gate per sweep, 1, 2 or 4
 DEVICE = None                                             # None: LOCAL_RANK or 0
 VERBOSE = True                                            # print the reference's summary lines
 

@@ -24,6 +24,7 @@
 
 #include "s17_kernels.cuh"
 #include "s17_layer2.cuh"
+#include "s17_layer3.cuh"
 #include "s17_layer4.cuh"
 
 namespace s17 {
@@ -724,6 +725,7 @@ struct s17_ctx {
     std::vector<LayerArg2> layers2[3], layers2d[3];   // support-aware / dense variants
     double2 *zero_page = nullptr;
     bool dense = false;               // option: full-state sweeps + explicit collapse (ProjectQ-equivalent traffic)
+    bool force_ring = false;          // option: use the TMA-ring kernel (k_layer2) for support-aware sweeps as well
     uint32_t *act_list = nullptr, *n_act = nullptr;
     int num_sms = 148;
     bool use_v1 = false;
@@ -813,6 +815,7 @@ extern "C" int s17_create(s17_ctx **out, int device, uint64_t max_shots) {
     CK(cudaFuncSetAttribute(k_layer, cudaFuncAttributeMaxDynamicSharedMemorySize, kTile * 16));
     CK(cudaFuncSetAttribute(k_layer2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kL2Smem));
     CK(cudaFuncSetAttribute(k_layer4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kL4Smem));
+    CK(cudaFuncSetAttribute(k_layer3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kL3Smem));
     CK(cudaMalloc(&ctx->act_list, B * 4));
     CK(cudaMalloc(&ctx->n_act, 4));
     CK(cudaMalloc(&ctx->zero_page, kRunBytes));
@@ -820,6 +823,8 @@ extern "C" int s17_create(s17_ctx **out, int device, uint64_t max_shots) {
     {
         const char *d = getenv("S17_DENSE");
         ctx->dense = d && d[0] == '1';
+        const char *r = getenv("S17_RING");
+        ctx->force_ring = r && r[0] == '1';
     }
     {
         cudaDeviceProp prop;
@@ -1150,6 +1155,10 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
             else if (ctx->use_v1)
                 k_layer<<<n * kTilesPerShot, kLayerThreads, kTile * 16, ctx->stream>>>(
                     ctx->state, Ls[i], ctx->ev, ctx->active, ctx->hist, ctx->counters, (i == 0) ? init_basis : -1);
+            else if (!dense && !ctx->force_ring)
+                k_layer3<<<ctx->num_sms * kL3CtasPerSm, kL3Threads, kL3Smem, ctx->stream>>>(
+                    ctx->state, Ls2[i], ctx->ev, ctx->act_list, ctx->n_act, ctx->hist, ctx->counters, ctx->aux,
+                    (i == 0) ? init_basis : -1);
             else
                 k_layer2<<<ctx->num_sms, kL2Threads, kL2Smem, ctx->stream>>>(
                     ctx->state, Ls2[i], ctx->ev, ctx->act_list, ctx->n_act, ctx->hist, ctx->counters, ctx->aux,
