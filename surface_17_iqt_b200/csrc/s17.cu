@@ -13,6 +13,7 @@
 //   k_pauli    : apply_correction (CS:901-907)
 //   k_readout  : logical_measurement (CS:52-93) + failure tally (CL:329-330, 433-434)
 // There is NO CPU fallback in this library.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -724,6 +725,7 @@ struct s17_ctx {
     std::vector<LayerArg> layers[3];   // prep, first noisy cycle, second noisy cycle
     std::vector<LayerArg2> layers2[3], layers2d[3];   // support-aware / dense variants
     double2 *zero_page = nullptr;
+    CUtensorMap tmap;                 // the state as rows of 128 B, 8 KiB boxes, 128-byte swizzle (k_layer3)
     bool dense = false;               // option: full-state sweeps + explicit collapse (ProjectQ-equivalent traffic)
     bool force_ring = false;          // option: use the TMA-ring kernel (k_layer2) for support-aware sweeps as well
     uint32_t *act_list = nullptr, *n_act = nullptr;
@@ -818,6 +820,23 @@ extern "C" int s17_create(s17_ctx **out, int device, uint64_t max_shots) {
     CK(cudaFuncSetAttribute(k_layer3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kL3Smem));
     CK(cudaMalloc(&ctx->act_list, B * 4));
     CK(cudaMalloc(&ctx->n_act, 4));
+    {
+        typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) return fail(ctx, S17_E_CUDA, "cuTensorMapEncodeTiled is not available");
+        const cuuint64_t dims[2] = {16, (cuuint64_t)B * (kDim / 8)};       // 16 doubles = 8 amplitudes = 128 B per row
+        const cuuint64_t strides[1] = {128};
+        const cuuint32_t box[2] = {16, kRun / 8};                          // one run: 64 rows = 8 KiB
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult r = ((EncodeFn)fn)(&ctx->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, ctx->state, dims, strides, box, estr,
+                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(ctx, S17_E_CUDA, "cuTensorMapEncodeTiled failed");
+    }
     CK(cudaMalloc(&ctx->zero_page, kRunBytes));
     CK(cudaMemset(ctx->zero_page, 0, kRunBytes));
     {
@@ -961,6 +980,29 @@ static LayerArg2 make_layer2(const LayerArg &A, uint32_t support /* ancilla bits
     flush();
     if (last_gate_pass >= 0) P.pass[last_gate_pass].last = 1;
     P.n_pass = (uint32_t)np;
+    // lane mapping for the 128B-swizzled layout: a quarter warp must hit 8 different 16-byte columns.  Column bit k
+    // of the swizzled index is idx[k] ^ idx[k+3], so the three lowest item bits go to positions k, or k+3 when k is
+    // held in registers by this pass.
+    const int tile_bits = 9 + n_anc;
+    for (int q = 0; q < np; ++q) {
+        PassC &ps = P.pass[q];
+        bool removed[16] = {false};
+        if (ps.kind != 2) { removed[P.oc[ps.o1].lb0] = removed[P.oc[ps.o1].lb1] = true; }
+        else { removed[0] = removed[9] = true; }
+        if (ps.kind == 1) { removed[P.oc[ps.o2].lb0] = removed[P.oc[ps.o2].lb1] = true; }
+        bool used[16] = {false};
+        int n = 0;
+        for (int k = 0; k < 3; ++k) {
+            int pos = !removed[k] ? k : (!removed[k + 3] && !used[k + 3] ? k + 3 : -1);
+            if (pos < 0 || used[pos]) {                          // unavoidable conflict: take any free bit
+                for (pos = 0; pos < tile_bits && (removed[pos] || used[pos]); ++pos) {}
+            }
+            used[pos] = true;
+            ps.pos[n++] = (uint8_t)pos;
+        }
+        for (int b = 0; b < tile_bits; ++b)
+            if (!removed[b] && !used[b] && n < 12) { used[b] = true; ps.pos[n++] = (uint8_t)b; }
+    }
     return P;
 }
 
@@ -1157,7 +1199,7 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
                     ctx->state, Ls[i], ctx->ev, ctx->active, ctx->hist, ctx->counters, (i == 0) ? init_basis : -1);
             else if (!dense && !ctx->force_ring)
                 k_layer3<<<ctx->num_sms * kL3CtasPerSm, kL3Threads, kL3Smem, ctx->stream>>>(
-                    ctx->state, Ls2[i], ctx->ev, ctx->act_list, ctx->n_act, ctx->hist, ctx->counters, ctx->aux,
+                    ctx->tmap, Ls2[i], ctx->ev, ctx->act_list, ctx->n_act, ctx->hist, ctx->counters, ctx->aux,
                     (i == 0) ? init_basis : -1);
             else
                 k_layer2<<<ctx->num_sms, kL2Threads, kL2Smem, ctx->stream>>>(

@@ -41,6 +41,9 @@ struct PassC {
     uint8_t idle_word;       // 255: none; else event word holding a 17-bit Z mask applied after the pass
     uint8_t last;            // 1: last pass with gates -> applies the deferred scale
     uint8_t pad[3];
+    // bank-conflict-free lane mapping for the 128B-swizzled tile layout (k_layer3): item bit k -> tile-local bit
+    // pos[k]; the three lowest item bits (a quarter warp) land on bits whose swizzled 16-byte columns differ
+    uint8_t pos[12];
 };
 
 struct LayerArg2 {
@@ -164,6 +167,34 @@ __device__ __forceinline__ void apply_op(double2 (&a)[16], const LayerArg2 &P, i
 
 struct PassGeom { int p0, p1, p2, p3, m0, m1, m2, m3, n; };   // n = thread-items per pass (tile amplitudes / 16)
 
+// 128-byte TMA swizzle expressed on amplitude (16-byte) indices: chunk bits 0-2 are XORed with row bits 3-5
+__device__ __forceinline__ int swz(int idx) { return idx ^ ((idx >> 3) & 7); }
+
+// swizzled-layout variant of item_offsets: deposits the item bits at PassC::pos and returns PHYSICAL offsets
+template <int KIND>
+__device__ __forceinline__ void item_offsets_swz(const PassGeom &g, const PassC &ps, int item, int (&off)[16]) {
+    const int nb = 31 - __clz(g.n);                 // item bits (8 for 4096-amplitude tiles)
+    int i0 = 0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+        if (k < nb) i0 |= ((item >> k) & 1) << ps.pos[k];
+    i0 = swz(i0);
+    if (KIND == 1) {
+        const int q0 = swz(g.m0), q1 = swz(g.m1), q2 = swz(g.m2), q3 = swz(g.m3);
+#pragma unroll
+        for (int r = 0; r < 16; ++r)
+            off[r] = i0 ^ ((r & 1) ? q0 : 0) ^ ((r & 2) ? q1 : 0) ^ ((r & 4) ? q2 : 0) ^ ((r & 8) ? q3 : 0);
+    } else {
+        const int q0 = swz(g.m0), q1 = swz(g.m1);
+        const int e0 = swz(1 << ps.pos[nb]), e1 = swz(1 << ps.pos[nb + 1]);    // the two quad-index bits
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                off[4 * i + k] = i0 ^ ((i & 1) ? e0 : 0) ^ ((i & 2) ? e1 : 0) ^ ((k & 1) ? q0 : 0) ^ ((k & 2) ? q1 : 0);
+    }
+}
+
 // tile offsets of the 16 amplitudes a thread owns in a pass.  KIND 1: one item, four register bits
 // (op1 data, op1 ancilla, op2 data, op2 ancilla); KIND 0: four items, two register bits each.
 template <int KIND>
@@ -208,12 +239,18 @@ __device__ __forceinline__ void fast_item(double2 *tile, const PassGeom &g, int 
 
 // everything else (Pauli events, leak-skipped Rxx, idle Z masks, coherent rotations): rare, kept out of line
 __device__ __noinline__ void slow_item(double2 *tile, const LayerArg2 *Pp, const PassC ps, const PassGeom g, int item,
-                                       uint32_t w1, uint32_t w2, uint32_t zm, uint32_t lm, uint32_t c0, double sc) {
+                                       uint32_t w1, uint32_t w2, uint32_t zm, uint32_t lm, uint32_t c0, double sc,
+                                       bool swizzled = false) {
     const LayerArg2 &P = *Pp;
     double2 a[16];
     int off[16];
-    if (ps.kind == 1) item_offsets<1>(g, item, off);
-    else item_offsets<0>(g, item, off);
+    if (swizzled) {
+        if (ps.kind == 1) item_offsets_swz<1>(g, ps, item, off);
+        else item_offsets_swz<0>(g, ps, item, off);
+    } else {
+        if (ps.kind == 1) item_offsets<1>(g, item, off);
+        else item_offsets<0>(g, item, off);
+    }
 #pragma unroll
     for (int r = 0; r < 16; ++r) a[r] = tile[off[r]];
     if (ps.kind == 1) {
@@ -224,8 +261,10 @@ __device__ __noinline__ void slow_item(double2 *tile, const LayerArg2 *Pp, const
     }
     if (zm) {
 #pragma unroll
-        for (int r = 0; r < 16; ++r)
-            if ((__popc(off[r] & lm) & 1u) ^ c0) a[r] = make_double2(-a[r].x, -a[r].y);
+        for (int r = 0; r < 16; ++r) {
+            const int logical = swizzled ? swz(off[r]) : off[r];       // the swizzle is an involution
+            if ((__popc(logical & lm) & 1u) ^ c0) a[r] = make_double2(-a[r].x, -a[r].y);
+        }
     }
 #pragma unroll
     for (int r = 0; r < 16; ++r) tile[off[r]] = make_double2(a[r].x * sc, a[r].y * sc);

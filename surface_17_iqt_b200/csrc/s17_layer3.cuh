@@ -7,6 +7,8 @@
 // doing math; the TMA load / store latency of one CTA hides behind the math of the other two.
 // (k_layer2 remains the kernel for dense, HBM-bound sweeps: S17_DENSE=1.)
 #pragma once
+#include <cuda.h>
+
 #include "s17_layer2.cuh"
 
 namespace s17 {
@@ -15,6 +17,20 @@ constexpr int kL3Threads = 128;
 constexpr int kL3CtasPerSm = 3;
 constexpr size_t kL3Smem = (size_t)kTile * 16 + kEvBytes + kAuxBytes + 64;
 
+// 2-D tensor-map TMA of one 8 KiB run (64 rows x 128 B) with the hardware 128-byte swizzle
+__device__ __forceinline__ void tma_load_run(void *dst_smem, const CUtensorMap *tm, int row, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(tm), "r"(0), "r"(row), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_run(const CUtensorMap *tm, int row, const void *src_smem) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tm), "r"(0),
+                 "r"(row), "r"(smem_u32(src_smem))
+                 : "memory");
+}
+
 // x-type operations (timesteps 1-4) have no Ry: two gate slots instead of four
 template <bool OP2>
 __device__ __forceinline__ void apply_fast_x(double2 (&a)[16], double s, double sx) {
@@ -22,11 +38,11 @@ __device__ __forceinline__ void apply_fast_x(double2 (&a)[16], double s, double 
 }
 
 template <int KIND, bool XONLY>
-__device__ __forceinline__ void fast_item3(double2 *tile, const PassGeom &g, int item, const FastC f1, const FastC f2,
-                                           double sc) {
+__device__ __forceinline__ void fast_item3(double2 *tile, const PassGeom &g, const PassC &ps, int item, const FastC f1,
+                                           const FastC f2, double sc) {
     double2 a[16];
     int off[16];
-    item_offsets<KIND>(g, item, off);
+    item_offsets_swz<KIND>(g, ps, item, off);
 #pragma unroll
     for (int r = 0; r < 16; ++r) a[r] = tile[off[r]];
     if (XONLY) {
@@ -41,7 +57,7 @@ __device__ __forceinline__ void fast_item3(double2 *tile, const PassGeom &g, int
 }
 
 __global__ void __launch_bounds__(kL3Threads, kL3CtasPerSm)
-k_layer3(double2 *__restrict__ state, const __grid_constant__ LayerArg2 P, const uint32_t *__restrict__ ev,
+k_layer3(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ LayerArg2 P, const uint32_t *__restrict__ ev,
          const uint32_t *__restrict__ act_list, const uint32_t *__restrict__ n_act_ptr, double *__restrict__ hist,
          unsigned long long *__restrict__ counters, const ShotAux *__restrict__ aux, int init_basis)
 {
@@ -76,7 +92,7 @@ k_layer3(double2 *__restrict__ state, const __grid_constant__ LayerArg2 P, const
         uint32_t base = 0;
 #pragma unroll
         for (int k = 0; k < 5; ++k) base |= ((tile_id >> k) & 1u) << P.A.other_bits[k];
-        double2 *sbase = state + (size_t)shot * kDim;
+        const int row0 = (int)(shot * (uint32_t)(kDim / 8));       // tensor-map row (8 amplitudes = 128 B) of the shot
 
         if (t == 0) {
             mbar_expect_tx(full, n_load * kRunBytes + kEvBytes + kAuxBytes);
@@ -84,14 +100,14 @@ k_layer3(double2 *__restrict__ state, const __grid_constant__ LayerArg2 P, const
                 // lazy collapse + reset: the only non-zero input is the surviving 512-amplitude block
                 const ShotAux ax = aux[shot];
                 const uint32_t blk = ax.collapsed ? 0u : ax.anc_outcome;
-                tma_load_1d(tile, sbase + (size_t)blk * kRun, kRunBytes, full);
+                tma_load_run(tile, &tmap, row0 + (int)blk * (kRun / 8), full);
             } else {
                 for (int r = 0; r < 8; ++r) {
                     if (!((load_mask >> r) & 1u)) continue;
                     uint32_t g = base;
 #pragma unroll
                     for (int k = 0; k < 3; ++k) g |= ((r >> k) & 1u) << P.A.L.anc_bits[k];
-                    tma_load_1d(tile + r * kRun, sbase + g, kRunBytes, full);
+                    tma_load_run(tile + r * kRun, &tmap, row0 + (int)(g >> 3), full);
                 }
             }
             tma_load_1d(evw, ev + (size_t)shot * S17_EV_WORDS, kEvBytes, full);
@@ -104,7 +120,7 @@ k_layer3(double2 *__restrict__ state, const __grid_constant__ LayerArg2 P, const
             for (int i = 0; i < kRun / kL3Threads; ++i) tile[r * kRun + t + kL3Threads * i] = make_double2(0.0, 0.0);
         }
         mbar_wait(full, j & 1);
-        if (init_basis >= 0 && tile_id == 0 && t == 0) tile[init_basis] = make_double2(1.0, 0.0);
+        if (init_basis >= 0 && tile_id == 0 && t == 0) tile[swz(init_basis)] = make_double2(1.0, 0.0);
         __syncthreads();
 
         // deferred 2^(-n/2): count the 1/sqrt2 gates this shot really executes in this layer
@@ -118,7 +134,7 @@ k_layer3(double2 *__restrict__ state, const __grid_constant__ LayerArg2 P, const
         if (P.first && init_basis < 0 && !auxs->collapsed) scale *= auxs->scale;   // renormalisation of the lazy collapse
 
         for (uint32_t p = 0; p < P.n_pass; ++p) {
-            const PassC ps = P.pass[p];
+            const PassC &ps = P.pass[p];
             uint32_t zm = 0, lm = 0, c0 = 0;
             if (ps.idle_word != 255) {
                 // Z on every qubit whose bit is set in the 17-bit idle mask (sympathetic_cooling, CS:762-772)
@@ -153,17 +169,17 @@ k_layer3(double2 *__restrict__ state, const __grid_constant__ LayerArg2 P, const
                 for (int it = 0; it < kTile / 16 / kL3Threads; ++it) {
                     const int item_t = t + kL3Threads * it;
                     if (ps.kind == 1) {
-                        if (xonly) fast_item3<1, true>(tile, g, item_t, f1, f2, sc);
-                        else fast_item3<1, false>(tile, g, item_t, f1, f2, sc);
+                        if (xonly) fast_item3<1, true>(tile, g, ps, item_t, f1, f2, sc);
+                        else fast_item3<1, false>(tile, g, ps, item_t, f1, f2, sc);
                     } else {
-                        if (xonly) fast_item3<0, true>(tile, g, item_t, f1, f2, sc);
-                        else fast_item3<0, false>(tile, g, item_t, f1, f2, sc);
+                        if (xonly) fast_item3<0, true>(tile, g, ps, item_t, f1, f2, sc);
+                        else fast_item3<0, false>(tile, g, ps, item_t, f1, f2, sc);
                     }
                 }
             } else {
 #pragma unroll 1
                 for (int it = 0; it < kTile / 16 / kL3Threads; ++it)
-                    slow_item(tile, &P, ps, g, t + kL3Threads * it, w1, w2, zm, lm, c0, sc);
+                    slow_item(tile, &P, ps, g, t + kL3Threads * it, w1, w2, zm, lm, c0, sc, true);
             }
             __syncthreads();
         }
@@ -176,7 +192,7 @@ k_layer3(double2 *__restrict__ state, const __grid_constant__ LayerArg2 P, const
                 uint32_t g = base;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) g |= ((r >> k) & 1u) << P.A.L.anc_bits[k];
-                tma_store_1d(sbase + g, tile + r * kRun, kRunBytes);
+                tma_store_run(&tmap, row0 + (int)(g >> 3), tile + r * kRun);
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
