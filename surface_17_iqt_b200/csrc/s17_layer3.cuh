@@ -15,7 +15,7 @@ namespace s17 {
 
 constexpr int kL3Threads = 128;
 constexpr int kL3CtasPerSm = 3;
-constexpr size_t kL3Smem = (size_t)kTile * 16 + kEvBytes + kAuxBytes + 64;
+constexpr size_t kL3Smem = (size_t)kTile * 16 + 2 * (kEvBytes + kAuxBytes) + 64;
 
 // 2-D tensor-map TMA of one 8 KiB run (64 rows x 128 B) with the hardware 128-byte swizzle
 __device__ __forceinline__ void tma_load_run(void *dst_smem, const CUtensorMap *tm, int row, uint64_t *bar) {
@@ -37,7 +37,7 @@ __device__ __forceinline__ void apply_fast_x(double2 (&a)[16], double s, double 
     S17_FOR_QUADS(g_rxx(v, s); g_rx(v, sx));
 }
 
-template <int KIND, bool XONLY>
+template <int KIND, bool XONLY, bool SCALE>
 __device__ __forceinline__ void fast_item3(double2 *tile, const PassGeom &g, const PassC &ps, int item, const FastC f1,
                                            const FastC f2, double sc) {
     double2 a[16];
@@ -53,7 +53,17 @@ __device__ __forceinline__ void fast_item3(double2 *tile, const PassGeom &g, con
         if (KIND == 1) apply_fast<true>(a, f2.v1, f2.s, f2.sx, f2.v2);
     }
 #pragma unroll
-    for (int r = 0; r < 16; ++r) tile[off[r]] = make_double2(a[r].x * sc, a[r].y * sc);
+    for (int r = 0; r < 16; ++r) tile[off[r]] = SCALE ? make_double2(a[r].x * sc, a[r].y * sc) : a[r];
+}
+
+template <int KIND, bool XONLY>
+__device__ __forceinline__ void fast_pass3(double2 *tile, const PassGeom &g, const PassC &ps, int t, const FastC f1,
+                                           const FastC f2, double sc, bool scale) {
+#pragma unroll 1
+    for (int it = 0; it < kTile / 16 / kL3Threads; ++it) {
+        if (scale) fast_item3<KIND, XONLY, true>(tile, g, ps, t + kL3Threads * it, f1, f2, sc);
+        else fast_item3<KIND, XONLY, false>(tile, g, ps, t + kL3Threads * it, f1, f2, sc);
+    }
 }
 
 __global__ void __launch_bounds__(kL3Threads, kL3CtasPerSm)
@@ -63,9 +73,10 @@ k_layer3(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Layer
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     double2 *tile = reinterpret_cast<double2 *>(smem_raw);
-    uint32_t *evw = reinterpret_cast<uint32_t *>(smem_raw + (size_t)kTile * 16);
-    ShotAux *auxs = reinterpret_cast<ShotAux *>(smem_raw + (size_t)kTile * 16 + kEvBytes);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kTile * 16 + kEvBytes + kAuxBytes);
+    uint32_t *evw2 = reinterpret_cast<uint32_t *>(smem_raw + (size_t)kTile * 16);                 // [2][32]
+    ShotAux *auxs2 = reinterpret_cast<ShotAux *>(smem_raw + (size_t)kTile * 16 + 2 * kEvBytes);   // [2]
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kTile * 16 + 2 * (kEvBytes + kAuxBytes));
+    uint64_t *meta = full + 1;                                                                   // [2]
 
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const uint32_t n_items = (*n_act_ptr) << P.tile_shift;
@@ -77,9 +88,19 @@ k_layer3(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Layer
 
     if (t == 0) {
         mbar_init(full, 1);
+        mbar_init(&meta[0], 1);
+        mbar_init(&meta[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // per-shot metadata (event words, collapse record) is prefetched one tile ahead
+    auto prefetch_meta = [&](uint32_t shot_, int slot) {
+        mbar_expect_tx(&meta[slot], kEvBytes + kAuxBytes);
+        tma_load_1d(evw2 + slot * S17_EV_WORDS, ev + (size_t)shot_ * S17_EV_WORDS, kEvBytes, &meta[slot]);
+        tma_load_1d(auxs2 + slot, aux + shot_, kAuxBytes, &meta[slot]);
+    };
+    uint32_t shot_next = act_list[first >> P.tile_shift];
+    if (t == 0) prefetch_meta(shot_next, 0);
 
     // which runs of a tile are read from HBM; everything else is known to be zero on input
     const uint32_t load_mask = init_basis >= 0 ? 0u : (P.first ? 1u : (uint32_t)P.in_runs);
@@ -87,19 +108,23 @@ k_layer3(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Layer
 
     for (uint32_t item = first; item < last; ++item) {
         const uint32_t j = item - first;
-        const uint32_t shot = act_list[item >> P.tile_shift];
+        const uint32_t shot = shot_next;
+        if (item + 1 < last) shot_next = act_list[(item + 1) >> P.tile_shift];     // consumed next iteration
+        const int slot = j & 1;
+        const uint32_t *evw = evw2 + slot * S17_EV_WORDS;
+        const ShotAux *auxs = auxs2 + slot;
         const int tile_id = P.tile_ids[item & tile_mask];
         uint32_t base = 0;
 #pragma unroll
         for (int k = 0; k < 5; ++k) base |= ((tile_id >> k) & 1u) << P.A.other_bits[k];
         const int row0 = (int)(shot * (uint32_t)(kDim / 8));       // tensor-map row (8 amplitudes = 128 B) of the shot
 
+        mbar_wait(&meta[slot], (j >> 1) & 1);
         if (t == 0) {
-            mbar_expect_tx(full, n_load * kRunBytes + kEvBytes + kAuxBytes);
+            if (n_load) mbar_expect_tx(full, n_load * kRunBytes);
             if (P.first && init_basis < 0) {
                 // lazy collapse + reset: the only non-zero input is the surviving 512-amplitude block
-                const ShotAux ax = aux[shot];
-                const uint32_t blk = ax.collapsed ? 0u : ax.anc_outcome;
+                const uint32_t blk = auxs->collapsed ? 0u : auxs->anc_outcome;
                 tma_load_run(tile, &tmap, row0 + (int)blk * (kRun / 8), full);
             } else {
                 for (int r = 0; r < 8; ++r) {
@@ -110,8 +135,7 @@ k_layer3(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Layer
                     tma_load_run(tile + r * kRun, &tmap, row0 + (int)(g >> 3), full);
                 }
             }
-            tma_load_1d(evw, ev + (size_t)shot * S17_EV_WORDS, kEvBytes, full);
-            tma_load_1d(auxs, aux + shot, kAuxBytes, full);
+            if (item + 1 < last) prefetch_meta(shot_next, slot ^ 1);
         }
         // zero-fill the runs that are not loaded (disjoint from the TMA destinations)
         for (int r = 0; r < 8; ++r) {
@@ -119,16 +143,16 @@ k_layer3(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Layer
 #pragma unroll
             for (int i = 0; i < kRun / kL3Threads; ++i) tile[r * kRun + t + kL3Threads * i] = make_double2(0.0, 0.0);
         }
-        mbar_wait(full, j & 1);
+        if (n_load) mbar_wait(full, j & 1);
         if (init_basis >= 0 && tile_id == 0 && t == 0) tile[swz(init_basis)] = make_double2(1.0, 0.0);
         __syncthreads();
 
         // deferred 2^(-n/2): count the 1/sqrt2 gates this shot really executes in this layer
+        const uint32_t skips = __ballot_sync(0xffffffffu, (evw[lane] >> 24) & 1u);    // bit w: op word w is leak-skipped
         int nsc = 0;
         for (int o = 0; o < P.A.L.n_ops; ++o) {
             if (P.A.L.ops[o].kind != S17_OP_ENT) continue;
-            const uint32_t skip = (evw[P.oc[o].ev_word] >> 24) & 1u;
-            nsc += P.oc[o].n_fixed + (skip ? 0 : P.oc[o].n_skip);
+            nsc += P.oc[o].n_fixed + (((skips >> P.oc[o].ev_word) & 1u) ? 0 : P.oc[o].n_skip);
         }
         double scale = ldexp((nsc & 1) ? 0.70710678118654752440 : 1.0, -(nsc >> 1));
         if (P.first && init_basis < 0 && !auxs->collapsed) scale *= auxs->scale;   // renormalisation of the lazy collapse
@@ -165,16 +189,13 @@ k_layer3(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Layer
             // 256 items per pass, two per thread
             if (fast) {
                 const FastC f1 = fast_coeffs(c1), f2 = fast_coeffs(c2);
-#pragma unroll 1
-                for (int it = 0; it < kTile / 16 / kL3Threads; ++it) {
-                    const int item_t = t + kL3Threads * it;
-                    if (ps.kind == 1) {
-                        if (xonly) fast_item3<1, true>(tile, g, ps, item_t, f1, f2, sc);
-                        else fast_item3<1, false>(tile, g, ps, item_t, f1, f2, sc);
-                    } else {
-                        if (xonly) fast_item3<0, true>(tile, g, ps, item_t, f1, f2, sc);
-                        else fast_item3<0, false>(tile, g, ps, item_t, f1, f2, sc);
-                    }
+                const bool scale = ps.last && sc != 1.0;
+                if (ps.kind == 1) {
+                    if (xonly) fast_pass3<1, true>(tile, g, ps, t, f1, f2, sc, scale);
+                    else fast_pass3<1, false>(tile, g, ps, t, f1, f2, sc, scale);
+                } else {
+                    if (xonly) fast_pass3<0, true>(tile, g, ps, t, f1, f2, sc, scale);
+                    else fast_pass3<0, false>(tile, g, ps, t, f1, f2, sc, scale);
                 }
             } else {
 #pragma unroll 1
@@ -200,12 +221,13 @@ k_layer3(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Layer
 #pragma unroll
             for (int rr = 0; rr < 8 / (kL3Threads / 32); ++rr) {
                 const int run = warp + (kL3Threads / 32) * rr;
-                double acc = 0.0;
+                double acc4[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
                 for (int i = 0; i < kRun / 32; ++i) {
                     const double2 v = tile[run * kRun + lane + 32 * i];
-                    acc = fma(v.x, v.x, fma(v.y, v.y, acc));
+                    acc4[i & 3] = fma(v.x, v.x, fma(v.y, v.y, acc4[i & 3]));
                 }
+                double acc = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
 #pragma unroll
                 for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
                 if (lane == 0) {
