@@ -14,7 +14,7 @@ only exchange is one all-reduce of the counters at the end (inside the timed reg
 `e2e`    : the same through the reference-shaped Python entry point
            surface_17_iqt_b200.calc_log_e_rate_arbitrary_error_model.s2_calculate_log_e_rate_error_subset
            with host inputs and host results, wall-clock around the calls.
-`roofline`: the gate sweep kernel k_layer2: algorithmic bytes = the 8 KiB amplitude runs it really reads and
+`roofline`: the gate sweep kernel (k_layer3 in the default support-aware schedule): algorithmic bytes = the 8 KiB amplitude runs it really reads and
            writes (a dense sweep is 2 MiB read + 2 MiB write per shot; regions of the state that are exactly zero
            after an ancilla reset are skipped unless S17_DENSE=1) / summed CUDA-event kernel time.
 `cpu_baseline` / --impl reference: the oracle port (one CPU sweep per gate, ProjectQ's execution model,
@@ -109,7 +109,9 @@ def workload_config(shots, n_gpus, fusion):
     return {"workload": "Surface-17 {} s2 importance sampling, subset {} over {} two-round slots, uniform placement"
             .format(MODEL, ESET, LOCS2), "shots_per_step_per_gpu": shots, "fusion": fusion,
             "state": "2^17 complex128 per shot resident in HBM", "parallelism": "shots sharded x{}".format(n_gpus),
-            "l2": "per-step working set (shots x 2 MiB) exceeds the 126 MB L2, no flush needed"}
+            "schedule": "support-aware sweeps (exactly-zero regions after an ancilla reset are skipped), X-type "
+                        "ancillas measured after timestep 4, lazy collapse; S17_DENSE=1 restores full-state sweeps",
+            "l2": "per-step working set (shots x >=128 KiB touched, 2 MiB allocated) exceeds the 126 MB L2, no flush needed"}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -223,8 +225,29 @@ def run_gpu(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = algo_bytes / (gate_ms * 1e-3) / 1e9 if gate_ms > 0 else 0.0
 
-    # e2e through the reference-shaped entry point: host args in, host tuple out, wall clock
+    # the same gate stream as full-state sweeps (ProjectQ-equivalent traffic, one sweep per timestep): the HBM-bound
+    # configuration the per-layer roofline fraction of BASELINE.json refers to
     sim.close()
+    dense = None
+    if rank == 0 and not args.no_dense:
+        os.environ["S17_DENSE"] = "1"
+        try:
+            dsim = api.Simulation(MODEL, LOCS2, args.dense_shots, ct, bt, fusion=1, device=local, error_models=models,
+                                  early_measure=False)
+            dsim.backend.set_subset(ESET, LOCS2)
+            dsim.backend.run("s2", args.dense_shots, L.NOISE_SUBSET, seed=args.seed)
+            dc = dsim.backend.run("s2", args.dense_shots, L.NOISE_SUBSET, seed=args.seed + 1)
+            dt = dsim.backend.timing()
+            d_ach = dc.sweep_bytes / (dt["gate_ms"] * 1e-3) / 1e9
+            dense = {"kernel": "k_layer2", "mode": "S17_DENSE=1, fusion=1 (8 full-state sweeps per cycle + explicit collapse)",
+                     "achieved": d_ach, "peak": peak, "unit": "GB/s", "frac": d_ach / peak,
+                     "shots_per_s": args.dense_shots / (dt["span_ms"] * 1e-3), "shots": args.dense_shots,
+                     "bytes_per_shot": dc.sweep_bytes / args.dense_shots}
+            dsim.close()
+        finally:
+            os.environ.pop("S17_DENSE", None)
+
+    # e2e through the reference-shaped entry point: host args in, host tuple out, wall clock
     drv.VERBOSE = False
     drv.BATCH_SHOTS, drv.FUSION, drv.DEVICE = B, args.fusion, local
     drv.s2_calculate_log_e_rate_error_subset(B, ct, MODEL, ESET, LOCS2, bt, PROB_LISTS)      # warm: builds the context
@@ -255,7 +278,7 @@ def run_gpu(args):
                     "h2d_bytes_per_step": 2048 * 8 + 3 * 4 * len(ESET) + 64, "d2h_bytes_per_step": 64 + 8 * 8,
                     "api": "s2_calculate_log_e_rate_error_subset(num_runs, ...) -> (rate, not0_rate, failed, not0)"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_layer4" if args.fusion == 4 else "k_layer2", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_layer4" if args.fusion == 4 else "k_layer3", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                          "traffic": None, "launches": int(gate_launches), "sweeps": int(sweeps),
                          "sweeps_per_shot": sweeps / (B * args.steps),
@@ -263,6 +286,8 @@ def run_gpu(args):
                          "gate_kernel_share_of_step": gate_ms / span_ms if span_ms else None},
             "counts": {"failed": int(tot[0]), "not0": int(tot[1]), "shots": total_shots},
         }
+        if dense is not None:
+            line["roofline_dense"] = dense
         if cpu is not None:
             line["cpu_baseline"] = {"value": cpu["shots_per_s"], "unit": "shots/s", "cores": cpu["cores"], "kind": "port",
                                     "sample": "{} s2 shots of the same workload, {} processes (oracle port)".format(
@@ -282,6 +307,8 @@ def main():
     ap.add_argument("--fusion", type=int, default=2)
     ap.add_argument("--seed", type=int, default=2026)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-dense", action="store_true")
+    ap.add_argument("--dense-shots", type=int, default=4096)
     ap.add_argument("--cpu-shots-per-core", type=int, default=60)
     ap.add_argument("--ref-shots-per-core", type=int, default=40)
     args = ap.parse_args()
