@@ -727,6 +727,8 @@ struct s17_ctx {
     double2 *zero_page = nullptr;
     CUtensorMap tmap;                 // the state as rows of 128 B, 8 KiB boxes, 128-byte swizzle (k_layer3)
     bool dense = false;               // option: full-state sweeps + explicit collapse (ProjectQ-equivalent traffic)
+    bool debug_sync = false;
+    std::string debug_note;
     bool force_ring = false;          // option: use the TMA-ring kernel (k_layer2) for support-aware sweeps as well
     uint32_t *act_list = nullptr, *n_act = nullptr;
     int num_sms = 148;
@@ -769,10 +771,22 @@ static cudaEvent_t get_event(s17_ctx *c) {
 }
 enum { CAT_GATE = 0, CAT_MEAS = 1, CAT_OTHER = 2 };
 struct Scope {
-    s17_ctx *c; TimedLaunch tl;
-    Scope(s17_ctx *c_, int cat) : c(c_) { tl.cat = cat; tl.e0 = get_event(c); tl.e1 = get_event(c); cudaEventRecord(tl.e0, c->stream); }
-    ~Scope() { cudaEventRecord(tl.e1, c->stream); c->launches.push_back(tl); }
+    s17_ctx *c; TimedLaunch tl; int line;
+    Scope(s17_ctx *c_, int cat, int line_ = 0) : c(c_), line(line_) {
+        tl.cat = cat; tl.e0 = get_event(c); tl.e1 = get_event(c); cudaEventRecord(tl.e0, c->stream);
+    }
+    ~Scope() {
+        cudaEventRecord(tl.e1, c->stream);
+        c->launches.push_back(tl);
+        if (c->debug_sync) {                   // S17_DEBUG_SYNC=1: find the launch that faults
+            cudaError_t e = cudaStreamSynchronize(c->stream);
+            if (e == cudaSuccess) e = cudaGetLastError();
+            if (e != cudaSuccess && c->debug_note.empty())
+                c->debug_note = std::string("first failing launch at s17.cu:") + std::to_string(line) + ": " + cudaGetErrorString(e);
+        }
+    }
 };
+#define SCOPE(cat) Scope s(ctx, cat, __LINE__)
 
 extern "C" int s17_device_count(void) {
     int n = 0;
@@ -814,6 +828,19 @@ extern "C" int s17_create(s17_ctx **out, int device, uint64_t max_shots) {
     CK(cudaMemset(ctx->probs, 0, 2048 * sizeof(double)));
     CK(cudaMemset(ctx->leak, 0, B * 4));
     CK(cudaMemset(ctx->ev, 0, B * S17_EV_WORDS * 4));
+    {
+        // debugging aid: S17_MEMSET=<bitmask> fills selected buffers with S17_MEMSET_BYTE at creation
+        const char *mm = getenv("S17_MEMSET");
+        const char *mb = getenv("S17_MEMSET_BYTE");
+        const int mask = mm ? atoi(mm) : 0, byte = mb ? atoi(mb) : 0;
+        if (mask & 1) CK(cudaMemset(ctx->state, byte, B * kDim * sizeof(double2)));
+        if (mask & 2) CK(cudaMemset(ctx->masks, byte, B * 2 * S17_MASK_WORDS * 4));
+        if (mask & 4) { CK(cudaMemset(ctx->active, byte, B)); CK(cudaMemset(ctx->ready, byte, B)); }
+        if (mask & 8) CK(cudaMemset(ctx->forced, byte, B * S17_MAX_OUTCOMES));
+        if (mask & 16) CK(cudaMemset(ctx->hist, byte, B * 256 * sizeof(double)));
+        if (mask & 32) CK(cudaMemset(ctx->aux, byte, B * sizeof(ShotAux)));
+        if (mask & 64) CK(cudaMemset(ctx->rec, byte, B * sizeof(s17_record)));
+    }
     CK(cudaFuncSetAttribute(k_layer, cudaFuncAttributeMaxDynamicSharedMemorySize, kTile * 16));
     CK(cudaFuncSetAttribute(k_layer2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kL2Smem));
     CK(cudaFuncSetAttribute(k_layer4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kL4Smem));
@@ -842,6 +869,8 @@ extern "C" int s17_create(s17_ctx **out, int device, uint64_t max_shots) {
     {
         const char *d = getenv("S17_DENSE");
         ctx->dense = d && d[0] == '1';
+        const char *ds = getenv("S17_DEBUG_SYNC");
+        ctx->debug_sync = ds && ds[0] == '1';
         const char *r = getenv("S17_RING");
         ctx->force_ring = r && r[0] == '1';
     }
@@ -861,7 +890,11 @@ extern "C" int s17_create(s17_ctx **out, int device, uint64_t max_shots) {
 extern "C" int s17_destroy(s17_ctx *ctx) {
     if (!ctx) return S17_OK;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        // the context is in a sticky error state (a kernel faulted): releasing resources would fault again
+        delete ctx;
+        return S17_E_CUDA;
+    }
     void *ptrs[] = {ctx->state, ctx->ev, ctx->masks, ctx->leak, ctx->active, ctx->ready, ctx->forced, ctx->hist,
                     ctx->aux, ctx->rec, ctx->counters, ctx->lut, ctx->cw16, ctx->probs, ctx->cum, ctx->plan,
                     ctx->rtf_slots, ctx->rtf_rounds, ctx->rtf_syndb, ctx->act_list, ctx->n_act, ctx->zero_page};
@@ -1167,7 +1200,7 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
     pa.first_shot = a.first_shot_id;
     pa.n_shots = n;
     {
-        Scope s(ctx, CAT_OTHER);
+        SCOPE(CAT_OTHER);
         k_plan<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(ctx->plan, pa, ctx->nd, ctx->probs, ctx->ev, ctx->masks,
                                                             ctx->leak, ctx->active);
     }
@@ -1177,7 +1210,7 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
     uint32_t nl = (uint32_t)Ls.size();
     if (max_layers && max_layers < nl) nl = max_layers;
     {
-        Scope s(ctx, CAT_OTHER);
+        SCOPE(CAT_OTHER);
         k_compact<<<1, 1024, 0, ctx->stream>>>(ctx->active, n, ctx->act_list, ctx->n_act);
     }
     MeasArgs ma;
@@ -1189,7 +1222,7 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
     ma.n_shots = n;
     for (uint32_t i = 0; i < nl; ++i) {
         {
-            Scope s(ctx, CAT_GATE);
+            SCOPE(CAT_GATE);
             if (Ls[i].L.n_anc == 4)
                 k_layer4<<<ctx->num_sms, kL4Threads, kL4Smem, ctx->stream>>>(
                     ctx->state, Ls2[i], ctx->ev, ctx->act_list, ctx->n_act, ctx->hist, ctx->counters, ctx->aux,
@@ -1213,7 +1246,7 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
         ma.final_part = final_part ? 1 : 0;
         ma.stream = 16u + (uint32_t)stage * 4u + (final_part ? 0u : 1u);
         {
-            Scope s(ctx, CAT_MEAS);
+            SCOPE(CAT_MEAS);
             k_measure<<<blocks_for((uint64_t)n * 32, 128), 128, 0, ctx->stream>>>(
                 ma, ctx->hist, ctx->forced, ctx->lut, ctx->leak, ctx->active, ctx->ready, ctx->aux, ctx->rec, ctx->counters);
         }
@@ -1224,7 +1257,7 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
 }
 
 static void collapse(s17_ctx *ctx, int n, const uint8_t *flag) {
-    Scope s(ctx, CAT_MEAS);
+    SCOPE(CAT_MEAS);
     k_collapse<<<n * 32, 256, 0, ctx->stream>>>(ctx->state, ctx->aux, flag);
 }
 
@@ -1244,7 +1277,7 @@ static int run_round(s17_ctx *ctx, const s17_run_args &a) {
         return run_cycle(ctx, a, 1, 0, -1, a.stop_layers ? a.stop_layers : 1000, dense, explicit_collapse);
     if (int rc = run_cycle(ctx, a, 1, 0, -1, 0, dense, explicit_collapse)) return rc;
     if (a.stop_stage == S17_STOP_AFTER_CYCLE1) {
-        Scope s(ctx, CAT_OTHER);
+        SCOPE(CAT_OTHER);
         cudaMemsetAsync(ctx->active, 1, n, ctx->stream);
         collapse(ctx, n, ctx->active);
         return S17_OK;
@@ -1256,7 +1289,7 @@ static int run_round(s17_ctx *ctx, const s17_run_args &a) {
     }
     if (a.materialize) {
         collapse(ctx, n, ctx->ready);
-        Scope s(ctx, CAT_OTHER);
+        SCOPE(CAT_OTHER);
         k_pauli<<<n * 32, 256, 0, ctx->stream>>>(ctx->state, ctx->rec, ctx->ready);
     }
     ReadArgs ra;
@@ -1268,7 +1301,7 @@ static int run_round(s17_ctx *ctx, const s17_run_args &a) {
     ra.first_shot = a.first_shot_id;
     ra.n_shots = n;
     {
-        Scope s(ctx, CAT_MEAS);
+        SCOPE(CAT_MEAS);
         k_readout<<<blocks_for((uint64_t)n * 32, 128), 128, 0, ctx->stream>>>(ra, ctx->state, ctx->aux, ctx->forced, ctx->cw16,
                                                                           ctx->leak, ctx->ready, ctx->rec, ctx->counters);
     }
@@ -1276,6 +1309,7 @@ static int run_round(s17_ctx *ctx, const s17_run_args &a) {
 }
 
 static int finish_timing(s17_ctx *ctx) {
+    if (!ctx->debug_note.empty()) return fail(ctx, S17_E_CUDA, ctx->debug_note);
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());
     for (const TimedLaunch &tl : ctx->launches) {
@@ -1307,12 +1341,12 @@ extern "C" int s17_run(s17_ctx *ctx, const s17_run_args *args, s17_counts *out) 
     CK(cudaEventRecord(ctx->span0, ctx->stream));
     CK(cudaMemsetAsync(ctx->counters, 0, C_N * sizeof(unsigned long long), ctx->stream));
     {
-        Scope s(ctx, CAT_OTHER);
+        SCOPE(CAT_OTHER);
         k_reset<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(n, ctx->leak, ctx->active, ctx->ready, ctx->rec, ctx->masks,
                                                              a.noise == S17_NOISE_PROB, 0);
     }
     if (a.noise == S17_NOISE_SUBSET) {
-        Scope s(ctx, CAT_OTHER);
+        SCOPE(CAT_OTHER);
         k_place<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(ctx->nd, ctx->cum, ctx->masks, a.seed, a.first_shot_id, n);
     }
     uint64_t shots_done = a.n_shots;

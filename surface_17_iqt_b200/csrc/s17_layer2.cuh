@@ -386,13 +386,17 @@ k_layer2(double2 *__restrict__ state, const __grid_constant__ LayerArg2 P, const
     const int grp = warp / (kGroupThreads / 32);
     const int tg = t - grp * kGroupThreads;                  // thread index inside the group
     const int gw = warp - grp * (kGroupThreads / 32);        // warp index inside the group
-    for (uint32_t j = grp; j < n_local; j += kGroups) {
+    for (uint32_t j = 0; j < n_local; ++j) {
         const int b = j % kRing;
+        // Every group observes EVERY fill of every buffer, in order, also the fills the other group consumes: a
+        // parity wait is only meaningful for the current or the immediately preceding phase, so a group that
+        // skipped a fill could see "phase k-1 complete" while waiting for phase k+1 and start on stale data.
+        mbar_wait(&full[b], (j / kRing) & 1);
+        if ((int)(j % kGroups) != grp) continue;
         double2 *tile = tiles + (size_t)b * kTile;
         const uint32_t *evw = evbuf + b * S17_EV_WORDS;
         const uint32_t item = first + j;
         const int tile_id = P.tile_ids[item & tile_mask];
-        mbar_wait(&full[b], (j / kRing) & 1);
         uint32_t base = 0;
 #pragma unroll
         for (int k = 0; k < 5; ++k) base |= ((tile_id >> k) & 1u) << P.A.other_bits[k];

@@ -334,3 +334,25 @@ def test_run_til_fail_bookkeeping(error_models, correction_table, bitflip_table)
     mean = rounds.mean()
     assert 2.0 < mean < 60.0
     sim.close()
+
+
+def test_dense_ring_kernel_stress(error_models, correction_table, bitflip_table, monkeypatch):
+    """Regression for the TMA-ring sweep (k_layer2) in its HBM-bound regime (dense, one timestep per sweep): with
+    two math groups sharing three buffers a group used to wait on an mbarrier phase it had not followed and could
+    start on a buffer that was still being filled (launch failures / hangs at thousands of shots).  Dense and
+    support-aware schedules must also agree exactly on every counter."""
+    locs = [24, 36, 48, 156, 48]
+    n = 4096
+    counts = {}
+    for dense in ("1", "0"):
+        monkeypatch.setenv("S17_DENSE", dense)
+        sim = make_sim(error_models, correction_table, bitflip_table, "PDD_model", locs, n, 1, early_measure=False)
+        sim.backend.set_subset([0, 0, 2, 1, 1], locs)
+        res = []
+        for k in range(3):
+            c = sim.backend.run("s2", n, L.NOISE_SUBSET, seed=77 + k)
+            assert c.errors == 0
+            res.append((c.failed, c.not0, c.counted))
+        counts[dense] = res
+        sim.close()
+    assert counts["1"] == counts["0"]
