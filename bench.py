@@ -312,7 +312,10 @@ def run_gpu(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_layer4" if args.fusion == 4 else "k_layer3", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
-                         "traffic": None, "launches": int(gate_launches), "sweeps": int(sweeps),
+                         # dram__bytes_read+write of one ncu --set full capture of this kernel, scaled to this run's
+                         # average launch: 3.173 GB measured for 3.221 GB algorithmic (profiles/r1h_k_layer3_ncu_full.csv)
+                         "traffic": (sweep_bytes / max(1, gate_launches)) * (3.173 / 3.221) if args.fusion != 4 else None,
+                         "launches": int(gate_launches), "sweeps": int(sweeps),
                          "sweeps_per_shot": sweeps / (B * args.steps),
                          "bytes_per_shot": sweep_bytes / (B * args.steps), "dense_bytes_per_sweep": SWEEP_BYTES,
                          "gate_kernel_share_of_step": gate_ms / span_ms if span_ms else None},
