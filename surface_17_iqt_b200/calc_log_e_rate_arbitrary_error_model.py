@@ -248,3 +248,13 @@ def calculate_log_e_rate(num_runs, filename, correction_table, e_model, e_probs,
             json.dump(results, file)
     log_e_rate, _A, _vals, _bins = fit_log_e_rate(results, num_bins)
     return log_e_rate
+
+
+# the host-side importance-sampling bookkeeping of the reference module (CL:460-753), same names
+from .importance_sampling import (  # noqa: E402,F401
+    subset_weight, weight_contribution_variable_e_rate, subset_weight_mixed, subset_weight_variable_e_rate,
+    weighted_logical_error_rate, increment, calculate_significant_subsets_incrementally,
+    find_significant_subsets_with_more_error, prob_s2_AND_eset_a_total_errors,
+    s2sim_calculate_significant_subsets_incrementally)
+from .compiled_surface_code_arbitrary_error_model import (  # noqa: E402,F401
+    load_lookup_table, instantiate_error_model, lookup, return_weight_classical_lookup)
