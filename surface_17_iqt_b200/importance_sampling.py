@@ -136,11 +136,18 @@ def find_significant_subsets_with_more_error(eset_a, error_subsets_list):
 
 
 def prob_s2_AND_eset_a_total_errors(eset_a, s2_rate_dict, significant_subsets_s1, significant_subsets_s1_and_s2,
-                                    locations1round, prob_lists_s1, prob_lists_s2):
-    """CL:678-697: P(second syndrome needed AND eset_a errors in total over both rounds)."""
+                                    locations1round, prob_lists_s1, prob_lists_s2, _reach_cache=None):
+    """CL:678-697: P(second syndrome needed AND eset_a errors in total over both rounds).
+    `_reach_cache` memoises find_significant_subsets_with_more_error per s1 subset (it does not depend on eset_a)."""
     sump, ratelist, sw1list, sw2list = 0, [], [], []
     for eset_s1 in significant_subsets_s1:
-        s2, s2_subtracted = find_significant_subsets_with_more_error(eset_s1, significant_subsets_s1_and_s2)
+        key = tuple(eset_s1)
+        if _reach_cache is not None and key in _reach_cache:
+            s2, s2_subtracted = _reach_cache[key]
+        else:
+            s2, s2_subtracted = find_significant_subsets_with_more_error(eset_s1, significant_subsets_s1_and_s2)
+            if _reach_cache is not None:
+                _reach_cache[key] = (s2, s2_subtracted)
         if eset_a in s2:
             eset_subtracted = s2_subtracted[s2.index(eset_a)]
             params1 = [(locations1round[i], prob_lists_s1[i], eset_s1[i]) for i in range(len(eset_s1))]
@@ -162,13 +169,14 @@ def s2sim_calculate_significant_subsets_incrementally(locations, prob_lists_s1, 
     zero = len(locations) * [0]
     esets = increment(zero)
     esets.append(zero)
+    reach = {}
 
     def visit(eset):
         if eset in already_checked:
             return
         weight = prob_s2_AND_eset_a_total_errors(eset, s2_rate_dict, significant_subsets_s1,
                                                  significant_subsets_s1_and_s2, locations, prob_lists_s1,
-                                                 prob_lists_s2)[0]
+                                                 prob_lists_s2, _reach_cache=reach)[0]
         if weight > cutoff_weight:
             error_subset_list.append(eset)
             subset_weight_list.append(weight)
