@@ -187,6 +187,30 @@ def _summary(failed_count, flipsa_not0_count, log_e_rate, flipsa_not0_rate, num_
     _log('total_time_taken_{}_runs_{}'.format(num_runs, time.perf_counter() - t_begin))
 
 
+def calculate_log_e_rate_true_probability(num_runs, correction_table, model, p_set, bitflip_table, protocol="single",
+                                          cooling=False, over_angles=None):
+    """True Bernoulli-per-slot noise with a one-round (or s1 / s2) protocol: the shot loop of CL:183-259 with the
+    probability lists bound directly (instantiate_error_model, CS:31-49) instead of 0/1 masks.  This is BASELINE
+    config 1 (`depolarising_model`, px = py = pz = p/3 on the 30 single-qubit slots, `depol` p on the 24 Rxx slots;
+    slot indexing per SURVEY App. C-1) and config 3 (`coherent_model`, angles via `over_angles`).
+    Returns (failed_count / counted, failed_count, counted, flipsa_not0_count)."""
+    p_set = [list(p) for p in p_set]
+    sim = _simulation(model, [len(p) for p in p_set], cooling, correction_table, bitflip_table, over_angles=over_angles)
+    names = sim.model["probabilities"]
+    sim.backend.set_slot_probs([[0.0] * len(p) if (over_angles and names[i] in over_angles) else p
+                                for i, p in enumerate(p_set)])
+    seed = random.getrandbits(64)
+    rank, world_size = distributed.world()
+    first, count = distributed.shard_range(num_runs, rank, world_size)
+    failed = not0 = counted = done = 0
+    while done < count:
+        n = min(BATCH_SHOTS, count - done)
+        c = sim.backend.run(protocol, n, L.NOISE_PROB, seed=seed, first_shot_id=first + done)
+        failed, not0, counted, done = failed + c.failed, not0 + c.not0, counted + c.counted, done + n
+    failed, not0, counted = distributed.allreduce_counts([failed, not0, counted])
+    return (failed / counted if counted else None), failed, counted, not0
+
+
 def f(t, A, r):
     """CL:756."""
     return A * np.exp(-r * t)

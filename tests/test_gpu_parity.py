@@ -356,3 +356,36 @@ def test_dense_ring_kernel_stress(error_models, correction_table, bitflip_table,
         counts[dense] = res
         sim.close()
     assert counts["1"] == counts["0"]
+
+
+def test_depolarising_true_probability_statistics(error_models, correction_table, bitflip_table):
+    """BASELINE config 1 (depolarising_model, Bernoulli per slot, single round): failure rate within binomial 3 sigma
+    of the oracle's own sampling, and every device-sampled shot replays bit-exactly through the oracle."""
+    import surface_17_iqt_b200.calc_log_e_rate_arbitrary_error_model as drv
+    p = 0.02
+    p_set = [30 * [p / 3], 30 * [p / 3], 30 * [p / 3], 24 * [p]]
+    drv.VERBOSE = False
+    drv.BATCH_SHOTS = 8192
+    rate, failed, counted, _ = drv.calculate_log_e_rate_true_probability(8192, correction_table, "depolarising_model",
+                                                                          p_set, bitflip_table)
+    drv.release()
+    assert counted == 8192
+    orc = so.ShotOracle(error_models, correction_table, bitflip_table)
+    rnd, mr = random.Random(5), random.Random(6)
+    m, ofail = 160, 0
+    for _ in range(m):
+        ofail += orc.run_shot("depolarising_model", p_set, "single", rnd=rnd, meas=so.SampledMeasure(mr))["fail"]
+    pooled = (failed + ofail) / (counted + m)
+    assert abs(rate - ofail / m) < 3 * np.sqrt(pooled * (1 - pooled) * (1 / counted + 1 / m)) + 1e-9
+    assert 0.02 < rate < 0.6
+
+
+def test_run_til_fail_sweep_example():
+    import importlib.util
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("vary_p", os.path.join(here, "examples", "vary_p.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    out = mod.sweep("Dress_model", runs=300, ps=(0.02, 0.01))
+    assert out["0.02"]["log_e_rate_fit"] > 0 and out["0.01"]["log_e_rate_fit"] > 0
+    assert out["0.02"]["rounds"] < out["0.01"]["rounds"] * 1.5      # more noise -> runs fail sooner
