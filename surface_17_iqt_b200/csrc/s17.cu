@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <algorithm>
 #include <vector>
 
 #include "s17_kernels.cuh"
@@ -358,6 +359,59 @@ struct MeasArgs {
     int n_shots;
 };
 
+// bookkeeping after the ancillas in ma.mask of `shot` were measured with raw outcome bits `a`: outcome log, and on the
+// final part of a cycle the leak override (CS:854-857), the syndrome comparison and the protocol's branch
+// (CL:240, 320-333, 415-424, 83-98) plus the lookup decode (CS:886-892)
+__device__ void record_measurement(const MeasArgs &ma, int shot, uint32_t a, uint32_t nout, bool bad,
+                                   const uint32_t *__restrict__ lut, uint32_t *__restrict__ leak,
+                                   uint8_t *__restrict__ active, uint8_t *__restrict__ ready, s17_record *__restrict__ rec,
+                                   unsigned long long *__restrict__ counters)
+{
+    s17_record r = rec[shot];
+    for (int j = 0; j < 8; ++j)
+        if (((ma.mask >> j) & 1u) && nout + j < S17_MAX_OUTCOMES) r.outcomes[nout + j] = (uint8_t)((a >> j) & 1u);
+    if (bad) { r.flags |= S17_F_ERROR; atomicAdd(&counters[C_ERRORS], 1ull); }
+    const uint32_t all = r.partial | a;
+    if (!ma.final_part) {
+        r.partial = (uint16_t)all;
+        rec[shot] = r;
+        return;
+    }
+    r.partial = 0;
+    r.n_outcomes = (uint8_t)min(nout + 8u, (uint32_t)S17_MAX_OUTCOMES);
+    // a leaked ancilla always reads 1 and is reset (CS:854-857)
+    uint32_t lk = leak[shot];
+    const uint32_t synd = all | ((lk >> 9) & 0xFFu);
+    lk &= 0x1FFu;
+    leak[shot] = lk;
+    r.leak = lk;
+
+    bool decode = false;
+    if (ma.stage == 0) {
+        r.quiescent = (uint8_t)synd;
+    } else if (ma.stage == 1) {
+        r.synd1 = (uint8_t)synd;
+        r.flips_a = r.quiescent ^ (uint8_t)synd;                  // (prev - synd) % 2, CL:240, 320, 415
+        const bool not0 = r.flips_a != 0;
+        if (not0) { r.flags |= S17_F_NOT0; atomicAdd(&counters[C_NOT0], 1ull); }
+        if (ma.protocol == S17_PROTO_SINGLE) decode = true;
+        else if (ma.protocol == S17_PROTO_S1) { decode = !not0; if (not0) active[shot] = 0; }      // CL:321, 332
+        else if (ma.protocol == S17_PROTO_S2) { if (!not0) active[shot] = 0; }                    // CL:416, 437
+        else { decode = !not0; if (!not0) active[shot] = 0; }                                     // CL:86-92
+    } else {
+        r.synd2 = (uint8_t)synd;
+        r.flags |= S17_F_SYND2;
+        decode = true;
+    }
+    if (decode) {
+        r.ft_syndrome = r.quiescent ^ (uint8_t)synd;             // CL:424; equals (flips_a + flips_b) % 2, CL:98
+        r.correction = lut[r.ft_syndrome];
+        r.flags |= S17_F_COUNTED;
+        ready[shot] = 1;
+    }
+    rec[shot] = r;
+}
+
 // one warp per shot: sample the ancillas in `mask` from the joint histogram, then (on the final part of a
 // cycle) apply the leak override and take the protocol's branch
 __global__ void __launch_bounds__(128)
@@ -408,56 +462,30 @@ k_measure(MeasArgs ma, const double *__restrict__ hist, const uint8_t *__restric
         seen |= 1u << j;
     }
     if (lane != 0) return;
-    s17_record r = rec[shot];
-    for (int j = 0; j < 8; ++j)
-        if (((ma.mask >> j) & 1u) && nout + j < S17_MAX_OUTCOMES) r.outcomes[nout + j] = (uint8_t)((a >> j) & 1u);
     const double pa = h[a];
     ShotAux ax;
     ax.scale = pa > 0.0 ? 1.0 / sqrt(pa) : 0.0;
     ax.anc_outcome = a;          // the surviving block; the ancillas measured earlier were already reset to 0
     ax.collapsed = 0;
     aux[shot] = ax;
-    if (bad) { r.flags |= S17_F_ERROR; atomicAdd(&counters[C_ERRORS], 1ull); }
-    const uint32_t all = r.partial | a;
-    if (!ma.final_part) {
-        r.partial = (uint16_t)all;
-        rec[shot] = r;
-        return;
-    }
-    r.partial = 0;
-    r.n_outcomes = (uint8_t)min(nout + 8u, (uint32_t)S17_MAX_OUTCOMES);
-    // a leaked ancilla always reads 1 and is reset (CS:854-857)
-    uint32_t lk = leak[shot];
-    const uint32_t synd = all | ((lk >> 9) & 0xFFu);
-    lk &= 0x1FFu;
-    leak[shot] = lk;
-    r.leak = lk;
-
-    bool decode = false;
-    if (ma.stage == 0) {
-        r.quiescent = (uint8_t)synd;
-    } else if (ma.stage == 1) {
-        r.synd1 = (uint8_t)synd;
-        r.flips_a = r.quiescent ^ (uint8_t)synd;                  // (prev - synd) % 2, CL:240, 320, 415
-        const bool not0 = r.flips_a != 0;
-        if (not0) { r.flags |= S17_F_NOT0; atomicAdd(&counters[C_NOT0], 1ull); }
-        if (ma.protocol == S17_PROTO_SINGLE) decode = true;
-        else if (ma.protocol == S17_PROTO_S1) { decode = !not0; if (not0) active[shot] = 0; }      // CL:321, 332
-        else if (ma.protocol == S17_PROTO_S2) { if (!not0) active[shot] = 0; }                    // CL:416, 437
-        else { decode = !not0; if (!not0) active[shot] = 0; }                                     // CL:86-92
-    } else {
-        r.synd2 = (uint8_t)synd;
-        r.flags |= S17_F_SYND2;
-        decode = true;
-    }
-    if (decode) {
-        r.ft_syndrome = r.quiescent ^ (uint8_t)synd;             // CL:424; equals (flips_a + flips_b) % 2, CL:98
-        r.correction = lut[r.ft_syndrome];
-        r.flags |= S17_F_COUNTED;
-        ready[shot] = 1;
-    }
-    rec[shot] = r;
+    record_measurement(ma, shot, a, nout, bad, lut, leak, active, ready, rec, counters);
 }
+
+// bookkeeping for the fused half-cycle path: both halves of a cycle were sampled inside k_half
+__global__ void k_record(MeasArgs ma, const uint32_t *__restrict__ meas_out, const uint32_t *__restrict__ lut,
+                         uint32_t *__restrict__ leak, uint8_t *__restrict__ active, uint8_t *__restrict__ ready,
+                         s17_record *__restrict__ rec, unsigned long long *__restrict__ counters)
+{
+    const int shot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (shot >= ma.n_shots || !active[shot]) return;
+    const uint32_t x = meas_out[2 * shot], z = meas_out[2 * shot + 1];
+    record_measurement(ma, shot, (x | z) & 0xFFu, 8u * (uint32_t)ma.stage, ((x | z) & 0x100u) != 0, lut, leak, active, ready,
+                       rec, counters);
+}
+
+}  // namespace s17
+#include "s17_half.cuh"
+namespace s17 {
 
 // ProjectQ collapse + renormalise for the 8 measured ancillas, fused with the reset X gates (CS:859-862):
 // the surviving 512-amplitude block moves to ancilla value 0, everything else becomes zero.
@@ -727,10 +755,15 @@ struct s17_ctx {
     double2 *zero_page = nullptr;
     CUtensorMap tmap;                 // the state as rows of 128 B, 8 KiB boxes, 128-byte swizzle (k_layer3)
     bool dense = false;               // option: full-state sweeps + explicit collapse (ProjectQ-equivalent traffic)
+    // fused half-cycle programs (k_half) per cycle kind: [prep | stab 0 | stab 1][X half | Z half]
+    LayerArg2 half_prog[3][2];
+    HalfTail half_tail[3][2];
+    bool half_ok[3] = {false, false, false};
+    bool no_fuse = false;
     bool debug_sync = false;
     std::string debug_note;
     bool force_ring = false;          // option: use the TMA-ring kernel (k_layer2) for support-aware sweeps as well
-    uint32_t *act_list = nullptr, *n_act = nullptr;
+    uint32_t *act_list = nullptr, *n_act = nullptr, *meas_out = nullptr;
     int num_sms = 148;
     bool use_v1 = false;
     NoiseDev nd{};
@@ -845,8 +878,10 @@ extern "C" int s17_create(s17_ctx **out, int device, uint64_t max_shots) {
     CK(cudaFuncSetAttribute(k_layer2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kL2Smem));
     CK(cudaFuncSetAttribute(k_layer4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kL4Smem));
     CK(cudaFuncSetAttribute(k_layer3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kL3Smem));
+    CK(cudaFuncSetAttribute(k_half, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kL3Smem));
     CK(cudaMalloc(&ctx->act_list, B * 4));
     CK(cudaMalloc(&ctx->n_act, 4));
+    CK(cudaMalloc(&ctx->meas_out, B * 2 * 4));
     {
         typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -871,6 +906,8 @@ extern "C" int s17_create(s17_ctx **out, int device, uint64_t max_shots) {
         ctx->dense = d && d[0] == '1';
         const char *ds = getenv("S17_DEBUG_SYNC");
         ctx->debug_sync = ds && ds[0] == '1';
+        const char *nf = getenv("S17_FUSE");
+        ctx->no_fuse = nf && nf[0] == '0';
         const char *r = getenv("S17_RING");
         ctx->force_ring = r && r[0] == '1';
     }
@@ -897,7 +934,7 @@ extern "C" int s17_destroy(s17_ctx *ctx) {
     }
     void *ptrs[] = {ctx->state, ctx->ev, ctx->masks, ctx->leak, ctx->active, ctx->ready, ctx->forced, ctx->hist,
                     ctx->aux, ctx->rec, ctx->counters, ctx->lut, ctx->cw16, ctx->probs, ctx->cum, ctx->plan,
-                    ctx->rtf_slots, ctx->rtf_rounds, ctx->rtf_syndb, ctx->act_list, ctx->n_act, ctx->zero_page};
+                    ctx->rtf_slots, ctx->rtf_rounds, ctx->rtf_syndb, ctx->act_list, ctx->n_act, ctx->zero_page, ctx->meas_out};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
@@ -925,7 +962,8 @@ static int check_layer(s17_ctx *ctx, const s17_layer &L) {
 }
 
 // host-side lowering of one sweep for k_layer2: per-op constants and the pass schedule
-static LayerArg2 make_layer2(const LayerArg &A, uint32_t support /* ancilla bits possibly non-zero */, bool first, bool dense) {
+static LayerArg2 make_layer2(const LayerArg &A, uint32_t support /* ancilla bits possibly non-zero */, bool first, bool dense,
+                             int n_main = -1 /* ops that get passes (default: all) */, const uint32_t *idle_filter = nullptr) {
     LayerArg2 P;
     memset(&P, 0, sizeof(P));
     P.A = A;
@@ -999,15 +1037,19 @@ static LayerArg2 make_layer2(const LayerArg &A, uint32_t support /* ancilla bits
         }
         run.clear();
     };
-    for (int o = 0; o < L.n_ops; ++o) {
+    const int n_sched = n_main < 0 ? (int)L.n_ops : n_main;
+    for (int o = 0; o < n_sched; ++o) {
         if (L.ops[o].kind == S17_OP_ENT) { run.push_back(o); continue; }
         flush();
+        const uint32_t filt = idle_filter ? idle_filter[o] : 0x1FFFFu;
         if (np == 0 || P.pass[np - 1].idle_word != 255) {      // nothing to attach to: idle-only pass
             P.pass[np].kind = 2;
             P.pass[np].idle_word = L.ops[o].ev_word;
+            P.pass[np].idle_filter = filt;
             ++np;
         } else {
             P.pass[np - 1].idle_word = L.ops[o].ev_word;
+            P.pass[np - 1].idle_filter = filt;
         }
     }
     flush();
@@ -1037,6 +1079,94 @@ static LayerArg2 make_layer2(const LayerArg &A, uint32_t support /* ancilla bits
             if (!removed[b] && !used[b] && n < 12) { used[b] = true; ps.pos[n++] = (uint8_t)b; }
     }
     return P;
+}
+
+// Lower one half cycle (the sweeps up to a measurement) to the fused k_half form.  Returns false when the half cycle
+// does not have the required shape (then the generic sweep kernels are used).
+static bool make_half(const std::vector<LayerArg> &layers, size_t begin, size_t end, LayerArg2 &P, HalfTail &T) {
+    std::vector<s17_op> ops;
+    for (size_t i = begin; i < end; ++i) {
+        if (layers[i].L.n_anc != 3) return false;
+        for (int o = 0; o < layers[i].L.n_ops; ++o) ops.push_back(layers[i].L.ops[o]);
+    }
+    const uint8_t mask = layers[end - 1].L.meas_mask;
+    if (!mask) return false;
+    // the four ancillas of the half cycle, the tail one = the one that is touched last for the first time
+    std::vector<int> anc;
+    for (const s17_op &op : ops)
+        if (op.kind == S17_OP_ENT) {
+            bool seen = false;
+            for (int a : anc) seen |= (a == op.anc_bit);
+            if (!seen) anc.push_back(op.anc_bit);
+        }
+    if (anc.size() != 4) return false;
+    uint8_t set = 0;
+    for (int a : anc) set |= (uint8_t)(1u << (a - 9));
+    if (set != mask) return false;
+    const int e = anc[3];
+    std::vector<int> tail;
+    for (size_t i = 0; i < ops.size(); ++i)
+        if (ops[i].kind == S17_OP_ENT && ops[i].anc_bit == e) tail.push_back((int)i);
+    if (tail.size() != 2 || ops[tail[0]].data_bit == ops[tail[1]].data_bit) return false;
+    for (int ti : tail)                                   // a moved operation must commute with everything it jumps over
+        for (size_t q = ti + 1; q < ops.size(); ++q)
+            if (ops[q].kind == S17_OP_ENT && ops[q].anc_bit != e && ops[q].data_bit == ops[ti].data_bit) return false;
+    for (const s17_op &op : ops)                          // uop parameters were re-indexed per sweep: coherent models keep the generic path
+        if (op.kind == S17_OP_ENT)
+            for (int u = 0; u < op.n_uops; ++u)
+                if (op.uops[u].type >= S17_U_ROT_X) return false;
+    LayerArg A;
+    memset(&A, 0, sizeof(A));
+    A.L.n_anc = 3;
+    int na = 0;
+    std::vector<int> main_anc(anc.begin(), anc.begin() + 3);
+    std::sort(main_anc.begin(), main_anc.end());
+    for (int a : main_anc) A.L.anc_bits[na++] = (uint8_t)a;
+    int k = 0;
+    for (int b = 9; b <= 16; ++b) {
+        bool in = false;
+        for (int a : main_anc) in |= (a == b);
+        if (!in) A.other_bits[k++] = (uint8_t)b;
+    }
+    memset(&T, 0, sizeof(T));
+    T.n_tail = 2;
+    T.e_bit = (uint8_t)e;
+    T.meas_mask = mask;
+    for (int q = 0; q < 3; ++q) T.idle_word[q] = 255;
+    uint32_t filt[S17_MAX_LAYER_OPS];
+    int n = 0;
+    uint32_t pend = 0;                                    // qubits whose (moved) operation precedes the current point
+    int seg = 0;                                          // 0: before tail op 0, 1: between, 2: after tail op 1
+    for (size_t i = 0; i < ops.size(); ++i) {
+        const s17_op &op = ops[i];
+        if (op.kind == S17_OP_ENT && op.anc_bit == e) {
+            pend |= (1u << op.data_bit) | (1u << e);
+            ++seg;
+            continue;
+        }
+        if (n >= (int)S17_MAX_LAYER_OPS - 2) return false;
+        if (op.kind == S17_OP_IDLE) {
+            filt[n] = 0x1FFFFu & ~pend;
+            if (pend) {
+                if (T.idle_word[seg] != 255) return false;        // one idle mask per tail segment
+                T.idle_word[seg] = op.ev_word;
+                T.idle_filter[seg] = pend;
+            }
+        } else {
+            filt[n] = 0x1FFFFu;
+        }
+        A.L.ops[n++] = op;
+    }
+    const int n_main = n;
+    T.op[0] = (uint8_t)n;
+    A.L.ops[n++] = ops[tail[0]];
+    T.op[1] = (uint8_t)n;
+    A.L.ops[n++] = ops[tail[1]];
+    filt[n - 2] = filt[n - 1] = 0x1FFFFu;
+    A.L.n_ops = (uint8_t)n;
+    A.L.meas_mask = mask;
+    P = make_layer2(A, 0, true, false, n_main, filt);
+    return P.n_pass <= S17_MAX_LAYER_OPS;
 }
 
 extern "C" int s17_load_program(s17_ctx *ctx, const s17_layer *layers, const uint32_t n_layers[3], const double *params,
@@ -1086,6 +1216,16 @@ extern "C" int s17_load_program(s17_ctx *ctx, const s17_layer *layers, const uin
         }
         if (ctx->layers[c].empty() || !ctx->layers[c].back().L.meas_mask)
             return fail(ctx, S17_E_ARG, "the last sweep of a cycle must carry a measurement mask");
+        {
+            // fused half-cycle form: needs exactly two measurement points (early X-ancilla measurement)
+            std::vector<size_t> cuts;
+            for (size_t i = 0; i < ctx->layers[c].size(); ++i)
+                if (ctx->layers[c][i].L.meas_mask) cuts.push_back(i + 1);
+            ctx->half_ok[c] = cuts.size() == 2 &&
+                              make_half(ctx->layers[c], 0, cuts[0], ctx->half_prog[c][0], ctx->half_tail[c][0]) &&
+                              make_half(ctx->layers[c], cuts[0], cuts[1], ctx->half_prog[c][1], ctx->half_tail[c][1]);
+            if (ctx->half_ok[c]) { ctx->half_tail[c][0].final_part = 0; ctx->half_tail[c][1].final_part = 1; }
+        }
     }
     if (ctx->plan) { cudaFree(ctx->plan); ctx->plan = nullptr; }
     CK(cudaMalloc(&ctx->plan, n_plan * sizeof(s17_pinstr)));
@@ -1220,6 +1360,27 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
     ma.seed = a.seed;
     ma.first_shot = a.first_shot_id;
     ma.n_shots = n;
+    if (ctx->half_ok[which] && !dense && !mid_collapse && !max_layers && !ctx->use_v1 && !ctx->force_ring && !ctx->no_fuse) {
+        // production path: one fused kernel per half cycle (gates + measurement + collapse), state stays on chip
+        for (int h = 0; h < 2; ++h) {
+            ma.mask = ctx->half_tail[which][h].meas_mask;
+            ma.final_part = h;
+            ma.stream = 16u + (uint32_t)stage * 4u + (h ? 0u : 1u);
+            SCOPE(CAT_GATE);
+            k_half<<<ctx->num_sms * kL3CtasPerSm, kL3Threads, kL3Smem, ctx->stream>>>(
+                ctx->tmap, ctx->half_prog[which][h], ctx->half_tail[which][h], ma, ctx->state, ctx->ev, ctx->act_list,
+                ctx->n_act, ctx->aux, ctx->forced, ctx->meas_out, ctx->counters, (h == 0) ? init_basis : -1);
+            ctx->n_gate++;
+        }
+        {
+            ma.mask = 0xFFu;
+            ma.final_part = 1;
+            SCOPE(CAT_MEAS);
+            k_record<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(ma, ctx->meas_out, ctx->lut, ctx->leak, ctx->active,
+                                                                  ctx->ready, ctx->rec, ctx->counters);
+        }
+        return S17_OK;
+    }
     for (uint32_t i = 0; i < nl; ++i) {
         {
             SCOPE(CAT_GATE);

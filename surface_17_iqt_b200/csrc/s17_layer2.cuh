@@ -44,6 +44,7 @@ struct PassC {
     // bank-conflict-free lane mapping for the 128B-swizzled tile layout (k_layer3): item bit k -> tile-local bit
     // pos[k]; the three lowest item bits (a quarter warp) land on bits whose swizzled 16-byte columns differ
     uint8_t pos[12];
+    uint32_t idle_filter;    // qubits of the idle mask applied at this point (0x1FFFF: all); used by k_half
 };
 
 struct LayerArg2 {
