@@ -297,29 +297,41 @@ k_half(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ LayerAr
             // bin b: bits 0-2 = main ancillas (anc_bits order), bit 3 = tail ancilla -> ancilla indices
             const uint32_t ajs[4] = {aj0, aj1, aj2, aje};
             const uint32_t nout = 8u * (uint32_t)ma.stage;      // outcomes consumed by the earlier cycles of this shot
-            Philox rng(ma.seed, ma.first_shot + shot, ma.stream);
-            uint32_t a = 0, chosen = 0, seen = 0;       // a: ancilla-indexed outcome, chosen/seen: bin-indexed
+            uint32_t a = 0, chosen = 0;                 // a: ancilla-indexed outcome, chosen: bin-indexed
             bool bad = false;
-            for (uint32_t jj = 0; jj < 8; ++jj) {           // ascending ancilla index, like k_measure
-                int k = -1;
-                for (int q = 0; q < 4; ++q)
-                    if (ajs[q] == jj) k = q;
-                if (k < 0 || !((ma.mask >> jj) & 1u)) continue;
-                double p0 = 0.0, p1 = 0.0;
+            if (ma.forced) {
+                // replay: the recorded outcome bits, in ascending ancilla index; each must have non-zero probability
+                uint32_t seen = 0;
+                for (uint32_t jj = 0; jj < 8; ++jj) {
+                    int k = -1;
+                    for (int q = 0; q < 4; ++q)
+                        if (ajs[q] == jj) k = q;
+                    if (k < 0 || !((ma.mask >> jj) & 1u)) continue;
+                    const uint32_t out = forced[(size_t)shot * S17_MAX_OUTCOMES + nout + jj] & 1u;
+                    double pc = 0.0;
+                    for (uint32_t b = 0; b < 16; ++b)
+                        if ((b & seen) == chosen && ((b >> k) & 1u) == out) pc += h[b];
+                    if (pc <= 0.0) bad = true;
+                    a |= out << jj;
+                    chosen |= out << k;
+                    seen |= 1u << k;
+                }
+            } else {
+                // the four Measure gates sample the joint distribution of the four ancillas; one uniform against the
+                // cumulative histogram draws from exactly that distribution (ProjectQ itself picks a basis state by a
+                // cumulative walk) and keeps the serial section of the CTA short
+                Philox rng(ma.seed, ma.first_shot + shot, ma.stream);
+                double tot = 0.0;
+                for (uint32_t b = 0; b < 16; ++b) tot += h[b];
+                const double u = rng.next() * tot;
+                double cum = 0.0;
+                chosen = 15;
                 for (uint32_t b = 0; b < 16; ++b) {
-                    if ((b & seen) != chosen) continue;
-                    if ((b >> k) & 1u) p1 += h[b]; else p0 += h[b];
+                    cum += h[b];
+                    if (u < cum) { chosen = b; break; }
                 }
-                uint32_t out;
-                if (ma.forced) {
-                    out = forced[(size_t)shot * S17_MAX_OUTCOMES + nout + jj] & 1u;
-                    if ((out ? p1 : p0) <= 0.0) bad = true;
-                } else {
-                    out = (rng.next() * (p0 + p1) < p1) ? 1u : 0u;
-                }
-                a |= out << jj;
-                chosen |= out << k;
-                seen |= 1u << k;
+                while (chosen > 0 && h[chosen] <= 0.0) --chosen;     // rounding guard: never select an empty bin
+                for (int q = 0; q < 4; ++q) a |= ((chosen >> q) & 1u) << ajs[q];
             }
             const double pa = h[chosen];
             s_inv = pa > 0.0 ? 1.0 / sqrt(pa) : 0.0;        // every deferred gate factor cancels in the renormalisation
