@@ -310,11 +310,15 @@ def run_gpu(args):
                     "h2d_bytes_per_step": 2048 * 8 + 3 * 4 * len(ESET) + 64, "d2h_bytes_per_step": 64 + 8 * 8,
                     "api": "s2_calculate_log_e_rate_error_subset(num_runs, ...) -> (rate, not0_rate, failed, not0)"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_layer4" if args.fusion == 4 else "k_layer3", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_half", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                          # dram__bytes_read+write of one ncu --set full capture of this kernel, scaled to this run's
                          # average launch: 3.173 GB measured for 3.221 GB algorithmic (profiles/r1h_k_layer3_ncu_full.csv)
-                         "traffic": (sweep_bytes / max(1, gate_launches)) * (3.173 / 3.221) if args.fusion != 4 else None,
+                         # (k_half: 217.8 MB measured for 268.4 MB algorithmic, profiles/r1i_k_half_ncu_full.csv)
+                         "traffic": (sweep_bytes / max(1, gate_launches)) * (217.8 / 268.4),
+                         "note": "the default schedule keeps a shot's half cycle in shared memory (8 KiB in / 8 KiB out), so "
+                                 "this kernel is bound by the FP64 pipe and shared memory (ncu: 24-49 % / 35-46 %), not by "
+                                 "HBM; the HBM-bound full-state configuration is reported in roofline_dense",
                          "launches": int(gate_launches), "sweeps": int(sweeps),
                          "sweeps_per_shot": sweeps / (B * args.steps),
                          "bytes_per_shot": sweep_bytes / (B * args.steps), "dense_bytes_per_sweep": SWEEP_BYTES,

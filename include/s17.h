@@ -68,7 +68,9 @@ typedef struct {
     uint8_t anc_bit;    /* state-vector bit of the ancilla qubit (9..16) */
     uint8_t n_uops;
     uint8_t ev_word;    /* index of this op's per-shot event word */
-    uint8_t pad[3];
+    uint8_t partial;    /* 1: holds only some gates of its entangling operation (one-gate-per-sweep mode): Pauli events
+                           must be applied gate by gate, not as the operation's net end-of-op Pauli */
+    uint8_t pad[2];
     s17_uop uops[8];
 } s17_op;
 

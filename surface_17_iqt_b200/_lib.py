@@ -30,7 +30,7 @@ class Uop(C.Structure):
 
 class Op(C.Structure):
     _fields_ = [("kind", C.c_uint8), ("data_bit", C.c_uint8), ("anc_bit", C.c_uint8), ("n_uops", C.c_uint8),
-                ("ev_word", C.c_uint8), ("pad", C.c_uint8 * 3), ("uops", Uop * 8)]
+                ("ev_word", C.c_uint8), ("partial", C.c_uint8), ("pad", C.c_uint8 * 2), ("uops", Uop * 8)]
 
 
 class Layer(C.Structure):

@@ -245,7 +245,10 @@ def compile_program(model, list_len, fusion=1, cooling=False, over_angles=None, 
                     else:
                         raise ValueError("unknown error kind {!r}".format(err))
                     emit(**kw)
-            emit(kind=L.P_OP_END, word=op.index)
+            # a: which single-qubit gates the op has, b: sign of the Rxx angle -- lets the planner conjugate the op's
+            # Pauli events through the remaining (Clifford) gates to one net Pauli at the end of the op
+            emit(kind=L.P_OP_END, word=op.index, a=int(op.has_ry1) | (int(op.has_rx) << 1) | (int(op.has_ry2) << 2),
+                 b=int(op.s > 0))
         if cooling and t < 7:                          # sympathetic_cooling (CS:762-772) after timesteps 1-7
             for q in range(N_DATA + N_ANC):
                 for err, pname, *_ in model["gates"]["Idle"]:
@@ -263,6 +266,7 @@ def compile_program(model, list_len, fusion=1, cooling=False, over_angles=None, 
     def make_op(op, cycle, only=None):
         o = L.Op()
         o.kind, o.data_bit, o.anc_bit, o.ev_word = L.OP_ENT, op.data_bit, op.anc_bit, op.index
+        o.partial = int(only is not None)
         uops = []
         for pos, gate, utype, sign, run_ind in gates_of(op):
             if only is not None and pos != only:

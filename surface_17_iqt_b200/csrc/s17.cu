@@ -282,6 +282,32 @@ __device__ __forceinline__ uint32_t pauli_mul(uint32_t f, int q, int p) {
     return f | (x << (2 * q)) | (z << (2 * q + 1)) | (k << 4);
 }
 
+// product A.B of two 2-qubit Pauli fields (x0 z0 x1 z1 k k):  i^k (X^x0 Z^z0)_data (X^x1 Z^z1)_anc
+__device__ __forceinline__ uint32_t pmul2(uint32_t A, uint32_t B) {
+    const uint32_t sign = ((A >> 1) & B & 1u) + ((A >> 3) & (B >> 2) & 1u);       // Z_a X_b = -X_b Z_a per qubit
+    const uint32_t k = ((A >> 4) + (B >> 4) + 2u * sign) & 3u;
+    return ((A ^ B) & 15u) | (k << 4);
+}
+// U P U^dagger for one of the cycle's Clifford gates; img_* are the images of X_d, Z_d, X_a, Z_a
+__device__ __forceinline__ uint32_t pconj(uint32_t P, uint32_t img_xd, uint32_t img_zd, uint32_t img_xa, uint32_t img_za) {
+    uint32_t R = P & 0x30u;
+    if (P & 1u) R = pmul2(R, img_xd);
+    if (P & 2u) R = pmul2(R, img_zd);
+    if (P & 4u) R = pmul2(R, img_xa);
+    if (P & 8u) R = pmul2(R, img_za);
+    return R;
+}
+__device__ __forceinline__ uint32_t pconj_rx(uint32_t P, int sigma) {     // Rx(sigma pi/2) on the data qubit: Z -> -sigma Y
+    return pconj(P, 0x01u, 0x03u | ((sigma > 0 ? 3u : 1u) << 4), 0x04u, 0x08u);
+}
+__device__ __forceinline__ uint32_t pconj_ry(uint32_t P, int v) {         // Ry(v pi/2): X -> -v Z, Z -> v X
+    return pconj(P, 0x02u | ((v > 0 ? 2u : 0u) << 4), 0x01u | ((v > 0 ? 0u : 2u) << 4), 0x04u, 0x08u);
+}
+__device__ __forceinline__ uint32_t pconj_rxx(uint32_t P, int s) {        // Rxx(s pi/2): Z_d -> -s Y_d X_a, Z_a -> -s X_d Y_a
+    const uint32_t k = (s > 0 ? 3u : 1u) << 4;
+    return pconj(P, 0x01u, 0x07u | k, 0x04u, 0x0Du | k);
+}
+
 __global__ void k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, NoiseDev nd, const double *__restrict__ probs,
                        uint32_t *__restrict__ ev, uint32_t *__restrict__ masks, uint32_t *__restrict__ leak,
                        const uint8_t *__restrict__ active)
@@ -304,7 +330,22 @@ __global__ void k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, NoiseDe
             w |= skip << 24;
             continue;
         }
-        if (in.kind == S17_P_OP_END) { evs[in.word] = w; continue; }
+        if (in.kind == S17_P_OP_END) {
+            // net Pauli at the END of the operation (bits 25-30): every event conjugated through the gates that follow
+            // it; exact because Rxx/Rx/Ry(+-pi/2) are Clifford.  The fast sweep path applies the gates branch-free
+            // and this single Pauli afterwards; the per-gate fields (bits 0-23) stay for the interpreter paths.
+            if (w & 0xFFFFFFu) {
+                const int s = in.b ? 1 : -1;
+                uint32_t N = 0;
+                if (in.a & 1) N = w & 63u;                                            // after Ry(+)
+                if (!skip) { N = pconj_rxx(N, s); N = pmul2((w >> 6) & 63u, N); }
+                if (in.a & 2) { N = pconj_rx(N, -s); N = pmul2((w >> 12) & 63u, N); }
+                if (in.a & 4) { N = pconj_ry(N, -1); N = pmul2((w >> 18) & 63u, N); }
+                w |= N << 25;
+            }
+            evs[in.word] = w;
+            continue;
+        }
         // S17_P_ERR / S17_P_IDLE: one Bernoulli draw per entry (CS:198), none inside a skipped Rxx block
         if (in.in_skip && skip) continue;
         if (pa.noiseless) continue;
@@ -1010,7 +1051,7 @@ static LayerArg2 make_layer2(const LayerArg &A, uint32_t support /* ancilla bits
             op.uops[u].ev_shift == 12) { shape |= 2; ++u; }
         if (ok && u < op.n_uops && op.uops[u].type == S17_U_RY && op.uops[u].sign == -1 && !op.uops[u].skippable &&
             op.uops[u].ev_shift == 18) { shape |= 4; ++u; }
-        if (u != op.n_uops) ok = false;
+        if (u != op.n_uops || op.partial) ok = false;
         c.generic = ok ? 0 : 1;
         c.shape = shape;
         c.s = s;

@@ -111,17 +111,20 @@ __device__ __forceinline__ void tail_slow_copy(const double2 (&in)[4], double2 (
 }
 
 // the same without Pauli events, leak skips, idle masks or coherent rotations: straight-line, constant-bank coefficients
-__device__ __forceinline__ void tail_fast(const double2 (&in)[4], double2 (&out)[8], const FastC f0, const FastC f1) {
+__device__ __forceinline__ void tail_fast(const double2 (&in)[4], double2 (&out)[8], const FastC f0, const FastC f1,
+                                          uint32_t e0, uint32_t e1) {
 #pragma unroll
     for (int bf = 0; bf < 2; ++bf) {          // op 0 acts on (bc, be); the tail ancilla starts in |0>
         double2 v[4] = {in[2 * bf], in[1 + 2 * bf], make_double2(0.0, 0.0), make_double2(0.0, 0.0)};
         g_ry(v, f0.v1); g_rxx(v, f0.s); g_rx(v, f0.sx); g_ry(v, f0.v2);
+        if (e0) g_pauli(v, e0);
         out[2 * bf] = v[0]; out[1 + 2 * bf] = v[1]; out[4 + 2 * bf] = v[2]; out[5 + 2 * bf] = v[3];
     }
 #pragma unroll
     for (int bc = 0; bc < 2; ++bc) {          // op 1 acts on (bf, be)
         double2 v[4] = {out[bc], out[bc + 2], out[bc + 4], out[bc + 6]};
         g_ry(v, f1.v1); g_rxx(v, f1.s); g_rx(v, f1.sx); g_ry(v, f1.v2);
+        if (e1) g_pauli(v, e1);
         out[bc] = v[0]; out[bc + 2] = v[1]; out[bc + 4] = v[2]; out[bc + 6] = v[3];
     }
 }
@@ -213,8 +216,8 @@ k_half(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ LayerAr
             const OpC c1 = P.oc[ps.o1], c2 = P.oc[ps.kind == 1 ? ps.o2 : ps.o1];
             const uint32_t w1 = evw[c1.ev_word];
             const uint32_t w2 = ps.kind == 1 ? evw[c2.ev_word] : 0u;
-            const bool fast = ps.kind != 2 && !(c1.generic | (ps.kind == 1 ? c2.generic : 0)) &&
-                              !((w1 | w2) & 0x1FFFFFFu) && zm == 0;
+            const bool fast = ps.kind != 2 && !(c1.generic | (ps.kind == 1 ? c2.generic : 0)) && zm == 0;
+            const uint32_t e1 = (w1 >> 25) & 63u, e2 = (w2 >> 25) & 63u;
             const bool xonly = !((c1.shape | c2.shape) & 5);
             PassGeom g;
             g.n = kTile / 16;
@@ -228,13 +231,13 @@ k_half(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ LayerAr
                 g.m0 = 1 << lb0; g.m1 = 1 << lb1; g.m2 = g.m3 = 0;
             }
             if (fast) {
-                const FastC f1 = fast_coeffs(c1), f2 = fast_coeffs(c2);
+                const FastC f1 = fast_coeffs(c1, w1), f2 = fast_coeffs(c2, w2);
                 if (ps.kind == 1) {
-                    if (xonly) fast_pass3<1, true>(tile, g, ps, t, f1, f2, 1.0, false);
-                    else fast_pass3<1, false>(tile, g, ps, t, f1, f2, 1.0, false);
+                    if (xonly) fast_pass3<1, true>(tile, g, ps, t, f1, f2, 1.0, false, e1, e2);
+                    else fast_pass3<1, false>(tile, g, ps, t, f1, f2, 1.0, false, e1, e2);
                 } else {
-                    if (xonly) fast_pass3<0, true>(tile, g, ps, t, f1, f2, 1.0, false);
-                    else fast_pass3<0, false>(tile, g, ps, t, f1, f2, 1.0, false);
+                    if (xonly) fast_pass3<0, true>(tile, g, ps, t, f1, f2, 1.0, false, e1, 0);
+                    else fast_pass3<0, false>(tile, g, ps, t, f1, f2, 1.0, false, e1, 0);
                 }
             } else {
 #pragma unroll 1
@@ -246,15 +249,20 @@ k_half(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ LayerAr
 
         // ---- tail operations on registers + 16-bin histogram over (main ancilla value = i, tail ancilla bit)
         bool tail_is_fast;
+        uint32_t te0, te1;
+        FastC tf0, tf1;
         {
             const uint32_t w0 = evw[P.oc[T.op[0]].ev_word], w1 = evw[P.oc[T.op[1]].ev_word];
             bool idle_hit = false;
 #pragma unroll
             for (int k = 0; k < 3; ++k)
                 if (T.idle_word[k] != 255 && (evw[T.idle_word[k]] & T.idle_filter[k])) idle_hit = true;
-            tail_is_fast = !(P.oc[T.op[0]].generic | P.oc[T.op[1]].generic) && !((w0 | w1) & 0x1FFFFFFu) && !idle_hit;
+            tail_is_fast = !(P.oc[T.op[0]].generic | P.oc[T.op[1]].generic) && !idle_hit;
+            te0 = (w0 >> 25) & 63u;
+            te1 = (w1 >> 25) & 63u;
+            tf0 = fast_coeffs(P.oc[T.op[0]], w0);
+            tf1 = fast_coeffs(P.oc[T.op[1]], w1);
         }
-        const FastC tf0 = fast_coeffs(P.oc[T.op[0]]), tf1 = fast_coeffs(P.oc[T.op[1]]);
         double acc[16];
 #pragma unroll
         for (int b = 0; b < 16; ++b) acc[b] = 0.0;
@@ -266,7 +274,7 @@ k_half(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ LayerAr
             for (int r = 0; r < 4; ++r) in[r] = tile[swz(idx0 | ((r & 1) << pC) | ((r >> 1) << pF))];
             const uint32_t gidx0 = (idx0 & 511u) | (((idx0 >> 9) & 1u) << P.A.L.anc_bits[0]) |
                                    (((idx0 >> 10) & 1u) << P.A.L.anc_bits[1]) | (((idx0 >> 11) & 1u) << P.A.L.anc_bits[2]);
-            if (tail_is_fast) tail_fast(in, out, tf0, tf1);
+            if (tail_is_fast) tail_fast(in, out, tf0, tf1, te0, te1);
             else tail_slow_copy(in, out, P, T, evw, gidx0, 1u << pC, 1u << pF);
             double n0 = 0.0, n1 = 0.0;
 #pragma unroll
@@ -357,7 +365,7 @@ k_half(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ LayerAr
             for (int r = 0; r < 4; ++r) in[r] = tile[swz(idx0 | ((r & 1) << pC) | ((r >> 1) << pF))];
             const uint32_t gidx0 = (idx0 & 511u) | (((idx0 >> 9) & 1u) << P.A.L.anc_bits[0]) |
                                    (((idx0 >> 10) & 1u) << P.A.L.anc_bits[1]) | (((idx0 >> 11) & 1u) << P.A.L.anc_bits[2]);
-            if (tail_is_fast) tail_fast(in, out, tf0, tf1);
+            if (tail_is_fast) tail_fast(in, out, tf0, tf1, te0, te1);
             else tail_slow_copy(in, out, P, T, evw, gidx0, 1u << pC, 1u << pF);
             const int be = (sel >> 3) & 1;
 #pragma unroll

@@ -150,11 +150,11 @@ __device__ __forceinline__ void apply_fast(double2 (&a)[16], double v1, double s
 }
 
 struct FastC { double v1, s, sx, v2; };
-__device__ __forceinline__ FastC fast_coeffs(const OpC c) {
+__device__ __forceinline__ FastC fast_coeffs(const OpC c, uint32_t w = 0) {
     FastC f;
     const double s = (double)c.s;
     f.v1 = (c.shape & 1) ? 1.0 : 0.0;
-    f.s = s;
+    f.s = ((w >> 24) & 1u) ? 0.0 : s;          // a leak-skipped Rxx is the identity
     f.sx = (c.shape & 2) ? -s : 0.0;
     f.v2 = (c.shape & 4) ? -1.0 : 0.0;
     return f;

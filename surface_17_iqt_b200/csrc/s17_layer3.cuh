@@ -37,9 +37,15 @@ __device__ __forceinline__ void apply_fast_x(double2 (&a)[16], double s, double 
     S17_FOR_QUADS(g_rxx(v, s); g_rx(v, sx));
 }
 
+template <bool OP2>
+__device__ __forceinline__ void apply_end_pauli(double2 (&a)[16], uint32_t e) {
+    S17_FOR_QUADS(g_pauli(v, e));
+}
+
+// e1 / e2: net Pauli event of the operation, conjugated to its end by k_plan (0: none)
 template <int KIND, bool XONLY, bool SCALE>
 __device__ __forceinline__ void fast_item3(double2 *tile, const PassGeom &g, const PassC &ps, int item, const FastC f1,
-                                           const FastC f2, double sc) {
+                                           const FastC f2, double sc, uint32_t e1 = 0, uint32_t e2 = 0) {
     double2 a[16];
     int off[16];
     item_offsets_swz<KIND>(g, ps, item, off);
@@ -47,22 +53,25 @@ __device__ __forceinline__ void fast_item3(double2 *tile, const PassGeom &g, con
     for (int r = 0; r < 16; ++r) a[r] = tile[off[r]];
     if (XONLY) {
         apply_fast_x<false>(a, f1.s, f1.sx);
+        if (e1) apply_end_pauli<false>(a, e1);
         if (KIND == 1) apply_fast_x<true>(a, f2.s, f2.sx);
     } else {
         apply_fast<false>(a, f1.v1, f1.s, f1.sx, f1.v2);
+        if (e1) apply_end_pauli<false>(a, e1);
         if (KIND == 1) apply_fast<true>(a, f2.v1, f2.s, f2.sx, f2.v2);
     }
+    if (KIND == 1 && e2) apply_end_pauli<true>(a, e2);
 #pragma unroll
     for (int r = 0; r < 16; ++r) tile[off[r]] = SCALE ? make_double2(a[r].x * sc, a[r].y * sc) : a[r];
 }
 
 template <int KIND, bool XONLY>
 __device__ __forceinline__ void fast_pass3(double2 *tile, const PassGeom &g, const PassC &ps, int t, const FastC f1,
-                                           const FastC f2, double sc, bool scale) {
+                                           const FastC f2, double sc, bool scale, uint32_t e1 = 0, uint32_t e2 = 0) {
 #pragma unroll 1
     for (int it = 0; it < kTile / 16 / kL3Threads; ++it) {
-        if (scale) fast_item3<KIND, XONLY, true>(tile, g, ps, t + kL3Threads * it, f1, f2, sc);
-        else fast_item3<KIND, XONLY, false>(tile, g, ps, t + kL3Threads * it, f1, f2, sc);
+        if (scale) fast_item3<KIND, XONLY, true>(tile, g, ps, t + kL3Threads * it, f1, f2, sc, e1, e2);
+        else fast_item3<KIND, XONLY, false>(tile, g, ps, t + kL3Threads * it, f1, f2, sc, e1, e2);
     }
 }
 
@@ -172,8 +181,10 @@ k_layer3(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Layer
             const OpC c1 = P.oc[ps.o1], c2 = P.oc[ps.kind == 1 ? ps.o2 : ps.o1];
             const uint32_t w1 = evw[c1.ev_word];
             const uint32_t w2 = ps.kind == 1 ? evw[c2.ev_word] : 0u;
-            const bool fast = ps.kind != 2 && !(c1.generic | (ps.kind == 1 ? c2.generic : 0)) &&
-                              !((w1 | w2) & 0x1FFFFFFu) && zm == 0;
+            // fast path: standard (Clifford) ops, no idle mask; Pauli events arrive as one net Pauli per op, a leak
+            // skip as a zero coefficient
+            const bool fast = ps.kind != 2 && !(c1.generic | (ps.kind == 1 ? c2.generic : 0)) && zm == 0;
+            const uint32_t e1 = (w1 >> 25) & 63u, e2 = (w2 >> 25) & 63u;
             const bool xonly = !((c1.shape | c2.shape) & 5);
             PassGeom g;
             g.n = kTile / 16;
@@ -188,14 +199,14 @@ k_layer3(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Layer
             }
             // 256 items per pass, two per thread
             if (fast) {
-                const FastC f1 = fast_coeffs(c1), f2 = fast_coeffs(c2);
+                const FastC f1 = fast_coeffs(c1, w1), f2 = fast_coeffs(c2, w2);
                 const bool scale = ps.last && sc != 1.0;
                 if (ps.kind == 1) {
-                    if (xonly) fast_pass3<1, true>(tile, g, ps, t, f1, f2, sc, scale);
-                    else fast_pass3<1, false>(tile, g, ps, t, f1, f2, sc, scale);
+                    if (xonly) fast_pass3<1, true>(tile, g, ps, t, f1, f2, sc, scale, e1, e2);
+                    else fast_pass3<1, false>(tile, g, ps, t, f1, f2, sc, scale, e1, e2);
                 } else {
-                    if (xonly) fast_pass3<0, true>(tile, g, ps, t, f1, f2, sc, scale);
-                    else fast_pass3<0, false>(tile, g, ps, t, f1, f2, sc, scale);
+                    if (xonly) fast_pass3<0, true>(tile, g, ps, t, f1, f2, sc, scale, e1, 0);
+                    else fast_pass3<0, false>(tile, g, ps, t, f1, f2, sc, scale, e1, 0);
                 }
             } else {
 #pragma unroll 1
