@@ -247,7 +247,13 @@ def compile_program(model, list_len, fusion=1, cooling=False, over_angles=None, 
                     emit(**kw)
             # a: which single-qubit gates the op has, b: sign of the Rxx angle -- lets the planner conjugate the op's
             # Pauli events through the remaining (Clifford) gates to one net Pauli at the end of the op
-            emit(kind=L.P_OP_END, word=op.index, a=int(op.has_ry1) | (int(op.has_rx) << 1) | (int(op.has_ry2) << 2),
+            # a bits 3-6 / slot: the frame in which the op's half cycle is diagonal (s17_diag.cuh): bit3 Hadamard frame
+            # (x-type half), bit4 first / bit6 last operation of its half, bit5 half index; slot = data bit
+            half = 0 if op.kind == "x" else 1
+            same = [o.index for o in ops if o.kind == op.kind]
+            emit(kind=L.P_OP_END, word=op.index, slot=op.data_bit,
+                 a=int(op.has_ry1) | (int(op.has_rx) << 1) | (int(op.has_ry2) << 2) | (int(op.kind == "x") << 3) |
+                 (int(op.index == min(same)) << 4) | (half << 5) | (int(op.index == max(same)) << 6),
                  b=int(op.s > 0))
         if cooling and t < 7:                          # sympathetic_cooling (CS:762-772) after timesteps 1-7
             for q in range(N_DATA + N_ANC):

@@ -310,11 +310,12 @@ __device__ __forceinline__ uint32_t pconj_rxx(uint32_t P, int s) {        // Rxx
 
 __global__ void k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, NoiseDev nd, const double *__restrict__ probs,
                        uint32_t *__restrict__ ev, uint32_t *__restrict__ masks, uint32_t *__restrict__ leak,
-                       const uint8_t *__restrict__ active)
+                       const uint8_t *__restrict__ active, uint32_t *__restrict__ frm)
 {
     const int shot = blockIdx.x * blockDim.x + threadIdx.x;
     if (shot >= pa.n_shots || !active[shot]) return;
     Philox rng(pa.seed, pa.first_shot + shot, pa.stream);
+    uint32_t f_flip = 0, f_sign = 0, f_phase = 0;      // frame bookkeeping of the current half cycle (k_cycle)
     uint32_t lk = leak[shot];
     uint32_t *evs = ev + (size_t)shot * S17_EV_WORDS;
     uint32_t *mk = masks + (size_t)shot * (2 * S17_MASK_WORDS);
@@ -334,15 +335,35 @@ __global__ void k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, NoiseDe
             // net Pauli at the END of the operation (bits 25-30): every event conjugated through the gates that follow
             // it; exact because Rxx/Rx/Ry(+-pi/2) are Clifford.  The fast sweep path applies the gates branch-free
             // and this single Pauli afterwards; the per-gate fields (bits 0-23) stay for the interpreter paths.
+            uint32_t N = 0;
             if (w & 0xFFFFFFu) {
                 const int s = in.b ? 1 : -1;
-                uint32_t N = 0;
                 if (in.a & 1) N = w & 63u;                                            // after Ry(+)
                 if (!skip) { N = pconj_rxx(N, s); N = pmul2((w >> 6) & 63u, N); }
                 if (in.a & 2) { N = pconj_rx(N, -s); N = pmul2((w >> 12) & 63u, N); }
                 if (in.a & 4) { N = pconj_ry(N, -1); N = pmul2((w >> 18) & 63u, N); }
                 w |= N << 25;
             }
+            // The same Pauli in the frame where the half cycle is diagonal (s17_diag.cuh; a: bit3 Hadamard frame,
+            // bit4 first / bit6 last operation of its half, bit5 half index; slot = data bit): a data X relabels
+            // the basis (flip mask; bit 31 tells the operation whether its own label bit is flipped), a data Z is a
+            // label-dependent sign (sign mask) and the rest is a global phase.
+            const uint32_t d = in.slot;
+            if (in.a & 16) { f_flip = 0; f_sign = 0; f_phase = 0; }
+            w |= ((f_flip >> d) & 1u) << 31;
+            if (N) {
+                uint32_t F = N;
+                if (in.a & 8) {                        // H X^x Z^z H = (-1)^{xz} X^z Z^x
+                    const uint32_t x = N & 1u, z = (N >> 1) & 1u, k = (N >> 4) & 3u;
+                    F = (N & 0x0Cu) | z | (x << 1) | (((k + 2u * (x & z)) & 3u) << 4);
+                } else if (!(in.a & 4)) {              // still inside the Ry bracket of its data qubit
+                    F = pconj_ry(N, -1);
+                }
+                if (F & 2u) { f_sign ^= 1u << d; f_phase += 2u * ((f_flip >> d) & 1u); }
+                if (F & 1u) f_flip ^= 1u << d;
+                f_phase += (F >> 4) & 3u;
+            }
+            if (in.a & 64) frm[(size_t)shot * 4 + ((in.a >> 5) & 1u)] = f_flip | (f_sign << 9) | ((f_phase & 3u) << 18);
             evs[in.word] = w;
             continue;
         }
@@ -526,6 +547,7 @@ __global__ void k_record(MeasArgs ma, const uint32_t *__restrict__ meas_out, con
 
 }  // namespace s17
 #include "s17_half.cuh"
+#include "s17_diag.cuh"
 namespace s17 {
 
 // ProjectQ collapse + renormalise for the 8 measured ancillas, fused with the reset X gates (CS:859-862):
@@ -800,6 +822,11 @@ struct s17_ctx {
     LayerArg2 half_prog[3][2];
     HalfTail half_tail[3][2];
     bool half_ok[3] = {false, false, false};
+    // whole-cycle diagonal-frame programs (k_cycle) per cycle kind, when the cycle has that structure
+    DiagProg diag_prog[3];
+    bool diag_ok[3] = {false, false, false};
+    bool no_diag = false;
+    uint32_t *frm = nullptr;          // per shot: frame words of the two half cycles (k_plan -> k_cycle)
     bool no_fuse = false;
     bool debug_sync = false;
     std::string debug_note;
@@ -923,6 +950,9 @@ extern "C" int s17_create(s17_ctx **out, int device, uint64_t max_shots) {
     CK(cudaMalloc(&ctx->act_list, B * 4));
     CK(cudaMalloc(&ctx->n_act, 4));
     CK(cudaMalloc(&ctx->meas_out, B * 2 * 4));
+    CK(cudaMalloc(&ctx->frm, B * 4 * 4));
+    CK(cudaMemset(ctx->frm, 0, B * 4 * 4));
+    CK(cudaFuncSetAttribute(k_cycle, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDgSmem));
     {
         typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -949,6 +979,8 @@ extern "C" int s17_create(s17_ctx **out, int device, uint64_t max_shots) {
         ctx->debug_sync = ds && ds[0] == '1';
         const char *nf = getenv("S17_FUSE");
         ctx->no_fuse = nf && nf[0] == '0';
+        const char *nd = getenv("S17_DIAG");
+        ctx->no_diag = nd && nd[0] == '0';
         const char *r = getenv("S17_RING");
         ctx->force_ring = r && r[0] == '1';
     }
@@ -975,7 +1007,8 @@ extern "C" int s17_destroy(s17_ctx *ctx) {
     }
     void *ptrs[] = {ctx->state, ctx->ev, ctx->masks, ctx->leak, ctx->active, ctx->ready, ctx->forced, ctx->hist,
                     ctx->aux, ctx->rec, ctx->counters, ctx->lut, ctx->cw16, ctx->probs, ctx->cum, ctx->plan,
-                    ctx->rtf_slots, ctx->rtf_rounds, ctx->rtf_syndb, ctx->act_list, ctx->n_act, ctx->zero_page, ctx->meas_out};
+                    ctx->rtf_slots, ctx->rtf_rounds, ctx->rtf_syndb, ctx->act_list, ctx->n_act, ctx->zero_page, ctx->meas_out,
+                    ctx->frm};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
@@ -1210,6 +1243,83 @@ static bool make_half(const std::vector<LayerArg> &layers, size_t begin, size_t 
     return P.n_pass <= S17_MAX_LAYER_OPS;
 }
 
+// Lower a fused half cycle (make_half) to the diagonal-frame form of k_cycle.  Returns false when the half cycle is not
+// of that form: an idle mask, a non-standard operation, or single-qubit gates that do not bracket the data qubits.
+static bool make_diag_half(const LayerArg2 &P, const HalfTail &T, int half_index, const s17_pinstr *plan, uint32_t n_plan,
+                           DiagHalf &H) {
+    memset(&H, 0, sizeof(H));
+    memset(H.lane_bit, 255, sizeof(H.lane_bit));
+    const s17_layer &L = P.A.L;
+    bool any_ry = false, all_x = true;
+    int first_idx[9], last_idx[9], min_word = 255, max_word = -1;
+    for (int d = 0; d < 9; ++d) first_idx[d] = last_idx[d] = -1;
+    std::vector<int> order;                                   // operations in time order (= event word order)
+    for (int o = 0; o < L.n_ops; ++o) {
+        if (L.ops[o].kind != S17_OP_ENT || P.oc[o].generic) return false;
+        order.push_back(o);
+    }
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return L.ops[a].ev_word < L.ops[b].ev_word; });
+    for (int o : order) {
+        const int d = L.ops[o].data_bit;
+        if (P.oc[o].shape & 5) { any_ry = true; all_x = false; }
+        if (first_idx[d] < 0) first_idx[d] = o;
+        last_idx[d] = o;
+        min_word = std::min(min_word, (int)L.ops[o].ev_word);
+        max_word = std::max(max_word, (int)L.ops[o].ev_word);
+    }
+    if (any_ry) {
+        // computational frame: on every data qubit the first operation opens the bracket with Ry(+), the last one
+        // closes it with Ry(-), nothing in between carries an Ry
+        for (int o : order) {
+            const int d = L.ops[o].data_bit;
+            const bool want1 = (o == first_idx[d]), want2 = (o == last_idx[d]);
+            if (((P.oc[o].shape & 1) != 0) != want1 || ((P.oc[o].shape & 4) != 0) != want2) return false;
+        }
+    }
+    H.frame_x = all_x ? 1 : 0;
+    for (int o : order) {
+        const s17_op &op = L.ops[o];
+        int k;
+        if (op.anc_bit == T.e_bit) k = 3;
+        else {
+            k = P.oc[o].lb1 - 9;
+            if (k < 0 || k > 2) return false;
+        }
+        if (H.n_ops[k] >= 4) return false;
+        for (int j = 0; j < H.n_ops[k]; ++j)
+            if (H.ops[k][j].d == op.data_bit) return false;          // table index bits must be distinct label bits
+        DiagOp &dop = H.ops[k][H.n_ops[k]++];
+        dop.d = op.data_bit;
+        dop.ev_word = op.ev_word;
+        dop.s_neg = P.oc[o].s < 0 ? 1 : 0;
+        dop.has_rx = (P.oc[o].shape & 2) ? 1 : 0;
+        H.aj[k] = (uint8_t)(op.anc_bit - 9);
+        // k_plan must have been told the same frame, data bit and half boundaries for this operation
+        bool found = false;
+        for (uint32_t i = 0; i < n_plan; ++i) {
+            const s17_pinstr &in = plan[i];
+            if (in.kind != S17_P_OP_END || in.word != op.ev_word) continue;
+            found = true;
+            if (in.slot != op.data_bit || ((in.a & 8) != 0) != all_x || ((in.a >> 5) & 1) != half_index) return false;
+            if (((in.a & 16) != 0) != (op.ev_word == min_word) || ((in.a & 64) != 0) != (op.ev_word == max_word)) return false;
+            if ((in.a & 7) != P.oc[o].shape || (in.b != 0) != (P.oc[o].s > 0)) return false;
+        }
+        if (!found) return false;
+    }
+    // where each table index bit comes from: label = i | lane << 4 in the Hadamard frame, lane | i << 5 otherwise
+    for (int k = 0; k < 4; ++k)
+        for (int j = 0; j < H.n_ops[k]; ++j) {
+            const int d = H.ops[k][j].d;
+            const int reg_lo = all_x ? 0 : 5, reg_n = 4, lane_lo = all_x ? 4 : 0;
+            if (d >= reg_lo && d < reg_lo + reg_n) {
+                for (int i = 0; i < 16; ++i) H.ridx[k][i] |= (uint8_t)(((i >> (d - reg_lo)) & 1) << j);
+            } else {
+                H.lane_bit[k][j] = (uint8_t)(d - lane_lo);
+            }
+        }
+    return true;
+}
+
 extern "C" int s17_load_program(s17_ctx *ctx, const s17_layer *layers, const uint32_t n_layers[3], const double *params,
                                 uint32_t n_params, const s17_pinstr *plan, uint32_t n_plan, const s17_lists *lists) {
     if (!ctx || !layers || !n_layers || !plan || !lists) return fail(ctx, S17_E_ARG, "s17_load_program: bad arguments");
@@ -1266,6 +1376,12 @@ extern "C" int s17_load_program(s17_ctx *ctx, const s17_layer *layers, const uin
                               make_half(ctx->layers[c], 0, cuts[0], ctx->half_prog[c][0], ctx->half_tail[c][0]) &&
                               make_half(ctx->layers[c], cuts[0], cuts[1], ctx->half_prog[c][1], ctx->half_tail[c][1]);
             if (ctx->half_ok[c]) { ctx->half_tail[c][0].final_part = 0; ctx->half_tail[c][1].final_part = 1; }
+            // whole-cycle diagonal-frame form: Hadamard-frame half followed by a computational-frame half
+            ctx->diag_ok[c] = ctx->half_ok[c] &&
+                              make_diag_half(ctx->half_prog[c][0], ctx->half_tail[c][0], 0, plan, n_plan, ctx->diag_prog[c].h[0]) &&
+                              make_diag_half(ctx->half_prog[c][1], ctx->half_tail[c][1], 1, plan, n_plan, ctx->diag_prog[c].h[1]) &&
+                              ctx->diag_prog[c].h[0].frame_x == 1 && ctx->diag_prog[c].h[1].frame_x == 0;
+            if (ctx->diag_ok[c]) { ctx->diag_prog[c].h[0].final_part = 0; ctx->diag_prog[c].h[1].final_part = 1; }
         }
     }
     if (ctx->plan) { cudaFree(ctx->plan); ctx->plan = nullptr; }
@@ -1383,7 +1499,7 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
     {
         SCOPE(CAT_OTHER);
         k_plan<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(ctx->plan, pa, ctx->nd, ctx->probs, ctx->ev, ctx->masks,
-                                                            ctx->leak, ctx->active);
+                                                            ctx->leak, ctx->active, ctx->frm);
     }
     const int which = stage == 0 ? 0 : (second ? 2 : 1);
     const std::vector<LayerArg> &Ls = ctx->layers[which];
@@ -1401,7 +1517,28 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
     ma.seed = a.seed;
     ma.first_shot = a.first_shot_id;
     ma.n_shots = n;
-    if (ctx->half_ok[which] && !dense && !mid_collapse && !max_layers && !ctx->use_v1 && !ctx->force_ring && !ctx->no_fuse) {
+    const bool fused_ok = !dense && !mid_collapse && !max_layers && !ctx->use_v1 && !ctx->force_ring && !ctx->no_fuse;
+    if (ctx->diag_ok[which] && fused_ok && !ctx->no_diag) {
+        // production path for Clifford cycles with Pauli / leakage noise: the whole cycle in the frame where it is
+        // diagonal, one warp per shot, the state in registers (s17_diag.cuh)
+        ma.mask = 0xFFu;
+        ma.final_part = 1;
+        ma.stream = 16u + (uint32_t)stage * 4u;
+        {
+            SCOPE(CAT_GATE);
+            k_cycle<<<ctx->num_sms, kDgThreads, kDgSmem, ctx->stream>>>(
+                ctx->diag_prog[which], ma, ctx->state, ctx->ev, ctx->frm, ctx->act_list, ctx->n_act, ctx->aux, ctx->forced,
+                ctx->meas_out, ctx->counters, init_basis);
+            ctx->n_gate++;
+        }
+        {
+            SCOPE(CAT_MEAS);
+            k_record<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(ma, ctx->meas_out, ctx->lut, ctx->leak, ctx->active,
+                                                                  ctx->ready, ctx->rec, ctx->counters);
+        }
+        return S17_OK;
+    }
+    if (ctx->half_ok[which] && fused_ok) {
         // production path: one fused kernel per half cycle (gates + measurement + collapse), state stays on chip
         for (int h = 0; h < 2; ++h) {
             ma.mask = ctx->half_tail[which][h].meas_mask;

@@ -1,0 +1,338 @@
+// s17_diag.cuh -- one whole stabiliser cycle per shot in the frame where its gates are diagonal (k_cycle).
+//
+// Both halves of the compiled cycle are diagonal in a product basis of the nine data qubits:
+//   * timesteps 1-4 (x_type_entangling, CS:291-309) contain only Rxx(+-pi/2) and Rx(-+pi/2): functions of X_d and
+//     X_d X_a, diagonal after a Walsh-Hadamard transform of the data register;
+//   * timesteps 5-8 (z_type_entangling, CS:312-344) bracket the same gates between Ry(+pi/2) ... Ry(-pi/2) on each data
+//     qubit, and Ry(-pi/2) f(X) Ry(+pi/2) = f(Z): diagonal in the computational basis as they stand.
+// With lambda = (-1)^{bit d of the basis label} an operation (d, a, s) is
+//     Rxx(s pi/2)  ->  (1 - i s lambda X_a)/sqrt2  on ancilla a,       Rx(-s pi/2)  ->  the phase (1 + i s lambda)/sqrt2,
+// so for a fixed label the four ancillas stay in a PRODUCT state that depends only on the <= 4 label bits of the data
+// qubits the ancilla talks to.  Per shot and half cycle the kernel therefore builds, per ancilla, a 16-entry table of
+// (amplitude for outcome 0, amplitude for outcome 1, their squared moduli) and the whole half cycle is
+//     for each ancilla:  P(0), P(1) = sum_x |psi_x|^2 |T[idx(x)][.]|^2;  sample;  psi_x *= T[idx(x)][outcome].
+// Pauli events (k_plan's net end-of-operation Pauli, conjugated into the frame) are label relabelings (flip mask),
+// signs (sign mask, global phase) and ancilla X/Z applied while the tables are built; a leak-skipped Rxx is the
+// identity.  The derivation is executable: tests/diag_model.py, checked against a brute-force simulation in
+// tests/test_diag_frame_model.py.
+//
+// One WARP owns one shot: the 512 amplitudes live in registers (16 per lane) for the whole cycle, the Walsh-Hadamard
+// transform is two in-register radix-16 passes, one shuffle stage and one exchange through shared memory.  HBM traffic
+// per shot and cycle: 8 KiB read + 8 KiB written (+ ~200 B of metadata), prefetched one shot ahead by TMA.
+// Exact same measurement semantics as k_half / k_measure (one Measure per ancilla, conditional on the earlier ones).
+// Included by s17.cu after MeasArgs.
+#pragma once
+
+namespace s17 {
+
+constexpr int kDgWarps = 11;                                   // warps (= shots in flight) per SM
+constexpr int kDgThreads = kDgWarps * 32;
+constexpr int kDgFrmBytes = 16;                                // per-shot frame words (4 x u32, two used)
+constexpr int kDgMetaBytes = kEvBytes + kAuxBytes + kDgFrmBytes;
+constexpr int kDgTabBytes = 3 * 64 * 16;                       // A0 / A1 / Q tables: 4 ancilla slots x 16 entries
+constexpr int kDgWarpBytes = 2 * kRunBytes + kDgTabBytes + 3 * kDgMetaBytes + 64;
+constexpr size_t kDgSmem = (size_t)kDgWarps * kDgWarpBytes;
+static_assert(kDgWarpBytes % 16 == 0, "per-warp shared memory must keep 16-byte alignment");
+
+struct DiagOp { uint8_t d, ev_word, s_neg, has_rx; };
+struct DiagHalf {
+    uint8_t frame_x;           // 1: Walsh-Hadamard frame (x-type half), 0: computational frame (z-type half)
+    uint8_t final_part;        // 1: completes the cycle's All(Measure) | ancilla
+    uint8_t pad[2];
+    uint8_t n_ops[4];          // operations per ancilla slot
+    uint8_t aj[4];             // ancilla index (outcome bit) of slot k
+    DiagOp ops[4][4];          // per slot, in time order; table index bit j = label bit of ops[k][j].d
+    uint8_t lane_bit[4][4];    // lane bit that feeds table index bit j (255: the bit comes from the register index)
+    uint8_t ridx[4][16];       // register-index part of the table index
+};
+struct DiagProg { DiagHalf h[2]; };
+
+__device__ __forceinline__ double2 dg_cmul(const double2 a, const double2 b) {
+    return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
+}
+// label of register i of this lane.  map 1: x = lane | i << 5 (as loaded / stored);  map 2: x = i | lane << 4
+template <int MAP>
+__device__ __forceinline__ uint32_t dg_label(int lane, int i) {
+    return MAP == 1 ? (uint32_t)(lane | (i << 5)) : (uint32_t)(i | (lane << 4));
+}
+// exchange layout: 16-byte column = low three label bits ^ bits 4-6, conflict-free for both mappings
+__device__ __forceinline__ int dg_swz(uint32_t x) { return (int)(x ^ ((x >> 4) & 7u)); }
+
+__device__ __forceinline__ void dg_wht16(double2 (&p)[16]) {
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if (i & (1 << b)) continue;
+            const double2 u = p[i], v = p[i | (1 << b)];
+            p[i] = make_double2(u.x + v.x, u.y + v.y);
+            p[i | (1 << b)] = make_double2(u.x - v.x, u.y - v.y);
+        }
+    }
+}
+__device__ __forceinline__ void dg_wht_lane4(double2 (&p)[16], int lane) {
+    const bool hi = (lane & 16) != 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const double ox = __shfl_xor_sync(0xffffffffu, p[i].x, 16), oy = __shfl_xor_sync(0xffffffffu, p[i].y, 16);
+        p[i] = hi ? make_double2(ox - p[i].x, oy - p[i].y) : make_double2(p[i].x + ox, p[i].y + oy);
+    }
+}
+// label bits 5-8 and 4 (map 1), exchange, label bits 0-3 (map 2)
+__device__ __forceinline__ void dg_wht_forward(double2 (&p)[16], double2 *xb, int lane) {
+    dg_wht16(p);
+    dg_wht_lane4(p, lane);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) xb[dg_swz(dg_label<1>(lane, i))] = p[i];
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) p[i] = xb[dg_swz(dg_label<2>(lane, i))];
+    dg_wht16(p);
+}
+__device__ __forceinline__ void dg_wht_inverse(double2 (&p)[16], double2 *xb, int lane) {
+    dg_wht16(p);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) xb[dg_swz(dg_label<2>(lane, i))] = p[i];
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) p[i] = xb[dg_swz(dg_label<1>(lane, i))];
+    dg_wht_lane4(p, lane);
+    dg_wht16(p);
+}
+
+// per-ancilla tables of one half cycle: two of the 64 (slot, index) entries per lane
+__device__ __forceinline__ void dg_build_tables(const DiagHalf &H, const uint32_t *evw, double2 *A0, double2 *A1,
+                                                double2 *Q, int lane) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int e = lane + 32 * r, k = e >> 4, idx = e & 15;
+        double2 u = make_double2(1.0, 0.0), v = make_double2(0.0, 0.0), ph = make_double2(1.0, 0.0);
+        const int n = H.n_ops[k];
+        for (int j = 0; j < n; ++j) {
+            const DiagOp op = H.ops[k][j];
+            const uint32_t w = evw[op.ev_word];
+            // sigma = s lambda, lambda evaluated on the label bit as relabeled by the data flips so far (bit 31)
+            const uint32_t neg = (uint32_t)op.s_neg ^ ((uint32_t)(idx >> j) & 1u) ^ (w >> 31);
+            const double sg = neg ? -1.0 : 1.0;
+            if (!((w >> 24) & 1u)) {                          // Rxx unless leak-skipped: (u, v) -> (u - i sg v, v - i sg u)
+                const double2 nu = make_double2(fma(sg, v.y, u.x), fma(-sg, v.x, u.y));
+                const double2 nv = make_double2(fma(sg, u.y, v.x), fma(-sg, u.x, v.y));
+                u = nu; v = nv;
+            }
+            if (op.has_rx) ph = make_double2(fma(-sg, ph.y, ph.x), fma(sg, ph.x, ph.y));      // (1 + i sg) ph
+            if ((w >> 28) & 1u) v = make_double2(-v.x, -v.y);                                  // net event: Z on the ancilla
+            if ((w >> 27) & 1u) { const double2 t = u; u = v; v = t; }                         //            X on the ancilla
+        }
+        const double2 a0 = dg_cmul(ph, u), a1 = dg_cmul(ph, v);
+        A0[e] = a0;
+        A1[e] = a1;
+        Q[e] = make_double2(fma(a0.x, a0.x, a0.y * a0.y), fma(a1.x, a1.x, a1.y * a1.y));
+    }
+}
+
+// one half cycle on the register-resident state.  Returns the raw outcome bits (ancilla-indexed) | 0x100 if a forced
+// outcome had probability zero.  FRAME_X: p is in map 1 on entry and exit, map 2 in between.
+template <bool FRAME_X>
+__device__ __forceinline__ uint32_t dg_half(double2 (&p)[16], const DiagHalf &H, const int (&lidx)[4], const uint32_t *evw,
+                                            uint32_t fw, double2 *A0, double2 *A1, double2 *Q, double2 *xb, int lane,
+                                            bool forced, uint32_t fo, double uu, int u_base) {
+    constexpr int MAP = FRAME_X ? 2 : 1;
+    if (FRAME_X) dg_wht_forward(p, xb, lane);
+    __syncwarp();
+    dg_build_tables(H, evw, A0, A1, Q, lane);
+    __syncwarp();
+    uint32_t a_out = 0;
+    bool bad = false;
+    double pfin = 1.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (H.n_ops[k] == 0) continue;
+        const int li = lidx[k] + 16 * k;
+        double p0 = 0.0, p1 = 0.0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const double2 q = Q[li | H.ridx[k][i]];
+            const double w = fma(p[i].x, p[i].x, p[i].y * p[i].y);
+            p0 = fma(w, q.x, p0);
+            p1 = fma(w, q.y, p1);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            p0 += __shfl_xor_sync(0xffffffffu, p0, d);
+            p1 += __shfl_xor_sync(0xffffffffu, p1, d);
+        }
+        uint32_t out;
+        if (forced) {
+            out = (fo >> H.aj[k]) & 1u;
+            if ((out ? p1 : p0) <= 0.0) bad = true;
+        } else {
+            const double u = __shfl_sync(0xffffffffu, uu, u_base + k);
+            out = (u * (p0 + p1) < p1) ? 1u : 0u;            // Measure: P(1) against one uniform, as k_measure
+        }
+        const double2 *A = out ? A1 : A0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) p[i] = dg_cmul(p[i], A[li | H.ridx[k][i]]);
+        a_out |= out << H.aj[k];
+        pfin = out ? p1 : p0;
+    }
+    // renormalise (the squared norm of the selected branch is the last conditional weight), event signs and phase
+    const uint32_t zacc = (fw >> 9) & 511u, g = (fw >> 18) & 3u, fm = fw & 511u;
+    const double nrm = FRAME_X ? pfin * 512.0 : pfin;          // the inverse transform multiplies the norm^2 by 512
+    const double inv = nrm > 0.0 ? 1.0 / sqrt(nrm) : 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const double sc = (__popc(dg_label<MAP>(lane, i) & zacc) & 1) ? -inv : inv;
+        double2 v = make_double2(p[i].x * sc, p[i].y * sc);
+        if (g == 1) v = make_double2(-v.y, v.x);
+        else if (g == 2) v = make_double2(-v.x, -v.y);
+        else if (g == 3) v = make_double2(v.y, -v.x);
+        p[i] = v;
+    }
+    if (FRAME_X) {
+        dg_wht_inverse(p, xb, lane);
+        if (fm) {                                             // data flips in the Hadamard frame are signs afterwards
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (__popc(dg_label<1>(lane, i) & fm) & 1) p[i] = make_double2(-p[i].x, -p[i].y);
+        }
+    }
+    return a_out | (bad ? 0x100u : 0u);
+}
+
+__global__ void __launch_bounds__(kDgThreads, 1)
+k_cycle(const __grid_constant__ DiagProg P, const __grid_constant__ MeasArgs ma, double2 *__restrict__ state,
+        const uint32_t *__restrict__ ev, const uint32_t *__restrict__ frm, const uint32_t *__restrict__ act_list,
+        const uint32_t *__restrict__ n_act_ptr, ShotAux *__restrict__ aux, const uint8_t *__restrict__ forced,
+        uint32_t *__restrict__ meas_out, unsigned long long *__restrict__ counters, int init_basis)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *wb = smem_raw + (size_t)warp * kDgWarpBytes;
+    double2 *buf = reinterpret_cast<double2 *>(wb);                                  // [2][512]
+    double2 *A0 = reinterpret_cast<double2 *>(wb + 2 * kRunBytes), *A1 = A0 + 64, *Q = A1 + 64;
+    unsigned char *meta = wb + 2 * kRunBytes + kDgTabBytes;                          // [3][kDgMetaBytes]
+    uint64_t *full = reinterpret_cast<uint64_t *>(meta + 3 * kDgMetaBytes);          // [2]
+    uint64_t *mfull = full + 2;                                                      // [3]
+
+    const uint32_t n_items = *n_act_ptr;
+    const uint32_t n_warps = gridDim.x * kDgWarps, gw = blockIdx.x * kDgWarps + warp;
+    const uint32_t chunk = (n_items + n_warps - 1) / n_warps;
+    const uint32_t first = gw * chunk, last = min(n_items, first + chunk);
+    if (first >= last) return;                    // no CTA-wide barrier below: warps are independent
+
+    if (lane == 0) {
+        mbar_init(&full[0], 1); mbar_init(&full[1], 1);
+        mbar_init(&mfull[0], 1); mbar_init(&mfull[1], 1); mbar_init(&mfull[2], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    // lane part of the table indices (shot independent)
+    int lidx[2][4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int li = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int lb = P.h[h].lane_bit[k][j];
+                if (lb != 255) li |= ((lane >> lb) & 1) << j;
+            }
+            lidx[h][k] = li;
+        }
+
+    auto issue_meta = [&](uint32_t shot_, int slot) {
+        unsigned char *m = meta + slot * kDgMetaBytes;
+        mbar_expect_tx(&mfull[slot], kDgMetaBytes);
+        tma_load_1d(m, ev + (size_t)shot_ * S17_EV_WORDS, kEvBytes, &mfull[slot]);
+        tma_load_1d(m + kEvBytes, aux + shot_, kAuxBytes, &mfull[slot]);
+        tma_load_1d(m + kEvBytes + kAuxBytes, frm + (size_t)shot_ * 4, kDgFrmBytes, &mfull[slot]);
+    };
+    auto issue_state = [&](uint32_t shot_, int slot, int sb) {
+        const ShotAux *ax = reinterpret_cast<const ShotAux *>(meta + slot * kDgMetaBytes + kEvBytes);
+        const uint32_t blk = ax->collapsed ? 0u : ax->anc_outcome;       // lazy collapse + reset: the surviving block
+        fence_proxy_async_smem();                 // the buffer was last touched through the generic proxy
+        mbar_expect_tx(&full[sb], kRunBytes);
+        tma_load_1d(buf + sb * kRun, state + (size_t)shot_ * kDim + (size_t)blk * kRun, kRunBytes, &full[sb]);
+    };
+
+    uint32_t shot = act_list[first];
+    uint32_t shot1 = first + 1 < last ? act_list[first + 1] : 0u;
+    if (lane == 0) {
+        issue_meta(shot, 0);
+        if (first + 1 < last) issue_meta(shot1, 1);
+    }
+    mbar_wait(&mfull[0], 0);
+    if (init_basis < 0 && lane == 0) issue_state(shot, 0, 0);
+
+    const uint32_t nout = 8u * (uint32_t)ma.stage;
+    uint32_t j = 0;
+    for (uint32_t item = first; item < last; ++item, ++j) {
+        const int slot = (int)(j % 3u), sb = (int)(j & 1u);
+        uint32_t shot2 = 0;
+        if (item + 2 < last) {
+            shot2 = act_list[item + 2];
+            if (lane == 0) issue_meta(shot2, (int)((j + 2u) % 3u));
+        }
+        if (item + 1 < last) {
+            mbar_wait(&mfull[(j + 1u) % 3u], ((j + 1u) / 3u) & 1u);
+            if (init_basis < 0 && lane == 0) issue_state(shot1, (int)((j + 1u) % 3u), sb ^ 1);
+        }
+        const uint32_t *evw = reinterpret_cast<const uint32_t *>(meta + slot * kDgMetaBytes);
+        const uint32_t *fwp = reinterpret_cast<const uint32_t *>(meta + slot * kDgMetaBytes + kEvBytes + kAuxBytes);
+        double2 *xb = buf + sb * kRun;
+
+        // replayed outcomes of this cycle's eight ancillas / the eight uniforms of its Measure gates
+        uint32_t fo = 0;
+        double uu = 0.0;
+        if (ma.forced) {
+            const uint32_t b = lane < 8 ? (uint32_t)forced[(size_t)shot * S17_MAX_OUTCOMES + nout + lane] : 0u;
+            fo = __ballot_sync(0xffffffffu, (b & 1u) != 0u) & 0xFFu;
+        } else if (lane < 8) {
+            Philox rng(ma.seed, ma.first_shot + shot, ma.stream + ((lane >> 2) ? 0u : 1u));
+            rng.c3 = (uint32_t)(lane & 3);
+            uu = rng.next();
+        }
+
+        double2 p[16];
+        if (init_basis < 0) {
+            mbar_wait(&full[sb], (j >> 1) & 1u);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) p[i] = xb[dg_label<1>(lane, i)];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                p[i] = make_double2((int)dg_label<1>(lane, i) == init_basis ? 1.0 : 0.0, 0.0);
+        }
+        __syncwarp();                             // every lane holds its amplitudes: the buffer becomes exchange scratch
+
+        const uint32_t r0 = dg_half<true>(p, P.h[0], lidx[0], evw, fwp[0], A0, A1, Q, xb, lane, ma.forced != 0, fo, uu, 0);
+        const uint32_t r1 = dg_half<false>(p, P.h[1], lidx[1], evw, fwp[1], A0, A1, Q, xb, lane, ma.forced != 0, fo, uu, 4);
+
+        // data flips of the computational-frame half are a relabeling: applied by the store
+        const uint32_t fm1 = fwp[1] & 511u;
+        double2 *sbase = state + (size_t)shot * kDim;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) sbase[dg_label<1>(lane, i) ^ fm1] = p[i];
+        if (lane == 0) {
+            ShotAux ax;
+            ax.scale = 1.0;
+            ax.anc_outcome = 0;
+            ax.collapsed = 1;                     // the normalised block is stored at ancilla value 0
+            aux[shot] = ax;
+            meas_out[2 * shot + P.h[0].final_part] = r0;
+            meas_out[2 * shot + P.h[1].final_part] = r1;
+        }
+        __syncwarp();                             // scratch, tables and the metadata slot are reused
+        shot = shot1;
+        shot1 = shot2;
+    }
+    if (lane == 0) {
+        atomicAdd(&counters[4], (unsigned long long)(last - first));                                     // C_SWEEPS
+        atomicAdd(&counters[8], (unsigned long long)(last - first) * (init_basis < 0 ? 2ull : 1ull));   // 8 KiB runs moved
+    }
+}
+
+}  // namespace s17

@@ -67,12 +67,15 @@ def test_golden_replays(error_models, correction_table, bitflip_table, golden, f
         sim.close()
 
 
-@pytest.mark.parametrize("dense,fusion,early", [("0", 2, True), ("1", 2, True), ("0", 4, True), ("0", 1, True),
-                                                ("0", 2, False), ("0", 0, True)])
-def test_golden_replays_fast_path(error_models, correction_table, bitflip_table, golden, dense, fusion, early,
+@pytest.mark.parametrize("dense,fusion,early,diag", [("0", 2, True, "1"), ("0", 2, True, "0"), ("1", 2, True, "1"),
+                                                     ("0", 4, True, "1"), ("0", 1, True, "1"), ("0", 2, False, "1"),
+                                                     ("0", 0, True, "1")])
+def test_golden_replays_fast_path(error_models, correction_table, bitflip_table, golden, dense, fusion, early, diag,
                                   monkeypatch):
-    """Same replays through the production path (lazy collapse, correction folded into the read-out)."""
+    """Same replays through the production path (lazy collapse, correction folded into the read-out).
+    diag=1: whole-cycle diagonal-frame kernel k_cycle where the cycle allows it; diag=0: k_half everywhere."""
     monkeypatch.setenv("S17_DENSE", dense)
+    monkeypatch.setenv("S17_DIAG", diag)
     reps = golden("replays.json")["replays"]
     groups = {}
     for r in reps:
@@ -166,11 +169,12 @@ def test_amplitudes_noisy_cycle_before_measurement(error_models, correction_tabl
     ("Dress_cooling", "s2", True, [0, 0, 1, 2, 0, 3]),
     ("PDD_cooling", "single", True, [1, 1, 1, 1, 1, 2]),
 ])
-@pytest.mark.parametrize("fusion", [2, 4])
+@pytest.mark.parametrize("fusion,diag", [(2, "1"), (2, "0"), (4, "1")])
 def test_sampled_trajectories_replay_bit_exact_in_oracle(error_models, correction_table, bitflip_table, model,
-                                                         protocol, cooling, eset, fusion):
+                                                         protocol, cooling, eset, fusion, diag, monkeypatch):
     """Device-sampled shots (Philox placement + outcomes): replaying their masks and outcomes through the
     oracle reproduces syndromes, corrections, read-outs and pass/fail bit for bit."""
+    monkeypatch.setenv("S17_DIAG", diag)
     per_round = circuit.list_lengths(error_models[model])
     locs = [2 * x for x in per_round] if protocol == "s2" else per_round
     n = 32
@@ -190,6 +194,38 @@ def test_sampled_trajectories_replay_bit_exact_in_oracle(error_models, correctio
         fails += ref["fail"]
         not0 += ref["not0"]
     assert (c.failed, c.not0, c.errors) == (fails, not0, 0)
+    sim.close()
+
+
+@pytest.mark.parametrize("model,eset", [("PDD_model", [2, 2, 3, 6, 2]), ("Dress_model", [1, 1, 2, 8, 1]),
+                                        ("PDD_model", [0, 0, 0, 0, 0])])
+def test_cycle_kernel_matches_half_kernel(error_models, correction_table, bitflip_table, model, eset, monkeypatch):
+    """The diagonal-frame cycle kernel (k_cycle) against the general amplitude kernel (k_half): the trajectories one
+    samples, replayed through the other, give the same records and the same stored amplitudes (<= 1e-10, phase
+    included) for every shot."""
+    per_round = circuit.list_lengths(error_models[model])
+    locs = [2 * x for x in per_round]
+    n = 96
+    monkeypatch.setenv("S17_DIAG", "1")
+    sim = make_sim(error_models, correction_table, bitflip_table, model, locs, n, 2)
+    sim.backend.set_subset(eset, locs)
+    c1 = sim.backend.run("s2", n, L.NOISE_SUBSET, seed=321, first_shot_id=5)
+    recs1, masks = sim.backend.records(n), sim.backend.masks(n)
+    states1 = [sim.backend.state(i)[:512].copy() for i in range(n)]
+    sim.close()
+    monkeypatch.setenv("S17_DIAG", "0")
+    sim = make_sim(error_models, correction_table, bitflip_table, model, locs, n, 2)
+    sim.backend.set_replay([list(masks[i, 0]) for i in range(n)], [r["outcomes"] for r in recs1])
+    c2 = sim.backend.run("s2", n, L.NOISE_REPLAY, forced=True)
+    recs2 = sim.backend.records(n)
+    assert (c1.failed, c1.not0, c1.counted, c1.errors) == (c2.failed, c2.not0, c2.counted, 0)
+    assert c1.sweeps != c2.sweeps                       # really two different kernels (one vs two sweeps per cycle)
+    for i in range(n):
+        for f in FIELDS + ("outcomes",):
+            assert recs1[i].get(f) == recs2[i].get(f), (i, f, recs1[i].get(f), recs2[i].get(f))
+        st2 = sim.backend.state(i)[:512]
+        assert abs(np.linalg.norm(states1[i]) - 1.0) < 1e-12
+        assert np.max(np.abs(states1[i] - st2)) < AMP_TOL, (i, np.max(np.abs(states1[i] - st2)))
     sim.close()
 
 
