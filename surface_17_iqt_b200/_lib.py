@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libs17.so")
+LIB_PATH = os.environ.get("S17_LIB") or os.path.join(_HERE, "libs17.so")
 
 N_QUBITS = 17
 DIM = 1 << 17

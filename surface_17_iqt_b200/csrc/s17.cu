@@ -1246,7 +1246,7 @@ static bool make_half(const std::vector<LayerArg> &layers, size_t begin, size_t 
 // Lower a fused half cycle (make_half) to the diagonal-frame form of k_cycle.  Returns false when the half cycle is not
 // of that form: an idle mask, a non-standard operation, or single-qubit gates that do not bracket the data qubits.
 static bool make_diag_half(const LayerArg2 &P, const HalfTail &T, int half_index, const s17_pinstr *plan, uint32_t n_plan,
-                           DiagHalf &H) {
+                           DiagHalf &H, uint32_t *covered /* data bits some slot of this half indexes */) {
     memset(&H, 0, sizeof(H));
     memset(H.lane_bit, 255, sizeof(H.lane_bit));
     const s17_layer &L = P.A.L;
@@ -1291,8 +1291,7 @@ static bool make_diag_half(const LayerArg2 &P, const HalfTail &T, int half_index
         DiagOp &dop = H.ops[k][H.n_ops[k]++];
         dop.d = op.data_bit;
         dop.ev_word = op.ev_word;
-        dop.s_neg = P.oc[o].s < 0 ? 1 : 0;
-        dop.has_rx = (P.oc[o].shape & 2) ? 1 : 0;
+        dop.flags = (uint8_t)((P.oc[o].s < 0 ? 1 : 0) | ((P.oc[o].shape & 2) ? 2 : 0));
         H.aj[k] = (uint8_t)(op.anc_bit - 9);
         // k_plan must have been told the same frame, data bit and half boundaries for this operation
         bool found = false;
@@ -1312,11 +1311,21 @@ static bool make_diag_half(const LayerArg2 &P, const HalfTail &T, int half_index
             const int d = H.ops[k][j].d;
             const int reg_lo = all_x ? 0 : 5, reg_n = 4, lane_lo = all_x ? 4 : 0;
             if (d >= reg_lo && d < reg_lo + reg_n) {
-                for (int i = 0; i < 16; ++i) H.ridx[k][i] |= (uint8_t)(((i >> (d - reg_lo)) & 1) << j);
+                for (int i = 0; i < 16; ++i) H.roff[k][i] |= (uint32_t)(((i >> (d - reg_lo)) & 1) << j) << 4;
             } else {
                 H.lane_bit[k][j] = (uint8_t)(d - lane_lo);
             }
         }
+    // label-dependent signs ride in the table of the lowest slot that indexes the label bit; every slot measures
+    uint32_t owned = 0;
+    for (int k = 0; k < 4; ++k) {
+        if (H.n_ops[k] == 0) return false;
+        for (int j = 0; j < H.n_ops[k]; ++j) {
+            const uint32_t bit = 1u << H.ops[k][j].d;
+            if (!(owned & bit)) { H.ops[k][j].flags |= 4; owned |= bit; }
+        }
+    }
+    *covered = owned;
     return true;
 }
 
@@ -1377,10 +1386,13 @@ extern "C" int s17_load_program(s17_ctx *ctx, const s17_layer *layers, const uin
                               make_half(ctx->layers[c], cuts[0], cuts[1], ctx->half_prog[c][1], ctx->half_tail[c][1]);
             if (ctx->half_ok[c]) { ctx->half_tail[c][0].final_part = 0; ctx->half_tail[c][1].final_part = 1; }
             // whole-cycle diagonal-frame form: Hadamard-frame half followed by a computational-frame half
+            // (the data flips of the first half become signs the second half's tables must be able to carry)
+            uint32_t cov0 = 0, cov1 = 0;
             ctx->diag_ok[c] = ctx->half_ok[c] &&
-                              make_diag_half(ctx->half_prog[c][0], ctx->half_tail[c][0], 0, plan, n_plan, ctx->diag_prog[c].h[0]) &&
-                              make_diag_half(ctx->half_prog[c][1], ctx->half_tail[c][1], 1, plan, n_plan, ctx->diag_prog[c].h[1]) &&
-                              ctx->diag_prog[c].h[0].frame_x == 1 && ctx->diag_prog[c].h[1].frame_x == 0;
+                              make_diag_half(ctx->half_prog[c][0], ctx->half_tail[c][0], 0, plan, n_plan, ctx->diag_prog[c].h[0], &cov0) &&
+                              make_diag_half(ctx->half_prog[c][1], ctx->half_tail[c][1], 1, plan, n_plan, ctx->diag_prog[c].h[1], &cov1) &&
+                              ctx->diag_prog[c].h[0].frame_x == 1 && ctx->diag_prog[c].h[1].frame_x == 0 &&
+                              (cov0 & ~cov1) == 0;
             if (ctx->diag_ok[c]) { ctx->diag_prog[c].h[0].final_part = 0; ctx->diag_prog[c].h[1].final_part = 1; }
         }
     }

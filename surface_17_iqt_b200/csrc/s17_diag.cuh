@@ -25,7 +25,10 @@
 
 namespace s17 {
 
-constexpr int kDgWarps = 11;                                   // warps (= shots in flight) per SM
+#ifndef S17_DG_WARPS
+#define S17_DG_WARPS 11
+#endif
+constexpr int kDgWarps = S17_DG_WARPS;                         // warps (= shots in flight) per SM
 constexpr int kDgThreads = kDgWarps * 32;
 constexpr int kDgFrmBytes = 16;                                // per-shot frame words (4 x u32, two used)
 constexpr int kDgMetaBytes = kEvBytes + kAuxBytes + kDgFrmBytes;
@@ -34,7 +37,11 @@ constexpr int kDgWarpBytes = 2 * kRunBytes + kDgTabBytes + 3 * kDgMetaBytes + 64
 constexpr size_t kDgSmem = (size_t)kDgWarps * kDgWarpBytes;
 static_assert(kDgWarpBytes % 16 == 0, "per-warp shared memory must keep 16-byte alignment");
 
-struct DiagOp { uint8_t d, ev_word, s_neg, has_rx; };
+struct DiagOp {
+    uint8_t d, ev_word;
+    uint8_t flags;             // bit0: Rxx sign is -1, bit1: followed by Rx(-s pi/2), bit2: this slot owns label bit d for signs
+    uint8_t pad;
+};
 struct DiagHalf {
     uint8_t frame_x;           // 1: Walsh-Hadamard frame (x-type half), 0: computational frame (z-type half)
     uint8_t final_part;        // 1: completes the cycle's All(Measure) | ancilla
@@ -43,7 +50,7 @@ struct DiagHalf {
     uint8_t aj[4];             // ancilla index (outcome bit) of slot k
     DiagOp ops[4][4];          // per slot, in time order; table index bit j = label bit of ops[k][j].d
     uint8_t lane_bit[4][4];    // lane bit that feeds table index bit j (255: the bit comes from the register index)
-    uint8_t ridx[4][16];       // register-index part of the table index
+    uint32_t roff[4][16];      // register-index part of the table index, as a byte offset (index << 4)
 };
 struct DiagProg { DiagHalf h[2]; };
 
@@ -71,11 +78,11 @@ __device__ __forceinline__ void dg_wht16(double2 (&p)[16]) {
     }
 }
 __device__ __forceinline__ void dg_wht_lane4(double2 (&p)[16], int lane) {
-    const bool hi = (lane & 16) != 0;
+    const double sg = (lane & 16) ? -1.0 : 1.0;      // upper half of the butterfly: partner - mine
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         const double ox = __shfl_xor_sync(0xffffffffu, p[i].x, 16), oy = __shfl_xor_sync(0xffffffffu, p[i].y, 16);
-        p[i] = hi ? make_double2(ox - p[i].x, oy - p[i].y) : make_double2(p[i].x + ox, p[i].y + oy);
+        p[i] = make_double2(fma(sg, p[i].x, ox), fma(sg, p[i].y, oy));
     }
 }
 // label bits 5-8 and 4 (map 1), exchange, label bits 0-3 (map 2)
@@ -102,8 +109,10 @@ __device__ __forceinline__ void dg_wht_inverse(double2 (&p)[16], double2 *xb, in
 }
 
 // per-ancilla tables of one half cycle: two of the 64 (slot, index) entries per lane
+// zmask: label bits whose value flips the sign of the amplitude (data Z events; data flips of the preceding
+// Hadamard-frame half), applied by the slot that owns the bit; g: global phase i^g, applied by the last slot
 __device__ __forceinline__ void dg_build_tables(const DiagHalf &H, const uint32_t *evw, double2 *A0, double2 *A1,
-                                                double2 *Q, int lane) {
+                                                double2 *Q, int lane, uint32_t zmask, uint32_t g) {
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
         const int e = lane + 32 * r, k = e >> 4, idx = e & 15;
@@ -113,16 +122,23 @@ __device__ __forceinline__ void dg_build_tables(const DiagHalf &H, const uint32_
             const DiagOp op = H.ops[k][j];
             const uint32_t w = evw[op.ev_word];
             // sigma = s lambda, lambda evaluated on the label bit as relabeled by the data flips so far (bit 31)
-            const uint32_t neg = (uint32_t)op.s_neg ^ ((uint32_t)(idx >> j) & 1u) ^ (w >> 31);
+            const uint32_t bit = (uint32_t)(idx >> j) & 1u;
+            if ((op.flags & 4u) && ((zmask >> op.d) & 1u) && bit) ph = make_double2(-ph.x, -ph.y);
+            const uint32_t neg = (uint32_t)(op.flags & 1u) ^ bit ^ (w >> 31);
             const double sg = neg ? -1.0 : 1.0;
             if (!((w >> 24) & 1u)) {                          // Rxx unless leak-skipped: (u, v) -> (u - i sg v, v - i sg u)
                 const double2 nu = make_double2(fma(sg, v.y, u.x), fma(-sg, v.x, u.y));
                 const double2 nv = make_double2(fma(sg, u.y, v.x), fma(-sg, u.x, v.y));
                 u = nu; v = nv;
             }
-            if (op.has_rx) ph = make_double2(fma(-sg, ph.y, ph.x), fma(sg, ph.x, ph.y));      // (1 + i sg) ph
+            if (op.flags & 2u) ph = make_double2(fma(-sg, ph.y, ph.x), fma(sg, ph.x, ph.y));   // (1 + i sg) ph
             if ((w >> 28) & 1u) v = make_double2(-v.x, -v.y);                                  // net event: Z on the ancilla
             if ((w >> 27) & 1u) { const double2 t = u; u = v; v = t; }                         //            X on the ancilla
+        }
+        if (k == 3) {
+            if (g == 1) ph = make_double2(-ph.y, ph.x);
+            else if (g == 2) ph = make_double2(-ph.x, -ph.y);
+            else if (g == 3) ph = make_double2(ph.y, -ph.x);
         }
         const double2 a0 = dg_cmul(ph, u), a1 = dg_cmul(ph, v);
         A0[e] = a0;
@@ -131,72 +147,59 @@ __device__ __forceinline__ void dg_build_tables(const DiagHalf &H, const uint32_
     }
 }
 
+// one ancilla slot: P(0), P(1) from the table of squared moduli, one Measure, multiply by the selected amplitudes.
+// tk: this lane's base into the tables of slot K (A0 at +0, A1 at +1024, Q at +2048)
+template <int K>
+__device__ __forceinline__ void dg_slot(double2 (&p)[16], const DiagHalf &H, const unsigned char *tk, bool forced, uint32_t fo,
+                                        double uu, int u_base, uint32_t &a_out, bool &bad, double &pfin) {
+    double p0 = 0.0, p1 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const double2 q = *reinterpret_cast<const double2 *>(tk + 2048 + H.roff[K][i]);
+        const double w = fma(p[i].x, p[i].x, p[i].y * p[i].y);
+        p0 = fma(w, q.x, p0);
+        p1 = fma(w, q.y, p1);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        p0 += __shfl_xor_sync(0xffffffffu, p0, d);
+        p1 += __shfl_xor_sync(0xffffffffu, p1, d);
+    }
+    uint32_t out;
+    if (forced) {
+        out = (fo >> H.aj[K]) & 1u;
+        if ((out ? p1 : p0) <= 0.0) bad = true;
+    } else {
+        const double u = __shfl_sync(0xffffffffu, uu, u_base + K);
+        out = (u * (p0 + p1) < p1) ? 1u : 0u;                // Measure: P(1) against one uniform, as k_measure
+    }
+    const unsigned char *ta = tk + (out ? 1024 : 0);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) p[i] = dg_cmul(p[i], *reinterpret_cast<const double2 *>(ta + H.roff[K][i]));
+    a_out |= out << H.aj[K];
+    pfin = out ? p1 : p0;
+}
+
 // one half cycle on the register-resident state.  Returns the raw outcome bits (ancilla-indexed) | 0x100 if a forced
-// outcome had probability zero.  FRAME_X: p is in map 1 on entry and exit, map 2 in between.
+// outcome had probability zero; pfin = squared norm of the state it leaves (the state is NOT renormalised here: the
+// caller scales once, when it stores).  FRAME_X: p is in map 1 on entry and exit, map 2 in between.
+// tl[k]: this lane's byte offset into the tables of slot k (shot independent).
 template <bool FRAME_X>
-__device__ __forceinline__ uint32_t dg_half(double2 (&p)[16], const DiagHalf &H, const int (&lidx)[4], const uint32_t *evw,
-                                            uint32_t fw, double2 *A0, double2 *A1, double2 *Q, double2 *xb, int lane,
-                                            bool forced, uint32_t fo, double uu, int u_base) {
-    constexpr int MAP = FRAME_X ? 2 : 1;
+__device__ __forceinline__ uint32_t dg_half(double2 (&p)[16], const DiagHalf &H, const uint32_t (&tl)[4], const uint32_t *evw,
+                                            uint32_t zmask, uint32_t g, unsigned char *tab, double2 *xb, int lane,
+                                            bool forced, uint32_t fo, double uu, int u_base, double &pfin) {
     if (FRAME_X) dg_wht_forward(p, xb, lane);
     __syncwarp();
-    dg_build_tables(H, evw, A0, A1, Q, lane);
+    dg_build_tables(H, evw, reinterpret_cast<double2 *>(tab), reinterpret_cast<double2 *>(tab) + 64,
+                    reinterpret_cast<double2 *>(tab) + 128, lane, zmask, g);
     __syncwarp();
     uint32_t a_out = 0;
     bool bad = false;
-    double pfin = 1.0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (H.n_ops[k] == 0) continue;
-        const int li = lidx[k] + 16 * k;
-        double p0 = 0.0, p1 = 0.0;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const double2 q = Q[li | H.ridx[k][i]];
-            const double w = fma(p[i].x, p[i].x, p[i].y * p[i].y);
-            p0 = fma(w, q.x, p0);
-            p1 = fma(w, q.y, p1);
-        }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            p0 += __shfl_xor_sync(0xffffffffu, p0, d);
-            p1 += __shfl_xor_sync(0xffffffffu, p1, d);
-        }
-        uint32_t out;
-        if (forced) {
-            out = (fo >> H.aj[k]) & 1u;
-            if ((out ? p1 : p0) <= 0.0) bad = true;
-        } else {
-            const double u = __shfl_sync(0xffffffffu, uu, u_base + k);
-            out = (u * (p0 + p1) < p1) ? 1u : 0u;            // Measure: P(1) against one uniform, as k_measure
-        }
-        const double2 *A = out ? A1 : A0;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) p[i] = dg_cmul(p[i], A[li | H.ridx[k][i]]);
-        a_out |= out << H.aj[k];
-        pfin = out ? p1 : p0;
-    }
-    // renormalise (the squared norm of the selected branch is the last conditional weight), event signs and phase
-    const uint32_t zacc = (fw >> 9) & 511u, g = (fw >> 18) & 3u, fm = fw & 511u;
-    const double nrm = FRAME_X ? pfin * 512.0 : pfin;          // the inverse transform multiplies the norm^2 by 512
-    const double inv = nrm > 0.0 ? 1.0 / sqrt(nrm) : 0.0;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const double sc = (__popc(dg_label<MAP>(lane, i) & zacc) & 1) ? -inv : inv;
-        double2 v = make_double2(p[i].x * sc, p[i].y * sc);
-        if (g == 1) v = make_double2(-v.y, v.x);
-        else if (g == 2) v = make_double2(-v.x, -v.y);
-        else if (g == 3) v = make_double2(v.y, -v.x);
-        p[i] = v;
-    }
-    if (FRAME_X) {
-        dg_wht_inverse(p, xb, lane);
-        if (fm) {                                             // data flips in the Hadamard frame are signs afterwards
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-                if (__popc(dg_label<1>(lane, i) & fm) & 1) p[i] = make_double2(-p[i].x, -p[i].y);
-        }
-    }
+    dg_slot<0>(p, H, tab + tl[0], forced, fo, uu, u_base, a_out, bad, pfin);
+    dg_slot<1>(p, H, tab + tl[1], forced, fo, uu, u_base, a_out, bad, pfin);
+    dg_slot<2>(p, H, tab + tl[2], forced, fo, uu, u_base, a_out, bad, pfin);
+    dg_slot<3>(p, H, tab + tl[3], forced, fo, uu, u_base, a_out, bad, pfin);
+    if (FRAME_X) { dg_wht_inverse(p, xb, lane); pfin *= 512.0; }      // the inverse transform multiplies the norm^2 by 512
     return a_out | (bad ? 0x100u : 0u);
 }
 
@@ -210,7 +213,7 @@ k_cycle(const __grid_constant__ DiagProg P, const __grid_constant__ MeasArgs ma,
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char *wb = smem_raw + (size_t)warp * kDgWarpBytes;
     double2 *buf = reinterpret_cast<double2 *>(wb);                                  // [2][512]
-    double2 *A0 = reinterpret_cast<double2 *>(wb + 2 * kRunBytes), *A1 = A0 + 64, *Q = A1 + 64;
+    unsigned char *tab = wb + 2 * kRunBytes;                                         // A0[64] | A1[64] | Q[64]
     unsigned char *meta = wb + 2 * kRunBytes + kDgTabBytes;                          // [3][kDgMetaBytes]
     uint64_t *full = reinterpret_cast<uint64_t *>(meta + 3 * kDgMetaBytes);          // [2]
     uint64_t *mfull = full + 2;                                                      // [3]
@@ -228,19 +231,19 @@ k_cycle(const __grid_constant__ DiagProg P, const __grid_constant__ MeasArgs ma,
     }
     __syncwarp();
 
-    // lane part of the table indices (shot independent)
-    int lidx[2][4];
+    // lane part of the table indices (shot independent), as byte offsets into the tables
+    uint32_t tl[2][4];
 #pragma unroll
     for (int h = 0; h < 2; ++h)
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            int li = 0;
+            uint32_t li = 0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int lb = P.h[h].lane_bit[k][j];
-                if (lb != 255) li |= ((lane >> lb) & 1) << j;
+                if (lb != 255) li |= (uint32_t)((lane >> lb) & 1) << j;
             }
-            lidx[h][k] = li;
+            tl[h][k] = (li + 16u * (uint32_t)k) << 4;
         }
 
     auto issue_meta = [&](uint32_t shot_, int slot) {
@@ -308,14 +311,22 @@ k_cycle(const __grid_constant__ DiagProg P, const __grid_constant__ MeasArgs ma,
         }
         __syncwarp();                             // every lane holds its amplitudes: the buffer becomes exchange scratch
 
-        const uint32_t r0 = dg_half<true>(p, P.h[0], lidx[0], evw, fwp[0], A0, A1, Q, xb, lane, ma.forced != 0, fo, uu, 0);
-        const uint32_t r1 = dg_half<false>(p, P.h[1], lidx[1], evw, fwp[1], A0, A1, Q, xb, lane, ma.forced != 0, fo, uu, 4);
+        // frame words: bits 0-8 flip mask, 9-17 sign mask, 18-19 phase.  Signs and phases ride in the tables; the data
+        // flips of the Hadamard-frame half are signs after its inverse transform, i.e. part of the next half's sign mask
+        const uint32_t f0 = fwp[0], f1 = fwp[1];
+        double pfin = 1.0;
+        const uint32_t r0 = dg_half<true>(p, P.h[0], tl[0], evw, (f0 >> 9) & 511u, (f0 >> 18) & 3u, tab, xb, lane,
+                                          ma.forced != 0, fo, uu, 0, pfin);
+        const uint32_t r1 = dg_half<false>(p, P.h[1], tl[1], evw, ((f1 >> 9) ^ f0) & 511u, (f1 >> 18) & 3u, tab, xb, lane,
+                                           ma.forced != 0, fo, uu, 4, pfin);
 
-        // data flips of the computational-frame half are a relabeling: applied by the store
-        const uint32_t fm1 = fwp[1] & 511u;
+        // renormalise once (the squared norm of the selected branch is the last conditional weight); the data flips of
+        // the computational-frame half are a relabeling, applied by the store
+        const double inv = pfin > 0.0 ? 1.0 / sqrt(pfin) : 0.0;
+        const uint32_t fm1 = f1 & 511u;
         double2 *sbase = state + (size_t)shot * kDim;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) sbase[dg_label<1>(lane, i) ^ fm1] = p[i];
+        for (int i = 0; i < 16; ++i) sbase[dg_label<1>(lane, i) ^ fm1] = make_double2(p[i].x * inv, p[i].y * inv);
         if (lane == 0) {
             ShotAux ax;
             ax.scale = 1.0;
