@@ -310,9 +310,10 @@ __device__ __forceinline__ uint32_t pconj_rxx(uint32_t P, int s) {        // Rxx
 
 __global__ void k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, NoiseDev nd, const double *__restrict__ probs,
                        uint32_t *__restrict__ ev, uint32_t *__restrict__ masks, uint32_t *__restrict__ leak,
-                       const uint8_t *__restrict__ active, uint32_t *__restrict__ frm)
+                       const uint8_t *__restrict__ active, uint32_t *__restrict__ frm, uint32_t *__restrict__ n_act)
 {
     const int shot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (shot == 0) *n_act = 0;                         // k_compact, next in the stream, appends to an empty list
     if (shot >= pa.n_shots || !active[shot]) return;
     Philox rng(pa.seed, pa.first_shot + shot, pa.stream);
     uint32_t f_flip = 0, f_sign = 0, f_phase = 0;      // frame bookkeeping of the current half cycle (k_cycle)
@@ -615,32 +616,20 @@ k_pauli(double2 *__restrict__ state, const s17_record *__restrict__ rec, const u
     }
 }
 
-// ordered list of the shots that still take part in gate sweeps (consumed by k_layer2)
-__global__ void __launch_bounds__(1024)
+// list of the shots that still take part in gate sweeps (consumed by the persistent sweep kernels).  Warp-aggregated
+// atomic append: the order of the list is arbitrary (it only decides which CTA / warp processes which shot), *n_act
+// must be zero on entry (k_plan clears it).
+__global__ void __launch_bounds__(256)
 k_compact(const uint8_t *__restrict__ active, int n, uint32_t *__restrict__ list, uint32_t *__restrict__ n_act)
 {
-    __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t base_s;
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    if (t == 0) base_s = 0;
-    __syncthreads();
-    for (int start = 0; start < n; start += 1024) {
-        const int i = start + t;
-        const bool flag = i < n && active[i];
-        const uint32_t ballot = __ballot_sync(0xffffffffu, flag);
-        if (lane == 0) warp_sums[warp] = __popc(ballot);
-        __syncthreads();
-        uint32_t woff = 0, total = 0;
-        for (int w = 0; w < 32; ++w) {
-            if (w < warp) woff += warp_sums[w];
-            total += warp_sums[w];
-        }
-        if (flag) list[base_s + woff + __popc(ballot & ((1u << lane) - 1u))] = (uint32_t)i;
-        __syncthreads();
-        if (t == 0) base_s += total;
-        __syncthreads();
-    }
-    if (t == 0) *n_act = base_s;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    const bool flag = i < n && active[i];
+    const uint32_t ballot = __ballot_sync(0xffffffffu, flag);
+    if (!ballot) return;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(n_act, (uint32_t)__popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (flag) list[base + __popc(ballot & ((1u << lane) - 1u))] = (uint32_t)i;
 }
 
 struct ReadArgs {
@@ -654,7 +643,7 @@ struct ReadArgs {
 
 // logical_measurement (CS:52-93): one warp per shot
 __global__ void __launch_bounds__(128)
-k_readout(ReadArgs ra, const double2 *__restrict__ state, const ShotAux *__restrict__ aux,
+k_readout(ReadArgs ra, const double2 *__restrict__ state, size_t stride, const ShotAux *__restrict__ aux,
           const uint8_t *__restrict__ forced, const uint8_t *__restrict__ cw16, const uint32_t *__restrict__ leak,
           const uint8_t *__restrict__ ready, s17_record *__restrict__ rec, unsigned long long *__restrict__ counters)
 {
@@ -665,7 +654,7 @@ k_readout(ReadArgs ra, const double2 *__restrict__ state, const ShotAux *__restr
     const double sc2 = ax.collapsed ? 1.0 : ax.scale * ax.scale;
     const uint32_t corr = rec[shot].correction;
     const uint32_t xc = ra.folded ? (corr & 0x1FFu) : 0u;
-    const double2 *blk = state + (size_t)shot * kDim + (size_t)sel * kRun;
+    const double2 *blk = state + (size_t)shot * stride + (size_t)sel * kRun;
     double p[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -673,36 +662,56 @@ k_readout(ReadArgs ra, const double2 *__restrict__ state, const ShotAux *__restr
         const double2 v = blk[d ^ xc];       // probability of reading d from the corrected state
         p[i] = (v.x * v.x + v.y * v.y) * sc2;
     }
-    Philox rng(ra.seed, ra.first_shot + shot, ra.stream);
-    uint32_t chosen = 0, nout = rec[shot].n_outcomes;
+    // All(Measure) | data (CS:56): the nine Measure gates sample one basis state from |psi|^2 (ProjectQ itself picks a
+    // basis state by a cumulative walk per Measure).  One uniform against the cumulative distribution in
+    // the order (lane, register): a lane-local sum, an inclusive scan over the lanes, a walk inside the selected lane.
+    uint32_t chosen = 0;
+    const uint32_t nout = rec[shot].n_outcomes;
     bool bad = false;
-    uint8_t outs[9];
-    for (int j = 0; j < 9; ++j) {
-        double p0 = 0.0, p1 = 0.0;
-        const uint32_t lowmask = (1u << j) - 1u;
+    if (ra.forced) {
+        const uint32_t b = lane < 9 ? (uint32_t)(forced[(size_t)shot * S17_MAX_OUTCOMES + nout + lane] & 1u) : 0u;
+        chosen = __ballot_sync(0xffffffffu, b != 0u) & 0x1FFu;
+        // every conditional probability along the nine Measure gates is positive iff the joint one is
+        double pc = 0.0;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const uint32_t d = lane + 32 * i;
-            if ((d & lowmask) != chosen) continue;
-            if ((d >> j) & 1u) p1 += p[i]; else p0 += p[i];
-        }
+        for (int i = 0; i < 16; ++i)
+            if ((uint32_t)(lane + 32 * i) == chosen) pc = p[i];
+        pc = __shfl_sync(0xffffffffu, pc, chosen & 31u);
+        bad = pc <= 0.0;
+    } else {
+        double mine = 0.0;
 #pragma unroll
-        for (int s = 16; s > 0; s >>= 1) {
-            p0 += __shfl_xor_sync(0xffffffffu, p0, s);
-            p1 += __shfl_xor_sync(0xffffffffu, p1, s);
+        for (int i = 0; i < 16; ++i) mine += p[i];
+        double incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
         }
-        uint32_t out;
-        if (ra.forced) {
-            out = forced[(size_t)shot * S17_MAX_OUTCOMES + nout + j] & 1u;
-            if ((out ? p1 : p0) <= 0.0) bad = true;
-        } else {
-            double u = rng.next();
-            u = __shfl_sync(0xffffffffu, u, 0);
-            out = (u * (p0 + p1) < p1) ? 1u : 0u;
+        const double total = __shfl_sync(0xffffffffu, incl, 31);
+        double u = 0.0;
+        if (lane == 0) { Philox rng(ra.seed, ra.first_shot + shot, ra.stream); u = rng.next(); }
+        const double target = __shfl_sync(0xffffffffu, u, 0) * total;
+        const uint32_t hit = __ballot_sync(0xffffffffu, target < incl);          // non-empty: target < total = incl[31]
+        const int sel = hit ? (__ffs(hit) - 1) : 31;
+        uint32_t mine_d = 0;
+        {
+            double cum = incl - mine;
+            int pick = -1, last_pos = 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                cum += p[i];
+                if (p[i] > 0.0) last_pos = i;
+                if (pick < 0 && target < cum && p[i] > 0.0) pick = i;
+            }
+            if (pick < 0) pick = last_pos;            // rounding guard: never select an empty state
+            mine_d = (uint32_t)(lane + 32 * pick);
         }
-        outs[j] = (uint8_t)out;
-        chosen |= out << j;
+        chosen = __shfl_sync(0xffffffffu, mine_d, sel);
     }
+    uint8_t outs[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) outs[j] = (uint8_t)((chosen >> j) & 1u);
     if (lane != 0) return;
     s17_record r = rec[shot];
     for (int j = 0; j < 9; ++j)
@@ -801,7 +810,10 @@ struct s17_ctx {
     int device = 0;
     uint64_t max_shots = 0;
     cudaStream_t stream = nullptr;
-    double2 *state = nullptr;
+    double2 *state = nullptr;         // allocated on first use: full (2 MiB per shot) or compact (8 KiB per shot)
+    bool state_full = false;
+    size_t stride = kDim;             // amplitudes per shot in `state`
+    void *encode_fn = nullptr;        // cuTensorMapEncodeTiled
     uint32_t *ev = nullptr, *masks = nullptr, *leak = nullptr, *lut = nullptr;
     uint8_t *active = nullptr, *ready = nullptr, *forced = nullptr, *cw16 = nullptr;
     double *hist = nullptr, *probs = nullptr, *cum = nullptr;
@@ -910,14 +922,12 @@ extern "C" int s17_create(s17_ctx **out, int device, uint64_t max_shots) {
     CK(cudaSetDevice(device));
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     const size_t B = max_shots;
-    CK(cudaMalloc(&ctx->state, B * kDim * sizeof(double2)));
     CK(cudaMalloc(&ctx->ev, B * S17_EV_WORDS * 4));
     CK(cudaMalloc(&ctx->masks, B * 2 * S17_MASK_WORDS * 4));
     CK(cudaMalloc(&ctx->leak, B * 4));
     CK(cudaMalloc(&ctx->active, B));
     CK(cudaMalloc(&ctx->ready, B));
     CK(cudaMalloc(&ctx->forced, B * S17_MAX_OUTCOMES));
-    CK(cudaMalloc(&ctx->hist, B * 256 * sizeof(double)));
     CK(cudaMalloc(&ctx->aux, B * sizeof(ShotAux)));
     CK(cudaMalloc(&ctx->rec, B * sizeof(s17_record)));
     CK(cudaMalloc(&ctx->counters, C_N * sizeof(unsigned long long)));
@@ -934,11 +944,9 @@ extern "C" int s17_create(s17_ctx **out, int device, uint64_t max_shots) {
         const char *mm = getenv("S17_MEMSET");
         const char *mb = getenv("S17_MEMSET_BYTE");
         const int mask = mm ? atoi(mm) : 0, byte = mb ? atoi(mb) : 0;
-        if (mask & 1) CK(cudaMemset(ctx->state, byte, B * kDim * sizeof(double2)));
         if (mask & 2) CK(cudaMemset(ctx->masks, byte, B * 2 * S17_MASK_WORDS * 4));
         if (mask & 4) { CK(cudaMemset(ctx->active, byte, B)); CK(cudaMemset(ctx->ready, byte, B)); }
         if (mask & 8) CK(cudaMemset(ctx->forced, byte, B * S17_MAX_OUTCOMES));
-        if (mask & 16) CK(cudaMemset(ctx->hist, byte, B * 256 * sizeof(double)));
         if (mask & 32) CK(cudaMemset(ctx->aux, byte, B * sizeof(ShotAux)));
         if (mask & 64) CK(cudaMemset(ctx->rec, byte, B * sizeof(s17_record)));
     }
@@ -961,14 +969,7 @@ extern "C" int s17_create(s17_ctx **out, int device, uint64_t max_shots) {
         cudaDriverEntryPointQueryResult qres;
         CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
         if (!fn || qres != cudaDriverEntryPointSuccess) return fail(ctx, S17_E_CUDA, "cuTensorMapEncodeTiled is not available");
-        const cuuint64_t dims[2] = {16, (cuuint64_t)B * (kDim / 8)};       // 16 doubles = 8 amplitudes = 128 B per row
-        const cuuint64_t strides[1] = {128};
-        const cuuint32_t box[2] = {16, kRun / 8};                          // one run: 64 rows = 8 KiB
-        const cuuint32_t estr[2] = {1, 1};
-        const CUresult r = ((EncodeFn)fn)(&ctx->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, ctx->state, dims, strides, box, estr,
-                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return fail(ctx, S17_E_CUDA, "cuTensorMapEncodeTiled failed");
+        ctx->encode_fn = fn;
     }
     CK(cudaMalloc(&ctx->zero_page, kRunBytes));
     CK(cudaMemset(ctx->zero_page, 0, kRunBytes));
@@ -1492,6 +1493,48 @@ extern "C" int s17_set_replay(s17_ctx *ctx, uint64_t n, const uint8_t *masks, ui
 
 static inline int blocks_for(uint64_t n, int per) { return (int)((n + per - 1) / per); }
 
+// The state buffer is allocated on first use.  The whole-cycle kernel (k_cycle) only ever touches the surviving
+// 512-amplitude block of a shot, so a context that runs nothing else keeps 8 KiB per shot ("compact"); any other path
+// (full-state sweeps, explicit collapse, parity read-backs of intermediate states) needs all 2^17 amplitudes.
+static int ensure_state(s17_ctx *ctx, bool need_full) {
+    if (ctx->state && (ctx->state_full || !need_full)) return S17_OK;
+    const size_t B = ctx->max_shots;
+    if (ctx->state) { CK(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->state); ctx->state = nullptr; }
+    ctx->state_full = need_full;
+    ctx->stride = need_full ? (size_t)kDim : (size_t)kRun;
+    if (cudaMalloc(&ctx->state, B * ctx->stride * sizeof(double2)) != cudaSuccess) {
+        cudaGetLastError();
+        ctx->state = nullptr;
+        return fail(ctx, S17_E_NOMEM, "out of device memory for the state vectors (" + std::to_string(B) + " shots x " +
+                                          std::to_string(ctx->stride * 16) + " bytes)");
+    }
+    {
+        const char *mm = getenv("S17_MEMSET");
+        const char *mb = getenv("S17_MEMSET_BYTE");
+        if (mm && (atoi(mm) & 1)) CK(cudaMemset(ctx->state, mb ? atoi(mb) : 0, B * ctx->stride * sizeof(double2)));
+    }
+    if (need_full) {
+        if (!ctx->hist) {
+            if (cudaMalloc(&ctx->hist, B * 256 * sizeof(double)) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(ctx, S17_E_NOMEM, "out of device memory for the ancilla histograms");
+            }
+        }
+        typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        const cuuint64_t dims[2] = {16, (cuuint64_t)B * (kDim / 8)};       // 16 doubles = 8 amplitudes = 128 B per row
+        const cuuint64_t strides[1] = {128};
+        const cuuint32_t box[2] = {16, kRun / 8};                          // one run: 64 rows = 8 KiB
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult r = ((EncodeFn)ctx->encode_fn)(&ctx->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, ctx->state, dims, strides,
+                                                      box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(ctx, S17_E_CUDA, "cuTensorMapEncodeTiled failed");
+    }
+    return S17_OK;
+}
+
 // one stabiliser cycle: plan -> gate sweeps -> ancilla measurement decisions
 static void collapse(s17_ctx *ctx, int n, const uint8_t *flag);
 
@@ -1511,7 +1554,7 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
     {
         SCOPE(CAT_OTHER);
         k_plan<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(ctx->plan, pa, ctx->nd, ctx->probs, ctx->ev, ctx->masks,
-                                                            ctx->leak, ctx->active, ctx->frm);
+                                                            ctx->leak, ctx->active, ctx->frm, ctx->n_act);
     }
     const int which = stage == 0 ? 0 : (second ? 2 : 1);
     const std::vector<LayerArg> &Ls = ctx->layers[which];
@@ -1520,7 +1563,7 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
     if (max_layers && max_layers < nl) nl = max_layers;
     {
         SCOPE(CAT_OTHER);
-        k_compact<<<1, 1024, 0, ctx->stream>>>(ctx->active, n, ctx->act_list, ctx->n_act);
+        k_compact<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(ctx->active, n, ctx->act_list, ctx->n_act);
     }
     MeasArgs ma;
     ma.stage = stage;
@@ -1539,7 +1582,7 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
         {
             SCOPE(CAT_GATE);
             k_cycle<<<ctx->num_sms, kDgThreads, kDgSmem, ctx->stream>>>(
-                ctx->diag_prog[which], ma, ctx->state, ctx->ev, ctx->frm, ctx->act_list, ctx->n_act, ctx->aux, ctx->forced,
+                ctx->diag_prog[which], ma, ctx->state, ctx->stride, ctx->ev, ctx->frm, ctx->act_list, ctx->n_act, ctx->aux, ctx->forced,
                 ctx->meas_out, ctx->counters, init_basis);
             ctx->n_gate++;
         }
@@ -1653,7 +1696,7 @@ static int run_round(s17_ctx *ctx, const s17_run_args &a) {
     ra.n_shots = n;
     {
         SCOPE(CAT_MEAS);
-        k_readout<<<blocks_for((uint64_t)n * 32, 128), 128, 0, ctx->stream>>>(ra, ctx->state, ctx->aux, ctx->forced, ctx->cw16,
+        k_readout<<<blocks_for((uint64_t)n * 32, 128), 128, 0, ctx->stream>>>(ra, ctx->state, ctx->stride, ctx->aux, ctx->forced, ctx->cw16,
                                                                           ctx->leak, ctx->ready, ctx->rec, ctx->counters);
     }
     return S17_OK;
@@ -1689,6 +1732,12 @@ extern "C" int s17_run(s17_ctx *ctx, const s17_run_args *args, s17_counts *out) 
     ctx->launches.clear();
     ctx->ev_used = 0;
     const int n = (int)a.n_shots;
+    {
+        const bool all_diag = ctx->diag_ok[0] && ctx->diag_ok[1] && ctx->diag_ok[2] && !ctx->no_diag && !ctx->dense &&
+                              !ctx->use_v1 && !ctx->force_ring && !ctx->no_fuse && !a.materialize &&
+                              a.stop_stage == S17_STOP_NONE;
+        if (int rc = ensure_state(ctx, !all_diag)) return rc;
+    }
     CK(cudaEventRecord(ctx->span0, ctx->stream));
     CK(cudaMemsetAsync(ctx->counters, 0, C_N * sizeof(unsigned long long), ctx->stream));
     {
@@ -1780,7 +1829,14 @@ extern "C" int s17_read_masks(s17_ctx *ctx, uint32_t *out, uint64_t n) {
 extern "C" int s17_read_state(s17_ctx *ctx, uint64_t shot, double *re_im) {
     if (!ctx || !re_im || shot >= ctx->max_shots) return fail(ctx, S17_E_ARG, "s17_read_state: bad arguments");
     CK(cudaSetDevice(ctx->device));
-    CK(cudaMemcpy(re_im, ctx->state + shot * kDim, kDim * sizeof(double2), cudaMemcpyDeviceToHost));
+    if (!ctx->state) return fail(ctx, S17_E_STATE, "s17_read_state: nothing has run yet");
+    if (ctx->state_full) {
+        CK(cudaMemcpy(re_im, ctx->state + shot * kDim, kDim * sizeof(double2), cudaMemcpyDeviceToHost));
+    } else {
+        // compact context: every ancilla is measured and reset, the state is its 512-amplitude data block
+        memset(re_im, 0, kDim * sizeof(double2));
+        CK(cudaMemcpy(re_im, ctx->state + shot * kRun, kRun * sizeof(double2), cudaMemcpyDeviceToHost));
+    }
     return S17_OK;
 }
 

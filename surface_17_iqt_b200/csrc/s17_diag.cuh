@@ -205,7 +205,7 @@ __device__ __forceinline__ uint32_t dg_half(double2 (&p)[16], const DiagHalf &H,
 
 __global__ void __launch_bounds__(kDgThreads, 1)
 k_cycle(const __grid_constant__ DiagProg P, const __grid_constant__ MeasArgs ma, double2 *__restrict__ state,
-        const uint32_t *__restrict__ ev, const uint32_t *__restrict__ frm, const uint32_t *__restrict__ act_list,
+        size_t stride, const uint32_t *__restrict__ ev, const uint32_t *__restrict__ frm, const uint32_t *__restrict__ act_list,
         const uint32_t *__restrict__ n_act_ptr, ShotAux *__restrict__ aux, const uint8_t *__restrict__ forced,
         uint32_t *__restrict__ meas_out, unsigned long long *__restrict__ counters, int init_basis)
 {
@@ -258,7 +258,7 @@ k_cycle(const __grid_constant__ DiagProg P, const __grid_constant__ MeasArgs ma,
         const uint32_t blk = ax->collapsed ? 0u : ax->anc_outcome;       // lazy collapse + reset: the surviving block
         fence_proxy_async_smem();                 // the buffer was last touched through the generic proxy
         mbar_expect_tx(&full[sb], kRunBytes);
-        tma_load_1d(buf + sb * kRun, state + (size_t)shot_ * kDim + (size_t)blk * kRun, kRunBytes, &full[sb]);
+        tma_load_1d(buf + sb * kRun, state + (size_t)shot_ * stride + (size_t)blk * kRun, kRunBytes, &full[sb]);
     };
 
     uint32_t shot = act_list[first];
@@ -324,7 +324,7 @@ k_cycle(const __grid_constant__ DiagProg P, const __grid_constant__ MeasArgs ma,
         // the computational-frame half are a relabeling, applied by the store
         const double inv = pfin > 0.0 ? 1.0 / sqrt(pfin) : 0.0;
         const uint32_t fm1 = f1 & 511u;
-        double2 *sbase = state + (size_t)shot * kDim;
+        double2 *sbase = state + (size_t)shot * stride;
 #pragma unroll
         for (int i = 0; i < 16; ++i) sbase[dg_label<1>(lane, i) ^ fm1] = make_double2(p[i].x * inv, p[i].y * inv);
         if (lane == 0) {
