@@ -838,6 +838,7 @@ struct s17_ctx {
     DiagProg diag_prog[3];
     bool diag_ok[3] = {false, false, false};
     bool no_diag = false;
+    bool last_collapsed = true;       // the previous cycle left every active shot collapsed to ancilla block 0
     uint32_t *frm = nullptr;          // per shot: frame words of the two half cycles (k_plan -> k_cycle)
     bool no_fuse = false;
     bool debug_sync = false;
@@ -1319,13 +1320,18 @@ static bool make_diag_half(const LayerArg2 &P, const HalfTail &T, int half_index
         }
     // label-dependent signs ride in the table of the lowest slot that indexes the label bit; every slot measures
     uint32_t owned = 0;
+    int entries = 0;
     for (int k = 0; k < 4; ++k) {
         if (H.n_ops[k] == 0) return false;
+        H.tbase[k] = (uint8_t)entries;
+        entries += 1 << H.n_ops[k];
         for (int j = 0; j < H.n_ops[k]; ++j) {
             const uint32_t bit = 1u << H.ops[k][j].d;
             if (!(owned & bit)) { H.ops[k][j].flags |= 4; owned |= bit; }
         }
     }
+    if (entries > kDgTabEntries) return false;
+    H.n_entries = (uint8_t)entries;
     *covered = owned;
     return true;
 }
@@ -1574,6 +1580,8 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
     ma.n_shots = n;
     const bool fused_ok = !dense && !mid_collapse && !max_layers && !ctx->use_v1 && !ctx->force_ring && !ctx->no_fuse;
     if (ctx->diag_ok[which] && fused_ok && !ctx->no_diag) {
+        if (init_basis < 0 && !ctx->last_collapsed) collapse(ctx, n, ctx->active);     // k_cycle reads the block at ancilla value 0
+        ctx->last_collapsed = true;
         // production path for Clifford cycles with Pauli / leakage noise: the whole cycle in the frame where it is
         // diagonal, one warp per shot, the state in registers (s17_diag.cuh)
         ma.mask = 0xFFu;
@@ -1594,6 +1602,7 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
         return S17_OK;
     }
     if (ctx->half_ok[which] && fused_ok) {
+        ctx->last_collapsed = true;
         // production path: one fused kernel per half cycle (gates + measurement + collapse), state stays on chip
         for (int h = 0; h < 2; ++h) {
             ma.mask = ctx->half_tail[which][h].meas_mask;
@@ -1614,6 +1623,7 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
         }
         return S17_OK;
     }
+    ctx->last_collapsed = false;
     for (uint32_t i = 0; i < nl; ++i) {
         {
             SCOPE(CAT_GATE);
@@ -1653,6 +1663,7 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
 static void collapse(s17_ctx *ctx, int n, const uint8_t *flag) {
     SCOPE(CAT_MEAS);
     k_collapse<<<n * 32, 256, 0, ctx->stream>>>(ctx->state, ctx->aux, flag);
+    ctx->last_collapsed = true;
 }
 
 // one full round for every active slot: prep, cycle A, optional cycle B, decode, read-out

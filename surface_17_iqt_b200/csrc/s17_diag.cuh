@@ -26,16 +26,18 @@
 namespace s17 {
 
 #ifndef S17_DG_WARPS
-#define S17_DG_WARPS 11
+#define S17_DG_WARPS 12
 #endif
 constexpr int kDgWarps = S17_DG_WARPS;                         // warps (= shots in flight) per SM
 constexpr int kDgThreads = kDgWarps * 32;
 constexpr int kDgFrmBytes = 16;                                // per-shot frame words (4 x u32, two used)
-constexpr int kDgMetaBytes = kEvBytes + kAuxBytes + kDgFrmBytes;
-constexpr int kDgTabBytes = 3 * 64 * 16;                       // A0 / A1 / Q tables: 4 ancilla slots x 16 entries
-constexpr int kDgWarpBytes = 2 * kRunBytes + kDgTabBytes + 3 * kDgMetaBytes + 64;
+constexpr int kDgMetaBytes = kEvBytes + kDgFrmBytes;
+constexpr int kDgTabEntries = 48;                              // table entries of one half cycle (sum over slots of 2^n_ops)
+constexpr int kDgTabBytes = 3 * kDgTabEntries * 16;            // A0 | A1 | Q
+constexpr int kDgWarpBytes = 2 * kRunBytes + kDgTabBytes + 2 * kDgMetaBytes + 64;
 constexpr size_t kDgSmem = (size_t)kDgWarps * kDgWarpBytes;
 static_assert(kDgWarpBytes % 16 == 0, "per-warp shared memory must keep 16-byte alignment");
+static_assert(kDgSmem <= 232448, "k_cycle: shared memory per SM");
 
 struct DiagOp {
     uint8_t d, ev_word;
@@ -45,9 +47,11 @@ struct DiagOp {
 struct DiagHalf {
     uint8_t frame_x;           // 1: Walsh-Hadamard frame (x-type half), 0: computational frame (z-type half)
     uint8_t final_part;        // 1: completes the cycle's All(Measure) | ancilla
-    uint8_t pad[2];
+    uint8_t n_entries;         // table entries in use
+    uint8_t pad;
     uint8_t n_ops[4];          // operations per ancilla slot
     uint8_t aj[4];             // ancilla index (outcome bit) of slot k
+    uint8_t tbase[4];          // first table entry of slot k
     DiagOp ops[4][4];          // per slot, in time order; table index bit j = label bit of ops[k][j].d
     uint8_t lane_bit[4][4];    // lane bit that feeds table index bit j (255: the bit comes from the register index)
     uint32_t roff[4][16];      // register-index part of the table index, as a byte offset (index << 4)
@@ -108,14 +112,15 @@ __device__ __forceinline__ void dg_wht_inverse(double2 (&p)[16], double2 *xb, in
     dg_wht16(p);
 }
 
-// per-ancilla tables of one half cycle: two of the 64 (slot, index) entries per lane
+// per-ancilla tables of one half cycle: up to two of the (slot, index) entries per lane.
 // zmask: label bits whose value flips the sign of the amplitude (data Z events; data flips of the preceding
 // Hadamard-frame half), applied by the slot that owns the bit; g: global phase i^g, applied by the last slot
-__device__ __forceinline__ void dg_build_tables(const DiagHalf &H, const uint32_t *evw, double2 *A0, double2 *A1,
-                                                double2 *Q, int lane, uint32_t zmask, uint32_t g) {
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        const int e = lane + 32 * r, k = e >> 4, idx = e & 15;
+__device__ __forceinline__ void dg_build_tables(const DiagHalf &H, const uint32_t *evw, double2 *tab, int lane,
+                                                uint32_t zmask, uint32_t g) {
+#pragma unroll 1
+    for (int e = lane; e < (int)H.n_entries; e += 32) {
+        const int k = (e >= H.tbase[1]) + (e >= H.tbase[2]) + (e >= H.tbase[3]);
+        const int idx = e - H.tbase[k];
         double2 u = make_double2(1.0, 0.0), v = make_double2(0.0, 0.0), ph = make_double2(1.0, 0.0);
         const int n = H.n_ops[k];
         for (int j = 0; j < n; ++j) {
@@ -141,21 +146,21 @@ __device__ __forceinline__ void dg_build_tables(const DiagHalf &H, const uint32_
             else if (g == 3) ph = make_double2(ph.y, -ph.x);
         }
         const double2 a0 = dg_cmul(ph, u), a1 = dg_cmul(ph, v);
-        A0[e] = a0;
-        A1[e] = a1;
-        Q[e] = make_double2(fma(a0.x, a0.x, a0.y * a0.y), fma(a1.x, a1.x, a1.y * a1.y));
+        tab[e] = a0;
+        tab[e + kDgTabEntries] = a1;
+        tab[e + 2 * kDgTabEntries] = make_double2(fma(a0.x, a0.x, a0.y * a0.y), fma(a1.x, a1.x, a1.y * a1.y));
     }
 }
 
 // one ancilla slot: P(0), P(1) from the table of squared moduli, one Measure, multiply by the selected amplitudes.
-// tk: this lane's base into the tables of slot K (A0 at +0, A1 at +1024, Q at +2048)
-template <int K>
-__device__ __forceinline__ void dg_slot(double2 (&p)[16], const DiagHalf &H, const unsigned char *tk, bool forced, uint32_t fo,
-                                        double uu, int u_base, uint32_t &a_out, bool &bad, double &pfin) {
+// tk: this lane's base into the tables of the slot (A0 at +0, A1 at +16 kDgTabEntries, Q at +32 kDgTabEntries);
+// roff: register-index part of the table offsets (kernel parameter space, warp-uniform)
+__device__ __forceinline__ void dg_slot(double2 (&p)[16], const uint32_t *roff, uint32_t aj, const unsigned char *tk,
+                                        bool forced, uint32_t fo, double u, uint32_t &a_out, bool &bad, double &pfin) {
     double p0 = 0.0, p1 = 0.0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        const double2 q = *reinterpret_cast<const double2 *>(tk + 2048 + H.roff[K][i]);
+        const double2 q = *reinterpret_cast<const double2 *>(tk + 32 * kDgTabEntries + roff[i]);
         const double w = fma(p[i].x, p[i].x, p[i].y * p[i].y);
         p0 = fma(w, q.x, p0);
         p1 = fma(w, q.y, p1);
@@ -167,42 +172,20 @@ __device__ __forceinline__ void dg_slot(double2 (&p)[16], const DiagHalf &H, con
     }
     uint32_t out;
     if (forced) {
-        out = (fo >> H.aj[K]) & 1u;
+        out = (fo >> aj) & 1u;
         if ((out ? p1 : p0) <= 0.0) bad = true;
     } else {
-        const double u = __shfl_sync(0xffffffffu, uu, u_base + K);
         out = (u * (p0 + p1) < p1) ? 1u : 0u;                // Measure: P(1) against one uniform, as k_measure
     }
-    const unsigned char *ta = tk + (out ? 1024 : 0);
+    const unsigned char *ta = tk + (out ? 16 * kDgTabEntries : 0);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) p[i] = dg_cmul(p[i], *reinterpret_cast<const double2 *>(ta + H.roff[K][i]));
-    a_out |= out << H.aj[K];
+    for (int i = 0; i < 16; ++i) p[i] = dg_cmul(p[i], *reinterpret_cast<const double2 *>(ta + roff[i]));
+    a_out |= out << aj;
     pfin = out ? p1 : p0;
 }
 
-// one half cycle on the register-resident state.  Returns the raw outcome bits (ancilla-indexed) | 0x100 if a forced
-// outcome had probability zero; pfin = squared norm of the state it leaves (the state is NOT renormalised here: the
-// caller scales once, when it stores).  FRAME_X: p is in map 1 on entry and exit, map 2 in between.
-// tl[k]: this lane's byte offset into the tables of slot k (shot independent).
-template <bool FRAME_X>
-__device__ __forceinline__ uint32_t dg_half(double2 (&p)[16], const DiagHalf &H, const uint32_t (&tl)[4], const uint32_t *evw,
-                                            uint32_t zmask, uint32_t g, unsigned char *tab, double2 *xb, int lane,
-                                            bool forced, uint32_t fo, double uu, int u_base, double &pfin) {
-    if (FRAME_X) dg_wht_forward(p, xb, lane);
-    __syncwarp();
-    dg_build_tables(H, evw, reinterpret_cast<double2 *>(tab), reinterpret_cast<double2 *>(tab) + 64,
-                    reinterpret_cast<double2 *>(tab) + 128, lane, zmask, g);
-    __syncwarp();
-    uint32_t a_out = 0;
-    bool bad = false;
-    dg_slot<0>(p, H, tab + tl[0], forced, fo, uu, u_base, a_out, bad, pfin);
-    dg_slot<1>(p, H, tab + tl[1], forced, fo, uu, u_base, a_out, bad, pfin);
-    dg_slot<2>(p, H, tab + tl[2], forced, fo, uu, u_base, a_out, bad, pfin);
-    dg_slot<3>(p, H, tab + tl[3], forced, fo, uu, u_base, a_out, bad, pfin);
-    if (FRAME_X) { dg_wht_inverse(p, xb, lane); pfin *= 512.0; }      // the inverse transform multiplies the norm^2 by 512
-    return a_out | (bad ? 0x100u : 0u);
-}
-
+// The input block of every shot is the collapsed, normalised one at ancilla value 0 (the host collapses explicitly when
+// the previous cycle went through the generic sweep kernels).
 __global__ void __launch_bounds__(kDgThreads, 1)
 k_cycle(const __grid_constant__ DiagProg P, const __grid_constant__ MeasArgs ma, double2 *__restrict__ state,
         size_t stride, const uint32_t *__restrict__ ev, const uint32_t *__restrict__ frm, const uint32_t *__restrict__ act_list,
@@ -213,10 +196,10 @@ k_cycle(const __grid_constant__ DiagProg P, const __grid_constant__ MeasArgs ma,
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char *wb = smem_raw + (size_t)warp * kDgWarpBytes;
     double2 *buf = reinterpret_cast<double2 *>(wb);                                  // [2][512]
-    unsigned char *tab = wb + 2 * kRunBytes;                                         // A0[64] | A1[64] | Q[64]
-    unsigned char *meta = wb + 2 * kRunBytes + kDgTabBytes;                          // [3][kDgMetaBytes]
-    uint64_t *full = reinterpret_cast<uint64_t *>(meta + 3 * kDgMetaBytes);          // [2]
-    uint64_t *mfull = full + 2;                                                      // [3]
+    unsigned char *tab = wb + 2 * kRunBytes;                                         // A0 | A1 | Q
+    unsigned char *meta = wb + 2 * kRunBytes + kDgTabBytes;                          // [2][kDgMetaBytes]
+    uint64_t *full = reinterpret_cast<uint64_t *>(meta + 2 * kDgMetaBytes);          // [2]
+    uint64_t *mfull = full + 2;                                                      // [2]
 
     const uint32_t n_items = *n_act_ptr;
     const uint32_t n_warps = gridDim.x * kDgWarps, gw = blockIdx.x * kDgWarps + warp;
@@ -226,71 +209,62 @@ k_cycle(const __grid_constant__ DiagProg P, const __grid_constant__ MeasArgs ma,
 
     if (lane == 0) {
         mbar_init(&full[0], 1); mbar_init(&full[1], 1);
-        mbar_init(&mfull[0], 1); mbar_init(&mfull[1], 1); mbar_init(&mfull[2], 1);
+        mbar_init(&mfull[0], 1); mbar_init(&mfull[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
 
-    // lane part of the table indices (shot independent), as byte offsets into the tables
-    uint32_t tl[2][4];
+    // this lane's first table entry per slot (shot independent): slot base + lane part of the index, one byte per slot
+    uint32_t tlp[2];
 #pragma unroll
-    for (int h = 0; h < 2; ++h)
+    for (int h = 0; h < 2; ++h) {
+        tlp[h] = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            uint32_t li = 0;
+            uint32_t li = P.h[h].tbase[k];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int lb = P.h[h].lane_bit[k][j];
-                if (lb != 255) li |= (uint32_t)((lane >> lb) & 1) << j;
+                if (lb != 255) li += (uint32_t)((lane >> lb) & 1) << j;
             }
-            tl[h][k] = (li + 16u * (uint32_t)k) << 4;
+            tlp[h] |= li << (8 * k);
         }
+    }
 
-    auto issue_meta = [&](uint32_t shot_, int slot) {
-        unsigned char *m = meta + slot * kDgMetaBytes;
-        mbar_expect_tx(&mfull[slot], kDgMetaBytes);
-        tma_load_1d(m, ev + (size_t)shot_ * S17_EV_WORDS, kEvBytes, &mfull[slot]);
-        tma_load_1d(m + kEvBytes, aux + shot_, kAuxBytes, &mfull[slot]);
-        tma_load_1d(m + kEvBytes + kAuxBytes, frm + (size_t)shot_ * 4, kDgFrmBytes, &mfull[slot]);
-    };
-    auto issue_state = [&](uint32_t shot_, int slot, int sb) {
-        const ShotAux *ax = reinterpret_cast<const ShotAux *>(meta + slot * kDgMetaBytes + kEvBytes);
-        const uint32_t blk = ax->collapsed ? 0u : ax->anc_outcome;       // lazy collapse + reset: the surviving block
-        fence_proxy_async_smem();                 // the buffer was last touched through the generic proxy
-        mbar_expect_tx(&full[sb], kRunBytes);
-        tma_load_1d(buf + sb * kRun, state + (size_t)shot_ * stride + (size_t)blk * kRun, kRunBytes, &full[sb]);
+    // one shot ahead: its event + frame words and its 8 KiB block
+    auto prefetch = [&](uint32_t shot_, int sb) {
+        unsigned char *m = meta + sb * kDgMetaBytes;
+        fence_proxy_async_smem();                 // the buffers were last touched through the generic proxy
+        mbar_expect_tx(&mfull[sb], kDgMetaBytes);
+        tma_load_1d(m, ev + (size_t)shot_ * S17_EV_WORDS, kEvBytes, &mfull[sb]);
+        tma_load_1d(m + kEvBytes, frm + (size_t)shot_ * 4, kDgFrmBytes, &mfull[sb]);
+        if (init_basis < 0) {
+            mbar_expect_tx(&full[sb], kRunBytes);
+            tma_load_1d(buf + sb * kRun, state + (size_t)shot_ * stride, kRunBytes, &full[sb]);
+        }
     };
 
     uint32_t shot = act_list[first];
-    uint32_t shot1 = first + 1 < last ? act_list[first + 1] : 0u;
-    if (lane == 0) {
-        issue_meta(shot, 0);
-        if (first + 1 < last) issue_meta(shot1, 1);
-    }
-    mbar_wait(&mfull[0], 0);
-    if (init_basis < 0 && lane == 0) issue_state(shot, 0, 0);
+    if (lane == 0) prefetch(shot, 0);
 
     const uint32_t nout = 8u * (uint32_t)ma.stage;
+    const bool is_forced = ma.forced != 0;
     uint32_t j = 0;
     for (uint32_t item = first; item < last; ++item, ++j) {
-        const int slot = (int)(j % 3u), sb = (int)(j & 1u);
-        uint32_t shot2 = 0;
-        if (item + 2 < last) {
-            shot2 = act_list[item + 2];
-            if (lane == 0) issue_meta(shot2, (int)((j + 2u) % 3u));
-        }
+        const int sb = (int)(j & 1u);
+        uint32_t shot1 = 0;
         if (item + 1 < last) {
-            mbar_wait(&mfull[(j + 1u) % 3u], ((j + 1u) / 3u) & 1u);
-            if (init_basis < 0 && lane == 0) issue_state(shot1, (int)((j + 1u) % 3u), sb ^ 1);
+            shot1 = act_list[item + 1];
+            if (lane == 0) prefetch(shot1, sb ^ 1);
         }
-        const uint32_t *evw = reinterpret_cast<const uint32_t *>(meta + slot * kDgMetaBytes);
-        const uint32_t *fwp = reinterpret_cast<const uint32_t *>(meta + slot * kDgMetaBytes + kEvBytes + kAuxBytes);
+        const uint32_t *evw = reinterpret_cast<const uint32_t *>(meta + sb * kDgMetaBytes);
+        const uint32_t *fwp = reinterpret_cast<const uint32_t *>(meta + sb * kDgMetaBytes + kEvBytes);
         double2 *xb = buf + sb * kRun;
 
         // replayed outcomes of this cycle's eight ancillas / the eight uniforms of its Measure gates
         uint32_t fo = 0;
         double uu = 0.0;
-        if (ma.forced) {
+        if (is_forced) {
             const uint32_t b = lane < 8 ? (uint32_t)forced[(size_t)shot * S17_MAX_OUTCOMES + nout + lane] : 0u;
             fo = __ballot_sync(0xffffffffu, (b & 1u) != 0u) & 0xFFu;
         } else if (lane < 8) {
@@ -309,36 +283,55 @@ k_cycle(const __grid_constant__ DiagProg P, const __grid_constant__ MeasArgs ma,
             for (int i = 0; i < 16; ++i)
                 p[i] = make_double2((int)dg_label<1>(lane, i) == init_basis ? 1.0 : 0.0, 0.0);
         }
+        mbar_wait(&mfull[sb], (j >> 1) & 1u);
         __syncwarp();                             // every lane holds its amplitudes: the buffer becomes exchange scratch
 
-        // frame words: bits 0-8 flip mask, 9-17 sign mask, 18-19 phase.  Signs and phases ride in the tables; the data
-        // flips of the Hadamard-frame half are signs after its inverse transform, i.e. part of the next half's sign mask
-        const uint32_t f0 = fwp[0], f1 = fwp[1];
+        // frame words: bits 0-8 flip mask, 9-17 sign mask, 18-19 phase.  Signs and phases ride in the tables.  The data
+        // flips of a Hadamard-frame half are signs after its inverse transform, i.e. part of the next half's sign mask;
+        // those of a computational-frame half are a relabeling, applied by the store.
+        uint32_t carry = 0, perm = 0;
         double pfin = 1.0;
-        const uint32_t r0 = dg_half<true>(p, P.h[0], tl[0], evw, (f0 >> 9) & 511u, (f0 >> 18) & 3u, tab, xb, lane,
-                                          ma.forced != 0, fo, uu, 0, pfin);
-        const uint32_t r1 = dg_half<false>(p, P.h[1], tl[1], evw, ((f1 >> 9) ^ f0) & 511u, (f1 >> 18) & 3u, tab, xb, lane,
-                                           ma.forced != 0, fo, uu, 4, pfin);
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            const DiagHalf &H = P.h[h];
+            const uint32_t fw = fwp[h];
+            if (H.frame_x) dg_wht_forward(p, xb, lane);
+            __syncwarp();
+            dg_build_tables(H, evw, reinterpret_cast<double2 *>(tab), lane, ((fw >> 9) ^ carry) & 511u, (fw >> 18) & 3u);
+            __syncwarp();
+            const uint32_t tl = h ? tlp[1] : tlp[0];
+            uint32_t a_out = 0;
+            bool bad = false;
+#pragma unroll 1
+            for (int k = 0; k < 4; ++k) {
+                const double u = __shfl_sync(0xffffffffu, uu, 4 * h + k);
+                dg_slot(p, H.roff[k], H.aj[k], tab + (((tl >> (8 * k)) & 0xFFu) << 4), is_forced, fo, u, a_out, bad, pfin);
+            }
+            if (H.frame_x) {
+                dg_wht_inverse(p, xb, lane);
+                pfin *= 512.0;                    // the inverse transform multiplies the norm^2 by 512
+                carry = fw & 511u;
+            } else {
+                carry = 0;
+                perm = fw & 511u;
+            }
+            if (lane == 0) meas_out[2 * shot + H.final_part] = a_out | (bad ? 0x100u : 0u);
+        }
 
-        // renormalise once (the squared norm of the selected branch is the last conditional weight); the data flips of
-        // the computational-frame half are a relabeling, applied by the store
+        // renormalise once (the squared norm of the selected branch is the last conditional weight)
         const double inv = pfin > 0.0 ? 1.0 / sqrt(pfin) : 0.0;
-        const uint32_t fm1 = f1 & 511u;
         double2 *sbase = state + (size_t)shot * stride;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) sbase[dg_label<1>(lane, i) ^ fm1] = make_double2(p[i].x * inv, p[i].y * inv);
+        for (int i = 0; i < 16; ++i) sbase[dg_label<1>(lane, i) ^ perm] = make_double2(p[i].x * inv, p[i].y * inv);
         if (lane == 0) {
             ShotAux ax;
             ax.scale = 1.0;
             ax.anc_outcome = 0;
             ax.collapsed = 1;                     // the normalised block is stored at ancilla value 0
             aux[shot] = ax;
-            meas_out[2 * shot + P.h[0].final_part] = r0;
-            meas_out[2 * shot + P.h[1].final_part] = r1;
         }
         __syncwarp();                             // scratch, tables and the metadata slot are reused
         shot = shot1;
-        shot1 = shot2;
     }
     if (lane == 0) {
         atomicAdd(&counters[4], (unsigned long long)(last - first));                                     // C_SWEEPS
