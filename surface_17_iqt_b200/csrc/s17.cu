@@ -837,6 +837,9 @@ struct s17_ctx {
     // whole-cycle diagonal-frame programs (k_cycle) per cycle kind, when the cycle has that structure
     DiagProg diag_prog[3];
     bool diag_ok[3] = {false, false, false};
+    DiagProg1 diag_prog1[3];          // the same with host-chosen label maps (k_cycle1), when such maps exist
+    bool diag1_ok[3] = {false, false, false};
+    bool no_diag1 = false;
     bool no_diag = false;
     bool last_collapsed = true;       // the previous cycle left every active shot collapsed to ancilla block 0
     uint32_t *frm = nullptr;          // per shot: frame words of the two half cycles (k_plan -> k_cycle)
@@ -962,6 +965,7 @@ extern "C" int s17_create(s17_ctx **out, int device, uint64_t max_shots) {
     CK(cudaMalloc(&ctx->frm, B * 4 * 4));
     CK(cudaMemset(ctx->frm, 0, B * 4 * 4));
     CK(cudaFuncSetAttribute(k_cycle, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDgSmem));
+    CK(cudaFuncSetAttribute(k_cycle1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDgSmem));
     {
         typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -982,7 +986,8 @@ extern "C" int s17_create(s17_ctx **out, int device, uint64_t max_shots) {
         const char *nf = getenv("S17_FUSE");
         ctx->no_fuse = nf && nf[0] == '0';
         const char *nd = getenv("S17_DIAG");
-        ctx->no_diag = nd && nd[0] == '0';
+        ctx->no_diag = nd && nd[0] == '0';          // 0: k_half everywhere; g: generic k_cycle only; default: k_cycle1 if possible
+        ctx->no_diag1 = nd && nd[0] == 'g';
         const char *r = getenv("S17_RING");
         ctx->force_ring = r && r[0] == '1';
     }
@@ -1336,6 +1341,108 @@ static bool make_diag_half(const LayerArg2 &P, const HalfTail &T, int half_index
     return true;
 }
 
+// ---- k_cycle1: choose label <-> (lane, register) maps under which every slot indexes its table with <= 1 register bit ----
+static bool gf2_invertible3(const uint8_t v[3]) {
+    // three 3-bit vectors are linearly independent over GF(2) iff no non-empty subset XORs to zero
+    for (int m = 1; m < 8; ++m) {
+        uint8_t x = 0;
+        for (int k = 0; k < 3; ++k)
+            if ((m >> k) & 1) x ^= v[k];
+        if (x == 0) return false;
+    }
+    return true;
+}
+
+static void fill_map(DiagMap &M, const std::vector<int> &reg, const std::vector<int> &lane, const uint8_t gvec[9]) {
+    memset(&M, 0, sizeof(M));
+    for (int j = 0; j < 4; ++j) M.reg[j] = (uint8_t)reg[j];
+    for (int m = 0; m < 5; ++m) M.lane[m] = (uint8_t)lane[m];
+    for (int i = 0; i < 16; ++i) {
+        uint32_t label = 0, c = 0;
+        for (int j = 0; j < 4; ++j)
+            if ((i >> j) & 1) label |= 1u << reg[j];
+        for (int b = 3; b < 9; ++b)
+            if ((label >> b) & 1u) c ^= gvec[b];
+        M.lin16[i] = label << 4;
+        M.swz16[i] = (label ^ c) << 4;
+    }
+}
+
+// lane_bit / single register bit of every slot of H under map M; false if a slot needs more than one register bit
+static bool apply_map1(DiagHalf &H, const DiagMap &M, uint8_t rbit[4], uint32_t off1[4]) {
+    memset(H.lane_bit, 255, sizeof(H.lane_bit));
+    for (int k = 0; k < 4; ++k) {
+        rbit[k] = 0;
+        off1[k] = 0;
+        int n_reg = 0;
+        for (int j = 0; j < H.n_ops[k]; ++j) {
+            const int d = H.ops[k][j].d;
+            bool placed = false;
+            for (int m = 0; m < 5; ++m)
+                if (M.lane[m] == d) { H.lane_bit[k][j] = (uint8_t)m; placed = true; }
+            for (int r = 0; r < 4; ++r)
+                if (M.reg[r] == d) { rbit[k] = (uint8_t)r; off1[k] = (uint32_t)(1u << j) << 4; ++n_reg; placed = true; }
+            if (!placed) return false;
+        }
+        if (n_reg > 1) return false;
+    }
+    return true;
+}
+
+static bool make_diag1(const DiagProg &G, DiagProg1 &P1) {
+    memset(&P1, 0, sizeof(P1));
+    const DiagHalf &hx = G.h[0], &hz = G.h[1];
+    auto count_ok = [](const DiagHalf &H, uint32_t regmask) {
+        for (int k = 0; k < 4; ++k) {
+            int n = 0;
+            for (int j = 0; j < H.n_ops[k]; ++j) n += (regmask >> H.ops[k][j].d) & 1u;
+            if (n > 1) return false;
+        }
+        return true;
+    };
+    for (uint32_t rz = 0; rz < 512; ++rz) {
+        if (__builtin_popcount(rz) != 4 || !count_ok(hz, rz)) continue;
+        for (int sh = 0; sh < 9; ++sh) {
+            if ((rz >> sh) & 1u) continue;
+            const uint32_t rx = 0x1FFu & ~rz & ~(1u << sh);
+            if (!count_ok(hx, rx)) continue;
+            std::vector<int> regA, laneA, regB, laneB;
+            for (int b = 0; b < 9; ++b) {
+                ((rz >> b) & 1u ? regA : laneA).push_back(b);
+                ((rx >> b) & 1u ? regB : laneB).push_back(b);
+            }
+            // exchange swizzle: the three lowest lane bits of either map must reach eight different 16-byte columns
+            std::vector<int> hi;                               // label bits >= 3 among those six lane bits
+            for (int m = 0; m < 3; ++m) {
+                if (laneA[m] >= 3) hi.push_back(laneA[m]);
+                if (laneB[m] >= 3 && std::find(hi.begin(), hi.end(), laneB[m]) == hi.end()) hi.push_back(laneB[m]);
+            }
+            uint8_t gvec[9] = {1, 2, 4, 0, 0, 0, 0, 0, 0};
+            bool found = false;
+            const uint32_t combos = 1u << (3 * hi.size());
+            for (uint32_t c = 0; c < combos && !found; ++c) {
+                for (size_t q = 0; q < hi.size(); ++q) gvec[hi[q]] = (uint8_t)((c >> (3 * q)) & 7u);
+                uint8_t va[3], vb[3];
+                for (int m = 0; m < 3; ++m) { va[m] = gvec[laneA[m]]; vb[m] = gvec[laneB[m]]; }
+                found = gf2_invertible3(va) && gf2_invertible3(vb);
+            }
+            if (!found) continue;
+            gvec[0] = gvec[1] = gvec[2] = 0;                   // bits 0-2 are the column itself
+            fill_map(P1.mapA, regA, laneA, gvec);
+            fill_map(P1.mapB, regB, laneB, gvec);
+            memcpy(P1.gvec, gvec, 9);
+            P1.h[0] = hx;
+            P1.h[1] = hz;
+            if (!apply_map1(P1.h[0], P1.mapB, P1.rbit[0], P1.off1[0])) continue;
+            if (!apply_map1(P1.h[1], P1.mapA, P1.rbit[1], P1.off1[1])) continue;
+            for (int m = 0; m < 5; ++m)
+                if (laneA[m] == sh) P1.sh_lane_bit = (uint8_t)m;
+            return true;
+        }
+    }
+    return false;
+}
+
 extern "C" int s17_load_program(s17_ctx *ctx, const s17_layer *layers, const uint32_t n_layers[3], const double *params,
                                 uint32_t n_params, const s17_pinstr *plan, uint32_t n_plan, const s17_lists *lists) {
     if (!ctx || !layers || !n_layers || !plan || !lists) return fail(ctx, S17_E_ARG, "s17_load_program: bad arguments");
@@ -1401,6 +1508,7 @@ extern "C" int s17_load_program(s17_ctx *ctx, const s17_layer *layers, const uin
                               ctx->diag_prog[c].h[0].frame_x == 1 && ctx->diag_prog[c].h[1].frame_x == 0 &&
                               (cov0 & ~cov1) == 0;
             if (ctx->diag_ok[c]) { ctx->diag_prog[c].h[0].final_part = 0; ctx->diag_prog[c].h[1].final_part = 1; }
+            ctx->diag1_ok[c] = ctx->diag_ok[c] && make_diag1(ctx->diag_prog[c], ctx->diag_prog1[c]);
         }
     }
     if (ctx->plan) { cudaFree(ctx->plan); ctx->plan = nullptr; }
@@ -1589,9 +1697,14 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
         ma.stream = 16u + (uint32_t)stage * 4u;
         {
             SCOPE(CAT_GATE);
-            k_cycle<<<ctx->num_sms, kDgThreads, kDgSmem, ctx->stream>>>(
-                ctx->diag_prog[which], ma, ctx->state, ctx->stride, ctx->ev, ctx->frm, ctx->act_list, ctx->n_act, ctx->aux, ctx->forced,
-                ctx->meas_out, ctx->counters, init_basis);
+            if (ctx->diag1_ok[which] && !ctx->no_diag1)
+                k_cycle1<<<ctx->num_sms, kDgThreads, kDgSmem, ctx->stream>>>(
+                    ctx->diag_prog1[which], ma, ctx->state, ctx->stride, ctx->ev, ctx->frm, ctx->act_list, ctx->n_act, ctx->aux,
+                    ctx->forced, ctx->meas_out, ctx->counters, init_basis);
+            else
+                k_cycle<<<ctx->num_sms, kDgThreads, kDgSmem, ctx->stream>>>(
+                    ctx->diag_prog[which], ma, ctx->state, ctx->stride, ctx->ev, ctx->frm, ctx->act_list, ctx->n_act, ctx->aux,
+                    ctx->forced, ctx->meas_out, ctx->counters, init_basis);
             ctx->n_gate++;
         }
         {

@@ -58,6 +58,25 @@ struct DiagHalf {
 };
 struct DiagProg { DiagHalf h[2]; };
 
+// k_cycle1: label <-> (lane, register) mappings chosen by the host so that every slot of a half cycle indexes its
+// table with at most ONE register bit: a lane then needs two table entries per slot instead of sixteen.
+struct DiagMap {
+    uint8_t reg[4];            // label bit carried by register index bit j
+    uint8_t lane[5];           // label bit carried by lane bit m
+    uint8_t pad[3];
+    uint32_t lin16[16];        // label part of register i, as a byte offset into a linear 512-amplitude buffer
+    uint32_t swz16[16];        // the same through the exchange swizzle
+};
+struct DiagProg1 {
+    DiagHalf h[2];             // lane_bit refers to the map of the half (B for the Hadamard frame, A otherwise)
+    DiagMap mapA, mapB;        // A: load / store and the computational-frame half; B: the Hadamard-frame half
+    uint8_t sh_lane_bit;       // lane bit (map A) of the one label bit transformed by the shuffle stage
+    uint8_t gvec[9];           // exchange swizzle: 16-byte column ^= gvec[b] for every set label bit b >= 3
+    uint8_t pad[2];
+    uint8_t rbit[2][4];        // register index bit that feeds the table index of slot k (any value when off1 == 0)
+    uint32_t off1[2][4];       // byte offset from the slot's entry for that bit = 0 to the one for bit = 1
+};
+
 __device__ __forceinline__ double2 dg_cmul(const double2 a, const double2 b) {
     return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
 }
@@ -334,6 +353,246 @@ k_cycle(const __grid_constant__ DiagProg P, const __grid_constant__ MeasArgs ma,
         shot = shot1;
     }
     if (lane == 0) {
+        atomicAdd(&counters[4], (unsigned long long)(last - first));                                     // C_SWEEPS
+        atomicAdd(&counters[8], (unsigned long long)(last - first) * (init_basis < 0 ? 2ull : 1ull));   // 8 KiB runs moved
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_cycle1: the same cycle with host-chosen mappings (DiagProg1).  Per slot a lane loads two table entries.
+// ------------------------------------------------------------------------------------------------------------------
+template <int B>
+__device__ __forceinline__ void dg_slot1(double2 (&p)[16], const unsigned char *tk0, const unsigned char *tk1, uint32_t aj,
+                                         bool forced, uint32_t fo, double u, uint32_t &a_out, bool &bad, double &pfin) {
+    const double2 q0 = *reinterpret_cast<const double2 *>(tk0 + 32 * kDgTabEntries);
+    const double2 q1 = *reinterpret_cast<const double2 *>(tk1 + 32 * kDgTabEntries);
+    double w0[2] = {0.0, 0.0}, w1[2] = {0.0, 0.0};           // two partial sums each: shorter dependency chains
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const double w = fma(p[i].x, p[i].x, p[i].y * p[i].y);
+        if ((i >> B) & 1) w1[(i >> ((B + 1) & 3)) & 1] += w;
+        else w0[(i >> ((B + 1) & 3)) & 1] += w;
+    }
+    const double W0 = w0[0] + w0[1], W1 = w1[0] + w1[1];
+    double p0 = fma(q0.x, W0, q1.x * W1), p1 = fma(q0.y, W0, q1.y * W1);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        p0 += __shfl_xor_sync(0xffffffffu, p0, d);
+        p1 += __shfl_xor_sync(0xffffffffu, p1, d);
+    }
+    uint32_t out;
+    if (forced) {
+        out = (fo >> aj) & 1u;
+        if ((out ? p1 : p0) <= 0.0) bad = true;
+    } else {
+        out = (u * (p0 + p1) < p1) ? 1u : 0u;                // Measure: P(1) against one uniform, as k_measure
+    }
+    const uint32_t sel = out ? 16u * kDgTabEntries : 0u;
+    const double2 a0 = *reinterpret_cast<const double2 *>(tk0 + sel), a1 = *reinterpret_cast<const double2 *>(tk1 + sel);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) p[i] = dg_cmul(p[i], ((i >> B) & 1) ? a1 : a0);
+    a_out |= out << aj;
+    pfin = out ? p1 : p0;
+}
+
+__global__ void __launch_bounds__(kDgThreads, 1)
+k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ MeasArgs ma, double2 *__restrict__ state,
+         size_t stride, const uint32_t *__restrict__ ev, const uint32_t *__restrict__ frm, const uint32_t *__restrict__ act_list,
+         const uint32_t *__restrict__ n_act_ptr, ShotAux *__restrict__ aux, const uint8_t *__restrict__ forced,
+         uint32_t *__restrict__ meas_out, unsigned long long *__restrict__ counters, int init_basis)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *wb = smem_raw + (size_t)warp * kDgWarpBytes;
+    unsigned char *buf = wb;                                                         // [2][8 KiB]
+    unsigned char *tab = wb + 2 * kRunBytes;                                         // A0 | A1 | Q
+    unsigned char *meta = wb + 2 * kRunBytes + kDgTabBytes;                          // [2][kDgMetaBytes]
+    uint64_t *full = reinterpret_cast<uint64_t *>(meta + 2 * kDgMetaBytes);          // [2]
+    uint64_t *mfull = full + 2;                                                      // [2]
+
+    const uint32_t n_items = *n_act_ptr;
+    const uint32_t n_warps = gridDim.x * kDgWarps, gw = blockIdx.x * kDgWarps + warp;
+    const uint32_t chunk = (n_items + n_warps - 1) / n_warps;
+    const uint32_t first = gw * chunk, last = min(n_items, first + chunk);
+    if (first >= last) return;                    // no CTA-wide barrier below: warps are independent
+
+    if (lane == 0) {
+        mbar_init(&full[0], 1); mbar_init(&full[1], 1);
+        mbar_init(&mfull[0], 1); mbar_init(&mfull[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    // lane parts (shot independent): label offsets of the two maps, linear and through the exchange swizzle, and this
+    // lane's first table entry per slot (one byte per slot)
+    uint32_t laneA = 0, laneB = 0;
+#pragma unroll
+    for (int m = 0; m < 5; ++m) {
+        if ((lane >> m) & 1) { laneA |= 1u << P.mapA.lane[m]; laneB |= 1u << P.mapB.lane[m]; }
+    }
+    auto swz = [&](uint32_t label) {
+        uint32_t c = 0;
+#pragma unroll
+        for (int b = 3; b < 9; ++b)
+            if ((label >> b) & 1u) c ^= P.gvec[b];
+        return label ^ c;
+    };
+    const uint32_t linA = laneA << 4, swzA = swz(laneA) << 4, swzB = swz(laneB) << 4;
+    const double sh_sign = ((lane >> P.sh_lane_bit) & 1) ? -1.0 : 1.0;
+    const int sh_mask = 1 << P.sh_lane_bit;
+    uint32_t tlp[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        tlp[h] = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t li = P.h[h].tbase[k];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int lb = P.h[h].lane_bit[k][j];
+                if (lb != 255) li += (uint32_t)((lane >> lb) & 1) << j;
+            }
+            tlp[h] |= li << (8 * k);
+        }
+    }
+
+    auto prefetch = [&](uint32_t shot_, int sb) {
+        unsigned char *m = meta + sb * kDgMetaBytes;
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the bulk store staged in this buffer has left it
+        fence_proxy_async_smem();                 // the buffers were last touched through the generic proxy
+        mbar_expect_tx(&mfull[sb], kDgMetaBytes);
+        tma_load_1d(m, ev + (size_t)shot_ * S17_EV_WORDS, kEvBytes, &mfull[sb]);
+        tma_load_1d(m + kEvBytes, frm + (size_t)shot_ * 4, kDgFrmBytes, &mfull[sb]);
+        if (init_basis < 0) {
+            mbar_expect_tx(&full[sb], kRunBytes);
+            tma_load_1d(buf + sb * kRunBytes, state + (size_t)shot_ * stride, kRunBytes, &full[sb]);
+        }
+    };
+    auto lane_stage = [&](double2 (&q)[16]) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const double ox = __shfl_xor_sync(0xffffffffu, q[i].x, sh_mask), oy = __shfl_xor_sync(0xffffffffu, q[i].y, sh_mask);
+            q[i] = make_double2(fma(sh_sign, q[i].x, ox), fma(sh_sign, q[i].y, oy));
+        }
+    };
+
+    uint32_t shot = act_list[first];
+    if (lane == 0) prefetch(shot, 0);
+
+    const uint32_t nout = 8u * (uint32_t)ma.stage;
+    const bool is_forced = ma.forced != 0;
+    uint32_t j = 0;
+    for (uint32_t item = first; item < last; ++item, ++j) {
+        const int sb = (int)(j & 1u);
+        uint32_t shot1 = 0;
+        if (item + 1 < last) {
+            shot1 = act_list[item + 1];
+            if (lane == 0) prefetch(shot1, sb ^ 1);
+        }
+        const uint32_t *evw = reinterpret_cast<const uint32_t *>(meta + sb * kDgMetaBytes);
+        const uint32_t *fwp = reinterpret_cast<const uint32_t *>(meta + sb * kDgMetaBytes + kEvBytes);
+        unsigned char *xb = buf + sb * kRunBytes;
+
+        uint32_t fo = 0;
+        double uu = 0.0;
+        if (is_forced) {
+            const uint32_t b = lane < 8 ? (uint32_t)forced[(size_t)shot * S17_MAX_OUTCOMES + nout + lane] : 0u;
+            fo = __ballot_sync(0xffffffffu, (b & 1u) != 0u) & 0xFFu;
+        } else if (lane < 8) {
+            Philox rng(ma.seed, ma.first_shot + shot, ma.stream + ((lane >> 2) ? 0u : 1u));
+            rng.c3 = (uint32_t)(lane & 3);
+            uu = rng.next();
+        }
+
+        double2 p[16];
+        if (init_basis < 0) {
+            mbar_wait(&full[sb], (j >> 1) & 1u);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) p[i] = *reinterpret_cast<const double2 *>(xb + (linA ^ P.mapA.lin16[i]));
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                p[i] = make_double2((linA ^ P.mapA.lin16[i]) == ((uint32_t)init_basis << 4) ? 1.0 : 0.0, 0.0);
+        }
+        mbar_wait(&mfull[sb], (j >> 1) & 1u);
+        __syncwarp();                             // every lane holds its amplitudes: the buffer becomes exchange scratch
+
+        uint32_t carry = 0, perm = 0;
+        double pfin = 1.0;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            const DiagHalf &H = P.h[h];
+            const uint32_t fw = fwp[h];
+            if (H.frame_x) {                      // register bits of map A, the shuffle bit, exchange, register bits of map B
+                dg_wht16(p);
+                lane_stage(p);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) *reinterpret_cast<double2 *>(xb + (swzA ^ P.mapA.swz16[i])) = p[i];
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) p[i] = *reinterpret_cast<const double2 *>(xb + (swzB ^ P.mapB.swz16[i]));
+                dg_wht16(p);
+            }
+            __syncwarp();
+            dg_build_tables(H, evw, reinterpret_cast<double2 *>(tab), lane, ((fw >> 9) ^ carry) & 511u, (fw >> 18) & 3u);
+            __syncwarp();
+            const uint32_t tl = h ? tlp[1] : tlp[0];
+            uint32_t a_out = 0;
+            bool bad = false;
+#pragma unroll 1
+            for (int k = 0; k < 4; ++k) {
+                const double u = __shfl_sync(0xffffffffu, uu, 4 * h + k);
+                const unsigned char *tk0 = tab + (((tl >> (8 * k)) & 0xFFu) << 4), *tk1 = tk0 + P.off1[h][k];
+                const uint32_t aj = H.aj[k];
+                switch (P.rbit[h][k] & 3) {
+                case 0: dg_slot1<0>(p, tk0, tk1, aj, is_forced, fo, u, a_out, bad, pfin); break;
+                case 1: dg_slot1<1>(p, tk0, tk1, aj, is_forced, fo, u, a_out, bad, pfin); break;
+                case 2: dg_slot1<2>(p, tk0, tk1, aj, is_forced, fo, u, a_out, bad, pfin); break;
+                default: dg_slot1<3>(p, tk0, tk1, aj, is_forced, fo, u, a_out, bad, pfin); break;
+                }
+            }
+            if (H.frame_x) {
+                dg_wht16(p);
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) *reinterpret_cast<double2 *>(xb + (swzB ^ P.mapB.swz16[i])) = p[i];
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) p[i] = *reinterpret_cast<const double2 *>(xb + (swzA ^ P.mapA.swz16[i]));
+                lane_stage(p);
+                dg_wht16(p);
+                pfin *= 512.0;                    // the inverse transform multiplies the norm^2 by 512
+                carry = fw & 511u;
+            } else {
+                carry = 0;
+                perm = fw & 511u;
+            }
+            if (lane == 0) meas_out[2 * shot + H.final_part] = a_out | (bad ? 0x100u : 0u);
+        }
+
+        // renormalise once, stage the block in label order (data flips of the computational-frame half relabel it) and
+        // hand it to one bulk store
+        const double inv = pfin > 0.0 ? 1.0 / sqrt(pfin) : 0.0;
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            *reinterpret_cast<double2 *>(xb + ((linA ^ P.mapA.lin16[i]) ^ (perm << 4))) = make_double2(p[i].x * inv, p[i].y * inv);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            tma_store_1d(state + (size_t)shot * stride, xb, kRunBytes);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            ShotAux ax;
+            ax.scale = 1.0;
+            ax.anc_outcome = 0;
+            ax.collapsed = 1;                     // the normalised block is stored at ancilla value 0
+            aux[shot] = ax;
+        }
+        __syncwarp();                             // tables and the metadata slot are reused
+        shot = shot1;
+    }
+    if (lane == 0) {
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         atomicAdd(&counters[4], (unsigned long long)(last - first));                                     // C_SWEEPS
         atomicAdd(&counters[8], (unsigned long long)(last - first) * (init_basis < 0 ? 2ull : 1ull));   // 8 KiB runs moved
     }

@@ -67,13 +67,14 @@ def test_golden_replays(error_models, correction_table, bitflip_table, golden, f
         sim.close()
 
 
-@pytest.mark.parametrize("dense,fusion,early,diag", [("0", 2, True, "1"), ("0", 2, True, "0"), ("1", 2, True, "1"),
+@pytest.mark.parametrize("dense,fusion,early,diag", [("0", 2, True, "1"), ("0", 2, True, "0"), ("0", 2, True, "g"), ("1", 2, True, "1"),
                                                      ("0", 4, True, "1"), ("0", 1, True, "1"), ("0", 2, False, "1"),
                                                      ("0", 0, True, "1")])
 def test_golden_replays_fast_path(error_models, correction_table, bitflip_table, golden, dense, fusion, early, diag,
                                   monkeypatch):
     """Same replays through the production path (lazy collapse, correction folded into the read-out).
-    diag=1: whole-cycle diagonal-frame kernel k_cycle where the cycle allows it; diag=0: k_half everywhere."""
+    diag=1: whole-cycle diagonal-frame kernel (k_cycle1, host-chosen label maps) where the cycle allows it; diag=g: its
+    generic form k_cycle; diag=0: k_half everywhere."""
     monkeypatch.setenv("S17_DENSE", dense)
     monkeypatch.setenv("S17_DIAG", diag)
     reps = golden("replays.json")["replays"]
@@ -169,7 +170,7 @@ def test_amplitudes_noisy_cycle_before_measurement(error_models, correction_tabl
     ("Dress_cooling", "s2", True, [0, 0, 1, 2, 0, 3]),
     ("PDD_cooling", "single", True, [1, 1, 1, 1, 1, 2]),
 ])
-@pytest.mark.parametrize("fusion,diag", [(2, "1"), (2, "0"), (4, "1")])
+@pytest.mark.parametrize("fusion,diag", [(2, "1"), (2, "0"), (2, "g"), (4, "1")])
 def test_sampled_trajectories_replay_bit_exact_in_oracle(error_models, correction_table, bitflip_table, model,
                                                          protocol, cooling, eset, fusion, diag, monkeypatch):
     """Device-sampled shots (Philox placement + outcomes): replaying their masks and outcomes through the
@@ -197,16 +198,17 @@ def test_sampled_trajectories_replay_bit_exact_in_oracle(error_models, correctio
     sim.close()
 
 
+@pytest.mark.parametrize("diag", ["1", "g"])
 @pytest.mark.parametrize("model,eset", [("PDD_model", [2, 2, 3, 6, 2]), ("Dress_model", [1, 1, 2, 8, 1]),
                                         ("PDD_model", [0, 0, 0, 0, 0])])
-def test_cycle_kernel_matches_half_kernel(error_models, correction_table, bitflip_table, model, eset, monkeypatch):
-    """The diagonal-frame cycle kernel (k_cycle) against the general amplitude kernel (k_half): the trajectories one
-    samples, replayed through the other, give the same records and the same stored amplitudes (<= 1e-10, phase
-    included) for every shot."""
+def test_cycle_kernel_matches_half_kernel(error_models, correction_table, bitflip_table, model, eset, diag, monkeypatch):
+    """The diagonal-frame cycle kernels (k_cycle1 / k_cycle) against the general amplitude kernel (k_half): the
+    trajectories one samples, replayed through the other, give the same records and the same stored amplitudes
+    (<= 1e-10, phase included) for every shot."""
     per_round = circuit.list_lengths(error_models[model])
     locs = [2 * x for x in per_round]
     n = 96
-    monkeypatch.setenv("S17_DIAG", "1")
+    monkeypatch.setenv("S17_DIAG", diag)
     sim = make_sim(error_models, correction_table, bitflip_table, model, locs, n, 2)
     sim.backend.set_subset(eset, locs)
     c1 = sim.backend.run("s2", n, L.NOISE_SUBSET, seed=321, first_shot_id=5)
