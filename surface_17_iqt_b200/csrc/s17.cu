@@ -1368,23 +1368,36 @@ static void fill_map(DiagMap &M, const std::vector<int> &reg, const std::vector<
     }
 }
 
-// lane_bit / single register bit of every slot of H under map M; false if a slot needs more than one register bit
-static bool apply_map1(DiagHalf &H, const DiagMap &M, uint8_t rbit[4], uint32_t off1[4]) {
-    memset(H.lane_bit, 255, sizeof(H.lane_bit));
-    for (int k = 0; k < 4; ++k) {
-        rbit[k] = 0;
-        off1[k] = 0;
-        int n_reg = 0;
+// Order the register bits of a map so that slot k of H is fed by register bit k (a slot takes at most one register bit
+// and a register bit feeds at most one slot), then fill lane_bit / off1.  false: no such order.
+static bool order_and_apply_map1(DiagHalf &H, std::vector<int> &reg, const std::vector<int> &lane, uint32_t off1[4]) {
+    int slot_of_bit[9], bit_of_slot[4] = {-1, -1, -1, -1};
+    for (int b = 0; b < 9; ++b) slot_of_bit[b] = -1;
+    for (int k = 0; k < 4; ++k)
         for (int j = 0; j < H.n_ops[k]; ++j) {
             const int d = H.ops[k][j].d;
+            if (std::find(reg.begin(), reg.end(), d) == reg.end()) continue;
+            if (slot_of_bit[d] >= 0 || bit_of_slot[k] >= 0) return false;
+            slot_of_bit[d] = k;
+            bit_of_slot[k] = d;
+        }
+    std::vector<int> spare;
+    for (int d : reg)
+        if (slot_of_bit[d] < 0) spare.push_back(d);
+    for (int k = 0; k < 4; ++k)
+        if (bit_of_slot[k] < 0) { bit_of_slot[k] = spare.back(); spare.pop_back(); }
+    for (int k = 0; k < 4; ++k) reg[k] = bit_of_slot[k];
+    memset(H.lane_bit, 255, sizeof(H.lane_bit));
+    for (int k = 0; k < 4; ++k) {
+        off1[k] = 0;
+        for (int j = 0; j < H.n_ops[k]; ++j) {
+            const int d = H.ops[k][j].d;
+            if (d == reg[k]) { off1[k] = (uint32_t)(1u << j) << 4; continue; }
             bool placed = false;
             for (int m = 0; m < 5; ++m)
-                if (M.lane[m] == d) { H.lane_bit[k][j] = (uint8_t)m; placed = true; }
-            for (int r = 0; r < 4; ++r)
-                if (M.reg[r] == d) { rbit[k] = (uint8_t)r; off1[k] = (uint32_t)(1u << j) << 4; ++n_reg; placed = true; }
+                if (lane[m] == d) { H.lane_bit[k][j] = (uint8_t)m; placed = true; }
             if (!placed) return false;
         }
-        if (n_reg > 1) return false;
     }
     return true;
 }
@@ -1428,13 +1441,13 @@ static bool make_diag1(const DiagProg &G, DiagProg1 &P1) {
             }
             if (!found) continue;
             gvec[0] = gvec[1] = gvec[2] = 0;                   // bits 0-2 are the column itself
+            P1.h[0] = hx;
+            P1.h[1] = hz;
+            if (!order_and_apply_map1(P1.h[0], regB, laneB, P1.off1[0])) continue;
+            if (!order_and_apply_map1(P1.h[1], regA, laneA, P1.off1[1])) continue;
             fill_map(P1.mapA, regA, laneA, gvec);
             fill_map(P1.mapB, regB, laneB, gvec);
             memcpy(P1.gvec, gvec, 9);
-            P1.h[0] = hx;
-            P1.h[1] = hz;
-            if (!apply_map1(P1.h[0], P1.mapB, P1.rbit[0], P1.off1[0])) continue;
-            if (!apply_map1(P1.h[1], P1.mapA, P1.rbit[1], P1.off1[1])) continue;
             for (int m = 0; m < 5; ++m)
                 if (laneA[m] == sh) P1.sh_lane_bit = (uint8_t)m;
             return true;

@@ -73,8 +73,8 @@ struct DiagProg1 {
     uint8_t sh_lane_bit;       // lane bit (map A) of the one label bit transformed by the shuffle stage
     uint8_t gvec[9];           // exchange swizzle: 16-byte column ^= gvec[b] for every set label bit b >= 3
     uint8_t pad[2];
-    uint8_t rbit[2][4];        // register index bit that feeds the table index of slot k (any value when off1 == 0)
-    uint32_t off1[2][4];       // byte offset from the slot's entry for that bit = 0 to the one for bit = 1
+    uint32_t off1[2][4];       // slot k's table index takes register index bit k: byte offset from the entry for that
+                               // bit = 0 to the one for bit = 1 (0: the slot does not depend on a register bit)
 };
 
 __device__ __forceinline__ double2 dg_cmul(const double2 a, const double2 b) {
@@ -539,18 +539,16 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ MeasArgs m
             const uint32_t tl = h ? tlp[1] : tlp[0];
             uint32_t a_out = 0;
             bool bad = false;
-#pragma unroll 1
-            for (int k = 0; k < 4; ++k) {
-                const double u = __shfl_sync(0xffffffffu, uu, 4 * h + k);
-                const unsigned char *tk0 = tab + (((tl >> (8 * k)) & 0xFFu) << 4), *tk1 = tk0 + P.off1[h][k];
-                const uint32_t aj = H.aj[k];
-                switch (P.rbit[h][k] & 3) {
-                case 0: dg_slot1<0>(p, tk0, tk1, aj, is_forced, fo, u, a_out, bad, pfin); break;
-                case 1: dg_slot1<1>(p, tk0, tk1, aj, is_forced, fo, u, a_out, bad, pfin); break;
-                case 2: dg_slot1<2>(p, tk0, tk1, aj, is_forced, fo, u, a_out, bad, pfin); break;
-                default: dg_slot1<3>(p, tk0, tk1, aj, is_forced, fo, u, a_out, bad, pfin); break;
-                }
+            // slot k indexes its table with register bit k (the host orders the register bits of both maps that way),
+            // so the four slot steps are four straight-line instances shared by both halves
+#define S17_DG_SLOT1(K)                                                                                              \
+            {                                                                                                        \
+                const double u = __shfl_sync(0xffffffffu, uu, 4 * h + K);                                            \
+                const unsigned char *tk0 = tab + (((tl >> (8 * K)) & 0xFFu) << 4);                                   \
+                dg_slot1<K>(p, tk0, tk0 + P.off1[h][K], H.aj[K], is_forced, fo, u, a_out, bad, pfin);                \
             }
+            S17_DG_SLOT1(0) S17_DG_SLOT1(1) S17_DG_SLOT1(2) S17_DG_SLOT1(3)
+#undef S17_DG_SLOT1
             if (H.frame_x) {
                 dg_wht16(p);
                 __syncwarp();
