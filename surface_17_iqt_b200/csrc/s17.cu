@@ -965,7 +965,7 @@ extern "C" int s17_create(s17_ctx **out, int device, uint64_t max_shots) {
     CK(cudaMalloc(&ctx->frm, B * 4 * 4));
     CK(cudaMemset(ctx->frm, 0, B * 4 * 4));
     CK(cudaFuncSetAttribute(k_cycle, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDgSmem));
-    CK(cudaFuncSetAttribute(k_cycle1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDgSmem));
+    CK(cudaFuncSetAttribute(k_cycle1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDgSmem1));
     {
         typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -1448,6 +1448,12 @@ static bool make_diag1(const DiagProg &G, DiagProg1 &P1) {
             fill_map(P1.mapA, regA, laneA, gvec);
             fill_map(P1.mapB, regB, laneB, gvec);
             memcpy(P1.gvec, gvec, 9);
+            for (int h = 0; h < 2; ++h)
+                for (int k = 0; k < 4; ++k) {
+                    P1.own[h][k] = 0;
+                    for (int j = 0; j < P1.h[h].n_ops[k]; ++j)
+                        if (P1.h[h].ops[k][j].flags & 4) P1.own[h][k] |= (uint16_t)(1u << P1.h[h].ops[k][j].d);
+                }
             for (int m = 0; m < 5; ++m)
                 if (laneA[m] == sh) P1.sh_lane_bit = (uint8_t)m;
             return true;
@@ -1711,7 +1717,7 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
         {
             SCOPE(CAT_GATE);
             if (ctx->diag1_ok[which] && !ctx->no_diag1)
-                k_cycle1<<<ctx->num_sms, kDgThreads, kDgSmem, ctx->stream>>>(
+                k_cycle1<<<ctx->num_sms, kDgThreads, kDgSmem1, ctx->stream>>>(
                     ctx->diag_prog1[which], ma, ctx->state, ctx->stride, ctx->ev, ctx->frm, ctx->act_list, ctx->n_act, ctx->aux,
                     ctx->forced, ctx->meas_out, ctx->counters, init_basis);
             else

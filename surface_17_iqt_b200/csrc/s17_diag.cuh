@@ -32,12 +32,14 @@ constexpr int kDgWarps = S17_DG_WARPS;                         // warps (= shots
 constexpr int kDgThreads = kDgWarps * 32;
 constexpr int kDgFrmBytes = 16;                                // per-shot frame words (4 x u32, two used)
 constexpr int kDgMetaBytes = kEvBytes + kDgFrmBytes;
-constexpr int kDgTabEntries = 48;                              // table entries of one half cycle (sum over slots of 2^n_ops)
+constexpr int kDgTabEntries = 40;                              // table entries of one half cycle (sum over slots of 2^n_ops)
 constexpr int kDgTabBytes = 3 * kDgTabEntries * 16;            // A0 | A1 | Q
 constexpr int kDgWarpBytes = 2 * kRunBytes + kDgTabBytes + 2 * kDgMetaBytes + 64;
 constexpr size_t kDgSmem = (size_t)kDgWarps * kDgWarpBytes;
+// k_cycle1 adds, per CTA, the tables of an event-free half cycle (both halves) and 128 zero bytes of event words
+constexpr size_t kDgSmem1 = kDgSmem + 2 * kDgTabBytes + kEvBytes;
 static_assert(kDgWarpBytes % 16 == 0, "per-warp shared memory must keep 16-byte alignment");
-static_assert(kDgSmem <= 232448, "k_cycle: shared memory per SM");
+static_assert(kDgSmem1 <= 232448, "k_cycle1: shared memory per SM");
 
 struct DiagOp {
     uint8_t d, ev_word;
@@ -73,6 +75,7 @@ struct DiagProg1 {
     uint8_t sh_lane_bit;       // lane bit (map A) of the one label bit transformed by the shuffle stage
     uint8_t gvec[9];           // exchange swizzle: 16-byte column ^= gvec[b] for every set label bit b >= 3
     uint8_t pad[2];
+    uint16_t own[2][4];        // label bits whose sign slot k carries (DiagOp flag bit 2), per half
     uint32_t off1[2][4];       // slot k's table index takes register index bit k: byte offset from the entry for that
                                // bit = 0 to the one for bit = 1 (0: the slot does not depend on a register bit)
 };
@@ -134,11 +137,13 @@ __device__ __forceinline__ void dg_wht_inverse(double2 (&p)[16], double2 *xb, in
 // per-ancilla tables of one half cycle: up to two of the (slot, index) entries per lane.
 // zmask: label bits whose value flips the sign of the amplitude (data Z events; data flips of the preceding
 // Hadamard-frame half), applied by the slot that owns the bit; g: global phase i^g, applied by the last slot
+// slots: bit k set = build the entries of slot k (the others keep using the event-free tables)
 __device__ __forceinline__ void dg_build_tables(const DiagHalf &H, const uint32_t *evw, double2 *tab, int lane,
-                                                uint32_t zmask, uint32_t g) {
+                                                uint32_t zmask, uint32_t g, uint32_t slots = 15u) {
 #pragma unroll 1
     for (int e = lane; e < (int)H.n_entries; e += 32) {
         const int k = (e >= H.tbase[1]) + (e >= H.tbase[2]) + (e >= H.tbase[3]);
+        if (!((slots >> k) & 1u)) continue;
         const int idx = e - H.tbase[k];
         double2 u = make_double2(1.0, 0.0), v = make_double2(0.0, 0.0), ph = make_double2(1.0, 0.0);
         const int n = H.n_ops[k];
@@ -409,6 +414,16 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ MeasArgs m
     unsigned char *meta = wb + 2 * kRunBytes + kDgTabBytes;                          // [2][kDgMetaBytes]
     uint64_t *full = reinterpret_cast<uint64_t *>(meta + 2 * kDgMetaBytes);          // [2]
     uint64_t *mfull = full + 2;                                                      // [2]
+    // per CTA: the tables of a half cycle without events (most slots of most shots), built once
+    unsigned char *clean = smem_raw + kDgSmem;                                       // [2][kDgTabBytes]
+    uint32_t *zero_ev = reinterpret_cast<uint32_t *>(clean + 2 * kDgTabBytes);       // [S17_EV_WORDS]
+    if (warp == 0) {
+        zero_ev[lane] = 0u;
+        __syncwarp();
+        dg_build_tables(P.h[0], zero_ev, reinterpret_cast<double2 *>(clean), lane, 0u, 0u);
+        dg_build_tables(P.h[1], zero_ev, reinterpret_cast<double2 *>(clean + kDgTabBytes), lane, 0u, 0u);
+    }
+    __syncthreads();
 
     const uint32_t n_items = *n_act_ptr;
     const uint32_t n_warps = gridDim.x * kDgWarps, gw = blockIdx.x * kDgWarps + warp;
@@ -422,6 +437,14 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ MeasArgs m
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
+
+    // which operation of which slot this lane checks for events (lanes 0-15: slot = lane / 4, op = lane % 4)
+    uint32_t chk_word[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int ck = (lane >> 2) & 3, cj = lane & 3;
+        chk_word[h] = (lane < 16 && cj < P.h[h].n_ops[ck]) ? (uint32_t)P.h[h].ops[ck][cj].ev_word : 0xFFu;
+    }
 
     // lane parts (shot independent): label offsets of the two maps, linear and through the exchange swizzle, and this
     // lane's first table entry per slot (one byte per slot)
@@ -534,8 +557,20 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ MeasArgs m
                 dg_wht16(p);
             }
             __syncwarp();
-            dg_build_tables(H, evw, reinterpret_cast<double2 *>(tab), lane, ((fw >> 9) ^ carry) & 511u, (fw >> 18) & 3u);
-            __syncwarp();
+            // slots touched by an event of this shot (an event word, a sign they carry, the global phase) get private
+            // tables; the others use the event-free ones
+            const uint32_t zmask = ((fw >> 9) ^ carry) & 511u, g = (fw >> 18) & 3u;
+            const uint32_t cw = h ? chk_word[1] : chk_word[0];
+            const uint32_t evb = __ballot_sync(0xffffffffu, cw != 0xFFu && evw[cw] != 0u);
+            uint32_t dirty = g ? 8u : 0u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (((evb >> (4 * k)) & 15u) || (zmask & P.own[h][k])) dirty |= 1u << k;
+            if (dirty) {
+                dg_build_tables(H, evw, reinterpret_cast<double2 *>(tab), lane, zmask, g, dirty);
+                __syncwarp();
+            }
+            const unsigned char *clean_h = clean + h * kDgTabBytes;
             const uint32_t tl = h ? tlp[1] : tlp[0];
             uint32_t a_out = 0;
             bool bad = false;
@@ -544,7 +579,7 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ MeasArgs m
 #define S17_DG_SLOT1(K)                                                                                              \
             {                                                                                                        \
                 const double u = __shfl_sync(0xffffffffu, uu, 4 * h + K);                                            \
-                const unsigned char *tk0 = tab + (((tl >> (8 * K)) & 0xFFu) << 4);                                   \
+                const unsigned char *tk0 = (((dirty >> K) & 1u) ? tab : clean_h) + (((tl >> (8 * K)) & 0xFFu) << 4);   \
                 dg_slot1<K>(p, tk0, tk0 + P.off1[h][K], H.aj[K], is_forced, fo, u, a_out, bad, pfin);                \
             }
             S17_DG_SLOT1(0) S17_DG_SLOT1(1) S17_DG_SLOT1(2) S17_DG_SLOT1(3)
