@@ -417,6 +417,8 @@ struct MeasArgs {
     int forced;
     uint32_t mask;    // ancillas measured by this call (bit j = ancilla j)
     int final_part;   // 1: completes the cycle's All(Measure) | ancilla
+    int sample_data;  // k_cycle1: also draw the basis state a data read-out of the stored block would find (k_readout_s)
+    uint32_t data_stream;
     uint32_t stream;
     uint64_t seed, first_shot;
     int n_shots;
@@ -734,6 +736,44 @@ k_readout(ReadArgs ra, const double2 *__restrict__ state, size_t stride, const S
     rec[shot] = r;
 }
 
+// logical_measurement (CS:52-93) when k_cycle1 already drew the data register's basis state d' from the stored block:
+// reading the corrected state gives d' ^ x-correction (a Pauli X relabels the computational basis).  One thread per
+// shot, no state traffic.
+__global__ void __launch_bounds__(256)
+k_readout_s(ReadArgs ra, const uint32_t *__restrict__ dsamp, const uint8_t *__restrict__ cw16, const uint32_t *__restrict__ leak,
+            const uint8_t *__restrict__ ready, s17_record *__restrict__ rec, unsigned long long *__restrict__ counters)
+{
+    const int shot = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = shot < ra.n_shots && ready[shot];
+    bool fail = false;
+    if (live) {
+        s17_record r = rec[shot];
+        const uint32_t chosen = (dsamp[shot] ^ r.correction) & 0x1FFu;
+        for (int j = 0; j < 9; ++j)
+            if (r.n_outcomes < S17_MAX_OUTCOMES) r.outcomes[r.n_outcomes++] = (uint8_t)((chosen >> j) & 1u);
+        const uint32_t dm = chosen | (leak[shot] & 0x1FFu);                 // leaked data reads 1 (CS:61-63)
+#define S17_B(i) ((dm >> (i)) & 1u)
+        const uint32_t q = r.quiescent;
+        const uint32_t c0 = (S17_B(0) ^ S17_B(1)) ^ ((q >> 0) & 1u);        // CS:71-77
+        const uint32_t c1 = (S17_B(1) ^ S17_B(2) ^ S17_B(4) ^ S17_B(5)) ^ ((q >> 2) & 1u);
+        const uint32_t c2 = (S17_B(3) ^ S17_B(4) ^ S17_B(6) ^ S17_B(7)) ^ ((q >> 5) & 1u);
+        const uint32_t c3 = (S17_B(7) ^ S17_B(8)) ^ ((q >> 7) & 1u);
+#undef S17_B
+        const uint32_t weight = cw16[c0 | (c1 << 1) | (c2 << 2) | (c3 << 3)];
+        const uint32_t logic = (__popc(dm) + weight) & 1u;                   // CS:86
+        r.data_meas = (uint16_t)dm;
+        r.logical_meas = (uint8_t)logic;
+        fail = logic != (uint32_t)ra.logical_state;
+        if (fail) r.flags |= S17_F_FAIL;
+        rec[shot] = r;
+    }
+    const uint32_t nl = __popc(__ballot_sync(0xffffffffu, live)), nf = __popc(__ballot_sync(0xffffffffu, fail));
+    if ((threadIdx.x & 31) == 0) {
+        if (nl) atomicAdd(&counters[C_COUNTED], (unsigned long long)nl);
+        if (nf) atomicAdd(&counters[C_FAILED], (unsigned long long)nf);
+    }
+}
+
 __global__ void k_reset(int n_shots, uint32_t *leak, uint8_t *active, uint8_t *ready, s17_record *rec, uint32_t *masks,
                         int clear_masks, int keep_leak)
 {
@@ -843,6 +883,8 @@ struct s17_ctx {
     bool no_diag = false;
     bool last_collapsed = true;       // the previous cycle left every active shot collapsed to ancilla block 0
     uint32_t *frm = nullptr;          // per shot: frame words of the two half cycles (k_plan -> k_cycle)
+    uint32_t *dsamp = nullptr;        // per shot: data basis state drawn by k_cycle1 for the read-out
+    bool use_dsamp = false;
     bool no_fuse = false;
     bool debug_sync = false;
     std::string debug_note;
@@ -963,6 +1005,7 @@ extern "C" int s17_create(s17_ctx **out, int device, uint64_t max_shots) {
     CK(cudaMalloc(&ctx->n_act, 4));
     CK(cudaMalloc(&ctx->meas_out, B * 2 * 4));
     CK(cudaMalloc(&ctx->frm, B * 4 * 4));
+    CK(cudaMalloc(&ctx->dsamp, B * 4));
     CK(cudaMemset(ctx->frm, 0, B * 4 * 4));
     CK(cudaFuncSetAttribute(k_cycle, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDgSmem));
     CK(cudaFuncSetAttribute(k_cycle1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDgSmem1));
@@ -1015,7 +1058,7 @@ extern "C" int s17_destroy(s17_ctx *ctx) {
     void *ptrs[] = {ctx->state, ctx->ev, ctx->masks, ctx->leak, ctx->active, ctx->ready, ctx->forced, ctx->hist,
                     ctx->aux, ctx->rec, ctx->counters, ctx->lut, ctx->cw16, ctx->probs, ctx->cum, ctx->plan,
                     ctx->rtf_slots, ctx->rtf_rounds, ctx->rtf_syndb, ctx->act_list, ctx->n_act, ctx->zero_page, ctx->meas_out,
-                    ctx->frm};
+                    ctx->frm, ctx->dsamp};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
@@ -1699,6 +1742,7 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
         k_compact<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(ctx->active, n, ctx->act_list, ctx->n_act);
     }
     MeasArgs ma;
+    memset(&ma, 0, sizeof(ma));
     ma.stage = stage;
     ma.protocol = (int)a.protocol;
     ma.forced = (int)a.forced;
@@ -1714,12 +1758,14 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
         ma.mask = 0xFFu;
         ma.final_part = 1;
         ma.stream = 16u + (uint32_t)stage * 4u;
+        ma.sample_data = (ctx->use_dsamp && stage > 0) ? 1 : 0;
+        ma.data_stream = 32u;
         {
             SCOPE(CAT_GATE);
             if (ctx->diag1_ok[which] && !ctx->no_diag1)
                 k_cycle1<<<ctx->num_sms, kDgThreads, kDgSmem1, ctx->stream>>>(
                     ctx->diag_prog1[which], ma, ctx->state, ctx->stride, ctx->ev, ctx->frm, ctx->act_list, ctx->n_act, ctx->aux,
-                    ctx->forced, ctx->meas_out, ctx->counters, init_basis);
+                    ctx->forced, ctx->meas_out, ctx->dsamp, ctx->counters, init_basis);
             else
                 k_cycle<<<ctx->num_sms, kDgThreads, kDgSmem, ctx->stream>>>(
                     ctx->diag_prog[which], ma, ctx->state, ctx->stride, ctx->ev, ctx->frm, ctx->act_list, ctx->n_act, ctx->aux,
@@ -1807,6 +1853,9 @@ static int run_round(s17_ctx *ctx, const s17_run_args &a) {
     // cover the part of the state that can be non-zero.
     const bool dense = ctx->dense || ctx->use_v1;
     const bool explicit_collapse = dense || a.materialize || a.stop_stage != S17_STOP_NONE;
+    // both noisy cycles go through k_cycle1 and outcomes are sampled: the cycle kernel also draws the data read-out
+    ctx->use_dsamp = ctx->diag1_ok[1] && ctx->diag1_ok[2] && !ctx->no_diag1 && !ctx->no_diag && !explicit_collapse &&
+                     !ctx->use_v1 && !ctx->force_ring && !ctx->no_fuse && !a.forced;
     if (int rc = run_cycle(ctx, a, 0, 0, basis_index, 0, dense, explicit_collapse)) return rc;
     if (explicit_collapse) collapse(ctx, n, ctx->active);
     if (a.stop_stage == S17_STOP_AFTER_PREP) return S17_OK;
@@ -1837,7 +1886,11 @@ static int run_round(s17_ctx *ctx, const s17_run_args &a) {
     ra.seed = a.seed;
     ra.first_shot = a.first_shot_id;
     ra.n_shots = n;
-    {
+    if (ctx->use_dsamp) {
+        SCOPE(CAT_MEAS);
+        k_readout_s<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(ra, ctx->dsamp, ctx->cw16, ctx->leak, ctx->ready, ctx->rec,
+                                                                 ctx->counters);
+    } else {
         SCOPE(CAT_MEAS);
         k_readout<<<blocks_for((uint64_t)n * 32, 128), 128, 0, ctx->stream>>>(ra, ctx->state, ctx->stride, ctx->aux, ctx->forced, ctx->cw16,
                                                                           ctx->leak, ctx->ready, ctx->rec, ctx->counters);

@@ -404,7 +404,8 @@ __global__ void __launch_bounds__(kDgThreads, 1)
 k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ MeasArgs ma, double2 *__restrict__ state,
          size_t stride, const uint32_t *__restrict__ ev, const uint32_t *__restrict__ frm, const uint32_t *__restrict__ act_list,
          const uint32_t *__restrict__ n_act_ptr, ShotAux *__restrict__ aux, const uint8_t *__restrict__ forced,
-         uint32_t *__restrict__ meas_out, unsigned long long *__restrict__ counters, int init_basis)
+         uint32_t *__restrict__ meas_out, uint32_t *__restrict__ dsamp, unsigned long long *__restrict__ counters,
+         int init_basis)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -525,6 +526,9 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ MeasArgs m
             Philox rng(ma.seed, ma.first_shot + shot, ma.stream + ((lane >> 2) ? 0u : 1u));
             rng.c3 = (uint32_t)(lane & 3);
             uu = rng.next();
+        } else if (lane == 8 && ma.sample_data) {
+            Philox rng(ma.seed, ma.first_shot + shot, ma.data_stream);       // the read-out's uniform (k_readout's stream)
+            uu = rng.next();
         }
 
         double2 p[16];
@@ -601,6 +605,35 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ MeasArgs m
                 perm = fw & 511u;
             }
             if (lane == 0) meas_out[2 * shot + H.final_part] = a_out | (bad ? 0x100u : 0u);
+        }
+
+        // All(Measure) | data of a read-out that may follow (CS:56): one basis state drawn from |psi|^2 -- one uniform
+        // against the cumulative weights in (lane, register) order.  The decoder's X correction relabels it later.
+        if (ma.sample_data) {
+            double wsum[16], mine = 0.0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { wsum[i] = fma(p[i].x, p[i].x, p[i].y * p[i].y); mine += wsum[i]; }
+            double incl = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const double o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            const double target = __shfl_sync(0xffffffffu, uu, 8) * __shfl_sync(0xffffffffu, incl, 31);
+            const uint32_t hit = __ballot_sync(0xffffffffu, target < incl);
+            const int sel = hit ? (__ffs(hit) - 1) : 31;
+            if (lane == sel) {
+                double cum = incl - mine;
+                int pick = -1, last_pos = 0;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    cum += wsum[i];
+                    if (wsum[i] > 0.0) last_pos = i;
+                    if (pick < 0 && target < cum && wsum[i] > 0.0) pick = i;
+                }
+                if (pick < 0) pick = last_pos;        // rounding guard: never select an empty state
+                dsamp[shot] = (((linA ^ P.mapA.lin16[pick]) >> 4) ^ perm) & 511u;
+            }
         }
 
         // renormalise once, stage the block in label order (data flips of the computational-frame half relabel it) and
