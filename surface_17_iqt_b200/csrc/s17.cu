@@ -308,19 +308,40 @@ __device__ __forceinline__ uint32_t pconj_rxx(uint32_t P, int s) {        // Rxx
     return pconj(P, 0x01u, 0x07u | k, 0x04u, 0x0Du | k);
 }
 
-__global__ void k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, NoiseDev nd, const double *__restrict__ probs,
-                       uint32_t *__restrict__ ev, uint32_t *__restrict__ masks, uint32_t *__restrict__ leak,
-                       const uint8_t *__restrict__ active, uint32_t *__restrict__ frm, uint32_t *__restrict__ n_act)
+// One thread per shot; a warp stages its 32 shots' slot bitsets and event words through shared memory (row stride 33
+// words) so that the global traffic is coalesced rows instead of 32 strided 4-byte accesses per instruction.
+constexpr int kPlanThreads = 128;
+constexpr int kPlanRow = 33;
+__global__ void __launch_bounds__(kPlanThreads)
+k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, NoiseDev nd, const double *__restrict__ probs,
+       uint32_t *__restrict__ ev, uint32_t *__restrict__ masks, uint32_t *__restrict__ leak,
+       const uint8_t *__restrict__ active, uint32_t *__restrict__ frm, uint32_t *__restrict__ n_act)
 {
-    const int shot = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ uint32_t s_mask[kPlanThreads / 32][32][kPlanRow], s_ev[kPlanThreads / 32][32][kPlanRow];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int shot = blockIdx.x * blockDim.x + threadIdx.x, shot0 = shot - lane;
     if (shot == 0) *n_act = 0;                         // k_compact, next in the stream, appends to an empty list
-    if (shot >= pa.n_shots || !active[shot]) return;
+    const bool act = shot < pa.n_shots && active[shot];
+    const uint32_t actmask = __ballot_sync(0xffffffffu, act);
+    if (!actmask) return;
+    const bool prob_mode = pa.noise == S17_NOISE_PROB;
+    for (int r = 0; r < 32; ++r)
+        if ((actmask >> r) & 1u)
+            s_mask[wib][r][lane] = prob_mode ? 0u : masks[(size_t)(shot0 + r) * (2 * S17_MASK_WORDS) + lane];
+    __syncwarp();
+    uint32_t *evs = s_ev[wib][lane];
+    uint32_t *mk = s_mask[wib][lane];                  // placed slots (subset / replay) or the slots fired now (prob mode)
+    uint32_t *mrec = mk;
+    uint32_t lk = 0;
     Philox rng(pa.seed, pa.first_shot + shot, pa.stream);
     uint32_t f_flip = 0, f_sign = 0, f_phase = 0;      // frame bookkeeping of the current half cycle (k_cycle)
-    uint32_t lk = leak[shot];
-    uint32_t *evs = ev + (size_t)shot * S17_EV_WORDS;
-    uint32_t *mk = masks + (size_t)shot * (2 * S17_MASK_WORDS);
-    uint32_t *mrec = mk + (pa.rec_half ? S17_MASK_WORDS : 0);
+    if (act) lk = leak[shot];
+    if (act && pa.noiseless && lk == 0) {
+        // noiseless preparation cycle without a leaked qubit: no event, no leak skip, identity frame
+        for (int i = 0; i < (int)S17_EV_WORDS; ++i) evs[i] = 0;
+        frm[(size_t)shot * 4] = 0;
+        frm[(size_t)shot * 4 + 1] = 0;
+    } else if (act) {
     for (int i = 24; i < (int)S17_EV_WORDS; ++i) evs[i] = 0;
     uint32_t w = 0, skip = 0;
     for (int i = 0; i < pa.n_instr; ++i) {
@@ -406,6 +427,14 @@ __global__ void k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, NoiseDe
         w = (w & ~(63u << in.field)) | (f << in.field);
     }
     leak[shot] = lk;
+    }
+    __syncwarp();
+    for (int r = 0; r < 32; ++r) {
+        if (!((actmask >> r) & 1u)) continue;
+        ev[(size_t)(shot0 + r) * S17_EV_WORDS + lane] = s_ev[wib][r][lane];
+        if (prob_mode)
+            masks[(size_t)(shot0 + r) * (2 * S17_MASK_WORDS) + (pa.rec_half ? S17_MASK_WORDS : 0) + lane] = s_mask[wib][r][lane];
+    }
 }
 
 // =================================================================================================
@@ -1729,7 +1758,7 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
     pa.n_shots = n;
     {
         SCOPE(CAT_OTHER);
-        k_plan<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(ctx->plan, pa, ctx->nd, ctx->probs, ctx->ev, ctx->masks,
+        k_plan<<<blocks_for(n, kPlanThreads), kPlanThreads, 0, ctx->stream>>>(ctx->plan, pa, ctx->nd, ctx->probs, ctx->ev, ctx->masks,
                                                             ctx->leak, ctx->active, ctx->frm, ctx->n_act);
     }
     const int which = stage == 0 ? 0 : (second ? 2 : 1);
@@ -1758,7 +1787,10 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
         ma.mask = 0xFFu;
         ma.final_part = 1;
         ma.stream = 16u + (uint32_t)stage * 4u;
-        ma.sample_data = (ctx->use_dsamp && stage > 0) ? 1 : 0;
+        // only cycles after which some shot is decoded: s2 decodes after its second cycle only (CL:424), s1 and the
+        // single-round protocol after the first; run-til-fail after either
+        const bool decodes = stage == 2 ? true : (stage == 1 && a.protocol != S17_PROTO_S2);
+        ma.sample_data = (ctx->use_dsamp && decodes) ? 1 : 0;
         ma.data_stream = 32u;
         {
             SCOPE(CAT_GATE);
