@@ -14,9 +14,12 @@ only exchange is one all-reduce of the counters at the end (inside the timed reg
 `e2e`    : the same through the reference-shaped Python entry point
            surface_17_iqt_b200.calc_log_e_rate_arbitrary_error_model.s2_calculate_log_e_rate_error_subset
            with host inputs and host results, wall-clock around the calls.
-`roofline`: the gate sweep kernel (k_layer3 in the default support-aware schedule): algorithmic bytes = the 8 KiB amplitude runs it really reads and
-           writes (a dense sweep is 2 MiB read + 2 MiB write per shot; regions of the state that are exactly zero
-           after an ancilla reset are skipped unless S17_DENSE=1) / summed CUDA-event kernel time.
+`roofline`: the dominant kernel, k_cycle1 (one whole stabiliser cycle per shot and launch, the state in registers):
+           algorithmic bytes = the 8 KiB block it reads + the 8 KiB block it writes per shot and cycle, divided by
+           the summed CUDA-event time of its launches.  The kernel is bound by the FP64 pipe and shared memory, not by
+           HBM; `roofline_dense` is the same gate stream as full-state sweeps (2 MiB read + 2 MiB written per shot
+           and sweep, S17_DENSE=1), the HBM-bound configuration BASELINE.json's "% of HBM roofline per gate layer"
+           refers to.
 `cpu_baseline` / --impl reference: the oracle port (one CPU sweep per gate, ProjectQ's execution model,
            python per-gate driver like the reference) on all host cores, bounded sample of the same workload.
 """
@@ -117,7 +120,9 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * wall / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
-        "config": workload_config(per_core * cores, 1, None),
+        "config": {"workload": workload_config(per_core * cores, 1, None)["workload"],
+                   "shots_per_step": per_core * cores,
+                   "sample": "bounded sample of the same workload: {} shots per step through the CPU oracle port".format(per_core * cores)},
         "cpu_baseline": {"value": value, "unit": "shots/s", "cores": cores, "kind": "port",
                          "sample": "{} s2 shots per step on {} processes (oracle port: C sweep per gate, python driver)"
                          .format(per_core * cores, cores)},
@@ -129,10 +134,14 @@ def run_reference(args):
 def workload_config(shots, n_gpus, fusion):
     return {"workload": "Surface-17 {} s2 importance sampling, subset {} over {} two-round slots, uniform placement"
             .format(MODEL, ESET, LOCS2), "shots_per_step_per_gpu": shots, "fusion": fusion,
-            "state": "2^17 complex128 per shot resident in HBM", "parallelism": "shots sharded x{}".format(n_gpus),
-            "schedule": "support-aware sweeps (exactly-zero regions after an ancilla reset are skipped), X-type "
-                        "ancillas measured after timestep 4, lazy collapse; S17_DENSE=1 restores full-state sweeps",
-            "l2": "per-step working set (shots x >=128 KiB touched, 2 MiB allocated) exceeds the 126 MB L2, no flush needed"}
+            "state": "complex128; between cycles the 2^9 amplitudes that can be non-zero after the ancilla resets "
+                     "(8 KiB per shot) are resident in HBM; S17_DENSE=1 keeps and sweeps all 2^17 (roofline_dense)",
+            "parallelism": "shots sharded x{}".format(n_gpus),
+            "schedule": "one kernel per stabiliser cycle (k_cycle1): the cycle in the frame where its gates are "
+                        "diagonal, X-type ancillas measured after timestep 4, one warp per shot; S17_DIAG=0 / "
+                        "S17_DENSE=1 select the general amplitude kernels",
+            "l2": "per-step working set (shots x 8 KiB read + 8 KiB written per cycle = {:.1f} GB) exceeds the 126 MB L2, "
+                  "no flush needed".format(shots * 16384 / 1e9)}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -310,15 +319,16 @@ def run_gpu(args):
                     "h2d_bytes_per_step": 2048 * 8 + 3 * 4 * len(ESET) + 64, "d2h_bytes_per_step": 64 + 8 * 8,
                     "api": "s2_calculate_log_e_rate_error_subset(num_runs, ...) -> (rate, not0_rate, failed, not0)"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_half", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_cycle1", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                          # dram__bytes_read+write of one ncu --set full capture of this kernel, scaled to this run's
-                         # average launch: 3.173 GB measured for 3.221 GB algorithmic (profiles/r1h_k_layer3_ncu_full.csv)
-                         # (k_half: 217.8 MB measured for 268.4 MB algorithmic, profiles/r1i_k_half_ncu_full.csv)
-                         "traffic": (sweep_bytes / max(1, gate_launches)) * (217.8 / 268.4),
-                         "note": "the default schedule keeps a shot's half cycle in shared memory (8 KiB in / 8 KiB out), so "
-                                 "this kernel is bound by the FP64 pipe and shared memory (ncu: 24-49 % / 35-46 %), not by "
-                                 "HBM; the HBM-bound full-state configuration is reported in roofline_dense",
+                         # average launch: 2.114 GB measured for 2.147 GB algorithmic at 131072 shots
+                         # (profiles/r1n_k_cycle1_ncu_full.csv)
+                         "traffic": (sweep_bytes / max(1, gate_launches)) * (2.1137 / 2.1475),
+                         "note": "one launch = one stabiliser cycle of every active shot: 8 KiB read + 8 KiB written per "
+                                 "shot, everything else in registers / shared memory; ncu: FP64 pipe 47 %, shared-memory "
+                                 "wavefronts 51 %, issue slots 54 % -- not HBM-bound; the HBM-bound full-state "
+                                 "configuration is roofline_dense",
                          "launches": int(gate_launches), "sweeps": int(sweeps),
                          "sweeps_per_shot": sweeps / (B * args.steps),
                          "bytes_per_shot": sweep_bytes / (B * args.steps), "dense_bytes_per_sweep": SWEEP_BYTES,
@@ -337,10 +347,10 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--shots", type=int, default=int(os.environ.get("S17_BENCH_SHOTS", "32768")), help="shots per GPU per step")
+    ap.add_argument("--shots", type=int, default=int(os.environ.get("S17_BENCH_SHOTS", "524288")), help="shots per GPU per step")
     ap.add_argument("--fusion", type=int, default=2)
     ap.add_argument("--seed", type=int, default=2026)
     ap.add_argument("--no-cpu", action="store_true")
