@@ -260,9 +260,24 @@ def compile_program(model, list_len, fusion=1, cooling=False, over_angles=None, 
                 for err, pname, *_ in model["gates"]["Idle"]:
                     if err != "Z":
                         raise NotImplementedError("only Z idle errors are supported")
-                    # stab_ind is not forwarded by the reference (CS:767), hence use_round=0
+                    # stab_ind is not forwarded by the reference (CS:767), hence use_round=0.
+                    # Frame information for the whole-cycle kernel (s17_diag.cuh), b: bit7 present, bit1 the gap belongs
+                    # to the x-type (Hadamard-frame) half, bit0 data qubit inside its Ry bracket; field / pad: for an
+                    # ancilla, index within its half / event word of the last operation on it so far (255: the ancilla
+                    # is still |0>, or already measured: Z acts trivially)
+                    half_ops = [o for o in ops if (o.timestep < 4) == (t < 4)]
+                    b = 0x80 | (0x02 if t < 4 else 0)
+                    fld, pad = 255, 0
+                    if q < N_DATA:
+                        mine = [o.timestep for o in half_ops if o.data == q]
+                        if t >= 4 and mine and min(mine) <= t < max(mine):
+                            b |= 0x01
+                    else:
+                        done = [o for o in half_ops if o.ancilla == q - N_DATA and o.timestep <= t]
+                        if done:
+                            fld, pad = half_ops.index(done[-1]), done[-1].index
                     emit(kind=L.P_IDLE, err=L.ERR_Z, list=names.index(pname), slot=t * 17 + q, a=q, word=24 + t,
-                         use_round=0)
+                         use_round=0, b=b, field=fld, pad=pad)
 
     # ---- gate stream ------------------------------------------------------------------------
     def param_index(c, s):

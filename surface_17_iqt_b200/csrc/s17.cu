@@ -334,7 +334,8 @@ k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, NoiseDev nd, const doub
     uint32_t *mrec = mk;
     uint32_t lk = 0;
     Philox rng(pa.seed, pa.first_shot + shot, pa.stream);
-    uint32_t f_flip = 0, f_sign = 0, f_phase = 0;      // frame bookkeeping of the current half cycle (k_cycle)
+    uint32_t f_flip = 0, f_sign = 0, f_phase = 0, f_ancz = 0;   // frame bookkeeping of the current half cycle (k_cycle)
+    int f_half = -1;
     if (act) lk = leak[shot];
     if (act && pa.noiseless && lk == 0) {
         // noiseless preparation cycle without a leaked qubit: no event, no leak skip, identity frame
@@ -371,7 +372,12 @@ k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, NoiseDev nd, const doub
             // the basis (flip mask; bit 31 tells the operation whether its own label bit is flipped), a data Z is a
             // label-dependent sign (sign mask) and the rest is a global phase.
             const uint32_t d = in.slot;
-            if (in.a & 16) { f_flip = 0; f_sign = 0; f_phase = 0; }
+            if (in.a & 16) {                           // first operation of a half: close the previous one (idle events may
+                if (f_half >= 0)                       // follow its last operation), start from the identity frame
+                    frm[(size_t)shot * 4 + f_half] = f_flip | (f_sign << 9) | ((f_phase & 3u) << 18) | (f_ancz << 20);
+                f_flip = 0; f_sign = 0; f_phase = 0; f_ancz = 0;
+                f_half = (int)((in.a >> 5) & 1u);
+            }
             w |= ((f_flip >> d) & 1u) << 31;
             if (N) {
                 uint32_t F = N;
@@ -385,7 +391,6 @@ k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, NoiseDev nd, const doub
                 if (F & 1u) f_flip ^= 1u << d;
                 f_phase += (F >> 4) & 3u;
             }
-            if (in.a & 64) frm[(size_t)shot * 4 + ((in.a >> 5) & 1u)] = f_flip | (f_sign << 9) | ((f_phase & 3u) << 18);
             evs[in.word] = w;
             continue;
         }
@@ -402,7 +407,20 @@ k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, NoiseDev nd, const doub
             fire = mask_get(mk, nd.list_off[in.list] + slot);
         }
         if (!fire) continue;
-        if (in.kind == S17_P_IDLE) { evs[in.word] |= 1u << in.a; continue; }
+        if (in.kind == S17_P_IDLE) {
+            evs[in.word] |= 1u << in.a;                // the 17-bit idle masks of the sweep kernels / k_half
+            if (in.b & 0x80u) {                        // the same Z in the frame of its half cycle (whole-cycle kernels)
+                if (in.a < 9u) {
+                    const uint32_t bit = 1u << in.a;
+                    if (in.b & 2u) f_flip ^= bit;                                   // H Z H = X
+                    else if (in.b & 1u) { f_flip ^= bit; f_phase += 2u; }           // Ry(-pi/2) Z Ry(+pi/2) = -X
+                    else { f_sign ^= bit; f_phase += 2u * ((f_flip >> in.a) & 1u); }
+                } else if (in.field != 255u) {
+                    f_ancz ^= 1u << in.field;          // Z on the ancilla after that operation (and its own events)
+                }
+            }
+            continue;
+        }
         uint32_t f = (w >> in.field) & 63u;
         switch (in.err) {
         case S17_ERR_X: f = pauli_mul(f, 0, 1); break;
@@ -426,6 +444,7 @@ k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, NoiseDev nd, const doub
         }
         w = (w & ~(63u << in.field)) | (f << in.field);
     }
+    if (f_half >= 0) frm[(size_t)shot * 4 + f_half] = f_flip | (f_sign << 9) | ((f_phase & 3u) << 18) | (f_ancz << 20);
     leak[shot] = lk;
     }
     __syncwarp();
@@ -1333,10 +1352,15 @@ static bool make_diag_half(const LayerArg2 &P, const HalfTail &T, int half_index
     int first_idx[9], last_idx[9], min_word = 255, max_word = -1;
     for (int d = 0; d < 9; ++d) first_idx[d] = last_idx[d] = -1;
     std::vector<int> order;                                   // operations in time order (= event word order)
+    bool has_idle = false;
     for (int o = 0; o < L.n_ops; ++o) {
+        if (L.ops[o].kind == S17_OP_IDLE) { has_idle = true; continue; }     // rides in the frame words (k_plan)
         if (L.ops[o].kind != S17_OP_ENT || P.oc[o].generic) return false;
         order.push_back(o);
     }
+    if (has_idle)                                             // the plan must carry the frame information of idle events
+        for (uint32_t i = 0; i < n_plan; ++i)
+            if (plan[i].kind == S17_P_IDLE && !(plan[i].b & 0x80u)) return false;
     std::sort(order.begin(), order.end(), [&](int a, int b) { return L.ops[a].ev_word < L.ops[b].ev_word; });
     for (int o : order) {
         const int d = L.ops[o].data_bit;
@@ -1371,6 +1395,12 @@ static bool make_diag_half(const LayerArg2 &P, const HalfTail &T, int half_index
         dop.d = op.data_bit;
         dop.ev_word = op.ev_word;
         dop.flags = (uint8_t)((P.oc[o].s < 0 ? 1 : 0) | ((P.oc[o].shape & 2) ? 2 : 0));
+        dop.pad = (uint8_t)(std::find(order.begin(), order.end(), o) - order.begin());     // index in time order
+        if (dop.pad >= 12) return false;                     // 12 ancilla-Z bits in a frame word
+        for (uint32_t i = 0; i < n_plan; ++i)                 // idle Z events that name this operation: same ancilla
+            if (plan[i].kind == S17_P_IDLE && (plan[i].b & 0x80u) && plan[i].field != 255 && plan[i].pad == op.ev_word &&
+                (plan[i].field != dop.pad || plan[i].a != op.anc_bit))
+                return false;
         H.aj[k] = (uint8_t)(op.anc_bit - 9);
         // k_plan must have been told the same frame, data bit and half boundaries for this operation
         bool found = false;

@@ -44,7 +44,7 @@ static_assert(kDgSmem1 <= 232448, "k_cycle1: shared memory per SM");
 struct DiagOp {
     uint8_t d, ev_word;
     uint8_t flags;             // bit0: Rxx sign is -1, bit1: followed by Rx(-s pi/2), bit2: this slot owns label bit d for signs
-    uint8_t pad;
+    uint8_t pad;               // index of the operation within its half cycle, in time order (bit 20 + pad of the frame word)
 };
 struct DiagHalf {
     uint8_t frame_x;           // 1: Walsh-Hadamard frame (x-type half), 0: computational frame (z-type half)
@@ -138,8 +138,9 @@ __device__ __forceinline__ void dg_wht_inverse(double2 (&p)[16], double2 *xb, in
 // zmask: label bits whose value flips the sign of the amplitude (data Z events; data flips of the preceding
 // Hadamard-frame half), applied by the slot that owns the bit; g: global phase i^g, applied by the last slot
 // slots: bit k set = build the entries of slot k (the others keep using the event-free tables)
+// ancz: bit i set = an idle Z hits the ancilla after operation i of the half cycle (sympathetic_cooling, CS:762-772)
 __device__ __forceinline__ void dg_build_tables(const DiagHalf &H, const uint32_t *evw, double2 *tab, int lane,
-                                                uint32_t zmask, uint32_t g, uint32_t slots = 15u) {
+                                                uint32_t zmask, uint32_t g, uint32_t ancz, uint32_t slots = 15u) {
 #pragma unroll 1
     for (int e = lane; e < (int)H.n_entries; e += 32) {
         const int k = (e >= H.tbase[1]) + (e >= H.tbase[2]) + (e >= H.tbase[3]);
@@ -163,6 +164,7 @@ __device__ __forceinline__ void dg_build_tables(const DiagHalf &H, const uint32_
             if (op.flags & 2u) ph = make_double2(fma(-sg, ph.y, ph.x), fma(sg, ph.x, ph.y));   // (1 + i sg) ph
             if ((w >> 28) & 1u) v = make_double2(-v.x, -v.y);                                  // net event: Z on the ancilla
             if ((w >> 27) & 1u) { const double2 t = u; u = v; v = t; }                         //            X on the ancilla
+            if ((ancz >> op.pad) & 1u) v = make_double2(-v.x, -v.y);                           // idle Z after the operation
         }
         if (k == 3) {
             if (g == 1) ph = make_double2(-ph.y, ph.x);
@@ -321,7 +323,7 @@ k_cycle(const __grid_constant__ DiagProg P, const __grid_constant__ MeasArgs ma,
             const uint32_t fw = fwp[h];
             if (H.frame_x) dg_wht_forward(p, xb, lane);
             __syncwarp();
-            dg_build_tables(H, evw, reinterpret_cast<double2 *>(tab), lane, ((fw >> 9) ^ carry) & 511u, (fw >> 18) & 3u);
+            dg_build_tables(H, evw, reinterpret_cast<double2 *>(tab), lane, ((fw >> 9) ^ carry) & 511u, (fw >> 18) & 3u, fw >> 20);
             __syncwarp();
             const uint32_t tl = h ? tlp[1] : tlp[0];
             uint32_t a_out = 0;
@@ -421,8 +423,8 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ MeasArgs m
     if (warp == 0) {
         zero_ev[lane] = 0u;
         __syncwarp();
-        dg_build_tables(P.h[0], zero_ev, reinterpret_cast<double2 *>(clean), lane, 0u, 0u);
-        dg_build_tables(P.h[1], zero_ev, reinterpret_cast<double2 *>(clean + kDgTabBytes), lane, 0u, 0u);
+        dg_build_tables(P.h[0], zero_ev, reinterpret_cast<double2 *>(clean), lane, 0u, 0u, 0u);
+        dg_build_tables(P.h[1], zero_ev, reinterpret_cast<double2 *>(clean + kDgTabBytes), lane, 0u, 0u, 0u);
     }
     __syncthreads();
 
@@ -440,11 +442,12 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ MeasArgs m
     __syncwarp();
 
     // which operation of which slot this lane checks for events (lanes 0-15: slot = lane / 4, op = lane % 4)
-    uint32_t chk_word[2];
+    uint32_t chk_word[2];                       // event word | index within the half << 8
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const int ck = (lane >> 2) & 3, cj = lane & 3;
-        chk_word[h] = (lane < 16 && cj < P.h[h].n_ops[ck]) ? (uint32_t)P.h[h].ops[ck][cj].ev_word : 0xFFu;
+        chk_word[h] = (lane < 16 && cj < P.h[h].n_ops[ck])
+                          ? ((uint32_t)P.h[h].ops[ck][cj].ev_word | ((uint32_t)P.h[h].ops[ck][cj].pad << 8)) : 0xFFu;
     }
 
     // lane parts (shot independent): label offsets of the two maps, linear and through the exchange swizzle, and this
@@ -565,13 +568,13 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ MeasArgs m
             // tables; the others use the event-free ones
             const uint32_t zmask = ((fw >> 9) ^ carry) & 511u, g = (fw >> 18) & 3u;
             const uint32_t cw = h ? chk_word[1] : chk_word[0];
-            const uint32_t evb = __ballot_sync(0xffffffffu, cw != 0xFFu && evw[cw] != 0u);
+            const uint32_t evb = __ballot_sync(0xffffffffu, cw != 0xFFu && (evw[cw & 0xFFu] != 0u || ((fw >> (20 + (cw >> 8))) & 1u)));
             uint32_t dirty = g ? 8u : 0u;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
                 if (((evb >> (4 * k)) & 15u) || (zmask & P.own[h][k])) dirty |= 1u << k;
             if (dirty) {
-                dg_build_tables(H, evw, reinterpret_cast<double2 *>(tab), lane, zmask, g, dirty);
+                dg_build_tables(H, evw, reinterpret_cast<double2 *>(tab), lane, zmask, g, fw >> 20, dirty);
                 __syncwarp();
             }
             const unsigned char *clean_h = clean + h * kDgTabBytes;

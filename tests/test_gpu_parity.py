@@ -200,7 +200,8 @@ def test_sampled_trajectories_replay_bit_exact_in_oracle(error_models, correctio
 
 @pytest.mark.parametrize("diag", ["1", "g"])
 @pytest.mark.parametrize("model,eset", [("PDD_model", [2, 2, 3, 6, 2]), ("Dress_model", [1, 1, 2, 8, 1]),
-                                        ("PDD_model", [0, 0, 0, 0, 0])])
+                                        ("PDD_model", [0, 0, 0, 0, 0]), ("PDD_cooling", [1, 1, 2, 4, 1, 12]),
+                                        ("Dress_cooling", [1, 1, 1, 6, 1, 20])])
 def test_cycle_kernel_matches_half_kernel(error_models, correction_table, bitflip_table, model, eset, diag, monkeypatch):
     """The diagonal-frame cycle kernels (k_cycle1 / k_cycle) against the general amplitude kernel (k_half): the
     trajectories one samples, replayed through the other, give the same records and the same stored amplitudes
@@ -208,15 +209,16 @@ def test_cycle_kernel_matches_half_kernel(error_models, correction_table, bitfli
     per_round = circuit.list_lengths(error_models[model])
     locs = [2 * x for x in per_round]
     n = 96
+    cooling = model.endswith("cooling")
     monkeypatch.setenv("S17_DIAG", diag)
-    sim = make_sim(error_models, correction_table, bitflip_table, model, locs, n, 2)
+    sim = make_sim(error_models, correction_table, bitflip_table, model, locs, n, 2, cooling)
     sim.backend.set_subset(eset, locs)
     c1 = sim.backend.run("s2", n, L.NOISE_SUBSET, seed=321, first_shot_id=5)
     recs1, masks = sim.backend.records(n), sim.backend.masks(n)
     states1 = [sim.backend.state(i)[:512].copy() for i in range(n)]
     sim.close()
     monkeypatch.setenv("S17_DIAG", "0")
-    sim = make_sim(error_models, correction_table, bitflip_table, model, locs, n, 2)
+    sim = make_sim(error_models, correction_table, bitflip_table, model, locs, n, 2, cooling)
     sim.backend.set_replay([list(masks[i, 0]) for i in range(n)], [r["outcomes"] for r in recs1])
     c2 = sim.backend.run("s2", n, L.NOISE_REPLAY, forced=True)
     recs2 = sim.backend.records(n)
