@@ -119,11 +119,16 @@ def rx(s):
     return np.array([[1, -1j * s], [-1j * s, 1]], dtype=complex) * SQ
 
 
-def brute_half(psi512, ops, words):
-    """ops: list of dict(d, slot, s, shape) in time order; words[i]: event word of op i.  Returns the 2^13 state."""
+def brute_half(psi512, ops, words, idle=None):
+    """ops: list of dict(d, slot, s, shape[, ts]) in time order; words[i]: event word of op i; idle: {ts: [qubits]} = Z
+    on data qubit q < 9 / ancilla slot q - 9 in the gap after timestep ts.  Returns the 2^13 state."""
     psi = np.zeros(1 << 13, dtype=complex)
     psi[:512] = psi512
-    for op, w in zip(ops, words):
+    idle = idle or {}
+    for n, (op, w) in enumerate(zip(ops, words)):
+        if n and ops[n - 1].get("ts") != op.get("ts"):
+            for q in idle.get(ops[n - 1].get("ts"), []):
+                apply_1q(psi, q, Z)
         bd, ba, s, shape = op["d"], 9 + op["slot"], op["s"], op["shape"]
         skip = (w >> 24) & 1
         if shape & 1:
@@ -138,6 +143,8 @@ def brute_half(psi512, ops, words):
         if shape & 4:
             apply_1q(psi, bd, ry(-1))
             apply_field(psi, (w >> 18) & 63, bd, ba)
+    for q in idle.get(ops[-1].get("ts"), []):
+        apply_1q(psi, q, Z)
     return psi
 
 
@@ -155,11 +162,35 @@ def wht(v):
     return v
 
 
-def plan_frame(ops, words, frame_x):
-    """k_plan's frame bookkeeping for one half: per-op flip bit, final flip mask, sign mask, global phase."""
+def plan_frame(ops, words, frame_x, idle=None):
+    """k_plan's frame bookkeeping for one half: per-op flip bit, final flip mask, sign mask, global phase, and the
+    operations after which an idle Z hits their ancilla."""
     Fm = ZACC = g = 0
     sflip, nets = [], []
-    for op, w in zip(ops, words):
+    ancz = set()
+    idle = idle or {}
+
+    def idle_gap(ts, upto):
+        nonlocal Fm, ZACC, g
+        for q in idle.get(ts, []):
+            if q < 9:
+                mine = [o["ts"] for o in ops if o["d"] == q]
+                if frame_x:
+                    Fm ^= 1 << q                               # H Z H = X
+                elif mine and min(mine) <= ts < max(mine):
+                    Fm ^= 1 << q                               # Ry(-pi/2) Z Ry(+pi/2) = -X
+                    g += 2
+                else:
+                    ZACC ^= 1 << q
+                    g += 2 * ((Fm >> q) & 1)
+            else:
+                done = [i for i in range(upto) if ops[i]["slot"] == q - 9]
+                if done:
+                    ancz.symmetric_difference_update({done[-1]})
+
+    for n, (op, w) in enumerate(zip(ops, words)):
+        if n and ops[n - 1].get("ts") != op.get("ts"):
+            idle_gap(ops[n - 1].get("ts"), n)
         d = op["d"]
         skip = (w >> 24) & 1
         N = net_pauli(w, op["shape"], op["s"], skip) if (w & 0xFFFFFF) else 0
@@ -173,13 +204,14 @@ def plan_frame(ops, words, frame_x):
         if xf:
             Fm ^= 1 << d
         g += kf
-    return sflip, nets, Fm, ZACC, g & 3
+    idle_gap(ops[-1].get("ts"), len(ops))
+    return sflip, nets, Fm, ZACC, g & 3, ancz
 
 
-def diag_half(psi512, ops, words, frame_x):
+def diag_half(psi512, ops, words, frame_x, idle=None):
     """Returns out[a] (512 amplitudes, unnormalised) for every joint outcome a of the 4 ancilla slots, and the factor
     that relates it to the brute-force projection."""
-    sflip, nets, Fm, ZACC, g = plan_frame(ops, words, frame_x)
+    sflip, nets, Fm, ZACC, g, ancz = plan_frame(ops, words, frame_x, idle)
     S = wht(psi512) if frame_x else psi512.copy()
     p = np.arange(512)
     amp = {a: S.copy() for a in range(16)}
@@ -203,6 +235,8 @@ def diag_half(psi512, ops, words, frame_x):
                     v = -v
                 if N & 4:
                     u, v = v, u
+                if i in ancz:
+                    v = -v
             T[idx] = (ph * u, ph * v)
         for i in mine:
             n_factors += (0 if (words[i] >> 24) & 1 else 1) + (1 if ops[i]["shape"] & 2 else 0)

@@ -20,7 +20,7 @@ def halves():
             if o.ancilla not in anc:
                 anc.append(o.ancilla)
         assert len(anc) == 4
-        out.append(([dict(d=o.data, slot=anc.index(o.ancilla), s=o.s,
+        out.append(([dict(d=o.data, slot=anc.index(o.ancilla), s=o.s, ts=o.timestep,
                           shape=int(o.has_ry1) | (int(o.has_rx) << 1) | (int(o.has_ry2) << 2)) for o in sel], frame_x))
     return out
 
@@ -48,5 +48,24 @@ def test_diag_half_equals_brute_force(density, skips):
             words = random_words(rng, ops, density, skips)
             brute = dm.brute_half(psi, ops, words)
             out, factor = dm.diag_half(psi, ops, words, frame_x)
+            for a in range(16):
+                np.testing.assert_allclose(out[a] * factor, brute[512 * a:512 * (a + 1)], atol=1e-12, rtol=0)
+
+
+@pytest.mark.parametrize("density", [0.0, 0.3])
+def test_diag_half_with_idle_z_events(density):
+    """sympathetic_cooling: Z on any data qubit / ancilla in the gaps after the timesteps (incl. the one before the
+    measurement of the x-type half)."""
+    rng = np.random.default_rng(7 + int(10 * density))
+    for ops, frame_x in halves():
+        steps = sorted({op["ts"] for op in ops})
+        gaps = steps if frame_x else steps[:-1]            # no idle slots after timestep 8 (CS:790-836)
+        for _ in range(4):
+            psi = rng.normal(size=512) + 1j * rng.normal(size=512)
+            psi /= np.linalg.norm(psi)
+            words = random_words(rng, ops, density, density > 0)
+            idle = {ts: [q for q in range(13) if rng.random() < 0.25] for ts in gaps}
+            brute = dm.brute_half(psi, ops, words, idle)
+            out, factor = dm.diag_half(psi, ops, words, frame_x, idle)
             for a in range(16):
                 np.testing.assert_allclose(out[a] * factor, brute[512 * a:512 * (a + 1)], atol=1e-12, rtol=0)
