@@ -525,43 +525,64 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ MeasArgs m
         if (is_forced) {
             const uint32_t b = lane < 8 ? (uint32_t)forced[(size_t)shot * S17_MAX_OUTCOMES + nout + lane] : 0u;
             fo = __ballot_sync(0xffffffffu, (b & 1u) != 0u) & 0xFFu;
-        } else if (lane < 8) {
-            Philox rng(ma.seed, ma.first_shot + shot, ma.stream + ((lane >> 2) ? 0u : 1u));
-            rng.c3 = (uint32_t)(lane & 3);
-            uu = rng.next();
-        } else if (lane == 8 && ma.sample_data) {
-            Philox rng(ma.seed, ma.first_shot + shot, ma.data_stream);       // the read-out's uniform (k_readout's stream)
+        } else if (lane < 9) {
+            // lanes 0-7: the uniforms of the eight Measure gates (stream per half, counter block = slot); lane 8: the
+            // read-out's uniform (k_readout's stream)
+            Philox rng(ma.seed, ma.first_shot + shot, lane == 8 ? ma.data_stream : ma.stream + ((lane >> 2) ? 0u : 1u));
+            rng.c3 = lane == 8 ? 0u : (uint32_t)(lane & 3);
             uu = rng.next();
         }
 
-        double2 p[16];
         if (init_basis < 0) {
             mbar_wait(&full[sb], (j >> 1) & 1u);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) p[i] = *reinterpret_cast<const double2 *>(xb + (linA ^ P.mapA.lin16[i]));
         } else {
-#pragma unroll
+            // first cycle of a shot: synthesise the computational basis state in the buffer instead of reading HBM
+#pragma unroll 1
             for (int i = 0; i < 16; ++i)
-                p[i] = make_double2((linA ^ P.mapA.lin16[i]) == ((uint32_t)init_basis << 4) ? 1.0 : 0.0, 0.0);
+                reinterpret_cast<double2 *>(xb)[lane + 32 * i] = make_double2(lane + 32 * i == init_basis ? 1.0 : 0.0, 0.0);
+            __syncwarp();
         }
+        double2 p[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) p[i] = *reinterpret_cast<const double2 *>(xb + (linA ^ P.mapA.lin16[i]));
         mbar_wait(&mfull[sb], (j >> 1) & 1u);
         __syncwarp();                             // every lane holds its amplitudes: the buffer becomes exchange scratch
 
+        // Six steps: per half cycle [transform into its frame] [tables + four ancilla slots] [transform back].  The loop is
+        // not unrolled, so the transform and the slot code exist once in the instruction stream (the working set of
+        // twelve warps at different points of it has to stay inside the instruction cache).
         uint32_t carry = 0, perm = 0;
         double pfin = 1.0;
 #pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
+        for (int st = 0; st < 6; ++st) {
+            const int h = st >= 3 ? 1 : 0, r = st - 3 * h;
             const DiagHalf &H = P.h[h];
             const uint32_t fw = fwp[h];
-            if (H.frame_x) {                      // register bits of map A, the shuffle bit, exchange, register bits of map B
-                dg_wht16(p);
-                lane_stage(p);
+            if (r != 1) {
+                if (!H.frame_x) continue;
+                // Walsh-Hadamard transform of the data register: the register bits of the current map, the exchange to the
+                // other map, its register bits; the one remaining label bit is a lane bit of map A (shuffle stage)
+                const int dir = r >> 1;                           // 0: map A -> B (into the frame), 1: map B -> A
+                const uint32_t wl = dir ? swzB : swzA, rl = dir ? swzA : swzB;
+                const uint32_t *wr = dir ? P.mapB.swz16 : P.mapA.swz16, *rr = dir ? P.mapA.swz16 : P.mapB.swz16;
+#pragma unroll 1
+                for (int half_pass = 0; half_pass < 2; ++half_pass) {
+                    if (half_pass == dir) lane_stage(p);          // in map A: before the first pass / before the last one
+                    dg_wht16(p);
+                    if (half_pass == 0) {
+                        __syncwarp();
 #pragma unroll
-                for (int i = 0; i < 16; ++i) *reinterpret_cast<double2 *>(xb + (swzA ^ P.mapA.swz16[i])) = p[i];
-                __syncwarp();
+                        for (int i = 0; i < 16; ++i) *reinterpret_cast<double2 *>(xb + (wl ^ wr[i])) = p[i];
+                        __syncwarp();
 #pragma unroll
-                for (int i = 0; i < 16; ++i) p[i] = *reinterpret_cast<const double2 *>(xb + (swzB ^ P.mapB.swz16[i]));
-                dg_wht16(p);
+                        for (int i = 0; i < 16; ++i) p[i] = *reinterpret_cast<const double2 *>(xb + (rl ^ rr[i]));
+                    }
+                }
+                if (dir) {
+                    pfin *= 512.0;                                // the two transforms multiply the norm^2 by 512
+                    carry = fw & 511u;                            // its data flips are signs now: next half's sign mask
+                }
+                continue;
             }
             __syncwarp();
             // slots touched by an event of this shot (an event word, a sign they carry, the global phase) get private
@@ -591,21 +612,9 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ MeasArgs m
             }
             S17_DG_SLOT1(0) S17_DG_SLOT1(1) S17_DG_SLOT1(2) S17_DG_SLOT1(3)
 #undef S17_DG_SLOT1
-            if (H.frame_x) {
-                dg_wht16(p);
-                __syncwarp();
-#pragma unroll
-                for (int i = 0; i < 16; ++i) *reinterpret_cast<double2 *>(xb + (swzB ^ P.mapB.swz16[i])) = p[i];
-                __syncwarp();
-#pragma unroll
-                for (int i = 0; i < 16; ++i) p[i] = *reinterpret_cast<const double2 *>(xb + (swzA ^ P.mapA.swz16[i]));
-                lane_stage(p);
-                dg_wht16(p);
-                pfin *= 512.0;                    // the inverse transform multiplies the norm^2 by 512
-                carry = fw & 511u;
-            } else {
+            if (!H.frame_x) {
                 carry = 0;
-                perm = fw & 511u;
+                perm = fw & 511u;                                 // data flips of a computational-frame half relabel the store
             }
             if (lane == 0) meas_out[2 * shot + H.final_part] = a_out | (bad ? 0x100u : 0u);
         }
