@@ -670,7 +670,8 @@ k_pauli(double2 *__restrict__ state, const s17_record *__restrict__ rec, const u
 // atomic append: the order of the list is arbitrary (it only decides which CTA / warp processes which shot), *n_act
 // must be zero on entry (k_plan clears it).
 __global__ void __launch_bounds__(256)
-k_compact(const uint8_t *__restrict__ active, int n, uint32_t *__restrict__ list, uint32_t *__restrict__ n_act)
+k_compact(const uint8_t *__restrict__ active, int n, uint32_t *__restrict__ list, uint32_t *__restrict__ n_act,
+          const uint8_t *__restrict__ leaf /* nullptr, or per shot: byte for bits 24-31 of its entry (k_cycle1 + prep cache) */)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
     const bool flag = i < n && active[i];
@@ -679,7 +680,7 @@ k_compact(const uint8_t *__restrict__ active, int n, uint32_t *__restrict__ list
     uint32_t base = 0;
     if (lane == 0) base = atomicAdd(n_act, (uint32_t)__popc(ballot));
     base = __shfl_sync(0xffffffffu, base, 0);
-    if (flag) list[base + __popc(ballot & ((1u << lane) - 1u))] = (uint32_t)i;
+    if (flag) list[base + __popc(ballot & ((1u << lane) - 1u))] = (uint32_t)i | (leaf ? (uint32_t)leaf[i] << 24 : 0u);
 }
 
 struct ReadArgs {
@@ -932,6 +933,13 @@ struct s17_ctx {
     bool last_collapsed = true;       // the previous cycle left every active shot collapsed to ancilla block 0
     uint32_t *frm = nullptr;          // per shot: frame words of the two half cycles (k_plan -> k_cycle)
     uint32_t *dsamp = nullptr;        // per shot: data basis state drawn by k_cycle1 for the read-out
+    // memoised preparation cycle (k_prep): 256 leaf blocks, (P0, P1) per node of the outcome tree, leaf per shot
+    double2 *prep_blocks = nullptr;
+    double *prep_pp = nullptr;
+    uint8_t *prep_leaf = nullptr;
+    int prep_basis = -1;              // basis index the cache was built for (-1: not built)
+    bool no_prep_cache = false, plan_has_leak = false, use_prep = false;
+    PrepTree prep_tree;
     bool use_dsamp = false;
     bool no_fuse = false;
     bool debug_sync = false;
@@ -1054,6 +1062,9 @@ extern "C" int s17_create(s17_ctx **out, int device, uint64_t max_shots) {
     CK(cudaMalloc(&ctx->meas_out, B * 2 * 4));
     CK(cudaMalloc(&ctx->frm, B * 4 * 4));
     CK(cudaMalloc(&ctx->dsamp, B * 4));
+    CK(cudaMalloc(&ctx->prep_leaf, B));
+    CK(cudaMalloc(&ctx->prep_blocks, 256 * (size_t)kRunBytes));
+    CK(cudaMalloc(&ctx->prep_pp, 2 * 255 * sizeof(double)));
     CK(cudaMemset(ctx->frm, 0, B * 4 * 4));
     CK(cudaFuncSetAttribute(k_cycle, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDgSmem));
     CK(cudaFuncSetAttribute(k_cycle1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDgSmem1));
@@ -1079,6 +1090,8 @@ extern "C" int s17_create(s17_ctx **out, int device, uint64_t max_shots) {
         const char *nd = getenv("S17_DIAG");
         ctx->no_diag = nd && nd[0] == '0';          // 0: k_half everywhere; g: generic k_cycle only; default: k_cycle1 if possible
         ctx->no_diag1 = nd && nd[0] == 'g';
+        const char *pc = getenv("S17_PREP_CACHE");
+        ctx->no_prep_cache = pc && pc[0] == '0';
         const char *r = getenv("S17_RING");
         ctx->force_ring = r && r[0] == '1';
     }
@@ -1106,7 +1119,7 @@ extern "C" int s17_destroy(s17_ctx *ctx) {
     void *ptrs[] = {ctx->state, ctx->ev, ctx->masks, ctx->leak, ctx->active, ctx->ready, ctx->forced, ctx->hist,
                     ctx->aux, ctx->rec, ctx->counters, ctx->lut, ctx->cw16, ctx->probs, ctx->cum, ctx->plan,
                     ctx->rtf_slots, ctx->rtf_rounds, ctx->rtf_syndb, ctx->act_list, ctx->n_act, ctx->zero_page, ctx->meas_out,
-                    ctx->frm, ctx->dsamp};
+                    ctx->frm, ctx->dsamp, ctx->prep_leaf, ctx->prep_blocks, ctx->prep_pp};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
@@ -1655,6 +1668,10 @@ extern "C" int s17_load_program(s17_ctx *ctx, const s17_layer *layers, const uin
         if (in.word >= S17_EV_WORDS) return fail(ctx, S17_E_ARG, "plan word out of range");
     }
     CK(cudaMemset(ctx->probs, 0, 2048 * sizeof(double)));
+    ctx->prep_basis = -1;
+    ctx->plan_has_leak = false;
+    for (uint32_t i = 0; i < n_plan; ++i)
+        if (plan[i].kind == S17_P_ERR && (plan[i].err == S17_ERR_LEAK_A || plan[i].err == S17_ERR_LEAK_AB)) ctx->plan_has_leak = true;
     ctx->have_program = true;
     return S17_OK;
 }
@@ -1770,12 +1787,108 @@ static int ensure_state(s17_ctx *ctx, bool need_full) {
     return S17_OK;
 }
 
+// Build the memoised preparation cycle for `basis`: run the production kernel once per outcome pattern (256 forced shots
+// on private buffers), keep the collapsed blocks and the probability pair of every Measure along the way.
+static int build_prep_cache(s17_ctx *ctx, int basis) {
+    if (ctx->prep_basis == basis) return S17_OK;
+    const DiagProg1 &P = ctx->diag_prog1[0];
+    const int N = 256;
+    uint32_t *ev = nullptr, *frm = nullptr, *list = nullptr, *nact = nullptr, *mo = nullptr, *ds = nullptr;
+    uint8_t *forced = nullptr;
+    ShotAux *aux = nullptr;
+    double *pp = nullptr;
+    unsigned long long *cnt = nullptr;
+    CK(cudaMalloc(&ev, N * S17_EV_WORDS * 4));
+    CK(cudaMalloc(&frm, N * 16));
+    CK(cudaMalloc(&list, N * 4));
+    CK(cudaMalloc(&nact, 4));
+    CK(cudaMalloc(&mo, N * 8));
+    CK(cudaMalloc(&ds, N * 4));
+    CK(cudaMalloc(&forced, N * S17_MAX_OUTCOMES));
+    CK(cudaMalloc(&aux, N * sizeof(ShotAux)));
+    CK(cudaMalloc(&pp, N * 16 * sizeof(double)));
+    CK(cudaMalloc(&cnt, C_N * sizeof(unsigned long long)));
+    CK(cudaMemset(ev, 0, N * S17_EV_WORDS * 4));
+    CK(cudaMemset(frm, 0, N * 16));
+    CK(cudaMemset(cnt, 0, C_N * sizeof(unsigned long long)));
+    std::vector<uint32_t> h_list(N);
+    std::vector<uint8_t> h_forced((size_t)N * S17_MAX_OUTCOMES, 0);
+    PrepTree &T = ctx->prep_tree;
+    memset(&T, 0, sizeof(T));
+    for (int s = 0; s < 8; ++s) T.aj[s] = P.h[s >> 2].aj[s & 3];
+    T.final_part[0] = P.h[0].final_part;
+    T.final_part[1] = P.h[1].final_part;
+    for (int L = 0; L < N; ++L) {
+        h_list[L] = (uint32_t)L;
+        for (int s = 0; s < 8; ++s) h_forced[(size_t)L * S17_MAX_OUTCOMES + T.aj[s]] = (uint8_t)((L >> s) & 1);
+    }
+    const uint32_t n_items = N;
+    CK(cudaMemcpy(list, h_list.data(), N * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(nact, &n_items, 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(forced, h_forced.data(), h_forced.size(), cudaMemcpyHostToDevice));
+    MeasArgs ma;
+    memset(&ma, 0, sizeof(ma));
+    ma.stage = 0;
+    ma.forced = 1;
+    ma.mask = 0xFFu;
+    ma.final_part = 1;
+    ma.stream = 16u;
+    ma.n_shots = N;
+    k_cycle1<<<ctx->num_sms, kDgThreads, kDgSmem1, ctx->stream>>>(P, ma, ctx->prep_blocks, (size_t)kRun, ev, frm, list, nact, aux,
+                                                                 forced, mo, ds, cnt, basis, nullptr, pp);
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    std::vector<double> h_pp((size_t)N * 16);
+    CK(cudaMemcpy(h_pp.data(), pp, h_pp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    // node (s, prefix) takes its pair from leaf = prefix: that leaf's path runs through the node, and if the node is
+    // reachable every earlier step of the path was possible
+    std::vector<double> node(2 * 255, 0.0);
+    for (int s = 0; s < 8; ++s)
+        for (int prefix = 0; prefix < (1 << s); ++prefix) {
+            node[2 * (((1 << s) - 1) + prefix)] = h_pp[(size_t)prefix * 16 + 2 * s];
+            node[2 * (((1 << s) - 1) + prefix) + 1] = h_pp[(size_t)prefix * 16 + 2 * s + 1];
+        }
+    CK(cudaMemcpy(ctx->prep_pp, node.data(), node.size() * sizeof(double), cudaMemcpyHostToDevice));
+    for (void *q : {(void *)ev, (void *)frm, (void *)list, (void *)nact, (void *)mo, (void *)ds, (void *)forced, (void *)aux,
+                    (void *)pp, (void *)cnt})
+        cudaFree(q);
+    ctx->prep_basis = basis;
+    return S17_OK;
+}
+
 // one stabiliser cycle: plan -> gate sweeps -> ancilla measurement decisions
 static void collapse(s17_ctx *ctx, int n, const uint8_t *flag);
 
 static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second, int init_basis, uint32_t max_layers, bool dense,
                      bool mid_collapse) {
     const int n = (int)a.n_shots;
+    if (stage == 0 && ctx->use_prep) {
+        // memoised noiseless preparation cycle: replay the kernel's decisions per shot, no state traffic
+        MeasArgs ma;
+        memset(&ma, 0, sizeof(ma));
+        ma.stage = 0;
+        ma.protocol = (int)a.protocol;
+        ma.forced = (int)a.forced;
+        ma.seed = a.seed;
+        ma.first_shot = a.first_shot_id;
+        ma.n_shots = n;
+        ma.mask = 0xFFu;
+        ma.final_part = 1;
+        ma.stream = 16u;
+        {
+            SCOPE(CAT_GATE);
+            k_prep<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(ctx->prep_tree, ma, ctx->prep_pp, ctx->forced, ctx->active,
+                                                                ctx->meas_out, ctx->prep_leaf, ctx->aux, ctx->counters);
+            ctx->n_gate++;
+        }
+        {
+            SCOPE(CAT_MEAS);
+            k_record<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(ma, ctx->meas_out, ctx->lut, ctx->leak, ctx->active,
+                                                                  ctx->ready, ctx->rec, ctx->counters);
+        }
+        ctx->last_collapsed = true;
+        return S17_OK;
+    }
     PlanArgs pa;
     pa.n_instr = ctx->n_plan;
     pa.noise = (int)a.noise;
@@ -1798,7 +1911,8 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
     if (max_layers && max_layers < nl) nl = max_layers;
     {
         SCOPE(CAT_OTHER);
-        k_compact<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(ctx->active, n, ctx->act_list, ctx->n_act);
+        k_compact<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(ctx->active, n, ctx->act_list, ctx->n_act,
+                                                               (ctx->use_prep && stage == 1) ? ctx->prep_leaf : nullptr);
     }
     MeasArgs ma;
     memset(&ma, 0, sizeof(ma));
@@ -1827,7 +1941,8 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
             if (ctx->diag1_ok[which] && !ctx->no_diag1)
                 k_cycle1<<<ctx->num_sms, kDgThreads, kDgSmem1, ctx->stream>>>(
                     ctx->diag_prog1[which], ma, ctx->state, ctx->stride, ctx->ev, ctx->frm, ctx->act_list, ctx->n_act, ctx->aux,
-                    ctx->forced, ctx->meas_out, ctx->dsamp, ctx->counters, init_basis);
+                    ctx->forced, ctx->meas_out, ctx->dsamp, ctx->counters, init_basis,
+                    (ctx->use_prep && stage == 1) ? ctx->prep_blocks : nullptr, nullptr);
             else
                 k_cycle<<<ctx->num_sms, kDgThreads, kDgSmem, ctx->stream>>>(
                     ctx->diag_prog[which], ma, ctx->state, ctx->stride, ctx->ev, ctx->frm, ctx->act_list, ctx->n_act, ctx->aux,
@@ -1918,6 +2033,13 @@ static int run_round(s17_ctx *ctx, const s17_run_args &a) {
     // both noisy cycles go through k_cycle1 and outcomes are sampled: the cycle kernel also draws the data read-out
     ctx->use_dsamp = ctx->diag1_ok[1] && ctx->diag1_ok[2] && !ctx->no_diag1 && !ctx->no_diag && !explicit_collapse &&
                      !ctx->use_v1 && !ctx->force_ring && !ctx->no_fuse && !a.forced;
+    // the noiseless preparation cycle is memoised when it and the first noisy cycle run on k_cycle1 and no leak flag can
+    // be set when it starts (run-til-fail keeps leak flags across the rounds of a run)
+    ctx->use_prep = ctx->diag1_ok[0] && ctx->diag1_ok[1] && !ctx->no_diag1 && !ctx->no_diag && !explicit_collapse &&
+                    !ctx->use_v1 && !ctx->force_ring && !ctx->no_fuse && !ctx->no_prep_cache && ctx->max_shots < (1u << 24) &&
+                    !(a.protocol == S17_PROTO_RTF && ctx->plan_has_leak);
+    if (ctx->use_prep)
+        if (int rc = build_prep_cache(ctx, basis_index)) return rc;
     if (int rc = run_cycle(ctx, a, 0, 0, basis_index, 0, dense, explicit_collapse)) return rc;
     if (explicit_collapse) collapse(ctx, n, ctx->active);
     if (a.stop_stage == S17_STOP_AFTER_PREP) return S17_OK;

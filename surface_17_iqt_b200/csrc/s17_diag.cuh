@@ -370,7 +370,8 @@ k_cycle(const __grid_constant__ DiagProg P, const __grid_constant__ MeasArgs ma,
 // ------------------------------------------------------------------------------------------------------------------
 template <int B>
 __device__ __forceinline__ void dg_slot1(double2 (&p)[16], const unsigned char *tk0, const unsigned char *tk1, uint32_t aj,
-                                         bool forced, uint32_t fo, double u, uint32_t &a_out, bool &bad, double &pfin) {
+                                         bool forced, uint32_t fo, double u, uint32_t &a_out, bool &bad, double &pfin,
+                                         double *pp) {
     const double2 q0 = *reinterpret_cast<const double2 *>(tk0 + 32 * kDgTabEntries);
     const double2 q1 = *reinterpret_cast<const double2 *>(tk1 + 32 * kDgTabEntries);
     double w0[2] = {0.0, 0.0}, w1[2] = {0.0, 0.0};           // two partial sums each: shorter dependency chains
@@ -387,6 +388,7 @@ __device__ __forceinline__ void dg_slot1(double2 (&p)[16], const unsigned char *
         p0 += __shfl_xor_sync(0xffffffffu, p0, d);
         p1 += __shfl_xor_sync(0xffffffffu, p1, d);
     }
+    if (pp) { pp[0] = p0; pp[1] = p1; }                      // every lane holds the same pair
     uint32_t out;
     if (forced) {
         out = (fo >> aj) & 1u;
@@ -407,8 +409,11 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ MeasArgs m
          size_t stride, const uint32_t *__restrict__ ev, const uint32_t *__restrict__ frm, const uint32_t *__restrict__ act_list,
          const uint32_t *__restrict__ n_act_ptr, ShotAux *__restrict__ aux, const uint8_t *__restrict__ forced,
          uint32_t *__restrict__ meas_out, uint32_t *__restrict__ dsamp, unsigned long long *__restrict__ counters,
-         int init_basis)
+         int init_basis, const double2 *__restrict__ alt_src, double *__restrict__ pp_out)
 {
+    // alt_src != nullptr: an entry of act_list is shot | leaf << 24 and the input block of the shot is alt_src[leaf]
+    // (the memoised outcome of the noiseless preparation cycle, s17.cu: build_prep_cache); pp_out != nullptr: record
+    // the (P(0), P(1)) pair of every Measure (used once, to build that cache)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char *wb = smem_raw + (size_t)warp * kDgWarpBytes;
@@ -483,7 +488,8 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ MeasArgs m
         }
     }
 
-    auto prefetch = [&](uint32_t shot_, int sb) {
+    auto prefetch = [&](uint32_t entry, int sb) {
+        const uint32_t shot_ = entry & 0xFFFFFFu;
         unsigned char *m = meta + sb * kDgMetaBytes;
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the bulk store staged in this buffer has left it
         fence_proxy_async_smem();                 // the buffers were last touched through the generic proxy
@@ -492,7 +498,8 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ MeasArgs m
         tma_load_1d(m + kEvBytes, frm + (size_t)shot_ * 4, kDgFrmBytes, &mfull[sb]);
         if (init_basis < 0) {
             mbar_expect_tx(&full[sb], kRunBytes);
-            tma_load_1d(buf + sb * kRunBytes, state + (size_t)shot_ * stride, kRunBytes, &full[sb]);
+            tma_load_1d(buf + sb * kRunBytes, alt_src ? alt_src + (size_t)(entry >> 24) * kRun : state + (size_t)shot_ * stride,
+                        kRunBytes, &full[sb]);
         }
     };
     auto lane_stage = [&](double2 (&q)[16]) {
@@ -503,18 +510,19 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ MeasArgs m
         }
     };
 
-    uint32_t shot = act_list[first];
-    if (lane == 0) prefetch(shot, 0);
+    uint32_t entry = act_list[first];
+    if (lane == 0) prefetch(entry, 0);
 
     const uint32_t nout = 8u * (uint32_t)ma.stage;
     const bool is_forced = ma.forced != 0;
     uint32_t j = 0;
     for (uint32_t item = first; item < last; ++item, ++j) {
         const int sb = (int)(j & 1u);
-        uint32_t shot1 = 0;
+        const uint32_t shot = entry & 0xFFFFFFu;
+        uint32_t entry1 = 0;
         if (item + 1 < last) {
-            shot1 = act_list[item + 1];
-            if (lane == 0) prefetch(shot1, sb ^ 1);
+            entry1 = act_list[item + 1];
+            if (lane == 0) prefetch(entry1, sb ^ 1);
         }
         const uint32_t *evw = reinterpret_cast<const uint32_t *>(meta + sb * kDgMetaBytes);
         const uint32_t *fwp = reinterpret_cast<const uint32_t *>(meta + sb * kDgMetaBytes + kEvBytes);
@@ -608,7 +616,8 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ MeasArgs m
             {                                                                                                        \
                 const double u = __shfl_sync(0xffffffffu, uu, 4 * h + K);                                            \
                 const unsigned char *tk0 = (((dirty >> K) & 1u) ? tab : clean_h) + (((tl >> (8 * K)) & 0xFFu) << 4);   \
-                dg_slot1<K>(p, tk0, tk0 + P.off1[h][K], H.aj[K], is_forced, fo, u, a_out, bad, pfin);                \
+                dg_slot1<K>(p, tk0, tk0 + P.off1[h][K], H.aj[K], is_forced, fo, u, a_out, bad, pfin,                 \
+                            pp_out ? pp_out + ((size_t)shot * 8 + 4 * h + K) * 2 : nullptr);                         \
             }
             S17_DG_SLOT1(0) S17_DG_SLOT1(1) S17_DG_SLOT1(2) S17_DG_SLOT1(3)
 #undef S17_DG_SLOT1
@@ -667,13 +676,65 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ MeasArgs m
             aux[shot] = ax;
         }
         __syncwarp();                             // tables and the metadata slot are reused
-        shot = shot1;
+        entry = entry1;
     }
     if (lane == 0) {
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         atomicAdd(&counters[4], (unsigned long long)(last - first));                                     // C_SWEEPS
-        atomicAdd(&counters[8], (unsigned long long)(last - first) * (init_basis < 0 ? 2ull : 1ull));   // 8 KiB runs moved
+        atomicAdd(&counters[8], (unsigned long long)(last - first) * ((init_basis < 0 && !alt_src) ? 2ull : 1ull));   // 8 KiB runs moved (HBM)
     }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Memoised preparation cycle.  logical_prep (CS:96-123) runs the NOISELESS cycle on |0...0>: without a leaked qubit its
+// result depends only on the eight measurement outcomes.  build_prep_cache (s17.cu) runs k_cycle1 once per outcome
+// pattern (256 forced shots) and keeps, per node of the outcome tree, the (P(0), P(1)) pair the kernel computed and, per
+// leaf, the collapsed block.  k_prep then replays the kernel's own decisions per shot -- same Philox uniforms, same
+// comparison, same doubles -- and the first noisy cycle reads its input block from the cache (L2 resident).
+// ------------------------------------------------------------------------------------------------------------------
+struct PrepTree {
+    uint8_t aj[8];             // ancilla index of Measure step s (half s / 4, slot s % 4)
+    uint8_t final_part[2];
+    uint8_t pad[6];
+};
+
+__global__ void __launch_bounds__(256)
+k_prep(const __grid_constant__ PrepTree T, const __grid_constant__ MeasArgs ma, const double *__restrict__ node_pp,
+       const uint8_t *__restrict__ forced, const uint8_t *__restrict__ active, uint32_t *__restrict__ meas_out,
+       uint8_t *__restrict__ leaf_out, ShotAux *__restrict__ aux, unsigned long long *__restrict__ counters)
+{
+    const int shot = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = shot < ma.n_shots && active[shot];
+    if (live) {
+        uint32_t prefix = 0, r[2] = {0u, 0u};
+        bool bad = false;
+#pragma unroll 1
+        for (int s = 0; s < 8; ++s) {
+            // node (s, prefix): nodes of depth s start at 2^s - 1
+            const double p0 = node_pp[2 * (((1u << s) - 1u) + prefix)], p1 = node_pp[2 * (((1u << s) - 1u) + prefix) + 1];
+            uint32_t out;
+            if (ma.forced) {
+                out = forced[(size_t)shot * S17_MAX_OUTCOMES + T.aj[s]] & 1u;           // stage 0: the first eight outcomes
+                if ((out ? p1 : p0) <= 0.0) bad = true;
+            } else {
+                Philox rng(ma.seed, ma.first_shot + shot, ma.stream + ((s >> 2) ? 0u : 1u));
+                rng.c3 = (uint32_t)(s & 3);
+                out = (rng.next() * (p0 + p1) < p1) ? 1u : 0u;
+            }
+            prefix |= out << s;
+            r[s >> 2] |= out << T.aj[s];
+        }
+        meas_out[2 * shot + T.final_part[0]] = r[0] | (bad ? 0x100u : 0u);
+        meas_out[2 * shot + T.final_part[1]] = r[1] | (bad ? 0x100u : 0u);
+        leaf_out[shot] = (uint8_t)prefix;
+        ShotAux ax;
+        ax.scale = 1.0;
+        ax.anc_outcome = 0;
+        ax.collapsed = 1;
+        aux[shot] = ax;
+    }
+    const uint32_t nl = __popc(__ballot_sync(0xffffffffu, live));
+    if ((threadIdx.x & 31) == 0 && nl) atomicAdd(&counters[4], (unsigned long long)nl);                  // C_SWEEPS
 }
 
 }  // namespace s17

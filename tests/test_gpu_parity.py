@@ -310,6 +310,38 @@ def test_full_size_properties(error_models, correction_table, bitflip_table):
     sim.close()
 
 
+@pytest.mark.parametrize("model,protocol,cooling,eset", [("PDD_model", "s2", False, [1, 1, 2, 2, 1]),
+                                                         ("Dress_cooling", "s1", True, [0, 1, 1, 3, 0, 4])])
+def test_memoised_preparation_is_bit_identical(error_models, correction_table, bitflip_table, model, protocol, cooling,
+                                               eset, monkeypatch):
+    """k_prep replays the decisions k_cycle1 takes in the noiseless preparation cycle (same uniforms, same probability
+    pairs) and hands the first noisy cycle the cached block: records, outcome logs and stored amplitudes are identical
+    to running the preparation cycle per shot, sampled and replayed."""
+    per_round = circuit.list_lengths(error_models[model])
+    locs = [2 * x for x in per_round] if protocol == "s2" else per_round
+    n = 4096
+    out = {}
+    for cache in ("1", "0"):
+        monkeypatch.setenv("S17_PREP_CACHE", cache)
+        sim = make_sim(error_models, correction_table, bitflip_table, model, locs, n, 2, cooling)
+        sim.backend.set_subset(eset, locs)
+        c = sim.backend.run(protocol, n, L.NOISE_SUBSET, seed=99, first_shot_id=12345)
+        recs = sim.backend.records(n)
+        states = np.stack([sim.backend.state(i)[:512] for i in range(0, n, 64)])
+        # forced replay of the first 64 trajectories through the same configuration
+        sim.backend.set_replay([list(m) for m in sim.backend.masks(64)[:, 0]], [r["outcomes"] for r in recs[:64]])
+        c2 = sim.backend.run(protocol, 64, L.NOISE_REPLAY, forced=True)
+        assert c2.errors == 0
+        out[cache] = ((c.failed, c.not0, c.counted, c.errors, c.sweeps), recs, states, sim.backend.records(64))
+        sim.close()
+    assert out["1"][0] == out["0"][0]
+    assert out["1"][1] == out["0"][1]
+    assert np.array_equal(out["1"][2], out["0"][2])
+    for i in range(64):
+        for f in FIELDS + ("outcomes",):
+            assert out["1"][3][i].get(f) == out["1"][1][i].get(f) == out["0"][3][i].get(f), (i, f)
+
+
 def test_cycle_kernel_large_batch_properties(error_models, correction_table, bitflip_table, monkeypatch):
     """The whole-cycle kernel at a batch where every warp walks a few dozen shots (prefetch ring, barrier phases): no
     noise => no detection and no failure; every single-error subset is corrected (distance 3); the searched-map kernel
