@@ -312,15 +312,22 @@ __device__ __forceinline__ uint32_t pconj_rxx(uint32_t P, int s) {        // Rxx
 // words) so that the global traffic is coalesced rows instead of 32 strided 4-byte accesses per instruction.
 constexpr int kPlanThreads = 128;
 constexpr int kPlanRow = 33;
+constexpr int kPlanMaxInstr = 640;
 __global__ void __launch_bounds__(kPlanThreads)
 k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, NoiseDev nd, const double *__restrict__ probs,
        uint32_t *__restrict__ ev, uint32_t *__restrict__ masks, uint32_t *__restrict__ leak,
        const uint8_t *__restrict__ active, uint32_t *__restrict__ frm, uint32_t *__restrict__ n_act)
 {
     __shared__ uint32_t s_mask[kPlanThreads / 32][32][kPlanRow], s_ev[kPlanThreads / 32][32][kPlanRow];
+    __shared__ uint32_t s_prog[kPlanMaxInstr * 3];     // the program of this cycle (slots resolved to absolute bit indices)
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int shot = blockIdx.x * blockDim.x + threadIdx.x, shot0 = shot - lane;
     if (shot == 0) *n_act = 0;                         // k_compact, next in the stream, appends to an empty list
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(prog);
+        for (int i = threadIdx.x; i < pa.n_instr * 3; i += blockDim.x) s_prog[i] = src[i];
+        __syncthreads();
+    }
     const bool act = shot < pa.n_shots && active[shot];
     const uint32_t actmask = __ballot_sync(0xffffffffu, act);
     if (!actmask) return;
@@ -346,7 +353,21 @@ k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, NoiseDev nd, const doub
     for (int i = 24; i < (int)S17_EV_WORDS; ++i) evs[i] = 0;
     uint32_t w = 0, skip = 0;
     for (int i = 0; i < pa.n_instr; ++i) {
-        const s17_pinstr in = prog[i];
+        const s17_pinstr in = reinterpret_cast<const s17_pinstr *>(s_prog)[i];
+        if (in.kind == S17_P_ERR || in.kind == S17_P_IDLE) {
+            // one Bernoulli draw per entry (CS:198), none inside a skipped Rxx block.  in.slot is the absolute index of
+            // the entry's slot in this cycle (list offset + slot + half the list in a second cycle, CS:191-193).
+            if ((in.in_skip && skip) || pa.noiseless) continue;
+            const uint32_t bit = in.slot;
+            bool fire;
+            if (prob_mode) {
+                fire = rng.next() < probs[bit];
+                if (fire) mask_set(mrec, bit);
+            } else {
+                fire = mask_get(mk, bit);
+            }
+            if (!fire) continue;
+        }
         if (in.kind == S17_P_OP_BEGIN) { w = 0; skip = 0; continue; }
         if (in.kind == S17_P_SKIP_TEST) {
             // evaluated AFTER the errors of a preceding Ry (which may just have leaked the data qubit)
@@ -394,19 +415,6 @@ k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, NoiseDev nd, const doub
             evs[in.word] = w;
             continue;
         }
-        // S17_P_ERR / S17_P_IDLE: one Bernoulli draw per entry (CS:198), none inside a skipped Rxx block
-        if (in.in_skip && skip) continue;
-        if (pa.noiseless) continue;
-        const uint32_t L = nd.list_len[in.list];
-        const uint32_t slot = in.slot + ((pa.second && in.use_round) ? (L >> 1) : 0u);
-        bool fire;
-        if (pa.noise == S17_NOISE_PROB) {
-            fire = rng.next() < probs[nd.list_off[in.list] + slot];
-            if (fire) mask_set(mrec, nd.list_off[in.list] + slot);
-        } else {
-            fire = mask_get(mk, nd.list_off[in.list] + slot);
-        }
-        if (!fire) continue;
         if (in.kind == S17_P_IDLE) {
             evs[in.word] |= 1u << in.a;                // the 17-bit idle masks of the sweep kernels / k_half
             if (in.b & 0x80u) {                        // the same Z in the frame of its half cycle (whole-cycle kernels)
@@ -1645,9 +1653,7 @@ extern "C" int s17_load_program(s17_ctx *ctx, const s17_layer *layers, const uin
             ctx->diag1_ok[c] = ctx->diag_ok[c] && make_diag1(ctx->diag_prog[c], ctx->diag_prog1[c]);
         }
     }
-    if (ctx->plan) { cudaFree(ctx->plan); ctx->plan = nullptr; }
-    CK(cudaMalloc(&ctx->plan, n_plan * sizeof(s17_pinstr)));
-    CK(cudaMemcpy(ctx->plan, plan, n_plan * sizeof(s17_pinstr), cudaMemcpyHostToDevice));
+    if (n_plan > (uint32_t)kPlanMaxInstr) return fail(ctx, S17_E_ARG, "injection program too long");
     ctx->n_plan = (int)n_plan;
     memset(&ctx->nd, 0, sizeof(ctx->nd));
     ctx->nd.n_lists = lists->n_lists;
@@ -1666,6 +1672,23 @@ extern "C" int s17_load_program(s17_ctx *ctx, const s17_layer *layers, const uin
             if (in.slot >= lists->list_len[in.list]) return fail(ctx, S17_E_ARG, "plan slot beyond its list (list too short)");
         }
         if (in.word >= S17_EV_WORDS) return fail(ctx, S17_E_ARG, "plan word out of range");
+    }
+    {
+        // device copies of the program with every slot resolved to its absolute bit / probability index: one for a first
+        // cycle, one for a second cycle (stab_ind=1: slots offset by half the list, CS:191-193)
+        std::vector<s17_pinstr> res(2 * (size_t)n_plan);
+        for (int c2 = 0; c2 < 2; ++c2)
+            for (uint32_t i = 0; i < n_plan; ++i) {
+                s17_pinstr in = plan[i];
+                if (in.kind == S17_P_ERR || in.kind == S17_P_IDLE) {
+                    const uint32_t L = lists->list_len[in.list];
+                    in.slot = (uint16_t)(ctx->nd.list_off[in.list] + in.slot + ((c2 && in.use_round) ? (L >> 1) : 0u));
+                }
+                res[(size_t)c2 * n_plan + i] = in;
+            }
+        if (ctx->plan) { cudaFree(ctx->plan); ctx->plan = nullptr; }
+        CK(cudaMalloc(&ctx->plan, res.size() * sizeof(s17_pinstr)));
+        CK(cudaMemcpy(ctx->plan, res.data(), res.size() * sizeof(s17_pinstr), cudaMemcpyHostToDevice));
     }
     CK(cudaMemset(ctx->probs, 0, 2048 * sizeof(double)));
     ctx->prep_basis = -1;
@@ -1901,7 +1924,7 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
     pa.n_shots = n;
     {
         SCOPE(CAT_OTHER);
-        k_plan<<<blocks_for(n, kPlanThreads), kPlanThreads, 0, ctx->stream>>>(ctx->plan, pa, ctx->nd, ctx->probs, ctx->ev, ctx->masks,
+        k_plan<<<blocks_for(n, kPlanThreads), kPlanThreads, 0, ctx->stream>>>(ctx->plan + (second ? ctx->n_plan : 0), pa, ctx->nd, ctx->probs, ctx->ev, ctx->masks,
                                                             ctx->leak, ctx->active, ctx->frm, ctx->n_act);
     }
     const int which = stage == 0 ? 0 : (second ? 2 : 1);
