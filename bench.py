@@ -15,8 +15,9 @@ only exchange is one all-reduce of the counters at the end (inside the timed reg
            surface_17_iqt_b200.calc_log_e_rate_arbitrary_error_model.s2_calculate_log_e_rate_error_subset
            with host inputs and host results, wall-clock around the calls.
 `roofline`: the dominant kernel, k_cycle1 (one whole stabiliser cycle per shot and launch, the state in registers):
-           algorithmic bytes = the 8 KiB block it reads + the 8 KiB block it writes per shot and cycle, divided by
-           the summed CUDA-event time of its launches.  The kernel is bound by the FP64 pipe and shared memory, not by
+           algorithmic bytes = the 8 KiB block it reads + the 8 KiB block it writes per shot and noisy cycle (the first
+           noisy cycle reads its input from the 2 MiB cache of the memoised preparation cycle, not counted), divided
+           by the summed CUDA-event time of its launches.  The kernel is bound by the FP64 pipe and shared memory, not by
            HBM; `roofline_dense` is the same gate stream as full-state sweeps (2 MiB read + 2 MiB written per shot
            and sweep, S17_DENSE=1), the HBM-bound configuration BASELINE.json's "% of HBM roofline per gate layer"
            refers to.
@@ -137,9 +138,10 @@ def workload_config(shots, n_gpus, fusion):
             "state": "complex128; between cycles the 2^9 amplitudes that can be non-zero after the ancilla resets "
                      "(8 KiB per shot) are resident in HBM; S17_DENSE=1 keeps and sweeps all 2^17 (roofline_dense)",
             "parallelism": "shots sharded x{}".format(n_gpus),
-            "schedule": "one kernel per stabiliser cycle (k_cycle1): the cycle in the frame where its gates are "
-                        "diagonal, X-type ancillas measured after timestep 4, one warp per shot; S17_DIAG=0 / "
-                        "S17_DENSE=1 select the general amplitude kernels",
+            "schedule": "one kernel per noisy stabiliser cycle (k_cycle1): the cycle in the frame where its gates are "
+                        "diagonal, X-type ancillas measured after timestep 4, one warp per shot; the noiseless "
+                        "preparation cycle replayed from a 256-leaf cache of the same kernel's decisions (k_prep); "
+                        "S17_PREP_CACHE=0 / S17_DIAG=0 / S17_DENSE=1 select the uncached / general amplitude paths",
             "l2": "per-step working set (shots x 8 KiB read + 8 KiB written per cycle = {:.1f} GB) exceeds the 126 MB L2, "
                   "no flush needed".format(shots * 16384 / 1e9)}
 
@@ -148,34 +150,60 @@ def workload_config(shots, n_gpus, fusion):
 # clocks
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons during the timed region: NVML when importable (a sample per ~2 ms), nvidia-smi
+    otherwise (a sample per ~0.2 s)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # LOCAL_RANK indexes the visible devices; NVML wants the physical one
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = int(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
     def run(self):
         while not self.stop_flag:
             try:
+                if self.nvml is not None:
+                    n = self.nvml
+                    sm = int(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                    r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                    bits = [n.nvmlClocksEventReasonHwSlowdown, n.nvmlClocksEventReasonHwThermalSlowdown,
+                            n.nvmlClocksEventReasonSwThermalSlowdown, n.nvmlClocksEventReasonSwPowerCap]
+                    self.samples.append([str(sm), str(self.sm_max)] + ["Active" if r & b else "Not Active" for b in bits])
+                    time.sleep(0.002)
+                    continue
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
                 parts = [p.strip() for p in out.strip().split(",")]
                 if len(parts) >= 6:
                     self.samples.append(parts)
             except Exception:
-                pass
+                if self.nvml is not None:
+                    self.nvml = None          # fall back to nvidia-smi
+                    continue
             time.sleep(0.2)
 
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        reasons = [n for i, n in enumerate(self.NAMES) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None,
                 "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.samples)}
+                "reasons": reasons, "samples": len(self.samples),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -325,10 +353,10 @@ def run_gpu(args):
                          # average launch: 2.114 GB measured for 2.147 GB algorithmic at 131072 shots
                          # (profiles/r1n_k_cycle1_ncu_full.csv)
                          "traffic": (sweep_bytes / max(1, gate_launches)) * (2.1137 / 2.1475),
-                         "note": "one launch = one stabiliser cycle of every active shot: 8 KiB read + 8 KiB written per "
-                                 "shot, everything else in registers / shared memory; ncu: FP64 pipe 47 %, shared-memory "
-                                 "wavefronts 51 %, issue slots 54 % -- not HBM-bound; the HBM-bound full-state "
-                                 "configuration is roofline_dense",
+                         "note": "one launch = one noisy stabiliser cycle of every active shot: 8 KiB read + 8 KiB written "
+                                 "per shot, everything else in registers / shared memory (the noiseless preparation cycle is "
+                                 "memoised: k_prep); ncu: FP64 pipe 42-47 %, shared-memory wavefronts 45-51 %, issue slots "
+                                 "47-54 % -- not HBM-bound; the HBM-bound full-state configuration is roofline_dense",
                          "launches": int(gate_launches), "sweeps": int(sweeps),
                          "sweeps_per_shot": sweeps / (B * args.steps),
                          "bytes_per_shot": sweep_bytes / (B * args.steps), "dense_bytes_per_sweep": SWEEP_BYTES,

@@ -23,7 +23,9 @@ from . import _lib as L
 from . import api, circuit, distributed
 
 # knobs (module-level like the reference's scripts; no CLI)
-BATCH_SHOTS = int(os.environ.get("S17_BATCH", "4096"))    # shots resident per device context (2 MiB each)
+# shots resident per device context: 8 KiB each when every cycle runs on the whole-cycle kernel, 2 MiB each otherwise
+# (the first out-of-memory error of a context shrinks the batch and retries, see _with_batch_retry)
+BATCH_SHOTS = int(os.environ.get("S17_BATCH", "262144"))
 FUSION = int(os.environ.get("S17_FUSION", "2"))           # timesteps per sweep: 0 = one gate per sweep, 1, 2 or 4
 DEVICE = None                                             # None: LOCAL_RANK or 0
 VERBOSE = True                                            # print the reference's summary lines
@@ -52,9 +54,26 @@ def _simulation(model, list_len, cooling, correction_table, bitflip_table, over_
         sim = api.Simulation(model, list_len, BATCH_SHOTS, correction_table, bitflip_table, fusion=FUSION,
                              cooling=cooling, device=_device(), over_angles=over_angles)
         _SIMS[key] = sim
-    else:
-        sim.backend.load_tables(correction_table, bitflip_table)
+        sim._tables = (correction_table, bitflip_table)
+    elif sim._tables[0] is not correction_table or sim._tables[1] is not bitflip_table:
+        sim.backend.load_tables(correction_table, bitflip_table)      # other table objects than last time: re-pack
+        sim._tables = (correction_table, bitflip_table)
     return sim
+
+
+def _with_batch_retry(fn):
+    """Run fn(); if the device cannot hold BATCH_SHOTS state vectors of the size this program needs (2 MiB per shot on
+    the general amplitude kernels), drop the context, cut the batch to a sixteenth and try again."""
+    global BATCH_SHOTS
+    while True:
+        try:
+            return fn()
+        except L.S17Error as exc:
+            if "out of device memory" not in str(exc) or BATCH_SHOTS <= 256:
+                raise
+            release()
+            BATCH_SHOTS = max(256, BATCH_SHOTS // 16)
+            _log("device memory: batch reduced to {} shots".format(BATCH_SHOTS))
 
 
 def release():
@@ -98,8 +117,12 @@ def generate_error_locations_non_uniform(num_e, num_e_locations, probs):
     return mask
 
 
-def _run_subset(protocol, num_runs, correction_table, model, eset, locations, bitflip_table, prob_lists, cz_comp,
-                cooling):
+def _run_subset(*args):
+    return _with_batch_retry(lambda: _run_subset_once(*args))
+
+
+def _run_subset_once(protocol, num_runs, correction_table, model, eset, locations, bitflip_table, prob_lists, cz_comp,
+                     cooling):
     if cz_comp:
         raise NotImplementedError("the experimental CZ compilation is outside the accelerated path (SURVEY C-9)")
     if len(eset) != len(locations) or len(prob_lists) != len(eset):
@@ -194,6 +217,11 @@ def calculate_log_e_rate_true_probability(num_runs, correction_table, model, p_s
     config 1 (`depolarising_model`, px = py = pz = p/3 on the 30 single-qubit slots, `depol` p on the 24 Rxx slots;
     slot indexing per SURVEY App. C-1) and config 3 (`coherent_model`, angles via `over_angles`).
     Returns (failed_count / counted, failed_count, counted, flipsa_not0_count)."""
+    return _with_batch_retry(lambda: _true_probability_once(num_runs, correction_table, model, p_set, bitflip_table,
+                                                            protocol, cooling, over_angles))
+
+
+def _true_probability_once(num_runs, correction_table, model, p_set, bitflip_table, protocol, cooling, over_angles):
     p_set = [list(p) for p in p_set]
     sim = _simulation(model, [len(p) for p in p_set], cooling, correction_table, bitflip_table, over_angles=over_angles)
     names = sim.model["probabilities"]
@@ -247,11 +275,15 @@ def calculate_log_e_rate(num_runs, filename, correction_table, e_model, e_probs,
     for k, plist, n in zip(names, p_set, need):
         if len(plist) < n:
             raise IndexError("probability list {} has {} entries, the cycle indexes {}".format(k, len(plist), n))
-    sim = _simulation(model_name, [len(p) for p in p_set], False, correction_table, bitflip_table)
-    sim.backend.set_slot_probs(p_set)
+    seed = random.getrandbits(64)
     t_begin = time.perf_counter()
-    c = sim.backend.run("rtf", min(BATCH_SHOTS, num_runs), L.NOISE_PROB, seed=random.getrandbits(64),
-                        rtf_runs=num_runs)
+
+    def run_once():
+        sim_ = _simulation(model_name, [len(p) for p in p_set], False, correction_table, bitflip_table)
+        sim_.backend.set_slot_probs(p_set)
+        return sim_, sim_.backend.run("rtf", min(BATCH_SHOTS, num_runs), L.NOISE_PROB, seed=seed, rtf_runs=num_runs)
+
+    sim, c = _with_batch_retry(run_once)
     rounds, syndb = sim.backend.rtf_results(num_runs)
     total_time_taken = time.perf_counter() - t_begin
     round_count_list = [int(v) for v in rounds]

@@ -500,3 +500,20 @@ def test_run_til_fail_sweep_example():
     out = mod.sweep("Dress_model", runs=300, ps=(0.02, 0.01))
     assert out["0.02"]["log_e_rate_fit"] > 0 and out["0.01"]["log_e_rate_fit"] > 0
     assert out["0.02"]["rounds"] < out["0.01"]["rounds"] * 1.5      # more noise -> runs fail sooner
+
+
+def test_driver_batch_shrinks_when_full_states_do_not_fit(correction_table, bitflip_table, monkeypatch):
+    """The drop-in drivers default to a batch sized for the whole-cycle kernel (8 KiB per shot).  A program that needs
+    full 2 MiB states (here: coherent over-rotations) makes the first allocation fail; the driver shrinks the batch and
+    carries on instead of surfacing the error."""
+    import surface_17_iqt_b200.calc_log_e_rate_arbitrary_error_model as drv
+    monkeypatch.setattr(drv, "BATCH_SHOTS", 262144)
+    monkeypatch.setattr(drv, "VERBOSE", False)
+    drv.release()
+    p_set = [[0.02] * 30, [0.02] * 24, [5e-3] * 24]
+    rate, failed, counted, not0 = drv.calculate_log_e_rate_true_probability(
+        2000, correction_table, "coherent_model", p_set, bitflip_table,
+        over_angles={"eps_1q": [0.02] * 30, "eps_2q": [0.02] * 24})
+    assert counted == 2000 and 0 <= failed <= counted
+    assert drv.BATCH_SHOTS == 262144 // 16
+    drv.release()
