@@ -316,16 +316,21 @@ constexpr int kPlanMaxInstr = 640;
 __global__ void __launch_bounds__(kPlanThreads)
 k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, NoiseDev nd, const double *__restrict__ probs,
        uint32_t *__restrict__ ev, uint32_t *__restrict__ masks, uint32_t *__restrict__ leak,
-       const uint8_t *__restrict__ active, uint32_t *__restrict__ frm, uint32_t *__restrict__ n_act)
+       const uint8_t *__restrict__ active, uint32_t *__restrict__ frm, uint32_t *__restrict__ n_act,
+       const uint32_t *__restrict__ hot)
 {
     __shared__ uint32_t s_mask[kPlanThreads / 32][32][kPlanRow], s_ev[kPlanThreads / 32][32][kPlanRow];
     __shared__ uint32_t s_prog[kPlanMaxInstr * 3];     // the program of this cycle (slots resolved to absolute bit indices)
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int shot = blockIdx.x * blockDim.x + threadIdx.x, shot0 = shot - lane;
     if (shot == 0) *n_act = 0;                         // k_compact, next in the stream, appends to an empty list
+    // one word per instruction for the common case (an entry that does not fire): bits 0-15 absolute slot, bit 16
+    // in_skip, bit 17 entry (S17_P_ERR / S17_P_IDLE); stored behind the two program variants
+    __shared__ uint32_t s_hot[kPlanMaxInstr];
     {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(prog);
         for (int i = threadIdx.x; i < pa.n_instr * 3; i += blockDim.x) s_prog[i] = src[i];
+        for (int i = threadIdx.x; i < pa.n_instr; i += blockDim.x) s_hot[i] = hot[i];
         __syncthreads();
     }
     const bool act = shot < pa.n_shots && active[shot];
@@ -353,12 +358,12 @@ k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, NoiseDev nd, const doub
     for (int i = 24; i < (int)S17_EV_WORDS; ++i) evs[i] = 0;
     uint32_t w = 0, skip = 0;
     for (int i = 0; i < pa.n_instr; ++i) {
-        const s17_pinstr in = reinterpret_cast<const s17_pinstr *>(s_prog)[i];
-        if (in.kind == S17_P_ERR || in.kind == S17_P_IDLE) {
-            // one Bernoulli draw per entry (CS:198), none inside a skipped Rxx block.  in.slot is the absolute index of
-            // the entry's slot in this cycle (list offset + slot + half the list in a second cycle, CS:191-193).
-            if ((in.in_skip && skip) || pa.noiseless) continue;
-            const uint32_t bit = in.slot;
+        const uint32_t hw = s_hot[i];
+        if (hw & 0x20000u) {
+            // one Bernoulli draw per entry (CS:198), none inside a skipped Rxx block.  The slot is the absolute index of
+            // the entry in this cycle (list offset + slot + half the list in a second cycle, CS:191-193).
+            if ((((hw >> 16) & 1u) & skip) || pa.noiseless) continue;
+            const uint32_t bit = hw & 0xFFFFu;
             bool fire;
             if (prob_mode) {
                 fire = rng.next() < probs[bit];
@@ -368,6 +373,7 @@ k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, NoiseDev nd, const doub
             }
             if (!fire) continue;
         }
+        const s17_pinstr in = reinterpret_cast<const s17_pinstr *>(s_prog)[i];
         if (in.kind == S17_P_OP_BEGIN) { w = 0; skip = 0; continue; }
         if (in.kind == S17_P_SKIP_TEST) {
             // evaluated AFTER the errors of a preceding Ry (which may just have leaked the data qubit)
@@ -918,6 +924,7 @@ struct s17_ctx {
     s17_record *rec = nullptr;
     unsigned long long *counters = nullptr;
     s17_pinstr *plan = nullptr;
+    uint32_t *plan_hot = nullptr;
     RtfSlot *rtf_slots = nullptr;
     uint32_t *rtf_rounds = nullptr, *rtf_syndb = nullptr;
     uint64_t rtf_capacity = 0;
@@ -1127,7 +1134,7 @@ extern "C" int s17_destroy(s17_ctx *ctx) {
     void *ptrs[] = {ctx->state, ctx->ev, ctx->masks, ctx->leak, ctx->active, ctx->ready, ctx->forced, ctx->hist,
                     ctx->aux, ctx->rec, ctx->counters, ctx->lut, ctx->cw16, ctx->probs, ctx->cum, ctx->plan,
                     ctx->rtf_slots, ctx->rtf_rounds, ctx->rtf_syndb, ctx->act_list, ctx->n_act, ctx->zero_page, ctx->meas_out,
-                    ctx->frm, ctx->dsamp, ctx->prep_leaf, ctx->prep_blocks, ctx->prep_pp};
+                    ctx->frm, ctx->dsamp, ctx->prep_leaf, ctx->prep_blocks, ctx->prep_pp, ctx->plan_hot};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
@@ -1686,9 +1693,17 @@ extern "C" int s17_load_program(s17_ctx *ctx, const s17_layer *layers, const uin
                 }
                 res[(size_t)c2 * n_plan + i] = in;
             }
+        std::vector<uint32_t> hot(res.size());
+        for (size_t i = 0; i < res.size(); ++i) {
+            const bool entry = res[i].kind == S17_P_ERR || res[i].kind == S17_P_IDLE;
+            hot[i] = entry ? ((uint32_t)res[i].slot | ((uint32_t)(res[i].in_skip ? 1u : 0u) << 16) | 0x20000u) : 0u;
+        }
         if (ctx->plan) { cudaFree(ctx->plan); ctx->plan = nullptr; }
+        if (ctx->plan_hot) { cudaFree(ctx->plan_hot); ctx->plan_hot = nullptr; }
         CK(cudaMalloc(&ctx->plan, res.size() * sizeof(s17_pinstr)));
         CK(cudaMemcpy(ctx->plan, res.data(), res.size() * sizeof(s17_pinstr), cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&ctx->plan_hot, hot.size() * 4));
+        CK(cudaMemcpy(ctx->plan_hot, hot.data(), hot.size() * 4, cudaMemcpyHostToDevice));
     }
     CK(cudaMemset(ctx->probs, 0, 2048 * sizeof(double)));
     ctx->prep_basis = -1;
@@ -1925,7 +1940,8 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
     {
         SCOPE(CAT_OTHER);
         k_plan<<<blocks_for(n, kPlanThreads), kPlanThreads, 0, ctx->stream>>>(ctx->plan + (second ? ctx->n_plan : 0), pa, ctx->nd, ctx->probs, ctx->ev, ctx->masks,
-                                                            ctx->leak, ctx->active, ctx->frm, ctx->n_act);
+                                                            ctx->leak, ctx->active, ctx->frm, ctx->n_act,
+                                                                          ctx->plan_hot + (second ? ctx->n_plan : 0));
     }
     const int which = stage == 0 ? 0 : (second ? 2 : 1);
     const std::vector<LayerArg> &Ls = ctx->layers[which];
