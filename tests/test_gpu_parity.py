@@ -517,3 +517,29 @@ def test_driver_batch_shrinks_when_full_states_do_not_fit(correction_table, bitf
     assert counted == 2000 and 0 <= failed <= counted
     assert drv.BATCH_SHOTS == 262144 // 16
     drv.release()
+
+
+@pytest.mark.parametrize("diag", ["1", "0"])
+def test_logical_one_preparation(error_models, correction_table, bitflip_table, diag, monkeypatch):
+    """state = 1 (All(X) | data before the preparation cycle, CS:103-104; dead in the reference's drivers, CL:274-281,
+    but part of logical_prep): sampled trajectories replay bit-exactly in the oracle, and a context alternates between
+    the two logical states (the memoised preparation cycle is rebuilt per basis state)."""
+    monkeypatch.setenv("S17_DIAG", diag)
+    model, locs, eset, n = "PDD_model", [24, 36, 48, 156, 48], [0, 1, 1, 2, 0], 48
+    sim = make_sim(error_models, correction_table, bitflip_table, model, locs, n, 2)
+    orc = so.ShotOracle(error_models, correction_table, bitflip_table)
+    for state in (1, 0, 1):
+        sim.backend.set_subset([0] * 5, locs)
+        c = sim.backend.run("s1", n, L.NOISE_SUBSET, seed=21 + state, logical_state=state)
+        assert (c.failed, c.not0, c.counted, c.errors) == (0, 0, n, 0)
+        assert all(r["logical_meas"] == state for r in sim.backend.records(n))
+        sim.backend.set_subset(eset, locs)
+        c = sim.backend.run("s2", n, L.NOISE_SUBSET, seed=5 + state, first_shot_id=9, logical_state=state)
+        recs, masks = sim.backend.records(n), sim.backend.masks(n)
+        for i in range(n):
+            ref = orc.run_shot(model, sim.backend.split_mask(masks[i, 0]), "s2", rnd=random.Random(0),
+                               meas=so.ForcedMeasure(recs[i]["outcomes"]), state=state)
+            for f in FIELDS:
+                assert recs[i].get(f) == ref.get(f), (state, i, f, recs[i].get(f), ref.get(f))
+        assert c.failed == sum(r["fail"] for r in recs)
+    sim.close()
