@@ -350,9 +350,9 @@ def run_gpu(args):
             "roofline": {"bound": "hbm", "kernel": "k_cycle1", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                          # dram__bytes_read+write of one ncu --set full capture of this kernel, scaled to this run's
-                         # average launch: 2.114 GB measured for 2.147 GB algorithmic at 131072 shots
-                         # (profiles/r1n_k_cycle1_ncu_full.csv)
-                         "traffic": (sweep_bytes / max(1, gate_launches)) * (2.1137 / 2.1475),
+                         # average launch: 1.834 GB measured for 1.870 GB algorithmic (second noisy cycle of a
+                         # 131072-shot batch, profiles/r1t_k_cycle1_ncu_full.csv / r1t_k_cycle1_summary.md)
+                         "traffic": (sweep_bytes / max(1, gate_launches)) * (1.834 / 1.870),
                          "note": "one launch = one noisy stabiliser cycle of every active shot: 8 KiB read + 8 KiB written "
                                  "per shot, everything else in registers / shared memory (the noiseless preparation cycle is "
                                  "memoised: k_prep); ncu: FP64 pipe 42-47 %, shared-memory wavefronts 45-51 %, issue slots "
