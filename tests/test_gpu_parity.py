@@ -543,3 +543,37 @@ def test_logical_one_preparation(error_models, correction_table, bitflip_table, 
                 assert recs[i].get(f) == ref.get(f), (state, i, f, recs[i].get(f), ref.get(f))
         assert c.failed == sum(r["fail"] for r in recs)
     sim.close()
+
+
+def test_compact_then_full_state_allocation(error_models, correction_table, bitflip_table):
+    """A context that has only run the whole-cycle kernel keeps 8 KiB per shot; a later call that needs full states
+    (materialised collapse + correction for a parity read-back) re-allocates and gives the same trajectories."""
+    locs = [24, 36, 48, 156, 48]
+    n = 64
+    sim = make_sim(error_models, correction_table, bitflip_table, "PDD_model", locs, n, 2)
+    sim.backend.set_subset([0, 1, 1, 2, 1], locs)
+    c1 = sim.backend.run("s2", n, L.NOISE_SUBSET, seed=8)
+    recs1, masks = sim.backend.records(n), sim.backend.masks(n)
+    compact = [sim.backend.state(i) for i in range(4)]
+    assert all(np.sum(np.abs(v[512:]) ** 2) == 0.0 for v in compact)
+    sim.backend.set_replay([list(masks[i, 0]) for i in range(n)], [r["outcomes"] for r in recs1])
+    c2 = sim.backend.run("s2", n, L.NOISE_REPLAY, forced=True, materialize=True)
+    recs2 = sim.backend.records(n)
+    assert (c1.failed, c1.not0, c1.counted) == (c2.failed, c2.not0, c2.counted) and c2.errors == 0
+    for i in range(n):
+        for f in FIELDS + ("outcomes",):
+            assert recs1[i].get(f) == recs2[i].get(f), (i, f)
+    # the materialised state is the stored block with the decoder's correction applied
+    for i in range(4):
+        if not recs1[i]["counted"]:
+            continue
+        full = sim.backend.state(i)
+        x = sum(b << k for k, b in enumerate(recs1[i]["correction"][:9]))
+        z = sum(b << k for k, b in enumerate(recs1[i]["correction"][9:]))
+        idx = np.arange(512)
+        sign = (-1.0) ** np.array([bin(int(m) & z).count("1") for m in idx])
+        expect = np.zeros(512, dtype=complex)
+        expect[idx] = sign * compact[i][:512][idx ^ x]
+        err = min(np.max(np.abs(full[:512] - expect)), np.max(np.abs(full[:512] + expect)))
+        assert err < AMP_TOL and np.sum(np.abs(full[512:]) ** 2) < 1e-20
+    sim.close()
