@@ -643,18 +643,25 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ MeasArgs m
             const double target = __shfl_sync(0xffffffffu, uu, 8) * __shfl_sync(0xffffffffu, incl, 31);
             const uint32_t hit = __ballot_sync(0xffffffffu, target < incl);
             const int sel = hit ? (__ffs(hit) - 1) : 31;
-            if (lane == sel) {
-                double cum = incl - mine;
-                int pick = -1, last_pos = 0;
+            // every lane walks its own sixteen weights, branch-free: pick = number of running sums <= target, starting
+            // from the previous lane's total (<= target for the selected lane).  A state of weight zero repeats the
+            // running sum before it, so it is counted past, never selected; only rounding at the very end can run off
+            // the list, then the last state of positive weight is taken.
+            double cum = __shfl_up_sync(0xffffffffu, incl, 1);
+            if (lane == 0) cum = 0.0;
+            int pick = 0, last_pos = 0;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    cum += wsum[i];
-                    if (wsum[i] > 0.0) last_pos = i;
-                    if (pick < 0 && target < cum && wsum[i] > 0.0) pick = i;
-                }
-                if (pick < 0) pick = last_pos;        // rounding guard: never select an empty state
-                dsamp[shot] = (((linA ^ P.mapA.lin16[pick]) >> 4) ^ perm) & 511u;
+            for (int i = 0; i < 16; ++i) {
+                cum += wsum[i];
+                pick += (cum <= target) ? 1 : 0;
+                last_pos = wsum[i] > 0.0 ? i : last_pos;
             }
+            pick = pick > 15 ? last_pos : pick;
+            uint32_t lab = 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) lab = (i == pick) ? ((linA ^ P.mapA.lin16[i]) >> 4) : lab;
+            lab = __shfl_sync(0xffffffffu, lab, sel);
+            if (lane == 0) dsamp[shot] = (lab ^ perm) & 511u;
         }
 
         // renormalise once, stage the block in label order (data flips of the computational-frame half relabel it) and
