@@ -177,6 +177,22 @@ int s17_device_count(void);
 int s17_load_program(s17_ctx *ctx, const s17_layer *layers, const uint32_t n_layers[3],
                      const double *params_cos_sin, uint32_t n_params,
                      const s17_pinstr *plan, uint32_t n_plan, const s17_lists *lists);
+/* Which kernels the host lowering selects for a compiled program, per cycle kind (0 preparation, 1 stab_ind=0,
+ * 2 stab_ind=1), and the label maps of the whole-cycle kernel.  Host-only (no device needed): the same code path
+ * s17_load_program runs before it uploads anything. */
+typedef struct {
+    uint32_t n_sweeps[3];
+    uint8_t half_kernel[3];         /* 1: the fused half-cycle kernel (k_half) applies */
+    uint8_t cycle_kernel[3];        /* 1: the whole-cycle diagonal-frame kernel (k_cycle) applies */
+    uint8_t cycle_kernel_maps[3];   /* 1: label maps with one register bit per ancilla slot exist (k_cycle1) */
+    uint8_t shuffle_bit[3];         /* data bit transformed by the shuffle stage of the Walsh-Hadamard transform */
+    uint8_t reg_bits_z[3][4];       /* data bits carried by the register index in the computational frame; slot k uses [k] */
+    uint8_t reg_bits_x[3][4];       /* ... in the Hadamard frame */
+    uint8_t table_entries[3][2];    /* table entries per half cycle */
+    uint8_t slot_ancilla[3][2][4];  /* ancilla index measured by slot k of half h */
+} s17_program_info;
+int s17_describe_program(const s17_layer *layers, const uint32_t n_layers[3], const double *params_cos_sin,
+                         uint32_t n_params, const s17_pinstr *plan, uint32_t n_plan, s17_program_info *out);
 /* decoder tables: lookup (CS:886-892) and return_weight_classical_lookup (CS:895-898) */
 int s17_load_tables(s17_ctx *ctx, const uint32_t *lut256, const uint8_t *classical_weight16);
 /* true-probability mode: the lists instantiate_error_model binds (CS:31-49) */

@@ -68,10 +68,17 @@ class Record(C.Structure):
                 ("data_meas", C.c_uint16), ("partial", C.c_uint16), ("outcomes", C.c_uint8 * MAX_OUTCOMES)]
 
 
+class ProgramInfo(C.Structure):
+    _fields_ = [("n_sweeps", C.c_uint32 * 3), ("half_kernel", C.c_uint8 * 3), ("cycle_kernel", C.c_uint8 * 3),
+                ("cycle_kernel_maps", C.c_uint8 * 3), ("shuffle_bit", C.c_uint8 * 3), ("reg_bits_z", (C.c_uint8 * 4) * 3),
+                ("reg_bits_x", (C.c_uint8 * 4) * 3), ("table_entries", (C.c_uint8 * 2) * 3),
+                ("slot_ancilla", ((C.c_uint8 * 4) * 2) * 3)]
+
+
 assert C.sizeof(Uop) == 8 and C.sizeof(Op) == 72 and C.sizeof(Layer) == 1160
 assert C.sizeof(PInstr) == 12 and C.sizeof(Record) == 60 and C.sizeof(RunArgs) == 64
 
-EXPORTS = ("s17_create", "s17_destroy", "s17_last_error", "s17_device_count", "s17_load_program",
+EXPORTS = ("s17_create", "s17_destroy", "s17_last_error", "s17_device_count", "s17_load_program", "s17_describe_program",
            "s17_load_tables", "s17_set_slot_probs", "s17_set_subset", "s17_set_replay", "s17_run",
            "s17_read_records", "s17_read_masks", "s17_read_events", "s17_read_state", "s17_read_rtf", "s17_last_timing")
 
@@ -99,6 +106,8 @@ def load():
     L.s17_device_count.argtypes = []
     L.s17_load_program.argtypes = [vp, C.POINTER(Layer), C.POINTER(u32), C.POINTER(C.c_double), u32,
                                    C.POINTER(PInstr), u32, C.POINTER(Lists)]
+    L.s17_describe_program.argtypes = [C.POINTER(Layer), C.POINTER(u32), C.POINTER(C.c_double), u32, C.POINTER(PInstr), u32,
+                                       C.POINTER(ProgramInfo)]
     L.s17_load_tables.argtypes = [vp, C.POINTER(u32), C.POINTER(C.c_uint8)]
     L.s17_set_slot_probs.argtypes = [vp, u32, C.POINTER(C.c_double), u32]
     L.s17_set_subset.argtypes = [vp, u32, C.POINTER(u32), C.POINTER(u32), C.POINTER(C.POINTER(C.c_double))]

@@ -40,6 +40,31 @@ def pack_bitflip_table(table):
     return w
 
 
+def describe_program(prog):
+    """Which kernels the library's host lowering selects for `prog` (circuit.Program), per cycle kind, and the label
+    maps of the whole-cycle kernel.  Needs no GPU (s17_describe_program)."""
+    lib = L.load()
+    flat = [lay for cyc in prog.layers for lay in cyc]
+    layers = (L.Layer * len(flat))(*flat)
+    counts = (C.c_uint32 * 3)(*[len(cyc) for cyc in prog.layers])
+    params = (C.c_double * max(1, len(prog.params)))(*prog.params)
+    plan = (L.PInstr * len(prog.plan))(*prog.plan)
+    info = L.ProgramInfo()
+    rc = lib.s17_describe_program(layers, counts, params, len(prog.params) // 2, plan, len(plan), C.byref(info))
+    if rc != 0:
+        raise L.S17Error(lib.s17_last_error(None).decode())
+    out = []
+    for c, name in enumerate(("preparation", "stab_ind=0", "stab_ind=1")):
+        out.append({
+            "cycle": name, "sweeps": int(info.n_sweeps[c]), "k_half": bool(info.half_kernel[c]),
+            "k_cycle": bool(info.cycle_kernel[c]), "k_cycle1": bool(info.cycle_kernel_maps[c]),
+            "shuffle_bit": int(info.shuffle_bit[c]),
+            "reg_bits_z": [int(v) for v in info.reg_bits_z[c]], "reg_bits_x": [int(v) for v in info.reg_bits_x[c]],
+            "table_entries": [int(v) for v in info.table_entries[c]],
+            "slot_ancilla": [[int(v) for v in info.slot_ancilla[c][h]] for h in range(2)]})
+    return out
+
+
 def bits_to_list(value, n):
     return [(int(value) >> i) & 1 for i in range(n)]
 

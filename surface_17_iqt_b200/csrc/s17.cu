@@ -1592,12 +1592,10 @@ static bool make_diag1(const DiagProg &G, DiagProg1 &P1) {
     return false;
 }
 
-extern "C" int s17_load_program(s17_ctx *ctx, const s17_layer *layers, const uint32_t n_layers[3], const double *params,
-                                uint32_t n_params, const s17_pinstr *plan, uint32_t n_plan, const s17_lists *lists) {
-    if (!ctx || !layers || !n_layers || !plan || !lists) return fail(ctx, S17_E_ARG, "s17_load_program: bad arguments");
-    if (!n_layers[0] || !n_layers[1] || !n_layers[2]) return fail(ctx, S17_E_ARG, "s17_load_program: empty sweep list");
-    if (lists->n_lists > S17_MAX_LISTS) return fail(ctx, S17_E_ARG, "too many probability lists");
-    CK(cudaSetDevice(ctx->device));
+// Host-only lowering of the compiled cycle: per-sweep constants, the fused half-cycle form, the diagonal-frame form and
+// its label maps.  No CUDA call: s17_describe_program runs it without a device.
+static int lower_program(s17_ctx *ctx, const s17_layer *layers, const uint32_t n_layers[3], const double *params,
+                         uint32_t n_params, const s17_pinstr *plan, uint32_t n_plan) {
     const s17_layer *src = layers;
     for (int c = 0; c < 3; ++c) {
         ctx->layers[c].clear();
@@ -1660,6 +1658,16 @@ extern "C" int s17_load_program(s17_ctx *ctx, const s17_layer *layers, const uin
             ctx->diag1_ok[c] = ctx->diag_ok[c] && make_diag1(ctx->diag_prog[c], ctx->diag_prog1[c]);
         }
     }
+    return S17_OK;
+}
+
+extern "C" int s17_load_program(s17_ctx *ctx, const s17_layer *layers, const uint32_t n_layers[3], const double *params,
+                                uint32_t n_params, const s17_pinstr *plan, uint32_t n_plan, const s17_lists *lists) {
+    if (!ctx || !layers || !n_layers || !plan || !lists) return fail(ctx, S17_E_ARG, "s17_load_program: bad arguments");
+    if (!n_layers[0] || !n_layers[1] || !n_layers[2]) return fail(ctx, S17_E_ARG, "s17_load_program: empty sweep list");
+    if (lists->n_lists > S17_MAX_LISTS) return fail(ctx, S17_E_ARG, "too many probability lists");
+    CK(cudaSetDevice(ctx->device));
+    if (int rc = lower_program(ctx, layers, n_layers, params, n_params, plan, n_plan)) return rc;
     if (n_plan > (uint32_t)kPlanMaxInstr) return fail(ctx, S17_E_ARG, "injection program too long");
     ctx->n_plan = (int)n_plan;
     memset(&ctx->nd, 0, sizeof(ctx->nd));
@@ -1711,6 +1719,32 @@ extern "C" int s17_load_program(s17_ctx *ctx, const s17_layer *layers, const uin
     for (uint32_t i = 0; i < n_plan; ++i)
         if (plan[i].kind == S17_P_ERR && (plan[i].err == S17_ERR_LEAK_A || plan[i].err == S17_ERR_LEAK_AB)) ctx->plan_has_leak = true;
     ctx->have_program = true;
+    return S17_OK;
+}
+
+extern "C" int s17_describe_program(const s17_layer *layers, const uint32_t n_layers[3], const double *params, uint32_t n_params,
+                                    const s17_pinstr *plan, uint32_t n_plan, s17_program_info *out) {
+    if (!layers || !n_layers || !plan || !out) return fail(nullptr, S17_E_ARG, "s17_describe_program: bad arguments");
+    if (!n_layers[0] || !n_layers[1] || !n_layers[2]) return fail(nullptr, S17_E_ARG, "s17_describe_program: empty sweep list");
+    s17_ctx *ctx = new s17_ctx();                      // host-side scratch only: no device, no stream
+    const int rc = lower_program(ctx, layers, n_layers, params, n_params, plan, n_plan);
+    if (rc) { g_err = ctx->err; delete ctx; return rc; }
+    memset(out, 0, sizeof(*out));
+    for (int c = 0; c < 3; ++c) {
+        out->n_sweeps[c] = (uint32_t)ctx->layers[c].size();
+        out->half_kernel[c] = ctx->half_ok[c] ? 1 : 0;
+        out->cycle_kernel[c] = ctx->diag_ok[c] ? 1 : 0;
+        out->cycle_kernel_maps[c] = ctx->diag1_ok[c] ? 1 : 0;
+        if (!ctx->diag1_ok[c]) continue;
+        const DiagProg1 &P = ctx->diag_prog1[c];
+        for (int j = 0; j < 4; ++j) { out->reg_bits_z[c][j] = P.mapA.reg[j]; out->reg_bits_x[c][j] = P.mapB.reg[j]; }
+        out->shuffle_bit[c] = P.mapA.lane[P.sh_lane_bit];
+        for (int h = 0; h < 2; ++h) {
+            out->table_entries[c][h] = P.h[h].n_entries;
+            for (int k = 0; k < 4; ++k) out->slot_ancilla[c][h][k] = P.h[h].aj[k];
+        }
+    }
+    delete ctx;
     return S17_OK;
 }
 

@@ -124,3 +124,31 @@ def test_product_never_imports_oracle():
     out = subprocess.run(["grep", "-rIl", "--include=*.py", "--include=*.cu", "--include=*.cuh", "-E",
                           r"(from|import) +oracle|oracle/", pkg], capture_output=True, text=True).stdout.strip()
     assert out == "", out
+
+
+def test_host_lowering_selects_the_whole_cycle_kernel(error_models):
+    """s17_describe_program (host only): the standard cycle gets the whole-cycle kernel with label maps in which every
+    ancilla slot indexes its table with exactly one register bit -- the unique assignment {0,3,5,8} / {1,2,6,7} with data
+    bit 4 left to the shuffle stage -- for the Pauli / leakage / cooling models, and only the noiseless preparation
+    cycle for the coherent model; without the early X-ancilla measurement there are no half cycles at all."""
+    from surface_17_iqt_b200 import backend
+    ops = circuit.build_cycle()
+    for model, cooling in (("PDD_model", False), ("Dress_model", False), ("depolarising_model", False),
+                           ("PDD_cooling", True), ("Dress_cooling", True)):
+        prog = circuit.compile_program(error_models[model], circuit.list_lengths(error_models[model]), fusion=2,
+                                       cooling=cooling, early_measure=True)
+        for info in backend.describe_program(prog):
+            assert info["k_half"] and info["k_cycle"] and info["k_cycle1"], (model, info)
+            assert sorted(info["reg_bits_z"]) == [0, 3, 5, 8] and sorted(info["reg_bits_x"]) == [1, 2, 6, 7]
+            assert info["shuffle_bit"] == 4 and info["table_entries"] == [40, 40]
+            for h, kind, regs in ((0, "x", info["reg_bits_x"]), (1, "z", info["reg_bits_z"])):
+                assert sorted(info["slot_ancilla"][h]) == sorted({o.ancilla for o in ops if o.kind == kind})
+                for k, anc in enumerate(info["slot_ancilla"][h]):
+                    data = {o.data for o in ops if o.kind == kind and o.ancilla == anc}
+                    assert data & set(regs) == {regs[k]}, (model, h, k, data, regs)      # slot k <-> register bit k
+    coherent = circuit.compile_program(error_models["coherent_model"], [30, 24, 24], fusion=2, early_measure=True,
+                                       over_angles={"eps_1q": [0.02] * 30, "eps_2q": [0.02] * 24})
+    info = backend.describe_program(coherent)
+    assert [i["k_cycle1"] for i in info] == [True, False, False]
+    late = circuit.compile_program(error_models["PDD_model"], [12, 18, 24, 78, 24], fusion=2, early_measure=False)
+    assert not any(i["k_half"] or i["k_cycle"] for i in backend.describe_program(late))
