@@ -577,3 +577,22 @@ def test_compact_then_full_state_allocation(error_models, correction_table, bitf
         err = min(np.max(np.abs(full[:512] - expect)), np.max(np.abs(full[:512] + expect)))
         assert err < AMP_TOL and np.sum(np.abs(full[512:]) ** 2) < 1e-20
     sim.close()
+
+
+def test_sampled_rates_against_reference_statistics(error_models, correction_table, bitflip_table, golden):
+    """Sampled s2 rates (not0 / runs and failed / not0) against the UNMODIFIED reference drivers run on the projectq
+    stand-in (tests/golden/stats_s2.json, oracle/make_golden_stats.py, 4000 shots per subset): within 3.5 binomial
+    sigma of the reference sample (the GPU sample of 2^20 shots adds < 2 % to the variance)."""
+    n = 1 << 20
+    for st in golden("stats_s2.json")["stats"]:
+        sim = make_sim(error_models, correction_table, bitflip_table, st["model"], st["locations"], n, 2)
+        sim.backend.set_subset(st["eset"], st["locations"])
+        c = sim.backend.run("s2", n, L.NOISE_SUBSET, seed=20260101)
+        sim.close()
+        assert c.errors == 0
+        p_ref, p_gpu = st["not0"] / st["runs"], c.not0 / n
+        sig = np.sqrt(max(p_ref * (1 - p_ref), 1e-6) / st["runs"] + p_gpu * (1 - p_gpu) / n)
+        assert abs(p_gpu - p_ref) < 3.5 * sig, (st["eset"], "not0", p_gpu, p_ref, sig)
+        f_ref, f_gpu = st["failed"] / max(1, st["not0"]), c.failed / max(1, c.not0)
+        sig = np.sqrt(max(f_ref * (1 - f_ref), 1e-6) / max(1, st["not0"]) + f_gpu * (1 - f_gpu) / max(1, c.not0))
+        assert abs(f_gpu - f_ref) < 3.5 * sig, (st["eset"], "failed", f_gpu, f_ref, sig)

@@ -101,3 +101,19 @@ def test_placement_routines():
     assert so.generate_error_locations_non_uniform(1, 10, w, rnd)[7] == 1
     with pytest.raises(ValueError):
         so.generate_error_locations(5, 4, rnd)
+
+
+def test_oracle_sampling_agrees_with_reference_statistics(oracle, golden):
+    """The oracle's own sampled s2 counters against 4000 shots of the unmodified reference driver on the projectq
+    stand-in (oracle/make_golden_stats.py): within 3.5 binomial sigma."""
+    import random
+    import numpy as np
+    from oracle import s17_oracle as so
+    st = golden("stats_s2.json")["stats"][0]
+    m = 200
+    failed, not0 = so.run_subset(oracle, "s2", m, st["model"], st["eset"], st["locations"], st["prob_lists"],
+                                 rnd=random.Random(3), meas_rng=random.Random(4))
+    p_ref, p = st["not0"] / st["runs"], not0 / m
+    assert abs(p - p_ref) < 3.5 * np.sqrt(p_ref * (1 - p_ref) * (1 / st["runs"] + 1 / m))
+    f_ref, f = st["failed"] / st["not0"], failed / max(1, not0)
+    assert abs(f - f_ref) < 3.5 * np.sqrt(f_ref * (1 - f_ref) * (1 / st["not0"] + 1 / max(1, not0)))
