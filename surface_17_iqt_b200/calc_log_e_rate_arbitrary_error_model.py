@@ -31,6 +31,7 @@ DEVICE = None                                             # None: LOCAL_RANK or 
 VERBOSE = True                                            # print the reference's summary lines
 
 _SIMS = {}
+_BATCH_OF = {}          # program key -> batch that fits (set when BATCH_SHOTS full-size states did not)
 LAST_TIMING = {}
 
 
@@ -44,17 +45,20 @@ def _device():
 
 
 def _simulation(model, list_len, cooling, correction_table, bitflip_table, over_angles=None):
-    key = (model, tuple(list_len), bool(cooling), FUSION, _device(), BATCH_SHOTS,
-           None if over_angles is None else json.dumps(over_angles, sort_keys=True))
+    pkey = (model, tuple(list_len), bool(cooling), FUSION,
+            None if over_angles is None else json.dumps(over_angles, sort_keys=True))
+    batch = _BATCH_OF.get(pkey, BATCH_SHOTS)
+    key = (model, tuple(list_len), bool(cooling), FUSION, _device(), batch, pkey[4])
     sim = _SIMS.get(key)
     if sim is None:
         for k in list(_SIMS):            # one resident context per device: free the previous program's state
             if k[4] == _device():
                 _SIMS.pop(k).close()
-        sim = api.Simulation(model, list_len, BATCH_SHOTS, correction_table, bitflip_table, fusion=FUSION,
+        sim = api.Simulation(model, list_len, batch, correction_table, bitflip_table, fusion=FUSION,
                              cooling=cooling, device=_device(), over_angles=over_angles)
         _SIMS[key] = sim
         sim._tables = (correction_table, bitflip_table)
+        sim._pkey = pkey
     elif sim._tables[0] is not correction_table or sim._tables[1] is not bitflip_table:
         sim.backend.load_tables(correction_table, bitflip_table)      # other table objects than last time: re-pack
         sim._tables = (correction_table, bitflip_table)
@@ -62,18 +66,25 @@ def _simulation(model, list_len, cooling, correction_table, bitflip_table, over_
 
 
 def _with_batch_retry(fn):
-    """Run fn(); if the device cannot hold BATCH_SHOTS state vectors of the size this program needs (2 MiB per shot on
-    the general amplitude kernels), drop the context, cut the batch to a sixteenth and try again."""
-    global BATCH_SHOTS
+    """Run fn(); if the device cannot hold a batch of state vectors of the size this program needs (2 MiB per shot on
+    the general amplitude kernels instead of 8 KiB), drop the context, cut the batch of THIS program to a sixteenth and
+    try again."""
     while True:
         try:
             return fn()
         except L.S17Error as exc:
-            if "out of device memory" not in str(exc) or BATCH_SHOTS <= 256:
+            if "out of device memory" not in str(exc):
                 raise
-            release()
-            BATCH_SHOTS = max(256, BATCH_SHOTS // 16)
-            _log("device memory: batch reduced to {} shots".format(BATCH_SHOTS))
+            shrunk = False
+            for k in list(_SIMS):
+                sim = _SIMS.pop(k)
+                if sim.max_shots > 256:
+                    _BATCH_OF[sim._pkey] = max(256, sim.max_shots // 16)
+                    shrunk = True
+                    _log("device memory: batch of {} reduced to {} shots".format(sim.model_name, _BATCH_OF[sim._pkey]))
+                sim.close()
+            if not shrunk:
+                raise
 
 
 def release():
@@ -138,7 +149,7 @@ def _run_subset_once(protocol, num_runs, correction_table, model, eset, location
     sweeps = launches = sweep_bytes = 0
     done = 0
     while done < count:
-        n = min(BATCH_SHOTS, count - done)
+        n = min(sim.max_shots, count - done)
         c = sim.backend.run(protocol, n, L.NOISE_SUBSET, seed=seed, first_shot_id=first + done)
         if c.errors:
             raise L.S17Error("{} shots hit a zero-probability outcome".format(c.errors))
@@ -232,7 +243,7 @@ def _true_probability_once(num_runs, correction_table, model, p_set, bitflip_tab
     first, count = distributed.shard_range(num_runs, rank, world_size)
     failed = not0 = counted = done = 0
     while done < count:
-        n = min(BATCH_SHOTS, count - done)
+        n = min(sim.max_shots, count - done)
         c = sim.backend.run(protocol, n, L.NOISE_PROB, seed=seed, first_shot_id=first + done)
         failed, not0, counted, done = failed + c.failed, not0 + c.not0, counted + c.counted, done + n
     failed, not0, counted = distributed.allreduce_counts([failed, not0, counted])
@@ -281,7 +292,7 @@ def calculate_log_e_rate(num_runs, filename, correction_table, e_model, e_probs,
     def run_once():
         sim_ = _simulation(model_name, [len(p) for p in p_set], False, correction_table, bitflip_table)
         sim_.backend.set_slot_probs(p_set)
-        return sim_, sim_.backend.run("rtf", min(BATCH_SHOTS, num_runs), L.NOISE_PROB, seed=seed, rtf_runs=num_runs)
+        return sim_, sim_.backend.run("rtf", min(sim_.max_shots, num_runs), L.NOISE_PROB, seed=seed, rtf_runs=num_runs)
 
     sim, c = _with_batch_retry(run_once)
     rounds, syndb = sim.backend.rtf_results(num_runs)

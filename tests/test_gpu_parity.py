@@ -515,8 +515,10 @@ def test_driver_batch_shrinks_when_full_states_do_not_fit(correction_table, bitf
         2000, correction_table, "coherent_model", p_set, bitflip_table,
         over_angles={"eps_1q": [0.02] * 30, "eps_2q": [0.02] * 24})
     assert counted == 2000 and 0 <= failed <= counted
-    assert drv.BATCH_SHOTS == 262144 // 16
+    assert drv.BATCH_SHOTS == 262144                         # the shrink is per program, not global
+    assert [v for k, v in drv._BATCH_OF.items() if k[0] == "coherent_model"] == [262144 // 16]
     drv.release()
+    drv._BATCH_OF.clear()
 
 
 @pytest.mark.parametrize("diag", ["1", "0"])
