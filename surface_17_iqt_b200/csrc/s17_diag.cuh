@@ -489,7 +489,7 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ MeasArgs m
     }
 
     auto prefetch = [&](uint32_t entry, int sb) {
-        const uint32_t shot_ = entry & 0xFFFFFFu;
+        const uint32_t shot_ = alt_src ? (entry & 0xFFFFFFu) : entry;     // plain shot index unless a leaf rides in bits 24-31
         unsigned char *m = meta + sb * kDgMetaBytes;
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the bulk store staged in this buffer has left it
         fence_proxy_async_smem();                 // the buffers were last touched through the generic proxy
@@ -518,7 +518,7 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ MeasArgs m
     uint32_t j = 0;
     for (uint32_t item = first; item < last; ++item, ++j) {
         const int sb = (int)(j & 1u);
-        const uint32_t shot = entry & 0xFFFFFFu;
+        const uint32_t shot = alt_src ? (entry & 0xFFFFFFu) : entry;
         uint32_t entry1 = 0;
         if (item + 1 < last) {
             entry1 = act_list[item + 1];

@@ -598,3 +598,31 @@ def test_sampled_rates_against_reference_statistics(error_models, correction_tab
         f_ref, f_gpu = st["failed"] / max(1, st["not0"]), c.failed / max(1, c.not0)
         sig = np.sqrt(max(f_ref * (1 - f_ref), 1e-6) / max(1, st["not0"]) + f_gpu * (1 - f_gpu) / max(1, c.not0))
         assert abs(f_gpu - f_ref) < 3.5 * sig, (st["eset"], "failed", f_gpu, f_ref, sig)
+
+
+@pytest.mark.parametrize("diag", ["1", "g", "0"])
+def test_impossible_forced_outcome_is_reported(error_models, correction_table, bitflip_table, diag, monkeypatch):
+    """A replay that forces an outcome of probability zero (a z-type ancilla reading 1 in the noiseless preparation
+    cycle; a flipped x-type ancilla in a noiseless second cycle) is counted in `errors` and flagged in the record on
+    every path (memoised preparation, whole-cycle kernels, half-cycle kernel) instead of yielding a garbage state."""
+    monkeypatch.setenv("S17_DIAG", diag)
+    locs = [12, 18, 24, 78, 24]
+    n = 8
+    sim = make_sim(error_models, correction_table, bitflip_table, "PDD_model", locs, n, 2)
+    zero = [0] * sum(locs)
+    good = [0, 1, 0, 0, 1, 0, 1, 0]
+    outs = []
+    for i in range(n):
+        o = good + good + [0] * 9
+        if i % 4 == 1:
+            o[0] = 1                      # z-type ancilla 0 cannot read 1 after a noiseless preparation
+        if i % 4 == 2:
+            o[8 + 1] = 0                  # x-type ancilla 1 must repeat its quiescent outcome
+        outs.append(o)
+    sim.backend.set_replay([zero] * n, outs)
+    c = sim.backend.run("s1", n, L.NOISE_REPLAY, forced=True)
+    recs = sim.backend.records(n)
+    assert c.errors >= n // 2
+    for i in range(n):
+        assert bool(recs[i]["error"]) == (i % 4 in (1, 2)), (i, recs[i])
+    sim.close()
