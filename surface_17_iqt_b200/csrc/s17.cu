@@ -317,7 +317,8 @@ __global__ void __launch_bounds__(kPlanThreads)
 k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, NoiseDev nd, const double *__restrict__ probs,
        uint32_t *__restrict__ ev, uint32_t *__restrict__ masks, uint32_t *__restrict__ leak,
        const uint8_t *__restrict__ active, uint32_t *__restrict__ frm, uint32_t *__restrict__ n_act,
-       const uint32_t *__restrict__ hot)
+       const uint32_t *__restrict__ hot, uint8_t *__restrict__ quiet /* nullptr, or per shot: 1 = no entry fired and no
+       qubit is leaked in this cycle (event-free: k_quiet replays it from the cache) */)
 {
     __shared__ uint32_t s_mask[kPlanThreads / 32][32][kPlanRow], s_ev[kPlanThreads / 32][32][kPlanRow];
     __shared__ uint32_t s_prog[kPlanMaxInstr * 3];     // the program of this cycle (slots resolved to absolute bit indices)
@@ -349,6 +350,7 @@ k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, NoiseDev nd, const doub
     uint32_t f_flip = 0, f_sign = 0, f_phase = 0, f_ancz = 0;   // frame bookkeeping of the current half cycle (k_cycle)
     int f_half = -1;
     if (act) lk = leak[shot];
+    bool any_event = lk != 0;
     if (act && pa.noiseless && lk == 0) {
         // noiseless preparation cycle without a leaked qubit: no event, no leak skip, identity frame
         for (int i = 0; i < (int)S17_EV_WORDS; ++i) evs[i] = 0;
@@ -372,6 +374,7 @@ k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, NoiseDev nd, const doub
                 fire = mask_get(mk, bit);
             }
             if (!fire) continue;
+            any_event = true;
         }
         const s17_pinstr in = reinterpret_cast<const s17_pinstr *>(s_prog)[i];
         if (in.kind == S17_P_OP_BEGIN) { w = 0; skip = 0; continue; }
@@ -461,6 +464,7 @@ k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, NoiseDev nd, const doub
     if (f_half >= 0) frm[(size_t)shot * 4 + f_half] = f_flip | (f_sign << 9) | ((f_phase & 3u) << 18) | (f_ancz << 20);
     leak[shot] = lk;
     }
+    if (quiet && act) quiet[shot] = any_event ? 0 : 1;
     __syncwarp();
     for (int r = 0; r < 32; ++r) {
         if (!((actmask >> r) & 1u)) continue;
@@ -685,10 +689,13 @@ k_pauli(double2 *__restrict__ state, const s17_record *__restrict__ rec, const u
 // must be zero on entry (k_plan clears it).
 __global__ void __launch_bounds__(256)
 k_compact(const uint8_t *__restrict__ active, int n, uint32_t *__restrict__ list, uint32_t *__restrict__ n_act,
-          const uint8_t *__restrict__ leaf /* nullptr, or per shot: byte for bits 24-31 of its entry (k_cycle1 + prep cache) */)
+          const uint8_t *__restrict__ leaf /* nullptr, or per shot: byte for bits 24-31 of its entry (k_cycle1 + prep cache) */,
+          const uint8_t *__restrict__ quiet, const uint8_t *__restrict__ quiet_ok /* nullptr, or: shots with quiet[i] and
+          quiet_ok[leaf[i]] are left out (k_quiet handles them) */)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
-    const bool flag = i < n && active[i];
+    bool flag = i < n && active[i];
+    if (flag && quiet && quiet[i] && quiet_ok[leaf[i]]) flag = false;
     const uint32_t ballot = __ballot_sync(0xffffffffu, flag);
     if (!ballot) return;
     uint32_t base = 0;
@@ -954,6 +961,11 @@ struct s17_ctx {
     uint8_t *prep_leaf = nullptr;
     int prep_basis = -1;              // basis index the cache was built for (-1: not built)
     bool no_prep_cache = false, plan_has_leak = false, use_prep = false;
+    // memoised event-free first cycle (k_quiet): per leaf the block k_cycle1 stores and its read-out weights
+    double2 *quiet_blocks = nullptr;
+    double *quiet_cdf = nullptr;
+    uint8_t *quiet_ok = nullptr, *quiet_flag = nullptr;
+    bool no_quiet = false, quiet_copy = true, use_quiet = false, any_quiet_leaf = false;
     PrepTree prep_tree;
     bool use_dsamp = false;
     bool no_fuse = false;
@@ -1080,6 +1092,11 @@ extern "C" int s17_create(s17_ctx **out, int device, uint64_t max_shots) {
     CK(cudaMalloc(&ctx->prep_leaf, B));
     CK(cudaMalloc(&ctx->prep_blocks, 256 * (size_t)kRunBytes));
     CK(cudaMalloc(&ctx->prep_pp, 2 * 255 * sizeof(double)));
+    CK(cudaMalloc(&ctx->quiet_blocks, 256 * (size_t)kRunBytes));
+    CK(cudaMalloc(&ctx->quiet_cdf, 256 * (size_t)kDgCdfDoubles * sizeof(double)));
+    CK(cudaMalloc(&ctx->quiet_ok, 256));
+    CK(cudaMemset(ctx->quiet_ok, 0, 256));
+    CK(cudaMalloc(&ctx->quiet_flag, B));
     CK(cudaMemset(ctx->frm, 0, B * 4 * 4));
     CK(cudaFuncSetAttribute(k_cycle, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDgSmem));
     CK(cudaFuncSetAttribute(k_cycle1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDgSmem1));
@@ -1107,6 +1124,10 @@ extern "C" int s17_create(s17_ctx **out, int device, uint64_t max_shots) {
         ctx->no_diag1 = nd && nd[0] == 'g';
         const char *pc = getenv("S17_PREP_CACHE");
         ctx->no_prep_cache = pc && pc[0] == '0';
+        const char *qc = getenv("S17_QUIET");            // 0: run event-free first cycles through k_cycle1 like any other
+        ctx->no_quiet = qc && qc[0] == '0';
+        const char *qcp = getenv("S17_QUIET_COPY");      // 0: do not copy the cached block into the shot's state
+        ctx->quiet_copy = !(qcp && qcp[0] == '0');
         const char *r = getenv("S17_RING");
         ctx->force_ring = r && r[0] == '1';
     }
@@ -1134,7 +1155,8 @@ extern "C" int s17_destroy(s17_ctx *ctx) {
     void *ptrs[] = {ctx->state, ctx->ev, ctx->masks, ctx->leak, ctx->active, ctx->ready, ctx->forced, ctx->hist,
                     ctx->aux, ctx->rec, ctx->counters, ctx->lut, ctx->cw16, ctx->probs, ctx->cum, ctx->plan,
                     ctx->rtf_slots, ctx->rtf_rounds, ctx->rtf_syndb, ctx->act_list, ctx->n_act, ctx->zero_page, ctx->meas_out,
-                    ctx->frm, ctx->dsamp, ctx->prep_leaf, ctx->prep_blocks, ctx->prep_pp, ctx->plan_hot};
+                    ctx->frm, ctx->dsamp, ctx->prep_leaf, ctx->prep_blocks, ctx->prep_pp, ctx->plan_hot,
+                    ctx->quiet_blocks, ctx->quiet_cdf, ctx->quiet_ok, ctx->quiet_flag};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
@@ -1907,7 +1929,7 @@ static int build_prep_cache(s17_ctx *ctx, int basis) {
     ma.stream = 16u;
     ma.n_shots = N;
     k_cycle1<<<ctx->num_sms, kDgThreads, kDgSmem1, ctx->stream>>>(P, ma, ctx->prep_blocks, (size_t)kRun, ev, frm, list, nact, aux,
-                                                                 forced, mo, ds, cnt, basis, nullptr, pp);
+                                                                 forced, mo, ds, cnt, basis, nullptr, pp, nullptr);
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());
     std::vector<double> h_pp((size_t)N * 16);
@@ -1921,6 +1943,47 @@ static int build_prep_cache(s17_ctx *ctx, int basis) {
             node[2 * (((1 << s) - 1) + prefix) + 1] = h_pp[(size_t)prefix * 16 + 2 * s + 1];
         }
     CK(cudaMemcpy(ctx->prep_pp, node.data(), node.size() * sizeof(double), cudaMemcpyHostToDevice));
+
+    // The event-free first cycle per leaf (k_quiet): run the first noisy cycle's program with no event word set on every
+    // reachable leaf, its outcomes forced to the leaf's own.  The leaf is memoised only if the kernel itself finds
+    // every other outcome to have probability exactly zero (then its decisions do not depend on the uniforms).
+    std::vector<uint8_t> quiet_ok(N, 0);
+    ctx->any_quiet_leaf = false;
+    if (ctx->diag1_ok[1]) {
+        std::vector<uint32_t> h_mo((size_t)N * 2);
+        CK(cudaMemcpy(h_mo.data(), mo, h_mo.size() * 4, cudaMemcpyDeviceToHost));
+        std::vector<uint8_t> reach(N, 0);
+        for (int L = 0; L < N; ++L) reach[L] = !((h_mo[2 * L] | h_mo[2 * L + 1]) & 0x100u);    // leaf was not impossible
+        for (int L = 0; L < N; ++L) {
+            h_list[L] = (uint32_t)L | ((uint32_t)L << 24);                                        // input block = leaf L
+            for (int s = 0; s < 8; ++s) h_forced[(size_t)L * S17_MAX_OUTCOMES + 8 + T.aj[s]] = (uint8_t)((L >> s) & 1);
+        }
+        CK(cudaMemcpy(list, h_list.data(), N * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(forced, h_forced.data(), h_forced.size(), cudaMemcpyHostToDevice));
+        double *cdf = ctx->quiet_cdf;
+        ma.stage = 1;
+        ma.stream = 16u + 4u;
+        ma.sample_data = 1;
+        ma.data_stream = 32u;
+        k_cycle1<<<ctx->num_sms, kDgThreads, kDgSmem1, ctx->stream>>>(ctx->diag_prog1[1], ma, ctx->quiet_blocks, (size_t)kRun, ev,
+                                                                     frm, list, nact, aux, forced, mo, ds, cnt, -1,
+                                                                     ctx->prep_blocks, pp, cdf);
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaGetLastError());
+        CK(cudaMemcpy(h_pp.data(), pp, h_pp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(h_mo.data(), mo, h_mo.size() * 4, cudaMemcpyDeviceToHost));
+        for (int L = 0; L < N; ++L) {
+            bool ok = reach[L] && !((h_mo[2 * L] | h_mo[2 * L + 1]) & 0x100u);
+            for (int s = 0; s < 8 && ok; ++s) {
+                const int out = (L >> s) & 1;
+                const double p_other = h_pp[(size_t)L * 16 + 2 * s + (out ? 0 : 1)], p_own = h_pp[(size_t)L * 16 + 2 * s + out];
+                ok = p_other == 0.0 && p_own > 0.0;
+            }
+            quiet_ok[L] = ok ? 1 : 0;
+            ctx->any_quiet_leaf |= ok;
+        }
+    }
+    CK(cudaMemcpy(ctx->quiet_ok, quiet_ok.data(), N, cudaMemcpyHostToDevice));
     for (void *q : {(void *)ev, (void *)frm, (void *)list, (void *)nact, (void *)mo, (void *)ds, (void *)forced, (void *)aux,
                     (void *)pp, (void *)cnt})
         cudaFree(q);
@@ -1975,7 +2038,8 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
         SCOPE(CAT_OTHER);
         k_plan<<<blocks_for(n, kPlanThreads), kPlanThreads, 0, ctx->stream>>>(ctx->plan + (second ? ctx->n_plan : 0), pa, ctx->nd, ctx->probs, ctx->ev, ctx->masks,
                                                             ctx->leak, ctx->active, ctx->frm, ctx->n_act,
-                                                                          ctx->plan_hot + (second ? ctx->n_plan : 0));
+                                                                          ctx->plan_hot + (second ? ctx->n_plan : 0),
+                                                                          (ctx->use_quiet && stage == 1) ? ctx->quiet_flag : nullptr);
     }
     const int which = stage == 0 ? 0 : (second ? 2 : 1);
     const std::vector<LayerArg> &Ls = ctx->layers[which];
@@ -1985,7 +2049,9 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
     {
         SCOPE(CAT_OTHER);
         k_compact<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(ctx->active, n, ctx->act_list, ctx->n_act,
-                                                               (ctx->use_prep && stage == 1) ? ctx->prep_leaf : nullptr);
+                                                               (ctx->use_prep && stage == 1) ? ctx->prep_leaf : nullptr,
+                                                               (ctx->use_quiet && stage == 1) ? ctx->quiet_flag : nullptr,
+                                                               ctx->quiet_ok);
     }
     MeasArgs ma;
     memset(&ma, 0, sizeof(ma));
@@ -2015,11 +2081,21 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
                 k_cycle1<<<ctx->num_sms, kDgThreads, kDgSmem1, ctx->stream>>>(
                     ctx->diag_prog1[which], ma, ctx->state, ctx->stride, ctx->ev, ctx->frm, ctx->act_list, ctx->n_act, ctx->aux,
                     ctx->forced, ctx->meas_out, ctx->dsamp, ctx->counters, init_basis,
-                    (ctx->use_prep && stage == 1) ? ctx->prep_blocks : nullptr, nullptr);
+                    (ctx->use_prep && stage == 1) ? ctx->prep_blocks : nullptr, nullptr, nullptr);
             else
                 k_cycle<<<ctx->num_sms, kDgThreads, kDgSmem, ctx->stream>>>(
                     ctx->diag_prog[which], ma, ctx->state, ctx->stride, ctx->ev, ctx->frm, ctx->act_list, ctx->n_act, ctx->aux,
                     ctx->forced, ctx->meas_out, ctx->counters, init_basis);
+            ctx->n_gate++;
+        }
+        if (ctx->use_quiet && stage == 1) {
+            // the shots k_compact left out: no event in this cycle, memoised leaf.  meas_out still holds the leaf's
+            // outcomes (k_prep wrote them), which are this cycle's outcomes too.
+            SCOPE(CAT_GATE);
+            k_quiet<<<blocks_for((uint64_t)n * 32, 128), 128, 0, ctx->stream>>>(
+                ctx->prep_tree, ma, ctx->diag_prog1[1].mapA, ctx->active, ctx->quiet_flag, ctx->quiet_ok, ctx->prep_leaf, ctx->quiet_blocks,
+                ctx->quiet_cdf, ctx->forced, ctx->state, ctx->stride, ctx->meas_out, ctx->dsamp, ctx->counters,
+                (ctx->quiet_copy || a.forced) ? 1 : 0);
             ctx->n_gate++;
         }
         {
@@ -2113,6 +2189,8 @@ static int run_round(s17_ctx *ctx, const s17_run_args &a) {
                     !(a.protocol == S17_PROTO_RTF && ctx->plan_has_leak);
     if (ctx->use_prep)
         if (int rc = build_prep_cache(ctx, basis_index)) return rc;
+    // an event-free first cycle of a shot that sits in a memoised preparation leaf is replayed from the cache as well
+    ctx->use_quiet = ctx->use_prep && !ctx->no_quiet && ctx->any_quiet_leaf;
     if (int rc = run_cycle(ctx, a, 0, 0, basis_index, 0, dense, explicit_collapse)) return rc;
     if (explicit_collapse) collapse(ctx, n, ctx->active);
     if (a.stop_stage == S17_STOP_AFTER_PREP) return S17_OK;

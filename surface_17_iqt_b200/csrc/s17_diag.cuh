@@ -59,6 +59,7 @@ struct DiagHalf {
     uint32_t roff[4][16];      // register-index part of the table index, as a byte offset (index << 4)
 };
 struct DiagProg { DiagHalf h[2]; };
+constexpr int kDgCdfDoubles = 32 + 512;    // read-out weights of one cached block: inclusive lane sums + per-state weights
 
 // k_cycle1: label <-> (lane, register) mappings chosen by the host so that every slot of a half cycle indexes its
 // table with at most ONE register bit: a lane then needs two table entries per slot instead of sixteen.
@@ -132,6 +133,15 @@ __device__ __forceinline__ void dg_wht_inverse(double2 (&p)[16], double2 *xb, in
     for (int i = 0; i < 16; ++i) p[i] = xb[dg_swz(dg_label<1>(lane, i))];
     dg_wht_lane4(p, lane);
     dg_wht16(p);
+}
+
+// label bits a lane carries under a map
+__device__ __forceinline__ uint32_t lane_label(const DiagMap &M, int lane) {
+    uint32_t l = 0;
+#pragma unroll
+    for (int m = 0; m < 5; ++m)
+        if ((lane >> m) & 1) l |= 1u << M.lane[m];
+    return l;
 }
 
 // per-ancilla tables of one half cycle: up to two of the (slot, index) entries per lane.
@@ -409,11 +419,12 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ MeasArgs m
          size_t stride, const uint32_t *__restrict__ ev, const uint32_t *__restrict__ frm, const uint32_t *__restrict__ act_list,
          const uint32_t *__restrict__ n_act_ptr, ShotAux *__restrict__ aux, const uint8_t *__restrict__ forced,
          uint32_t *__restrict__ meas_out, uint32_t *__restrict__ dsamp, unsigned long long *__restrict__ counters,
-         int init_basis, const double2 *__restrict__ alt_src, double *__restrict__ pp_out)
+         int init_basis, const double2 *__restrict__ alt_src, double *__restrict__ pp_out, double *__restrict__ cdf_out)
 {
     // alt_src != nullptr: an entry of act_list is shot | leaf << 24 and the input block of the shot is alt_src[leaf]
     // (the memoised outcome of the noiseless preparation cycle, s17.cu: build_prep_cache); pp_out != nullptr: record
-    // the (P(0), P(1)) pair of every Measure (used once, to build that cache)
+    // the (P(0), P(1)) pair of every Measure, cdf_out != nullptr: the read-out's cumulative weights (used once, to
+    // build those caches)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char *wb = smem_raw + (size_t)warp * kDgWarpBytes;
@@ -640,6 +651,11 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ MeasArgs m
                 const double o = __shfl_up_sync(0xffffffffu, incl, d);
                 if (lane >= d) incl += o;
             }
+            if (cdf_out) {                        // kDgCdfDoubles per shot: 32 inclusive lane sums, then 16 weights per lane
+                cdf_out[(size_t)shot * kDgCdfDoubles + lane] = incl;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) cdf_out[(size_t)shot * kDgCdfDoubles + 32 + 16 * lane + i] = wsum[i];
+            }
             const double target = __shfl_sync(0xffffffffu, uu, 8) * __shfl_sync(0xffffffffu, incl, 31);
             const uint32_t hit = __ballot_sync(0xffffffffu, target < incl);
             const int sel = hit ? (__ffs(hit) - 1) : 31;
@@ -742,6 +758,62 @@ k_prep(const __grid_constant__ PrepTree T, const __grid_constant__ MeasArgs ma, 
     }
     const uint32_t nl = __popc(__ballot_sync(0xffffffffu, live));
     if ((threadIdx.x & 31) == 0 && nl) atomicAdd(&counters[4], (unsigned long long)nl);                  // C_SWEEPS
+}
+
+// Memoised event-free first cycle.  A first noisy cycle in which no error slot fires and no qubit is leaked is the
+// noiseless cycle applied to the preparation leaf the shot is in: it repeats the leaf's syndrome with certainty and
+// returns the same block.  build_prep_cache runs k_cycle1 once per leaf for this case too, checks that the kernel
+// itself finds every other outcome to have probability exactly zero, and keeps the block it stores and the read-out
+// weights it computes.  One warp per such shot: copy the block (optional), replay the read-out draw bit for bit.
+__global__ void __launch_bounds__(128)
+k_quiet(const __grid_constant__ PrepTree T, const __grid_constant__ MeasArgs ma, const __grid_constant__ DiagMap mapA,
+        const uint8_t *__restrict__ active, const uint8_t *__restrict__ quiet,
+        const uint8_t *__restrict__ quiet_ok, const uint8_t *__restrict__ leaf_of, const double2 *__restrict__ blocks,
+        const double *__restrict__ cdf, const uint8_t *__restrict__ forced, double2 *__restrict__ state, size_t stride,
+        uint32_t *__restrict__ meas_out, uint32_t *__restrict__ dsamp, unsigned long long *__restrict__ counters, int copy_block)
+{
+    const int shot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (shot >= ma.n_shots || !active[shot] || !quiet[shot]) return;
+    const uint32_t leaf = leaf_of[shot];
+    if (!quiet_ok[leaf]) return;                      // this shot went through k_cycle1 (k_compact kept it in the list)
+    if (ma.forced && lane == 0) {
+        // replay: the recorded outcomes of this cycle must be the leaf's (anything else has probability zero)
+        uint32_t bad = 0;
+        for (int s = 0; s < 8; ++s)
+            bad |= ((uint32_t)forced[(size_t)shot * S17_MAX_OUTCOMES + 8 + T.aj[s]] & 1u) ^ ((leaf >> s) & 1u);
+        if (bad) { meas_out[2 * shot] |= 0x100u; meas_out[2 * shot + 1] |= 0x100u; }
+    }
+    if (copy_block) {
+        const double2 *src = blocks + (size_t)leaf * kRun;
+        double2 *dst = state + (size_t)shot * stride;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dst[lane + 32 * i] = src[lane + 32 * i];
+    }
+    if (ma.sample_data) {
+        // the draw of k_cycle1, from the weights it computed for this block: same order, same doubles
+        const double *c = cdf + (size_t)leaf * kDgCdfDoubles;
+        const double incl = c[lane];
+        double u = 0.0;
+        if (lane == 0) { Philox rng(ma.seed, ma.first_shot + shot, ma.data_stream); u = rng.next(); }
+        const double target = __shfl_sync(0xffffffffu, u, 0) * __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t hit = __ballot_sync(0xffffffffu, target < incl);
+        const int sel = hit ? (__ffs(hit) - 1) : 31;
+        double cum = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) cum = 0.0;
+        int pick = 0, last_pos = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const double w = c[32 + 16 * lane + i];
+            cum += w;
+            pick += (cum <= target) ? 1 : 0;
+            last_pos = w > 0.0 ? i : last_pos;
+        }
+        pick = pick > 15 ? last_pos : pick;
+        uint32_t lab = ((uint32_t)lane_label(mapA, lane) | (mapA.lin16[pick] >> 4));
+        lab = __shfl_sync(0xffffffffu, lab, sel);
+        if (lane == 0) dsamp[shot] = lab & 511u;      // a computational-frame half without events relabels nothing
+    }
+    if (lane == 0) atomicAdd(&counters[4], 1ull);                                                        // C_SWEEPS
 }
 
 }  // namespace s17

@@ -626,3 +626,40 @@ def test_impossible_forced_outcome_is_reported(error_models, correction_table, b
     for i in range(n):
         assert bool(recs[i]["error"]) == (i % 4 in (1, 2)), (i, recs[i])
     sim.close()
+
+
+@pytest.mark.parametrize("model,protocol,cooling,p", [("PDD_model", "s1", False, 2e-3), ("depolarising_model", "single", False, 1e-3),
+                                                      ("PDD_cooling", "s2", True, 1e-3), ("Dress_model", "s1", False, 3e-3)])
+def test_memoised_event_free_cycle_is_bit_identical(error_models, correction_table, bitflip_table, model, protocol, cooling,
+                                                    p, monkeypatch):
+    """True-probability noise at rates where most first cycles have no event: k_quiet replays those from the cache of
+    k_cycle1's own results (outcomes = the preparation leaf's, the block and the read-out weights the kernel produced).
+    Counters, records, outcome logs and stored blocks are identical to running every cycle (S17_QUIET=0), and the
+    sampled trajectories replay bit-exactly in the oracle."""
+    per_round = circuit.list_lengths(error_models[model])
+    locs = [2 * x for x in per_round] if protocol == "s2" else per_round
+    n = 8192
+    out = {}
+    for quiet in ("1", "0"):
+        monkeypatch.setenv("S17_QUIET", quiet)
+        sim = make_sim(error_models, correction_table, bitflip_table, model, locs, n, 2, cooling)
+        sim.backend.set_slot_probs([[p] * x for x in locs])
+        c = sim.backend.run(protocol, n, L.NOISE_PROB, seed=77, first_shot_id=3)
+        recs, masks = sim.backend.records(n), sim.backend.masks(n)
+        states = np.stack([sim.backend.state(i)[:512] for i in range(0, n, 128)])
+        out[quiet] = ((c.failed, c.not0, c.counted, c.errors), recs, states, masks, c.sweeps)
+        if quiet == "1" and model != "depolarising_model":          # (the 15-way depolarising choice is not in the masks)
+            orc = so.ShotOracle(error_models, correction_table, bitflip_table)
+            for i in range(48):
+                ref = orc.run_shot(model, sim.backend.split_mask(masks[i, 0] | masks[i, 1]) if protocol == "s2" else
+                                   sim.backend.split_mask(masks[i, 0]), protocol, cooling=cooling, rnd=random.Random(0),
+                                   meas=so.ForcedMeasure(recs[i]["outcomes"]))
+                for f in FIELDS:
+                    assert recs[i].get(f) == ref.get(f), (i, f, recs[i].get(f), ref.get(f))
+        sim.close()
+    assert out["1"][0] == out["0"][0] and out["1"][4] == out["0"][4]
+    assert out["1"][1] == out["0"][1]
+    assert np.array_equal(out["1"][3], out["0"][3])
+    assert np.array_equal(out["1"][2], out["0"][2])
+    quiet_fraction = np.mean(out["1"][3][:, 0].sum(axis=1) == 0)
+    assert quiet_fraction > 0.3                                     # the memoised path really carried a large share
