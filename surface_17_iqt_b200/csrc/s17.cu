@@ -2011,10 +2011,9 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
         ma.final_part = 1;
         ma.stream = 16u;
         {
-            SCOPE(CAT_GATE);
+            SCOPE(CAT_OTHER);      // (the gate category times the amplitude kernels only: it is the roofline's denominator)
             k_prep<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(ctx->prep_tree, ma, ctx->prep_pp, ctx->forced, ctx->active,
                                                                 ctx->meas_out, ctx->prep_leaf, ctx->aux, ctx->counters);
-            ctx->n_gate++;
         }
         {
             SCOPE(CAT_MEAS);
@@ -2091,12 +2090,11 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
         if (ctx->use_quiet && stage == 1) {
             // the shots k_compact left out: no event in this cycle, memoised leaf.  meas_out still holds the leaf's
             // outcomes (k_prep wrote them), which are this cycle's outcomes too.
-            SCOPE(CAT_GATE);
+            SCOPE(CAT_OTHER);
             k_quiet<<<blocks_for((uint64_t)n * 32, 128), 128, 0, ctx->stream>>>(
                 ctx->prep_tree, ma, ctx->diag_prog1[1].mapA, ctx->active, ctx->quiet_flag, ctx->quiet_ok, ctx->prep_leaf, ctx->quiet_blocks,
                 ctx->quiet_cdf, ctx->forced, ctx->state, ctx->stride, ctx->meas_out, ctx->dsamp, ctx->counters,
                 (ctx->quiet_copy || a.forced) ? 1 : 0);
-            ctx->n_gate++;
         }
         {
             SCOPE(CAT_MEAS);
