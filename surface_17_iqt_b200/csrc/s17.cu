@@ -691,17 +691,23 @@ __global__ void __launch_bounds__(256)
 k_compact(const uint8_t *__restrict__ active, int n, uint32_t *__restrict__ list, uint32_t *__restrict__ n_act,
           const uint8_t *__restrict__ leaf /* nullptr, or per shot: byte for bits 24-31 of its entry (k_cycle1 + prep cache) */,
           const uint8_t *__restrict__ quiet, const uint8_t *__restrict__ quiet_ok /* nullptr, or: shots with quiet[i] and
-          quiet_ok[leaf[i]] are left out (k_quiet handles them) */)
+          quiet_ok[leaf[i]] are left out (k_quiet handles them) */,
+          const uint8_t *__restrict__ done /* nullptr, or per shot: 1 = the memoised preparation handled it */, int skip_done)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
     bool flag = i < n && active[i];
     if (flag && quiet && quiet[i] && quiet_ok[leaf[i]]) flag = false;
+    if (flag && done && skip_done && done[i]) flag = false;          // preparation stage: only the shots k_prep left
     const uint32_t ballot = __ballot_sync(0xffffffffu, flag);
     if (!ballot) return;
     uint32_t base = 0;
     if (lane == 0) base = atomicAdd(n_act, (uint32_t)__popc(ballot));
     base = __shfl_sync(0xffffffffu, base, 0);
-    if (flag) list[base + __popc(ballot & ((1u << lane) - 1u))] = (uint32_t)i | (leaf ? (uint32_t)leaf[i] << 24 : 0u);
+    if (flag) {
+        uint32_t entry = (uint32_t)i;
+        if (leaf) entry |= (done && !done[i]) ? 0x800000u : ((uint32_t)leaf[i] << 24);     // own state / cached leaf
+        list[base + __popc(ballot & ((1u << lane) - 1u))] = entry;
+    }
 }
 
 struct ReadArgs {
@@ -958,7 +964,8 @@ struct s17_ctx {
     // memoised preparation cycle (k_prep): 256 leaf blocks, (P0, P1) per node of the outcome tree, leaf per shot
     double2 *prep_blocks = nullptr;
     double *prep_pp = nullptr;
-    uint8_t *prep_leaf = nullptr;
+    uint8_t *prep_leaf = nullptr, *prep_done = nullptr;
+    bool prep_mixed = false;           // run-til-fail with a leakage model: shots with a leak flag run their own preparation
     int prep_basis = -1;              // basis index the cache was built for (-1: not built)
     bool no_prep_cache = false, plan_has_leak = false, use_prep = false;
     // memoised event-free first cycle (k_quiet): per leaf the block k_cycle1 stores and its read-out weights
@@ -1090,6 +1097,7 @@ extern "C" int s17_create(s17_ctx **out, int device, uint64_t max_shots) {
     CK(cudaMalloc(&ctx->frm, B * 4 * 4));
     CK(cudaMalloc(&ctx->dsamp, B * 4));
     CK(cudaMalloc(&ctx->prep_leaf, B));
+    CK(cudaMalloc(&ctx->prep_done, B));
     CK(cudaMalloc(&ctx->prep_blocks, 256 * (size_t)kRunBytes));
     CK(cudaMalloc(&ctx->prep_pp, 2 * 255 * sizeof(double)));
     CK(cudaMalloc(&ctx->quiet_blocks, 256 * (size_t)kRunBytes));
@@ -1155,7 +1163,7 @@ extern "C" int s17_destroy(s17_ctx *ctx) {
     void *ptrs[] = {ctx->state, ctx->ev, ctx->masks, ctx->leak, ctx->active, ctx->ready, ctx->forced, ctx->hist,
                     ctx->aux, ctx->rec, ctx->counters, ctx->lut, ctx->cw16, ctx->probs, ctx->cum, ctx->plan,
                     ctx->rtf_slots, ctx->rtf_rounds, ctx->rtf_syndb, ctx->act_list, ctx->n_act, ctx->zero_page, ctx->meas_out,
-                    ctx->frm, ctx->dsamp, ctx->prep_leaf, ctx->prep_blocks, ctx->prep_pp, ctx->plan_hot,
+                    ctx->frm, ctx->dsamp, ctx->prep_leaf, ctx->prep_done, ctx->prep_blocks, ctx->prep_pp, ctx->plan_hot,
                     ctx->quiet_blocks, ctx->quiet_cdf, ctx->quiet_ok, ctx->quiet_flag};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -2013,15 +2021,17 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
         {
             SCOPE(CAT_OTHER);      // (the gate category times the amplitude kernels only: it is the roofline's denominator)
             k_prep<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(ctx->prep_tree, ma, ctx->prep_pp, ctx->forced, ctx->active,
-                                                                ctx->meas_out, ctx->prep_leaf, ctx->aux, ctx->counters);
+                                                                ctx->meas_out, ctx->prep_leaf, ctx->aux, ctx->counters,
+                                                                ctx->prep_mixed ? ctx->leak : nullptr, ctx->prep_done);
         }
-        {
+        if (!ctx->prep_mixed) {
             SCOPE(CAT_MEAS);
             k_record<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(ma, ctx->meas_out, ctx->lut, ctx->leak, ctx->active,
                                                                   ctx->ready, ctx->rec, ctx->counters);
+            ctx->last_collapsed = true;
+            return S17_OK;
         }
-        ctx->last_collapsed = true;
-        return S17_OK;
+        // mixed: the shots with a leak flag go through the regular preparation cycle below (k_compact lists only them)
     }
     PlanArgs pa;
     pa.n_instr = ctx->n_plan;
@@ -2050,7 +2060,8 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
         k_compact<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(ctx->active, n, ctx->act_list, ctx->n_act,
                                                                (ctx->use_prep && stage == 1) ? ctx->prep_leaf : nullptr,
                                                                (ctx->use_quiet && stage == 1) ? ctx->quiet_flag : nullptr,
-                                                               ctx->quiet_ok);
+                                                               ctx->quiet_ok, (ctx->use_prep && stage <= 1) ? ctx->prep_done : nullptr,
+                                                               stage == 0 ? 1 : 0);
     }
     MeasArgs ma;
     memset(&ma, 0, sizeof(ma));
@@ -2180,11 +2191,11 @@ static int run_round(s17_ctx *ctx, const s17_run_args &a) {
     // both noisy cycles go through k_cycle1 and outcomes are sampled: the cycle kernel also draws the data read-out
     ctx->use_dsamp = ctx->diag1_ok[1] && ctx->diag1_ok[2] && !ctx->no_diag1 && !ctx->no_diag && !explicit_collapse &&
                      !ctx->use_v1 && !ctx->force_ring && !ctx->no_fuse && !a.forced;
-    // the noiseless preparation cycle is memoised when it and the first noisy cycle run on k_cycle1 and no leak flag can
-    // be set when it starts (run-til-fail keeps leak flags across the rounds of a run)
+    // the noiseless preparation cycle is memoised when it and the first noisy cycle run on k_cycle1; where a leak flag can
+    // be set when it starts (run-til-fail keeps leak flags across the rounds of a run) only for the shots without one
     ctx->use_prep = ctx->diag1_ok[0] && ctx->diag1_ok[1] && !ctx->no_diag1 && !ctx->no_diag && !explicit_collapse &&
-                    !ctx->use_v1 && !ctx->force_ring && !ctx->no_fuse && !ctx->no_prep_cache && ctx->max_shots < (1u << 24) &&
-                    !(a.protocol == S17_PROTO_RTF && ctx->plan_has_leak);
+                    !ctx->use_v1 && !ctx->force_ring && !ctx->no_fuse && !ctx->no_prep_cache && ctx->max_shots < (1u << 23);
+    ctx->prep_mixed = ctx->use_prep && a.protocol == S17_PROTO_RTF && ctx->plan_has_leak;
     if (ctx->use_prep)
         if (int rc = build_prep_cache(ctx, basis_index)) return rc;
     // an event-free first cycle of a shot that sits in a memoised preparation leaf is replayed from the cache as well

@@ -421,7 +421,8 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ MeasArgs m
          uint32_t *__restrict__ meas_out, uint32_t *__restrict__ dsamp, unsigned long long *__restrict__ counters,
          int init_basis, const double2 *__restrict__ alt_src, double *__restrict__ pp_out, double *__restrict__ cdf_out)
 {
-    // alt_src != nullptr: an entry of act_list is shot | leaf << 24 and the input block of the shot is alt_src[leaf]
+    // alt_src != nullptr: an entry of act_list is shot | own << 23 | leaf << 24 and the input block of the shot is
+    // alt_src[leaf] unless `own` is set (the shot ran its own preparation cycle: a leak flag was set)
     // (the memoised outcome of the noiseless preparation cycle, s17.cu: build_prep_cache); pp_out != nullptr: record
     // the (P(0), P(1)) pair of every Measure, cdf_out != nullptr: the read-out's cumulative weights (used once, to
     // build those caches)
@@ -500,7 +501,9 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ MeasArgs m
     }
 
     auto prefetch = [&](uint32_t entry, int sb) {
-        const uint32_t shot_ = alt_src ? (entry & 0xFFFFFFu) : entry;     // plain shot index unless a leaf rides in bits 24-31
+        // plain shot index, or (preparation cache in use) shot | own-state flag << 23 | leaf << 24
+        const uint32_t shot_ = alt_src ? (entry & 0x7FFFFFu) : entry;
+        const bool cached = alt_src && !(entry & 0x800000u);
         unsigned char *m = meta + sb * kDgMetaBytes;
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the bulk store staged in this buffer has left it
         fence_proxy_async_smem();                 // the buffers were last touched through the generic proxy
@@ -509,7 +512,7 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ MeasArgs m
         tma_load_1d(m + kEvBytes, frm + (size_t)shot_ * 4, kDgFrmBytes, &mfull[sb]);
         if (init_basis < 0) {
             mbar_expect_tx(&full[sb], kRunBytes);
-            tma_load_1d(buf + sb * kRunBytes, alt_src ? alt_src + (size_t)(entry >> 24) * kRun : state + (size_t)shot_ * stride,
+            tma_load_1d(buf + sb * kRunBytes, cached ? alt_src + (size_t)(entry >> 24) * kRun : state + (size_t)shot_ * stride,
                         kRunBytes, &full[sb]);
         }
     };
@@ -529,7 +532,7 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ MeasArgs m
     uint32_t j = 0;
     for (uint32_t item = first; item < last; ++item, ++j) {
         const int sb = (int)(j & 1u);
-        const uint32_t shot = alt_src ? (entry & 0xFFFFFFu) : entry;
+        const uint32_t shot = alt_src ? (entry & 0x7FFFFFu) : entry;
         uint32_t entry1 = 0;
         if (item + 1 < last) {
             entry1 = act_list[item + 1];
@@ -724,10 +727,17 @@ struct PrepTree {
 __global__ void __launch_bounds__(256)
 k_prep(const __grid_constant__ PrepTree T, const __grid_constant__ MeasArgs ma, const double *__restrict__ node_pp,
        const uint8_t *__restrict__ forced, const uint8_t *__restrict__ active, uint32_t *__restrict__ meas_out,
-       uint8_t *__restrict__ leaf_out, ShotAux *__restrict__ aux, unsigned long long *__restrict__ counters)
+       uint8_t *__restrict__ leaf_out, ShotAux *__restrict__ aux, unsigned long long *__restrict__ counters,
+       const uint32_t *__restrict__ leak /* nullptr, or: shots with a set leak flag run the real preparation cycle */,
+       uint8_t *__restrict__ done)
 {
     const int shot = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = shot < ma.n_shots && active[shot];
+    bool live = shot < ma.n_shots && active[shot];
+    if (live) {
+        const bool own = leak && leak[shot] != 0;
+        done[shot] = own ? 0 : 1;
+        live = !own;
+    }
     if (live) {
         uint32_t prefix = 0, r[2] = {0u, 0u};
         bool bad = false;

@@ -663,3 +663,29 @@ def test_memoised_event_free_cycle_is_bit_identical(error_models, correction_tab
     assert np.array_equal(out["1"][2], out["0"][2])
     quiet_fraction = np.mean(out["1"][3][:, 0].sum(axis=1) == 0)
     assert quiet_fraction > 0.3                                     # the memoised path really carried a large share
+
+
+@pytest.mark.parametrize("model,p_leak", [("Dress_model", 3e-3), ("PDD_model", 1e-3)])
+def test_run_til_fail_memoisation_is_bit_identical(error_models, correction_table, bitflip_table, model, p_leak,
+                                                   monkeypatch):
+    """Run-til-fail with every memoisation (preparation leaves, event-free first cycles; with a leakage model only for
+    the shots without a set leak flag, the others run their own preparation cycle) against running every cycle of
+    every round: the same rounds-til-fail and second-syndrome counts.  (A freed slot takes the next run id by an atomic
+    counter, so which run id labels which trajectory can differ between two executions; the trajectories themselves
+    are keyed by slot and round, hence the comparison of the sorted lists.)"""
+    locs = [12, 18, 24, 78, 24]
+    runs, slots = 3000, 512
+    res = {}
+    for cache in ("1", "0"):
+        monkeypatch.setenv("S17_PREP_CACHE", cache)
+        sim = make_sim(error_models, correction_table, bitflip_table, model, locs, slots, 2)
+        p = 0.01
+        sim.backend.set_slot_probs([[p / 10] * 12, [p / 10] * 18, [p] * 24, [p_leak] * 78, [0.0] * 24])
+        c = sim.backend.run("rtf", slots, L.NOISE_PROB, seed=11, rtf_runs=runs)
+        rounds, syndb = sim.backend.rtf_results(runs)
+        res[cache] = (rounds.copy(), syndb.copy(), c.rounds, c.failed)
+        sim.close()
+    assert res["1"][2:] == res["0"][2:]
+    assert np.array_equal(res["1"][0][:slots], res["0"][0][:slots]) and np.array_equal(res["1"][1][:slots], res["0"][1][:slots])
+    both = lambda r: sorted(zip(r[0].tolist(), r[1].tolist()))
+    assert both(res["1"]) == both(res["0"])
