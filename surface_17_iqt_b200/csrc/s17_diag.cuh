@@ -18,8 +18,16 @@
 //
 // One WARP owns one shot: the 512 amplitudes live in registers (16 per lane) for the whole cycle, the Walsh-Hadamard
 // transform is two in-register radix-16 passes, one shuffle stage and one exchange through shared memory.  HBM traffic
-// per shot and cycle: 8 KiB read + 8 KiB written (+ ~200 B of metadata), prefetched one shot ahead by TMA.
+// per shot and cycle: 8 KiB read + 8 KiB written (+ ~150 B of metadata), prefetched one shot ahead by TMA.
 // Exact same measurement semantics as k_half / k_measure (one Measure per ancilla, conditional on the earlier ones).
+//
+// Kernels in this file:
+//   k_cycle   the algorithm with fixed label <-> (lane, register) maps (up to 16 table entries per lane and slot);
+//   k_cycle1  the production form: maps searched by the host (make_diag1 in s17.cu) so that every slot indexes its
+//             table with one register bit (two entries per lane), event-free tables shared per CTA, the data
+//             read-out drawn from the registers, bulk store of the staged block;
+//   k_prep    the memoised noiseless preparation cycle (replays k_cycle1's own decisions per preparation leaf);
+//   k_quiet   the memoised event-free first noisy cycle (replays k_cycle1's cached result for the shot's leaf).
 // Included by s17.cu after MeasArgs.
 #pragma once
 
