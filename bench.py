@@ -21,6 +21,9 @@ only exchange is one all-reduce of the counters at the end (inside the timed reg
            HBM; `roofline_dense` is the same gate stream as full-state sweeps (2 MiB read + 2 MiB written per shot
            and sweep, S17_DENSE=1), the HBM-bound configuration BASELINE.json's "% of HBM roofline per gate layer"
            refers to.
+`without_memoisation`: the same steps with S17_PREP_CACHE=0, i.e. the noiseless preparation cycle (and the few
+           event-free first cycles) computed per shot instead of replayed from the cache of the kernel's own results;
+           same counters, reported so that the effect of the memoisation is visible in the line itself.
 `cpu_baseline` / --impl reference: the oracle port (one CPU sweep per gate, ProjectQ's execution model,
            python per-gate driver like the reference) on all host cores, bounded sample of the same workload.
 """
@@ -289,9 +292,39 @@ def run_gpu(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = algo_bytes / (gate_ms * 1e-3) / 1e9 if gate_ms > 0 else 0.0
 
+    # the same steps with every memoisation off (S17_PREP_CACHE=0: the noiseless preparation cycle and event-free first
+    # cycles run through k_cycle1 per shot like any other cycle): reported beside `value`, same counters
+    sim.close()
+    plain = None
+    if rank == 0 and not args.no_plain:
+        note("steps without memoisation")
+        os.environ["S17_PREP_CACHE"] = "0"
+        try:
+            psim = api.Simulation(MODEL, LOCS2, B, ct, bt, fusion=args.fusion, device=local, error_models=models)
+            psim.backend.set_subset(ESET, LOCS2)
+            for k in range(min(3, args.warmup)):
+                psim.backend.run("s2", B, L.NOISE_SUBSET, seed=args.seed, first_shot_id=(k * world + rank) * B)
+            p_span = p_gate = 0.0
+            p_failed = p_not0 = 0
+            p_steps = min(args.steps, 5)
+            for k in range(p_steps):
+                c = psim.backend.run("s2", B, L.NOISE_SUBSET, seed=args.seed,
+                                     first_shot_id=((args.warmup + k) * world + rank) * B)
+                t = psim.backend.timing()
+                p_span, p_gate = p_span + t["span_ms"], p_gate + t["gate_ms"]
+                p_failed, p_not0 = p_failed + c.failed, p_not0 + c.not0
+            plain = {"value": B * p_steps / (p_span * 1e-3), "unit": "shots/s (this rank)", "steps": p_steps,
+                     "ms_per_step": p_span / p_steps, "gate_kernel_share_of_step": p_gate / p_span,
+                     "counts": {"failed": int(p_failed), "not0": int(p_not0), "shots": B * p_steps},
+                     "mode": "S17_PREP_CACHE=0: preparation cycle and event-free cycles computed per shot"}
+            psim.close()
+        except Exception as exc:          # evidence only: never lose the main line over it
+            plain = {"error": str(exc)[:200]}
+        finally:
+            os.environ.pop("S17_PREP_CACHE", None)
+
     # the same gate stream as full-state sweeps (ProjectQ-equivalent traffic, one sweep per timestep): the HBM-bound
     # configuration the per-layer roofline fraction of BASELINE.json refers to
-    sim.close()
     dense = None
     note("dense-mode roofline run")
     if rank == 0 and not args.no_dense:
@@ -363,6 +396,8 @@ def run_gpu(args):
                          "gate_kernel_share_of_step": gate_ms / span_ms if span_ms else None},
             "counts": {"failed": int(tot[0]), "not0": int(tot[1]), "shots": total_shots},
         }
+        if plain is not None:
+            line["without_memoisation"] = plain
         if dense is not None:
             line["roofline_dense"] = dense
         if cpu is not None:
@@ -383,6 +418,7 @@ def main():
     ap.add_argument("--seed", type=int, default=2026)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-dense", action="store_true")
+    ap.add_argument("--no-plain", action="store_true")
     ap.add_argument("--dense-shots", type=int, default=4096)
     ap.add_argument("--cpu-shots-per-core", type=int, default=40)
     ap.add_argument("--ref-shots-per-core", type=int, default=40)
