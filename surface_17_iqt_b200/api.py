@@ -2,7 +2,7 @@
 import json
 import os
 
-from . import _lib as L
+from . import _lib as L  # noqa: F401  (re-exported: api.L holds the constants)
 from . import circuit
 from .backend import Backend
 
