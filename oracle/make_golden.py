@@ -64,6 +64,12 @@ def ref_shot(CS, pq, model, p_set, protocol, cooling, forced=None, seed=None, wa
         ft = (np.array(quiescent) - synd2) % 2
     rec["not0"] = int(not stop)
     rec["counted"] = int(ft is not None)
+    if want_block:
+        # the state the last executed cycle leaves behind (ancillas measured and reset: only psi[:512] is populated),
+        # BEFORE lookup / apply_correction -- what a whole-cycle kernel stores
+        eng.flush()
+        rec["_pre_block"] = eng.backend.psi[:512].copy()
+        rec["pre_block_norm_outside"] = float(np.sum(np.abs(eng.backend.psi[512:]) ** 2))
     if ft is not None:
         vec = CS.lookup(ft, correction_table)
         CS.apply_correction(vec, data)
@@ -125,7 +131,7 @@ def main():
 
     # 2. replay trajectories: masks + recorded outcomes -> records (bit-exact fields) + 512-amp blocks
     rng = random.Random(20261019)
-    replays, blocks = [], []
+    replays, blocks, pre_blocks = [], [], []
     cases = []
     for model in ("PDD_model", "Dress_model", "PDD_cooling", "Dress_cooling"):
         nt = len(LOC[model])
@@ -147,6 +153,11 @@ def main():
             rec2, _ = ref_shot(CS, pq, model, p_set, protocol, cooling, forced=rec["outcomes"], want_block=True)
         blk = rec.pop("_block", None)
         blk2 = rec2.pop("_block", None)
+        pre, pre2 = rec.pop("_pre_block"), rec2.pop("_pre_block")
+        assert np.allclose(pre, pre2, atol=1e-14)
+        rec["pre_block_index"] = len(pre_blocks)
+        rec2["pre_block_index"] = len(pre_blocks)
+        pre_blocks.append(pre)
         assert {k: v for k, v in rec.items() if k != "meas_probs"} == {k: v for k, v in rec2.items() if k != "meas_probs"}
         if blk is not None:
             assert np.allclose(blk, blk2, atol=1e-14)
@@ -156,7 +167,7 @@ def main():
             blocks.append(blk)
         replays.append(rec)
     json.dump({"replays": replays}, open(os.path.join(OUT, "replays.json"), "w"))
-    np.savez_compressed(os.path.join(OUT, "replay_blocks.npz"), blocks=np.array(blocks))
+    np.savez_compressed(os.path.join(OUT, "replay_blocks.npz"), blocks=np.array(blocks), pre_blocks=np.array(pre_blocks))
 
     # 3. single-fault table for PDD_model under the s2 protocol (two-round masks one-hot in round 1)
     table = []

@@ -442,3 +442,36 @@ def run_subset(oracle, protocol, num_runs, model, eset, locations, prob_lists, c
         failed += rec["fail"]
         not0 += rec["not0"]
     return failed, not0
+
+
+def run_til_fail(oracle, num_runs, model, e_probs, rnd=None, meas_rng=None, leak_reset="never", max_rounds=None):
+    """The run loop of calculate_log_e_rate (CL:33-148): every run repeats fresh-start rounds (run_round_rtf) until the
+    logical read-out is wrong.  Returns (rounds_til_fail_list, syndrome_b_measured_list).
+
+    leak_reset: 'never' = the reference, whose leak register is created once for all runs (CL:49, SURVEY C-6);
+    'run' / 'round' clear it at the start of every run / round (the variants the batched backend also offers).
+    The two dead `random.random() < 1` basis/state draws per run (CL:54-61) are consumed so that the error-draw stream
+    stays aligned with the reference for a given seed."""
+    rnd = rnd if rnd is not None else _random
+    meas = SampledMeasure(meas_rng if meas_rng is not None else _random)
+    if leak_reset not in ("never", "run", "round"):
+        raise ValueError(leak_reset)
+    leaked = N_QUBITS * [0]
+    rounds_list, syndb_list = [], []
+    for _ in range(num_runs):
+        rnd.random()
+        rnd.random()
+        if leak_reset == "run":
+            leaked = N_QUBITS * [0]
+        rounds = took_b_total = 0
+        while True:
+            if leak_reset == "round":
+                leaked = N_QUBITS * [0]
+            fail, took_b = oracle.run_round_rtf(model, e_probs, leaked, rnd, meas)
+            rounds += 1
+            took_b_total += took_b
+            if fail or (max_rounds and rounds >= max_rounds):
+                break
+        rounds_list.append(rounds)
+        syndb_list.append(took_b_total)
+    return rounds_list, syndb_list

@@ -117,3 +117,19 @@ def test_oracle_sampling_agrees_with_reference_statistics(oracle, golden):
     assert abs(p - p_ref) < 3.5 * np.sqrt(p_ref * (1 - p_ref) * (1 / st["runs"] + 1 / m))
     f_ref, f = st["failed"] / st["not0"], failed / max(1, not0)
     assert abs(f - f_ref) < 3.5 * np.sqrt(f_ref * (1 - f_ref) * (1 / st["not0"] + 1 / max(1, not0)))
+
+
+def test_run_til_fail_matches_reference_chains(oracle, golden):
+    """`oracle.run_til_fail` (CL:33-148 restated) with the seeds of oracle/make_golden_rtf.py reproduces the UNMODIFIED
+    reference driver's rounds_til_fail_list and syndrome_b_measured_list run by run -- including the reference's
+    never-reset leak register (CL:49) for Dress_model.  Two chains per model here (the CPU suite stays short); the GPU
+    statistics test uses all of them."""
+    for case in golden("rtf_ref.json")["cases"]:
+        names = oracle.error_models[case["model"]]["probabilities"]
+        e_probs = dict(zip(names, case["p_set"]))
+        for chain in case["chains"][:2]:
+            n = 6
+            rounds, syndb = so.run_til_fail(oracle, n, case["model"], e_probs, rnd=random.Random(chain["seed"]),
+                                            meas_rng=random.Random(chain["meas_seed"]), leak_reset="never")
+            assert rounds == chain["rounds_til_fail_list"][:n], (case["model"], chain["seed"])
+            assert syndb == chain["syndrome_b_measured_list"][:n], (case["model"], chain["seed"])
