@@ -139,7 +139,20 @@ typedef struct {
     uint32_t forced;          /* 1: measurement outcomes come from s17_set_replay */
     uint32_t rtf_runs;        /* S17_PROTO_RTF: number of runs to complete */
     uint32_t rtf_max_rounds;  /* S17_PROTO_RTF: safety cap on rounds per run (0 = none) */
+    uint32_t leak_reset;      /* S17_PROTO_RTF: S17_LEAK_RESET_* -- when the leak register of a slot is cleared */
+    uint32_t rtf_poll;        /* S17_PROTO_RTF: rounds between two host reads of the live-slot count (0 = default) */
+    uint64_t rtf_round_budget; /* S17_PROTO_RTF: stop once this many rounds were simulated in total (0 = run every run to
+                                  its failure); runs still in flight then stay censored (0 in s17_read_rtf) */
+    uint32_t rtf_chain_runs;  /* S17_PROTO_RTF: 0 = a freed slot takes the next unassigned run id (in slot order);
+                                  K > 0 = every slot is a chain of exactly K consecutive runs, ids slot*K .. slot*K+K-1
+                                  (rtf_runs must be n_shots*K): with S17_LEAK_RESET_NEVER a slot then IS one call of the
+                                  reference's calculate_log_e_rate(K, ...) (CL:33-148) */
+    uint32_t pad0;
 } s17_run_args;
+/* leaked_q_reg of calculate_log_e_rate is created once for all runs (CL:49): NEVER is the reference's literal behaviour
+ * (per slot here: a slot is one sequential chain of runs); RUN clears it when a slot starts a new run, ROUND at every
+ * round.  The library's callers default to RUN (SURVEY C-6). */
+enum { S17_LEAK_RESET_NEVER = 0, S17_LEAK_RESET_RUN = 1, S17_LEAK_RESET_ROUND = 2 };
 
 typedef struct {
     uint64_t shots;        /* shots executed */
@@ -211,10 +224,52 @@ int s17_read_masks(s17_ctx *ctx, uint32_t *out /* n x 2 x S17_MASK_WORDS: cycle-
 int s17_read_events(s17_ctx *ctx, uint32_t *out, uint64_t n);
 int s17_read_state(s17_ctx *ctx, uint64_t shot, double *re_im /* 2 * 2^17 doubles */);
 int s17_read_rtf(s17_ctx *ctx, uint32_t *rounds_til_fail, uint32_t *syndrome_b_count, uint64_t n_runs);
+/* run-til-fail (CL:33-148) as a job, for callers that want to look at the slots between rounds (parity tests replay
+ * every round through the oracle): s17_run with S17_PROTO_RTF is begin + step until no slot is live + end.  A slot is
+ * one run in flight; a slot whose run failed takes the next run id, in slot order.  After a step the records / masks of
+ * the last round are readable with s17_read_records / s17_read_masks (cycle-A slots in the first half, cycle-B slots in
+ * the second). */
+int s17_rtf_begin(s17_ctx *ctx, const s17_run_args *args);
+int s17_rtf_step(s17_ctx *ctx, uint32_t n_rounds, uint64_t *alive_slots, uint64_t *rounds_total);
+int s17_rtf_end(s17_ctx *ctx, s17_counts *out);
+int s17_read_rtf_slots(s17_ctx *ctx, uint32_t *out /* n x {run_id, rounds so far, second syndromes so far, alive} */, uint64_t n);
 /* device time of the last s17_run, CUDA events on the launch stream (ms): per kernel class, and the span from
  * the first to the last device operation of the call */
 int s17_last_timing(s17_ctx *ctx, double *gate_ms, double *measure_ms, double *other_ms,
                     uint64_t *gate_launches, uint64_t *all_launches, double *span_ms);
+
+/* ---- engine-level face: ProjectQ's Simulator backend for a batch of state vectors -------------------------------
+ *
+ * The reference drives its backend gate by gate: `MainEngine(Simulator())` (CL:63, 221, 299, 392), `Gate | qubits`
+ * (CS:291-344; the Paulis of insert_error CS:198-217), `All(Measure) | qureg; eng.flush(); int(q)` (CS:56-58, 848-851).
+ * These entry points are that surface for `batch` state vectors of 2^n_bits complex128 amplitudes at once (one sweep per
+ * gate, like ProjectQ's default gate_fusion=False): surface_17_iqt_b200/pq_compat/projectq binds them behind ProjectQ's
+ * own class names, so the reference's unmodified circuit functions run on the GPU.  Bit k = k-th allocated qubit.
+ * Gate calls are asynchronous (stream order); measure / flush / read_state / timing synchronise. */
+typedef struct s17_eng s17_eng;
+enum { S17_MEAS_SAMPLE = 0,     /* one Philox uniform per shot against P(1) */
+       S17_MEAS_LOCKSTEP = 1,   /* the outcome drawn for shot 0 is imposed on every shot (the batch holds N copies of
+                                   one trajectory: `int(qubit)` has one value) */
+       S17_MEAS_FORCED = 2 };   /* outcomes given per shot (replays) */
+int s17_eng_create(s17_eng **out, int device, uint32_t n_bits, uint64_t batch, uint64_t seed);
+int s17_eng_destroy(s17_eng *eng);
+const char *s17_eng_last_error(const s17_eng *eng);
+int s17_eng_reset(s17_eng *eng);                               /* every shot back to |0...0> */
+/* m: row-major complex matrix as (re, im) pairs, 8 / 32 doubles; two-qubit index = bit0 value + 2 * bit1 value.
+ * pred: NULL, or one byte per shot (host): the gate is applied to the shots with a non-zero byte only
+ * (`if int(a) == 1: X | a`, CS:859-862). */
+int s17_eng_gate1(s17_eng *eng, uint32_t bit, const double *m, const uint8_t *pred);
+int s17_eng_gate2(s17_eng *eng, uint32_t bit0, uint32_t bit1, const double *m, const uint8_t *pred);
+/* Measure | qubit: P(1) reduction, outcome, collapse + renormalise.  out: one byte per shot (host); prob: NULL or the
+ * probability each shot's outcome had; n_impossible: shots whose imposed outcome had probability zero. */
+int s17_eng_measure(s17_eng *eng, uint32_t bit, uint32_t mode, const uint8_t *forced, uint8_t *out, double *prob,
+                    uint32_t *n_impossible);
+int s17_eng_prob1(s17_eng *eng, uint32_t bit, double *p1 /* per shot */);   /* ProjectQ's check before deallocation */
+int s17_eng_flush(s17_eng *eng);
+int s17_eng_read_state(s17_eng *eng, uint64_t shot, double *re_im /* 2 * 2^n_bits doubles */);
+/* device time (CUDA events on the launch stream) and launch counts since the last call with clear != 0:
+ * [0] gate sweeps, [1] probability reductions, [2] collapses */
+int s17_eng_timing(s17_eng *eng, double ms[3], uint64_t calls[3], int clear);
 
 #ifdef __cplusplus
 }

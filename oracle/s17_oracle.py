@@ -363,9 +363,12 @@ class ShotOracle:
         rec["leaked"] = list(leaked)
         return rec
 
-    def run_round_rtf(self, model, e_probs, leaked, rnd, meas, basis="Z", state=0):
+    def run_round_rtf(self, model, e_probs, leaked, rnd, meas, basis="Z", state=0, e_probs_b=None, want_record=False):
         """One round of run-til-fail (CL:68-113): fresh |0..0>, prep, cycle A, optional cycle B with the
-        SAME (stab_ind=0) probabilities, decode (flips_a + flips_b) % 2, correct, read out."""
+        SAME (stab_ind=0) probabilities, decode (flips_a + flips_b) % 2, correct, read out.
+
+        e_probs_b (test hook): other lists for cycle B -- a replay passes the 0/1 masks of the slots that fired in each
+        cycle.  want_record: return the round's record dict instead of (fail, took_b)."""
         m = self.error_models[model]
         gates = m["gates"]
         st = _sv.StateVector(N_QUBITS)
@@ -373,16 +376,25 @@ class ShotOracle:
         synd_a = np.array(self.stabilizer_cycle(st, leaked, gates, e_probs, rnd, meas))
         flips_a = (quiescent - synd_a) % 2
         took_b = 0
+        synd_b = None
         if np.all(flips_a == 0):
             ft = flips_a
         else:
-            synd_b = np.array(self.stabilizer_cycle(st, leaked, gates, e_probs, rnd, meas))
+            synd_b = np.array(self.stabilizer_cycle(st, leaked, gates, e_probs if e_probs_b is None else e_probs_b, rnd, meas))
             took_b = 1
             flips_b = (synd_a - synd_b) % 2
             ft = (flips_a + flips_b) % 2
         vec = self.lookup(ft)
         self.apply_correction(st, vec)
         logic, dm = self.logical_measurement(st, basis, quiescent, leaked, meas)
+        if want_record:
+            rec = {"quiescent": [int(b) for b in quiescent], "synd1": [int(b) for b in synd_a],
+                   "flips_a": [int(b) for b in flips_a], "not0": int(took_b), "counted": 1,
+                   "ft_syndrome": [int(b) for b in ft], "correction": [int(b) for b in vec], "data_meas": dm,
+                   "logical_meas": int(logic), "fail": int(logic != state), "leaked": list(leaked)}
+            if synd_b is not None:
+                rec["synd2"] = [int(b) for b in synd_b]
+            return rec
         return int(logic != state), took_b
 
 

@@ -21,6 +21,8 @@ PROTO_SINGLE, PROTO_S1, PROTO_S2, PROTO_RTF = 0, 1, 2, 3
 NOISE_PROB, NOISE_SUBSET, NOISE_REPLAY = 0, 1, 2
 STOP_NONE, STOP_AFTER_PREP, STOP_CYCLE1_GATES, STOP_AFTER_CYCLE1, STOP_AFTER_CORRECTION = 0, 1, 2, 3, 4
 F_NOT0, F_COUNTED, F_FAIL, F_ERROR, F_SYND2 = 1, 2, 4, 8, 16
+LEAK_RESET = {"never": 0, "run": 1, "round": 2}
+MEAS_SAMPLE, MEAS_LOCKSTEP, MEAS_FORCED = 0, 1, 2
 
 
 class Uop(C.Structure):
@@ -53,7 +55,8 @@ class RunArgs(C.Structure):
                 ("n_shots", C.c_uint64), ("seed", C.c_uint64), ("logical_state", C.c_uint32),
                 ("basis_x", C.c_uint32), ("materialize", C.c_uint32), ("stop_stage", C.c_uint32),
                 ("stop_layers", C.c_uint32), ("forced", C.c_uint32), ("rtf_runs", C.c_uint32),
-                ("rtf_max_rounds", C.c_uint32)]
+                ("rtf_max_rounds", C.c_uint32), ("leak_reset", C.c_uint32), ("rtf_poll", C.c_uint32),
+                ("rtf_round_budget", C.c_uint64), ("rtf_chain_runs", C.c_uint32), ("pad0", C.c_uint32)]
 
 
 class Counts(C.Structure):
@@ -76,11 +79,14 @@ class ProgramInfo(C.Structure):
 
 
 assert C.sizeof(Uop) == 8 and C.sizeof(Op) == 72 and C.sizeof(Layer) == 1160
-assert C.sizeof(PInstr) == 12 and C.sizeof(Record) == 60 and C.sizeof(RunArgs) == 64
+assert C.sizeof(PInstr) == 12 and C.sizeof(Record) == 60 and C.sizeof(RunArgs) == 88
 
 EXPORTS = ("s17_create", "s17_destroy", "s17_last_error", "s17_device_count", "s17_load_program", "s17_describe_program",
            "s17_load_tables", "s17_set_slot_probs", "s17_set_subset", "s17_set_replay", "s17_run",
-           "s17_read_records", "s17_read_masks", "s17_read_events", "s17_read_state", "s17_read_rtf", "s17_last_timing")
+           "s17_read_records", "s17_read_masks", "s17_read_events", "s17_read_state", "s17_read_rtf", "s17_last_timing",
+           "s17_rtf_begin", "s17_rtf_step", "s17_rtf_end", "s17_read_rtf_slots",
+           "s17_eng_create", "s17_eng_destroy", "s17_eng_last_error", "s17_eng_reset", "s17_eng_gate1", "s17_eng_gate2",
+           "s17_eng_measure", "s17_eng_prob1", "s17_eng_flush", "s17_eng_read_state", "s17_eng_timing")
 
 _LIB = None
 
@@ -120,8 +126,25 @@ def load():
     L.s17_read_rtf.argtypes = [vp, C.POINTER(u32), C.POINTER(u32), u64]
     L.s17_last_timing.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                   C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_double)]
+    L.s17_rtf_begin.argtypes = [vp, C.POINTER(RunArgs)]
+    L.s17_rtf_step.argtypes = [vp, u32, C.POINTER(u64), C.POINTER(u64)]
+    L.s17_rtf_end.argtypes = [vp, C.POINTER(Counts)]
+    L.s17_read_rtf_slots.argtypes = [vp, C.POINTER(u32), u64]
+    dp, bp = C.POINTER(C.c_double), C.c_void_p
+    L.s17_eng_create.argtypes = [C.POINTER(vp), i32, u32, u64, u64]
+    L.s17_eng_destroy.argtypes = [vp]
+    L.s17_eng_last_error.argtypes = [vp]
+    L.s17_eng_last_error.restype = C.c_char_p
+    L.s17_eng_reset.argtypes = [vp]
+    L.s17_eng_gate1.argtypes = [vp, u32, dp, bp]
+    L.s17_eng_gate2.argtypes = [vp, u32, u32, dp, bp]
+    L.s17_eng_measure.argtypes = [vp, u32, u32, bp, bp, dp, C.POINTER(u32)]
+    L.s17_eng_prob1.argtypes = [vp, u32, dp]
+    L.s17_eng_flush.argtypes = [vp]
+    L.s17_eng_read_state.argtypes = [vp, u64, dp]
+    L.s17_eng_timing.argtypes = [vp, dp, C.POINTER(u64), i32]
     for name in EXPORTS:
-        if name != "s17_last_error":
+        if name not in ("s17_last_error", "s17_eng_last_error"):
             getattr(L, name).restype = i32
     _LIB = L
     return L

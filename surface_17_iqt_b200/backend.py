@@ -155,8 +155,9 @@ class Backend:
                                           None if o is None else o.ctypes.data, os_))
 
     # ---- execution ------------------------------------------------------------------------------
-    def run(self, protocol, n_shots, noise, seed=0, first_shot_id=0, logical_state=0, materialize=False,
-            stop_stage=L.STOP_NONE, stop_layers=0, forced=False, rtf_runs=0, rtf_max_rounds=0):
+    def _args(self, protocol, n_shots, noise, seed=0, first_shot_id=0, logical_state=0, materialize=False,
+              stop_stage=L.STOP_NONE, stop_layers=0, forced=False, rtf_runs=0, rtf_max_rounds=0, leak_reset="run",
+              rtf_poll=0, rtf_round_budget=0, rtf_chain_runs=0):
         a = L.RunArgs()
         a.protocol = PROTOCOLS[protocol] if isinstance(protocol, str) else int(protocol)
         a.noise = int(noise)
@@ -164,10 +165,39 @@ class Backend:
         a.logical_state, a.basis_x = int(logical_state), 0
         a.materialize, a.stop_stage, a.stop_layers = int(materialize), int(stop_stage), int(stop_layers)
         a.forced, a.rtf_runs, a.rtf_max_rounds = int(forced), int(rtf_runs), int(rtf_max_rounds)
+        a.leak_reset = L.LEAK_RESET[leak_reset] if isinstance(leak_reset, str) else int(leak_reset)
+        a.rtf_poll, a.rtf_round_budget, a.rtf_chain_runs = int(rtf_poll), int(rtf_round_budget), int(rtf_chain_runs)
+        return a
+
+    def run(self, protocol, n_shots, noise, **kw):
+        """One batch of shots of `protocol` ('single' | 's1' | 's2' | 'rtf'); keyword arguments as in `_args`."""
+        a = self._args(protocol, n_shots, noise, **kw)
         c = L.Counts()
         self._ck(self._lib.s17_run(self._h, C.byref(a), C.byref(c)))
         self.last_counts = c
         return c
+
+    # run-til-fail as a job (s17_rtf_begin / _step / _end): lets a caller look at every round
+    def rtf_begin(self, n_slots, noise, **kw):
+        a = self._args("rtf", n_slots, noise, **kw)
+        self._ck(self._lib.s17_rtf_begin(self._h, C.byref(a)))
+
+    def rtf_step(self, n_rounds=1):
+        alive, rounds = C.c_uint64(), C.c_uint64()
+        self._ck(self._lib.s17_rtf_step(self._h, int(n_rounds), C.byref(alive), C.byref(rounds)))
+        return alive.value, rounds.value
+
+    def rtf_end(self):
+        c = L.Counts()
+        self._ck(self._lib.s17_rtf_end(self._h, C.byref(c)))
+        self.last_counts = c
+        return c
+
+    def rtf_slots(self, n):
+        """[n][4] uint32: run id, rounds so far, second syndromes so far, alive."""
+        buf = np.zeros((n, 4), dtype=np.uint32)
+        self._ck(self._lib.s17_read_rtf_slots(self._h, buf.ctypes.data_as(C.POINTER(C.c_uint32)), n))
+        return buf
 
     def timing(self):
         g, m, o, sp = C.c_double(), C.c_double(), C.c_double(), C.c_double()
@@ -206,6 +236,12 @@ class Backend:
         bits = ((buf[:, :, None] >> np.arange(32, dtype=np.uint32)[None, None, :]) & 1).astype(np.uint8)
         bits = bits.reshape(n, 2, L.MASK_WORDS * 32)
         return bits[:, :, :total]
+
+    def masks_packed(self, n):
+        """The same as bit sets: uint32 [n][2 * MASK_WORDS], bit b of word w of a half = slot 32 w + b."""
+        buf = np.zeros((n, 2 * L.MASK_WORDS), dtype=np.uint32)
+        self._ck(self._lib.s17_read_masks(self._h, buf.ctypes.data_as(C.POINTER(C.c_uint32)), n))
+        return buf
 
     def events(self, n):
         buf = np.zeros((n, L.EV_WORDS), dtype=np.uint32)

@@ -141,25 +141,26 @@ def _run_subset_once(protocol, num_runs, correction_table, model, eset, location
     sim = _simulation(model, list(locations), cooling, correction_table, bitflip_table)
     weights = [None if len(p) == 1 else list(p) for p in prob_lists]     # CL:287: one entry => uniform placement
     sim.backend.set_subset(eset, locations, weights)
-    seed = random.getrandbits(64)
+    seed = distributed.broadcast_seed(random.getrandbits(64))
     rank, world_size = distributed.world()
     first, count = distributed.shard_range(num_runs, rank, world_size)
-    failed = not0 = counted = 0
+    failed = not0 = counted = errors = 0
     gate_ms = span_ms = 0.0
     sweeps = launches = sweep_bytes = 0
     done = 0
     while done < count:
         n = min(sim.max_shots, count - done)
         c = sim.backend.run(protocol, n, L.NOISE_SUBSET, seed=seed, first_shot_id=first + done)
-        if c.errors:
-            raise L.S17Error("{} shots hit a zero-probability outcome".format(c.errors))
         t = sim.backend.timing()
-        failed, not0, counted = failed + c.failed, not0 + c.not0, counted + c.counted
+        failed, not0, counted, errors = failed + c.failed, not0 + c.not0, counted + c.counted, errors + c.errors
         gate_ms, span_ms = gate_ms + t["gate_ms"], span_ms + t["span_ms"]
         sweeps, launches = sweeps + c.sweeps, launches + t["launches"]
         sweep_bytes += c.sweep_bytes
         done += n
-    failed, not0, counted = distributed.allreduce_counts([failed, not0, counted])
+    # the error count rides in the reduced vector: every rank leaves the collective before any of them raises
+    failed, not0, counted, errors = distributed.allreduce_counts([failed, not0, counted, errors])
+    if errors:
+        raise L.S17Error("{} shots hit a zero-probability outcome".format(errors))
     LAST_TIMING.update(gate_ms=gate_ms, span_ms=span_ms, sweeps=sweeps, sweep_bytes=sweep_bytes, launches=launches,
                        shots=count)
     return failed, not0, counted
@@ -167,7 +168,11 @@ def _run_subset_once(protocol, num_runs, correction_table, model, eset, location
 
 def calculate_log_e_rate_error_subset(num_runs, correction_table, model, eset, locations, bitflip_table,
                                       prob_lists, cz_comp=False):
-    """CL:183-259: single round, always decode flips_a.  Returns failed_count / num_runs."""
+    """CL:183-259: single round, always decode flips_a.  Returns failed_count / num_runs.
+
+    Deviation: the reference chooses non-uniform placement for EVERY error type as soon as prob_lists[0] is a list
+    (CL:207-214), which for a one-element list always places the error on location 0; here a one-element list means
+    uniform placement, as in the s1 / s2 drivers (CL:287)."""
     t_begin = time.perf_counter()
     if not isinstance(prob_lists[0], list):      # CL:207: a flat list of floats means uniform placement
         prob_lists = [[p] for p in prob_lists]
@@ -238,15 +243,18 @@ def _true_probability_once(num_runs, correction_table, model, p_set, bitflip_tab
     names = sim.model["probabilities"]
     sim.backend.set_slot_probs([[0.0] * len(p) if (over_angles and names[i] in over_angles) else p
                                 for i, p in enumerate(p_set)])
-    seed = random.getrandbits(64)
+    seed = distributed.broadcast_seed(random.getrandbits(64))
     rank, world_size = distributed.world()
     first, count = distributed.shard_range(num_runs, rank, world_size)
-    failed = not0 = counted = done = 0
+    failed = not0 = counted = errors = done = 0
     while done < count:
         n = min(sim.max_shots, count - done)
         c = sim.backend.run(protocol, n, L.NOISE_PROB, seed=seed, first_shot_id=first + done)
         failed, not0, counted, done = failed + c.failed, not0 + c.not0, counted + c.counted, done + n
-    failed, not0, counted = distributed.allreduce_counts([failed, not0, counted])
+        errors += c.errors
+    failed, not0, counted, errors = distributed.allreduce_counts([failed, not0, counted, errors])
+    if errors:
+        raise L.S17Error("{} shots hit a zero-probability outcome".format(errors))
     return (failed / counted if counted else None), failed, counted, not0
 
 
@@ -267,11 +275,18 @@ def fit_log_e_rate(results, num_bins, include_b=False):
 
 
 def calculate_log_e_rate(num_runs, filename, correction_table, e_model, e_probs, bitflip_table, num_bins=20,
-                         cz_compilation=False, model_name=None, save=True):
+                         cz_compilation=False, model_name=None, save=True, leak_reset="run", max_rounds=0,
+                         round_budget=0, fit=True):
     """CL:33-148: run-til-fail with true Bernoulli noise, JSON dump and exponential fit; returns log_e_rate.
 
-    `e_model` is the model dict returned by instantiate_error_model (or its name), `e_probs` the
-    {name: list} dict.  Deviation (SURVEY C-6): the leak register is reset at the start of every run.
+    `e_model` is the model dict returned by instantiate_error_model (or its name), `e_probs` the {name: list} dict.
+    leak_reset: when the leak register is cleared -- 'run' (default; documented deviation, SURVEY C-6), 'round', or
+    'never', the reference's literal behaviour (CL:49: one register for the whole call; here one per device slot, a slot
+    being one sequential chain of runs).
+    Under torch.distributed the runs are sharded over the ranks (each rank's slots are independent chains), the lists
+    are concatenated in rank order, and rank 0 alone writes data/<filename>.json.
+    max_rounds / round_budget (extensions): cap the rounds of one run / the total number of rounds of the call; runs the
+    caps cut short are reported with their censored length in 'censored_runs' and excluded from the fit.
     """
     if cz_compilation:
         raise NotImplementedError("the experimental CZ compilation is outside the accelerated path (SURVEY C-9)")
@@ -279,41 +294,74 @@ def calculate_log_e_rate(num_runs, filename, correction_table, e_model, e_probs,
     if isinstance(e_model, str):
         model_name, e_model = e_model, models[e_model]
     if model_name is None:
-        model_name = next(k for k, v in models.items() if v == e_model)
+        model_name = next((k for k, v in models.items() if v == e_model), None)
+        if model_name is None:
+            raise ValueError("e_model is not one of the models in error_models.json; pass model_name= for a custom model "
+                             "that the file in the working directory defines")
     names = e_model['probabilities']
     p_set = [list(e_probs[k]) for k in names]
     need = circuit.list_lengths(e_model)
     for k, plist, n in zip(names, p_set, need):
         if len(plist) < n:
             raise IndexError("probability list {} has {} entries, the cycle indexes {}".format(k, len(plist), n))
-    seed = random.getrandbits(64)
+    seed = distributed.broadcast_seed(random.getrandbits(64))
+    rank, world_size = distributed.world()
+    _first, my_runs = distributed.shard_range(num_runs, rank, world_size)
     t_begin = time.perf_counter()
 
     def run_once():
         sim_ = _simulation(model_name, [len(p) for p in p_set], False, correction_table, bitflip_table)
         sim_.backend.set_slot_probs(p_set)
-        return sim_, sim_.backend.run("rtf", min(sim_.max_shots, num_runs), L.NOISE_PROB, seed=seed, rtf_runs=num_runs)
+        if my_runs == 0:
+            return sim_, None
+        slots = min(sim_.max_shots, my_runs)
+        # the Philox counter is (first_shot_id + slot): rank r's slots continue where rank r-1's end
+        return sim_, sim_.backend.run("rtf", slots, L.NOISE_PROB, seed=seed, first_shot_id=rank * sim_.max_shots,
+                                      rtf_runs=my_runs, leak_reset=leak_reset, rtf_max_rounds=max_rounds,
+                                      rtf_round_budget=round_budget)
 
     sim, c = _with_batch_retry(run_once)
-    rounds, syndb = sim.backend.rtf_results(num_runs)
+    if c is not None:
+        rounds, syndb = sim.backend.rtf_results(my_runs)
+        my_rounds, my_syndb, my_total, my_errors = [int(v) for v in rounds], [int(v) for v in syndb], int(c.rounds), int(c.errors)
+        span_ms = sim.backend.timing()["span_ms"]
+    else:
+        my_rounds, my_syndb, my_total, my_errors, span_ms = [], [], 0, 0, 0.0
+    round_count_list = distributed.gather_lists(my_rounds)
+    syndrome_b_list = distributed.gather_lists(my_syndb)
+    total_rounds, errors = distributed.allreduce_counts([my_total, my_errors])
+    if errors:
+        raise L.S17Error("{} rounds hit a zero-probability outcome".format(errors))
     total_time_taken = time.perf_counter() - t_begin
-    round_count_list = [int(v) for v in rounds]
     _log('total time taken {}'.format(total_time_taken))
+    censored = [i for i, r in enumerate(round_count_list) if r == 0]         # cut short by round_budget
+    if max_rounds:
+        censored += [i for i, r in enumerate(round_count_list) if r >= max_rounds]
     results = {
         'total_time_taken_{}_runs'.format(num_runs): total_time_taken,
         'probability_set': e_probs,
         'rounds_til_fail_list': round_count_list,
-        'syndrome_b_measured_list': [int(v) for v in syndb],
+        'syndrome_b_measured_list': syndrome_b_list,
         'rounds_til_fail_list_X0': [], 'rounds_til_fail_list_X1': [],
         'rounds_til_fail_list_Z0': round_count_list, 'rounds_til_fail_list_Z1': [],
         'error_model': e_model,
     }
-    LAST_TIMING.update(rounds=int(c.rounds), span_ms=sim.backend.timing()["span_ms"])
-    if save:
+    if censored:
+        results['censored_runs'] = sorted(set(censored))
+    results['total_rounds'] = int(total_rounds)
+    LAST_TIMING.update(rounds=int(total_rounds), span_ms=span_ms)
+    if save and rank == 0:
         os.makedirs("data", exist_ok=True)
         with open(os.path.join("data", filename + '.json'), 'w') as file:
             json.dump(results, file)
-    log_e_rate, _A, _vals, _bins = fit_log_e_rate(results, num_bins)
+    if not fit:
+        return None
+    done = dict(results)
+    if censored:
+        skip = set(censored)
+        done['rounds_til_fail_list'] = [r for i, r in enumerate(round_count_list) if i not in skip]
+        done['syndrome_b_measured_list'] = [r for i, r in enumerate(syndrome_b_list) if i not in skip]
+    log_e_rate, _A, _vals, _bins = fit_log_e_rate(done, num_bins)
     return log_e_rate
 
 

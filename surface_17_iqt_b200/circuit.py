@@ -168,8 +168,13 @@ def _uop(type_, sign=0, skippable=0, ev_shift=255, param=0):
     return u
 
 
-def compile_program(model, list_len, fusion=1, cooling=False, over_angles=None, early_measure=False) -> Program:
+def compile_program(model, list_len, fusion=1, cooling=False, over_angles=None, early_measure=False, ops=None,
+                    slots=None, idle_slots=None) -> Program:
     """Compile `model` (one entry of error_models.json) for lists of total length `list_len`.
+
+    ops / slots / idle_slots: the cycle table, the slot of every error entry {(operation, gate position, entry number):
+    slot} and of every idle entry {(timestep, qubit): slot} as TRACED from a module's own stabilizer_cycle_error_index
+    (tracer.trace_cycle); default: this module's table (build_cycle) and rule (slot_index).
 
     fusion: 0 = one sweep per gate (ProjectQ's execution model), 1 = one sweep per timestep,
             2 = one sweep per two timesteps, 4 = one sweep per four timesteps (8192-amplitude tiles).
@@ -185,7 +190,7 @@ def compile_program(model, list_len, fusion=1, cooling=False, over_angles=None, 
         raise ValueError("make sure you pass enough probabilities to specify the error model - see error_model.json")
     if cooling and "Idle" not in model["gates"]:
         raise KeyError("Idle")     # the reference raises KeyError at error_model['gates'][gate] (CS:132)
-    ops = build_cycle()
+    ops = list(ops) if ops is not None else build_cycle()
     prog = Program(list_len=list(list_len), fusion=fusion)
     over_angles = over_angles or {}
 
@@ -216,14 +221,15 @@ def compile_program(model, list_len, fusion=1, cooling=False, over_angles=None, 
                 rx_i = op.rx_ind if gate == "Rx" else 0
                 ry_i = run_ind if gate == "Ry" else 0
                 seen_pauli = False
-                for err, pname, *_ in model["gates"].get(gate, []):
+                for k_entry, (err, pname, *_) in enumerate(model["gates"].get(gate, [])):
                     lid = names.index(pname)
                     if err in _OVER:
                         if seen_pauli:
                             raise NotImplementedError("coherent entries must precede stochastic ones in a gate's list")
                         continue                      # deterministic: lives in the gate stream, not the plan
                     seen_pauli = True
-                    slot = slot_index(pname, gate, err, rx_i, ry_i, op.index)
+                    slot = (slots[(op.index, pos, k_entry)] if slots is not None else
+                            slot_index(pname, gate, err, rx_i, ry_i, op.index))
                     kw = dict(kind=L.P_ERR, list=lid, slot=slot, field=FIELD_OF_GATE[pos], word=op.index,
                               in_skip=int(gate == "Rxx"), use_round=1)
                     c_ind, t_ind = (op.a_leak, op.d_leak) if op.kind == "x" else (op.d_leak, op.a_leak)  # CS:297, 326
@@ -276,7 +282,8 @@ def compile_program(model, list_len, fusion=1, cooling=False, over_angles=None, 
                         done = [o for o in half_ops if o.ancilla == q - N_DATA and o.timestep <= t]
                         if done:
                             fld, pad = half_ops.index(done[-1]), done[-1].index
-                    emit(kind=L.P_IDLE, err=L.ERR_Z, list=names.index(pname), slot=t * 17 + q, a=q, word=24 + t,
+                    emit(kind=L.P_IDLE, err=L.ERR_Z, list=names.index(pname),
+                         slot=idle_slots[(t, q)] if idle_slots is not None else t * 17 + q, a=q, word=24 + t,
                          use_round=0, b=b, field=fld, pad=pad)
 
     # ---- gate stream ------------------------------------------------------------------------

@@ -28,11 +28,12 @@
 #include "s17_layer2.cuh"
 #include "s17_layer3.cuh"
 #include "s17_layer4.cuh"
+#include "s17_engine.cuh"
 
 namespace s17 {
 
 enum { C_FAILED = 0, C_NOT0 = 1, C_COUNTED = 2, C_ERRORS = 3, C_SWEEPS = 4, C_ROUNDS = 5, C_NEXT_RUN = 6, C_ALIVE = 7,
-       C_RUNS_MOVED = 8, C_N = 10 };
+       C_RUNS_MOVED = 8, C_RUNS_DONE = 9, C_N = 10 };
 
 // =================================================================================================
 // gate sweep
@@ -865,52 +866,132 @@ __global__ void k_reset(int n_shots, uint32_t *leak, uint8_t *active, uint8_t *r
         for (int i = 0; i < 2 * (int)S17_MASK_WORDS; ++i) masks[(size_t)shot * 2 * S17_MASK_WORDS + i] = 0;
 }
 
-// run-til-fail bookkeeping (CL:52-127): one slot = one run in flight; a failed run frees its slot for the next run id
+// run-til-fail bookkeeping (CL:52-127): one slot = one run in flight; a failed run frees its slot for the next run id.
+// alive: 0 idle, 1 running, 2 finished in the round that just ended (between k_rtf_finish and k_rtf_assign)
 struct RtfSlot { uint32_t run_id, rounds, synd_b, alive; };
+constexpr int kRtfThreads = 256;
 
-__global__ void k_rtf_init(int n_slots, uint32_t total_runs, RtfSlot *slots, unsigned long long *counters)
+__global__ void k_rtf_init(int n_slots, uint32_t total_runs, uint32_t chain, RtfSlot *slots, uint32_t *leak,
+                           unsigned long long *counters)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_slots) return;
     RtfSlot sl;
-    sl.run_id = (uint32_t)s; sl.rounds = 0; sl.synd_b = 0; sl.alive = (uint32_t)s < total_runs;
+    sl.run_id = chain ? (uint32_t)s * chain : (uint32_t)s; sl.rounds = 0; sl.synd_b = 0; sl.alive = sl.run_id < total_runs;
     slots[s] = sl;
+    leak[s] = 0;
     if (s == 0) { counters[C_NEXT_RUN] = (unsigned long long)min((uint32_t)n_slots, total_runs); }
 }
 
-__global__ void k_rtf_begin_round(int n_slots, const RtfSlot *slots, uint8_t *active, uint8_t *ready, s17_record *rec)
+__global__ void k_rtf_begin_round(int n_slots, const RtfSlot *slots, uint8_t *active, uint8_t *ready, s17_record *rec,
+                                  uint32_t *leak, int reset_leak /* leak_reset = round */)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_slots) return;
-    active[s] = (uint8_t)slots[s].alive;
+    active[s] = (uint8_t)(slots[s].alive != 0);
     ready[s] = 0;
+    if (reset_leak) leak[s] = 0;
     s17_record z;
     memset(&z, 0, sizeof(z));
     rec[s] = z;
 }
 
-__global__ void k_rtf_end_round(int n_slots, uint32_t total_runs, uint32_t max_rounds, RtfSlot *slots,
-                                const s17_record *rec, uint32_t *leak, uint32_t *rounds_out, uint32_t *syndb_out,
-                                unsigned long long *counters)
+// End of a round, pass 1: count the round, close the runs that failed (or hit the cap), and count them per block.  The
+// block that finishes last turns the per-block counts into exclusive offsets: the freed slots then take the next run ids
+// in SLOT ORDER (k_rtf_assign), so the labelling of the runs is reproducible (no race on a shared counter).
+__global__ void __launch_bounds__(kRtfThreads)
+k_rtf_finish(int n_slots, uint32_t max_rounds, RtfSlot *slots, const s17_record *rec, uint32_t *rounds_out, uint32_t *syndb_out,
+             uint32_t *block_cnt, uint32_t *block_off, unsigned long long *counters, uint32_t *ticket)
 {
+    __shared__ uint32_t s_w[kRtfThreads / 32], s_r[kRtfThreads / 32];
+    __shared__ bool s_last;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n_slots) return;
-    RtfSlot sl = slots[s];
-    if (!sl.alive) return;
-    const s17_record r = rec[s];
-    sl.rounds += 1;
-    if (r.flags & S17_F_SYND2) sl.synd_b += 1;
-    atomicAdd(&counters[C_ROUNDS], 1ull);
-    const bool fail = (r.flags & S17_F_FAIL) != 0;
-    if (fail || (max_rounds && sl.rounds >= max_rounds)) {
-        rounds_out[sl.run_id] = sl.rounds;
-        syndb_out[sl.run_id] = sl.synd_b;
-        const unsigned long long nxt = atomicAdd(&counters[C_NEXT_RUN], 1ull);
-        if (nxt < total_runs) { sl.run_id = (uint32_t)nxt; sl.rounds = 0; sl.synd_b = 0; leak[s] = 0; }
-        else { sl.alive = 0; }
+    bool ran = false, fin = false;
+    if (s < n_slots) {
+        RtfSlot sl = slots[s];
+        if (sl.alive) {
+            ran = true;
+            const s17_record r = rec[s];
+            sl.rounds += 1;
+            if (r.flags & S17_F_SYND2) sl.synd_b += 1;
+            if ((r.flags & S17_F_FAIL) || (max_rounds && sl.rounds >= max_rounds)) {
+                fin = true;
+                rounds_out[sl.run_id] = sl.rounds;
+                syndb_out[sl.run_id] = sl.synd_b;
+                sl.alive = 2;
+            }
+            slots[s] = sl;
+        }
     }
-    if (sl.alive) atomicAdd(&counters[C_ALIVE], 1ull);
-    slots[s] = sl;
+    const uint32_t bf = __ballot_sync(0xffffffffu, fin), br = __ballot_sync(0xffffffffu, ran);
+    if ((threadIdx.x & 31) == 0) { s_w[threadIdx.x >> 5] = __popc(bf); s_r[threadIdx.x >> 5] = __popc(br); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t nf = 0, nr = 0;
+        for (int w = 0; w < kRtfThreads / 32; ++w) { nf += s_w[w]; nr += s_r[w]; }
+        block_cnt[blockIdx.x] = nf;
+        if (nr) atomicAdd(&counters[C_ROUNDS], (unsigned long long)nr);
+        __threadfence();
+        s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // exclusive scan of the block counts by the last block (<= a few thousand entries)
+    __shared__ uint32_t s_sum[kRtfThreads];
+    const int nb = gridDim.x, per = (nb + kRtfThreads - 1) / kRtfThreads;
+    uint32_t mine = 0;
+    for (int i = 0; i < per; ++i) {
+        const int b = threadIdx.x * per + i;
+        if (b < nb) mine += reinterpret_cast<volatile uint32_t *>(block_cnt)[b];
+    }
+    s_sum[threadIdx.x] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int t = 0; t < kRtfThreads; ++t) { const uint32_t v = s_sum[t]; s_sum[t] = run; run += v; }
+        counters[C_RUNS_DONE] = counters[C_NEXT_RUN];            // base id of this round's re-assignments
+        counters[C_NEXT_RUN] += run;
+        *ticket = 0;
+    }
+    __syncthreads();
+    uint32_t run = s_sum[threadIdx.x];
+    for (int i = 0; i < per; ++i) {
+        const int b = threadIdx.x * per + i;
+        if (b < nb) { block_off[b] = run; run += reinterpret_cast<volatile uint32_t *>(block_cnt)[b]; }
+    }
+}
+
+// End of a round, pass 2: freed slots take run ids base + rank (rank = position among the freed slots in slot order)
+// while ids remain; count the slots that go on.
+__global__ void __launch_bounds__(kRtfThreads)
+k_rtf_assign(int n_slots, uint32_t total_runs, uint32_t chain, RtfSlot *slots, uint32_t *leak, const uint32_t *block_off,
+             unsigned long long *counters, int reset_leak /* leak_reset = run */)
+{
+    __shared__ uint32_t s_w[kRtfThreads / 32];
+    const int s = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    RtfSlot sl;
+    sl.alive = 0;
+    if (s < n_slots) sl = slots[s];
+    const bool fin = sl.alive == 2;
+    const uint32_t bf = __ballot_sync(0xffffffffu, fin);
+    if (lane == 0) s_w[w] = __popc(bf);
+    __syncthreads();
+    if (fin) {
+        uint32_t rank = block_off[blockIdx.x] + __popc(bf & ((1u << lane) - 1u));
+        for (int i = 0; i < w; ++i) rank += s_w[i];
+        unsigned long long id = counters[C_RUNS_DONE] + rank;
+        if (chain) id = (sl.run_id % chain) + 1u < chain ? (unsigned long long)sl.run_id + 1u : (unsigned long long)total_runs;
+        if (id < total_runs) {
+            sl.run_id = (uint32_t)id; sl.rounds = 0; sl.synd_b = 0; sl.alive = 1;
+            if (reset_leak) leak[s] = 0;
+        } else {
+            sl.alive = 0;
+        }
+        slots[s] = sl;
+    }
+    const uint32_t ba = __ballot_sync(0xffffffffu, sl.alive == 1);
+    if (lane == 0 && ba) atomicAdd(&counters[C_ALIVE], (unsigned long long)__popc(ba));
 }
 
 }  // namespace s17
@@ -940,7 +1021,11 @@ struct s17_ctx {
     uint32_t *plan_hot = nullptr;
     RtfSlot *rtf_slots = nullptr;
     uint32_t *rtf_rounds = nullptr, *rtf_syndb = nullptr;
+    uint32_t *rtf_block_cnt = nullptr, *rtf_block_off = nullptr, *rtf_ticket = nullptr;
     uint64_t rtf_capacity = 0;
+    s17_run_args rtf_args{};          // the run-til-fail job in progress (s17_rtf_begin .. s17_rtf_end)
+    uint64_t rtf_round_no = 0, rtf_alive = 0, rtf_rounds_total = 0;
+    bool rtf_open = false;
     int n_plan = 0;
     std::vector<LayerArg> layers[3];   // prep, first noisy cycle, second noisy cycle
     std::vector<LayerArg2> layers2[3], layers2d[3];   // support-aware / dense variants
@@ -985,6 +1070,7 @@ struct s17_ctx {
     NoiseDev nd{};
     uint32_t total_slots = 0;
     bool have_program = false, have_tables = false, have_replay = false;
+    bool two_round_lists = false;     // every use_round entry satisfies slot + len/2 < len (needed by a stab_ind=1 cycle)
     uint64_t last_n = 0;
     // timing
     std::vector<cudaEvent_t> ev_pool;
@@ -1072,6 +1158,10 @@ extern "C" int s17_create(s17_ctx **out, int device, uint64_t max_shots) {
     CK(cudaMalloc(&ctx->probs, 2048 * sizeof(double)));
     CK(cudaMalloc(&ctx->cum, 2048 * sizeof(double)));
     CK(cudaMalloc(&ctx->rtf_slots, B * sizeof(RtfSlot)));
+    CK(cudaMalloc(&ctx->rtf_block_cnt, (B / kRtfThreads + 1) * 4));
+    CK(cudaMalloc(&ctx->rtf_block_off, (B / kRtfThreads + 1) * 4));
+    CK(cudaMalloc(&ctx->rtf_ticket, 4));
+    CK(cudaMemset(ctx->rtf_ticket, 0, 4));
     CK(cudaMemset(ctx->probs, 0, 2048 * sizeof(double)));
     CK(cudaMemset(ctx->leak, 0, B * 4));
     CK(cudaMemset(ctx->ev, 0, B * S17_EV_WORDS * 4));
@@ -1162,7 +1252,7 @@ extern "C" int s17_destroy(s17_ctx *ctx) {
     }
     void *ptrs[] = {ctx->state, ctx->ev, ctx->masks, ctx->leak, ctx->active, ctx->ready, ctx->forced, ctx->hist,
                     ctx->aux, ctx->rec, ctx->counters, ctx->lut, ctx->cw16, ctx->probs, ctx->cum, ctx->plan,
-                    ctx->rtf_slots, ctx->rtf_rounds, ctx->rtf_syndb, ctx->act_list, ctx->n_act, ctx->zero_page, ctx->meas_out,
+                    ctx->rtf_slots, ctx->rtf_rounds, ctx->rtf_syndb, ctx->rtf_block_cnt, ctx->rtf_block_off, ctx->rtf_ticket, ctx->act_list, ctx->n_act, ctx->zero_page, ctx->meas_out,
                     ctx->frm, ctx->dsamp, ctx->prep_leaf, ctx->prep_done, ctx->prep_blocks, ctx->prep_pp, ctx->plan_hot,
                     ctx->quiet_blocks, ctx->quiet_cdf, ctx->quiet_ok, ctx->quiet_flag};
     for (void *p : ptrs)
@@ -1746,6 +1836,11 @@ extern "C" int s17_load_program(s17_ctx *ctx, const s17_layer *layers, const uin
     CK(cudaMemset(ctx->probs, 0, 2048 * sizeof(double)));
     ctx->prep_basis = -1;
     ctx->plan_has_leak = false;
+    ctx->two_round_lists = true;
+    for (uint32_t i = 0; i < n_plan; ++i)
+        if ((plan[i].kind == S17_P_ERR || plan[i].kind == S17_P_IDLE) && plan[i].use_round &&
+            (uint32_t)plan[i].slot + (lists->list_len[plan[i].list] >> 1) >= lists->list_len[plan[i].list])
+            ctx->two_round_lists = false;
     for (uint32_t i = 0; i < n_plan; ++i)
         if (plan[i].kind == S17_P_ERR && (plan[i].err == S17_ERR_LEAK_A || plan[i].err == S17_ERR_LEAK_AB)) ctx->plan_has_leak = true;
     ctx->have_program = true;
@@ -2257,72 +2352,43 @@ static int finish_timing(s17_ctx *ctx) {
     return S17_OK;
 }
 
-extern "C" int s17_run(s17_ctx *ctx, const s17_run_args *args, s17_counts *out) {
-    if (!ctx || !args || !out) return fail(ctx, S17_E_ARG, "s17_run: bad arguments");
+static int check_run_args(s17_ctx *ctx, const s17_run_args &a) {
     if (!ctx->have_program || !ctx->have_tables) return fail(ctx, S17_E_STATE, "s17_run: load the program and tables first");
-    s17_run_args a = *args;
     if (a.n_shots == 0 || a.n_shots > ctx->max_shots) return fail(ctx, S17_E_ARG, "s17_run: n_shots out of range");
     if (a.protocol > S17_PROTO_RTF || a.noise > S17_NOISE_REPLAY) return fail(ctx, S17_E_ARG, "s17_run: bad protocol/noise");
+    if (a.leak_reset > S17_LEAK_RESET_ROUND) return fail(ctx, S17_E_ARG, "s17_run: bad leak_reset");
     if (a.basis_x) return fail(ctx, S17_E_ARG, "s17_run: X-basis preparation is not implemented (dead in the reference, CL:274)");
     if ((a.noise == S17_NOISE_REPLAY || a.forced) && !ctx->have_replay)
         return fail(ctx, S17_E_STATE, "s17_run: replay requested but s17_set_replay was not called");
+    if (a.protocol == S17_PROTO_S2 && !ctx->two_round_lists)
+        return fail(ctx, S17_E_ARG, "s17_run: the s2 protocol indexes the second half of every probability list (CS:191-193); "
+                                    "load the program with two-round list lengths");
+    if (ctx->rtf_open && a.protocol != S17_PROTO_RTF) return fail(ctx, S17_E_STATE, "s17_run: a run-til-fail job is open (s17_rtf_end)");
+    return S17_OK;
+}
+
+static int begin_call(s17_ctx *ctx, const s17_run_args &a) {
     CK(cudaSetDevice(ctx->device));
     ctx->t_gate = ctx->t_meas = ctx->t_other = 0;
     ctx->n_gate = ctx->n_all = 0;
     ctx->launches.clear();
     ctx->ev_used = 0;
-    const int n = (int)a.n_shots;
-    {
-        const bool all_diag = ctx->diag_ok[0] && ctx->diag_ok[1] && ctx->diag_ok[2] && !ctx->no_diag && !ctx->dense &&
-                              !ctx->use_v1 && !ctx->force_ring && !ctx->no_fuse && !a.materialize &&
-                              a.stop_stage == S17_STOP_NONE;
-        if (int rc = ensure_state(ctx, !all_diag)) return rc;
-    }
+    const bool all_diag = ctx->diag_ok[0] && ctx->diag_ok[1] && ctx->diag_ok[2] && !ctx->no_diag && !ctx->dense &&
+                          !ctx->use_v1 && !ctx->force_ring && !ctx->no_fuse && !a.materialize &&
+                          a.stop_stage == S17_STOP_NONE;
+    if (int rc = ensure_state(ctx, !all_diag)) return rc;
     CK(cudaEventRecord(ctx->span0, ctx->stream));
     CK(cudaMemsetAsync(ctx->counters, 0, C_N * sizeof(unsigned long long), ctx->stream));
+    const int n = (int)a.n_shots;
     {
         SCOPE(CAT_OTHER);
         k_reset<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(n, ctx->leak, ctx->active, ctx->ready, ctx->rec, ctx->masks,
                                                              a.noise == S17_NOISE_PROB, 0);
     }
-    if (a.noise == S17_NOISE_SUBSET) {
-        SCOPE(CAT_OTHER);
-        k_place<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(ctx->nd, ctx->cum, ctx->masks, a.seed, a.first_shot_id, n);
-    }
-    uint64_t shots_done = a.n_shots;
-    if (a.protocol != S17_PROTO_RTF) {
-        if (int rc = run_round(ctx, a)) return rc;
-        if (int rc = finish_timing(ctx)) return rc;
-    } else {
-        // run-til-fail (CL:33-148): every slot carries one run; rounds are fresh restarts (CL:70-73) that
-        // share only the leak register (reset per run here; the reference never resets it, CL:49)
-        if (a.rtf_runs == 0) return fail(ctx, S17_E_ARG, "s17_run: rtf_runs must be > 0");
-        if (ctx->rtf_capacity < a.rtf_runs) {
-            if (ctx->rtf_rounds) cudaFree(ctx->rtf_rounds);
-            if (ctx->rtf_syndb) cudaFree(ctx->rtf_syndb);
-            CK(cudaMalloc(&ctx->rtf_rounds, (size_t)a.rtf_runs * 4));
-            CK(cudaMalloc(&ctx->rtf_syndb, (size_t)a.rtf_runs * 4));
-            ctx->rtf_capacity = a.rtf_runs;
-        }
-        CK(cudaMemsetAsync(ctx->rtf_rounds, 0, (size_t)a.rtf_runs * 4, ctx->stream));
-        CK(cudaMemsetAsync(ctx->rtf_syndb, 0, (size_t)a.rtf_runs * 4, ctx->stream));
-        k_rtf_init<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(n, a.rtf_runs, ctx->rtf_slots, ctx->counters);
-        uint64_t round_no = 0;
-        for (;;) {
-            k_rtf_begin_round<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(n, ctx->rtf_slots, ctx->active, ctx->ready, ctx->rec);
-            s17_run_args ar = a;
-            ar.seed = a.seed + 0x9E3779B97F4A7C15ull * (round_no + 1);   // fresh Philox key per round
-            if (int rc = run_round(ctx, ar)) return rc;
-            CK(cudaMemsetAsync(ctx->counters + C_ALIVE, 0, sizeof(unsigned long long), ctx->stream));
-            k_rtf_end_round<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(n, a.rtf_runs, a.rtf_max_rounds, ctx->rtf_slots, ctx->rec,
-                                                                         ctx->leak, ctx->rtf_rounds, ctx->rtf_syndb, ctx->counters);
-            if (int rc = finish_timing(ctx)) return rc;
-            unsigned long long alive = 0;
-            CK(cudaMemcpy(&alive, ctx->counters + C_ALIVE, sizeof(alive), cudaMemcpyDeviceToHost));
-            ++round_no;
-            if (alive == 0) break;
-        }
-    }
+    return S17_OK;
+}
+
+static int end_call(s17_ctx *ctx, const s17_run_args &a, s17_counts *out) {
     unsigned long long c[C_N];
     CK(cudaEventRecord(ctx->span1, ctx->stream));
     CK(cudaMemcpyAsync(c, ctx->counters, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
@@ -2333,7 +2399,7 @@ extern "C" int s17_run(s17_ctx *ctx, const s17_run_args *args, s17_counts *out) 
         ctx->t_span = ms;
     }
     memset(out, 0, sizeof(*out));
-    out->shots = shots_done;
+    out->shots = a.n_shots;
     out->failed = c[C_FAILED];
     out->not0 = c[C_NOT0];
     out->counted = c[C_COUNTED];
@@ -2343,6 +2409,124 @@ extern "C" int s17_run(s17_ctx *ctx, const s17_run_args *args, s17_counts *out) 
     out->sweep_bytes = c[C_RUNS_MOVED] * (unsigned long long)kRunBytes;   // algorithmic HBM bytes moved by the gate sweeps
     ctx->last_n = a.n_shots;
     return S17_OK;
+}
+
+// ---- run-til-fail (CL:33-148) as a job: begin, step (a number of rounds for every live slot), end ---------------------
+// Every slot carries one run; rounds are fresh restarts (CL:70-73) that share only the leak register, which the
+// reference never clears (CL:49; S17_LEAK_RESET_NEVER, per slot here), or which is cleared per run / per round.
+extern "C" int s17_rtf_begin(s17_ctx *ctx, const s17_run_args *args) {
+    if (!ctx || !args) return fail(ctx, S17_E_ARG, "s17_rtf_begin: bad arguments");
+    s17_run_args a = *args;
+    a.protocol = S17_PROTO_RTF;
+    if (ctx->rtf_open) return fail(ctx, S17_E_STATE, "s17_rtf_begin: a run-til-fail job is already open");
+    if (int rc = check_run_args(ctx, a)) return rc;
+    if (a.rtf_runs == 0) return fail(ctx, S17_E_ARG, "s17_run: rtf_runs must be > 0");
+    if (a.rtf_chain_runs && (uint64_t)a.rtf_chain_runs * a.n_shots != a.rtf_runs)
+        return fail(ctx, S17_E_ARG, "s17_run: with rtf_chain_runs = K, rtf_runs must be n_shots * K");
+    if (a.noise == S17_NOISE_REPLAY || a.forced) return fail(ctx, S17_E_ARG, "s17_rtf_begin: run-til-fail samples its outcomes");
+    if (int rc = begin_call(ctx, a)) return rc;
+    const int n = (int)a.n_shots;
+    if (a.noise == S17_NOISE_SUBSET) {
+        SCOPE(CAT_OTHER);
+        k_place<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(ctx->nd, ctx->cum, ctx->masks, a.seed, a.first_shot_id, n);
+    }
+    if (ctx->rtf_capacity < a.rtf_runs) {
+        if (ctx->rtf_rounds) cudaFree(ctx->rtf_rounds);
+        if (ctx->rtf_syndb) cudaFree(ctx->rtf_syndb);
+        ctx->rtf_rounds = ctx->rtf_syndb = nullptr;
+        ctx->rtf_capacity = 0;
+        CK(cudaMalloc(&ctx->rtf_rounds, (size_t)a.rtf_runs * 4));
+        CK(cudaMalloc(&ctx->rtf_syndb, (size_t)a.rtf_runs * 4));
+        ctx->rtf_capacity = a.rtf_runs;
+    }
+    CK(cudaMemsetAsync(ctx->rtf_rounds, 0, (size_t)a.rtf_runs * 4, ctx->stream));
+    CK(cudaMemsetAsync(ctx->rtf_syndb, 0, (size_t)a.rtf_runs * 4, ctx->stream));
+    k_rtf_init<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(n, a.rtf_runs, a.rtf_chain_runs, ctx->rtf_slots, ctx->leak, ctx->counters);
+    ctx->rtf_args = a;
+    ctx->rtf_round_no = 0;
+    ctx->rtf_rounds_total = 0;
+    ctx->rtf_alive = std::min<uint64_t>(a.n_shots, a.rtf_runs);
+    ctx->rtf_open = true;
+    return S17_OK;
+}
+
+extern "C" int s17_rtf_step(s17_ctx *ctx, uint32_t n_rounds, uint64_t *alive, uint64_t *rounds_total) {
+    if (!ctx || !ctx->rtf_open) return fail(ctx, S17_E_STATE, "s17_rtf_step: no run-til-fail job is open");
+    CK(cudaSetDevice(ctx->device));
+    const s17_run_args &a = ctx->rtf_args;
+    const int n = (int)a.n_shots;
+    for (uint32_t k = 0; k < n_rounds; ++k) {
+        k_rtf_begin_round<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(n, ctx->rtf_slots, ctx->active, ctx->ready, ctx->rec,
+                                                                       ctx->leak, a.leak_reset == S17_LEAK_RESET_ROUND);
+        s17_run_args ar = a;
+        ar.seed = a.seed + 0x9E3779B97F4A7C15ull * (ctx->rtf_round_no + 1);   // fresh Philox key per round
+        if (int rc = run_round(ctx, ar)) return rc;
+        CK(cudaMemsetAsync(ctx->counters + C_ALIVE, 0, sizeof(unsigned long long), ctx->stream));
+        const int nb = blocks_for(n, kRtfThreads);
+        k_rtf_finish<<<nb, kRtfThreads, 0, ctx->stream>>>(n, a.rtf_max_rounds, ctx->rtf_slots, ctx->rec, ctx->rtf_rounds,
+                                                         ctx->rtf_syndb, ctx->rtf_block_cnt, ctx->rtf_block_off, ctx->counters,
+                                                         ctx->rtf_ticket);
+        k_rtf_assign<<<nb, kRtfThreads, 0, ctx->stream>>>(n, a.rtf_runs, a.rtf_chain_runs, ctx->rtf_slots, ctx->leak, ctx->rtf_block_off,
+                                                         ctx->counters, a.leak_reset == S17_LEAK_RESET_RUN);
+        ++ctx->rtf_round_no;
+        // the timing pool is bounded: resolve it every few rounds (a synchronisation, but no host read of the result)
+        if (ctx->launches.size() > 2048)
+            if (int rc = finish_timing(ctx)) return rc;
+    }
+    if (int rc = finish_timing(ctx)) return rc;
+    unsigned long long c[2] = {0, 0};
+    CK(cudaMemcpy(&c[0], ctx->counters + C_ALIVE, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&c[1], ctx->counters + C_ROUNDS, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (n_rounds) ctx->rtf_alive = c[0];
+    ctx->rtf_rounds_total = c[1];
+    if (alive) *alive = ctx->rtf_alive;
+    if (rounds_total) *rounds_total = ctx->rtf_rounds_total;
+    return S17_OK;
+}
+
+extern "C" int s17_rtf_end(s17_ctx *ctx, s17_counts *out) {
+    if (!ctx || !out || !ctx->rtf_open) return fail(ctx, S17_E_STATE, "s17_rtf_end: no run-til-fail job is open");
+    CK(cudaSetDevice(ctx->device));
+    ctx->rtf_open = false;
+    if (int rc = end_call(ctx, ctx->rtf_args, out)) return rc;
+    // failed_count of a run-til-fail job = runs that ended with a logical failure; the per-round tallies of the
+    // read-out kernels count the same events
+    return S17_OK;
+}
+
+extern "C" int s17_read_rtf_slots(s17_ctx *ctx, uint32_t *out /* n x {run_id, rounds, synd_b, alive} */, uint64_t n) {
+    if (!ctx || !out || n > ctx->max_shots) return fail(ctx, S17_E_ARG, "s17_read_rtf_slots: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy(out, ctx->rtf_slots, n * sizeof(RtfSlot), cudaMemcpyDeviceToHost));
+    return S17_OK;
+}
+
+extern "C" int s17_run(s17_ctx *ctx, const s17_run_args *args, s17_counts *out) {
+    if (!ctx || !args || !out) return fail(ctx, S17_E_ARG, "s17_run: bad arguments");
+    s17_run_args a = *args;
+    if (a.protocol == S17_PROTO_RTF) {
+        // poll the live-slot count every few rounds: the tail of a job (few live slots) is launch-bound, and a host
+        // round trip per round would double its cost
+        if (int rc = s17_rtf_begin(ctx, &a)) return rc;
+        const uint32_t poll = a.rtf_poll ? a.rtf_poll : 4u;
+        for (;;) {
+            uint64_t alive = 0, rounds = 0;
+            if (int rc = s17_rtf_step(ctx, poll, &alive, &rounds)) { ctx->rtf_open = false; return rc; }
+            if (alive == 0) break;
+            if (a.rtf_round_budget && rounds >= a.rtf_round_budget) break;      // the rest of the runs stay censored
+        }
+        return s17_rtf_end(ctx, out);
+    }
+    if (int rc = check_run_args(ctx, a)) return rc;
+    if (int rc = begin_call(ctx, a)) return rc;
+    const int n = (int)a.n_shots;
+    if (a.noise == S17_NOISE_SUBSET) {
+        SCOPE(CAT_OTHER);
+        k_place<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(ctx->nd, ctx->cum, ctx->masks, a.seed, a.first_shot_id, n);
+    }
+    if (int rc = run_round(ctx, a)) return rc;
+    if (int rc = finish_timing(ctx)) return rc;
+    return end_call(ctx, a, out);
 }
 
 extern "C" int s17_read_records(s17_ctx *ctx, s17_record *out, uint64_t n) {

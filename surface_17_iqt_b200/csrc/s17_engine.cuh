@@ -227,6 +227,8 @@ k_eng_reset(double2 *__restrict__ state, uint32_t n_bits, uint64_t n_shots)
 // =================================================================================================
 // host side: engine context + C ABI (include/s17.h, "engine-level face")
 // =================================================================================================
+using namespace s17;
+
 struct EngTimed { int cat; cudaEvent_t e0, e1; };
 
 struct s17_eng {

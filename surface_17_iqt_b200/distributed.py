@@ -7,15 +7,28 @@ all-reduce(sum) of the integer counters at the end (NCCL over NVLink on GPUs, gl
 import os
 
 
+_warned = False
+
+
 def world():
-    """(rank, world_size) from torch.distributed when initialised, else from the torchrun env, else (0, 1)."""
+    """(rank, world_size) of the initialised torch.distributed process group, else (0, 1).
+
+    Sharding and the counter all-reduce use the SAME condition: a process that was launched by torchrun but never
+    called init_process_group simulates the whole shot range itself (every rank returns the full, correct counters;
+    a warning says so) instead of returning a silent fraction of them."""
+    global _warned
     try:
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized():
             return dist.get_rank(), dist.get_world_size()
     except ImportError:
         pass
-    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and not _warned:
+        _warned = True
+        import sys
+        print("surface_17_iqt_b200: WORLD_SIZE > 1 but torch.distributed is not initialised -- this process runs every "
+              "shot itself (call torch.distributed.init_process_group to shard the shots over the ranks)", file=sys.stderr)
+    return 0, 1
 
 
 def shard_range(n, rank, world_size):
@@ -41,3 +54,50 @@ def allreduce_counts(values, device=None):
     t = torch.tensor([int(v) for v in values], dtype=torch.int64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return [int(v) for v in t.tolist()]
+
+
+def _group_device(dist):
+    import torch
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+
+
+def broadcast_seed(seed):
+    """Rank 0's 64-bit seed on every rank (each rank draws its own from Python's `random`, whose state need not agree
+    between ranks; the counters are independent of the sharding only if all ranks use one Philox key)."""
+    try:
+        import torch
+        import torch.distributed as dist
+    except ImportError:
+        return seed
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return seed
+    t = torch.tensor([seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF], dtype=torch.int64, device=_group_device(dist))
+    dist.broadcast(t, src=0)
+    lo, hi = [int(v) for v in t.tolist()]
+    return lo | (hi << 32)
+
+
+def gather_lists(values):
+    """Concatenate one list of ints per rank in rank order (run-til-fail: rounds_til_fail_list of every rank's runs)."""
+    try:
+        import torch
+        import torch.distributed as dist
+    except ImportError:
+        return list(values)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return list(values)
+    dev = _group_device(dist)
+    n = torch.tensor([len(values)], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(dist.get_world_size())]
+    dist.all_gather(sizes, n)
+    sizes = [int(v.item()) for v in sizes]
+    pad = max(sizes) if sizes else 0
+    mine = torch.zeros(pad, dtype=torch.int64, device=dev)
+    if values:
+        mine[:len(values)] = torch.tensor([int(v) for v in values], dtype=torch.int64, device=dev)
+    parts = [torch.zeros(pad, dtype=torch.int64, device=dev) for _ in sizes]
+    dist.all_gather(parts, mine)
+    out = []
+    for sz, part in zip(sizes, parts):
+        out.extend(int(v) for v in part[:sz].tolist())
+    return out

@@ -30,9 +30,15 @@ class Error:
 
     # -- what the reference does with gates, as data -------------------------------------------------------------
     def insert_error(self, *qubits):
-        """The (Pauli, qubit) pairs this error applies (error.py:39-61 apply ``X | q`` / ``Z | q`` / ``Y | q``)."""
+        """error.py:39-61: ``X | q`` / ``Z | q`` / ``Y | q`` on each qubit when they are engine qubits (gate-by-gate
+        path); returns the (Pauli, qubit) pairs either way (the batched path only needs those)."""
         if self.pauli is None:
             raise Exception("This error does not have a defined insert_error function.")
+        from . import pq_core
+        gate = {"X": pq_core.X, "Y": pq_core.Y, "Z": pq_core.Z}[self.pauli]
+        for q in qubits:
+            if isinstance(q, pq_core.Qubit):
+                gate | q
         return [(self.pauli, q) for q in qubits]
 
     def generate_location_list(self):

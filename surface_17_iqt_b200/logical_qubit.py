@@ -15,98 +15,84 @@ import numpy as np
 from . import _lib as L
 from . import api, circuit
 from .error import DephasingError, Error, XCtrlError, YCtrlError  # noqa: F401
-
-
-class _Rotation:
-    name = "?"
-
-    def __init__(self, angle):
-        self.angle = float(angle)
-
-    def __repr__(self):
-        return "{}({})".format(self.name, self.angle)
-
-
-class Rx(_Rotation):
-    name = "Rx"
-
-
-class Ry(_Rotation):
-    name = "Ry"
-
-
-class Rxx(_Rotation):
-    name = "Rxx"
-
+from .pq_core import Qubit, Rx, Rxx, Ry          # the gate objects of the projectq-shaped face (`Gate | qubits`)
 
 pdd_error_model = {Rxx: [XCtrlError, DephasingError], Rx: [XCtrlError, DephasingError], Ry: [YCtrlError, DephasingError]}
 
-_PI = np.pi
+HALF_PI = np.pi / 2
+_TABLE = circuit.build_cycle()                   # the 24 entangling operations: (timestep, data, ancilla, which gates)
+
+
+def _on_engine(qubits):
+    qs = qubits if isinstance(qubits, (list, tuple)) else (qubits,)
+    return all(isinstance(q, Qubit) for q in qs)
 
 
 class NoisyGate:
-    """A gate plus its location and the errors the error model allows after it (logical_qubit.py:14-45)."""
+    """A gate, where it sits (``location``) and the error types the model allows behind it (logical_qubit.py:14-45).
+
+    ``apply`` sends the gate to the engine of its qubits and then every error of ``error_list`` placed at this location
+    (`Gate | qubits`, like the reference).  With plain qubit indices instead of engine qubits -- the batched path, where
+    the whole cycle is one device program -- nothing is sent; either way the errors that sit here are returned."""
 
     def __init__(self, gate, qubits, location=None, error_model={}):
-        self.gate = gate
-        self.qubits = qubits
-        self.location = location
-        self.error_model = error_model
+        self.gate, self.qubits, self.location, self.error_model = gate, qubits, location, error_model
         self.possible_errors = self.get_errors_from_error_model()
 
-    def __str__(self):
-        return "NoisyGate: \n Gate: {}, \n Qubits : {}, \n Location: {}, \n Error model: {}, \n Errors, {}".format(
-            self.gate, self.qubits, self.location, self.error_model, self.possible_errors)
-
     def get_errors_from_error_model(self):
-        errors = []
-        for gate in self.error_model.keys():
-            if type(self.gate) == gate:
-                for error in self.error_model[gate]:
-                    errors.append(error())
-        return errors
+        return [kind() for kind in self.error_model.get(type(self.gate), ())]
+
+    def __str__(self):
+        fields = (("Gate", self.gate), ("Qubits", self.qubits), ("Location", self.location),
+                  ("Error model", self.error_model), ("Errors", self.possible_errors))
+        return "NoisyGate: " + ", ".join("{}: {}".format(k, v) for k, v in fields)
 
     def apply(self, error_list=[]):
-        """Returns the errors of error_list that sit at this gate (they are applied by the device path)."""
-        return [e for e in error_list if e.location == self.location]
+        here = [e for e in error_list if e.location == self.location]
+        if _on_engine(self.qubits):
+            self.gate | self.qubits
+            for e in here:
+                e.insert_error(*(self.qubits if isinstance(self.qubits, (list, tuple)) else (self.qubits,)))
+        return here
 
 
 class EntanglingOperation:
+    """One data qubit entangled with one ancilla (logical_qubit.py:48-69); subclasses list the gates."""
+
     def __init__(self, location=None, dataq=None, ancillaq=None, cancel_data_rx=None, s=None, v=None, error_model=None):
-        self.location = location
-        self.dataq = dataq
-        self.ancillaq = ancillaq
-        self.error_model = error_model
-        self.cancel_data_rx = cancel_data_rx
-        self.s = s
-        self.v = v
+        self.location, self.error_model = location, error_model
+        self.dataq, self.ancillaq = dataq, ancillaq
+        self.cancel_data_rx, self.s, self.v = cancel_data_rx, s, v
         self.noisy_gates = self.build_noisy_gates()
 
-    def build_noisy_gates(self):
+    def gate_sequence(self):
         raise Exception("No build_noisy_gates function defined.")
+
+    def build_noisy_gates(self):
+        # a gate's location = the operation's location + its position in the operation
+        return [NoisyGate(gate, qubits, self.location + [k], self.error_model)
+                for k, (gate, qubits) in enumerate(self.gate_sequence())]
 
     def run(self, error_list=[]):
         return [e for g in self.noisy_gates for e in g.apply(error_list)]
 
 
 class XTypeEntanglingOp(EntanglingOperation):
-    def build_noisy_gates(self):
-        gates = [NoisyGate(Rxx(self.s * _PI / 2), [self.dataq, self.ancillaq], self.location + [0], self.error_model)]
+    def gate_sequence(self):
+        seq = [(Rxx(self.s * HALF_PI), (self.dataq, self.ancillaq))]
         if not self.cancel_data_rx:
-            gates.append(NoisyGate(Rx(-self.s * _PI / 2), [self.dataq], self.location + [1], self.error_model))
-        return gates
+            seq.append((Rx(-self.s * HALF_PI), self.dataq))
+        return seq
 
 
 class ZTypeEntanglingOp(EntanglingOperation):
-    def build_noisy_gates(self):
-        gates = [NoisyGate(Ry(self.v * _PI / 2), [self.dataq], self.location + [0], self.error_model),
-                 NoisyGate(Rxx(self.s * _PI / 2), [self.dataq, self.ancillaq], self.location + [1], self.error_model)]
+    def gate_sequence(self):
+        # the reference's OO circuit keeps both Ry of every operation and gives them the same sign (SURVEY C-14)
+        seq = [(Ry(self.v * HALF_PI), self.dataq), (Rxx(self.s * HALF_PI), (self.dataq, self.ancillaq))]
         if not self.cancel_data_rx:
-            gates.append(NoisyGate(Rx(-self.s * _PI / 2), [self.dataq], self.location + [2], self.error_model))
-            gates.append(NoisyGate(Ry(self.v * _PI / 2), [self.dataq], self.location + [3], self.error_model))
-        else:
-            gates.append(NoisyGate(Ry(self.v * _PI / 2), [self.dataq], self.location + [2], self.error_model))
-        return gates
+            seq.append((Rx(-self.s * HALF_PI), self.dataq))
+        seq.append((Ry(self.v * HALF_PI), self.dataq))
+        return seq
 
 
 class StabiliserTimestep:
@@ -123,18 +109,17 @@ class StabiliserTimestep:
             raise Exception("Entangling type not recognized, should be \"X\" or \"Z\". "
                             "Please check stabilizer_timestep instantiation.")
         klass = XTypeEntanglingOp if self.ent_type == "X" else ZTypeEntanglingOp
-        return [klass(location=self.location + [k], dataq=self.data[self.qu_ind[k][0]],
-                      ancillaq=self.ancilla[self.qu_ind[k][1]], cancel_data_rx=self.cancel_data_rx[k], s=1, v=1,
-                      error_model=self.error_model) for k in range(3)]
+        return [klass(location=self.location + [k], dataq=self.data[d], ancillaq=self.ancilla[a],
+                      cancel_data_rx=self.cancel_data_rx[k], s=1, v=1, error_model=self.error_model)
+                for k, (d, a) in enumerate(self.qu_ind)]
 
     def run(self, error_list=[]):
         return [e for op in self.entangling_operations for e in op.run(error_list)]
 
 
-QU_IND = ([[4, 1], [8, 6], [6, 4]], [[1, 1], [5, 6], [3, 4]], [[3, 1], [7, 6], [5, 3]], [[0, 1], [4, 6], [2, 3]],
-          [[1, 2], [3, 5], [7, 7]], [[2, 2], [4, 5], [8, 7]], [[4, 2], [6, 5], [0, 0]], [[5, 2], [7, 5], [1, 0]])
-CANCEL_DATA_RX = ([True, False, False], [False, True, True], [True, False, True], [False, True, False],
-                  [True, False, True], [False, True, False], [True, False, False], [False, True, True])
+# (data, ancilla) pairs and Rx cancellations per timestep, read off the compiled cycle table
+QU_IND = tuple([[op.data, op.ancilla] for op in _TABLE if op.timestep == t] for t in range(8))
+CANCEL_DATA_RX = tuple([not op.has_rx for op in _TABLE if op.timestep == t] for t in range(8))
 
 
 class StabiliserCycle:
@@ -151,18 +136,22 @@ class StabiliserCycle:
         self.errors_to_insert = Error.generate_error_list(error_subset, self.error_locations)
         self.dropped_locations = []
 
-    def generate_gate_and_error_locations(self):
-        gate_locations = {Rx: [], Ry: [], Rxx: []}
-        all_gate_locations = []
-        error_locations = {XCtrlError: [], YCtrlError: [], DephasingError: []}
+    def noisy_gates(self):
         for timestep in self.stabiliser_timesteps:
-            for entangling_op in timestep.entangling_operations:
-                for noisy_gate in entangling_op.noisy_gates:
-                    all_gate_locations.append(noisy_gate.location)
-                    gate_locations[type(noisy_gate.gate)].append(noisy_gate.location)
-                    for error in noisy_gate.possible_errors:
-                        error_locations[type(error)].append(noisy_gate.location)
-        return all_gate_locations, error_locations, gate_locations
+            for op in timestep.entangling_operations:
+                yield from op.noisy_gates
+
+    def generate_gate_and_error_locations(self):
+        """(every gate location, {error class: locations it can occur at}, {gate class: locations})."""
+        by_gate = {Rx: [], Ry: [], Rxx: []}
+        by_error = {XCtrlError: [], YCtrlError: [], DephasingError: []}
+        everything = []
+        for g in self.noisy_gates():
+            everything.append(g.location)
+            by_gate[type(g.gate)].append(g.location)
+            for e in g.possible_errors:
+                by_error[type(e)].append(g.location)
+        return everything, by_error, by_gate
 
     def build_stabiliser_timesteps(self, data, ancilla, circuit_type):
         if len(data) != 9:

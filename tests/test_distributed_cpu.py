@@ -24,9 +24,19 @@ def test_shard_range_partitions_exactly():
         distributed.shard_range(10, 2, 2)
 
 
-def test_allreduce_is_identity_without_process_group():
+def test_no_process_group_means_no_sharding(monkeypatch, capsys):
+    """Sharding and the all-reduce use one condition: under a torchrun environment WITHOUT an initialised process group
+    a rank keeps the whole shot range (and says so) instead of returning a silent 1/world_size of the counters."""
     assert distributed.allreduce_counts([3, 4, 5]) == [3, 4, 5]
-    assert distributed.world() == (int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")))
+    assert distributed.world() == (0, 1)
+    monkeypatch.setenv("RANK", "1")
+    monkeypatch.setenv("WORLD_SIZE", "4")
+    monkeypatch.setattr(distributed, "_warned", False)
+    assert distributed.world() == (0, 1)
+    assert "not initialised" in capsys.readouterr().err
+    assert distributed.shard_range(1000, *distributed.world()) == (0, 1000)
+    assert distributed.broadcast_seed(12345678901234567890) == 12345678901234567890
+    assert distributed.gather_lists([4, 5]) == [4, 5]
 
 
 WORKER = textwrap.dedent("""
@@ -41,8 +51,12 @@ WORKER = textwrap.dedent("""
     ids = range(first, first + count)
     local = [sum(1 for i in ids if i % 7 == 0), sum(1 for i in ids if i % 3 == 0), count]
     total = distributed.allreduce_counts(local)
+    # run-til-fail sharding: one Philox key for every rank, per-rank lists concatenated in rank order
+    seed = distributed.broadcast_seed(0xFEDCBA9876543210 + rank)
+    runs_first, runs = distributed.shard_range(7, rank, world)
+    lists = distributed.gather_lists([100 * rank + i for i in range(runs)])
     if rank == 0:
-        print(json.dumps(total))
+        print(json.dumps(total + [seed] + lists))
     dist.destroy_process_group()
 """)
 
@@ -58,4 +72,7 @@ def test_two_rank_gloo_allreduce(tmp_path):
                          capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stderr[-2000:]
     line = [ln for ln in out.stdout.splitlines() if ln.startswith("[")][-1]
-    assert eval(line) == [sum(1 for i in range(1001) if i % 7 == 0), sum(1 for i in range(1001) if i % 3 == 0), 1001]
+    got = eval(line)
+    assert got[:3] == [sum(1 for i in range(1001) if i % 7 == 0), sum(1 for i in range(1001) if i % 3 == 0), 1001]
+    assert got[3] == 0xFEDCBA9876543210                      # rank 0's seed on every rank
+    assert got[4:] == [0, 1, 2, 3, 100, 101, 102]           # 4 runs on rank 0, 3 on rank 1, rank order

@@ -582,22 +582,31 @@ def test_compact_then_full_state_allocation(error_models, correction_table, bitf
 
 
 def test_sampled_rates_against_reference_statistics(error_models, correction_table, bitflip_table, golden):
-    """Sampled s2 rates (not0 / runs and failed / not0) against the UNMODIFIED reference drivers run on the projectq
-    stand-in (tests/golden/stats_s2.json, oracle/make_golden_stats.py, 4000 shots per subset): within 3.5 binomial
-    sigma of the reference sample (the GPU sample of 2^20 shots adds < 2 % to the variance)."""
+    """Sampled s1 / s2 rates against the UNMODIFIED reference drivers run on the projectq stand-in
+    (tests/golden/stats_s2.json, oracle/make_golden_stats.py, 4000 shots per subset): PDD_model with uniform placement and
+    with the linear-heating lists of importance_sampling_syndrome_processing.py:20-36 (non-uniform placement), Dress_model
+    (leakage), Dress_cooling / PDD_cooling with cooling=True (ISC:19-34).  not0 / runs and failed / decoded within 3.5
+    binomial sigma of the reference sample (the GPU sample of 2^20 shots adds < 2 % to the variance)."""
     n = 1 << 20
-    for st in golden("stats_s2.json")["stats"]:
-        sim = make_sim(error_models, correction_table, bitflip_table, st["model"], st["locations"], n, 2)
-        sim.backend.set_subset(st["eset"], st["locations"])
-        c = sim.backend.run("s2", n, L.NOISE_SUBSET, seed=20260101)
+    stats = golden("stats_s2.json")["stats"]
+    assert len(stats) >= 11 and {s_["model"] for s_ in stats} >= {"PDD_model", "Dress_model", "Dress_cooling", "PDD_cooling"}
+    for st in stats:
+        cooling = bool(st.get("cooling", False))
+        sim = make_sim(error_models, correction_table, bitflip_table, st["model"], st["locations"], n, 2, cooling)
+        sim.backend.set_subset(st["eset"], st["locations"], [None if len(p) == 1 else p for p in st["prob_lists"]])
+        c = sim.backend.run(st["protocol"], n, L.NOISE_SUBSET, seed=20260101)
         sim.close()
         assert c.errors == 0
         p_ref, p_gpu = st["not0"] / st["runs"], c.not0 / n
         sig = np.sqrt(max(p_ref * (1 - p_ref), 1e-6) / st["runs"] + p_gpu * (1 - p_gpu) / n)
-        assert abs(p_gpu - p_ref) < 3.5 * sig, (st["eset"], "not0", p_gpu, p_ref, sig)
-        f_ref, f_gpu = st["failed"] / max(1, st["not0"]), c.failed / max(1, c.not0)
-        sig = np.sqrt(max(f_ref * (1 - f_ref), 1e-6) / max(1, st["not0"]) + f_gpu * (1 - f_gpu) / max(1, c.not0))
-        assert abs(f_gpu - f_ref) < 3.5 * sig, (st["eset"], "failed", f_gpu, f_ref, sig)
+        assert abs(p_gpu - p_ref) < 3.5 * sig, (st["model"], st["eset"], "not0", p_gpu, p_ref, sig)
+        # s2 decodes the shots whose first syndrome changed (CL:416), s1 the others (CL:321)
+        d_ref = st["not0"] if st["protocol"] == "s2" else st["runs"] - st["not0"]
+        d_gpu = c.not0 if st["protocol"] == "s2" else n - c.not0
+        assert c.counted == d_gpu
+        f_ref, f_gpu = st["failed"] / max(1, d_ref), c.failed / max(1, d_gpu)
+        sig = np.sqrt(max(f_ref * (1 - f_ref), 1e-6) / max(1, d_ref) + f_gpu * (1 - f_gpu) / max(1, d_gpu))
+        assert abs(f_gpu - f_ref) < 3.5 * sig, (st["model"], st["eset"], "failed", f_gpu, f_ref, sig)
 
 
 @pytest.mark.parametrize("diag", ["1", "g", "0"])
