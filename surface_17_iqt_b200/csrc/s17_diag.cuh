@@ -384,42 +384,148 @@ k_cycle(const __grid_constant__ DiagProg P, const __grid_constant__ MeasArgs ma,
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// k_cycle1: the same cycle with host-chosen mappings (DiagProg1).  Per slot a lane loads two table entries.
+// k_cycle1: the same cycle with host-chosen mappings (DiagProg1).  Per slot a lane needs two table entries (register
+// bit k of the amplitude index <-> slot k), which makes the half cycle cheap:
+//   * the four Measures only need the REAL weights |psi|^2: sixteen per lane, reduced once to marginal sums over the
+//     register bits; slot k costs a handful of multiply-adds with the (|A0|^2, |A1|^2) pairs of its two entries and the
+//     factors already selected by slots < k, then one warp reduction of (P0, P1);
+//   * the complex amplitudes are updated ONCE per half cycle with the product of the four selected factors
+//     (F01[b0 b1] F23[b2 b3]: 8 + 32 complex multiplications instead of 64);
+//   * per-shot events touch few table entries: a data flip upstream of an operation is an XOR on the table index, a
+//     label-dependent sign or the global phase multiplies the selected factors, and only a slot whose own operations
+//     carry an ancilla Pauli / a leak skip / an idle Z gets private entries (exact integer arithmetic: every entry is a
+//     Gaussian integer);
+//   * the renormalisation rides in the last factor table; a preparation cycle starts from the Walsh-Hadamard transform
+//     of its basis state, which is a sign pattern.
 // ------------------------------------------------------------------------------------------------------------------
-template <int B>
-__device__ __forceinline__ void dg_slot1(double2 (&p)[16], const unsigned char *tk0, const unsigned char *tk1, uint32_t aj,
-                                         bool forced, uint32_t fo, double u, uint32_t &a_out, bool &bad, double &pfin,
-                                         double *pp) {
-    const double2 q0 = *reinterpret_cast<const double2 *>(tk0 + 32 * kDgTabEntries);
-    const double2 q1 = *reinterpret_cast<const double2 *>(tk1 + 32 * kDgTabEntries);
-    double w0[2] = {0.0, 0.0}, w1[2] = {0.0, 0.0};           // two partial sums each: shorter dependency chains
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const double w = fma(p[i].x, p[i].x, p[i].y * p[i].y);
-        if ((i >> B) & 1) w1[(i >> ((B + 1) & 3)) & 1] += w;
-        else w0[(i >> ((B + 1) & 3)) & 1] += w;
+__device__ __forceinline__ double2 dg_neg_if(const double2 a, uint32_t neg) {       // (-1)^neg a, sign-bit flip
+    const int s = (int)(neg << 31);
+    return make_double2(__hiloint2double(__double2hiint(a.x) ^ s, __double2loint(a.x)),
+                        __hiloint2double(__double2hiint(a.y) ^ s, __double2loint(a.y)));
+}
+__device__ __forceinline__ double2 dg_times_i_pow(const double2 a, uint32_t g) {    // i^g a
+    const double2 r = (g & 1u) ? make_double2(-a.y, a.x) : a;
+    return dg_neg_if(r, (g >> 1) & 1u);
+}
+
+// private entries of ONE slot (k) for one shot: lanes with idx < 2^n_ops[k] compute entry idx.  Events: bit 31 data flip
+// seen by the operation, bit 24 leak skip, bits 27 / 28 net X / Z on the ancilla after the operation, ancz idle Z after
+// it.  Signs and the global phase are NOT part of the entries (the caller applies them to the selected factors).
+__device__ __forceinline__ void dg_build_slot(const DiagHalf &H, const uint32_t *evw, double2 *tab, int k, int idx,
+                                              uint32_t ancz) {
+    int ur = 1, ui = 0, vr = 0, vi = 0, pr = 1, pi = 0;
+    const int n = H.n_ops[k];
+    for (int j = 0; j < n; ++j) {
+        const DiagOp op = H.ops[k][j];
+        const uint32_t w = evw[op.ev_word];
+        const uint32_t neg = (uint32_t)(op.flags & 1u) ^ ((uint32_t)(idx >> j) & 1u) ^ (w >> 31);
+        const int sg = neg ? -1 : 1;
+        if (!((w >> 24) & 1u)) {                              // Rxx unless leak-skipped: (u, v) -> (u - i sg v, v - i sg u)
+            const int nur = ur + sg * vi, nui = ui - sg * vr, nvr = vr + sg * ui, nvi = vi - sg * ur;
+            ur = nur; ui = nui; vr = nvr; vi = nvi;
+        }
+        if (op.flags & 2u) { const int npr = pr - sg * pi, npi = pi + sg * pr; pr = npr; pi = npi; }   // (1 + i sg) ph
+        if ((w >> 28) & 1u) { vr = -vr; vi = -vi; }                                                   // net event: Z on the ancilla
+        if ((w >> 27) & 1u) { int t = ur; ur = vr; vr = t; t = ui; ui = vi; vi = t; }                 //            X on the ancilla
+        if ((ancz >> op.pad) & 1u) { vr = -vr; vi = -vi; }                                            // idle Z after the operation
     }
-    const double W0 = w0[0] + w0[1], W1 = w1[0] + w1[1];
-    double p0 = fma(q0.x, W0, q1.x * W1), p1 = fma(q0.y, W0, q1.y * W1);
+    const int a0r = pr * ur - pi * ui, a0i = pr * ui + pi * ur, a1r = pr * vr - pi * vi, a1i = pr * vi + pi * vr;
+    const int e = H.tbase[k] + idx;
+    tab[e] = make_double2((double)a0r, (double)a0i);
+    tab[e + kDgTabEntries] = make_double2((double)a1r, (double)a1i);
+    tab[e + 2 * kDgTabEntries] = make_double2((double)(a0r * a0r + a0i * a0i), (double)(a1r * a1r + a1i * a1i));
+}
+// the four Measures of one half cycle from the real weights, then one complex update of the amplitudes.
+// tk0[k] / tk1[k]: this lane's table entries of slot k for register bit k = 0 / 1 (A0 at +0, A1 at +16 kDgTabEntries, Q
+// at +32 kDgTabEntries).  lane_neg: (-1)^lane_neg multiplies this lane's amplitudes; reg_neg bit j: amplitudes with
+// register bit j set change sign; g: global phase i^g.  scale_out: fold 1/sqrt(final weight) into the update.
+__device__ __forceinline__ void dg_half1(double2 (&p)[16], const unsigned char *(&tk0)[4], const unsigned char *(&tk1)[4],
+                                         const uint8_t (&aj)[4], bool forced, uint32_t fo, double uu, int u_lane0,
+                                         uint32_t lane_neg, uint32_t reg_neg, uint32_t g, bool scale_out, uint32_t &a_out,
+                                         bool &bad, double &pfin, double *pp) {
+    double w[16];
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        p0 += __shfl_xor_sync(0xffffffffu, p0, d);
-        p1 += __shfl_xor_sync(0xffffffffu, p1, d);
-    }
-    if (pp) { pp[0] = p0; pp[1] = p1; }                      // every lane holds the same pair
-    uint32_t out;
-    if (forced) {
-        out = (fo >> aj) & 1u;
-        if ((out ? p1 : p0) <= 0.0) bad = true;
-    } else {
-        out = (u * (p0 + p1) < p1) ? 1u : 0u;                // Measure: P(1) against one uniform, as k_measure
-    }
-    const uint32_t sel = out ? 16u * kDgTabEntries : 0u;
-    const double2 a0 = *reinterpret_cast<const double2 *>(tk0 + sel), a1 = *reinterpret_cast<const double2 *>(tk1 + sel);
+    for (int i = 0; i < 16; ++i) w[i] = fma(p[i].x, p[i].x, p[i].y * p[i].y);
+    double m3[8], m2[4], m1[2];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) p[i] = dg_cmul(p[i], ((i >> B) & 1) ? a1 : a0);
-    a_out |= out << aj;
-    pfin = out ? p1 : p0;
+    for (int j = 0; j < 8; ++j) m3[j] = w[j] + w[j + 8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) m2[j] = m3[j] + m3[j + 4];
+    m1[0] = m2[0] + m2[2];
+    m1[1] = m2[1] + m2[3];
+    uint32_t outs = 0;
+    double csel[4][2];            // |A_out|^2 of the entries selected so far, per slot and register bit
+    // one Measure: (t0, t1) = this lane's weight with register bit K clear / set, already scaled by the factors of the
+    // earlier slots
+    auto measure = [&](int K, double t0, double t1) {
+        const double2 q0 = *reinterpret_cast<const double2 *>(tk0[K] + 32 * kDgTabEntries);
+        const double2 q1 = *reinterpret_cast<const double2 *>(tk1[K] + 32 * kDgTabEntries);
+        double p0 = fma(q0.x, t0, q1.x * t1), p1 = fma(q0.y, t0, q1.y * t1);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            p0 += __shfl_xor_sync(0xffffffffu, p0, d);
+            p1 += __shfl_xor_sync(0xffffffffu, p1, d);
+        }
+        if (pp) { pp[2 * K] = p0; pp[2 * K + 1] = p1; }      // every lane holds the same pair
+        uint32_t out;
+        if (forced) {
+            out = (fo >> aj[K]) & 1u;
+            if ((out ? p1 : p0) <= 0.0) bad = true;
+        } else {
+            const double u = __shfl_sync(0xffffffffu, uu, u_lane0 + K);
+            out = (u * (p0 + p1) < p1) ? 1u : 0u;            // Measure: P(1) against one uniform, as k_measure
+        }
+        csel[K][0] = out ? q0.y : q0.x;
+        csel[K][1] = out ? q1.y : q1.x;
+        outs |= out << K;
+        a_out |= out << aj[K];
+        pfin = out ? p1 : p0;
+    };
+    measure(0, m1[0], m1[1]);
+    measure(1, fma(m2[0], csel[0][0], m2[1] * csel[0][1]), fma(m2[2], csel[0][0], m2[3] * csel[0][1]));
+    double c01[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c01[j] = csel[0][j & 1] * csel[1][j >> 1];
+    {
+        double t0 = m3[0] * c01[0], t1 = m3[4] * c01[0];
+#pragma unroll
+        for (int j = 1; j < 4; ++j) { t0 = fma(m3[j], c01[j], t0); t1 = fma(m3[4 + j], c01[j], t1); }
+        measure(2, t0, t1);
+    }
+    {
+        double c012[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) c012[j] = c01[j & 3] * csel[2][j >> 2];
+        double t0 = w[0] * c012[0], t1 = w[8] * c012[0];
+#pragma unroll
+        for (int j = 1; j < 8; ++j) { t0 = fma(w[j], c012[j], t0); t1 = fma(w[8 + j], c012[j], t1); }
+        measure(3, t0, t1);
+    }
+    // the selected complex factors, with the shot's signs and phase
+    double2 f[4][2];
+#pragma unroll
+    for (int K = 0; K < 4; ++K) {
+        const uint32_t sel = ((outs >> K) & 1u) ? 16u * kDgTabEntries : 0u;
+        f[K][0] = *reinterpret_cast<const double2 *>(tk0[K] + sel);
+        f[K][1] = dg_neg_if(*reinterpret_cast<const double2 *>(tk1[K] + sel), (reg_neg >> K) & 1u);
+    }
+    f[0][0] = dg_neg_if(f[0][0], lane_neg);
+    f[0][1] = dg_neg_if(f[0][1], lane_neg);
+    f[3][0] = dg_times_i_pow(f[3][0], g);
+    f[3][1] = dg_times_i_pow(f[3][1], g);
+    if (scale_out) {
+        const double inv = pfin > 0.0 ? 1.0 / sqrt(pfin) : 0.0;
+        f[3][0] = make_double2(f[3][0].x * inv, f[3][0].y * inv);
+        f[3][1] = make_double2(f[3][1].x * inv, f[3][1].y * inv);
+    }
+    double2 F01[4], F23[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        F01[j] = dg_cmul(f[0][j & 1], f[1][j >> 1]);
+        F23[j] = dg_cmul(f[2][j & 1], f[3][j >> 1]);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) p[i] = dg_cmul(dg_cmul(p[i], F01[i & 3]), F23[i >> 2]);
 }
 
 __global__ void __launch_bounds__(kDgThreads, 1)
@@ -492,19 +598,18 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ MeasArgs m
     const uint32_t linA = laneA << 4, swzA = swz(laneA) << 4, swzB = swz(laneB) << 4;
     const double sh_sign = ((lane >> P.sh_lane_bit) & 1) ? -1.0 : 1.0;
     const int sh_mask = 1 << P.sh_lane_bit;
-    uint32_t tlp[2];
+    // lane part of this lane's table index per slot (4 bits each; the register-fed index bit stays 0)
+    uint32_t lidx[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        tlp[h] = 0;
+        lidx[h] = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            uint32_t li = P.h[h].tbase[k];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int lb = P.h[h].lane_bit[k][j];
-                if (lb != 255) li += (uint32_t)((lane >> lb) & 1) << j;
+                if (lb != 255) lidx[h] |= (uint32_t)((lane >> lb) & 1) << (4 * k + j);
             }
-            tlp[h] |= li << (8 * k);
         }
     }
 
@@ -563,18 +668,18 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ MeasArgs m
             uu = rng.next();
         }
 
+        double2 p[16];
         if (init_basis < 0) {
             mbar_wait(&full[sb], (j >> 1) & 1u);
-        } else {
-            // first cycle of a shot: synthesise the computational basis state in the buffer instead of reading HBM
-#pragma unroll 1
-            for (int i = 0; i < 16; ++i)
-                reinterpret_cast<double2 *>(xb)[lane + 32 * i] = make_double2(lane + 32 * i == init_basis ? 1.0 : 0.0, 0.0);
-            __syncwarp();
-        }
-        double2 p[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) p[i] = *reinterpret_cast<const double2 *>(xb + (linA ^ P.mapA.lin16[i]));
+            for (int i = 0; i < 16; ++i) p[i] = *reinterpret_cast<const double2 *>(xb + (linA ^ P.mapA.lin16[i]));
+        } else {
+            // first cycle of a shot: the (unnormalised) Walsh-Hadamard transform of the basis state |b> is the sign
+            // pattern (-1)^{y.b} -- exactly what the transform below would compute from it -- written in map B
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                p[i] = make_double2((__popc((laneB | (P.mapB.lin16[i] >> 4)) & (uint32_t)init_basis) & 1) ? -1.0 : 1.0, 0.0);
+        }
         mbar_wait(&mfull[sb], (j >> 1) & 1u);
         __syncwarp();                             // every lane holds its amplitudes: the buffer becomes exchange scratch
 
@@ -590,6 +695,7 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ MeasArgs m
             const uint32_t fw = fwp[h];
             if (r != 1) {
                 if (!H.frame_x) continue;
+                if (st == 0 && init_basis >= 0) continue;         // already in the frame (see above)
                 // Walsh-Hadamard transform of the data register: the register bits of the current map, the exchange to the
                 // other map, its register bits; the one remaining label bit is a lane bit of map A (shuffle stage)
                 const int dir = r >> 1;                           // 0: map A -> B (into the frame), 1: map B -> A
@@ -608,41 +714,55 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ MeasArgs m
                         for (int i = 0; i < 16; ++i) p[i] = *reinterpret_cast<const double2 *>(xb + (rl ^ rr[i]));
                     }
                 }
-                if (dir) {
-                    pfin *= 512.0;                                // the two transforms multiply the norm^2 by 512
-                    carry = fw & 511u;                            // its data flips are signs now: next half's sign mask
-                }
+                if (dir) carry = fw & 511u;                       // its data flips are signs now: next half's sign mask
                 continue;
             }
             __syncwarp();
-            // slots touched by an event of this shot (an event word, a sign they carry, the global phase) get private
-            // tables; the others use the event-free ones
+            // This shot's events in this half cycle.  Data flips upstream of an operation (bit 31 of its event word) are
+            // an XOR on the table index of its slot; signs (sign mask, flips of the preceding Hadamard-frame half) and
+            // the global phase multiply the selected factors; only slots whose own operations carry an ancilla Pauli, a
+            // leak skip or an idle Z get private entries.
             const uint32_t zmask = ((fw >> 9) ^ carry) & 511u, g = (fw >> 18) & 3u;
             const uint32_t cw = h ? chk_word[1] : chk_word[0];
-            const uint32_t evb = __ballot_sync(0xffffffffu, cw != 0xFFu && (evw[cw & 0xFFu] != 0u || ((fw >> (20 + (cw >> 8))) & 1u)));
-            uint32_t dirty = g ? 8u : 0u;
+            const uint32_t wv = cw != 0xFFu ? evw[cw & 0xFFu] : 0u;
+            const uint32_t evd = __ballot_sync(0xffffffffu, cw != 0xFFu && ((wv & 0x7FFFFFFFu) != 0u || ((fw >> (20 + (cw >> 8))) & 1u)));
+            uint32_t flipb = __ballot_sync(0xffffffffu, (wv >> 31) != 0u);
+            uint32_t dirty = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                if (((evb >> (4 * k)) & 15u) || (zmask & P.own[h][k])) dirty |= 1u << k;
+                if ((evd >> (4 * k)) & 15u) { dirty |= 1u << k; flipb &= ~(15u << (4 * k)); }     // flips are part of private entries
             if (dirty) {
-                dg_build_tables(H, evw, reinterpret_cast<double2 *>(tab), lane, zmask, g, fw >> 20, dirty);
+                uint32_t d = dirty;
+                while (d) {                                    // two slots per pass: lanes 0-15 / 16-31
+                    const int k0 = __ffs(d) - 1;
+                    d &= d - 1;
+                    const int k1 = d ? __ffs(d) - 1 : -1;
+                    d &= d - 1;
+                    const int k = lane < 16 ? k0 : k1, idx = lane & 15;
+                    if (k >= 0 && idx < (1 << H.n_ops[k]))
+                        dg_build_slot(H, evw, reinterpret_cast<double2 *>(tab), k, idx, fw >> 20);
+                }
                 __syncwarp();
             }
             const unsigned char *clean_h = clean + h * kDgTabBytes;
-            const uint32_t tl = h ? tlp[1] : tlp[0];
+            const uint32_t li = (h ? lidx[1] : lidx[0]) ^ flipb;
+            const unsigned char *tk0[4], *tk1[4];
+            uint32_t reg_neg = 0;
+            const DiagMap &M = H.frame_x ? P.mapB : P.mapA;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t rmask = P.off1[h][k] >> 4;                          // index bit fed by register bit k (or 0)
+                const uint32_t ix = (li >> (4 * k)) & 15u;
+                const unsigned char *base = (((dirty >> k) & 1u) ? tab : clean_h) + ((uint32_t)H.tbase[k] << 4);
+                tk0[k] = base + (ix << 4);                                         // (ix & rmask: that operation sees its bit flipped)
+                tk1[k] = base + ((ix ^ rmask) << 4);
+                reg_neg |= ((zmask >> M.reg[k]) & 1u) << k;
+            }
+            const uint32_t lane_neg = __popc((H.frame_x ? laneB : laneA) & zmask) & 1u;
             uint32_t a_out = 0;
             bool bad = false;
-            // slot k indexes its table with register bit k (the host orders the register bits of both maps that way),
-            // so the four slot steps are four straight-line instances shared by both halves
-#define S17_DG_SLOT1(K)                                                                                              \
-            {                                                                                                        \
-                const double u = __shfl_sync(0xffffffffu, uu, 4 * h + K);                                            \
-                const unsigned char *tk0 = (((dirty >> K) & 1u) ? tab : clean_h) + (((tl >> (8 * K)) & 0xFFu) << 4);   \
-                dg_slot1<K>(p, tk0, tk0 + P.off1[h][K], H.aj[K], is_forced, fo, u, a_out, bad, pfin,                 \
-                            pp_out ? pp_out + ((size_t)shot * 8 + 4 * h + K) * 2 : nullptr);                         \
-            }
-            S17_DG_SLOT1(0) S17_DG_SLOT1(1) S17_DG_SLOT1(2) S17_DG_SLOT1(3)
-#undef S17_DG_SLOT1
+            dg_half1(p, tk0, tk1, H.aj, is_forced, fo, uu, 4 * h, lane_neg, reg_neg, g, h == 1, a_out, bad, pfin,
+                     pp_out ? pp_out + ((size_t)shot * 8 + 4 * h) * 2 : nullptr);
             if (!H.frame_x) {
                 carry = 0;
                 perm = fw & 511u;                                 // data flips of a computational-frame half relabel the store
@@ -691,13 +811,11 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ MeasArgs m
             if (lane == 0) dsamp[shot] = (lab ^ perm) & 511u;
         }
 
-        // renormalise once, stage the block in label order (data flips of the computational-frame half relabel it) and
-        // hand it to one bulk store
-        const double inv = pfin > 0.0 ? 1.0 / sqrt(pfin) : 0.0;
+        // stage the (already renormalised) block in label order (data flips of the computational-frame half relabel it)
+        // and hand it to one bulk store
         __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-            *reinterpret_cast<double2 *>(xb + ((linA ^ P.mapA.lin16[i]) ^ (perm << 4))) = make_double2(p[i].x * inv, p[i].y * inv);
+        for (int i = 0; i < 16; ++i) *reinterpret_cast<double2 *>(xb + ((linA ^ P.mapA.lin16[i]) ^ (perm << 4))) = p[i];
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {

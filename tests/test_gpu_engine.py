@@ -113,11 +113,12 @@ def test_circuit_functions_on_the_engine_reproduce_reference_replays(error_model
     npz = np.load(os.path.join(GOLDEN, "replay_blocks.npz"))
     fields = ("quiescent", "synd1", "synd2", "flips_a", "ft_syndrome", "correction", "data_meas", "logical_meas", "fail",
               "not0", "counted", "leaked")
-    backend = Simulator(batch=2, rnd_seed=3)
-    eng = MainEngine(backend)
     picked = [r for i, r in enumerate(reps) if i % 2 == 0]
     for r in picked:
-        backend.forced.clear()
+        # a fresh engine per shot, like the reference's drivers (CL:299): a re-used engine carries the global phase of
+        # the previous shot's final basis state into the next one
+        backend = Simulator(batch=2, rnd_seed=3)
+        eng = MainEngine(backend)
         backend.forced.extend(r["outcomes"])
         rec = run_protocol(eng, backend, r["model"], r["p_set"], r["protocol"], r["cooling"], correction_table, bitflip_table)
         for f in fields:
@@ -127,7 +128,7 @@ def test_circuit_functions_on_the_engine_reproduce_reference_replays(error_model
             assert np.max(np.abs(rec["block"] - npz["blocks"][r["block_index"]])) < AMP_TOL and rec["outside"] < 1e-20
         assert not backend.forced and backend.impossible == 0
         assert sorted(backend.free) == list(range(17)) and not backend.pos      # every bit came back
-    backend.close()
+        backend.close()
     assert len(picked) >= 18
 
 
