@@ -435,71 +435,82 @@ __device__ __forceinline__ void dg_build_slot(const DiagHalf &H, const uint32_t 
     tab[e + kDgTabEntries] = make_double2((double)a1r, (double)a1i);
     tab[e + 2 * kDgTabEntries] = make_double2((double)(a0r * a0r + a0i * a0i), (double)(a1r * a1r + a1i * a1i));
 }
+// warp all-reduce of four doubles at the price of ten shuffles (instead of twenty): two transposing butterfly stages leave
+// one partial sum per lane, three plain stages finish it, four broadcasts hand every lane all four totals
+__device__ __forceinline__ void dg_reduce4(double (&v)[4], int lane) {
+    const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0;
+    const double k0 = (b4 ? v[2] : v[0]) + __shfl_xor_sync(0xffffffffu, b4 ? v[0] : v[2], 16);
+    const double k1 = (b4 ? v[3] : v[1]) + __shfl_xor_sync(0xffffffffu, b4 ? v[1] : v[3], 16);
+    double s = (b3 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, b3 ? k0 : k1, 8);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = __shfl_sync(0xffffffffu, s, 8 * i);      // lane 8 i holds the total of v[i]
+}
+
 // the four Measures of one half cycle from the real weights, then one complex update of the amplitudes.
 // tk0[k] / tk1[k]: this lane's table entries of slot k for register bit k = 0 / 1 (A0 at +0, A1 at +16 kDgTabEntries, Q
 // at +32 kDgTabEntries).  lane_neg: (-1)^lane_neg multiplies this lane's amplitudes; reg_neg bit j: amplitudes with
 // register bit j set change sign; g: global phase i^g.  scale_out: fold 1/sqrt(final weight) into the update.
+// The Measures are taken two at a time: the joint weights J[o_a][o_b] of a pair of slots need one reduction, and
+// P(o_a) = J[o_a][0] + J[o_a][1], P(o_b | o_a) = J[o_a][o_b] / P(o_a) are the sequential Measures' own probabilities.
 __device__ __forceinline__ void dg_half1(double2 (&p)[16], const unsigned char *(&tk0)[4], const unsigned char *(&tk1)[4],
                                          const uint8_t (&aj)[4], bool forced, uint32_t fo, double uu, int u_lane0,
                                          uint32_t lane_neg, uint32_t reg_neg, uint32_t g, bool scale_out, uint32_t &a_out,
-                                         bool &bad, double &pfin, double *pp) {
+                                         bool &bad, double &pfin, double *pp, int lane) {
     double w[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) w[i] = fma(p[i].x, p[i].x, p[i].y * p[i].y);
-    double m3[8], m2[4], m1[2];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) m3[j] = w[j] + w[j + 8];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) m2[j] = m3[j] + m3[j + 4];
-    m1[0] = m2[0] + m2[2];
-    m1[1] = m2[1] + m2[3];
     uint32_t outs = 0;
-    double csel[4][2];            // |A_out|^2 of the entries selected so far, per slot and register bit
-    // one Measure: (t0, t1) = this lane's weight with register bit K clear / set, already scaled by the factors of the
-    // earlier slots
-    auto measure = [&](int K, double t0, double t1) {
-        const double2 q0 = *reinterpret_cast<const double2 *>(tk0[K] + 32 * kDgTabEntries);
-        const double2 q1 = *reinterpret_cast<const double2 *>(tk1[K] + 32 * kDgTabEntries);
-        double p0 = fma(q0.x, t0, q1.x * t1), p1 = fma(q0.y, t0, q1.y * t1);
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            p0 += __shfl_xor_sync(0xffffffffu, p0, d);
-            p1 += __shfl_xor_sync(0xffffffffu, p1, d);
-        }
-        if (pp) { pp[2 * K] = p0; pp[2 * K + 1] = p1; }      // every lane holds the same pair
-        uint32_t out;
+    double csel[4][2];            // |A_out|^2 of the selected entries, per slot and register bit
+    // slots (KA, KB) = (0, 1) / (2, 3); m[b_a + 2 b_b]: this lane's weight per value of the two register bits
+    auto measure_pair = [&](int KA, const double (&m)[4]) {
+        const int KB = KA + 1;
+        const double2 qa0 = *reinterpret_cast<const double2 *>(tk0[KA] + 32 * kDgTabEntries);
+        const double2 qa1 = *reinterpret_cast<const double2 *>(tk1[KA] + 32 * kDgTabEntries);
+        const double2 qb0 = *reinterpret_cast<const double2 *>(tk0[KB] + 32 * kDgTabEntries);
+        const double2 qb1 = *reinterpret_cast<const double2 *>(tk1[KB] + 32 * kDgTabEntries);
+        // t[b_b][o_a], then J[o_a + 2 o_b]
+        const double t00 = fma(m[0], qa0.x, m[1] * qa1.x), t01 = fma(m[0], qa0.y, m[1] * qa1.y);
+        const double t10 = fma(m[2], qa0.x, m[3] * qa1.x), t11 = fma(m[2], qa0.y, m[3] * qa1.y);
+        double J[4] = {fma(t00, qb0.x, t10 * qb1.x), fma(t01, qb0.x, t11 * qb1.x),
+                       fma(t00, qb0.y, t10 * qb1.y), fma(t01, qb0.y, t11 * qb1.y)};
+        dg_reduce4(J, lane);
+        const double a0 = J[0] + J[2], a1 = J[1] + J[3];                     // P(o_a = 0), P(o_a = 1) (unnormalised)
+        uint32_t oa, ob;
         if (forced) {
-            out = (fo >> aj[K]) & 1u;
-            if ((out ? p1 : p0) <= 0.0) bad = true;
+            oa = (fo >> aj[KA]) & 1u;
+            ob = (fo >> aj[KB]) & 1u;
         } else {
-            const double u = __shfl_sync(0xffffffffu, uu, u_lane0 + K);
-            out = (u * (p0 + p1) < p1) ? 1u : 0u;            // Measure: P(1) against one uniform, as k_measure
+            oa = (__shfl_sync(0xffffffffu, uu, u_lane0 + KA) * (a0 + a1) < a1) ? 1u : 0u;   // Measure: P(1) against one uniform
         }
-        csel[K][0] = out ? q0.y : q0.x;
-        csel[K][1] = out ? q1.y : q1.x;
-        outs |= out << K;
-        a_out |= out << aj[K];
-        pfin = out ? p1 : p0;
+        const double b0 = oa ? J[1] : J[0], b1 = oa ? J[3] : J[2];            // P(o_a, o_b = 0), P(o_a, o_b = 1)
+        if (!forced) ob = (__shfl_sync(0xffffffffu, uu, u_lane0 + KB) * (b0 + b1) < b1) ? 1u : 0u;
+        if (forced && ((oa ? a1 : a0) <= 0.0 || (ob ? b1 : b0) <= 0.0)) bad = true;
+        if (pp) { pp[2 * KA] = a0; pp[2 * KA + 1] = a1; pp[2 * KB] = b0; pp[2 * KB + 1] = b1; }   // every lane holds the same pairs
+        csel[KA][0] = oa ? qa0.y : qa0.x;
+        csel[KA][1] = oa ? qa1.y : qa1.x;
+        csel[KB][0] = ob ? qb0.y : qb0.x;
+        csel[KB][1] = ob ? qb1.y : qb1.x;
+        outs |= (oa << KA) | (ob << KB);
+        a_out |= (oa << aj[KA]) | (ob << aj[KB]);
+        pfin = ob ? b1 : b0;
     };
-    measure(0, m1[0], m1[1]);
-    measure(1, fma(m2[0], csel[0][0], m2[1] * csel[0][1]), fma(m2[2], csel[0][0], m2[3] * csel[0][1]));
-    double c01[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) c01[j] = csel[0][j & 1] * csel[1][j >> 1];
     {
-        double t0 = m3[0] * c01[0], t1 = m3[4] * c01[0];
+        double m[4];                                                          // sum over register bits 2, 3
 #pragma unroll
-        for (int j = 1; j < 4; ++j) { t0 = fma(m3[j], c01[j], t0); t1 = fma(m3[4 + j], c01[j], t1); }
-        measure(2, t0, t1);
+        for (int j = 0; j < 4; ++j) m[j] = (w[j] + w[j + 4]) + (w[j + 8] + w[j + 12]);
+        measure_pair(0, m);
     }
     {
-        double c012[8];
+        double c01[4], m[4];                                                  // weight of (b2, b3) given the first two outcomes
 #pragma unroll
-        for (int j = 0; j < 8; ++j) c012[j] = c01[j & 3] * csel[2][j >> 2];
-        double t0 = w[0] * c012[0], t1 = w[8] * c012[0];
+        for (int j = 0; j < 4; ++j) c01[j] = csel[0][j & 1] * csel[1][j >> 1];
 #pragma unroll
-        for (int j = 1; j < 8; ++j) { t0 = fma(w[j], c012[j], t0); t1 = fma(w[8 + j], c012[j], t1); }
-        measure(3, t0, t1);
+        for (int q = 0; q < 4; ++q)
+            m[q] = fma(w[4 * q], c01[0], fma(w[4 * q + 1], c01[1], fma(w[4 * q + 2], c01[2], w[4 * q + 3] * c01[3])));
+        measure_pair(2, m);
     }
     // the selected complex factors, with the shot's signs and phase
     double2 f[4][2];
@@ -762,7 +773,7 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ MeasArgs m
             uint32_t a_out = 0;
             bool bad = false;
             dg_half1(p, tk0, tk1, H.aj, is_forced, fo, uu, 4 * h, lane_neg, reg_neg, g, h == 1, a_out, bad, pfin,
-                     pp_out ? pp_out + ((size_t)shot * 8 + 4 * h) * 2 : nullptr);
+                     pp_out ? pp_out + ((size_t)shot * 8 + 4 * h) * 2 : nullptr, lane);
             if (!H.frame_x) {
                 carry = 0;
                 perm = fw & 511u;                                 // data flips of a computational-frame half relabel the store
