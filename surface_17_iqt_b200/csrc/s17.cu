@@ -311,18 +311,32 @@ __device__ __forceinline__ uint32_t pconj_rxx(uint32_t P, int s) {        // Rxx
 
 // One thread per shot; a warp stages its 32 shots' slot bitsets and event words through shared memory (row stride 33
 // words) so that the global traffic is coalesced rows instead of 32 strided 4-byte accesses per instruction.
+//
+// The program is walked by GROUP (one entangling operation, or the idle slots of one gap between timesteps, in program
+// order).  A shot first finds which groups have a fired entry at all -- from its placed / replayed slot bits, or, with
+// true probabilities, by sampling the position of the next firing entry from the survival products of the program
+// (geometric skipping: P(first fire at i) = S_i p_i, S_i = prod_{j<i} (1 - p_j); one uniform per event instead of one
+// per entry) -- and only those groups are walked instruction by instruction; every other operation takes its default
+// event word (the data-flip bit of the frame).  A set leak flag, or a fired leakage entry, makes the shot walk every
+// group (the skip predicate of every later operation may change).
 constexpr int kPlanThreads = 128;
 constexpr int kPlanRow = 33;
 constexpr int kPlanMaxInstr = 640;
+constexpr int kPlanMaxGroups = 32;
+// group word: bits 0-9 first instruction, 10-19 one past the last, 20 gap (idle) group, 21-25 event word, 26-29 data bit,
+// 30 first operation of its half cycle, 31 half index
 __global__ void __launch_bounds__(kPlanThreads)
 k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, NoiseDev nd, const double *__restrict__ probs,
        uint32_t *__restrict__ ev, uint32_t *__restrict__ masks, uint32_t *__restrict__ leak,
        const uint8_t *__restrict__ active, uint32_t *__restrict__ frm, uint32_t *__restrict__ n_act,
        const uint32_t *__restrict__ hot, uint8_t *__restrict__ quiet /* nullptr, or per shot: 1 = no entry fired and no
-       qubit is leaked in this cycle (event-free: k_quiet replays it from the cache) */)
+       qubit is leaked in this cycle (event-free: k_quiet replays it from the cache) */,
+       const uint32_t *__restrict__ grp, int n_grp, const uint8_t *__restrict__ bit2grp /* slot bit -> group | leak << 7 */,
+       const double *__restrict__ surv /* nullptr, or survival products S_0 .. S_n of this cycle's entries */)
 {
     __shared__ uint32_t s_mask[kPlanThreads / 32][32][kPlanRow], s_ev[kPlanThreads / 32][32][kPlanRow];
     __shared__ uint32_t s_prog[kPlanMaxInstr * 3];     // the program of this cycle (slots resolved to absolute bit indices)
+    __shared__ uint32_t s_grp[kPlanMaxGroups];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int shot = blockIdx.x * blockDim.x + threadIdx.x, shot0 = shot - lane;
     if (shot == 0) *n_act = 0;                         // k_compact, next in the stream, appends to an empty list
@@ -333,6 +347,7 @@ k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, NoiseDev nd, const doub
         const uint32_t *src = reinterpret_cast<const uint32_t *>(prog);
         for (int i = threadIdx.x; i < pa.n_instr * 3; i += blockDim.x) s_prog[i] = src[i];
         for (int i = threadIdx.x; i < pa.n_instr; i += blockDim.x) s_hot[i] = hot[i];
+        if (threadIdx.x < kPlanMaxGroups) s_grp[threadIdx.x] = threadIdx.x < n_grp ? grp[threadIdx.x] : 0u;
         __syncthreads();
     }
     const bool act = shot < pa.n_shots && active[shot];
@@ -345,7 +360,6 @@ k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, NoiseDev nd, const doub
     __syncwarp();
     uint32_t *evs = s_ev[wib][lane];
     uint32_t *mk = s_mask[wib][lane];                  // placed slots (subset / replay) or the slots fired now (prob mode)
-    uint32_t *mrec = mk;
     uint32_t lk = 0;
     Philox rng(pa.seed, pa.first_shot + shot, pa.stream);
     uint32_t f_flip = 0, f_sign = 0, f_phase = 0, f_ancz = 0;   // frame bookkeeping of the current half cycle (k_cycle)
@@ -359,23 +373,65 @@ k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, NoiseDev nd, const doub
         frm[(size_t)shot * 4 + 1] = 0;
     } else if (act) {
     for (int i = 24; i < (int)S17_EV_WORDS; ++i) evs[i] = 0;
+    // ---- which entries fire ----
+    if (prob_mode && !pa.noiseless) {
+        if (surv) {
+            int pos = 0;
+            const double s_end = surv[pa.n_instr];
+            for (;;) {
+                const double target = rng.next() * surv[pos];
+                if (!(s_end < target)) break;                        // nothing fires in the rest of the cycle
+                int lo = pos, hi = pa.n_instr - 1;                   // smallest i >= pos with S_{i+1} < target
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (surv[mid + 1] < target) hi = mid; else lo = mid + 1;
+                }
+                mask_set(mk, s_hot[lo] & 0xFFFFu);
+                pos = lo + 1;
+            }
+        } else {
+            for (int i = 0; i < pa.n_instr; ++i) {                   // one Bernoulli draw per entry (CS:198)
+                const uint32_t hw = s_hot[i];
+                if ((hw & 0x20000u) && rng.next() < probs[hw & 0xFFFFu]) mask_set(mk, hw & 0xFFFFu);
+            }
+        }
+    }
+    uint32_t flagged = 0, leak_event = 0;
+    if (!pa.noiseless) {
+        for (int wi = 0; wi < (int)S17_MASK_WORDS; ++wi) {
+            uint32_t word = mk[wi];
+            while (word) {
+                const uint32_t g = bit2grp[32 * wi + __ffs(word) - 1];
+                word &= word - 1;
+                if (g != 0xFFu) { flagged |= 1u << (g & 31u); leak_event |= g >> 7; }
+            }
+        }
+    }
+    any_event = any_event || flagged != 0;
+    const uint32_t todo = (lk != 0 || leak_event) ? 0xFFFFFFFFu : flagged;
     uint32_t w = 0, skip = 0;
-    for (int i = 0; i < pa.n_instr; ++i) {
+    for (int gi = 0; gi < n_grp; ++gi) {
+    const uint32_t gm = s_grp[gi];
+    if (!((todo >> gi) & 1u)) {
+        // no entry of this group fires and no qubit is leaked: the default of an operation is its data-flip bit
+        if (!((gm >> 20) & 1u)) {
+            if ((gm >> 30) & 1u) {
+                if (f_half >= 0)
+                    frm[(size_t)shot * 4 + f_half] = f_flip | (f_sign << 9) | ((f_phase & 3u) << 18) | (f_ancz << 20);
+                f_flip = 0; f_sign = 0; f_phase = 0; f_ancz = 0;
+                f_half = (int)(gm >> 31);
+            }
+            evs[(gm >> 21) & 31u] = ((f_flip >> ((gm >> 26) & 15u)) & 1u) << 31;
+        }
+        continue;
+    }
+    for (int i = (int)(gm & 1023u); i < (int)((gm >> 10) & 1023u); ++i) {
         const uint32_t hw = s_hot[i];
         if (hw & 0x20000u) {
-            // one Bernoulli draw per entry (CS:198), none inside a skipped Rxx block.  The slot is the absolute index of
-            // the entry in this cycle (list offset + slot + half the list in a second cycle, CS:191-193).
+            // a fired entry acts unless it sits inside a skipped Rxx block (CS:293, 322).  The slot is the absolute index
+            // of the entry in this cycle (list offset + slot + half the list in a second cycle, CS:191-193).
             if ((((hw >> 16) & 1u) & skip) || pa.noiseless) continue;
-            const uint32_t bit = hw & 0xFFFFu;
-            bool fire;
-            if (prob_mode) {
-                fire = rng.next() < probs[bit];
-                if (fire) mask_set(mrec, bit);
-            } else {
-                fire = mask_get(mk, bit);
-            }
-            if (!fire) continue;
-            any_event = true;
+            if (!mask_get(mk, hw & 0xFFFFu)) continue;
         }
         const s17_pinstr in = reinterpret_cast<const s17_pinstr *>(s_prog)[i];
         if (in.kind == S17_P_OP_BEGIN) { w = 0; skip = 0; continue; }
@@ -461,6 +517,7 @@ k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, NoiseDev nd, const doub
         default: break;
         }
         w = (w & ~(63u << in.field)) | (f << in.field);
+    }
     }
     if (f_half >= 0) frm[(size_t)shot * 4 + f_half] = f_flip | (f_sign << 9) | ((f_phase & 3u) << 18) | (f_ancz << 20);
     leak[shot] = lk;
@@ -1019,6 +1076,14 @@ struct s17_ctx {
     unsigned long long *counters = nullptr;
     s17_pinstr *plan = nullptr;
     uint32_t *plan_hot = nullptr;
+    // k_plan's group tables, per cycle variant (first / second cycle): group words, slot bit -> group, survival products
+    uint32_t *plan_grp = nullptr;
+    uint8_t *plan_bit2grp = nullptr;
+    double *plan_surv = nullptr;
+    int n_grp[2] = {0, 0};
+    bool geo_ok[2] = {false, false}, plan_dup_slot = false, no_geo = false;
+    std::vector<s17_pinstr> plan_res;     // host copy of the resolved program (both variants)
+    std::vector<double> h_probs;          // host copy of the slot probabilities
     RtfSlot *rtf_slots = nullptr;
     uint32_t *rtf_rounds = nullptr, *rtf_syndb = nullptr;
     uint32_t *rtf_block_cnt = nullptr, *rtf_block_off = nullptr, *rtf_ticket = nullptr;
@@ -1228,6 +1293,8 @@ extern "C" int s17_create(s17_ctx **out, int device, uint64_t max_shots) {
         ctx->quiet_copy = !(qcp && qcp[0] == '0');
         const char *r = getenv("S17_RING");
         ctx->force_ring = r && r[0] == '1';
+        const char *ge = getenv("S17_GEO");               // 0: one Bernoulli draw per entry instead of geometric skipping
+        ctx->no_geo = ge && ge[0] == '0';
     }
     {
         cudaDeviceProp prop;
@@ -1254,6 +1321,7 @@ extern "C" int s17_destroy(s17_ctx *ctx) {
                     ctx->aux, ctx->rec, ctx->counters, ctx->lut, ctx->cw16, ctx->probs, ctx->cum, ctx->plan,
                     ctx->rtf_slots, ctx->rtf_rounds, ctx->rtf_syndb, ctx->rtf_block_cnt, ctx->rtf_block_off, ctx->rtf_ticket, ctx->act_list, ctx->n_act, ctx->zero_page, ctx->meas_out,
                     ctx->frm, ctx->dsamp, ctx->prep_leaf, ctx->prep_done, ctx->prep_blocks, ctx->prep_pp, ctx->plan_hot,
+                    ctx->plan_grp, ctx->plan_bit2grp, ctx->plan_surv,
                     ctx->quiet_blocks, ctx->quiet_cdf, ctx->quiet_ok, ctx->quiet_flag};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -1832,6 +1900,55 @@ extern "C" int s17_load_program(s17_ctx *ctx, const s17_layer *layers, const uin
         CK(cudaMemcpy(ctx->plan, res.data(), res.size() * sizeof(s17_pinstr), cudaMemcpyHostToDevice));
         CK(cudaMalloc(&ctx->plan_hot, hot.size() * 4));
         CK(cudaMemcpy(ctx->plan_hot, hot.data(), hot.size() * 4, cudaMemcpyHostToDevice));
+        // groups of the program (one entangling operation / the idle entries of one gap), in program order
+        std::vector<uint32_t> grp(2 * kPlanMaxGroups, 0u);
+        std::vector<uint8_t> b2g(2 * 2048, 0xFFu);
+        ctx->plan_dup_slot = false;
+        for (int c2 = 0; c2 < 2; ++c2) {
+            int ng = 0;
+            uint32_t i = 0;
+            while (i < n_plan) {
+                const s17_pinstr *q = &res[(size_t)c2 * n_plan];
+                uint32_t j = i, meta = 0;
+                if (q[i].kind == S17_P_OP_BEGIN) {
+                    while (j < n_plan && q[j].kind != S17_P_OP_END) ++j;
+                    if (j == n_plan) return fail(ctx, S17_E_ARG, "plan: operation without an end");
+                    const s17_pinstr &e = q[j];
+                    meta = ((uint32_t)e.word << 1) | ((uint32_t)(plan[j].slot & 15u) << 6) | (((e.a >> 4) & 1u) << 10) |
+                           (((e.a >> 5) & 1u) << 11);
+                    ++j;
+                } else if (q[i].kind == S17_P_IDLE) {
+                    while (j < n_plan && q[j].kind == S17_P_IDLE && q[j].word == q[i].word) ++j;
+                    meta = 1u | ((uint32_t)q[i].word << 1);
+                } else {
+                    return fail(ctx, S17_E_ARG, "plan: entry outside an operation");
+                }
+                if (ng >= kPlanMaxGroups) return fail(ctx, S17_E_ARG, "plan: too many groups");
+                grp[(size_t)c2 * kPlanMaxGroups + ng] = i | (j << 10) | (meta << 20);
+                for (uint32_t k = i; k < j; ++k)
+                    if (q[k].kind == S17_P_ERR || q[k].kind == S17_P_IDLE) {
+                        uint8_t &slot = b2g[(size_t)c2 * 2048 + q[k].slot];
+                        const bool lk_kind = q[k].kind == S17_P_ERR && (q[k].err == S17_ERR_LEAK_A || q[k].err == S17_ERR_LEAK_AB);
+                        if (slot != 0xFFu && (slot & 31u) != (uint32_t)ng) ctx->plan_dup_slot = true;   // one slot, two groups
+                        if (slot != 0xFFu) ctx->plan_dup_slot = true;
+                        slot = (uint8_t)((slot == 0xFFu ? 0u : (slot & 0x80u)) | (uint32_t)ng | (lk_kind ? 0x80u : 0u));
+                    }
+                ++ng;
+                i = j;
+            }
+            ctx->n_grp[c2] = ng;
+        }
+        for (void *q : {(void *)ctx->plan_grp, (void *)ctx->plan_bit2grp, (void *)ctx->plan_surv})
+            if (q) cudaFree(q);
+        ctx->plan_grp = nullptr; ctx->plan_bit2grp = nullptr; ctx->plan_surv = nullptr;
+        CK(cudaMalloc(&ctx->plan_grp, grp.size() * 4));
+        CK(cudaMemcpy(ctx->plan_grp, grp.data(), grp.size() * 4, cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&ctx->plan_bit2grp, b2g.size()));
+        CK(cudaMemcpy(ctx->plan_bit2grp, b2g.data(), b2g.size(), cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&ctx->plan_surv, 2 * (size_t)(kPlanMaxInstr + 1) * sizeof(double)));
+        ctx->plan_res = res;
+        ctx->h_probs.assign(2048, 0.0);
+        ctx->geo_ok[0] = ctx->geo_ok[1] = false;
     }
     CK(cudaMemset(ctx->probs, 0, 2048 * sizeof(double)));
     ctx->prep_basis = -1;
@@ -1888,6 +2005,24 @@ extern "C" int s17_set_slot_probs(s17_ctx *ctx, uint32_t list_id, const double *
         return fail(ctx, S17_E_ARG, "make sure you pass enough probabilities to specify the error model");
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpy(ctx->probs + ctx->nd.list_off[list_id], p, len * sizeof(double), cudaMemcpyHostToDevice));
+    for (uint32_t i = 0; i < len; ++i) ctx->h_probs[ctx->nd.list_off[list_id] + i] = p[i];
+    // survival products of the program's entries, per cycle variant (k_plan's geometric skipping).  Only used while a
+    // cycle is mostly event-free (S_n > 1/4): with more noise than that the one-draw-per-entry walk is as cheap, and it
+    // copes with probabilities of 1; also not when two entries share a slot (they would need separate draws).
+    const int n = ctx->n_plan;
+    std::vector<double> surv(2 * (size_t)(kPlanMaxInstr + 1), 1.0);
+    for (int c2 = 0; c2 < 2; ++c2) {
+        double *S = &surv[(size_t)c2 * (kPlanMaxInstr + 1)];
+        for (int i = 0; i < n; ++i) {
+            const s17_pinstr &in = ctx->plan_res[(size_t)c2 * n + i];
+            const bool entry = in.kind == S17_P_ERR || in.kind == S17_P_IDLE;
+            double q = entry ? ctx->h_probs[in.slot] : 0.0;
+            q = q < 0.0 ? 0.0 : (q > 1.0 ? 1.0 : q);
+            S[i + 1] = S[i] * (1.0 - q);
+        }
+        ctx->geo_ok[c2] = !ctx->plan_dup_slot && !ctx->no_geo && S[n] > 0.25;
+    }
+    CK(cudaMemcpy(ctx->plan_surv, surv.data(), surv.size() * sizeof(double), cudaMemcpyHostToDevice));
     return S17_OK;
 }
 
@@ -2143,7 +2278,11 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
         k_plan<<<blocks_for(n, kPlanThreads), kPlanThreads, 0, ctx->stream>>>(ctx->plan + (second ? ctx->n_plan : 0), pa, ctx->nd, ctx->probs, ctx->ev, ctx->masks,
                                                             ctx->leak, ctx->active, ctx->frm, ctx->n_act,
                                                                           ctx->plan_hot + (second ? ctx->n_plan : 0),
-                                                                          (ctx->use_quiet && stage == 1) ? ctx->quiet_flag : nullptr);
+                                                                          (ctx->use_quiet && stage == 1) ? ctx->quiet_flag : nullptr,
+                                                                          ctx->plan_grp + (second ? kPlanMaxGroups : 0), ctx->n_grp[second ? 1 : 0],
+                                                                          ctx->plan_bit2grp + (second ? 2048 : 0),
+                                                                          (a.noise == S17_NOISE_PROB && ctx->geo_ok[second ? 1 : 0])
+                                                                              ? ctx->plan_surv + (second ? kPlanMaxInstr + 1 : 0) : nullptr);
     }
     const int which = stage == 0 ? 0 : (second ? 2 : 1);
     const std::vector<LayerArg> &Ls = ctx->layers[which];
