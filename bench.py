@@ -358,17 +358,58 @@ def run_gpu(args):
     if rank == 0 and not args.no_dense:
         os.environ["S17_DENSE"] = "1"
         try:
-            dsim = api.Simulation(MODEL, LOCS2, args.dense_shots, ct, bt, fusion=1, device=local, error_models=models,
+            D = args.dense_shots
+            dsim = api.Simulation(MODEL, LOCS2, D, ct, bt, fusion=1, device=local, error_models=models,
                                   early_measure=False)
             dsim.backend.set_subset(ESET, LOCS2)
-            dsim.backend.run("s2", args.dense_shots, L.NOISE_SUBSET, seed=args.seed)
-            dc = dsim.backend.run("s2", args.dense_shots, L.NOISE_SUBSET, seed=args.seed + 1)
-            dt = dsim.backend.timing()
-            d_ach = dc.sweep_bytes / (dt["gate_ms"] * 1e-3) / 1e9
+            dsim.backend.run("s2", D, L.NOISE_SUBSET, seed=args.seed)                 # warm-up
+            g_ms = g_bytes = g_launch = 0
+            c_ms = c_shots = c_launch = 0
+            m_ms = m_launch = 0
+            d_span = 0.0
+            d_sweeps = 0
+            for rep in range(args.dense_reps):
+                dc = dsim.backend.run("s2", D, L.NOISE_SUBSET, seed=args.seed + 1 + rep)
+                dt = dsim.backend.timing()
+                g_ms += dt["gate_ms"]
+                g_bytes += dc.sweep_bytes
+                g_launch += dt["gate_launches"]
+                d_sweeps += dc.sweeps
+                d_span += dt["span_ms"]
+                cl = dt["classes"]
+                c_ms += cl["collapse"]["ms"]
+                c_launch += cl["collapse"]["launches"]
+                c_shots += cl["collapse"]["units"]
+                m_ms += cl["sample"]["ms"]
+                m_launch += cl["sample"]["launches"]
+            d_ach = g_bytes / (g_ms * 1e-3) / 1e9
+            # the measurement layer as this library runs it in full-state mode: the probability reduction is fused into
+            # the gate sweep before the Measure (no extra pass over the state), k_measure samples from 256 weights
+            # (2 KiB per shot), k_collapse reads the surviving 8 KiB block and writes the whole 2 MiB state (block at
+            # ancilla value 0, zeros elsewhere).  SURVEY 8(d) counts reduce 2 MiB + collapse 4 MiB = 6 291 456 B for
+            # ProjectQ's form of the same layer.
+            COLLAPSE_MOVED = (1 << 17) * 16 + 8192
+            c_ach = c_shots * COLLAPSE_MOVED / (c_ms * 1e-3) / 1e9 if c_ms > 0 else None
             dense = {"kernel": "k_layer2", "mode": "S17_DENSE=1, fusion=1 (8 full-state sweeps per cycle + explicit collapse)",
                      "achieved": d_ach, "peak": peak, "unit": "GB/s", "frac": d_ach / peak,
-                     "shots_per_s": args.dense_shots / (dt["span_ms"] * 1e-3), "shots": args.dense_shots,
-                     "bytes_per_shot": dc.sweep_bytes / args.dense_shots}
+                     "shots_per_s": D * args.dense_reps / (d_span * 1e-3), "shots": D, "repetitions": args.dense_reps,
+                     "bytes_per_shot": g_bytes / (D * args.dense_reps),
+                     "gate_layer": {"kernel": "k_layer2", "bytes_per_shot_and_layer": SWEEP_BYTES, "layers": int(d_sweeps),
+                                    "launches": int(g_launch), "ms": g_ms, "achieved": d_ach, "frac": d_ach / peak,
+                                    "note": "layers = full-state sweeps counted by the kernel (one per shot and launch); "
+                                            "bytes = layers x 4 194 304"},
+                     "measure_layer": {"kernels": ["k_layer2 (fused probability reduction)", "k_measure", "k_collapse"],
+                                       "collapse_launches": int(c_launch), "collapse_shots": int(c_shots), "collapse_ms": c_ms,
+                                       "moved_bytes_per_shot": COLLAPSE_MOVED,
+                                       "achieved": c_ach, "frac": (c_ach / peak) if c_ach else None,
+                                       "sample_ms": m_ms, "sample_launches": int(m_launch),
+                                       "survey_bytes_per_shot": 6291456,
+                                       "survey_equivalent": (c_shots * 6291456 / ((c_ms + m_ms) * 1e-3) / 1e9 / peak) if c_ms > 0 else None,
+                                       "note": "achieved/frac = bytes k_collapse really moves (8 KiB read + 2 MiB written per shot) "
+                                               "over its CUDA-event time; survey_equivalent = SURVEY 8(d)'s 6 291 456 B per shot "
+                                               "over k_measure + k_collapse time, as a fraction of peak -- above 1 means the fused "
+                                               "reduction and the write-only collapse move fewer bytes than ProjectQ's form, not "
+                                               "that the bus is faster"}}
             dsim.close()
         except Exception as exc:          # evidence only: never lose the main line over it
             dense = {"error": str(exc)[:200]}
@@ -392,6 +433,43 @@ def run_gpu(args):
     e2e_value = B * world * args.steps / float(e2e_t.item())
     drv.release()
 
+    # the binding unit of k_cycle1 is the FP64 pipe, not HBM: instruction counts and DRAM traffic per shot-cycle come
+    # from the committed ncu capture of this kernel (profiles/k_cycle1_counts.json, written by
+    # profiles/tools/ncu_counts.py from an `ncu --set full` report), the time is this run's
+    counts = {}
+    try:
+        counts = json.load(open(os.path.join(REPO, "profiles", "k_cycle1_counts.json")))
+    except Exception:
+        pass
+    sm_hz = (sampler.summary().get("sm_mhz") or 1965) * 1e6
+    n_sms = torch.cuda.get_device_properties(local).multi_processor_count
+    fp64 = None
+    if counts.get("fp64_warp_instr_per_shot_cycle") and gate_ms > 0:
+        # 64 FP64 lanes per SM and clock: one warp instruction occupies an SM's FP64 pipes for half a clock
+        floor_ms = 1e3 * counts["fp64_warp_instr_per_shot_cycle"] * sweeps * 0.5 / (n_sms * sm_hz)
+        fp64 = {"warp_instr_per_shot_cycle": counts["fp64_warp_instr_per_shot_cycle"],
+                "all_warp_instr_per_shot_cycle": counts.get("warp_instr_per_shot_cycle"),
+                "floor_ms": floor_ms, "kernel_ms": gate_ms, "frac": floor_ms / gate_ms,
+                "peak": "64 FP64 lanes per SM and clock x {} SMs x {:.0f} MHz".format(n_sms, sm_hz / 1e6),
+                "source": counts.get("source")}
+    traffic = None
+    if counts.get("dram_bytes_per_shot_cycle") and gate_launches:
+        traffic = counts["dram_bytes_per_shot_cycle"] * sweeps / gate_launches
+    roofline = {"bound": "hbm", "kernel": "k_cycle1", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                "traffic": traffic,
+                "traffic_source": counts.get("source"),
+                "binding_unit": "fp64 pipe", "fp64": fp64,
+                "note": "one launch = one stabiliser cycle of every active shot: 8 KiB read (none in the preparation "
+                        "cycle) + 8 KiB written per shot, everything else in registers / shared memory, so the HBM "
+                        "fraction is low by construction; the unit that binds is the FP64 pipe (`fp64`: counted FP64 warp "
+                        "instructions x 0.5 clock / kernel time).  SURVEY 8(d)'s per-layer bytes (4 194 304 per gate layer, "
+                        "6 291 456 per measurement layer) apply to the full-state configuration: `roofline_dense`",
+                "launches": int(gate_launches), "sweeps": int(sweeps),
+                "sweeps_per_shot": sweeps / (B * args.steps),
+                "bytes_per_shot": sweep_bytes / (B * args.steps), "dense_bytes_per_sweep": SWEEP_BYTES,
+                "gate_kernel_share_of_step": gate_ms / span_ms if span_ms else None}
+
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu:
@@ -408,20 +486,7 @@ def run_gpu(args):
                     "h2d_bytes_per_step": 2048 * 8 + 3 * 4 * len(ESET) + 64, "d2h_bytes_per_step": 64 + 8 * 8,
                     "api": "s2_calculate_log_e_rate_error_subset(num_runs, ...) -> (rate, not0_rate, failed, not0)"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_cycle1", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
-                         # dram__bytes_read+write of one ncu --set full capture of this kernel, scaled to this run's
-                         # average launch: 1.834 GB measured for 1.870 GB algorithmic (second noisy cycle of a
-                         # 131072-shot batch, profiles/r1t_k_cycle1_ncu_full.csv / r1t_k_cycle1_summary.md)
-                         "traffic": (sweep_bytes / max(1, gate_launches)) * (1.834 / 1.870),
-                         "note": "one launch = one stabiliser cycle of every active shot: 8 KiB read (none in the preparation "
-                                 "cycle) + 8 KiB written per shot, everything else in registers / shared memory; ncu: FP64 "
-                                 "pipe 42-47 %, shared-memory wavefronts 45-51 %, issue slots 47-54 % -- not HBM-bound; the "
-                                 "HBM-bound full-state configuration is roofline_dense",
-                         "launches": int(gate_launches), "sweeps": int(sweeps),
-                         "sweeps_per_shot": sweeps / (B * args.steps),
-                         "bytes_per_shot": sweep_bytes / (B * args.steps), "dense_bytes_per_sweep": SWEEP_BYTES,
-                         "gate_kernel_share_of_step": gate_ms / span_ms if span_ms else None},
+            "roofline": roofline,
             "counts": {"failed": int(tot[0]), "not0": int(tot[1]), "shots": total_shots},
         }
         if plain is not None:
@@ -436,6 +501,125 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------------
+# run-til-fail workload (BASELINE config 5): --workload rtf
+# ---------------------------------------------------------------------------------------------------
+def run_gpu_rtf(args):
+    """calculate_log_e_rate's loop (CL:33-148) at the size of BASELINE config 5: Dress_model (leakage) with true Bernoulli
+    noise p_set = [12 x p/10, 18 x p/10, 24 x p, 78 x p_leak = 1e-4, 24 x 0], every GPU a fixed budget of rounds per step
+    (10^8 rounds over 8 GPUs = 1.25e7 per GPU).  A step = one run-til-fail job of --shots slots per GPU that stops when
+    its round budget is spent (a slot whose run fails takes the next run id).  value = rounds/s over all GPUs,
+    device-timed span (max over ranks); e2e = the same through calculate_log_e_rate(..., round_budget=...) with host
+    lists out.  The runs shard over the ranks; the only exchange is the gather of the per-run lists at the end."""
+    import torch
+    import torch.distributed as dist
+    from surface_17_iqt_b200 import _lib as L
+    from surface_17_iqt_b200 import api
+    import surface_17_iqt_b200.calc_log_e_rate_arbitrary_error_model as drv
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ct, bt, models = load_tables()
+    p = args.p
+    lens = [12, 18, 24, 78, 24]
+    p_set = [[p / 10] * 12, [p / 10] * 18, [p] * 24, [1e-4] * 78, [0.0] * 24]
+    B, budget = args.shots, args.rtf_rounds
+    sim = api.Simulation("Dress_model", lens, B, ct, bt, fusion=args.fusion, device=local, error_models=models)
+    sim.backend.set_slot_probs(p_set)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(k):
+        c = sim.backend.run("rtf", B, L.NOISE_PROB, seed=args.seed + k, first_shot_id=rank * B, rtf_runs=B * 2,
+                            leak_reset="run", rtf_round_budget=budget)
+        return c, sim.backend.timing()
+
+    for k in range(args.warmup):
+        step(k)
+    torch.zeros(1, device="cuda")
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    span_ms = gate_ms = 0.0
+    rounds = launches = gate_launches = sweeps = failed_runs = 0
+    for k in range(args.steps):
+        c, t = step(args.warmup + k)
+        span_ms += t["span_ms"]
+        gate_ms += t["gate_ms"]
+        rounds += c.rounds
+        sweeps += c.sweeps
+        failed_runs += c.failed
+        launches += t["launches"]
+        gate_launches += t["gate_launches"]
+    tot = torch.tensor([rounds, failed_runs, sweeps], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tot)
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    sampler.stop_flag = True
+    times = torch.tensor([span_ms, wall_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    span_ms_max, wall_ms_max = [float(v) for v in times.tolist()]
+    total_rounds = int(tot[0].item())
+    value = total_rounds / (span_ms_max * 1e-3)
+    sim.close()
+
+    # e2e: the drop-in with host results (per-run lists gathered to every rank, no fit, no file)
+    drv.VERBOSE = False
+    drv.BATCH_SHOTS, drv.FUSION, drv.DEVICE = B, args.fusion, local
+    e_model, e_probs = "Dress_model", dict(zip(models["Dress_model"]["probabilities"], p_set))
+    drv.calculate_log_e_rate(B * 2 * world, "bench", ct, e_model, e_probs, bt, save=False, fit=False,
+                             round_budget=budget)
+    barrier()
+    t1 = time.perf_counter()
+    e_rounds = 0
+    for _ in range(args.steps):
+        drv.calculate_log_e_rate(B * 2 * world, "bench", ct, e_model, e_probs, bt, save=False, fit=False,
+                                 round_budget=budget)
+        e_rounds += drv.LAST_TIMING["rounds"]
+    barrier()
+    e2e_t = torch.tensor([time.perf_counter() - t1], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    drv.release()
+    if rank == 0:
+        line = {
+            "metric": "noisy Surface-17 run-til-fail rounds/sec", "value": value, "unit": "rounds/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": span_ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128)",
+            "data": "synthetic",
+            "config": {"workload": "Surface-17 Dress_model (leakage) run-til-fail, true Bernoulli noise p = {:g}, "
+                                   "p_leak = 1e-4 (BASELINE config 5)".format(p),
+                       "slots_per_gpu": B, "round_budget_per_gpu_and_step": budget, "leak_reset": "run",
+                       "parallelism": "runs sharded x{}".format(world),
+                       "l2": "per-round working set (slots x 16 KiB) exceeds the 126 MB L2, no flush needed"},
+            "wall_ms_per_step": wall_ms_max / args.steps, "clocks": sampler.summary(),
+            "e2e": {"value": e_rounds / float(e2e_t.item()), "unit": "rounds/s",
+                    "h2d_bytes_per_step": 2048 * 8 + 64, "d2h_bytes_per_step": 2 * 4 * B * 2,
+                    "api": "calculate_log_e_rate(num_runs, ..., round_budget=...) -> rounds_til_fail_list, syndrome_b_measured_list"},
+            "gpu_launches": int(launches),
+            "rounds": total_rounds, "runs_failed": int(tot[1].item()),
+            "cycles_per_round": int(tot[2].item()) / max(1, total_rounds),
+            "gate_kernel_share_of_step": gate_ms / span_ms if span_ms else None,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -445,17 +629,24 @@ def main():
     ap.add_argument("--shots", type=int, default=int(os.environ.get("S17_BENCH_SHOTS", "524288")), help="shots per GPU per step")
     ap.add_argument("--fusion", type=int, default=2)
     ap.add_argument("--seed", type=int, default=2026)
+    ap.add_argument("--workload", default="subset", choices=["subset", "rtf"],
+                    help="subset: BASELINE config 2 (the headline); rtf: run-til-fail, BASELINE config 5")
+    ap.add_argument("--p", type=float, default=1e-3, help="rtf: physical error rate")
+    ap.add_argument("--rtf-rounds", type=int, default=12500000, help="rtf: round budget per GPU and step")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-dense", action="store_true")
     ap.add_argument("--no-plain", action="store_true")
     ap.add_argument("--memo-headline", action="store_true",
                     help="time the library default (memoised preparation cycle) as value / e2e and the full computation as the extra")
-    ap.add_argument("--dense-shots", type=int, default=4096)
+    ap.add_argument("--dense-shots", type=int, default=16384)
+    ap.add_argument("--dense-reps", type=int, default=5)
     ap.add_argument("--cpu-shots-per-core", type=int, default=40)
     ap.add_argument("--ref-shots-per-core", type=int, default=40)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "rtf":
+        run_gpu_rtf(args)
     else:
         run_gpu(args)
 

@@ -203,6 +203,8 @@ typedef struct {
     uint8_t reg_bits_x[3][4];       /* ... in the Hadamard frame */
     uint8_t table_entries[3][2];    /* table entries per half cycle */
     uint8_t slot_ancilla[3][2][4];  /* ancilla index measured by slot k of half h */
+    uint8_t coherent[3];            /* 1: the cycle carries coherent over-rotations and runs on the whole-cycle kernel's
+                                       coherent form (its Clifford skeleton fixed the maps above) */
 } s17_program_info;
 int s17_describe_program(const s17_layer *layers, const uint32_t n_layers[3], const double *params_cos_sin,
                          uint32_t n_params, const s17_pinstr *plan, uint32_t n_plan, s17_program_info *out);
@@ -237,6 +239,19 @@ int s17_read_rtf_slots(s17_ctx *ctx, uint32_t *out /* n x {run_id, rounds so far
  * the first to the last device operation of the call */
 int s17_last_timing(s17_ctx *ctx, double *gate_ms, double *measure_ms, double *other_ms,
                     uint64_t *gate_launches, uint64_t *all_launches, double *span_ms);
+/* the same per kernel class: ms[S17_T_N] and launches[S17_T_N], indexed by S17_T_* (the measurement layer of a
+ * full-state run is S17_T_SAMPLE + S17_T_COLLAPSE: the probability reduction itself is fused into the gate sweep that
+ * precedes the Measure) */
+enum { S17_T_COLLAPSE = 0,   /* k_collapse: ProjectQ's collapse + renormalise + reset, materialised */
+       S17_T_SAMPLE = 1,     /* k_measure: the Measure gates of one All(Measure) from the joint weights */
+       S17_T_PLAN = 2,       /* k_plan: error insertion (insert_errors / insert_error) -> per-operation events */
+       S17_T_COMPACT = 3,    /* k_compact */
+       S17_T_RECORD = 4,     /* k_record: leak override, protocol branch, lookup decode */
+       S17_T_READOUT = 5,    /* k_readout / k_readout_s: logical_measurement */
+       S17_T_PLACE = 6,      /* k_reset + k_place: generate_error_locations(_non_uniform) */
+       S17_T_N = 8 };
+int s17_last_timing_detail(s17_ctx *ctx, double *ms, uint64_t *launches,
+                           uint64_t *units /* NULL, or [S17_T_COLLAPSE] = shots whose collapse was materialised */);
 
 /* ---- engine-level face: ProjectQ's Simulator backend for a batch of state vectors -------------------------------
  *

@@ -58,6 +58,7 @@ def describe_program(prog):
         out.append({
             "cycle": name, "sweeps": int(info.n_sweeps[c]), "k_half": bool(info.half_kernel[c]),
             "k_cycle": bool(info.cycle_kernel[c]), "k_cycle1": bool(info.cycle_kernel_maps[c]),
+            "coherent": bool(info.coherent[c]),
             "shuffle_bit": int(info.shuffle_bit[c]),
             "reg_bits_z": [int(v) for v in info.reg_bits_z[c]], "reg_bits_x": [int(v) for v in info.reg_bits_x[c]],
             "table_entries": [int(v) for v in info.table_entries[c]],
@@ -108,6 +109,11 @@ class Backend:
         self._ck(self._lib.s17_load_program(self._h, layers, counts, params, len(prog.params) // 2, plan,
                                             len(plan), C.byref(lists)))
         self.program = prog
+
+    @property
+    def program_info(self):
+        """Which kernels the lowering selects for the loaded program (describe_program: the same host code path)."""
+        return describe_program(self.program)
 
     def load_tables(self, correction_table, bitflip_table):
         lut = pack_correction_table(correction_table)
@@ -204,8 +210,13 @@ class Backend:
         ng, na = C.c_uint64(), C.c_uint64()
         self._ck(self._lib.s17_last_timing(self._h, C.byref(g), C.byref(m), C.byref(o), C.byref(ng), C.byref(na),
                                            C.byref(sp)))
+        ms = (C.c_double * len(L.T_CLASSES))()
+        nl = (C.c_uint64 * len(L.T_CLASSES))()
+        un = (C.c_uint64 * len(L.T_CLASSES))()
+        self._ck(self._lib.s17_last_timing_detail(self._h, ms, nl, un))
         return {"gate_ms": g.value, "measure_ms": m.value, "other_ms": o.value, "gate_launches": ng.value,
-                "launches": na.value, "span_ms": sp.value}
+                "launches": na.value, "span_ms": sp.value,
+                "classes": {k: {"ms": ms[i], "launches": int(nl[i]), "units": int(un[i])} for i, k in enumerate(L.T_CLASSES)}}
 
     def records(self, n):
         buf = (L.Record * n)()

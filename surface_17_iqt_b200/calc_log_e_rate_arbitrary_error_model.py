@@ -323,20 +323,23 @@ def calculate_log_e_rate(num_runs, filename, correction_table, e_model, e_probs,
     sim, c = _with_batch_retry(run_once)
     if c is not None:
         rounds, syndb = sim.backend.rtf_results(my_runs)
-        my_rounds, my_syndb, my_total, my_errors = [int(v) for v in rounds], [int(v) for v in syndb], int(c.rounds), int(c.errors)
+        my_rounds, my_syndb = np.asarray(rounds, dtype=np.int64), np.asarray(syndb, dtype=np.int64)
+        my_total, my_errors = int(c.rounds), int(c.errors)
         span_ms = sim.backend.timing()["span_ms"]
     else:
-        my_rounds, my_syndb, my_total, my_errors, span_ms = [], [], 0, 0, 0.0
-    round_count_list = distributed.gather_lists(my_rounds)
-    syndrome_b_list = distributed.gather_lists(my_syndb)
+        my_rounds, my_syndb, my_total, my_errors, span_ms = np.zeros(0, np.int64), np.zeros(0, np.int64), 0, 0, 0.0
+    rounds_arr = distributed.gather_lists(my_rounds)
+    syndb_arr = distributed.gather_lists(my_syndb)
     total_rounds, errors = distributed.allreduce_counts([my_total, my_errors])
     if errors:
         raise L.S17Error("{} rounds hit a zero-probability outcome".format(errors))
     total_time_taken = time.perf_counter() - t_begin
     _log('total time taken {}'.format(total_time_taken))
-    censored = [i for i, r in enumerate(round_count_list) if r == 0]         # cut short by round_budget
+    cens = rounds_arr == 0                                                    # cut short by round_budget
     if max_rounds:
-        censored += [i for i, r in enumerate(round_count_list) if r >= max_rounds]
+        cens |= rounds_arr >= max_rounds
+    censored = np.nonzero(cens)[0].tolist()
+    round_count_list, syndrome_b_list = rounds_arr.tolist(), syndb_arr.tolist()
     results = {
         'total_time_taken_{}_runs'.format(num_runs): total_time_taken,
         'probability_set': e_probs,
@@ -347,7 +350,7 @@ def calculate_log_e_rate(num_runs, filename, correction_table, e_model, e_probs,
         'error_model': e_model,
     }
     if censored:
-        results['censored_runs'] = sorted(set(censored))
+        results['censored_runs'] = censored
     results['total_rounds'] = int(total_rounds)
     LAST_TIMING.update(rounds=int(total_rounds), span_ms=span_ms)
     if save and rank == 0:
@@ -358,9 +361,8 @@ def calculate_log_e_rate(num_runs, filename, correction_table, e_model, e_probs,
         return None
     done = dict(results)
     if censored:
-        skip = set(censored)
-        done['rounds_til_fail_list'] = [r for i, r in enumerate(round_count_list) if i not in skip]
-        done['syndrome_b_measured_list'] = [r for i, r in enumerate(syndrome_b_list) if i not in skip]
+        done['rounds_til_fail_list'] = rounds_arr[~cens].tolist()
+        done['syndrome_b_measured_list'] = syndb_arr[~cens].tolist()
     log_e_rate, _A, _vals, _bins = fit_log_e_rate(done, num_bins)
     return log_e_rate
 

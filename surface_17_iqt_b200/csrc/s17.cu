@@ -33,7 +33,7 @@
 namespace s17 {
 
 enum { C_FAILED = 0, C_NOT0 = 1, C_COUNTED = 2, C_ERRORS = 3, C_SWEEPS = 4, C_ROUNDS = 5, C_NEXT_RUN = 6, C_ALIVE = 7,
-       C_RUNS_MOVED = 8, C_RUNS_DONE = 9, C_N = 10 };
+       C_RUNS_MOVED = 8, C_RUNS_DONE = 9, C_COLLAPSED = 10, C_N = 11 };
 
 // =================================================================================================
 // gate sweep
@@ -323,8 +323,9 @@ constexpr int kPlanThreads = 128;
 constexpr int kPlanRow = 33;
 constexpr int kPlanMaxInstr = 640;
 constexpr int kPlanMaxGroups = 32;
-// group word: bits 0-9 first instruction, 10-19 one past the last, 20 gap (idle) group, 21-25 event word, 26-29 data bit,
-// 30 first operation of its half cycle, 31 half index
+// group words: [g] bits 0-9 first instruction, 10-19 one past the last; [32 + g] bit 0 gap (idle) group, 1-5 event word,
+// 6-9 data bit, 10 first operation of its half cycle, 11 half index, 12 Hadamard frame, 13 the operation closes the Ry
+// bracket of its data qubit
 __global__ void __launch_bounds__(kPlanThreads)
 k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, NoiseDev nd, const double *__restrict__ probs,
        uint32_t *__restrict__ ev, uint32_t *__restrict__ masks, uint32_t *__restrict__ leak,
@@ -336,10 +337,9 @@ k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, NoiseDev nd, const doub
 {
     __shared__ uint32_t s_mask[kPlanThreads / 32][32][kPlanRow], s_ev[kPlanThreads / 32][32][kPlanRow];
     __shared__ uint32_t s_prog[kPlanMaxInstr * 3];     // the program of this cycle (slots resolved to absolute bit indices)
-    __shared__ uint32_t s_grp[kPlanMaxGroups];
+    __shared__ uint32_t s_grp[2 * kPlanMaxGroups];     // [0..31] instruction range, [32..63] operation word (below)
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int shot = blockIdx.x * blockDim.x + threadIdx.x, shot0 = shot - lane;
-    if (shot == 0) *n_act = 0;                         // k_compact, next in the stream, appends to an empty list
+    if (blockIdx.x == 0 && threadIdx.x == 0) *n_act = 0;     // k_compact, next in the stream, appends to an empty list
     // one word per instruction for the common case (an entry that does not fire): bits 0-15 absolute slot, bit 16
     // in_skip, bit 17 entry (S17_P_ERR / S17_P_IDLE); stored behind the two program variants
     __shared__ uint32_t s_hot[kPlanMaxInstr];
@@ -347,13 +347,18 @@ k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, NoiseDev nd, const doub
         const uint32_t *src = reinterpret_cast<const uint32_t *>(prog);
         for (int i = threadIdx.x; i < pa.n_instr * 3; i += blockDim.x) s_prog[i] = src[i];
         for (int i = threadIdx.x; i < pa.n_instr; i += blockDim.x) s_hot[i] = hot[i];
-        if (threadIdx.x < kPlanMaxGroups) s_grp[threadIdx.x] = threadIdx.x < n_grp ? grp[threadIdx.x] : 0u;
+        if (threadIdx.x < 2 * kPlanMaxGroups) s_grp[threadIdx.x] = (threadIdx.x & (kPlanMaxGroups - 1)) < n_grp ? grp[threadIdx.x] : 0u;
         __syncthreads();
     }
+    const bool prob_mode = pa.noise == S17_NOISE_PROB;
+    uint32_t gap_mask = 0;
+    for (int gi = 0; gi < n_grp; ++gi) gap_mask |= (s_grp[kPlanMaxGroups + gi] & 1u) << gi;
+    // persistent over groups of kPlanThreads shots: the program is staged once per CTA (no CTA-wide barrier below)
+    for (int base = blockIdx.x * kPlanThreads; base < pa.n_shots; base += gridDim.x * kPlanThreads) {
+    const int shot = base + threadIdx.x, shot0 = shot - lane;
     const bool act = shot < pa.n_shots && active[shot];
     const uint32_t actmask = __ballot_sync(0xffffffffu, act);
-    if (!actmask) return;
-    const bool prob_mode = pa.noise == S17_NOISE_PROB;
+    if (!actmask) continue;
     for (int r = 0; r < 32; ++r)
         if ((actmask >> r) & 1u)
             s_mask[wib][r][lane] = prob_mode ? 0u : masks[(size_t)(shot0 + r) * (2 * S17_MASK_WORDS) + lane];
@@ -409,115 +414,127 @@ k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, NoiseDev nd, const doub
     }
     any_event = any_event || flagged != 0;
     const uint32_t todo = (lk != 0 || leak_event) ? 0xFFFFFFFFu : flagged;
-    uint32_t w = 0, skip = 0;
+    // ---- pass 1: the operations with a fired entry (every operation while a qubit is leaked), each lane walking ITS OWN
+    // list of groups: one instruction per trip of a single loop, so a warp spends the longest lane's walk, not the union
+    // of its lanes' groups.  Leaves the operation's event word (per-gate fields, skip bit, net Pauli) in evs[].
+    {
+        uint32_t td = todo & (n_grp >= 32 ? 0xFFFFFFFFu : ((1u << n_grp) - 1u)) & ~gap_mask;
+        int i = 0, end = 0;
+        uint32_t w = 0, skip = 0;
+        for (;;) {
+            if (i == end) {
+                if (!td) break;
+                const uint32_t gm = s_grp[__ffs(td) - 1];
+                td &= td - 1;
+                i = (int)(gm & 1023u);
+                end = (int)((gm >> 10) & 1023u);
+            }
+            const uint32_t hw = s_hot[i];
+            const int ii = i++;
+            if (hw & 0x20000u) {
+                // a fired entry acts unless it sits inside a skipped Rxx block (CS:293, 322).  The slot is the absolute index
+                // of the entry in this cycle (list offset + slot + half the list in a second cycle, CS:191-193).
+                if ((((hw >> 16) & 1u) & skip) || pa.noiseless) continue;
+                if (!mask_get(mk, hw & 0xFFFFu)) continue;
+            }
+            const s17_pinstr in = reinterpret_cast<const s17_pinstr *>(s_prog)[ii];
+            if (in.kind == S17_P_OP_BEGIN) { w = 0; skip = 0; continue; }
+            if (in.kind == S17_P_SKIP_TEST) {
+                // evaluated AFTER the errors of a preceding Ry (which may just have leaked the data qubit)
+                skip = ((lk >> in.a) | (lk >> in.b)) & 1u;
+                w |= skip << 24;
+                continue;
+            }
+            if (in.kind == S17_P_OP_END) {
+                // net Pauli at the END of the operation (bits 25-30): every event conjugated through the gates that follow
+                // it; exact because Rxx/Rx/Ry(+-pi/2) are Clifford.  The fast sweep path applies the gates branch-free
+                // and this single Pauli afterwards; the per-gate fields (bits 0-23) stay for the interpreter paths.
+                if (w & 0xFFFFFFu) {
+                    uint32_t N = 0;
+                    const int s = in.b ? 1 : -1;
+                    if (in.a & 1) N = w & 63u;                                            // after Ry(+)
+                    if (!skip) { N = pconj_rxx(N, s); N = pmul2((w >> 6) & 63u, N); }
+                    if (in.a & 2) { N = pconj_rx(N, -s); N = pmul2((w >> 12) & 63u, N); }
+                    if (in.a & 4) { N = pconj_ry(N, -1); N = pmul2((w >> 18) & 63u, N); }
+                    w |= N << 25;
+                }
+                evs[in.word] = w;
+                continue;
+            }
+            uint32_t f = (w >> in.field) & 63u;
+            switch (in.err) {
+            case S17_ERR_X: f = pauli_mul(f, 0, 1); break;
+            case S17_ERR_Y: f = pauli_mul(f, 0, 2); break;
+            case S17_ERR_Z: f = pauli_mul(f, 0, 3); break;
+            case S17_ERR_ZC: f = pauli_mul(f, 0, 3); break;
+            case S17_ERR_ZT: f = pauli_mul(f, 1, 3); break;
+            case S17_ERR_XX: f = pauli_mul(pauli_mul(f, 0, 1), 1, 1); break;
+            case S17_ERR_ZZ: f = pauli_mul(pauli_mul(f, 0, 3), 1, 3); break;
+            case S17_ERR_LEAK_A: lk |= 1u << in.a; break;
+            case S17_ERR_LEAK_AB: lk |= (1u << in.a) | (1u << in.b); break;
+            case S17_ERR_DEPOL: {
+                // insert_2q_error (CS:237-283): 15 equiprobable non-identity pairs, first letter -> qubits[0]
+                int k = (int)(rng.next() * 15.0);
+                if (k > 14) k = 14;
+                const int code = k + 1, p0 = code >> 2, p1 = code & 3;   // IX,IY,IZ,XI,...,ZZ
+                if (p0) f = pauli_mul(f, 0, p0);
+                if (p1) f = pauli_mul(f, 1, p1);
+            } break;
+            default: break;
+            }
+            w = (w & ~(63u << in.field)) | (f << in.field);
+        }
+    }
+    // ---- pass 2: every group in program order (warp-uniform trip count): the net Pauli of each operation in the frame
+    // where its half cycle is diagonal (s17_diag.cuh) -- a data X relabels the basis (flip mask; bit 31 tells the
+    // operation whether its own label bit is flipped), a data Z is a label-dependent sign (sign mask), the rest is a
+    // global phase -- and the idle entries of the gaps (sympathetic_cooling, CS:762-772).
     for (int gi = 0; gi < n_grp; ++gi) {
-    const uint32_t gm = s_grp[gi];
-    if (!((todo >> gi) & 1u)) {
-        // no entry of this group fires and no qubit is leaked: the default of an operation is its data-flip bit
-        if (!((gm >> 20) & 1u)) {
-            if ((gm >> 30) & 1u) {
-                if (f_half >= 0)
-                    frm[(size_t)shot * 4 + f_half] = f_flip | (f_sign << 9) | ((f_phase & 3u) << 18) | (f_ancz << 20);
-                f_flip = 0; f_sign = 0; f_phase = 0; f_ancz = 0;
-                f_half = (int)(gm >> 31);
-            }
-            evs[(gm >> 21) & 31u] = ((f_flip >> ((gm >> 26) & 15u)) & 1u) << 31;
-        }
-        continue;
-    }
-    for (int i = (int)(gm & 1023u); i < (int)((gm >> 10) & 1023u); ++i) {
-        const uint32_t hw = s_hot[i];
-        if (hw & 0x20000u) {
-            // a fired entry acts unless it sits inside a skipped Rxx block (CS:293, 322).  The slot is the absolute index
-            // of the entry in this cycle (list offset + slot + half the list in a second cycle, CS:191-193).
-            if ((((hw >> 16) & 1u) & skip) || pa.noiseless) continue;
-            if (!mask_get(mk, hw & 0xFFFFu)) continue;
-        }
-        const s17_pinstr in = reinterpret_cast<const s17_pinstr *>(s_prog)[i];
-        if (in.kind == S17_P_OP_BEGIN) { w = 0; skip = 0; continue; }
-        if (in.kind == S17_P_SKIP_TEST) {
-            // evaluated AFTER the errors of a preceding Ry (which may just have leaked the data qubit)
-            skip = ((lk >> in.a) | (lk >> in.b)) & 1u;
-            w |= skip << 24;
-            continue;
-        }
-        if (in.kind == S17_P_OP_END) {
-            // net Pauli at the END of the operation (bits 25-30): every event conjugated through the gates that follow
-            // it; exact because Rxx/Rx/Ry(+-pi/2) are Clifford.  The fast sweep path applies the gates branch-free
-            // and this single Pauli afterwards; the per-gate fields (bits 0-23) stay for the interpreter paths.
-            uint32_t N = 0;
-            if (w & 0xFFFFFFu) {
-                const int s = in.b ? 1 : -1;
-                if (in.a & 1) N = w & 63u;                                            // after Ry(+)
-                if (!skip) { N = pconj_rxx(N, s); N = pmul2((w >> 6) & 63u, N); }
-                if (in.a & 2) { N = pconj_rx(N, -s); N = pmul2((w >> 12) & 63u, N); }
-                if (in.a & 4) { N = pconj_ry(N, -1); N = pmul2((w >> 18) & 63u, N); }
-                w |= N << 25;
-            }
-            // The same Pauli in the frame where the half cycle is diagonal (s17_diag.cuh; a: bit3 Hadamard frame,
-            // bit4 first / bit6 last operation of its half, bit5 half index; slot = data bit): a data X relabels
-            // the basis (flip mask; bit 31 tells the operation whether its own label bit is flipped), a data Z is a
-            // label-dependent sign (sign mask) and the rest is a global phase.
-            const uint32_t d = in.slot;
-            if (in.a & 16) {                           // first operation of a half: close the previous one (idle events may
-                if (f_half >= 0)                       // follow its last operation), start from the identity frame
-                    frm[(size_t)shot * 4 + f_half] = f_flip | (f_sign << 9) | ((f_phase & 3u) << 18) | (f_ancz << 20);
-                f_flip = 0; f_sign = 0; f_phase = 0; f_ancz = 0;
-                f_half = (int)((in.a >> 5) & 1u);
-            }
-            w |= ((f_flip >> d) & 1u) << 31;
-            if (N) {
-                uint32_t F = N;
-                if (in.a & 8) {                        // H X^x Z^z H = (-1)^{xz} X^z Z^x
-                    const uint32_t x = N & 1u, z = (N >> 1) & 1u, k = (N >> 4) & 3u;
-                    F = (N & 0x0Cu) | z | (x << 1) | (((k + 2u * (x & z)) & 3u) << 4);
-                } else if (!(in.a & 4)) {              // still inside the Ry bracket of its data qubit
-                    F = pconj_ry(N, -1);
-                }
-                if (F & 2u) { f_sign ^= 1u << d; f_phase += 2u * ((f_flip >> d) & 1u); }
-                if (F & 1u) f_flip ^= 1u << d;
-                f_phase += (F >> 4) & 3u;
-            }
-            evs[in.word] = w;
-            continue;
-        }
-        if (in.kind == S17_P_IDLE) {
-            evs[in.word] |= 1u << in.a;                // the 17-bit idle masks of the sweep kernels / k_half
-            if (in.b & 0x80u) {                        // the same Z in the frame of its half cycle (whole-cycle kernels)
-                if (in.a < 9u) {
-                    const uint32_t bit = 1u << in.a;
-                    if (in.b & 2u) f_flip ^= bit;                                   // H Z H = X
-                    else if (in.b & 1u) { f_flip ^= bit; f_phase += 2u; }           // Ry(-pi/2) Z Ry(+pi/2) = -X
-                    else { f_sign ^= bit; f_phase += 2u * ((f_flip >> in.a) & 1u); }
-                } else if (in.field != 255u) {
-                    f_ancz ^= 1u << in.field;          // Z on the ancilla after that operation (and its own events)
+        const uint32_t gm = s_grp[gi], g2 = s_grp[kPlanMaxGroups + gi];
+        const bool walked = (todo >> gi) & 1u;
+        if (g2 & 1u) {                                 // gap between two timesteps: its fired idle entries
+            if (!walked || pa.noiseless) continue;
+            for (int i = (int)(gm & 1023u); i < (int)((gm >> 10) & 1023u); ++i) {
+                const uint32_t hw = s_hot[i];
+                if (!mask_get(mk, hw & 0xFFFFu)) continue;
+                const s17_pinstr in = reinterpret_cast<const s17_pinstr *>(s_prog)[i];
+                evs[in.word] |= 1u << in.a;            // the 17-bit idle masks of the sweep kernels / k_half
+                if (in.b & 0x80u) {                    // the same Z in the frame of its half cycle (whole-cycle kernels)
+                    if (in.a < 9u) {
+                        const uint32_t bit = 1u << in.a;
+                        if (in.b & 2u) f_flip ^= bit;                                   // H Z H = X
+                        else if (in.b & 1u) { f_flip ^= bit; f_phase += 2u; }           // Ry(-pi/2) Z Ry(+pi/2) = -X
+                        else { f_sign ^= bit; f_phase += 2u * ((f_flip >> in.a) & 1u); }
+                    } else if (in.field != 255u) {
+                        f_ancz ^= 1u << in.field;      // Z on the ancilla after that operation (and its own events)
+                    }
                 }
             }
             continue;
         }
-        uint32_t f = (w >> in.field) & 63u;
-        switch (in.err) {
-        case S17_ERR_X: f = pauli_mul(f, 0, 1); break;
-        case S17_ERR_Y: f = pauli_mul(f, 0, 2); break;
-        case S17_ERR_Z: f = pauli_mul(f, 0, 3); break;
-        case S17_ERR_ZC: f = pauli_mul(f, 0, 3); break;
-        case S17_ERR_ZT: f = pauli_mul(f, 1, 3); break;
-        case S17_ERR_XX: f = pauli_mul(pauli_mul(f, 0, 1), 1, 1); break;
-        case S17_ERR_ZZ: f = pauli_mul(pauli_mul(f, 0, 3), 1, 3); break;
-        case S17_ERR_LEAK_A: lk |= 1u << in.a; break;
-        case S17_ERR_LEAK_AB: lk |= (1u << in.a) | (1u << in.b); break;
-        case S17_ERR_DEPOL: {
-            // insert_2q_error (CS:237-283): 15 equiprobable non-identity pairs, first letter -> qubits[0]
-            int k = (int)(rng.next() * 15.0);
-            if (k > 14) k = 14;
-            const int code = k + 1, p0 = code >> 2, p1 = code & 3;   // IX,IY,IZ,XI,...,ZZ
-            if (p0) f = pauli_mul(f, 0, p0);
-            if (p1) f = pauli_mul(f, 1, p1);
-        } break;
-        default: break;
+        const uint32_t word = (g2 >> 1) & 31u, d = (g2 >> 6) & 15u;
+        uint32_t w = walked ? evs[word] : 0u;
+        if ((g2 >> 10) & 1u) {                         // first operation of a half: close the previous one (idle events may
+            if (f_half >= 0)                           // follow its last operation), start from the identity frame
+                frm[(size_t)shot * 4 + f_half] = f_flip | (f_sign << 9) | ((f_phase & 3u) << 18) | (f_ancz << 20);
+            f_flip = 0; f_sign = 0; f_phase = 0; f_ancz = 0;
+            f_half = (int)((g2 >> 11) & 1u);
         }
-        w = (w & ~(63u << in.field)) | (f << in.field);
-    }
+        w |= ((f_flip >> d) & 1u) << 31;
+        const uint32_t N = (w >> 25) & 63u;
+        if (N) {
+            uint32_t F = N;
+            if ((g2 >> 12) & 1u) {                     // H X^x Z^z H = (-1)^{xz} X^z Z^x
+                const uint32_t x = N & 1u, z = (N >> 1) & 1u, k = (N >> 4) & 3u;
+                F = (N & 0x0Cu) | z | (x << 1) | (((k + 2u * (x & z)) & 3u) << 4);
+            } else if (!((g2 >> 13) & 1u)) {           // still inside the Ry bracket of its data qubit
+                F = pconj_ry(N, -1);
+            }
+            if (F & 2u) { f_sign ^= 1u << d; f_phase += 2u * ((f_flip >> d) & 1u); }
+            if (F & 1u) f_flip ^= 1u << d;
+            f_phase += (F >> 4) & 3u;
+        }
+        evs[word] = w;
     }
     if (f_half >= 0) frm[(size_t)shot * 4 + f_half] = f_flip | (f_sign << 9) | ((f_phase & 3u) << 18) | (f_ancz << 20);
     leak[shot] = lk;
@@ -529,6 +546,8 @@ k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, NoiseDev nd, const doub
         ev[(size_t)(shot0 + r) * S17_EV_WORDS + lane] = s_ev[wib][r][lane];
         if (prob_mode)
             masks[(size_t)(shot0 + r) * (2 * S17_MASK_WORDS) + (pa.rec_half ? S17_MASK_WORDS : 0) + lane] = s_mask[wib][r][lane];
+    }
+    __syncwarp();                                      // the staging rows are reused by the next group
     }
 }
 
@@ -680,7 +699,8 @@ namespace s17 {
 // ProjectQ collapse + renormalise for the 8 measured ancillas, fused with the reset X gates (CS:859-862):
 // the surviving 512-amplitude block moves to ancilla value 0, everything else becomes zero.
 __global__ void __launch_bounds__(256)
-k_collapse(double2 *__restrict__ state, ShotAux *__restrict__ aux, const uint8_t *__restrict__ flag)
+k_collapse(double2 *__restrict__ state, ShotAux *__restrict__ aux, const uint8_t *__restrict__ flag,
+           unsigned long long *__restrict__ counters)
 {
     const int shot = blockIdx.x / 32, part = blockIdx.x % 32, t = threadIdx.x;
     if (!flag[shot]) return;
@@ -706,7 +726,7 @@ k_collapse(double2 *__restrict__ state, ShotAux *__restrict__ aux, const uint8_t
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < 2; ++i) s[t + 256 * i] = keep[i];
-        if (t == 0) aux[shot].collapsed = 1;
+        if (t == 0) { aux[shot].collapsed = 1; atomicAdd(&counters[C_COLLAPSED], 1ull); }
     }
 }
 
@@ -1058,7 +1078,7 @@ k_rtf_assign(int n_slots, uint32_t total_runs, uint32_t chain, RtfSlot *slots, u
 // =================================================================================================
 using namespace s17;
 
-struct TimedLaunch { int cat; cudaEvent_t e0, e1; };
+struct TimedLaunch { int cat, sub; cudaEvent_t e0, e1; };
 
 struct s17_ctx {
     int device = 0;
@@ -1106,6 +1126,9 @@ struct s17_ctx {
     bool diag_ok[3] = {false, false, false};
     DiagProg1 diag_prog1[3];          // the same with host-chosen label maps (k_cycle1), when such maps exist
     bool diag1_ok[3] = {false, false, false};
+    DiagCoh diag_coh[3];              // coherent over-rotations of a cycle that runs on k_cycle1<true>
+    bool coh_ok[3] = {false, false, false};
+    bool no_coh = false;              // S17_COH=0: coherent models keep the sweep kernels
     bool no_diag1 = false;
     bool no_diag = false;
     bool last_collapsed = true;       // the previous cycle left every active shot collapsed to ancilla block 0
@@ -1142,6 +1165,8 @@ struct s17_ctx {
     size_t ev_used = 0;
     std::vector<TimedLaunch> launches;
     double t_gate = 0, t_meas = 0, t_other = 0, t_span = 0;
+    double t_sub[S17_T_N] = {};       // per kernel class (S17_T_*)
+    uint64_t n_sub[S17_T_N] = {}, u_sub[S17_T_N] = {};
     uint64_t n_gate = 0, n_all = 0;
     cudaEvent_t span0 = nullptr, span1 = nullptr;
     std::string err;
@@ -1172,8 +1197,8 @@ static cudaEvent_t get_event(s17_ctx *c) {
 enum { CAT_GATE = 0, CAT_MEAS = 1, CAT_OTHER = 2 };
 struct Scope {
     s17_ctx *c; TimedLaunch tl; int line;
-    Scope(s17_ctx *c_, int cat, int line_ = 0) : c(c_), line(line_) {
-        tl.cat = cat; tl.e0 = get_event(c); tl.e1 = get_event(c); cudaEventRecord(tl.e0, c->stream);
+    Scope(s17_ctx *c_, int cat, int line_ = 0, int sub = -1) : c(c_), line(line_) {
+        tl.cat = cat; tl.sub = sub; tl.e0 = get_event(c); tl.e1 = get_event(c); cudaEventRecord(tl.e0, c->stream);
     }
     ~Scope() {
         cudaEventRecord(tl.e1, c->stream);
@@ -1187,6 +1212,7 @@ struct Scope {
     }
 };
 #define SCOPE(cat) Scope s(ctx, cat, __LINE__)
+#define SCOPE2(cat, sub) Scope s(ctx, cat, __LINE__, sub)
 
 extern "C" int s17_device_count(void) {
     int n = 0;
@@ -1262,7 +1288,8 @@ extern "C" int s17_create(s17_ctx **out, int device, uint64_t max_shots) {
     CK(cudaMalloc(&ctx->quiet_flag, B));
     CK(cudaMemset(ctx->frm, 0, B * 4 * 4));
     CK(cudaFuncSetAttribute(k_cycle, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDgSmem));
-    CK(cudaFuncSetAttribute(k_cycle1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDgSmem1));
+    CK(cudaFuncSetAttribute(k_cycle1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDgSmem1));
+    CK(cudaFuncSetAttribute(k_cycle1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDgSmem1));
     {
         typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -1780,11 +1807,103 @@ static bool make_diag1(const DiagProg &G, DiagProg1 &P1) {
     return false;
 }
 
+// ---- coherent over-rotations on the whole-cycle kernel ------------------------------------------------------------------
+// With the over-rotation micro-ops taken out a coherent cycle is the Clifford cycle; its diagonal-frame form and label
+// maps carry over (the rotations are functions of the same X_d X_a / X_d, or real rotations of one data qubit around its
+// Ry bracket: DiagCoh in s17_diag.cuh).  What does not carry over is k_plan's Clifford conjugation of a Pauli event to
+// the end of its operation and into the frame: it stays exact only for events that are a sign of the basis label or an
+// ancilla Pauli where they act, or that come after the last gate of the data qubit in this cycle.
+static bool coherent_events_ok(const s17_pinstr *plan, uint32_t n_plan) {
+    for (uint32_t i = 0; i < n_plan; ++i) {
+        const s17_pinstr &in = plan[i];
+        if (in.kind == S17_P_IDLE) return false;             // an idle Z on a data qubit is a flip in the Hadamard frame
+        if (in.kind != S17_P_ERR) continue;
+        if (in.err == S17_ERR_LEAK_A || in.err == S17_ERR_LEAK_AB) continue;      // classical flags
+        const bool after_bracket = in.field == 18;           // after Ry(-pi/2) and its over-rotation
+        const bool sign_like = in.err == S17_ERR_X || in.err == S17_ERR_XX || in.err == S17_ERR_ZT;
+        const bool data_pauli = in.err == S17_ERR_X || in.err == S17_ERR_Y || in.err == S17_ERR_Z || in.err == S17_ERR_ZC;
+        if (!(sign_like || (after_bracket && data_pauli))) return false;
+    }
+    return true;
+}
+
+// strip the rotation micro-ops of every operation (the event field of a group moves to the gate the rotation followed)
+static bool strip_rotations(const std::vector<LayerArg> &in, std::vector<LayerArg> &out) {
+    bool any = false;
+    out = in;
+    for (LayerArg &A : out)
+        for (int o = 0; o < A.L.n_ops; ++o) {
+            s17_op &op = A.L.ops[o];
+            if (op.kind != S17_OP_ENT) continue;
+            int n = 0;
+            for (int u = 0; u < op.n_uops; ++u) {
+                if (op.uops[u].type >= S17_U_ROT_X) {
+                    any = true;
+                    if (n == 0) return false;
+                    if (op.uops[u].ev_shift != 255) op.uops[n - 1].ev_shift = op.uops[u].ev_shift;
+                    continue;
+                }
+                op.uops[n++] = op.uops[u];
+            }
+            op.n_uops = (uint8_t)n;
+        }
+    return any;
+}
+
+// the rotation angles of the operations of `layers`, laid out for the slots / maps of P1
+static bool fill_coherent(const std::vector<LayerArg> &layers, const DiagProg1 &P1, DiagCoh &C) {
+    double2 pre[9], post[9];
+    for (int d = 0; d < 9; ++d) { pre[d] = make_double2(1.0, 0.0); post[d] = make_double2(1.0, 0.0); }
+    for (int h = 0; h < 2; ++h)
+        for (int k = 0; k < 4; ++k)
+            for (int j = 0; j < 4; ++j) { C.rxx[h][k][j] = make_double2(1.0, 1.0); C.rx[h][k][j] = make_double2(1.0, 0.0); }
+    for (int h = 0; h < 2; ++h)
+        for (int k = 0; k < 4; ++k)
+            for (int j = 0; j < P1.h[h].n_ops[k]; ++j) {
+                const DiagOp &dop = P1.h[h].ops[k][j];
+                const s17_op *op = nullptr;
+                const LayerArg *lay = nullptr;
+                for (const LayerArg &A : layers)
+                    for (int o = 0; o < A.L.n_ops; ++o)
+                        if (A.L.ops[o].kind == S17_OP_ENT && A.L.ops[o].ev_word == dop.ev_word) { op = &A.L.ops[o]; lay = &A; }
+                if (!op) return false;
+                const double s = (dop.flags & 1u) ? -1.0 : 1.0;            // sign of the Rxx angle
+                double2 exx = make_double2(1.0, 0.0), ex = make_double2(1.0, 0.0);
+                int last = -1;                                             // 0 Ry(+), 1 Rxx, 2 Rx, 3 Ry(-)
+                for (int u = 0; u < op->n_uops; ++u) {
+                    const s17_uop &up = op->uops[u];
+                    if (up.type == S17_U_RY) last = up.sign > 0 ? 0 : 3;
+                    else if (up.type == S17_U_RXX) last = 1;
+                    else if (up.type == S17_U_RX) last = 2;
+                    else if (up.type == S17_U_ROT_Y && (last == 0 || last == 3)) (last == 0 ? pre : post)[dop.d] = lay->prm[up.param];
+                    else if (up.type == S17_U_ROT_XX && last == 1) exx = lay->prm[up.param];
+                    else if (up.type == S17_U_ROT_X && last == 2) ex = lay->prm[up.param];
+                    else return false;
+                }
+                // sqrt2 (cos, sin) of the half angle of Rxx(s pi/2 + eps) and of Rx(-s pi/2 + eps)
+                C.rxx[h][k][j] = make_double2(exx.x - s * exx.y, s * exx.x + exx.y);
+                if (dop.flags & 2u) C.rx[h][k][j] = make_double2(ex.x + s * ex.y, -s * ex.x + ex.y);
+            }
+    auto ab = [&](int d) { return make_double2(pre[d].x - pre[d].y, pre[d].x + pre[d].y); };     // Ry(eps) H = [[a, b], [b, -a]]
+    for (int j = 0; j < 4; ++j) {
+        C.preB[j] = ab(P1.mapB.reg[j]);
+        C.preA[j] = ab(P1.mapA.reg[j]);
+        C.postR[j] = post[P1.mapA.reg[j]];
+    }
+    C.preSh = ab(P1.mapA.lane[P1.sh_lane_bit]);
+    for (int m = 0; m < 5; ++m) C.postL[m] = post[P1.mapA.lane[m]];
+    return true;
+}
+
 // Host-only lowering of the compiled cycle: per-sweep constants, the fused half-cycle form, the diagonal-frame form and
 // its label maps.  No CUDA call: s17_describe_program runs it without a device.
 static int lower_program(s17_ctx *ctx, const s17_layer *layers, const uint32_t n_layers[3], const double *params,
                          uint32_t n_params, const s17_pinstr *plan, uint32_t n_plan) {
     const s17_layer *src = layers;
+    {
+        const char *co = getenv("S17_COH");               // 0: coherent models keep the sweep kernels
+        ctx->no_coh = co && co[0] == '0';
+    }
     for (int c = 0; c < 3; ++c) {
         ctx->layers[c].clear();
         for (uint32_t i = 0; i < n_layers[c]; ++i, ++src) {
@@ -1844,6 +1963,24 @@ static int lower_program(s17_ctx *ctx, const s17_layer *layers, const uint32_t n
                               (cov0 & ~cov1) == 0;
             if (ctx->diag_ok[c]) { ctx->diag_prog[c].h[0].final_part = 0; ctx->diag_prog[c].h[1].final_part = 1; }
             ctx->diag1_ok[c] = ctx->diag_ok[c] && make_diag1(ctx->diag_prog[c], ctx->diag_prog1[c]);
+            // a cycle with coherent over-rotations: lower its Clifford skeleton, then attach the angles
+            ctx->coh_ok[c] = false;
+            std::vector<LayerArg> skel;
+            if (!ctx->diag1_ok[c] && !ctx->no_coh && cuts.size() == 2 && strip_rotations(ctx->layers[c], skel) &&
+                coherent_events_ok(plan, n_plan)) {
+                LayerArg2 hp[2];
+                HalfTail ht[2];
+                DiagProg G;
+                uint32_t c0 = 0, c1 = 0;
+                if (make_half(skel, 0, cuts[0], hp[0], ht[0]) && make_half(skel, cuts[0], cuts[1], hp[1], ht[1]) &&
+                    make_diag_half(hp[0], ht[0], 0, plan, n_plan, G.h[0], &c0) && make_diag_half(hp[1], ht[1], 1, plan, n_plan, G.h[1], &c1) &&
+                    G.h[0].frame_x == 1 && G.h[1].frame_x == 0 && (c0 & ~c1) == 0) {
+                    G.h[0].final_part = 0;
+                    G.h[1].final_part = 1;
+                    if (make_diag1(G, ctx->diag_prog1[c]) && fill_coherent(ctx->layers[c], ctx->diag_prog1[c], ctx->diag_coh[c]))
+                        ctx->coh_ok[c] = ctx->diag1_ok[c] = true;
+                }
+            }
         }
     }
     return S17_OK;
@@ -1901,7 +2038,7 @@ extern "C" int s17_load_program(s17_ctx *ctx, const s17_layer *layers, const uin
         CK(cudaMalloc(&ctx->plan_hot, hot.size() * 4));
         CK(cudaMemcpy(ctx->plan_hot, hot.data(), hot.size() * 4, cudaMemcpyHostToDevice));
         // groups of the program (one entangling operation / the idle entries of one gap), in program order
-        std::vector<uint32_t> grp(2 * kPlanMaxGroups, 0u);
+        std::vector<uint32_t> grp(4 * kPlanMaxGroups, 0u);     // per variant: 32 instruction ranges, 32 operation words
         std::vector<uint8_t> b2g(2 * 2048, 0xFFu);
         ctx->plan_dup_slot = false;
         for (int c2 = 0; c2 < 2; ++c2) {
@@ -1915,7 +2052,7 @@ extern "C" int s17_load_program(s17_ctx *ctx, const s17_layer *layers, const uin
                     if (j == n_plan) return fail(ctx, S17_E_ARG, "plan: operation without an end");
                     const s17_pinstr &e = q[j];
                     meta = ((uint32_t)e.word << 1) | ((uint32_t)(plan[j].slot & 15u) << 6) | (((e.a >> 4) & 1u) << 10) |
-                           (((e.a >> 5) & 1u) << 11);
+                           (((e.a >> 5) & 1u) << 11) | (((e.a >> 3) & 1u) << 12) | (((e.a >> 2) & 1u) << 13);
                     ++j;
                 } else if (q[i].kind == S17_P_IDLE) {
                     while (j < n_plan && q[j].kind == S17_P_IDLE && q[j].word == q[i].word) ++j;
@@ -1924,7 +2061,8 @@ extern "C" int s17_load_program(s17_ctx *ctx, const s17_layer *layers, const uin
                     return fail(ctx, S17_E_ARG, "plan: entry outside an operation");
                 }
                 if (ng >= kPlanMaxGroups) return fail(ctx, S17_E_ARG, "plan: too many groups");
-                grp[(size_t)c2 * kPlanMaxGroups + ng] = i | (j << 10) | (meta << 20);
+                grp[(size_t)c2 * 2 * kPlanMaxGroups + ng] = i | (j << 10);
+                grp[(size_t)(c2 * 2 + 1) * kPlanMaxGroups + ng] = meta;
                 for (uint32_t k = i; k < j; ++k)
                     if (q[k].kind == S17_P_ERR || q[k].kind == S17_P_IDLE) {
                         uint8_t &slot = b2g[(size_t)c2 * 2048 + q[k].slot];
@@ -1977,6 +2115,7 @@ extern "C" int s17_describe_program(const s17_layer *layers, const uint32_t n_la
         out->half_kernel[c] = ctx->half_ok[c] ? 1 : 0;
         out->cycle_kernel[c] = ctx->diag_ok[c] ? 1 : 0;
         out->cycle_kernel_maps[c] = ctx->diag1_ok[c] ? 1 : 0;
+        out->coherent[c] = ctx->coh_ok[c] ? 1 : 0;
         if (!ctx->diag1_ok[c]) continue;
         const DiagProg1 &P = ctx->diag_prog1[c];
         for (int j = 0; j < 4; ++j) { out->reg_bits_z[c][j] = P.mapA.reg[j]; out->reg_bits_x[c][j] = P.mapB.reg[j]; }
@@ -2119,6 +2258,21 @@ static int ensure_state(s17_ctx *ctx, bool need_full) {
     return S17_OK;
 }
 
+// the whole-cycle kernel of cycle kind `which` (0 preparation, 1 stab_ind=0, 2 stab_ind=1): Clifford or coherent form
+static void launch_cycle1(s17_ctx *ctx, int which, const MeasArgs &ma, double2 *state, size_t stride, const uint32_t *ev,
+                          const uint32_t *frm, const uint32_t *list, const uint32_t *n_act, ShotAux *aux, const uint8_t *forced,
+                          uint32_t *meas_out, uint32_t *dsamp, unsigned long long *counters, int init_basis,
+                          const double2 *alt_src, double *pp_out, double *cdf_out) {
+    if (ctx->coh_ok[which])
+        k_cycle1<true><<<ctx->num_sms, kDgThreads, kDgSmem1, ctx->stream>>>(ctx->diag_prog1[which], ctx->diag_coh[which], ma, state,
+                                                                           stride, ev, frm, list, n_act, aux, forced, meas_out,
+                                                                           dsamp, counters, init_basis, alt_src, pp_out, cdf_out);
+    else
+        k_cycle1<false><<<ctx->num_sms, kDgThreads, kDgSmem1, ctx->stream>>>(ctx->diag_prog1[which], ctx->diag_coh[which], ma, state,
+                                                                            stride, ev, frm, list, n_act, aux, forced, meas_out,
+                                                                            dsamp, counters, init_basis, alt_src, pp_out, cdf_out);
+}
+
 // Build the memoised preparation cycle for `basis`: run the production kernel once per outcome pattern (256 forced shots
 // on private buffers), keep the collapsed blocks and the probability pair of every Measure along the way.
 static int build_prep_cache(s17_ctx *ctx, int basis) {
@@ -2166,8 +2320,7 @@ static int build_prep_cache(s17_ctx *ctx, int basis) {
     ma.final_part = 1;
     ma.stream = 16u;
     ma.n_shots = N;
-    k_cycle1<<<ctx->num_sms, kDgThreads, kDgSmem1, ctx->stream>>>(P, ma, ctx->prep_blocks, (size_t)kRun, ev, frm, list, nact, aux,
-                                                                 forced, mo, ds, cnt, basis, nullptr, pp, nullptr);
+    launch_cycle1(ctx, 0, ma, ctx->prep_blocks, (size_t)kRun, ev, frm, list, nact, aux, forced, mo, ds, cnt, basis, nullptr, pp, nullptr);
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());
     std::vector<double> h_pp((size_t)N * 16);
@@ -2203,9 +2356,8 @@ static int build_prep_cache(s17_ctx *ctx, int basis) {
         ma.stream = 16u + 4u;
         ma.sample_data = 1;
         ma.data_stream = 32u;
-        k_cycle1<<<ctx->num_sms, kDgThreads, kDgSmem1, ctx->stream>>>(ctx->diag_prog1[1], ma, ctx->quiet_blocks, (size_t)kRun, ev,
-                                                                     frm, list, nact, aux, forced, mo, ds, cnt, -1,
-                                                                     ctx->prep_blocks, pp, cdf);
+        launch_cycle1(ctx, 1, ma, ctx->quiet_blocks, (size_t)kRun, ev, frm, list, nact, aux, forced, mo, ds, cnt, -1,
+                      ctx->prep_blocks, pp, cdf);
         CK(cudaStreamSynchronize(ctx->stream));
         CK(cudaGetLastError());
         CK(cudaMemcpy(h_pp.data(), pp, h_pp.size() * sizeof(double), cudaMemcpyDeviceToHost));
@@ -2255,7 +2407,7 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
                                                                 ctx->prep_mixed ? ctx->leak : nullptr, ctx->prep_done);
         }
         if (!ctx->prep_mixed) {
-            SCOPE(CAT_MEAS);
+            SCOPE2(CAT_MEAS, S17_T_RECORD);
             k_record<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(ma, ctx->meas_out, ctx->lut, ctx->leak, ctx->active,
                                                                   ctx->ready, ctx->rec, ctx->counters);
             ctx->last_collapsed = true;
@@ -2274,12 +2426,12 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
     pa.first_shot = a.first_shot_id;
     pa.n_shots = n;
     {
-        SCOPE(CAT_OTHER);
-        k_plan<<<blocks_for(n, kPlanThreads), kPlanThreads, 0, ctx->stream>>>(ctx->plan + (second ? ctx->n_plan : 0), pa, ctx->nd, ctx->probs, ctx->ev, ctx->masks,
+        SCOPE2(CAT_OTHER, S17_T_PLAN);
+        k_plan<<<std::min(blocks_for(n, kPlanThreads), ctx->num_sms * 5), kPlanThreads, 0, ctx->stream>>>(ctx->plan + (second ? ctx->n_plan : 0), pa, ctx->nd, ctx->probs, ctx->ev, ctx->masks,
                                                             ctx->leak, ctx->active, ctx->frm, ctx->n_act,
                                                                           ctx->plan_hot + (second ? ctx->n_plan : 0),
                                                                           (ctx->use_quiet && stage == 1) ? ctx->quiet_flag : nullptr,
-                                                                          ctx->plan_grp + (second ? kPlanMaxGroups : 0), ctx->n_grp[second ? 1 : 0],
+                                                                          ctx->plan_grp + (second ? 2 * kPlanMaxGroups : 0), ctx->n_grp[second ? 1 : 0],
                                                                           ctx->plan_bit2grp + (second ? 2048 : 0),
                                                                           (a.noise == S17_NOISE_PROB && ctx->geo_ok[second ? 1 : 0])
                                                                               ? ctx->plan_surv + (second ? kPlanMaxInstr + 1 : 0) : nullptr);
@@ -2290,7 +2442,7 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
     uint32_t nl = (uint32_t)Ls.size();
     if (max_layers && max_layers < nl) nl = max_layers;
     {
-        SCOPE(CAT_OTHER);
+        SCOPE2(CAT_OTHER, S17_T_COMPACT);
         k_compact<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(ctx->active, n, ctx->act_list, ctx->n_act,
                                                                (ctx->use_prep && stage == 1) ? ctx->prep_leaf : nullptr,
                                                                (ctx->use_quiet && stage == 1) ? ctx->quiet_flag : nullptr,
@@ -2306,7 +2458,7 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
     ma.first_shot = a.first_shot_id;
     ma.n_shots = n;
     const bool fused_ok = !dense && !mid_collapse && !max_layers && !ctx->use_v1 && !ctx->force_ring && !ctx->no_fuse;
-    if (ctx->diag_ok[which] && fused_ok && !ctx->no_diag) {
+    if ((ctx->diag_ok[which] || (ctx->coh_ok[which] && !ctx->no_diag1)) && fused_ok && !ctx->no_diag) {
         if (init_basis < 0 && !ctx->last_collapsed) collapse(ctx, n, ctx->active);     // k_cycle reads the block at ancilla value 0
         ctx->last_collapsed = true;
         // production path for Clifford cycles with Pauli / leakage noise: the whole cycle in the frame where it is
@@ -2322,10 +2474,9 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
         {
             SCOPE(CAT_GATE);
             if (ctx->diag1_ok[which] && !ctx->no_diag1)
-                k_cycle1<<<ctx->num_sms, kDgThreads, kDgSmem1, ctx->stream>>>(
-                    ctx->diag_prog1[which], ma, ctx->state, ctx->stride, ctx->ev, ctx->frm, ctx->act_list, ctx->n_act, ctx->aux,
-                    ctx->forced, ctx->meas_out, ctx->dsamp, ctx->counters, init_basis,
-                    (ctx->use_prep && stage == 1) ? ctx->prep_blocks : nullptr, nullptr, nullptr);
+                launch_cycle1(ctx, which, ma, ctx->state, ctx->stride, ctx->ev, ctx->frm, ctx->act_list, ctx->n_act, ctx->aux,
+                              ctx->forced, ctx->meas_out, ctx->dsamp, ctx->counters, init_basis,
+                              (ctx->use_prep && stage == 1) ? ctx->prep_blocks : nullptr, nullptr, nullptr);
             else
                 k_cycle<<<ctx->num_sms, kDgThreads, kDgSmem, ctx->stream>>>(
                     ctx->diag_prog[which], ma, ctx->state, ctx->stride, ctx->ev, ctx->frm, ctx->act_list, ctx->n_act, ctx->aux,
@@ -2342,7 +2493,7 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
                 (ctx->quiet_copy || a.forced) ? 1 : 0);
         }
         {
-            SCOPE(CAT_MEAS);
+            SCOPE2(CAT_MEAS, S17_T_RECORD);
             k_record<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(ma, ctx->meas_out, ctx->lut, ctx->leak, ctx->active,
                                                                   ctx->ready, ctx->rec, ctx->counters);
         }
@@ -2364,7 +2515,7 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
         {
             ma.mask = 0xFFu;
             ma.final_part = 1;
-            SCOPE(CAT_MEAS);
+            SCOPE2(CAT_MEAS, S17_T_RECORD);
             k_record<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(ma, ctx->meas_out, ctx->lut, ctx->leak, ctx->active,
                                                                   ctx->ready, ctx->rec, ctx->counters);
         }
@@ -2397,7 +2548,7 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
         ma.final_part = final_part ? 1 : 0;
         ma.stream = 16u + (uint32_t)stage * 4u + (final_part ? 0u : 1u);
         {
-            SCOPE(CAT_MEAS);
+            SCOPE2(CAT_MEAS, S17_T_SAMPLE);
             k_measure<<<blocks_for((uint64_t)n * 32, 128), 128, 0, ctx->stream>>>(
                 ma, ctx->hist, ctx->forced, ctx->lut, ctx->leak, ctx->active, ctx->ready, ctx->aux, ctx->rec, ctx->counters);
         }
@@ -2408,8 +2559,8 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
 }
 
 static void collapse(s17_ctx *ctx, int n, const uint8_t *flag) {
-    SCOPE(CAT_MEAS);
-    k_collapse<<<n * 32, 256, 0, ctx->stream>>>(ctx->state, ctx->aux, flag);
+    SCOPE2(CAT_MEAS, S17_T_COLLAPSE);
+    k_collapse<<<n * 32, 256, 0, ctx->stream>>>(ctx->state, ctx->aux, flag, ctx->counters);
     ctx->last_collapsed = true;
 }
 
@@ -2465,11 +2616,11 @@ static int run_round(s17_ctx *ctx, const s17_run_args &a) {
     ra.first_shot = a.first_shot_id;
     ra.n_shots = n;
     if (ctx->use_dsamp) {
-        SCOPE(CAT_MEAS);
+        SCOPE2(CAT_MEAS, S17_T_READOUT);
         k_readout_s<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(ra, ctx->dsamp, ctx->cw16, ctx->leak, ctx->ready, ctx->rec,
                                                                  ctx->counters);
     } else {
-        SCOPE(CAT_MEAS);
+        SCOPE2(CAT_MEAS, S17_T_READOUT);
         k_readout<<<blocks_for((uint64_t)n * 32, 128), 128, 0, ctx->stream>>>(ra, ctx->state, ctx->stride, ctx->aux, ctx->forced, ctx->cw16,
                                                                           ctx->leak, ctx->ready, ctx->rec, ctx->counters);
     }
@@ -2484,6 +2635,7 @@ static int finish_timing(s17_ctx *ctx) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, tl.e0, tl.e1);
         (tl.cat == CAT_GATE ? ctx->t_gate : tl.cat == CAT_MEAS ? ctx->t_meas : ctx->t_other) += ms;
+        if (tl.sub >= 0 && tl.sub < S17_T_N) { ctx->t_sub[tl.sub] += ms; ctx->n_sub[tl.sub]++; }
     }
     ctx->n_all += ctx->launches.size();
     ctx->launches.clear();
@@ -2509,10 +2661,12 @@ static int check_run_args(s17_ctx *ctx, const s17_run_args &a) {
 static int begin_call(s17_ctx *ctx, const s17_run_args &a) {
     CK(cudaSetDevice(ctx->device));
     ctx->t_gate = ctx->t_meas = ctx->t_other = 0;
+    for (int i = 0; i < S17_T_N; ++i) { ctx->t_sub[i] = 0; ctx->n_sub[i] = 0; }
     ctx->n_gate = ctx->n_all = 0;
     ctx->launches.clear();
     ctx->ev_used = 0;
-    const bool all_diag = ctx->diag_ok[0] && ctx->diag_ok[1] && ctx->diag_ok[2] && !ctx->no_diag && !ctx->dense &&
+    auto cyc_ok = [&](int c) { return ctx->diag_ok[c] || (ctx->coh_ok[c] && !ctx->no_diag1); };
+    const bool all_diag = cyc_ok(0) && cyc_ok(1) && cyc_ok(2) && !ctx->no_diag && !ctx->dense &&
                           !ctx->use_v1 && !ctx->force_ring && !ctx->no_fuse && !a.materialize &&
                           a.stop_stage == S17_STOP_NONE;
     if (int rc = ensure_state(ctx, !all_diag)) return rc;
@@ -2520,7 +2674,7 @@ static int begin_call(s17_ctx *ctx, const s17_run_args &a) {
     CK(cudaMemsetAsync(ctx->counters, 0, C_N * sizeof(unsigned long long), ctx->stream));
     const int n = (int)a.n_shots;
     {
-        SCOPE(CAT_OTHER);
+        SCOPE2(CAT_OTHER, S17_T_PLACE);
         k_reset<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(n, ctx->leak, ctx->active, ctx->ready, ctx->rec, ctx->masks,
                                                              a.noise == S17_NOISE_PROB, 0);
     }
@@ -2546,6 +2700,7 @@ static int end_call(s17_ctx *ctx, const s17_run_args &a, s17_counts *out) {
     out->sweeps = c[C_SWEEPS];
     out->rounds = c[C_ROUNDS];
     out->sweep_bytes = c[C_RUNS_MOVED] * (unsigned long long)kRunBytes;   // algorithmic HBM bytes moved by the gate sweeps
+    ctx->u_sub[S17_T_COLLAPSE] = c[C_COLLAPSED];                         // shots whose collapse was materialised
     ctx->last_n = a.n_shots;
     return S17_OK;
 }
@@ -2566,7 +2721,7 @@ extern "C" int s17_rtf_begin(s17_ctx *ctx, const s17_run_args *args) {
     if (int rc = begin_call(ctx, a)) return rc;
     const int n = (int)a.n_shots;
     if (a.noise == S17_NOISE_SUBSET) {
-        SCOPE(CAT_OTHER);
+        SCOPE2(CAT_OTHER, S17_T_PLACE);
         k_place<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(ctx->nd, ctx->cum, ctx->masks, a.seed, a.first_shot_id, n);
     }
     if (ctx->rtf_capacity < a.rtf_runs) {
@@ -2660,7 +2815,7 @@ extern "C" int s17_run(s17_ctx *ctx, const s17_run_args *args, s17_counts *out) 
     if (int rc = begin_call(ctx, a)) return rc;
     const int n = (int)a.n_shots;
     if (a.noise == S17_NOISE_SUBSET) {
-        SCOPE(CAT_OTHER);
+        SCOPE2(CAT_OTHER, S17_T_PLACE);
         k_place<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(ctx->nd, ctx->cum, ctx->masks, a.seed, a.first_shot_id, n);
     }
     if (int rc = run_round(ctx, a)) return rc;
@@ -2708,6 +2863,16 @@ extern "C" int s17_read_rtf(s17_ctx *ctx, uint32_t *rounds, uint32_t *syndb, uin
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpy(rounds, ctx->rtf_rounds, n_runs * 4, cudaMemcpyDeviceToHost));
     if (syndb) CK(cudaMemcpy(syndb, ctx->rtf_syndb, n_runs * 4, cudaMemcpyDeviceToHost));
+    return S17_OK;
+}
+
+extern "C" int s17_last_timing_detail(s17_ctx *ctx, double *ms, uint64_t *launches, uint64_t *units) {
+    if (!ctx || !ms || !launches) return fail(ctx, S17_E_ARG, "s17_last_timing_detail: bad arguments");
+    for (int i = 0; i < S17_T_N; ++i) {
+        ms[i] = ctx->t_sub[i];
+        launches[i] = ctx->n_sub[i];
+        if (units) units[i] = ctx->u_sub[i];
+    }
     return S17_OK;
 }
 

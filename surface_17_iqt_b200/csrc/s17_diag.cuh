@@ -89,6 +89,23 @@ struct DiagProg1 {
                                // bit = 0 to the one for bit = 1 (0: the slot does not depend on a register bit)
 };
 
+// Coherent over-rotations of a noisy cycle (k_cycle1<true>; the `*_over` entries of an error model, SURVEY C-10).
+//   * Rxx(s pi/2) Rxx(eps) and Rx(-s pi/2) Rx(eps) are still functions of X_d X_a / X_d: diagonal in the same frames,
+//     their tables just stop being Gaussian integers.  rxx / rx hold sqrt2 (cos, sin) of the total half angle per
+//     operation (Rxx sign folded in): (u, v) -> (c u - i lambda sn v, c v - i lambda sn u), phase (c - i lambda sn).
+//   * Ry(+pi/2) Ry(eps_a) ... Ry(-pi/2) Ry(eps_b) = Ry(eps_b) [Ry(-pi/2) ... Ry(+pi/2)] Ry(eps_a): the bracket stays
+//     diagonal, with one real rotation per data qubit before and after the computational-frame half.  The one before
+//     is merged into the butterflies of the inverse Walsh-Hadamard transform that precedes it (Ry(eps) H =
+//     [[a, b], [b, -a]], a = c - s, b = c + s), the one after is a pass of its own.
+// Pauli events must stay Paulis in the frame: the host only selects this kernel for models whose stochastic entries
+// are signs / ancilla Paulis where they act (s17.cu: coherent_events_ok).
+struct DiagCoh {
+    double2 rxx[2][4][4];      // per half, slot, operation
+    double2 rx[2][4][4];       // (1, 0) for an operation without Rx
+    double2 preB[4], preSh, preA[4];   // (a, b) per register bit of map B, the shuffle bit, per register bit of map A
+    double2 postR[4], postL[5];        // (cos, sin) of eps_b / 2 per register bit / lane bit of map A
+};
+
 __device__ __forceinline__ double2 dg_cmul(const double2 a, const double2 b) {
     return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
 }
@@ -435,6 +452,65 @@ __device__ __forceinline__ void dg_build_slot(const DiagHalf &H, const uint32_t 
     tab[e + kDgTabEntries] = make_double2((double)a1r, (double)a1i);
     tab[e + 2 * kDgTabEntries] = make_double2((double)(a0r * a0r + a0i * a0i), (double)(a1r * a1r + a1i * a1i));
 }
+// one table entry (slot k, index idx) of a half cycle with coherent over-rotations: the same recursion in doubles.
+// Events as dg_build_slot (data flip seen by the operation, leak skip, net ancilla Pauli, idle Z).
+__device__ __forceinline__ void dg_build_entry_coh(const DiagHalf &H, const double2 (&rxx)[4][4], const double2 (&rx)[4][4],
+                                                   const uint32_t *evw, double2 *tab, int k, int idx, uint32_t ancz) {
+    double2 u = make_double2(1.0, 0.0), v = make_double2(0.0, 0.0), ph = make_double2(1.0, 0.0);
+    const int n = H.n_ops[k];
+    for (int j = 0; j < n; ++j) {
+        const DiagOp op = H.ops[k][j];
+        const uint32_t w = evw[op.ev_word];
+        const double lam = ((((uint32_t)(idx >> j)) ^ (w >> 31)) & 1u) ? -1.0 : 1.0;
+        if (!((w >> 24) & 1u)) {                              // Rxx(theta) unless leak-skipped (its over-rotation with it)
+            const double c = rxx[k][j].x, sn = lam * rxx[k][j].y;
+            const double2 nu = make_double2(fma(sn, v.y, c * u.x), fma(-sn, v.x, c * u.y));
+            const double2 nv = make_double2(fma(sn, u.y, c * v.x), fma(-sn, u.x, c * v.y));
+            u = nu; v = nv;
+        }
+        if (op.flags & 2u) {                                  // Rx(theta): phase (c - i lambda sn)
+            const double c = rx[k][j].x, sn = lam * rx[k][j].y;
+            ph = make_double2(fma(sn, ph.y, c * ph.x), fma(-sn, ph.x, c * ph.y));
+        }
+        if ((w >> 28) & 1u) v = make_double2(-v.x, -v.y);
+        if ((w >> 27) & 1u) { const double2 t = u; u = v; v = t; }
+        if ((ancz >> op.pad) & 1u) v = make_double2(-v.x, -v.y);
+    }
+    const double2 a0 = dg_cmul(ph, u), a1 = dg_cmul(ph, v);
+    const int e = H.tbase[k] + idx;
+    tab[e] = a0;
+    tab[e + kDgTabEntries] = a1;
+    tab[e + 2 * kDgTabEntries] = make_double2(fma(a0.x, a0.x, a0.y * a0.y), fma(a1.x, a1.x, a1.y * a1.y));
+}
+// radix-16 pass with a butterfly [[a, b], [b, -a]] per register bit (Ry(eps) H; a = b = 1 is dg_wht16)
+__device__ __forceinline__ void dg_rot16(double2 (&p)[16], const double2 (&ab)[4]) {
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        const double al = ab[b].x, be = ab[b].y;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if (i & (1 << b)) continue;
+            const double2 u = p[i], v = p[i | (1 << b)];
+            p[i] = make_double2(fma(al, u.x, be * v.x), fma(al, u.y, be * v.y));
+            p[i | (1 << b)] = make_double2(fma(be, u.x, -al * v.x), fma(be, u.y, -al * v.y));
+        }
+    }
+}
+// plain rotation [[c, -s], [s, c]] per register bit
+__device__ __forceinline__ void dg_ry16(double2 (&p)[16], const double2 (&cs)[4]) {
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        const double c = cs[b].x, sn = cs[b].y;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if (i & (1 << b)) continue;
+            const double2 u = p[i], v = p[i | (1 << b)];
+            p[i] = make_double2(fma(c, u.x, -sn * v.x), fma(c, u.y, -sn * v.y));
+            p[i | (1 << b)] = make_double2(fma(sn, u.x, c * v.x), fma(sn, u.y, c * v.y));
+        }
+    }
+}
+
 // warp all-reduce of four doubles at the price of ten shuffles (instead of twenty): two transposing butterfly stages leave
 // one partial sum per lane, three plain stages finish it, four broadcasts hand every lane all four totals
 __device__ __forceinline__ void dg_reduce4(double (&v)[4], int lane) {
@@ -539,8 +615,10 @@ __device__ __forceinline__ void dg_half1(double2 (&p)[16], const unsigned char *
     for (int i = 0; i < 16; ++i) p[i] = dg_cmul(dg_cmul(p[i], F01[i & 3]), F23[i >> 2]);
 }
 
+template <bool COH>
 __global__ void __launch_bounds__(kDgThreads, 1)
-k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ MeasArgs ma, double2 *__restrict__ state,
+k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C, const __grid_constant__ MeasArgs ma,
+         double2 *__restrict__ state,
          size_t stride, const uint32_t *__restrict__ ev, const uint32_t *__restrict__ frm, const uint32_t *__restrict__ act_list,
          const uint32_t *__restrict__ n_act_ptr, ShotAux *__restrict__ aux, const uint8_t *__restrict__ forced,
          uint32_t *__restrict__ meas_out, uint32_t *__restrict__ dsamp, unsigned long long *__restrict__ counters,
@@ -565,8 +643,18 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ MeasArgs m
     if (warp == 0) {
         zero_ev[lane] = 0u;
         __syncwarp();
-        dg_build_tables(P.h[0], zero_ev, reinterpret_cast<double2 *>(clean), lane, 0u, 0u, 0u);
-        dg_build_tables(P.h[1], zero_ev, reinterpret_cast<double2 *>(clean + kDgTabBytes), lane, 0u, 0u, 0u);
+        if (COH) {
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h)
+                for (int e = lane; e < (int)P.h[h].n_entries; e += 32) {
+                    const int k = (e >= P.h[h].tbase[1]) + (e >= P.h[h].tbase[2]) + (e >= P.h[h].tbase[3]);
+                    dg_build_entry_coh(P.h[h], C.rxx[h], C.rx[h], zero_ev, reinterpret_cast<double2 *>(clean + h * kDgTabBytes), k,
+                                       e - P.h[h].tbase[k], 0u);
+                }
+        } else {
+            dg_build_tables(P.h[0], zero_ev, reinterpret_cast<double2 *>(clean), lane, 0u, 0u, 0u);
+            dg_build_tables(P.h[1], zero_ev, reinterpret_cast<double2 *>(clean + kDgTabBytes), lane, 0u, 0u, 0u);
+        }
     }
     __syncthreads();
 
@@ -705,6 +793,20 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ MeasArgs m
             const DiagHalf &H = P.h[h];
             const uint32_t fw = fwp[h];
             if (r != 1) {
+                if (COH && st == 5) {
+                    // Ry(eps_b) on every data qubit after its bracket: register bits in place, lane bits by shuffle
+                    dg_ry16(p, C.postR);
+#pragma unroll 1
+                    for (int m = 0; m < 5; ++m) {
+                        const double c = C.postL[m].x, sn = ((lane >> m) & 1) ? C.postL[m].y : -C.postL[m].y;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const double ox = __shfl_xor_sync(0xffffffffu, p[i].x, 1 << m), oy = __shfl_xor_sync(0xffffffffu, p[i].y, 1 << m);
+                            p[i] = make_double2(fma(sn, ox, c * p[i].x), fma(sn, oy, c * p[i].y));
+                        }
+                    }
+                    continue;
+                }
                 if (!H.frame_x) continue;
                 if (st == 0 && init_basis >= 0) continue;         // already in the frame (see above)
                 // Walsh-Hadamard transform of the data register: the register bits of the current map, the exchange to the
@@ -714,8 +816,23 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ MeasArgs m
                 const uint32_t *wr = dir ? P.mapB.swz16 : P.mapA.swz16, *rr = dir ? P.mapA.swz16 : P.mapB.swz16;
 #pragma unroll 1
                 for (int half_pass = 0; half_pass < 2; ++half_pass) {
+                    if (COH && dir) {
+                        // back to the computational frame, with Ry(eps_a) of every data qubit merged into its butterfly
+                        if (half_pass) {
+                            const double al = ((lane >> P.sh_lane_bit) & 1) ? -C.preSh.x : C.preSh.x, be = C.preSh.y;
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const double ox = __shfl_xor_sync(0xffffffffu, p[i].x, sh_mask), oy = __shfl_xor_sync(0xffffffffu, p[i].y, sh_mask);
+                                p[i] = make_double2(fma(al, p[i].x, be * ox), fma(al, p[i].y, be * oy));
+                            }
+                            dg_rot16(p, C.preA);
+                        } else {
+                            dg_rot16(p, C.preB);
+                        }
+                    } else {
                     if (half_pass == dir) lane_stage(p);          // in map A: before the first pass / before the last one
                     dg_wht16(p);
+                    }
                     if (half_pass == 0) {
                         __syncwarp();
 #pragma unroll
@@ -750,8 +867,10 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ MeasArgs m
                     const int k1 = d ? __ffs(d) - 1 : -1;
                     d &= d - 1;
                     const int k = lane < 16 ? k0 : k1, idx = lane & 15;
-                    if (k >= 0 && idx < (1 << H.n_ops[k]))
-                        dg_build_slot(H, evw, reinterpret_cast<double2 *>(tab), k, idx, fw >> 20);
+                    if (k >= 0 && idx < (1 << H.n_ops[k])) {
+                        if (COH) dg_build_entry_coh(H, C.rxx[h], C.rx[h], evw, reinterpret_cast<double2 *>(tab), k, idx, fw >> 20);
+                        else dg_build_slot(H, evw, reinterpret_cast<double2 *>(tab), k, idx, fw >> 20);
+                    }
                 }
                 __syncwarp();
             }

@@ -78,14 +78,17 @@ def broadcast_seed(seed):
 
 
 def gather_lists(values):
-    """Concatenate one list of ints per rank in rank order (run-til-fail: rounds_til_fail_list of every rank's runs)."""
+    """Concatenate one list of ints per rank in rank order (run-til-fail: rounds_til_fail_list of every rank's runs).
+    Accepts and returns a numpy array when given one (large run counts never become Python ints on the way)."""
+    import numpy as np
+    as_array = isinstance(values, np.ndarray)
     try:
         import torch
         import torch.distributed as dist
     except ImportError:
-        return list(values)
+        return values if as_array else list(values)
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-        return list(values)
+        return values if as_array else list(values)
     dev = _group_device(dist)
     n = torch.tensor([len(values)], dtype=torch.int64, device=dev)
     sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(dist.get_world_size())]
@@ -93,11 +96,9 @@ def gather_lists(values):
     sizes = [int(v.item()) for v in sizes]
     pad = max(sizes) if sizes else 0
     mine = torch.zeros(pad, dtype=torch.int64, device=dev)
-    if values:
-        mine[:len(values)] = torch.tensor([int(v) for v in values], dtype=torch.int64, device=dev)
+    if len(values):
+        mine[:len(values)] = torch.as_tensor(np.asarray(values, dtype=np.int64), device=dev)
     parts = [torch.zeros(pad, dtype=torch.int64, device=dev) for _ in sizes]
     dist.all_gather(parts, mine)
-    out = []
-    for sz, part in zip(sizes, parts):
-        out.extend(int(v) for v in part[:sz].tolist())
-    return out
+    out = np.concatenate([part[:sz].cpu().numpy() for sz, part in zip(sizes, parts)]) if sizes else np.zeros(0, np.int64)
+    return out if as_array else [int(v) for v in out]

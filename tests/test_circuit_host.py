@@ -149,6 +149,23 @@ def test_host_lowering_selects_the_whole_cycle_kernel(error_models):
     coherent = circuit.compile_program(error_models["coherent_model"], [30, 24, 24], fusion=2, early_measure=True,
                                        over_angles={"eps_1q": [0.02] * 30, "eps_2q": [0.02] * 24})
     info = backend.describe_program(coherent)
-    assert [i["k_cycle1"] for i in info] == [True, False, False]
+    # coherent over-rotations: the noisy cycles keep the maps of their Clifford skeleton and run on the coherent form of the
+    # whole-cycle kernel (k_half / the generic-map k_cycle do not apply); the preparation cycle is the plain one
+    assert [i["k_cycle1"] for i in info] == [True, True, True]
+    assert [i["coherent"] for i in info] == [False, True, True]
+    assert [i["k_cycle"] for i in info] == [True, False, False] and [i["k_half"] for i in info] == [True, False, False]
+    plain = backend.describe_program(circuit.compile_program(error_models["PDD_model"], [12, 18, 24, 78, 24], fusion=2,
+                                                            early_measure=True))
+    for c in (1, 2):
+        for key in ("reg_bits_z", "reg_bits_x", "shuffle_bit", "slot_ancilla", "table_entries"):
+            assert info[c][key] == plain[c][key]
+    # ... but only while every stochastic entry stays a Pauli in the frame next to the rotations: a Z on the data qubit
+    # after an over-rotated Rx is a basis flip in the Hadamard frame that does not commute with them -> sweep kernels
+    import copy
+    flipping = copy.deepcopy(error_models["coherent_model"])
+    flipping["gates"]["Rx"].append(["Z", "p_XX_ctrl", "test: dephasing after Rx"])
+    info = backend.describe_program(circuit.compile_program(flipping, [30, 24, 24], fusion=2, early_measure=True,
+                                                            over_angles={"eps_1q": [0.02] * 30, "eps_2q": [0.02] * 24}))
+    assert [i["k_cycle1"] for i in info] == [True, False, False] and not any(i["coherent"] for i in info)
     late = circuit.compile_program(error_models["PDD_model"], [12, 18, 24, 78, 24], fusion=2, early_measure=False)
     assert not any(i["k_half"] or i["k_cycle"] for i in backend.describe_program(late))

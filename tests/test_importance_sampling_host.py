@@ -96,3 +96,33 @@ def test_lookup_table_generation_properties():
         assert " ".join(map(str, synd)) == key
     assert hist == {0: 1, 1: 23, 2: 120, 3: 96, 4: 16}
     assert len(glt.generate_classical_bitflip_table()) == 16
+    # and the generated tables ARE the shipped ones (the reference's files, byte for byte in the JSON format it writes)
+    data = os.path.join(os.path.dirname(GOLDEN), os.pardir, "surface_17_iqt_b200", "data")
+    shipped = json.load(open(os.path.join(data, "correction_table_depolarising.json")))
+    assert {k: [list(v[0]), v[1]] for k, v in table.items()} == {k: [list(v[0]), v[1]] for k, v in shipped.items()}
+    shipped_c = json.load(open(os.path.join(data, "correction_table_classical_bitflip.json")))
+    mine_c = glt.generate_classical_bitflip_table()
+    assert {k: [list(v[0]), v[1]] for k, v in mine_c.items()} == {k: [list(v[0]), v[1]] for k, v in shipped_c.items()}
+
+
+def test_run_til_fail_fit_equals_the_reference_fit():
+    """fit_log_e_rate (histogram + scipy curve_fit of A exp(-r t), CL:546-565 without the plotting) on the seeded
+    rounds-til-fail lists of the reference's own driver (tests/golden/rtf_ref.json, minted by oracle/make_golden_rtf.py:
+    `reference_fit` is what the unmodified calculate_log_e_rate returned for the same list and num_bins = 5): equal to
+    1e-12 relative; where the reference's fit did not converge, ours raises too."""
+    import warnings
+    from surface_17_iqt_b200.calc_log_e_rate_arbitrary_error_model import fit_log_e_rate
+    cases = json.load(open(os.path.join(GOLDEN, "rtf_ref.json")))["cases"]
+    checked = 0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for case in cases:
+            for chain in case["chains"]:
+                if chain["reference_fit"] is None:
+                    with pytest.raises(RuntimeError):
+                        fit_log_e_rate(chain, 5)
+                    continue
+                got = fit_log_e_rate(chain, 5)[0]
+                assert got == pytest.approx(chain["reference_fit"], rel=1e-12)
+                checked += 1
+    assert checked >= 12
