@@ -225,16 +225,12 @@ struct NoiseDev {
 __device__ __forceinline__ bool mask_get(const uint32_t *m, uint32_t bit) { return (m[bit >> 5] >> (bit & 31)) & 1u; }
 __device__ __forceinline__ void mask_set(uint32_t *m, uint32_t bit) { m[bit >> 5] |= 1u << (bit & 31); }
 
-// generate_error_locations (uniform, rejection) / generate_error_locations_non_uniform (CL:151-181)
-__global__ void k_place(NoiseDev nd, const double *__restrict__ cum, uint32_t *__restrict__ masks, uint64_t seed,
-                        uint64_t first_shot, int n_shots)
+// generate_error_locations (uniform, rejection) / generate_error_locations_non_uniform (CL:151-181) for one shot:
+// sets the placed slots in the (zeroed) bitset m
+__device__ __forceinline__ void place_errors(const NoiseDev &nd, const double *__restrict__ cum, uint32_t *m, uint64_t seed,
+                                             uint64_t shot_id)
 {
-    const int shot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (shot >= n_shots) return;
-    uint32_t m[S17_MASK_WORDS];
-#pragma unroll
-    for (int i = 0; i < (int)S17_MASK_WORDS; ++i) m[i] = 0;
-    Philox rng(seed, first_shot + shot, 1u);
+    Philox rng(seed, shot_id, 1u);
     for (uint32_t t = 0; t < nd.n_lists; ++t) {
         const uint32_t L = nd.list_len[t], off = nd.list_off[t];
         const double total = nd.weighted[t] ? cum[off + L - 1] : 0.0;
@@ -257,9 +253,6 @@ __global__ void k_place(NoiseDev nd, const double *__restrict__ cum, uint32_t *_
             }
         }
     }
-    uint32_t *out = masks + (size_t)shot * (2 * S17_MASK_WORDS);
-#pragma unroll
-    for (int i = 0; i < (int)S17_MASK_WORDS; ++i) out[i] = m[i];
 }
 
 struct PlanArgs {
@@ -268,6 +261,7 @@ struct PlanArgs {
     int noiseless;    // prep cycle: nothing fires, only the leak skip predicate is evaluated
     int second;       // 1: second (stab_ind=1) cycle -> use_round slots are offset by len/2 (CS:191-193)
     int rec_half;     // PROB mode: which half of the mask record receives the fired bits (0/1)
+    int place;        // SUBSET mode, first noisy cycle: draw the shot's fixed-weight placement here (and record it)
     uint32_t stream;
     uint64_t seed, first_shot;
     int n_shots;
@@ -309,248 +303,6 @@ __device__ __forceinline__ uint32_t pconj_rxx(uint32_t P, int s) {        // Rxx
     return pconj(P, 0x01u, 0x07u | k, 0x04u, 0x0Du | k);
 }
 
-// One thread per shot; a warp stages its 32 shots' slot bitsets and event words through shared memory (row stride 33
-// words) so that the global traffic is coalesced rows instead of 32 strided 4-byte accesses per instruction.
-//
-// The program is walked by GROUP (one entangling operation, or the idle slots of one gap between timesteps, in program
-// order).  A shot first finds which groups have a fired entry at all -- from its placed / replayed slot bits, or, with
-// true probabilities, by sampling the position of the next firing entry from the survival products of the program
-// (geometric skipping: P(first fire at i) = S_i p_i, S_i = prod_{j<i} (1 - p_j); one uniform per event instead of one
-// per entry) -- and only those groups are walked instruction by instruction; every other operation takes its default
-// event word (the data-flip bit of the frame).  A set leak flag, or a fired leakage entry, makes the shot walk every
-// group (the skip predicate of every later operation may change).
-constexpr int kPlanThreads = 128;
-constexpr int kPlanRow = 33;
-constexpr int kPlanMaxInstr = 640;
-constexpr int kPlanMaxGroups = 32;
-// group words: [g] bits 0-9 first instruction, 10-19 one past the last; [32 + g] bit 0 gap (idle) group, 1-5 event word,
-// 6-9 data bit, 10 first operation of its half cycle, 11 half index, 12 Hadamard frame, 13 the operation closes the Ry
-// bracket of its data qubit
-__global__ void __launch_bounds__(kPlanThreads)
-k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, NoiseDev nd, const double *__restrict__ probs,
-       uint32_t *__restrict__ ev, uint32_t *__restrict__ masks, uint32_t *__restrict__ leak,
-       const uint8_t *__restrict__ active, uint32_t *__restrict__ frm, uint32_t *__restrict__ n_act,
-       const uint32_t *__restrict__ hot, uint8_t *__restrict__ quiet /* nullptr, or per shot: 1 = no entry fired and no
-       qubit is leaked in this cycle (event-free: k_quiet replays it from the cache) */,
-       const uint32_t *__restrict__ grp, int n_grp, const uint8_t *__restrict__ bit2grp /* slot bit -> group | leak << 7 */,
-       const double *__restrict__ surv /* nullptr, or survival products S_0 .. S_n of this cycle's entries */)
-{
-    __shared__ uint32_t s_mask[kPlanThreads / 32][32][kPlanRow], s_ev[kPlanThreads / 32][32][kPlanRow];
-    __shared__ uint32_t s_prog[kPlanMaxInstr * 3];     // the program of this cycle (slots resolved to absolute bit indices)
-    __shared__ uint32_t s_grp[2 * kPlanMaxGroups];     // [0..31] instruction range, [32..63] operation word (below)
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    if (blockIdx.x == 0 && threadIdx.x == 0) *n_act = 0;     // k_compact, next in the stream, appends to an empty list
-    // one word per instruction for the common case (an entry that does not fire): bits 0-15 absolute slot, bit 16
-    // in_skip, bit 17 entry (S17_P_ERR / S17_P_IDLE); stored behind the two program variants
-    __shared__ uint32_t s_hot[kPlanMaxInstr];
-    {
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(prog);
-        for (int i = threadIdx.x; i < pa.n_instr * 3; i += blockDim.x) s_prog[i] = src[i];
-        for (int i = threadIdx.x; i < pa.n_instr; i += blockDim.x) s_hot[i] = hot[i];
-        if (threadIdx.x < 2 * kPlanMaxGroups) s_grp[threadIdx.x] = (threadIdx.x & (kPlanMaxGroups - 1)) < n_grp ? grp[threadIdx.x] : 0u;
-        __syncthreads();
-    }
-    const bool prob_mode = pa.noise == S17_NOISE_PROB;
-    uint32_t gap_mask = 0;
-    for (int gi = 0; gi < n_grp; ++gi) gap_mask |= (s_grp[kPlanMaxGroups + gi] & 1u) << gi;
-    // persistent over groups of kPlanThreads shots: the program is staged once per CTA (no CTA-wide barrier below)
-    for (int base = blockIdx.x * kPlanThreads; base < pa.n_shots; base += gridDim.x * kPlanThreads) {
-    const int shot = base + threadIdx.x, shot0 = shot - lane;
-    const bool act = shot < pa.n_shots && active[shot];
-    const uint32_t actmask = __ballot_sync(0xffffffffu, act);
-    if (!actmask) continue;
-    for (int r = 0; r < 32; ++r)
-        if ((actmask >> r) & 1u)
-            s_mask[wib][r][lane] = prob_mode ? 0u : masks[(size_t)(shot0 + r) * (2 * S17_MASK_WORDS) + lane];
-    __syncwarp();
-    uint32_t *evs = s_ev[wib][lane];
-    uint32_t *mk = s_mask[wib][lane];                  // placed slots (subset / replay) or the slots fired now (prob mode)
-    uint32_t lk = 0;
-    Philox rng(pa.seed, pa.first_shot + shot, pa.stream);
-    uint32_t f_flip = 0, f_sign = 0, f_phase = 0, f_ancz = 0;   // frame bookkeeping of the current half cycle (k_cycle)
-    int f_half = -1;
-    if (act) lk = leak[shot];
-    bool any_event = lk != 0;
-    if (act && pa.noiseless && lk == 0) {
-        // noiseless preparation cycle without a leaked qubit: no event, no leak skip, identity frame
-        for (int i = 0; i < (int)S17_EV_WORDS; ++i) evs[i] = 0;
-        frm[(size_t)shot * 4] = 0;
-        frm[(size_t)shot * 4 + 1] = 0;
-    } else if (act) {
-    for (int i = 24; i < (int)S17_EV_WORDS; ++i) evs[i] = 0;
-    // ---- which entries fire ----
-    if (prob_mode && !pa.noiseless) {
-        if (surv) {
-            int pos = 0;
-            const double s_end = surv[pa.n_instr];
-            for (;;) {
-                const double target = rng.next() * surv[pos];
-                if (!(s_end < target)) break;                        // nothing fires in the rest of the cycle
-                int lo = pos, hi = pa.n_instr - 1;                   // smallest i >= pos with S_{i+1} < target
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (surv[mid + 1] < target) hi = mid; else lo = mid + 1;
-                }
-                mask_set(mk, s_hot[lo] & 0xFFFFu);
-                pos = lo + 1;
-            }
-        } else {
-            for (int i = 0; i < pa.n_instr; ++i) {                   // one Bernoulli draw per entry (CS:198)
-                const uint32_t hw = s_hot[i];
-                if ((hw & 0x20000u) && rng.next() < probs[hw & 0xFFFFu]) mask_set(mk, hw & 0xFFFFu);
-            }
-        }
-    }
-    uint32_t flagged = 0, leak_event = 0;
-    if (!pa.noiseless) {
-        for (int wi = 0; wi < (int)S17_MASK_WORDS; ++wi) {
-            uint32_t word = mk[wi];
-            while (word) {
-                const uint32_t g = bit2grp[32 * wi + __ffs(word) - 1];
-                word &= word - 1;
-                if (g != 0xFFu) { flagged |= 1u << (g & 31u); leak_event |= g >> 7; }
-            }
-        }
-    }
-    any_event = any_event || flagged != 0;
-    const uint32_t todo = (lk != 0 || leak_event) ? 0xFFFFFFFFu : flagged;
-    // ---- pass 1: the operations with a fired entry (every operation while a qubit is leaked), each lane walking ITS OWN
-    // list of groups: one instruction per trip of a single loop, so a warp spends the longest lane's walk, not the union
-    // of its lanes' groups.  Leaves the operation's event word (per-gate fields, skip bit, net Pauli) in evs[].
-    {
-        uint32_t td = todo & (n_grp >= 32 ? 0xFFFFFFFFu : ((1u << n_grp) - 1u)) & ~gap_mask;
-        int i = 0, end = 0;
-        uint32_t w = 0, skip = 0;
-        for (;;) {
-            if (i == end) {
-                if (!td) break;
-                const uint32_t gm = s_grp[__ffs(td) - 1];
-                td &= td - 1;
-                i = (int)(gm & 1023u);
-                end = (int)((gm >> 10) & 1023u);
-            }
-            const uint32_t hw = s_hot[i];
-            const int ii = i++;
-            if (hw & 0x20000u) {
-                // a fired entry acts unless it sits inside a skipped Rxx block (CS:293, 322).  The slot is the absolute index
-                // of the entry in this cycle (list offset + slot + half the list in a second cycle, CS:191-193).
-                if ((((hw >> 16) & 1u) & skip) || pa.noiseless) continue;
-                if (!mask_get(mk, hw & 0xFFFFu)) continue;
-            }
-            const s17_pinstr in = reinterpret_cast<const s17_pinstr *>(s_prog)[ii];
-            if (in.kind == S17_P_OP_BEGIN) { w = 0; skip = 0; continue; }
-            if (in.kind == S17_P_SKIP_TEST) {
-                // evaluated AFTER the errors of a preceding Ry (which may just have leaked the data qubit)
-                skip = ((lk >> in.a) | (lk >> in.b)) & 1u;
-                w |= skip << 24;
-                continue;
-            }
-            if (in.kind == S17_P_OP_END) {
-                // net Pauli at the END of the operation (bits 25-30): every event conjugated through the gates that follow
-                // it; exact because Rxx/Rx/Ry(+-pi/2) are Clifford.  The fast sweep path applies the gates branch-free
-                // and this single Pauli afterwards; the per-gate fields (bits 0-23) stay for the interpreter paths.
-                if (w & 0xFFFFFFu) {
-                    uint32_t N = 0;
-                    const int s = in.b ? 1 : -1;
-                    if (in.a & 1) N = w & 63u;                                            // after Ry(+)
-                    if (!skip) { N = pconj_rxx(N, s); N = pmul2((w >> 6) & 63u, N); }
-                    if (in.a & 2) { N = pconj_rx(N, -s); N = pmul2((w >> 12) & 63u, N); }
-                    if (in.a & 4) { N = pconj_ry(N, -1); N = pmul2((w >> 18) & 63u, N); }
-                    w |= N << 25;
-                }
-                evs[in.word] = w;
-                continue;
-            }
-            uint32_t f = (w >> in.field) & 63u;
-            switch (in.err) {
-            case S17_ERR_X: f = pauli_mul(f, 0, 1); break;
-            case S17_ERR_Y: f = pauli_mul(f, 0, 2); break;
-            case S17_ERR_Z: f = pauli_mul(f, 0, 3); break;
-            case S17_ERR_ZC: f = pauli_mul(f, 0, 3); break;
-            case S17_ERR_ZT: f = pauli_mul(f, 1, 3); break;
-            case S17_ERR_XX: f = pauli_mul(pauli_mul(f, 0, 1), 1, 1); break;
-            case S17_ERR_ZZ: f = pauli_mul(pauli_mul(f, 0, 3), 1, 3); break;
-            case S17_ERR_LEAK_A: lk |= 1u << in.a; break;
-            case S17_ERR_LEAK_AB: lk |= (1u << in.a) | (1u << in.b); break;
-            case S17_ERR_DEPOL: {
-                // insert_2q_error (CS:237-283): 15 equiprobable non-identity pairs, first letter -> qubits[0]
-                int k = (int)(rng.next() * 15.0);
-                if (k > 14) k = 14;
-                const int code = k + 1, p0 = code >> 2, p1 = code & 3;   // IX,IY,IZ,XI,...,ZZ
-                if (p0) f = pauli_mul(f, 0, p0);
-                if (p1) f = pauli_mul(f, 1, p1);
-            } break;
-            default: break;
-            }
-            w = (w & ~(63u << in.field)) | (f << in.field);
-        }
-    }
-    // ---- pass 2: every group in program order (warp-uniform trip count): the net Pauli of each operation in the frame
-    // where its half cycle is diagonal (s17_diag.cuh) -- a data X relabels the basis (flip mask; bit 31 tells the
-    // operation whether its own label bit is flipped), a data Z is a label-dependent sign (sign mask), the rest is a
-    // global phase -- and the idle entries of the gaps (sympathetic_cooling, CS:762-772).
-    for (int gi = 0; gi < n_grp; ++gi) {
-        const uint32_t gm = s_grp[gi], g2 = s_grp[kPlanMaxGroups + gi];
-        const bool walked = (todo >> gi) & 1u;
-        if (g2 & 1u) {                                 // gap between two timesteps: its fired idle entries
-            if (!walked || pa.noiseless) continue;
-            for (int i = (int)(gm & 1023u); i < (int)((gm >> 10) & 1023u); ++i) {
-                const uint32_t hw = s_hot[i];
-                if (!mask_get(mk, hw & 0xFFFFu)) continue;
-                const s17_pinstr in = reinterpret_cast<const s17_pinstr *>(s_prog)[i];
-                evs[in.word] |= 1u << in.a;            // the 17-bit idle masks of the sweep kernels / k_half
-                if (in.b & 0x80u) {                    // the same Z in the frame of its half cycle (whole-cycle kernels)
-                    if (in.a < 9u) {
-                        const uint32_t bit = 1u << in.a;
-                        if (in.b & 2u) f_flip ^= bit;                                   // H Z H = X
-                        else if (in.b & 1u) { f_flip ^= bit; f_phase += 2u; }           // Ry(-pi/2) Z Ry(+pi/2) = -X
-                        else { f_sign ^= bit; f_phase += 2u * ((f_flip >> in.a) & 1u); }
-                    } else if (in.field != 255u) {
-                        f_ancz ^= 1u << in.field;      // Z on the ancilla after that operation (and its own events)
-                    }
-                }
-            }
-            continue;
-        }
-        const uint32_t word = (g2 >> 1) & 31u, d = (g2 >> 6) & 15u;
-        uint32_t w = walked ? evs[word] : 0u;
-        if ((g2 >> 10) & 1u) {                         // first operation of a half: close the previous one (idle events may
-            if (f_half >= 0)                           // follow its last operation), start from the identity frame
-                frm[(size_t)shot * 4 + f_half] = f_flip | (f_sign << 9) | ((f_phase & 3u) << 18) | (f_ancz << 20);
-            f_flip = 0; f_sign = 0; f_phase = 0; f_ancz = 0;
-            f_half = (int)((g2 >> 11) & 1u);
-        }
-        w |= ((f_flip >> d) & 1u) << 31;
-        const uint32_t N = (w >> 25) & 63u;
-        if (N) {
-            uint32_t F = N;
-            if ((g2 >> 12) & 1u) {                     // H X^x Z^z H = (-1)^{xz} X^z Z^x
-                const uint32_t x = N & 1u, z = (N >> 1) & 1u, k = (N >> 4) & 3u;
-                F = (N & 0x0Cu) | z | (x << 1) | (((k + 2u * (x & z)) & 3u) << 4);
-            } else if (!((g2 >> 13) & 1u)) {           // still inside the Ry bracket of its data qubit
-                F = pconj_ry(N, -1);
-            }
-            if (F & 2u) { f_sign ^= 1u << d; f_phase += 2u * ((f_flip >> d) & 1u); }
-            if (F & 1u) f_flip ^= 1u << d;
-            f_phase += (F >> 4) & 3u;
-        }
-        evs[word] = w;
-    }
-    if (f_half >= 0) frm[(size_t)shot * 4 + f_half] = f_flip | (f_sign << 9) | ((f_phase & 3u) << 18) | (f_ancz << 20);
-    leak[shot] = lk;
-    }
-    if (quiet && act) quiet[shot] = any_event ? 0 : 1;
-    __syncwarp();
-    for (int r = 0; r < 32; ++r) {
-        if (!((actmask >> r) & 1u)) continue;
-        ev[(size_t)(shot0 + r) * S17_EV_WORDS + lane] = s_ev[wib][r][lane];
-        if (prob_mode)
-            masks[(size_t)(shot0 + r) * (2 * S17_MASK_WORDS) + (pa.rec_half ? S17_MASK_WORDS : 0) + lane] = s_mask[wib][r][lane];
-    }
-    __syncwarp();                                      // the staging rows are reused by the next group
-    }
-}
-
 // =================================================================================================
 // measurement, collapse, correction, read-out
 // =================================================================================================
@@ -566,6 +318,15 @@ struct MeasArgs {
     uint64_t seed, first_shot;
     int n_shots;
 };
+
+__device__ __forceinline__ void reset_shot(int shot, uint8_t *__restrict__ active, uint8_t *__restrict__ ready,
+                                           s17_record *__restrict__ rec) {
+    active[shot] = 1;
+    ready[shot] = 0;
+    s17_record z;
+    memset(&z, 0, sizeof(z));
+    rec[shot] = z;
+}
 
 // bookkeeping after the ancillas in ma.mask of `shot` were measured with raw outcome bits `a`: outcome log, and on the
 // final part of a cycle the leak override (CS:854-857), the syndrome comparison and the protocol's branch
@@ -691,6 +452,357 @@ __global__ void k_record(MeasArgs ma, const uint32_t *__restrict__ meas_out, con
                        rec, counters);
 }
 
+// =================================================================================================
+// k_plan: one launch between two cycle kernels
+// =================================================================================================
+// One thread per shot; a warp stages its 32 shots' slot bitsets and event words through shared memory (row stride 33
+// words) so that the global traffic is coalesced rows instead of 32 strided 4-byte accesses per instruction.  Per shot:
+//   1. the bookkeeping of the cycle that just ended (StepArgs::do_record; the body of k_record: outcome log, leak
+//      override, protocol branch, lookup decode), so that a step needs no separate launch for it;
+//   2. error insertion for the cycle that starts (insert_errors / insert_error, CS:127-234) -> one event word per
+//      operation + the frame words of the whole-cycle kernel.  The program is walked by GROUP (one entangling operation,
+//      or the idle slots of one gap between timesteps, in program order).  A shot first finds which entries fire -- its
+//      placed / replayed slot bits, or, with true probabilities, the position of the next firing entry sampled from the
+//      survival products of the program (geometric skipping: P(first fire at i) = S_i p_i, S_i = prod_{j<i} (1 - p_j);
+//      one uniform per event instead of one per entry) -- and marks them in a bitmap over the INSTRUCTIONS of the
+//      program; an operation with a fired entry then visits just those instructions (in program order) and its end;
+//      every other operation takes its default event word (the data-flip bit of the frame).  A set leak flag, or a
+//      fired leakage entry, makes the shot walk every instruction of every group (the skip predicate of every later
+//      operation may change), as does a program in which two entries share a slot;
+//   3. the list of shots the cycle kernel will run (StepArgs::do_compact).
+constexpr int kPlanThreads = 128;
+constexpr int kPlanRow = 33;
+constexpr int kPlanMaxInstr = 640;
+constexpr int kPlanMaxGroups = 32;
+constexpr int kPlanFiWords = kPlanMaxInstr / 32;       // fired-instruction bitmap of one shot
+constexpr int kPlanFiRow = kPlanFiWords + 1;           // odd row stride: conflict-free
+constexpr size_t kPlanSmem = (size_t)(2 * (kPlanThreads / 32) * 32 * kPlanRow + kPlanThreads * kPlanFiRow +
+                                      kPlanMaxInstr * 3 + kPlanMaxInstr + 2 * kPlanMaxGroups) * 4;
+struct StepArgs {
+    int do_record;                 // 1: first apply the previous cycle's measurement outcomes (rec_ma.stage) to the shot
+    MeasArgs rec_ma;
+    const uint32_t *meas_out;
+    const uint32_t *lut;
+    uint8_t *ready;
+    s17_record *rec;
+    unsigned long long *counters;
+    int do_compact;                // 1: append the shots the cycle kernel runs to `list` (*n_act must be 0 on entry)
+    uint32_t *list;
+    const uint8_t *leaf;           // nullptr, or per shot: byte for bits 24-31 of its entry (k_cycle1 + prep cache)
+    const uint8_t *quiet_ok;       // nullptr, or: event-free shots in a leaf with quiet_ok[leaf] are left out (k_quiet)
+    const uint8_t *done;           // nullptr, or per shot: 1 = the memoised preparation handled it
+    int skip_done;
+    int walk_all;                  // 1: two entries share a slot somewhere in the program -> no per-entry shortcuts
+    int do_reset;                  // 1: first launch of a call: fresh flags, record (and leak register unless keep_leak)
+    int keep_leak;
+    NoiseDev nd;                   // PlanArgs::place: the subset to place
+    const double *cum;
+};
+// hot word of an instruction: bits 0-15 absolute slot, 16 in_skip, 17 entry (S17_P_ERR / S17_P_IDLE), 18-22 group,
+// 23 leakage entry.  group words: [g] bits 0-9 first instruction, 10-19 one past the last; [32 + g] bit 0 gap (idle)
+// group, 1-5 event word, 6-9 data bit, 10 first operation of its half cycle, 11 half index, 12 Hadamard frame, 13 the
+// operation closes the Ry bracket of its data qubit (Ry(-)), 14 it opens it (Ry(+)), 15 it has an Rx, 16 Rxx sign is +
+__device__ __forceinline__ uint32_t plan_apply_error(uint32_t f, const s17_pinstr &in, uint32_t &lk, Philox &rng) {
+    switch (in.err) {
+    case S17_ERR_X: f = pauli_mul(f, 0, 1); break;
+    case S17_ERR_Y: f = pauli_mul(f, 0, 2); break;
+    case S17_ERR_Z: f = pauli_mul(f, 0, 3); break;
+    case S17_ERR_ZC: f = pauli_mul(f, 0, 3); break;
+    case S17_ERR_ZT: f = pauli_mul(f, 1, 3); break;
+    case S17_ERR_XX: f = pauli_mul(pauli_mul(f, 0, 1), 1, 1); break;
+    case S17_ERR_ZZ: f = pauli_mul(pauli_mul(f, 0, 3), 1, 3); break;
+    case S17_ERR_LEAK_A: lk |= 1u << in.a; break;
+    case S17_ERR_LEAK_AB: lk |= (1u << in.a) | (1u << in.b); break;
+    case S17_ERR_DEPOL: {
+        // insert_2q_error (CS:237-283): 15 equiprobable non-identity pairs, first letter -> qubits[0]
+        int k = (int)(rng.next() * 15.0);
+        if (k > 14) k = 14;
+        const int code = k + 1, p0 = code >> 2, p1 = code & 3;   // IX,IY,IZ,XI,...,ZZ
+        if (p0) f = pauli_mul(f, 0, p0);
+        if (p1) f = pauli_mul(f, 1, p1);
+    } break;
+    default: break;
+    }
+    return f;
+}
+// net Pauli at the END of an operation (bits 25-30 of its event word): every event conjugated through the gates that
+// follow it; exact because Rxx/Rx/Ry(+-pi/2) are Clifford.  The fast sweep path applies the gates branch-free and this
+// single Pauli afterwards; the per-gate fields (bits 0-23) stay for the interpreter paths.
+__device__ __forceinline__ uint32_t plan_net_pauli(uint32_t w, uint32_t skip, bool ry1, bool rx, bool ry2, int s) {
+    if (!(w & 0xFFFFFFu)) return w;
+    uint32_t N = 0;
+    if (ry1) N = w & 63u;                                                 // after Ry(+)
+    if (!skip) { N = pconj_rxx(N, s); N = pmul2((w >> 6) & 63u, N); }
+    if (rx) { N = pconj_rx(N, -s); N = pmul2((w >> 12) & 63u, N); }
+    if (ry2) { N = pconj_ry(N, -1); N = pmul2((w >> 18) & 63u, N); }
+    return w | (N << 25);
+}
+
+__global__ void __launch_bounds__(kPlanThreads)
+k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, const __grid_constant__ StepArgs sa, const double *__restrict__ probs,
+       uint32_t *__restrict__ ev, uint32_t *__restrict__ masks, uint32_t *__restrict__ leak,
+       uint8_t *__restrict__ active, uint32_t *__restrict__ frm, uint32_t *__restrict__ n_act /* this cycle's list length */,
+       uint32_t *__restrict__ n_act_next /* zeroed here for the launch after this one */,
+       const uint32_t *__restrict__ hot, uint8_t *__restrict__ quiet /* nullptr, or per shot: 1 = no entry fired and no
+       qubit is leaked in this cycle (event-free: k_quiet replays it from the cache) */,
+       const uint32_t *__restrict__ grp, int n_grp, const uint16_t *__restrict__ bit2instr /* slot bit -> instruction */,
+       const double *__restrict__ surv /* nullptr, or survival products S_0 .. S_n of this cycle's entries */)
+{
+    extern __shared__ uint32_t plan_smem[];
+    uint32_t (*s_mask)[32][kPlanRow] = reinterpret_cast<uint32_t (*)[32][kPlanRow]>(plan_smem);
+    uint32_t (*s_ev)[32][kPlanRow] = reinterpret_cast<uint32_t (*)[32][kPlanRow]>(plan_smem + (kPlanThreads / 32) * 32 * kPlanRow);
+    uint32_t *s_fi = plan_smem + 2 * (kPlanThreads / 32) * 32 * kPlanRow;       // [kPlanThreads][kPlanFiRow]
+    uint32_t *s_prog = s_fi + kPlanThreads * kPlanFiRow;   // the program of this cycle (slots resolved to absolute bit indices)
+    uint32_t *s_hot = s_prog + kPlanMaxInstr * 3;
+    uint32_t *s_grp = s_hot + kPlanMaxInstr;               // [0..31] instruction range, [32..63] operation word
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *n_act_next = 0;
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(prog);
+        for (int i = threadIdx.x; i < pa.n_instr * 3; i += blockDim.x) s_prog[i] = src[i];
+        for (int i = threadIdx.x; i < pa.n_instr; i += blockDim.x) s_hot[i] = hot[i];
+        if (threadIdx.x < 2 * kPlanMaxGroups) s_grp[threadIdx.x] = (threadIdx.x & (kPlanMaxGroups - 1)) < n_grp ? grp[threadIdx.x] : 0u;
+        __syncthreads();
+    }
+    const bool prob_mode = pa.noise == S17_NOISE_PROB;
+    const int fi_words = (pa.n_instr + 31) >> 5;
+    uint32_t gap_mask = 0;
+    for (int gi = 0; gi < n_grp; ++gi) gap_mask |= (s_grp[kPlanMaxGroups + gi] & 1u) << gi;
+    // persistent over groups of kPlanThreads shots: the program is staged once per CTA (no CTA-wide barrier below)
+    for (int base = blockIdx.x * kPlanThreads; base < pa.n_shots; base += gridDim.x * kPlanThreads) {
+    const int shot = base + threadIdx.x, shot0 = shot - lane;
+    if (sa.do_reset && shot < pa.n_shots) {
+        if (!sa.keep_leak) leak[shot] = 0;
+        reset_shot(shot, active, sa.ready, sa.rec);
+    }
+    bool act = shot < pa.n_shots && (sa.do_reset || active[shot]);
+    if (sa.do_record && act) {
+        const uint32_t x = sa.meas_out[2 * shot], z = sa.meas_out[2 * shot + 1];
+        record_measurement(sa.rec_ma, shot, (x | z) & 0xFFu, 8u * (uint32_t)sa.rec_ma.stage, ((x | z) & 0x100u) != 0, sa.lut, leak,
+                           active, sa.ready, sa.rec, sa.counters);
+        act = active[shot] != 0;                       // the protocol may have retired the shot (CL:321, 416, 86)
+    }
+    const uint32_t actmask = __ballot_sync(0xffffffffu, act);
+    if (!actmask) continue;
+    // the shots' slot bitsets: placed / replayed ones are loaded, eight rows in flight; sampled or placed here: start empty
+    const bool load_masks = !prob_mode && !pa.place && !pa.noiseless;
+#pragma unroll 1
+    for (int r0 = 0; r0 < 32; r0 += 8) {
+        uint32_t v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            v[k] = (load_masks && ((actmask >> (r0 + k)) & 1u)) ? masks[(size_t)(shot0 + r0 + k) * (2 * S17_MASK_WORDS) + lane] : 0u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s_mask[wib][r0 + k][lane] = v[k];
+    }
+    __syncwarp();
+    uint32_t *evs = s_ev[wib][lane];
+    uint32_t *mk = s_mask[wib][lane];                  // placed slots (subset / replay) or the slots fired now (prob mode)
+    uint32_t *fi = s_fi + threadIdx.x * kPlanFiRow;
+    uint32_t lk = 0;
+    Philox rng(pa.seed, pa.first_shot + shot, pa.stream);
+    uint32_t f_flip = 0, f_sign = 0, f_phase = 0, f_ancz = 0;   // frame bookkeeping of the current half cycle (k_cycle)
+    int f_half = -1;
+    if (act) lk = leak[shot];
+    bool any_event = lk != 0;
+    if (act && pa.noiseless && lk == 0) {
+        // noiseless preparation cycle without a leaked qubit: no event, no leak skip, identity frame
+        for (int i = 0; i < (int)S17_EV_WORDS; ++i) evs[i] = 0;
+        frm[(size_t)shot * 4] = 0;
+        frm[(size_t)shot * 4 + 1] = 0;
+    } else if (act) {
+    for (int i = 24; i < (int)S17_EV_WORDS; ++i) evs[i] = 0;
+    // ---- which entries fire ----
+    if (pa.place) place_errors(sa.nd, sa.cum, mk, pa.seed, pa.first_shot + shot);
+    if (prob_mode && !pa.noiseless) {
+        if (surv) {
+            int pos = 0;
+            const double s_end = surv[pa.n_instr];
+            for (;;) {
+                const double target = rng.next() * surv[pos];
+                if (!(s_end < target)) break;                        // nothing fires in the rest of the cycle
+                int lo = pos, hi = pa.n_instr - 1;                   // smallest i >= pos with S_{i+1} < target
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (surv[mid + 1] < target) hi = mid; else lo = mid + 1;
+                }
+                mask_set(mk, s_hot[lo] & 0xFFFFu);
+                pos = lo + 1;
+            }
+        } else {
+            for (int i = 0; i < pa.n_instr; ++i) {                   // one Bernoulli draw per entry (CS:198)
+                const uint32_t hw = s_hot[i];
+                if ((hw & 0x20000u) && rng.next() < probs[hw & 0xFFFFu]) mask_set(mk, hw & 0xFFFFu);
+            }
+        }
+    }
+    // fired slots -> fired instructions, the groups they sit in, whether one of them is a leakage entry
+    uint32_t flagged = 0, leak_event = 0;
+    for (int i = 0; i < fi_words; ++i) fi[i] = 0;
+    if (!pa.noiseless) {
+        for (int wi = 0; wi < (int)S17_MASK_WORDS; ++wi) {
+            uint32_t word = mk[wi];
+            while (word) {
+                const uint32_t ii = bit2instr[32 * wi + __ffs(word) - 1];
+                word &= word - 1;
+                if (ii == 0xFFFFu) continue;                         // a slot of the other cycle
+                const uint32_t hw = s_hot[ii];
+                flagged |= 1u << ((hw >> 18) & 31u);
+                leak_event |= (hw >> 23) & 1u;
+                fi[ii >> 5] |= 1u << (ii & 31u);
+            }
+        }
+    }
+    any_event = any_event || flagged != 0;
+    const bool walk = lk != 0 || leak_event != 0 || sa.walk_all;
+    const uint32_t todo = walk ? 0xFFFFFFFFu : flagged;
+    if (!walk) {
+        // ---- pass 1, usual case (no leaked qubit, no leakage entry): per operation with a fired entry, the fired
+        // instructions in program order, then the net Pauli of the operation.  Each lane runs over ITS OWN operations.
+        uint32_t td = flagged & ~gap_mask;
+        while (td) {
+            const int gi = __ffs(td) - 1;
+            td &= td - 1;
+            const uint32_t gm = s_grp[gi], g2 = s_grp[kPlanMaxGroups + gi];
+            const int first = (int)(gm & 1023u), last = (int)((gm >> 10) & 1023u);
+            uint32_t w = 0;
+            for (int wi = first >> 5; wi <= (last - 1) >> 5; ++wi) {
+                uint32_t bits = fi[wi];
+                if (wi == (first >> 5)) bits &= 0xFFFFFFFFu << (first & 31);
+                if (wi == ((last - 1) >> 5) && (last & 31)) bits &= 0xFFFFFFFFu >> (32 - (last & 31));
+                while (bits) {
+                    const int ii = 32 * wi + __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    const s17_pinstr in = reinterpret_cast<const s17_pinstr *>(s_prog)[ii];
+                    const uint32_t f = plan_apply_error((w >> in.field) & 63u, in, lk, rng);
+                    w = (w & ~(63u << in.field)) | (f << in.field);
+                }
+            }
+            evs[(g2 >> 1) & 31u] = plan_net_pauli(w, 0u, (g2 >> 14) & 1u, (g2 >> 15) & 1u, (g2 >> 13) & 1u, ((g2 >> 16) & 1u) ? 1 : -1);
+        }
+    } else {
+        // ---- pass 1, general case: every instruction of every group, in program order (one instruction per trip of a
+        // single loop).  Leaves the operation's event word (per-gate fields, skip bit, net Pauli) in evs[].
+        uint32_t td = todo & (n_grp >= 32 ? 0xFFFFFFFFu : ((1u << n_grp) - 1u)) & ~gap_mask;
+        int i = 0, end = 0;
+        uint32_t w = 0, skip = 0;
+        for (;;) {
+            if (i == end) {
+                if (!td) break;
+                const uint32_t gm = s_grp[__ffs(td) - 1];
+                td &= td - 1;
+                i = (int)(gm & 1023u);
+                end = (int)((gm >> 10) & 1023u);
+            }
+            const uint32_t hw = s_hot[i];
+            const int ii = i++;
+            if (hw & 0x20000u) {
+                // a fired entry acts unless it sits inside a skipped Rxx block (CS:293, 322).  The slot is the absolute index
+                // of the entry in this cycle (list offset + slot + half the list in a second cycle, CS:191-193).
+                if ((((hw >> 16) & 1u) & skip) || pa.noiseless) continue;
+                if (!mask_get(mk, hw & 0xFFFFu)) continue;
+            }
+            const s17_pinstr in = reinterpret_cast<const s17_pinstr *>(s_prog)[ii];
+            if (in.kind == S17_P_OP_BEGIN) { w = 0; skip = 0; continue; }
+            if (in.kind == S17_P_SKIP_TEST) {
+                // evaluated AFTER the errors of a preceding Ry (which may just have leaked the data qubit)
+                skip = ((lk >> in.a) | (lk >> in.b)) & 1u;
+                w |= skip << 24;
+                continue;
+            }
+            if (in.kind == S17_P_OP_END) {
+                evs[in.word] = plan_net_pauli(w, skip, in.a & 1, in.a & 2, in.a & 4, in.b ? 1 : -1);
+                continue;
+            }
+            const uint32_t f = plan_apply_error((w >> in.field) & 63u, in, lk, rng);
+            w = (w & ~(63u << in.field)) | (f << in.field);
+        }
+    }
+    // ---- pass 2: every group in program order (warp-uniform trip count): the net Pauli of each operation in the frame
+    // where its half cycle is diagonal (s17_diag.cuh) -- a data X relabels the basis (flip mask; bit 31 tells the
+    // operation whether its own label bit is flipped), a data Z is a label-dependent sign (sign mask), the rest is a
+    // global phase -- and the idle entries of the gaps (sympathetic_cooling, CS:762-772).
+    for (int gi = 0; gi < n_grp; ++gi) {
+        const uint32_t gm = s_grp[gi], g2 = s_grp[kPlanMaxGroups + gi];
+        const bool walked = (todo >> gi) & 1u;
+        if (g2 & 1u) {                                 // gap between two timesteps: its fired idle entries
+            if (!walked || pa.noiseless) continue;
+            for (int i = (int)(gm & 1023u); i < (int)((gm >> 10) & 1023u); ++i) {
+                const uint32_t hw = s_hot[i];
+                if (!mask_get(mk, hw & 0xFFFFu)) continue;
+                const s17_pinstr in = reinterpret_cast<const s17_pinstr *>(s_prog)[i];
+                evs[in.word] |= 1u << in.a;            // the 17-bit idle masks of the sweep kernels / k_half
+                if (in.b & 0x80u) {                    // the same Z in the frame of its half cycle (whole-cycle kernels)
+                    if (in.a < 9u) {
+                        const uint32_t bit = 1u << in.a;
+                        if (in.b & 2u) f_flip ^= bit;                                   // H Z H = X
+                        else if (in.b & 1u) { f_flip ^= bit; f_phase += 2u; }           // Ry(-pi/2) Z Ry(+pi/2) = -X
+                        else { f_sign ^= bit; f_phase += 2u * ((f_flip >> in.a) & 1u); }
+                    } else if (in.field != 255u) {
+                        f_ancz ^= 1u << in.field;      // Z on the ancilla after that operation (and its own events)
+                    }
+                }
+            }
+            continue;
+        }
+        const uint32_t word = (g2 >> 1) & 31u, d = (g2 >> 6) & 15u;
+        uint32_t w = walked ? evs[word] : 0u;
+        if ((g2 >> 10) & 1u) {                         // first operation of a half: close the previous one (idle events may
+            if (f_half >= 0)                           // follow its last operation), start from the identity frame
+                frm[(size_t)shot * 4 + f_half] = f_flip | (f_sign << 9) | ((f_phase & 3u) << 18) | (f_ancz << 20);
+            f_flip = 0; f_sign = 0; f_phase = 0; f_ancz = 0;
+            f_half = (int)((g2 >> 11) & 1u);
+        }
+        w |= ((f_flip >> d) & 1u) << 31;
+        const uint32_t N = (w >> 25) & 63u;
+        if (N) {
+            uint32_t F = N;
+            if ((g2 >> 12) & 1u) {                     // H X^x Z^z H = (-1)^{xz} X^z Z^x
+                const uint32_t x = N & 1u, z = (N >> 1) & 1u, k = (N >> 4) & 3u;
+                F = (N & 0x0Cu) | z | (x << 1) | (((k + 2u * (x & z)) & 3u) << 4);
+            } else if (!((g2 >> 13) & 1u)) {           // still inside the Ry bracket of its data qubit
+                F = pconj_ry(N, -1);
+            }
+            if (F & 2u) { f_sign ^= 1u << d; f_phase += 2u * ((f_flip >> d) & 1u); }
+            if (F & 1u) f_flip ^= 1u << d;
+            f_phase += (F >> 4) & 3u;
+        }
+        evs[word] = w;
+    }
+    if (f_half >= 0) frm[(size_t)shot * 4 + f_half] = f_flip | (f_sign << 9) | ((f_phase & 3u) << 18) | (f_ancz << 20);
+    leak[shot] = lk;
+    }
+    if (quiet && act) quiet[shot] = any_event ? 0 : 1;
+    __syncwarp();
+#pragma unroll 4
+    for (int r = 0; r < 32; ++r) {
+        if (!((actmask >> r) & 1u)) continue;
+        ev[(size_t)(shot0 + r) * S17_EV_WORDS + lane] = s_ev[wib][r][lane];
+        if (prob_mode || pa.place)
+            masks[(size_t)(shot0 + r) * (2 * S17_MASK_WORDS) + (pa.rec_half ? S17_MASK_WORDS : 0) + lane] = s_mask[wib][r][lane];
+    }
+    if (sa.do_compact) {
+        // the shots that take part in the cycle kernel's sweep.  Warp-aggregated atomic append: the order of the list
+        // is arbitrary (it only decides which warp processes which shot).
+        bool flag = act;
+        if (flag && quiet && !any_event && sa.quiet_ok[sa.leaf[shot]]) flag = false;          // k_quiet handles it
+        if (flag && sa.done && sa.skip_done && sa.done[shot]) flag = false;                    // the memoised preparation did
+        const uint32_t ballot = __ballot_sync(0xffffffffu, flag);
+        if (ballot) {
+            uint32_t pos = 0;
+            if (lane == 0) pos = atomicAdd(n_act, (uint32_t)__popc(ballot));
+            pos = __shfl_sync(0xffffffffu, pos, 0);
+            if (flag) {
+                uint32_t entry = (uint32_t)shot;
+                if (sa.leaf) entry |= (sa.done && !sa.done[shot]) ? 0x800000u : ((uint32_t)sa.leaf[shot] << 24);   // own state / cached leaf
+                sa.list[pos + __popc(ballot & ((1u << lane) - 1u))] = entry;
+            }
+        }
+    }
+    __syncwarp();                                      // the staging rows are reused by the next group
+    }
+}
+
 }  // namespace s17
 #include "s17_half.cuh"
 #include "s17_diag.cuh"
@@ -759,32 +871,6 @@ k_pauli(double2 *__restrict__ state, const s17_record *__restrict__ rec, const u
         const double s1 = (__popc(m0 & z) & 1) ? -g : g;
         s[m0] = make_double2(s0 * v1.x, s0 * v1.y);
         s[m1] = make_double2(s1 * v0.x, s1 * v0.y);
-    }
-}
-
-// list of the shots that still take part in gate sweeps (consumed by the persistent sweep kernels).  Warp-aggregated
-// atomic append: the order of the list is arbitrary (it only decides which CTA / warp processes which shot), *n_act
-// must be zero on entry (k_plan clears it).
-__global__ void __launch_bounds__(256)
-k_compact(const uint8_t *__restrict__ active, int n, uint32_t *__restrict__ list, uint32_t *__restrict__ n_act,
-          const uint8_t *__restrict__ leaf /* nullptr, or per shot: byte for bits 24-31 of its entry (k_cycle1 + prep cache) */,
-          const uint8_t *__restrict__ quiet, const uint8_t *__restrict__ quiet_ok /* nullptr, or: shots with quiet[i] and
-          quiet_ok[leaf[i]] are left out (k_quiet handles them) */,
-          const uint8_t *__restrict__ done /* nullptr, or per shot: 1 = the memoised preparation handled it */, int skip_done)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
-    bool flag = i < n && active[i];
-    if (flag && quiet && quiet[i] && quiet_ok[leaf[i]]) flag = false;
-    if (flag && done && skip_done && done[i]) flag = false;          // preparation stage: only the shots k_prep left
-    const uint32_t ballot = __ballot_sync(0xffffffffu, flag);
-    if (!ballot) return;
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(n_act, (uint32_t)__popc(ballot));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (flag) {
-        uint32_t entry = (uint32_t)i;
-        if (leaf) entry |= (done && !done[i]) ? 0x800000u : ((uint32_t)leaf[i] << 24);     // own state / cached leaf
-        list[base + __popc(ballot & ((1u << lane) - 1u))] = entry;
     }
 }
 
@@ -894,10 +980,17 @@ k_readout(ReadArgs ra, const double2 *__restrict__ state, size_t stride, const S
 // reading the corrected state gives d' ^ x-correction (a Pauli X relabels the computational basis).  One thread per
 // shot, no state traffic.
 __global__ void __launch_bounds__(256)
-k_readout_s(ReadArgs ra, const uint32_t *__restrict__ dsamp, const uint8_t *__restrict__ cw16, const uint32_t *__restrict__ leak,
-            const uint8_t *__restrict__ ready, s17_record *__restrict__ rec, unsigned long long *__restrict__ counters)
+k_readout_s(ReadArgs ra, const uint32_t *__restrict__ dsamp, const uint8_t *__restrict__ cw16, uint32_t *__restrict__ leak,
+            uint8_t *__restrict__ ready, s17_record *__restrict__ rec, unsigned long long *__restrict__ counters,
+            int do_record /* 1: first the bookkeeping of the cycle that just ended (k_record's body) */, MeasArgs rec_ma,
+            const uint32_t *__restrict__ meas_out, const uint32_t *__restrict__ lut, uint8_t *__restrict__ active)
 {
     const int shot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (do_record && shot < ra.n_shots && active[shot]) {
+        const uint32_t x = meas_out[2 * shot], z = meas_out[2 * shot + 1];
+        record_measurement(rec_ma, shot, (x | z) & 0xFFu, 8u * (uint32_t)rec_ma.stage, ((x | z) & 0x100u) != 0, lut, leak, active,
+                           ready, rec, counters);
+    }
     const bool live = shot < ra.n_shots && ready[shot];
     bool fail = false;
     if (live) {
@@ -928,19 +1021,27 @@ k_readout_s(ReadArgs ra, const uint32_t *__restrict__ dsamp, const uint8_t *__re
     }
 }
 
+// start of a call: fresh per-shot flags and records, and (fixed-weight noise, run-til-fail) the placement of the shot's
+// errors.  A plain s17_run folds both into k_plan: the reset into the preparation cycle's launch, the placement into the
+// first noisy cycle's.
 __global__ void k_reset(int n_shots, uint32_t *leak, uint8_t *active, uint8_t *ready, s17_record *rec, uint32_t *masks,
-                        int clear_masks, int keep_leak)
+                        int clear_masks, int keep_leak, int place, NoiseDev nd, const double *__restrict__ cum, uint64_t seed,
+                        uint64_t first_shot)
 {
     const int shot = blockIdx.x * blockDim.x + threadIdx.x;
     if (shot >= n_shots) return;
     if (!keep_leak) leak[shot] = 0;
-    active[shot] = 1;
-    ready[shot] = 0;
-    s17_record z;
-    memset(&z, 0, sizeof(z));
-    rec[shot] = z;
+    reset_shot(shot, active, ready, rec);
     if (clear_masks)
         for (int i = 0; i < 2 * (int)S17_MASK_WORDS; ++i) masks[(size_t)shot * 2 * S17_MASK_WORDS + i] = 0;
+    if (place) {
+        uint32_t m[S17_MASK_WORDS];
+#pragma unroll
+        for (int i = 0; i < (int)S17_MASK_WORDS; ++i) m[i] = 0;
+        place_errors(nd, cum, m, seed, first_shot + shot);
+#pragma unroll
+        for (int i = 0; i < (int)S17_MASK_WORDS; ++i) masks[(size_t)shot * (2 * S17_MASK_WORDS) + i] = m[i];
+    }
 }
 
 // run-til-fail bookkeeping (CL:52-127): one slot = one run in flight; a failed run frees its slot for the next run id.
@@ -1098,7 +1199,7 @@ struct s17_ctx {
     uint32_t *plan_hot = nullptr;
     // k_plan's group tables, per cycle variant (first / second cycle): group words, slot bit -> group, survival products
     uint32_t *plan_grp = nullptr;
-    uint8_t *plan_bit2grp = nullptr;
+    uint16_t *plan_bit2grp = nullptr;   // slot bit -> instruction index of its entry, per cycle variant
     double *plan_surv = nullptr;
     int n_grp[2] = {0, 0};
     bool geo_ok[2] = {false, false}, plan_dup_slot = false, no_geo = false;
@@ -1153,6 +1254,11 @@ struct s17_ctx {
     std::string debug_note;
     bool force_ring = false;          // option: use the TMA-ring kernel (k_layer2) for support-aware sweeps as well
     uint32_t *act_list = nullptr, *n_act = nullptr, *meas_out = nullptr;
+    uint32_t *n_act2 = nullptr;       // two list lengths used in turn: k_plan fills one and clears the other (n_act points at the current one)
+    uint32_t plan_seq = 0;
+    bool pend_reset = false;          // the per-shot reset of a call is still to be done: the preparation cycle's k_plan does it
+    bool pend_rec = false;            // the bookkeeping (k_record) of the last cycle is still to be applied: the next k_plan /
+    MeasArgs pend_ma;                 // k_readout_s does it, or flush_record
     int num_sms = 148;
     bool use_v1 = false;
     NoiseDev nd{};
@@ -1273,7 +1379,9 @@ extern "C" int s17_create(s17_ctx **out, int device, uint64_t max_shots) {
     CK(cudaFuncSetAttribute(k_layer3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kL3Smem));
     CK(cudaFuncSetAttribute(k_half, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kL3Smem));
     CK(cudaMalloc(&ctx->act_list, B * 4));
-    CK(cudaMalloc(&ctx->n_act, 4));
+    CK(cudaMalloc(&ctx->n_act2, 8));
+    CK(cudaMemset(ctx->n_act2, 0, 8));
+    ctx->n_act = ctx->n_act2;
     CK(cudaMalloc(&ctx->meas_out, B * 2 * 4));
     CK(cudaMalloc(&ctx->frm, B * 4 * 4));
     CK(cudaMalloc(&ctx->dsamp, B * 4));
@@ -1288,6 +1396,7 @@ extern "C" int s17_create(s17_ctx **out, int device, uint64_t max_shots) {
     CK(cudaMalloc(&ctx->quiet_flag, B));
     CK(cudaMemset(ctx->frm, 0, B * 4 * 4));
     CK(cudaFuncSetAttribute(k_cycle, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDgSmem));
+    CK(cudaFuncSetAttribute(k_plan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPlanSmem));
     CK(cudaFuncSetAttribute(k_cycle1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDgSmem1));
     CK(cudaFuncSetAttribute(k_cycle1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDgSmem1));
     {
@@ -1346,7 +1455,7 @@ extern "C" int s17_destroy(s17_ctx *ctx) {
     }
     void *ptrs[] = {ctx->state, ctx->ev, ctx->masks, ctx->leak, ctx->active, ctx->ready, ctx->forced, ctx->hist,
                     ctx->aux, ctx->rec, ctx->counters, ctx->lut, ctx->cw16, ctx->probs, ctx->cum, ctx->plan,
-                    ctx->rtf_slots, ctx->rtf_rounds, ctx->rtf_syndb, ctx->rtf_block_cnt, ctx->rtf_block_off, ctx->rtf_ticket, ctx->act_list, ctx->n_act, ctx->zero_page, ctx->meas_out,
+                    ctx->rtf_slots, ctx->rtf_rounds, ctx->rtf_syndb, ctx->rtf_block_cnt, ctx->rtf_block_off, ctx->rtf_ticket, ctx->act_list, ctx->n_act2, ctx->zero_page, ctx->meas_out,
                     ctx->frm, ctx->dsamp, ctx->prep_leaf, ctx->prep_done, ctx->prep_blocks, ctx->prep_pp, ctx->plan_hot,
                     ctx->plan_grp, ctx->plan_bit2grp, ctx->plan_surv,
                     ctx->quiet_blocks, ctx->quiet_cdf, ctx->quiet_ok, ctx->quiet_flag};
@@ -2032,14 +2141,11 @@ extern "C" int s17_load_program(s17_ctx *ctx, const s17_layer *layers, const uin
             hot[i] = entry ? ((uint32_t)res[i].slot | ((uint32_t)(res[i].in_skip ? 1u : 0u) << 16) | 0x20000u) : 0u;
         }
         if (ctx->plan) { cudaFree(ctx->plan); ctx->plan = nullptr; }
-        if (ctx->plan_hot) { cudaFree(ctx->plan_hot); ctx->plan_hot = nullptr; }
         CK(cudaMalloc(&ctx->plan, res.size() * sizeof(s17_pinstr)));
         CK(cudaMemcpy(ctx->plan, res.data(), res.size() * sizeof(s17_pinstr), cudaMemcpyHostToDevice));
-        CK(cudaMalloc(&ctx->plan_hot, hot.size() * 4));
-        CK(cudaMemcpy(ctx->plan_hot, hot.data(), hot.size() * 4, cudaMemcpyHostToDevice));
         // groups of the program (one entangling operation / the idle entries of one gap), in program order
         std::vector<uint32_t> grp(4 * kPlanMaxGroups, 0u);     // per variant: 32 instruction ranges, 32 operation words
-        std::vector<uint8_t> b2g(2 * 2048, 0xFFu);
+        std::vector<uint16_t> b2i(2 * 2048, 0xFFFFu);          // slot bit -> instruction of its entry (per variant)
         ctx->plan_dup_slot = false;
         for (int c2 = 0; c2 < 2; ++c2) {
             int ng = 0;
@@ -2052,7 +2158,8 @@ extern "C" int s17_load_program(s17_ctx *ctx, const s17_layer *layers, const uin
                     if (j == n_plan) return fail(ctx, S17_E_ARG, "plan: operation without an end");
                     const s17_pinstr &e = q[j];
                     meta = ((uint32_t)e.word << 1) | ((uint32_t)(plan[j].slot & 15u) << 6) | (((e.a >> 4) & 1u) << 10) |
-                           (((e.a >> 5) & 1u) << 11) | (((e.a >> 3) & 1u) << 12) | (((e.a >> 2) & 1u) << 13);
+                           (((e.a >> 5) & 1u) << 11) | (((e.a >> 3) & 1u) << 12) | (((e.a >> 2) & 1u) << 13) |
+                           ((e.a & 1u) << 14) | (((e.a >> 1) & 1u) << 15) | ((e.b ? 1u : 0u) << 16);
                     ++j;
                 } else if (q[i].kind == S17_P_IDLE) {
                     while (j < n_plan && q[j].kind == S17_P_IDLE && q[j].word == q[i].word) ++j;
@@ -2065,24 +2172,27 @@ extern "C" int s17_load_program(s17_ctx *ctx, const s17_layer *layers, const uin
                 grp[(size_t)(c2 * 2 + 1) * kPlanMaxGroups + ng] = meta;
                 for (uint32_t k = i; k < j; ++k)
                     if (q[k].kind == S17_P_ERR || q[k].kind == S17_P_IDLE) {
-                        uint8_t &slot = b2g[(size_t)c2 * 2048 + q[k].slot];
+                        uint16_t &slot = b2i[(size_t)c2 * 2048 + q[k].slot];
                         const bool lk_kind = q[k].kind == S17_P_ERR && (q[k].err == S17_ERR_LEAK_A || q[k].err == S17_ERR_LEAK_AB);
-                        if (slot != 0xFFu && (slot & 31u) != (uint32_t)ng) ctx->plan_dup_slot = true;   // one slot, two groups
-                        if (slot != 0xFFu) ctx->plan_dup_slot = true;
-                        slot = (uint8_t)((slot == 0xFFu ? 0u : (slot & 0x80u)) | (uint32_t)ng | (lk_kind ? 0x80u : 0u));
+                        if (slot != 0xFFFFu) ctx->plan_dup_slot = true;       // one slot, two entries: k_plan walks everything
+                        slot = (uint16_t)k;
+                        hot[(size_t)c2 * n_plan + k] |= ((uint32_t)ng << 18) | (lk_kind ? (1u << 23) : 0u);
                     }
                 ++ng;
                 i = j;
             }
             ctx->n_grp[c2] = ng;
         }
+        if (ctx->plan_hot) { cudaFree(ctx->plan_hot); ctx->plan_hot = nullptr; }
+        CK(cudaMalloc(&ctx->plan_hot, hot.size() * 4));
+        CK(cudaMemcpy(ctx->plan_hot, hot.data(), hot.size() * 4, cudaMemcpyHostToDevice));
         for (void *q : {(void *)ctx->plan_grp, (void *)ctx->plan_bit2grp, (void *)ctx->plan_surv})
             if (q) cudaFree(q);
         ctx->plan_grp = nullptr; ctx->plan_bit2grp = nullptr; ctx->plan_surv = nullptr;
         CK(cudaMalloc(&ctx->plan_grp, grp.size() * 4));
         CK(cudaMemcpy(ctx->plan_grp, grp.data(), grp.size() * 4, cudaMemcpyHostToDevice));
-        CK(cudaMalloc(&ctx->plan_bit2grp, b2g.size()));
-        CK(cudaMemcpy(ctx->plan_bit2grp, b2g.data(), b2g.size(), cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&ctx->plan_bit2grp, b2i.size() * 2));
+        CK(cudaMemcpy(ctx->plan_bit2grp, b2i.data(), b2i.size() * 2, cudaMemcpyHostToDevice));
         CK(cudaMalloc(&ctx->plan_surv, 2 * (size_t)(kPlanMaxInstr + 1) * sizeof(double)));
         ctx->plan_res = res;
         ctx->h_probs.assign(2048, 0.0);
@@ -2384,10 +2494,29 @@ static int build_prep_cache(s17_ctx *ctx, int basis) {
 // one stabiliser cycle: plan -> gate sweeps -> ancilla measurement decisions
 static void collapse(s17_ctx *ctx, int n, const uint8_t *flag);
 
+// the per-shot reset of a call, when its first kernel is not k_plan
+static void flush_reset(s17_ctx *ctx, int n) {
+    if (!ctx->pend_reset) return;
+    ctx->pend_reset = false;
+    SCOPE2(CAT_OTHER, S17_T_PLACE);
+    k_reset<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(n, ctx->leak, ctx->active, ctx->ready, ctx->rec, ctx->masks, 0, 0, 0, ctx->nd,
+                                                         ctx->cum, 0ull, 0ull);
+}
+
+// apply a deferred cycle bookkeeping now (something other than k_plan / k_readout_s is about to read the shot flags)
+static void flush_record(s17_ctx *ctx, int n) {
+    if (!ctx->pend_rec) return;
+    ctx->pend_rec = false;
+    SCOPE2(CAT_MEAS, S17_T_RECORD);
+    k_record<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(ctx->pend_ma, ctx->meas_out, ctx->lut, ctx->leak, ctx->active, ctx->ready,
+                                                          ctx->rec, ctx->counters);
+}
+
 static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second, int init_basis, uint32_t max_layers, bool dense,
                      bool mid_collapse) {
     const int n = (int)a.n_shots;
     if (stage == 0 && ctx->use_prep) {
+        flush_reset(ctx, n);
         // memoised noiseless preparation cycle: replay the kernel's decisions per shot, no state traffic
         MeasArgs ma;
         memset(&ma, 0, sizeof(ma));
@@ -2407,13 +2536,12 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
                                                                 ctx->prep_mixed ? ctx->leak : nullptr, ctx->prep_done);
         }
         if (!ctx->prep_mixed) {
-            SCOPE2(CAT_MEAS, S17_T_RECORD);
-            k_record<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(ma, ctx->meas_out, ctx->lut, ctx->leak, ctx->active,
-                                                                  ctx->ready, ctx->rec, ctx->counters);
+            ctx->pend_rec = true;          // applied by the next cycle's k_plan
+            ctx->pend_ma = ma;
             ctx->last_collapsed = true;
             return S17_OK;
         }
-        // mixed: the shots with a leak flag go through the regular preparation cycle below (k_compact lists only them)
+        // mixed: the shots with a leak flag go through the regular preparation cycle below (k_plan lists only them)
     }
     PlanArgs pa;
     pa.n_instr = ctx->n_plan;
@@ -2421,34 +2549,53 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
     pa.noiseless = (stage == 0);
     pa.second = second;
     pa.rec_half = (stage == 2) ? 1 : 0;
+    // fixed-weight noise: the placement (generate_error_locations, CL:151-181) is drawn where the first noisy cycle is
+    // planned; a run-til-fail job places once, when it begins (k_reset)
+    pa.place = (a.noise == S17_NOISE_SUBSET && stage == 1 && a.protocol != S17_PROTO_RTF) ? 1 : 0;
     pa.stream = 8u + (uint32_t)stage;
     pa.seed = a.seed;
     pa.first_shot = a.first_shot_id;
     pa.n_shots = n;
     {
+        StepArgs sa;
+        memset(&sa, 0, sizeof(sa));
+        sa.do_record = ctx->pend_rec ? 1 : 0;
+        if (ctx->pend_rec) sa.rec_ma = ctx->pend_ma;
+        ctx->pend_rec = false;
+        sa.meas_out = ctx->meas_out;
+        sa.lut = ctx->lut;
+        sa.ready = ctx->ready;
+        sa.rec = ctx->rec;
+        sa.counters = ctx->counters;
+        sa.do_compact = 1;
+        sa.list = ctx->act_list;
+        sa.leaf = (ctx->use_prep && stage == 1) ? ctx->prep_leaf : nullptr;
+        sa.quiet_ok = ctx->quiet_ok;
+        sa.done = (ctx->use_prep && stage <= 1) ? ctx->prep_done : nullptr;
+        sa.skip_done = stage == 0 ? 1 : 0;
+        sa.walk_all = ctx->plan_dup_slot ? 1 : 0;
+        sa.do_reset = ctx->pend_reset ? 1 : 0;
+        sa.keep_leak = 0;
+        ctx->pend_reset = false;
+        sa.nd = ctx->nd;
+        sa.cum = ctx->cum;
+        // the list length of this cycle is the counter the previous k_plan cleared; this one clears the other
+        ctx->n_act = ctx->n_act2 + (ctx->plan_seq & 1u);
+        uint32_t *n_next = ctx->n_act2 + ((ctx->plan_seq + 1u) & 1u);
+        ++ctx->plan_seq;
         SCOPE2(CAT_OTHER, S17_T_PLAN);
-        k_plan<<<std::min(blocks_for(n, kPlanThreads), ctx->num_sms * 5), kPlanThreads, 0, ctx->stream>>>(ctx->plan + (second ? ctx->n_plan : 0), pa, ctx->nd, ctx->probs, ctx->ev, ctx->masks,
-                                                            ctx->leak, ctx->active, ctx->frm, ctx->n_act,
-                                                                          ctx->plan_hot + (second ? ctx->n_plan : 0),
-                                                                          (ctx->use_quiet && stage == 1) ? ctx->quiet_flag : nullptr,
-                                                                          ctx->plan_grp + (second ? 2 * kPlanMaxGroups : 0), ctx->n_grp[second ? 1 : 0],
-                                                                          ctx->plan_bit2grp + (second ? 2048 : 0),
-                                                                          (a.noise == S17_NOISE_PROB && ctx->geo_ok[second ? 1 : 0])
-                                                                              ? ctx->plan_surv + (second ? kPlanMaxInstr + 1 : 0) : nullptr);
+        k_plan<<<std::min(blocks_for(n, kPlanThreads), ctx->num_sms * 4), kPlanThreads, kPlanSmem, ctx->stream>>>(
+            ctx->plan + (second ? ctx->n_plan : 0), pa, sa, ctx->probs, ctx->ev, ctx->masks, ctx->leak, ctx->active, ctx->frm,
+            ctx->n_act, n_next, ctx->plan_hot + (second ? ctx->n_plan : 0),
+            (ctx->use_quiet && stage == 1) ? ctx->quiet_flag : nullptr, ctx->plan_grp + (second ? 2 * kPlanMaxGroups : 0),
+            ctx->n_grp[second ? 1 : 0], ctx->plan_bit2grp + (second ? 2048 : 0),
+            (a.noise == S17_NOISE_PROB && ctx->geo_ok[second ? 1 : 0]) ? ctx->plan_surv + (second ? kPlanMaxInstr + 1 : 0) : nullptr);
     }
     const int which = stage == 0 ? 0 : (second ? 2 : 1);
     const std::vector<LayerArg> &Ls = ctx->layers[which];
     const std::vector<LayerArg2> &Ls2 = dense ? ctx->layers2d[which] : ctx->layers2[which];
     uint32_t nl = (uint32_t)Ls.size();
     if (max_layers && max_layers < nl) nl = max_layers;
-    {
-        SCOPE2(CAT_OTHER, S17_T_COMPACT);
-        k_compact<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(ctx->active, n, ctx->act_list, ctx->n_act,
-                                                               (ctx->use_prep && stage == 1) ? ctx->prep_leaf : nullptr,
-                                                               (ctx->use_quiet && stage == 1) ? ctx->quiet_flag : nullptr,
-                                                               ctx->quiet_ok, (ctx->use_prep && stage <= 1) ? ctx->prep_done : nullptr,
-                                                               stage == 0 ? 1 : 0);
-    }
     MeasArgs ma;
     memset(&ma, 0, sizeof(ma));
     ma.stage = stage;
@@ -2484,7 +2631,7 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
             ctx->n_gate++;
         }
         if (ctx->use_quiet && stage == 1) {
-            // the shots k_compact left out: no event in this cycle, memoised leaf.  meas_out still holds the leaf's
+            // the shots k_plan left out of the list: no event in this cycle, memoised leaf.  meas_out still holds the leaf's
             // outcomes (k_prep wrote them), which are this cycle's outcomes too.
             SCOPE(CAT_OTHER);
             k_quiet<<<blocks_for((uint64_t)n * 32, 128), 128, 0, ctx->stream>>>(
@@ -2492,11 +2639,10 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
                 ctx->quiet_cdf, ctx->forced, ctx->state, ctx->stride, ctx->meas_out, ctx->dsamp, ctx->counters,
                 (ctx->quiet_copy || a.forced) ? 1 : 0);
         }
-        {
-            SCOPE2(CAT_MEAS, S17_T_RECORD);
-            k_record<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(ma, ctx->meas_out, ctx->lut, ctx->leak, ctx->active,
-                                                                  ctx->ready, ctx->rec, ctx->counters);
-        }
+        // the cycle's bookkeeping (outcome log, leak override, protocol branch, decode) is applied per shot by whichever
+        // kernel touches the shots next: the next cycle's k_plan, k_readout_s, or flush_record
+        ctx->pend_rec = true;
+        ctx->pend_ma = ma;
         return S17_OK;
     }
     if (ctx->half_ok[which] && fused_ok) {
@@ -2585,24 +2731,30 @@ static int run_round(s17_ctx *ctx, const s17_run_args &a) {
         if (int rc = build_prep_cache(ctx, basis_index)) return rc;
     // an event-free first cycle of a shot that sits in a memoised preparation leaf is replayed from the cache as well
     ctx->use_quiet = ctx->use_prep && !ctx->no_quiet && ctx->any_quiet_leaf;
+    ctx->pend_rec = false;
     if (int rc = run_cycle(ctx, a, 0, 0, basis_index, 0, dense, explicit_collapse)) return rc;
-    if (explicit_collapse) collapse(ctx, n, ctx->active);
-    if (a.stop_stage == S17_STOP_AFTER_PREP) return S17_OK;
-    if (a.stop_stage == S17_STOP_CYCLE1_GATES)
-        return run_cycle(ctx, a, 1, 0, -1, a.stop_layers ? a.stop_layers : 1000, dense, explicit_collapse);
+    if (explicit_collapse) { flush_record(ctx, n); collapse(ctx, n, ctx->active); }
+    if (a.stop_stage == S17_STOP_AFTER_PREP) { flush_record(ctx, n); return S17_OK; }
+    if (a.stop_stage == S17_STOP_CYCLE1_GATES) {
+        const int rc = run_cycle(ctx, a, 1, 0, -1, a.stop_layers ? a.stop_layers : 1000, dense, explicit_collapse);
+        flush_record(ctx, n);
+        return rc;
+    }
     if (int rc = run_cycle(ctx, a, 1, 0, -1, 0, dense, explicit_collapse)) return rc;
     if (a.stop_stage == S17_STOP_AFTER_CYCLE1) {
+        flush_record(ctx, n);
         SCOPE(CAT_OTHER);
         cudaMemsetAsync(ctx->active, 1, n, ctx->stream);
         collapse(ctx, n, ctx->active);
         return S17_OK;
     }
     if (a.protocol == S17_PROTO_S2 || a.protocol == S17_PROTO_RTF) {
-        if (explicit_collapse) collapse(ctx, n, ctx->active);
+        if (explicit_collapse) { flush_record(ctx, n); collapse(ctx, n, ctx->active); }
         // s2: stab_ind=1 slots (CL:422); run-til-fail: cycle B reuses the stab_ind=0 probabilities (CL:92)
         if (int rc = run_cycle(ctx, a, 2, a.protocol == S17_PROTO_S2 ? 1 : 0, -1, 0, dense, explicit_collapse)) return rc;
     }
     if (a.materialize) {
+        flush_record(ctx, n);
         collapse(ctx, n, ctx->ready);
         SCOPE(CAT_OTHER);
         k_pauli<<<n * 32, 256, 0, ctx->stream>>>(ctx->state, ctx->rec, ctx->ready);
@@ -2616,10 +2768,14 @@ static int run_round(s17_ctx *ctx, const s17_run_args &a) {
     ra.first_shot = a.first_shot_id;
     ra.n_shots = n;
     if (ctx->use_dsamp) {
+        const int do_record = ctx->pend_rec ? 1 : 0;          // the last cycle's bookkeeping rides in the read-out kernel
+        ctx->pend_rec = false;
         SCOPE2(CAT_MEAS, S17_T_READOUT);
         k_readout_s<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(ra, ctx->dsamp, ctx->cw16, ctx->leak, ctx->ready, ctx->rec,
-                                                                 ctx->counters);
+                                                                 ctx->counters, do_record, ctx->pend_ma, ctx->meas_out, ctx->lut,
+                                                                 ctx->active);
     } else {
+        flush_record(ctx, n);
         SCOPE2(CAT_MEAS, S17_T_READOUT);
         k_readout<<<blocks_for((uint64_t)n * 32, 128), 128, 0, ctx->stream>>>(ra, ctx->state, ctx->stride, ctx->aux, ctx->forced, ctx->cw16,
                                                                           ctx->leak, ctx->ready, ctx->rec, ctx->counters);
@@ -2673,10 +2829,16 @@ static int begin_call(s17_ctx *ctx, const s17_run_args &a) {
     CK(cudaEventRecord(ctx->span0, ctx->stream));
     CK(cudaMemsetAsync(ctx->counters, 0, C_N * sizeof(unsigned long long), ctx->stream));
     const int n = (int)a.n_shots;
-    {
+    // a plain run starts with the preparation cycle's k_plan, which resets the shots itself (flush_reset when the memoised
+    // preparation runs instead); true-probability runs also clear both halves of the mask record (256 B per shot) and a
+    // run-til-fail job places its fixed-weight errors once: k_reset
+    ctx->pend_reset = a.protocol != S17_PROTO_RTF && a.noise != S17_NOISE_PROB;
+    if (!ctx->pend_reset) {
         SCOPE2(CAT_OTHER, S17_T_PLACE);
         k_reset<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(n, ctx->leak, ctx->active, ctx->ready, ctx->rec, ctx->masks,
-                                                             a.noise == S17_NOISE_PROB, 0);
+                                                             a.noise == S17_NOISE_PROB, 0,
+                                                             a.noise == S17_NOISE_SUBSET && a.protocol == S17_PROTO_RTF, ctx->nd,
+                                                             ctx->cum, a.seed, a.first_shot_id);
     }
     return S17_OK;
 }
@@ -2720,10 +2882,6 @@ extern "C" int s17_rtf_begin(s17_ctx *ctx, const s17_run_args *args) {
     if (a.noise == S17_NOISE_REPLAY || a.forced) return fail(ctx, S17_E_ARG, "s17_rtf_begin: run-til-fail samples its outcomes");
     if (int rc = begin_call(ctx, a)) return rc;
     const int n = (int)a.n_shots;
-    if (a.noise == S17_NOISE_SUBSET) {
-        SCOPE2(CAT_OTHER, S17_T_PLACE);
-        k_place<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(ctx->nd, ctx->cum, ctx->masks, a.seed, a.first_shot_id, n);
-    }
     if (ctx->rtf_capacity < a.rtf_runs) {
         if (ctx->rtf_rounds) cudaFree(ctx->rtf_rounds);
         if (ctx->rtf_syndb) cudaFree(ctx->rtf_syndb);
@@ -2813,11 +2971,6 @@ extern "C" int s17_run(s17_ctx *ctx, const s17_run_args *args, s17_counts *out) 
     }
     if (int rc = check_run_args(ctx, a)) return rc;
     if (int rc = begin_call(ctx, a)) return rc;
-    const int n = (int)a.n_shots;
-    if (a.noise == S17_NOISE_SUBSET) {
-        SCOPE2(CAT_OTHER, S17_T_PLACE);
-        k_place<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(ctx->nd, ctx->cum, ctx->masks, a.seed, a.first_shot_id, n);
-    }
     if (int rc = run_round(ctx, a)) return rc;
     if (int rc = finish_timing(ctx)) return rc;
     return end_call(ctx, a, out);

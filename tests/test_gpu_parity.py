@@ -504,9 +504,10 @@ def test_run_til_fail_sweep_example():
 
 def test_driver_batch_shrinks_when_full_states_do_not_fit(correction_table, bitflip_table, monkeypatch):
     """The drop-in drivers default to a batch sized for the whole-cycle kernel (8 KiB per shot).  A program that needs
-    full 2 MiB states (here: coherent over-rotations) makes the first allocation fail; the driver shrinks the batch and
-    carries on instead of surfacing the error."""
+    full 2 MiB states (here: coherent over-rotations kept on the sweep kernels, S17_COH=0) makes the first allocation
+    fail; the driver shrinks the batch and carries on instead of surfacing the error."""
     import surface_17_iqt_b200.calc_log_e_rate_arbitrary_error_model as drv
+    monkeypatch.setenv("S17_COH", "0")
     monkeypatch.setattr(drv, "BATCH_SHOTS", 262144)
     monkeypatch.setattr(drv, "VERBOSE", False)
     drv.release()
