@@ -196,7 +196,7 @@ int s17_load_program(s17_ctx *ctx, const s17_layer *layers, const uint32_t n_lay
 typedef struct {
     uint32_t n_sweeps[3];
     uint8_t half_kernel[3];         /* 1: the fused half-cycle kernel (k_half) applies */
-    uint8_t cycle_kernel[3];        /* 1: the whole-cycle diagonal-frame kernel (k_cycle) applies */
+    uint8_t cycle_kernel[3];        /* 1: the cycle has the Clifford diagonal-frame form (tables of Gaussian integers) */
     uint8_t cycle_kernel_maps[3];   /* 1: label maps with one register bit per ancilla slot exist (k_cycle1) */
     uint8_t shuffle_bit[3];         /* data bit transformed by the shuffle stage of the Walsh-Hadamard transform */
     uint8_t reg_bits_z[3][4];       /* data bits carried by the register index in the computational frame; slot k uses [k] */

@@ -177,14 +177,14 @@ def compile_program(model, list_len, fusion=1, cooling=False, over_angles=None, 
     (tracer.trace_cycle); default: this module's table (build_cycle) and rule (slot_index).
 
     fusion: 0 = one sweep per gate (ProjectQ's execution model), 1 = one sweep per timestep,
-            2 = one sweep per two timesteps, 4 = one sweep per four timesteps (8192-amplitude tiles).
+            2 = one sweep per two timesteps (the form the half-cycle and whole-cycle kernels are lowered from).
     over_angles: {prob_name: [angles]} for the coherent ``*_over`` entries (extension, SURVEY C-10).
     early_measure: measure the four X-type ancillas right after timestep 4 (no later gate touches them, so
             this commutes with the rest of the cycle: same joint outcome statistics and the same collapsed
             state up to a global sign) -- the Z-type half of the cycle then runs on a 2^13-amplitude support.
     """
-    if fusion not in (0, 1, 2, 4):
-        raise ValueError("fusion must be 0, 1, 2 or 4")
+    if fusion not in (0, 1, 2):
+        raise ValueError("fusion must be 0, 1 or 2")
     names = list(model["probabilities"])
     if len(names) != len(list_len):
         raise ValueError("make sure you pass enough probabilities to specify the error model - see error_model.json")

@@ -2,9 +2,10 @@
 //
 // Reference behaviour being replaced (citations: CS = compiled_surface_code_arbitrary_error_model.py,
 // CL = calc_log_e_rate_arbitrary_error_model.py of Alexowens94/Surface_17_IQT):
-//   k_layer    : the Rxx/Rx/Ry gate stream of stabiliser_timestep_1..8 (CS:365-650) plus the Pauli
+//   k_layer2/3 : the Rxx/Rx/Ry gate stream of stabiliser_timestep_1..8 (CS:365-650) plus the Pauli
 //                gates insert_error applies (CS:198-217), ProjectQ's per-gate sweeps fused per layer
-//   k_place    : generate_error_locations / _non_uniform (CL:151-181)
+//   k_half, k_cycle1 : the same per half cycle / per whole cycle, with the measurements
+//   place_errors : generate_error_locations / _non_uniform (CL:151-181)
 //   k_plan     : insert_errors / insert_error / insert_2q_error / insert_leakage decision logic
 //                (CS:127-288) and the leak skip predicate (CS:293, 322), one thread per shot
 //   k_measure  : All(Measure) | ancilla, leak override, reset decision (CS:848-862) and the
@@ -27,189 +28,12 @@
 #include "s17_kernels.cuh"
 #include "s17_layer2.cuh"
 #include "s17_layer3.cuh"
-#include "s17_layer4.cuh"
 #include "s17_engine.cuh"
 
 namespace s17 {
 
 enum { C_FAILED = 0, C_NOT0 = 1, C_COUNTED = 2, C_ERRORS = 3, C_SWEEPS = 4, C_ROUNDS = 5, C_NEXT_RUN = 6, C_ALIVE = 7,
        C_RUNS_MOVED = 8, C_RUNS_DONE = 9, C_COLLAPSED = 10, C_N = 11 };
-
-// =================================================================================================
-// gate sweep
-// =================================================================================================
-
-__global__ void __launch_bounds__(kLayerThreads, 3)
-k_layer(double2 *__restrict__ state, const __grid_constant__ LayerArg A, const uint32_t *__restrict__ ev,
-        const uint8_t *__restrict__ active, double *__restrict__ hist, unsigned long long *__restrict__ counters,
-        int init_basis)
-{
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    double2 *tile = reinterpret_cast<double2 *>(smem_raw);
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ uint32_t s_ev[S17_EV_WORDS];
-
-    const int shot = blockIdx.x / kTilesPerShot;
-    const int tile_id = blockIdx.x % kTilesPerShot;
-    if (!active[shot]) return;
-    const int t = threadIdx.x;
-
-    uint32_t base = 0;
-#pragma unroll
-    for (int k = 0; k < 5; ++k) base |= ((tile_id >> k) & 1u) << A.other_bits[k];
-    uint32_t run_off[8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        uint32_t g = base;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) g |= ((r >> k) & 1u) << A.L.anc_bits[k];
-        run_off[r] = g;
-    }
-    double2 *sbase = state + (size_t)shot * kDim;
-
-    if (t < (int)S17_EV_WORDS) s_ev[t] = ev[(size_t)shot * S17_EV_WORDS + t];
-    if (init_basis < 0) {
-        if (t == 0) {
-            mbar_init(&bar, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncthreads();
-        if (t == 0) {
-            mbar_expect_tx(&bar, kTile * 16);
-#pragma unroll
-            for (int r = 0; r < 8; ++r) tma_load_1d(tile + r * kRun, sbase + run_off[r], kRunBytes, &bar);
-        }
-        mbar_wait(&bar, 0);
-    } else {
-        // first sweep of a shot: synthesise the computational basis state instead of reading HBM
-#pragma unroll
-        for (int i = 0; i < kTile / kLayerThreads; ++i) tile[t + kLayerThreads * i] = make_double2(0.0, 0.0);
-        __syncthreads();
-        if (tile_id == 0 && t == 0) tile[init_basis] = make_double2(1.0, 0.0);
-        __syncthreads();
-    }
-
-    // how many 1/sqrt(2) factors this shot really picks up in this layer, and which op applies them
-    int nsc = 0, last_ent = -1;
-    for (int o = 0; o < A.L.n_ops; ++o) {
-        const s17_op &op = A.L.ops[o];
-        if (op.kind != S17_OP_ENT) continue;
-        last_ent = o;
-        const uint32_t skip = (s_ev[op.ev_word] >> 24) & 1u;
-        for (int u = 0; u < op.n_uops; ++u) {
-            const s17_uop up = op.uops[u];
-            if (up.type <= S17_U_H && !(up.skippable && skip)) ++nsc;
-        }
-    }
-    const double scale = ldexp((nsc & 1) ? 0.70710678118654752440 : 1.0, -(nsc >> 1));
-
-    for (int o = 0; o < A.L.n_ops; ++o) {
-        const s17_op &op = A.L.ops[o];
-        if (op.kind == S17_OP_IDLE) {
-            // Z on every qubit whose bit is set in the 17-bit idle mask (sympathetic_cooling, CS:762-772)
-            const uint32_t zm = s_ev[op.ev_word];
-            if (zm) {
-                uint32_t lm = zm & 0x1FFu;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) lm |= ((zm >> A.L.anc_bits[k]) & 1u) << (9 + k);
-                const uint32_t c0 = __popc(base & zm) & 1u;
-#pragma unroll 4
-                for (int i = 0; i < kTile / kLayerThreads; ++i) {
-                    const int l = t + kLayerThreads * i;
-                    if ((__popc(l & lm) & 1u) ^ c0) {
-                        double2 v = tile[l];
-                        tile[l] = make_double2(-v.x, -v.y);
-                    }
-                }
-                __syncthreads();
-            }
-            continue;
-        }
-        const uint32_t w = s_ev[op.ev_word];
-        const uint32_t skip = (w >> 24) & 1u;
-        const int lb0 = op.data_bit;
-        int lb1 = 9;
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-            if (A.L.anc_bits[k] == op.anc_bit) lb1 = 9 + k;
-        const int m0 = 1 << lb0, m1 = 1 << lb1;
-        const bool do_scale = (o == last_ent) && (nsc != 0);
-
-#pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
-            int idx[2];
-            double2 a[2][4];
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int item = t + kLayerThreads * (pass * 2 + i);
-                idx[i] = insert0(insert0(item, lb0), lb1);
-                a[i][0] = tile[idx[i]];
-                a[i][1] = tile[idx[i] | m0];
-                a[i][2] = tile[idx[i] | m1];
-                a[i][3] = tile[idx[i] | m0 | m1];
-            }
-            for (int u = 0; u < op.n_uops; ++u) {
-                const s17_uop up = op.uops[u];
-                if (up.skippable && skip) continue;
-                const double sg = (double)up.sign;
-                switch (up.type) {
-                case S17_U_RY:  g_ry(a[0], sg);  g_ry(a[1], sg);  break;
-                case S17_U_RXX: g_rxx(a[0], sg); g_rxx(a[1], sg); break;
-                case S17_U_RX:  g_rx(a[0], sg);  g_rx(a[1], sg);  break;
-                case S17_U_H:   g_h(a[0]);       g_h(a[1]);       break;
-                case S17_U_ROT_X:  { const double2 p = A.prm[up.param]; g_rot_x(a[0], p.x, p.y);  g_rot_x(a[1], p.x, p.y);  } break;
-                case S17_U_ROT_Y:  { const double2 p = A.prm[up.param]; g_rot_y(a[0], p.x, p.y);  g_rot_y(a[1], p.x, p.y);  } break;
-                case S17_U_ROT_XX: { const double2 p = A.prm[up.param]; g_rot_xx(a[0], p.x, p.y); g_rot_xx(a[1], p.x, p.y); } break;
-                default: break;
-                }
-                if (up.ev_shift != 255) {
-                    const uint32_t f = (w >> up.ev_shift) & 63u;
-                    if (f) { g_pauli(a[0], f); g_pauli(a[1], f); }
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                if (do_scale) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) { a[i][q].x *= scale; a[i][q].y *= scale; }
-                }
-                tile[idx[i]] = a[i][0];
-                tile[idx[i] | m0] = a[i][1];
-                tile[idx[i] | m1] = a[i][2];
-                tile[idx[i] | m0 | m1] = a[i][3];
-            }
-        }
-        __syncthreads();
-    }
-
-    if (A.L.meas_mask) {
-        // joint ancilla histogram: warp w owns run w (one ancilla value, all 512 data amplitudes)
-        const int wid = t >> 5, lane = t & 31;
-        double acc = 0.0;
-#pragma unroll
-        for (int i = 0; i < kRun / 32; ++i) {
-            const double2 v = tile[wid * kRun + lane + 32 * i];
-            acc = fma(v.x, v.x, fma(v.y, v.y, acc));
-        }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-        if (lane == 0) {
-            uint32_t g = base;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) g |= ((wid >> k) & 1u) << A.L.anc_bits[k];
-            hist[(size_t)shot * 256 + (g >> 9)] = acc;
-        }
-    }
-
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (t == 0) {
-#pragma unroll
-        for (int r = 0; r < 8; ++r) tma_store_1d(sbase + run_off[r], tile + r * kRun, kRunBytes);
-        tma_store_commit_and_wait_read();
-        if (tile_id == 0) atomicAdd(&counters[C_SWEEPS], 1ull);
-    }
-}
 
 // =================================================================================================
 // error placement + per-shot event planning
@@ -1230,7 +1054,6 @@ struct s17_ctx {
     DiagCoh diag_coh[3];              // coherent over-rotations of a cycle that runs on k_cycle1<true>
     bool coh_ok[3] = {false, false, false};
     bool no_coh = false;              // S17_COH=0: coherent models keep the sweep kernels
-    bool no_diag1 = false;
     bool no_diag = false;
     bool last_collapsed = true;       // the previous cycle left every active shot collapsed to ancilla block 0
     uint32_t *frm = nullptr;          // per shot: frame words of the two half cycles (k_plan -> k_cycle)
@@ -1260,7 +1083,6 @@ struct s17_ctx {
     bool pend_rec = false;            // the bookkeeping (k_record) of the last cycle is still to be applied: the next k_plan /
     MeasArgs pend_ma;                 // k_readout_s does it, or flush_record
     int num_sms = 148;
-    bool use_v1 = false;
     NoiseDev nd{};
     uint32_t total_slots = 0;
     bool have_program = false, have_tables = false, have_replay = false;
@@ -1373,9 +1195,7 @@ extern "C" int s17_create(s17_ctx **out, int device, uint64_t max_shots) {
         if (mask & 32) CK(cudaMemset(ctx->aux, byte, B * sizeof(ShotAux)));
         if (mask & 64) CK(cudaMemset(ctx->rec, byte, B * sizeof(s17_record)));
     }
-    CK(cudaFuncSetAttribute(k_layer, cudaFuncAttributeMaxDynamicSharedMemorySize, kTile * 16));
     CK(cudaFuncSetAttribute(k_layer2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kL2Smem));
-    CK(cudaFuncSetAttribute(k_layer4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kL4Smem));
     CK(cudaFuncSetAttribute(k_layer3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kL3Smem));
     CK(cudaFuncSetAttribute(k_half, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kL3Smem));
     CK(cudaMalloc(&ctx->act_list, B * 4));
@@ -1395,7 +1215,6 @@ extern "C" int s17_create(s17_ctx **out, int device, uint64_t max_shots) {
     CK(cudaMemset(ctx->quiet_ok, 0, 256));
     CK(cudaMalloc(&ctx->quiet_flag, B));
     CK(cudaMemset(ctx->frm, 0, B * 4 * 4));
-    CK(cudaFuncSetAttribute(k_cycle, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDgSmem));
     CK(cudaFuncSetAttribute(k_plan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPlanSmem));
     CK(cudaFuncSetAttribute(k_cycle1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDgSmem1));
     CK(cudaFuncSetAttribute(k_cycle1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDgSmem1));
@@ -1419,8 +1238,7 @@ extern "C" int s17_create(s17_ctx **out, int device, uint64_t max_shots) {
         const char *nf = getenv("S17_FUSE");
         ctx->no_fuse = nf && nf[0] == '0';
         const char *nd = getenv("S17_DIAG");
-        ctx->no_diag = nd && nd[0] == '0';          // 0: k_half everywhere; g: generic k_cycle only; default: k_cycle1 if possible
-        ctx->no_diag1 = nd && nd[0] == 'g';
+        ctx->no_diag = nd && nd[0] == '0';          // 0: k_half / the sweep kernels instead of the whole-cycle kernel
         const char *pc = getenv("S17_PREP_CACHE");
         ctx->no_prep_cache = pc && pc[0] == '0';
         const char *qc = getenv("S17_QUIET");            // 0: run event-free first cycles through k_cycle1 like any other
@@ -1436,8 +1254,6 @@ extern "C" int s17_create(s17_ctx **out, int device, uint64_t max_shots) {
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, device));
         ctx->num_sms = prop.multiProcessorCount;
-        const char *v1 = getenv("S17_LAYER_V1");
-        ctx->use_v1 = v1 && v1[0] == '1';
     }
     CK(cudaEventCreate(&ctx->span0));
     CK(cudaEventCreate(&ctx->span1));
@@ -1468,8 +1284,8 @@ extern "C" int s17_destroy(s17_ctx *ctx) {
 }
 
 static int check_layer(s17_ctx *ctx, const s17_layer &L) {
-    if (L.n_anc != 3 && L.n_anc != 4) return fail(ctx, S17_E_ARG, "layer must stage 3 or 4 ancilla bits");
-    if (L.n_ops > (L.n_anc == 4 ? 16 : 8)) return fail(ctx, S17_E_ARG, "too many ops in one layer");
+    if (L.n_anc != 3) return fail(ctx, S17_E_ARG, "a sweep stages three ancilla bits (at most two timesteps per sweep)");
+    if (L.n_ops > 8) return fail(ctx, S17_E_ARG, "too many ops in one layer");
     for (int k = 0; k < L.n_anc; ++k)
         if (L.anc_bits[k] < 9 || L.anc_bits[k] > 16 || (k && L.anc_bits[k] <= L.anc_bits[k - 1]))
             return fail(ctx, S17_E_ARG, "layer anc_bits must be ascending ancilla bits in 9..16");
@@ -2604,8 +2420,8 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
     ma.seed = a.seed;
     ma.first_shot = a.first_shot_id;
     ma.n_shots = n;
-    const bool fused_ok = !dense && !mid_collapse && !max_layers && !ctx->use_v1 && !ctx->force_ring && !ctx->no_fuse;
-    if ((ctx->diag_ok[which] || (ctx->coh_ok[which] && !ctx->no_diag1)) && fused_ok && !ctx->no_diag) {
+    const bool fused_ok = !dense && !mid_collapse && !max_layers && !ctx->force_ring && !ctx->no_fuse;
+    if (ctx->diag1_ok[which] && fused_ok && !ctx->no_diag) {
         if (init_basis < 0 && !ctx->last_collapsed) collapse(ctx, n, ctx->active);     // k_cycle reads the block at ancilla value 0
         ctx->last_collapsed = true;
         // production path for Clifford cycles with Pauli / leakage noise: the whole cycle in the frame where it is
@@ -2620,14 +2436,9 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
         ma.data_stream = 32u;
         {
             SCOPE(CAT_GATE);
-            if (ctx->diag1_ok[which] && !ctx->no_diag1)
-                launch_cycle1(ctx, which, ma, ctx->state, ctx->stride, ctx->ev, ctx->frm, ctx->act_list, ctx->n_act, ctx->aux,
-                              ctx->forced, ctx->meas_out, ctx->dsamp, ctx->counters, init_basis,
-                              (ctx->use_prep && stage == 1) ? ctx->prep_blocks : nullptr, nullptr, nullptr);
-            else
-                k_cycle<<<ctx->num_sms, kDgThreads, kDgSmem, ctx->stream>>>(
-                    ctx->diag_prog[which], ma, ctx->state, ctx->stride, ctx->ev, ctx->frm, ctx->act_list, ctx->n_act, ctx->aux,
-                    ctx->forced, ctx->meas_out, ctx->counters, init_basis);
+            launch_cycle1(ctx, which, ma, ctx->state, ctx->stride, ctx->ev, ctx->frm, ctx->act_list, ctx->n_act, ctx->aux,
+                          ctx->forced, ctx->meas_out, ctx->dsamp, ctx->counters, init_basis,
+                          (ctx->use_prep && stage == 1) ? ctx->prep_blocks : nullptr, nullptr, nullptr);
             ctx->n_gate++;
         }
         if (ctx->use_quiet && stage == 1) {
@@ -2671,14 +2482,7 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
     for (uint32_t i = 0; i < nl; ++i) {
         {
             SCOPE(CAT_GATE);
-            if (Ls[i].L.n_anc == 4)
-                k_layer4<<<ctx->num_sms, kL4Threads, kL4Smem, ctx->stream>>>(
-                    ctx->state, Ls2[i], ctx->ev, ctx->act_list, ctx->n_act, ctx->hist, ctx->counters, ctx->aux,
-                    (i == 0) ? init_basis : -1);
-            else if (ctx->use_v1)
-                k_layer<<<n * kTilesPerShot, kLayerThreads, kTile * 16, ctx->stream>>>(
-                    ctx->state, Ls[i], ctx->ev, ctx->active, ctx->hist, ctx->counters, (i == 0) ? init_basis : -1);
-            else if (!dense && !ctx->force_ring)
+            if (!dense && !ctx->force_ring)
                 k_layer3<<<ctx->num_sms * kL3CtasPerSm, kL3Threads, kL3Smem, ctx->stream>>>(
                     ctx->tmap, Ls2[i], ctx->ev, ctx->act_list, ctx->n_act, ctx->hist, ctx->counters, ctx->aux,
                     (i == 0) ? init_basis : -1);
@@ -2717,15 +2521,15 @@ static int run_round(s17_ctx *ctx, const s17_run_args &a) {
     // dense: every sweep covers the full state and ProjectQ's collapse is materialised after each measurement.
     // otherwise the collapse + reset is lazy: the next sweep reads the surviving block, scaled, and sweeps only
     // cover the part of the state that can be non-zero.
-    const bool dense = ctx->dense || ctx->use_v1;
+    const bool dense = ctx->dense;
     const bool explicit_collapse = dense || a.materialize || a.stop_stage != S17_STOP_NONE;
     // both noisy cycles go through k_cycle1 and outcomes are sampled: the cycle kernel also draws the data read-out
-    ctx->use_dsamp = ctx->diag1_ok[1] && ctx->diag1_ok[2] && !ctx->no_diag1 && !ctx->no_diag && !explicit_collapse &&
-                     !ctx->use_v1 && !ctx->force_ring && !ctx->no_fuse && !a.forced;
+    ctx->use_dsamp = ctx->diag1_ok[1] && ctx->diag1_ok[2] && !ctx->no_diag && !explicit_collapse &&
+                     !ctx->force_ring && !ctx->no_fuse && !a.forced;
     // the noiseless preparation cycle is memoised when it and the first noisy cycle run on k_cycle1; where a leak flag can
     // be set when it starts (run-til-fail keeps leak flags across the rounds of a run) only for the shots without one
-    ctx->use_prep = ctx->diag1_ok[0] && ctx->diag1_ok[1] && !ctx->no_diag1 && !ctx->no_diag && !explicit_collapse &&
-                    !ctx->use_v1 && !ctx->force_ring && !ctx->no_fuse && !ctx->no_prep_cache && ctx->max_shots < (1u << 23);
+    ctx->use_prep = ctx->diag1_ok[0] && ctx->diag1_ok[1] && !ctx->no_diag && !explicit_collapse &&
+                    !ctx->force_ring && !ctx->no_fuse && !ctx->no_prep_cache && ctx->max_shots < (1u << 23);
     ctx->prep_mixed = ctx->use_prep && a.protocol == S17_PROTO_RTF && ctx->plan_has_leak;
     if (ctx->use_prep)
         if (int rc = build_prep_cache(ctx, basis_index)) return rc;
@@ -2821,9 +2625,8 @@ static int begin_call(s17_ctx *ctx, const s17_run_args &a) {
     ctx->n_gate = ctx->n_all = 0;
     ctx->launches.clear();
     ctx->ev_used = 0;
-    auto cyc_ok = [&](int c) { return ctx->diag_ok[c] || (ctx->coh_ok[c] && !ctx->no_diag1); };
-    const bool all_diag = cyc_ok(0) && cyc_ok(1) && cyc_ok(2) && !ctx->no_diag && !ctx->dense &&
-                          !ctx->use_v1 && !ctx->force_ring && !ctx->no_fuse && !a.materialize &&
+    const bool all_diag = ctx->diag1_ok[0] && ctx->diag1_ok[1] && ctx->diag1_ok[2] && !ctx->no_diag && !ctx->dense &&
+                          !ctx->force_ring && !ctx->no_fuse && !a.materialize &&
                           a.stop_stage == S17_STOP_NONE;
     if (int rc = ensure_state(ctx, !all_diag)) return rc;
     CK(cudaEventRecord(ctx->span0, ctx->stream));

@@ -109,14 +109,6 @@ struct DiagCoh {
 __device__ __forceinline__ double2 dg_cmul(const double2 a, const double2 b) {
     return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
 }
-// label of register i of this lane.  map 1: x = lane | i << 5 (as loaded / stored);  map 2: x = i | lane << 4
-template <int MAP>
-__device__ __forceinline__ uint32_t dg_label(int lane, int i) {
-    return MAP == 1 ? (uint32_t)(lane | (i << 5)) : (uint32_t)(i | (lane << 4));
-}
-// exchange layout: 16-byte column = low three label bits ^ bits 4-6, conflict-free for both mappings
-__device__ __forceinline__ int dg_swz(uint32_t x) { return (int)(x ^ ((x >> 4) & 7u)); }
-
 __device__ __forceinline__ void dg_wht16(double2 (&p)[16]) {
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
@@ -129,37 +121,6 @@ __device__ __forceinline__ void dg_wht16(double2 (&p)[16]) {
         }
     }
 }
-__device__ __forceinline__ void dg_wht_lane4(double2 (&p)[16], int lane) {
-    const double sg = (lane & 16) ? -1.0 : 1.0;      // upper half of the butterfly: partner - mine
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const double ox = __shfl_xor_sync(0xffffffffu, p[i].x, 16), oy = __shfl_xor_sync(0xffffffffu, p[i].y, 16);
-        p[i] = make_double2(fma(sg, p[i].x, ox), fma(sg, p[i].y, oy));
-    }
-}
-// label bits 5-8 and 4 (map 1), exchange, label bits 0-3 (map 2)
-__device__ __forceinline__ void dg_wht_forward(double2 (&p)[16], double2 *xb, int lane) {
-    dg_wht16(p);
-    dg_wht_lane4(p, lane);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) xb[dg_swz(dg_label<1>(lane, i))] = p[i];
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 16; ++i) p[i] = xb[dg_swz(dg_label<2>(lane, i))];
-    dg_wht16(p);
-}
-__device__ __forceinline__ void dg_wht_inverse(double2 (&p)[16], double2 *xb, int lane) {
-    dg_wht16(p);
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 16; ++i) xb[dg_swz(dg_label<2>(lane, i))] = p[i];
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 16; ++i) p[i] = xb[dg_swz(dg_label<1>(lane, i))];
-    dg_wht_lane4(p, lane);
-    dg_wht16(p);
-}
-
 // label bits a lane carries under a map
 __device__ __forceinline__ uint32_t lane_label(const DiagMap &M, int lane) {
     uint32_t l = 0;
@@ -210,193 +171,6 @@ __device__ __forceinline__ void dg_build_tables(const DiagHalf &H, const uint32_
         tab[e] = a0;
         tab[e + kDgTabEntries] = a1;
         tab[e + 2 * kDgTabEntries] = make_double2(fma(a0.x, a0.x, a0.y * a0.y), fma(a1.x, a1.x, a1.y * a1.y));
-    }
-}
-
-// one ancilla slot: P(0), P(1) from the table of squared moduli, one Measure, multiply by the selected amplitudes.
-// tk: this lane's base into the tables of the slot (A0 at +0, A1 at +16 kDgTabEntries, Q at +32 kDgTabEntries);
-// roff: register-index part of the table offsets (kernel parameter space, warp-uniform)
-__device__ __forceinline__ void dg_slot(double2 (&p)[16], const uint32_t *roff, uint32_t aj, const unsigned char *tk,
-                                        bool forced, uint32_t fo, double u, uint32_t &a_out, bool &bad, double &pfin) {
-    double p0 = 0.0, p1 = 0.0;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const double2 q = *reinterpret_cast<const double2 *>(tk + 32 * kDgTabEntries + roff[i]);
-        const double w = fma(p[i].x, p[i].x, p[i].y * p[i].y);
-        p0 = fma(w, q.x, p0);
-        p1 = fma(w, q.y, p1);
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        p0 += __shfl_xor_sync(0xffffffffu, p0, d);
-        p1 += __shfl_xor_sync(0xffffffffu, p1, d);
-    }
-    uint32_t out;
-    if (forced) {
-        out = (fo >> aj) & 1u;
-        if ((out ? p1 : p0) <= 0.0) bad = true;
-    } else {
-        out = (u * (p0 + p1) < p1) ? 1u : 0u;                // Measure: P(1) against one uniform, as k_measure
-    }
-    const unsigned char *ta = tk + (out ? 16 * kDgTabEntries : 0);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) p[i] = dg_cmul(p[i], *reinterpret_cast<const double2 *>(ta + roff[i]));
-    a_out |= out << aj;
-    pfin = out ? p1 : p0;
-}
-
-// The input block of every shot is the collapsed, normalised one at ancilla value 0 (the host collapses explicitly when
-// the previous cycle went through the generic sweep kernels).
-__global__ void __launch_bounds__(kDgThreads, 1)
-k_cycle(const __grid_constant__ DiagProg P, const __grid_constant__ MeasArgs ma, double2 *__restrict__ state,
-        size_t stride, const uint32_t *__restrict__ ev, const uint32_t *__restrict__ frm, const uint32_t *__restrict__ act_list,
-        const uint32_t *__restrict__ n_act_ptr, ShotAux *__restrict__ aux, const uint8_t *__restrict__ forced,
-        uint32_t *__restrict__ meas_out, unsigned long long *__restrict__ counters, int init_basis)
-{
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned char *wb = smem_raw + (size_t)warp * kDgWarpBytes;
-    double2 *buf = reinterpret_cast<double2 *>(wb);                                  // [2][512]
-    unsigned char *tab = wb + 2 * kRunBytes;                                         // A0 | A1 | Q
-    unsigned char *meta = wb + 2 * kRunBytes + kDgTabBytes;                          // [2][kDgMetaBytes]
-    uint64_t *full = reinterpret_cast<uint64_t *>(meta + 2 * kDgMetaBytes);          // [2]
-    uint64_t *mfull = full + 2;                                                      // [2]
-
-    const uint32_t n_items = *n_act_ptr;
-    const uint32_t n_warps = gridDim.x * kDgWarps, gw = blockIdx.x * kDgWarps + warp;
-    const uint32_t chunk = (n_items + n_warps - 1) / n_warps;
-    const uint32_t first = gw * chunk, last = min(n_items, first + chunk);
-    if (first >= last) return;                    // no CTA-wide barrier below: warps are independent
-
-    if (lane == 0) {
-        mbar_init(&full[0], 1); mbar_init(&full[1], 1);
-        mbar_init(&mfull[0], 1); mbar_init(&mfull[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-
-    // this lane's first table entry per slot (shot independent): slot base + lane part of the index, one byte per slot
-    uint32_t tlp[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        tlp[h] = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            uint32_t li = P.h[h].tbase[k];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int lb = P.h[h].lane_bit[k][j];
-                if (lb != 255) li += (uint32_t)((lane >> lb) & 1) << j;
-            }
-            tlp[h] |= li << (8 * k);
-        }
-    }
-
-    // one shot ahead: its event + frame words and its 8 KiB block
-    auto prefetch = [&](uint32_t shot_, int sb) {
-        unsigned char *m = meta + sb * kDgMetaBytes;
-        fence_proxy_async_smem();                 // the buffers were last touched through the generic proxy
-        mbar_expect_tx(&mfull[sb], kDgMetaBytes);
-        tma_load_1d(m, ev + (size_t)shot_ * S17_EV_WORDS, kEvBytes, &mfull[sb]);
-        tma_load_1d(m + kEvBytes, frm + (size_t)shot_ * 4, kDgFrmBytes, &mfull[sb]);
-        if (init_basis < 0) {
-            mbar_expect_tx(&full[sb], kRunBytes);
-            tma_load_1d(buf + sb * kRun, state + (size_t)shot_ * stride, kRunBytes, &full[sb]);
-        }
-    };
-
-    uint32_t shot = act_list[first];
-    if (lane == 0) prefetch(shot, 0);
-
-    const uint32_t nout = 8u * (uint32_t)ma.stage;
-    const bool is_forced = ma.forced != 0;
-    uint32_t j = 0;
-    for (uint32_t item = first; item < last; ++item, ++j) {
-        const int sb = (int)(j & 1u);
-        uint32_t shot1 = 0;
-        if (item + 1 < last) {
-            shot1 = act_list[item + 1];
-            if (lane == 0) prefetch(shot1, sb ^ 1);
-        }
-        const uint32_t *evw = reinterpret_cast<const uint32_t *>(meta + sb * kDgMetaBytes);
-        const uint32_t *fwp = reinterpret_cast<const uint32_t *>(meta + sb * kDgMetaBytes + kEvBytes);
-        double2 *xb = buf + sb * kRun;
-
-        // replayed outcomes of this cycle's eight ancillas / the eight uniforms of its Measure gates
-        uint32_t fo = 0;
-        double uu = 0.0;
-        if (is_forced) {
-            const uint32_t b = lane < 8 ? (uint32_t)forced[(size_t)shot * S17_MAX_OUTCOMES + nout + lane] : 0u;
-            fo = __ballot_sync(0xffffffffu, (b & 1u) != 0u) & 0xFFu;
-        } else if (lane < 8) {
-            Philox rng(ma.seed, ma.first_shot + shot, ma.stream + ((lane >> 2) ? 0u : 1u));
-            rng.c3 = (uint32_t)(lane & 3);
-            uu = rng.next();
-        }
-
-        double2 p[16];
-        if (init_basis < 0) {
-            mbar_wait(&full[sb], (j >> 1) & 1u);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) p[i] = xb[dg_label<1>(lane, i)];
-        } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-                p[i] = make_double2((int)dg_label<1>(lane, i) == init_basis ? 1.0 : 0.0, 0.0);
-        }
-        mbar_wait(&mfull[sb], (j >> 1) & 1u);
-        __syncwarp();                             // every lane holds its amplitudes: the buffer becomes exchange scratch
-
-        // frame words: bits 0-8 flip mask, 9-17 sign mask, 18-19 phase.  Signs and phases ride in the tables.  The data
-        // flips of a Hadamard-frame half are signs after its inverse transform, i.e. part of the next half's sign mask;
-        // those of a computational-frame half are a relabeling, applied by the store.
-        uint32_t carry = 0, perm = 0;
-        double pfin = 1.0;
-#pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-            const DiagHalf &H = P.h[h];
-            const uint32_t fw = fwp[h];
-            if (H.frame_x) dg_wht_forward(p, xb, lane);
-            __syncwarp();
-            dg_build_tables(H, evw, reinterpret_cast<double2 *>(tab), lane, ((fw >> 9) ^ carry) & 511u, (fw >> 18) & 3u, fw >> 20);
-            __syncwarp();
-            const uint32_t tl = h ? tlp[1] : tlp[0];
-            uint32_t a_out = 0;
-            bool bad = false;
-#pragma unroll 1
-            for (int k = 0; k < 4; ++k) {
-                const double u = __shfl_sync(0xffffffffu, uu, 4 * h + k);
-                dg_slot(p, H.roff[k], H.aj[k], tab + (((tl >> (8 * k)) & 0xFFu) << 4), is_forced, fo, u, a_out, bad, pfin);
-            }
-            if (H.frame_x) {
-                dg_wht_inverse(p, xb, lane);
-                pfin *= 512.0;                    // the inverse transform multiplies the norm^2 by 512
-                carry = fw & 511u;
-            } else {
-                carry = 0;
-                perm = fw & 511u;
-            }
-            if (lane == 0) meas_out[2 * shot + H.final_part] = a_out | (bad ? 0x100u : 0u);
-        }
-
-        // renormalise once (the squared norm of the selected branch is the last conditional weight)
-        const double inv = pfin > 0.0 ? 1.0 / sqrt(pfin) : 0.0;
-        double2 *sbase = state + (size_t)shot * stride;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) sbase[dg_label<1>(lane, i) ^ perm] = make_double2(p[i].x * inv, p[i].y * inv);
-        if (lane == 0) {
-            ShotAux ax;
-            ax.scale = 1.0;
-            ax.anc_outcome = 0;
-            ax.collapsed = 1;                     // the normalised block is stored at ancilla value 0
-            aux[shot] = ax;
-        }
-        __syncwarp();                             // scratch, tables and the metadata slot are reused
-        shot = shot1;
-    }
-    if (lane == 0) {
-        atomicAdd(&counters[4], (unsigned long long)(last - first));                                     // C_SWEEPS
-        atomicAdd(&counters[8], (unsigned long long)(last - first) * (init_basis < 0 ? 2ull : 1ull));   // 8 KiB runs moved
     }
 }
 

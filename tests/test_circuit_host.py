@@ -43,7 +43,7 @@ def test_leak_index_quirk_preserved():
             assert (o.d_leak, o.a_leak) == (o.data, 9 + o.ancilla)
 
 
-@pytest.mark.parametrize("fusion,n_layers", [(0, 54), (1, 8), (2, 4), (4, 2)])
+@pytest.mark.parametrize("fusion,n_layers", [(0, 54), (1, 8), (2, 4)])
 def test_program_shapes(error_models, fusion, n_layers):
     prog = circuit.compile_program(error_models["PDD_model"], [12, 18, 24, 78, 24], fusion=fusion)
     assert len(prog.layers[0]) == len(prog.layers[1]) == len(prog.layers[2]) == n_layers

@@ -31,9 +31,9 @@ def make_sim(models, ct, bt, model, list_len, n, fusion=1, cooling=False, **kw):
                           bitflip_table=bt, error_models=models, **kw)
 
 
-@pytest.mark.parametrize("fusion,dense,early", [(0, "0", False), (1, "0", False), (2, "0", False), (4, "0", False),
-                                                (2, "1", False), (0, "1", False), (4, "1", False),
-                                                (0, "0", True), (1, "0", True), (2, "0", True), (4, "0", True),
+@pytest.mark.parametrize("fusion,dense,early", [(0, "0", False), (1, "0", False), (2, "0", False),
+                                                (2, "1", False), (0, "1", False),
+                                                (0, "0", True), (1, "0", True), (2, "0", True),
                                                 (2, "1", True)])
 def test_golden_replays(error_models, correction_table, bitflip_table, golden, fusion, dense, early, monkeypatch):
     """Replayed reference trajectories (masks + forced outcomes): every record field bit-exact, and the
@@ -67,8 +67,8 @@ def test_golden_replays(error_models, correction_table, bitflip_table, golden, f
         sim.close()
 
 
-@pytest.mark.parametrize("dense,fusion,early,diag", [("0", 2, True, "1"), ("0", 2, True, "0"), ("0", 2, True, "g"), ("1", 2, True, "1"),
-                                                     ("0", 4, True, "1"), ("0", 1, True, "1"), ("0", 2, False, "1"),
+@pytest.mark.parametrize("dense,fusion,early,diag", [("0", 2, True, "1"), ("0", 2, True, "0"), ("1", 2, True, "1"),
+                                                     ("0", 1, True, "1"), ("0", 2, False, "1"),
                                                      ("0", 0, True, "1")])
 def test_golden_replays_fast_path(error_models, correction_table, bitflip_table, golden, dense, fusion, early, diag,
                                   monkeypatch):
@@ -120,7 +120,7 @@ def test_amplitudes_after_every_gate(error_models, correction_table, bitflip_tab
     sim.close()
 
 
-@pytest.mark.parametrize("fusion", [1, 2, 4])
+@pytest.mark.parametrize("fusion", [1, 2])
 def test_amplitudes_noisy_cycle_before_measurement(error_models, correction_table, bitflip_table, fusion):
     """Full state after the gates of a noisy cycle (Pauli events of every kind, leak skips, idle Z)."""
     rng = random.Random(99)
@@ -170,7 +170,7 @@ def test_amplitudes_noisy_cycle_before_measurement(error_models, correction_tabl
     ("Dress_cooling", "s2", True, [0, 0, 1, 2, 0, 3]),
     ("PDD_cooling", "single", True, [1, 1, 1, 1, 1, 2]),
 ])
-@pytest.mark.parametrize("fusion,diag", [(2, "1"), (2, "0"), (2, "g"), (4, "1")])
+@pytest.mark.parametrize("fusion,diag", [(2, "1"), (2, "0"), (1, "1")])
 def test_sampled_trajectories_replay_bit_exact_in_oracle(error_models, correction_table, bitflip_table, model,
                                                          protocol, cooling, eset, fusion, diag, monkeypatch):
     """Device-sampled shots (Philox placement + outcomes): replaying their masks and outcomes through the
@@ -198,7 +198,7 @@ def test_sampled_trajectories_replay_bit_exact_in_oracle(error_models, correctio
     sim.close()
 
 
-@pytest.mark.parametrize("diag", ["1", "g"])
+@pytest.mark.parametrize("diag", ["1"])
 @pytest.mark.parametrize("model,eset", [("PDD_model", [2, 2, 3, 6, 2]), ("Dress_model", [1, 1, 2, 8, 1]),
                                         ("PDD_model", [0, 0, 0, 0, 0]), ("PDD_cooling", [1, 1, 2, 4, 1, 12]),
                                         ("Dress_cooling", [1, 1, 1, 6, 1, 20])])
@@ -344,9 +344,9 @@ def test_memoised_preparation_is_bit_identical(error_models, correction_table, b
 
 def test_cycle_kernel_large_batch_properties(error_models, correction_table, bitflip_table, monkeypatch):
     """The whole-cycle kernel at a batch where every warp walks a few dozen shots (prefetch ring, barrier phases): no
-    noise => no detection and no failure; every single-error subset is corrected (distance 3); the searched-map kernel
-    (k_cycle1) and the fixed-map one (k_cycle) tally the same sampled batch identically; the tallies do not depend on
-    how the shot range is split."""
+    noise => no detection and no failure; every single-error subset is corrected (distance 3); the whole-cycle kernel
+    and the fused half-cycle kernel (S17_DIAG=0) tally the same sampled batch alike; the tallies do not depend on how the
+    shot range is split."""
     locs = [24, 36, 48, 156, 48]
     n = 65536
     monkeypatch.setenv("S17_DIAG", "1")
@@ -369,12 +369,12 @@ def test_cycle_kernel_large_batch_properties(error_models, correction_table, bit
         parts = [parts[0] + c.failed, parts[1] + c.not0, parts[2] + c.counted]
     assert tuple(parts) == whole
     sim.close()
-    monkeypatch.setenv("S17_DIAG", "g")
+    monkeypatch.setenv("S17_DIAG", "0")
     sim = make_sim(error_models, correction_table, bitflip_table, "PDD_model", locs, n, 2)
     sim.backend.set_subset([0, 0, 2, 1, 1], locs)
     c = sim.backend.run("s2", n, L.NOISE_SUBSET, seed=17, first_shot_id=1000)
     # same placements and the same uniforms for the ancilla Measures: the not0 tally is identical; the data read-out of
-    # k_cycle is drawn by k_readout in a different order, so failures agree statistically
+    # the k_half path is drawn by k_readout in a different order, so failures agree statistically
     assert c.not0 == whole[1] and c.counted == whole[2]
     p = (c.failed + whole[0]) / (2 * whole[2])
     assert abs(c.failed - whole[0]) < 5 * np.sqrt(2 * whole[2] * p * (1 - p))
@@ -402,7 +402,7 @@ def test_statistics_against_oracle_sampling(error_models, correction_table, bitf
     assert abs(f_gpu - f_cpu) < 3 * np.sqrt(f * (1 - f) * (1 / max(1, c.not0) + 1 / max(1, not0))) + 1e-9
 
 
-@pytest.mark.parametrize("fusion", [1, 4])
+@pytest.mark.parametrize("fusion", [1, 2])
 def test_coherent_overrotation_against_oracle(error_models, correction_table, bitflip_table, fusion):
     """BASELINE config 3 (extension): deterministic over-rotations + stochastic XX, full-state parity."""
     eps1, eps2 = [0.02] * 30, [0.02] * 24
@@ -610,7 +610,7 @@ def test_sampled_rates_against_reference_statistics(error_models, correction_tab
         assert abs(f_gpu - f_ref) < 3.5 * sig, (st["model"], st["eset"], "failed", f_gpu, f_ref, sig)
 
 
-@pytest.mark.parametrize("diag", ["1", "g", "0"])
+@pytest.mark.parametrize("diag", ["1", "0"])
 def test_impossible_forced_outcome_is_reported(error_models, correction_table, bitflip_table, diag, monkeypatch):
     """A replay that forces an outcome of probability zero (a z-type ancilla reading 1 in the noiseless preparation
     cycle; a flipped x-type ancilla in a noiseless second cycle) is counted in `errors` and flagged in the record on

@@ -83,7 +83,7 @@ def test_reference_cycle_traces_to_the_compiled_program(name, cooling):
     check_trace(tr, model, one, cooling, 0)
     check_trace(tr2, model, two, cooling, 1)
     # the program lowered from the reference's trace is byte-identical with the one compiled from circuit.py's tables
-    for fusion, early in ((0, False), (1, False), (2, True), (4, True)):
+    for fusion, early in ((0, False), (1, False), (2, True)):
         a = circuit.compile_program(model, two, fusion=fusion, cooling=cooling, early_measure=early)
         b = circuit.compile_program(model, two, fusion=fusion, cooling=cooling, early_measure=early, ops=tr.ops,
                                     slots=tr.slots(), idle_slots={(t, q): s for t, q, _n, s in tr.idle} if cooling else None)
