@@ -301,7 +301,8 @@ constexpr int kPlanMaxGroups = 32;
 constexpr int kPlanFiWords = kPlanMaxInstr / 32;       // fired-instruction bitmap of one shot
 constexpr int kPlanFiRow = kPlanFiWords + 1;           // odd row stride: conflict-free
 constexpr size_t kPlanSmem = (size_t)(2 * (kPlanThreads / 32) * 32 * kPlanRow + kPlanThreads * kPlanFiRow +
-                                      kPlanMaxInstr * 3 + kPlanMaxInstr + 2 * kPlanMaxGroups) * 4;
+                                      kPlanMaxInstr * 3 + kPlanMaxInstr + 2 * kPlanMaxGroups) * 4 +
+                             (size_t)(kPlanMaxInstr + 2) * 8;             // + the survival products (true-probability noise)
 struct StepArgs {
     int do_record;                 // 1: first apply the previous cycle's measurement outcomes (rec_ma.stage) to the shot
     MeasArgs rec_ma;
@@ -325,7 +326,8 @@ struct StepArgs {
 // hot word of an instruction: bits 0-15 absolute slot, 16 in_skip, 17 entry (S17_P_ERR / S17_P_IDLE), 18-22 group,
 // 23 leakage entry.  group words: [g] bits 0-9 first instruction, 10-19 one past the last; [32 + g] bit 0 gap (idle)
 // group, 1-5 event word, 6-9 data bit, 10 first operation of its half cycle, 11 half index, 12 Hadamard frame, 13 the
-// operation closes the Ry bracket of its data qubit (Ry(-)), 14 it opens it (Ry(+)), 15 it has an Rx, 16 Rxx sign is +
+// operation closes the Ry bracket of its data qubit (Ry(-)), 14 it opens it (Ry(+)), 15 it has an Rx, 16 Rxx sign is +,
+// 17-22 offset of the operation's leak test (S17_P_SKIP_TEST) from its first instruction
 __device__ __forceinline__ uint32_t plan_apply_error(uint32_t f, const s17_pinstr &in, uint32_t &lk, Philox &rng) {
     switch (in.err) {
     case S17_ERR_X: f = pauli_mul(f, 0, 1); break;
@@ -379,6 +381,7 @@ k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, const __grid_constant__
     uint32_t *s_prog = s_fi + kPlanThreads * kPlanFiRow;   // the program of this cycle (slots resolved to absolute bit indices)
     uint32_t *s_hot = s_prog + kPlanMaxInstr * 3;
     uint32_t *s_grp = s_hot + kPlanMaxInstr;               // [0..31] instruction range, [32..63] operation word
+    double *s_surv = reinterpret_cast<double *>(s_grp + 2 * kPlanMaxGroups);   // (the words before it are an even count)
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     if (blockIdx.x == 0 && threadIdx.x == 0) *n_act_next = 0;
     {
@@ -386,6 +389,8 @@ k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, const __grid_constant__
         for (int i = threadIdx.x; i < pa.n_instr * 3; i += blockDim.x) s_prog[i] = src[i];
         for (int i = threadIdx.x; i < pa.n_instr; i += blockDim.x) s_hot[i] = hot[i];
         if (threadIdx.x < 2 * kPlanMaxGroups) s_grp[threadIdx.x] = (threadIdx.x & (kPlanMaxGroups - 1)) < n_grp ? grp[threadIdx.x] : 0u;
+        if (surv)
+            for (int i = threadIdx.x; i <= pa.n_instr; i += blockDim.x) s_surv[i] = surv[i];
         __syncthreads();
     }
     const bool prob_mode = pa.noise == S17_NOISE_PROB;
@@ -406,6 +411,8 @@ k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, const __grid_constant__
                            active, sa.ready, sa.rec, sa.counters);
         act = active[shot] != 0;                       // the protocol may have retired the shot (CL:321, 416, 86)
     }
+    // preparation stage next to the memoised one (k_prep): only the shots it left (a set leak flag) run a cycle
+    if (act && sa.skip_done && sa.done && sa.done[shot]) act = false;
     const uint32_t actmask = __ballot_sync(0xffffffffu, act);
     if (!actmask) continue;
     // the shots' slot bitsets: placed / replayed ones are loaded, eight rows in flight; sampled or placed here: start empty
@@ -441,14 +448,14 @@ k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, const __grid_constant__
     if (prob_mode && !pa.noiseless) {
         if (surv) {
             int pos = 0;
-            const double s_end = surv[pa.n_instr];
+            const double s_end = s_surv[pa.n_instr];
             for (;;) {
-                const double target = rng.next() * surv[pos];
+                const double target = rng.next() * s_surv[pos];
                 if (!(s_end < target)) break;                        // nothing fires in the rest of the cycle
                 int lo = pos, hi = pa.n_instr - 1;                   // smallest i >= pos with S_{i+1} < target
                 while (lo < hi) {
                     const int mid = (lo + hi) >> 1;
-                    if (surv[mid + 1] < target) hi = mid; else lo = mid + 1;
+                    if (s_surv[mid + 1] < target) hi = mid; else lo = mid + 1;
                 }
                 mask_set(mk, s_hot[lo] & 0xFFFFu);
                 pos = lo + 1;
@@ -480,16 +487,20 @@ k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, const __grid_constant__
     any_event = any_event || flagged != 0;
     const bool walk = lk != 0 || leak_event != 0 || sa.walk_all;
     const uint32_t todo = walk ? 0xFFFFFFFFu : flagged;
-    if (!walk) {
-        // ---- pass 1, usual case (no leaked qubit, no leakage entry): per operation with a fired entry, the fired
-        // instructions in program order, then the net Pauli of the operation.  Each lane runs over ITS OWN operations.
-        uint32_t td = flagged & ~gap_mask;
+    if (!sa.walk_all) {
+        // ---- pass 1: per operation, its fired instructions in program order, then its net Pauli.  Without a leaked
+        // qubit only the operations with a fired entry are visited (each lane runs over ITS OWN operations); with one
+        // (or with a leakage entry firing in this cycle) every operation is, because its leak test (evaluated right
+        // before its Rxx, after the errors of a preceding Ry: CS:293, 322) may skip the Rxx block and its entries.
+        uint32_t td = (walk ? (n_grp >= 32 ? 0xFFFFFFFFu : ((1u << n_grp) - 1u)) : flagged) & ~gap_mask;
         while (td) {
             const int gi = __ffs(td) - 1;
             td &= td - 1;
             const uint32_t gm = s_grp[gi], g2 = s_grp[kPlanMaxGroups + gi];
             const int first = (int)(gm & 1023u), last = (int)((gm >> 10) & 1023u);
-            uint32_t w = 0;
+            const int sk = first + (int)((g2 >> 17) & 63u);              // the operation's leak test
+            uint32_t w = 0, skip = 0;
+            bool tested = !walk;                                         // no leaked qubit: the test is negative
             for (int wi = first >> 5; wi <= (last - 1) >> 5; ++wi) {
                 uint32_t bits = fi[wi];
                 if (wi == (first >> 5)) bits &= 0xFFFFFFFFu << (first & 31);
@@ -497,16 +508,27 @@ k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, const __grid_constant__
                 while (bits) {
                     const int ii = 32 * wi + __ffs(bits) - 1;
                     bits &= bits - 1;
+                    if (!tested && ii > sk) {
+                        const s17_pinstr t = reinterpret_cast<const s17_pinstr *>(s_prog)[sk];
+                        skip = ((lk >> t.a) | (lk >> t.b)) & 1u;
+                        tested = true;
+                    }
+                    if (((s_hot[ii] >> 16) & 1u) & skip) continue;       // an entry inside a skipped Rxx block
                     const s17_pinstr in = reinterpret_cast<const s17_pinstr *>(s_prog)[ii];
                     const uint32_t f = plan_apply_error((w >> in.field) & 63u, in, lk, rng);
                     w = (w & ~(63u << in.field)) | (f << in.field);
                 }
             }
-            evs[(g2 >> 1) & 31u] = plan_net_pauli(w, 0u, (g2 >> 14) & 1u, (g2 >> 15) & 1u, (g2 >> 13) & 1u, ((g2 >> 16) & 1u) ? 1 : -1);
+            if (!tested) {
+                const s17_pinstr t = reinterpret_cast<const s17_pinstr *>(s_prog)[sk];
+                skip = ((lk >> t.a) | (lk >> t.b)) & 1u;
+            }
+            w |= skip << 24;
+            evs[(g2 >> 1) & 31u] = plan_net_pauli(w, skip, (g2 >> 14) & 1u, (g2 >> 15) & 1u, (g2 >> 13) & 1u, ((g2 >> 16) & 1u) ? 1 : -1);
         }
     } else {
-        // ---- pass 1, general case: every instruction of every group, in program order (one instruction per trip of a
-        // single loop).  Leaves the operation's event word (per-gate fields, skip bit, net Pauli) in evs[].
+        // ---- pass 1 for a program in which two entries share a slot: every instruction of every group, in program
+        // order (one instruction per trip of a single loop)
         uint32_t td = todo & (n_grp >= 32 ? 0xFFFFFFFFu : ((1u << n_grp) - 1u)) & ~gap_mask;
         int i = 0, end = 0;
         uint32_t w = 0, skip = 0;
@@ -602,7 +624,7 @@ k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, const __grid_constant__
     for (int r = 0; r < 32; ++r) {
         if (!((actmask >> r) & 1u)) continue;
         ev[(size_t)(shot0 + r) * S17_EV_WORDS + lane] = s_ev[wib][r][lane];
-        if (prob_mode || pa.place)
+        if ((prob_mode && !pa.noiseless) || pa.place)
             masks[(size_t)(shot0 + r) * (2 * S17_MASK_WORDS) + (pa.rec_half ? S17_MASK_WORDS : 0) + lane] = s_mask[wib][r][lane];
     }
     if (sa.do_compact) {
@@ -610,7 +632,6 @@ k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, const __grid_constant__
         // is arbitrary (it only decides which warp processes which shot).
         bool flag = act;
         if (flag && quiet && !any_event && sa.quiet_ok[sa.leaf[shot]]) flag = false;          // k_quiet handles it
-        if (flag && sa.done && sa.skip_done && sa.done[shot]) flag = false;                    // the memoised preparation did
         const uint32_t ballot = __ballot_sync(0xffffffffu, flag);
         if (ballot) {
             uint32_t pos = 0;
@@ -1026,7 +1047,7 @@ struct s17_ctx {
     uint16_t *plan_bit2grp = nullptr;   // slot bit -> instruction index of its entry, per cycle variant
     double *plan_surv = nullptr;
     int n_grp[2] = {0, 0};
-    bool geo_ok[2] = {false, false}, plan_dup_slot = false, no_geo = false;
+    bool geo_ok[2] = {false, false}, plan_dup_slot[2] = {false, false}, no_geo = false;   // per cycle variant
     std::vector<s17_pinstr> plan_res;     // host copy of the resolved program (both variants)
     std::vector<double> h_probs;          // host copy of the slot probabilities
     RtfSlot *rtf_slots = nullptr;
@@ -1068,8 +1089,10 @@ struct s17_ctx {
     // memoised event-free first cycle (k_quiet): per leaf the block k_cycle1 stores and its read-out weights
     double2 *quiet_blocks = nullptr;
     double *quiet_cdf = nullptr;
+    uint8_t *quiet_last = nullptr;    // per leaf and lane: the lane's last basis state of positive weight (k_quiet)
     uint8_t *quiet_ok = nullptr, *quiet_flag = nullptr;
-    bool no_quiet = false, quiet_copy = true, use_quiet = false, any_quiet_leaf = false;
+    bool no_quiet = false, quiet_copy = false, use_quiet = false, any_quiet_leaf = false;
+    bool quiet_lazy = false;          // the last run left event-free shots' blocks in the cache (s17_read_state looks there)
     PrepTree prep_tree;
     bool use_dsamp = false;
     bool no_fuse = false;
@@ -1211,6 +1234,7 @@ extern "C" int s17_create(s17_ctx **out, int device, uint64_t max_shots) {
     CK(cudaMalloc(&ctx->prep_pp, 2 * 255 * sizeof(double)));
     CK(cudaMalloc(&ctx->quiet_blocks, 256 * (size_t)kRunBytes));
     CK(cudaMalloc(&ctx->quiet_cdf, 256 * (size_t)kDgCdfDoubles * sizeof(double)));
+    CK(cudaMalloc(&ctx->quiet_last, 256 * 32));
     CK(cudaMalloc(&ctx->quiet_ok, 256));
     CK(cudaMemset(ctx->quiet_ok, 0, 256));
     CK(cudaMalloc(&ctx->quiet_flag, B));
@@ -1243,8 +1267,8 @@ extern "C" int s17_create(s17_ctx **out, int device, uint64_t max_shots) {
         ctx->no_prep_cache = pc && pc[0] == '0';
         const char *qc = getenv("S17_QUIET");            // 0: run event-free first cycles through k_cycle1 like any other
         ctx->no_quiet = qc && qc[0] == '0';
-        const char *qcp = getenv("S17_QUIET_COPY");      // 0: do not copy the cached block into the shot's state
-        ctx->quiet_copy = !(qcp && qcp[0] == '0');
+        const char *qcp = getenv("S17_QUIET_COPY");      // 1: always copy the cached block into the shot's state
+        ctx->quiet_copy = qcp && qcp[0] == '1';
         const char *r = getenv("S17_RING");
         ctx->force_ring = r && r[0] == '1';
         const char *ge = getenv("S17_GEO");               // 0: one Bernoulli draw per entry instead of geometric skipping
@@ -1274,7 +1298,7 @@ extern "C" int s17_destroy(s17_ctx *ctx) {
                     ctx->rtf_slots, ctx->rtf_rounds, ctx->rtf_syndb, ctx->rtf_block_cnt, ctx->rtf_block_off, ctx->rtf_ticket, ctx->act_list, ctx->n_act2, ctx->zero_page, ctx->meas_out,
                     ctx->frm, ctx->dsamp, ctx->prep_leaf, ctx->prep_done, ctx->prep_blocks, ctx->prep_pp, ctx->plan_hot,
                     ctx->plan_grp, ctx->plan_bit2grp, ctx->plan_surv,
-                    ctx->quiet_blocks, ctx->quiet_cdf, ctx->quiet_ok, ctx->quiet_flag};
+                    ctx->quiet_blocks, ctx->quiet_cdf, ctx->quiet_last, ctx->quiet_ok, ctx->quiet_flag};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
@@ -1962,7 +1986,7 @@ extern "C" int s17_load_program(s17_ctx *ctx, const s17_layer *layers, const uin
         // groups of the program (one entangling operation / the idle entries of one gap), in program order
         std::vector<uint32_t> grp(4 * kPlanMaxGroups, 0u);     // per variant: 32 instruction ranges, 32 operation words
         std::vector<uint16_t> b2i(2 * 2048, 0xFFFFu);          // slot bit -> instruction of its entry (per variant)
-        ctx->plan_dup_slot = false;
+        ctx->plan_dup_slot[0] = ctx->plan_dup_slot[1] = false;
         for (int c2 = 0; c2 < 2; ++c2) {
             int ng = 0;
             uint32_t i = 0;
@@ -1973,7 +1997,11 @@ extern "C" int s17_load_program(s17_ctx *ctx, const s17_layer *layers, const uin
                     while (j < n_plan && q[j].kind != S17_P_OP_END) ++j;
                     if (j == n_plan) return fail(ctx, S17_E_ARG, "plan: operation without an end");
                     const s17_pinstr &e = q[j];
-                    meta = ((uint32_t)e.word << 1) | ((uint32_t)(plan[j].slot & 15u) << 6) | (((e.a >> 4) & 1u) << 10) |
+                    uint32_t sk = 0;
+                    for (uint32_t k = i; k < j; ++k)
+                        if (q[k].kind == S17_P_SKIP_TEST) sk = k - i;
+                    if (sk == 0 || sk > 63u) ctx->plan_dup_slot[c2] = true;   // no (or a far) leak test: plain walk
+                    meta = (sk << 17) | ((uint32_t)e.word << 1) | ((uint32_t)(plan[j].slot & 15u) << 6) | (((e.a >> 4) & 1u) << 10) |
                            (((e.a >> 5) & 1u) << 11) | (((e.a >> 3) & 1u) << 12) | (((e.a >> 2) & 1u) << 13) |
                            ((e.a & 1u) << 14) | (((e.a >> 1) & 1u) << 15) | ((e.b ? 1u : 0u) << 16);
                     ++j;
@@ -1990,7 +2018,7 @@ extern "C" int s17_load_program(s17_ctx *ctx, const s17_layer *layers, const uin
                     if (q[k].kind == S17_P_ERR || q[k].kind == S17_P_IDLE) {
                         uint16_t &slot = b2i[(size_t)c2 * 2048 + q[k].slot];
                         const bool lk_kind = q[k].kind == S17_P_ERR && (q[k].err == S17_ERR_LEAK_A || q[k].err == S17_ERR_LEAK_AB);
-                        if (slot != 0xFFFFu) ctx->plan_dup_slot = true;       // one slot, two entries: k_plan walks everything
+                        if (slot != 0xFFFFu) ctx->plan_dup_slot[c2] = true;   // one slot, two entries: k_plan walks everything
                         slot = (uint16_t)k;
                         hot[(size_t)c2 * n_plan + k] |= ((uint32_t)ng << 18) | (lk_kind ? (1u << 23) : 0u);
                     }
@@ -2085,7 +2113,7 @@ extern "C" int s17_set_slot_probs(s17_ctx *ctx, uint32_t list_id, const double *
             q = q < 0.0 ? 0.0 : (q > 1.0 ? 1.0 : q);
             S[i + 1] = S[i] * (1.0 - q);
         }
-        ctx->geo_ok[c2] = !ctx->plan_dup_slot && !ctx->no_geo && S[n] > 0.25;
+        ctx->geo_ok[c2] = !ctx->plan_dup_slot[c2] && !ctx->no_geo && S[n] > 0.25;
     }
     CK(cudaMemcpy(ctx->plan_surv, surv.data(), surv.size() * sizeof(double), cudaMemcpyHostToDevice));
     return S17_OK;
@@ -2288,6 +2316,28 @@ static int build_prep_cache(s17_ctx *ctx, int basis) {
         CK(cudaGetLastError());
         CK(cudaMemcpy(h_pp.data(), pp, h_pp.size() * sizeof(double), cudaMemcpyDeviceToHost));
         CK(cudaMemcpy(h_mo.data(), mo, h_mo.size() * 4, cudaMemcpyDeviceToHost));
+        {
+            // k_quiet replays the kernel's read-out draw with one thread per shot: turn each leaf's per-state weights into
+            // the running sums the kernel's lanes form (same additions in the same order: the previous lane's inclusive
+            // sum, then the lane's sixteen weights one by one), and note each lane's last state of positive weight
+            std::vector<double> h_cdf((size_t)N * kDgCdfDoubles);
+            std::vector<uint8_t> h_last((size_t)N * 32, 0);
+            CK(cudaMemcpy(h_cdf.data(), cdf, h_cdf.size() * sizeof(double), cudaMemcpyDeviceToHost));
+            for (int L = 0; L < N; ++L) {
+                double *c = &h_cdf[(size_t)L * kDgCdfDoubles];
+                for (int lane = 0; lane < 32; ++lane) {
+                    double cum = lane ? c[lane - 1] : 0.0;
+                    for (int i = 0; i < 16; ++i) {
+                        const double w = c[32 + 16 * lane + i];
+                        if (w > 0.0) h_last[(size_t)L * 32 + lane] = (uint8_t)i;
+                        cum += w;
+                        c[32 + 16 * lane + i] = cum;
+                    }
+                }
+            }
+            CK(cudaMemcpy(cdf, h_cdf.data(), h_cdf.size() * sizeof(double), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(ctx->quiet_last, h_last.data(), h_last.size(), cudaMemcpyHostToDevice));
+        }
         for (int L = 0; L < N; ++L) {
             bool ok = reach[L] && !((h_mo[2 * L] | h_mo[2 * L + 1]) & 0x100u);
             for (int s = 0; s < 8 && ok; ++s) {
@@ -2389,7 +2439,7 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
         sa.quiet_ok = ctx->quiet_ok;
         sa.done = (ctx->use_prep && stage <= 1) ? ctx->prep_done : nullptr;
         sa.skip_done = stage == 0 ? 1 : 0;
-        sa.walk_all = ctx->plan_dup_slot ? 1 : 0;
+        sa.walk_all = ctx->plan_dup_slot[second ? 1 : 0] ? 1 : 0;
         sa.do_reset = ctx->pend_reset ? 1 : 0;
         sa.keep_leak = 0;
         ctx->pend_reset = false;
@@ -2400,12 +2450,14 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
         uint32_t *n_next = ctx->n_act2 + ((ctx->plan_seq + 1u) & 1u);
         ++ctx->plan_seq;
         SCOPE2(CAT_OTHER, S17_T_PLAN);
-        k_plan<<<std::min(blocks_for(n, kPlanThreads), ctx->num_sms * 4), kPlanThreads, kPlanSmem, ctx->stream>>>(
+        const bool geo = a.noise == S17_NOISE_PROB && ctx->geo_ok[second ? 1 : 0];
+        const size_t smem = kPlanSmem - (geo ? 0 : (size_t)(kPlanMaxInstr + 2) * 8);          // 59 / 54 KiB: 3 / 4 CTAs per SM
+        k_plan<<<std::min(blocks_for(n, kPlanThreads), ctx->num_sms * (geo ? 3 : 4)), kPlanThreads, smem, ctx->stream>>>(
             ctx->plan + (second ? ctx->n_plan : 0), pa, sa, ctx->probs, ctx->ev, ctx->masks, ctx->leak, ctx->active, ctx->frm,
             ctx->n_act, n_next, ctx->plan_hot + (second ? ctx->n_plan : 0),
             (ctx->use_quiet && stage == 1) ? ctx->quiet_flag : nullptr, ctx->plan_grp + (second ? 2 * kPlanMaxGroups : 0),
             ctx->n_grp[second ? 1 : 0], ctx->plan_bit2grp + (second ? 2048 : 0),
-            (a.noise == S17_NOISE_PROB && ctx->geo_ok[second ? 1 : 0]) ? ctx->plan_surv + (second ? kPlanMaxInstr + 1 : 0) : nullptr);
+            geo ? ctx->plan_surv + (second ? kPlanMaxInstr + 1 : 0) : nullptr);
     }
     const int which = stage == 0 ? 0 : (second ? 2 : 1);
     const std::vector<LayerArg> &Ls = ctx->layers[which];
@@ -2444,11 +2496,14 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
         if (ctx->use_quiet && stage == 1) {
             // the shots k_plan left out of the list: no event in this cycle, memoised leaf.  meas_out still holds the leaf's
             // outcomes (k_prep wrote them), which are this cycle's outcomes too.
+            // Their state is the cached block of their leaf: copied into the shot's slot only when something on the device
+            // will read it (a replay / a state-reading read-out, or S17_QUIET_COPY=1); s17_read_state finds it either way.
+            const int copy = (ctx->quiet_copy || a.forced || !ctx->use_dsamp) ? 1 : 0;
+            ctx->quiet_lazy = !copy;
             SCOPE(CAT_OTHER);
-            k_quiet<<<blocks_for((uint64_t)n * 32, 128), 128, 0, ctx->stream>>>(
+            k_quiet<<<blocks_for(copy ? (uint64_t)n * 32 : (uint64_t)n, 128), 128, 0, ctx->stream>>>(
                 ctx->prep_tree, ma, ctx->diag_prog1[1].mapA, ctx->active, ctx->quiet_flag, ctx->quiet_ok, ctx->prep_leaf, ctx->quiet_blocks,
-                ctx->quiet_cdf, ctx->forced, ctx->state, ctx->stride, ctx->meas_out, ctx->dsamp, ctx->counters,
-                (ctx->quiet_copy || a.forced) ? 1 : 0);
+                ctx->quiet_cdf, ctx->quiet_last, ctx->forced, ctx->state, ctx->stride, ctx->meas_out, ctx->dsamp, ctx->counters, copy);
         }
         // the cycle's bookkeeping (outcome log, leak override, protocol branch, decode) is applied per shot by whichever
         // kernel touches the shots next: the next cycle's k_plan, k_readout_s, or flush_record
@@ -2804,6 +2859,18 @@ extern "C" int s17_read_state(s17_ctx *ctx, uint64_t shot, double *re_im) {
     if (!ctx || !re_im || shot >= ctx->max_shots) return fail(ctx, S17_E_ARG, "s17_read_state: bad arguments");
     CK(cudaSetDevice(ctx->device));
     if (!ctx->state) return fail(ctx, S17_E_STATE, "s17_read_state: nothing has run yet");
+    if (ctx->use_quiet && ctx->quiet_lazy) {
+        // a shot whose first noisy cycle was event-free and that stopped there: its block is the memoised one of its leaf
+        uint8_t q = 0, leaf = 0, ok = 0;
+        CK(cudaMemcpy(&q, ctx->quiet_flag + shot, 1, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(&leaf, ctx->prep_leaf + shot, 1, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(&ok, ctx->quiet_ok + leaf, 1, cudaMemcpyDeviceToHost));
+        if (q && ok) {
+            memset(re_im, 0, kDim * sizeof(double2));
+            CK(cudaMemcpy(re_im, ctx->quiet_blocks + (size_t)leaf * kRun, kRun * sizeof(double2), cudaMemcpyDeviceToHost));
+            return S17_OK;
+        }
+    }
     if (ctx->state_full) {
         CK(cudaMemcpy(re_im, ctx->state + shot * kDim, kDim * sizeof(double2), cudaMemcpyDeviceToHost));
     } else {

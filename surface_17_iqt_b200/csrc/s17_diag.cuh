@@ -809,51 +809,53 @@ __global__ void __launch_bounds__(128)
 k_quiet(const __grid_constant__ PrepTree T, const __grid_constant__ MeasArgs ma, const __grid_constant__ DiagMap mapA,
         const uint8_t *__restrict__ active, const uint8_t *__restrict__ quiet,
         const uint8_t *__restrict__ quiet_ok, const uint8_t *__restrict__ leaf_of, const double2 *__restrict__ blocks,
-        const double *__restrict__ cdf, const uint8_t *__restrict__ forced, double2 *__restrict__ state, size_t stride,
+        const double *__restrict__ cdf /* per leaf: 32 inclusive lane sums, then per lane its 16 running sums */,
+        const uint8_t *__restrict__ last_pos /* per leaf and lane: last state of positive weight */,
+        const uint8_t *__restrict__ forced, double2 *__restrict__ state, size_t stride,
         uint32_t *__restrict__ meas_out, uint32_t *__restrict__ dsamp, unsigned long long *__restrict__ counters, int copy_block)
 {
-    const int shot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (shot >= ma.n_shots || !active[shot] || !quiet[shot]) return;
-    const uint32_t leaf = leaf_of[shot];
-    if (!quiet_ok[leaf]) return;                      // this shot went through k_cycle1 (k_compact kept it in the list)
-    if (ma.forced && lane == 0) {
-        // replay: the recorded outcomes of this cycle must be the leaf's (anything else has probability zero)
-        uint32_t bad = 0;
-        for (int s = 0; s < 8; ++s)
-            bad |= ((uint32_t)forced[(size_t)shot * S17_MAX_OUTCOMES + 8 + T.aj[s]] & 1u) ^ ((leaf >> s) & 1u);
-        if (bad) { meas_out[2 * shot] |= 0x100u; meas_out[2 * shot + 1] |= 0x100u; }
-    }
-    if (copy_block) {
-        const double2 *src = blocks + (size_t)leaf * kRun;
-        double2 *dst = state + (size_t)shot * stride;
+    // one thread per shot (copy_block: one warp per shot, lane 0 does the scalar part)
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int shot = copy_block ? (gid >> 5) : gid, lane = copy_block ? (threadIdx.x & 31) : 0;
+    const bool live = shot < ma.n_shots && active[shot] && quiet[shot] && quiet_ok[leaf_of[shot]];
+    if (live) {
+        const uint32_t leaf = leaf_of[shot];
+        if (copy_block) {
+            const double2 *src = blocks + (size_t)leaf * kRun;
+            double2 *dst = state + (size_t)shot * stride;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) dst[lane + 32 * i] = src[lane + 32 * i];
-    }
-    if (ma.sample_data) {
-        // the draw of k_cycle1, from the weights it computed for this block: same order, same doubles
-        const double *c = cdf + (size_t)leaf * kDgCdfDoubles;
-        const double incl = c[lane];
-        double u = 0.0;
-        if (lane == 0) { Philox rng(ma.seed, ma.first_shot + shot, ma.data_stream); u = rng.next(); }
-        const double target = __shfl_sync(0xffffffffu, u, 0) * __shfl_sync(0xffffffffu, incl, 31);
-        const uint32_t hit = __ballot_sync(0xffffffffu, target < incl);
-        const int sel = hit ? (__ffs(hit) - 1) : 31;
-        double cum = __shfl_up_sync(0xffffffffu, incl, 1);
-        if (lane == 0) cum = 0.0;
-        int pick = 0, last_pos = 0;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const double w = c[32 + 16 * lane + i];
-            cum += w;
-            pick += (cum <= target) ? 1 : 0;
-            last_pos = w > 0.0 ? i : last_pos;
+            for (int i = 0; i < 16; ++i) dst[lane + 32 * i] = src[lane + 32 * i];
         }
-        pick = pick > 15 ? last_pos : pick;
-        uint32_t lab = ((uint32_t)lane_label(mapA, lane) | (mapA.lin16[pick] >> 4));
-        lab = __shfl_sync(0xffffffffu, lab, sel);
-        if (lane == 0) dsamp[shot] = lab & 511u;      // a computational-frame half without events relabels nothing
+        if (lane == 0) {
+            if (ma.forced) {
+                // replay: the recorded outcomes of this cycle must be the leaf's (anything else has probability zero)
+                uint32_t bad = 0;
+                for (int s = 0; s < 8; ++s)
+                    bad |= ((uint32_t)forced[(size_t)shot * S17_MAX_OUTCOMES + 8 + T.aj[s]] & 1u) ^ ((leaf >> s) & 1u);
+                if (bad) { meas_out[2 * shot] |= 0x100u; meas_out[2 * shot + 1] |= 0x100u; }
+            }
+            if (ma.sample_data) {
+                // the draw of k_cycle1 from the weights it computed for this block -- the same comparisons on the same
+                // doubles: the first lane whose inclusive sum exceeds the target, then the number of that lane's running
+                // sums that do not
+                const double *c = cdf + (size_t)leaf * kDgCdfDoubles;
+                Philox rng(ma.seed, ma.first_shot + shot, ma.data_stream);
+                const double target = rng.next() * c[31];
+                int sel = 31;                              // (a scan in another order may round a sum below its neighbour:
+#pragma unroll 8
+                for (int l = 30; l >= 0; --l)              //  take the first lane exactly as the kernel's ballot does)
+                    if (target < c[l]) sel = l;
+                int pick = 0;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) pick += (c[32 + 16 * sel + i] <= target) ? 1 : 0;
+                pick = pick > 15 ? (int)last_pos[leaf * 32 + sel] : pick;
+                const uint32_t lab = (uint32_t)lane_label(mapA, sel) | (mapA.lin16[pick] >> 4);
+                dsamp[shot] = lab & 511u;                  // a computational-frame half without events relabels nothing
+            }
+        }
     }
-    if (lane == 0) atomicAdd(&counters[4], 1ull);                                                        // C_SWEEPS
+    const uint32_t nl = __popc(__ballot_sync(0xffffffffu, live && lane == 0));
+    if ((threadIdx.x & 31) == 0 && nl) atomicAdd(&counters[4], (unsigned long long)nl);                  // C_SWEEPS
 }
 
 }  // namespace s17
