@@ -220,6 +220,10 @@ int s17_set_replay(s17_ctx *ctx, uint64_t n_shots, const uint8_t *masks, uint64_
                    const uint8_t *outcomes, uint64_t outcome_stride);
 /* the shot loops of CL:183 / 261 / 355 / 33 */
 int s17_run(s17_ctx *ctx, const s17_run_args *args, s17_counts *out);
+/* Sum of the counters of several contexts of one process (one context per GPU per host thread).  Across processes
+ * (one per GPU under torchrun, the layout bench.py and the drop-in drivers use) the same sum is one all_reduce of these
+ * integers over NCCL: surface_17_iqt_b200/distributed.py. */
+int s17_allreduce_counts(const s17_counts *per_ctx, int n_ctx, s17_counts *out);
 int s17_read_records(s17_ctx *ctx, s17_record *out, uint64_t n);
 int s17_read_masks(s17_ctx *ctx, uint32_t *out /* n x 2 x S17_MASK_WORDS: cycle-1 / cycle-2 record */, uint64_t n);
 /* per-shot event words of the most recent cycle (debug / parity): n x S17_EV_WORDS */

@@ -84,7 +84,7 @@ assert C.sizeof(PInstr) == 12 and C.sizeof(Record) == 60 and C.sizeof(RunArgs) =
 EXPORTS = ("s17_create", "s17_destroy", "s17_last_error", "s17_device_count", "s17_load_program", "s17_describe_program",
            "s17_load_tables", "s17_set_slot_probs", "s17_set_subset", "s17_set_replay", "s17_run",
            "s17_read_records", "s17_read_masks", "s17_read_events", "s17_read_state", "s17_read_rtf", "s17_last_timing",
-           "s17_last_timing_detail",
+           "s17_last_timing_detail", "s17_allreduce_counts",
            "s17_rtf_begin", "s17_rtf_step", "s17_rtf_end", "s17_read_rtf_slots",
            "s17_eng_create", "s17_eng_destroy", "s17_eng_last_error", "s17_eng_reset", "s17_eng_gate1", "s17_eng_gate2",
            "s17_eng_measure", "s17_eng_prob1", "s17_eng_flush", "s17_eng_read_state", "s17_eng_timing")
@@ -131,6 +131,7 @@ def load():
     L.s17_last_timing.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                   C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_double)]
     L.s17_last_timing_detail.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64), C.POINTER(u64)]
+    L.s17_allreduce_counts.argtypes = [C.POINTER(Counts), C.c_int, C.POINTER(Counts)]
     L.s17_rtf_begin.argtypes = [vp, C.POINTER(RunArgs)]
     L.s17_rtf_step.argtypes = [vp, u32, C.POINTER(u64), C.POINTER(u64)]
     L.s17_rtf_end.argtypes = [vp, C.POINTER(Counts)]

@@ -16,6 +16,7 @@
 // There is NO CPU fallback in this library.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>      // header-only: ranges show up under nsys / ncu --nvtx, cost nothing otherwise
 
 #include <cmath>
 #include <cstdio>
@@ -1161,6 +1162,11 @@ struct Scope {
                 c->debug_note = std::string("first failing launch at s17.cu:") + std::to_string(line) + ": " + cudaGetErrorString(e);
         }
     }
+};
+// NVTX range around a phase of a call (tracing): s17_run > preparation / cycle 1 / cycle 2 / read-out
+struct Nvtx {
+    explicit Nvtx(const char *name) { nvtxRangePushA(name); }
+    ~Nvtx() { nvtxRangePop(); }
 };
 #define SCOPE(cat) Scope s(ctx, cat, __LINE__)
 #define SCOPE2(cat, sub) Scope s(ctx, cat, __LINE__, sub)
@@ -2543,7 +2549,7 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
                     (i == 0) ? init_basis : -1);
             else
                 k_layer2<<<ctx->num_sms, kL2Threads, kL2Smem, ctx->stream>>>(
-                    ctx->state, Ls2[i], ctx->ev, ctx->act_list, ctx->n_act, ctx->hist, ctx->counters, ctx->aux,
+                    ctx->tmap, ctx->state, Ls2[i], ctx->ev, ctx->act_list, ctx->n_act, ctx->hist, ctx->counters, ctx->aux,
                     ctx->zero_page, (i == 0) ? init_basis : -1);
             ctx->n_gate++;
         }
@@ -2591,7 +2597,10 @@ static int run_round(s17_ctx *ctx, const s17_run_args &a) {
     // an event-free first cycle of a shot that sits in a memoised preparation leaf is replayed from the cache as well
     ctx->use_quiet = ctx->use_prep && !ctx->no_quiet && ctx->any_quiet_leaf;
     ctx->pend_rec = false;
-    if (int rc = run_cycle(ctx, a, 0, 0, basis_index, 0, dense, explicit_collapse)) return rc;
+    {
+        Nvtx r("s17: preparation cycle");
+        if (int rc = run_cycle(ctx, a, 0, 0, basis_index, 0, dense, explicit_collapse)) return rc;
+    }
     if (explicit_collapse) { flush_record(ctx, n); collapse(ctx, n, ctx->active); }
     if (a.stop_stage == S17_STOP_AFTER_PREP) { flush_record(ctx, n); return S17_OK; }
     if (a.stop_stage == S17_STOP_CYCLE1_GATES) {
@@ -2599,7 +2608,10 @@ static int run_round(s17_ctx *ctx, const s17_run_args &a) {
         flush_record(ctx, n);
         return rc;
     }
-    if (int rc = run_cycle(ctx, a, 1, 0, -1, 0, dense, explicit_collapse)) return rc;
+    {
+        Nvtx r("s17: first noisy cycle");
+        if (int rc = run_cycle(ctx, a, 1, 0, -1, 0, dense, explicit_collapse)) return rc;
+    }
     if (a.stop_stage == S17_STOP_AFTER_CYCLE1) {
         flush_record(ctx, n);
         SCOPE(CAT_OTHER);
@@ -2610,6 +2622,7 @@ static int run_round(s17_ctx *ctx, const s17_run_args &a) {
     if (a.protocol == S17_PROTO_S2 || a.protocol == S17_PROTO_RTF) {
         if (explicit_collapse) { flush_record(ctx, n); collapse(ctx, n, ctx->active); }
         // s2: stab_ind=1 slots (CL:422); run-til-fail: cycle B reuses the stab_ind=0 probabilities (CL:92)
+        Nvtx r("s17: second noisy cycle");
         if (int rc = run_cycle(ctx, a, 2, a.protocol == S17_PROTO_S2 ? 1 : 0, -1, 0, dense, explicit_collapse)) return rc;
     }
     if (a.materialize) {
@@ -2618,6 +2631,7 @@ static int run_round(s17_ctx *ctx, const s17_run_args &a) {
         SCOPE(CAT_OTHER);
         k_pauli<<<n * 32, 256, 0, ctx->stream>>>(ctx->state, ctx->rec, ctx->ready);
     }
+    Nvtx r_read("s17: decode + read-out");
     ReadArgs ra;
     ra.forced = (int)a.forced;
     ra.folded = a.materialize ? 0 : 1;
@@ -2811,8 +2825,25 @@ extern "C" int s17_read_rtf_slots(s17_ctx *ctx, uint32_t *out /* n x {run_id, ro
     return S17_OK;
 }
 
+// Sum the counters of several contexts of ONE process (one context per GPU per host thread): the reduction the
+// reference's loops do with `failed_count += 1` across the whole run.  Across processes (one per GPU, torchrun) the same
+// sum is one all_reduce of these integers (surface_17_iqt_b200/distributed.py: NCCL over NVLink).
+extern "C" int s17_allreduce_counts(const s17_counts *per_ctx, int n_ctx, s17_counts *out) {
+    if (!per_ctx || !out || n_ctx <= 0) return fail(nullptr, S17_E_ARG, "s17_allreduce_counts: bad arguments");
+    s17_counts t;
+    memset(&t, 0, sizeof(t));
+    for (int i = 0; i < n_ctx; ++i) {
+        t.shots += per_ctx[i].shots; t.failed += per_ctx[i].failed; t.not0 += per_ctx[i].not0;
+        t.counted += per_ctx[i].counted; t.errors += per_ctx[i].errors; t.sweeps += per_ctx[i].sweeps;
+        t.rounds += per_ctx[i].rounds; t.sweep_bytes += per_ctx[i].sweep_bytes;
+    }
+    *out = t;
+    return S17_OK;
+}
+
 extern "C" int s17_run(s17_ctx *ctx, const s17_run_args *args, s17_counts *out) {
     if (!ctx || !args || !out) return fail(ctx, S17_E_ARG, "s17_run: bad arguments");
+    Nvtx r_run("s17_run");
     s17_run_args a = *args;
     if (a.protocol == S17_PROTO_RTF) {
         // poll the live-slot count every few rounds: the tail of a job (few live slots) is launch-bound, and a host

@@ -36,6 +36,13 @@ namespace s17 {
 #ifndef S17_DG_WARPS
 #define S17_DG_WARPS 12
 #endif
+#ifndef S17_DG_ST_UNROLL
+#define S17_DG_ST_UNROLL 1      // the six-step loop of a cycle (1: the transform and the half-cycle code exist once)
+#endif
+#ifndef S17_DG_HP_UNROLL
+#define S17_DG_HP_UNROLL 1      // the two passes of a transform
+#endif
+constexpr int kDgStUnroll = S17_DG_ST_UNROLL, kDgHpUnroll = S17_DG_HP_UNROLL;
 constexpr int kDgWarps = S17_DG_WARPS;                         // warps (= shots in flight) per SM
 constexpr int kDgThreads = kDgWarps * 32;
 constexpr int kDgFrmBytes = 16;                                // per-shot frame words (4 x u32, two used)
@@ -561,7 +568,7 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
         // twelve warps at different points of it has to stay inside the instruction cache).
         uint32_t carry = 0, perm = 0;
         double pfin = 1.0;
-#pragma unroll 1
+#pragma unroll kDgStUnroll
         for (int st = 0; st < 6; ++st) {
             const int h = st >= 3 ? 1 : 0, r = st - 3 * h;
             const DiagHalf &H = P.h[h];
@@ -588,7 +595,7 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
                 const int dir = r >> 1;                           // 0: map A -> B (into the frame), 1: map B -> A
                 const uint32_t wl = dir ? swzB : swzA, rl = dir ? swzA : swzB;
                 const uint32_t *wr = dir ? P.mapB.swz16 : P.mapA.swz16, *rr = dir ? P.mapA.swz16 : P.mapB.swz16;
-#pragma unroll 1
+#pragma unroll kDgHpUnroll
                 for (int half_pass = 0; half_pass < 2; ++half_pass) {
                     if (COH && dir) {
                         // back to the computational frame, with Ry(eps_a) of every data qubit merged into its butterfly

@@ -9,6 +9,7 @@
 // so HBM reads, FP64 math and HBM writes of different tiles overlap inside every SM.
 // Algorithmic traffic per (shot, sweep) is unchanged: 2 MiB read + 2 MiB write.
 #pragma once
+#include <cuda.h>
 #include "s17_kernels.cuh"
 
 #ifndef S17_MATH_THREADS
@@ -238,6 +239,45 @@ __device__ __forceinline__ void fast_item(double2 *tile, const PassGeom &g, int 
     }
 }
 
+// 2-D tensor-map TMA of one 8 KiB run (64 rows x 128 B) with the hardware 128-byte swizzle
+__device__ __forceinline__ void tma_load_run(void *dst_smem, const CUtensorMap *tm, int row, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(tm), "r"(0), "r"(row), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_run(const CUtensorMap *tm, int row, const void *src_smem) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tm), "r"(0),
+                 "r"(row), "r"(smem_u32(src_smem))
+                 : "memory");
+}
+
+// fast_item on the 128-byte-swizzled tile layout (tensor-map TMA): the item bits are deposited at PassC::pos so that a
+// quarter warp's 16-byte accesses land on eight different bank groups whatever data bit the pass holds in registers
+template <int KIND>
+__device__ __forceinline__ void fast_item_swz(double2 *tile, const PassGeom &g, const PassC &ps, int item, const FastC f1,
+                                              const FastC f2, double sc) {
+    double2 a[16];
+    {
+        int off[16];
+        item_offsets_swz<KIND>(g, ps, item, off);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) a[r] = tile[off[r]];
+    }
+    apply_fast<false>(a, f1.v1, f1.s, f1.sx, f1.v2);
+    if (KIND == 1) apply_fast<true>(a, f2.v1, f2.s, f2.sx, f2.v2);
+    {
+        // recompute the offsets instead of keeping 16 address registers live across the FP64 block
+        int item2 = item;
+        asm volatile("" : "+r"(item2));
+        int off[16];
+        item_offsets_swz<KIND>(g, ps, item2, off);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) tile[off[r]] = make_double2(a[r].x * sc, a[r].y * sc);
+    }
+}
+
 // everything else (Pauli events, leak-skipped Rxx, idle Z masks, coherent rotations): rare, kept out of line
 __device__ __noinline__ void slow_item(double2 *tile, const LayerArg2 *Pp, const PassC ps, const PassGeom g, int item,
                                        uint32_t w1, uint32_t w2, uint32_t zm, uint32_t lm, uint32_t c0, double sc,
@@ -285,7 +325,8 @@ __device__ __forceinline__ void tile_coords(const LayerArg &A, int tile_id, uint
 }
 
 __global__ void __launch_bounds__(kL2Threads, 1)
-k_layer2(double2 *__restrict__ state, const __grid_constant__ LayerArg2 P, const uint32_t *__restrict__ ev,
+k_layer2(const __grid_constant__ CUtensorMap tmap, double2 *__restrict__ state, const __grid_constant__ LayerArg2 P,
+         const uint32_t *__restrict__ ev,
          const uint32_t *__restrict__ act_list, const uint32_t *__restrict__ n_act_ptr, double *__restrict__ hist,
          unsigned long long *__restrict__ counters, const ShotAux *__restrict__ aux, const double2 *__restrict__ zero_page,
          int init_basis)
@@ -329,7 +370,7 @@ k_layer2(double2 *__restrict__ state, const __grid_constant__ LayerArg2 P, const
                 const uint32_t shot = act_list[item >> P.tile_shift];
                 uint32_t base, run_off[8];
                 tile_coords(P.A, P.tile_ids[item & tile_mask], base, run_off);
-                const double2 *sbase = state + (size_t)shot * kDim;
+                const int row0 = (int)(shot * (uint32_t)(kDim / 8));       // tensor-map row (8 amplitudes = 128 B) of the shot
                 double2 *tile = tiles + (size_t)b * kTile;
                 if (init_basis < 0) {
                     mbar_expect_tx(&full[b], kTile * 16 + kEvBytes + kAuxBytes);
@@ -337,14 +378,15 @@ k_layer2(double2 *__restrict__ state, const __grid_constant__ LayerArg2 P, const
                         // lazy collapse + reset: the only non-zero input is the surviving 512-amplitude block
                         const ShotAux ax = aux[shot];
                         const uint32_t blk = ax.collapsed ? 0u : ax.anc_outcome;
-                        tma_load_1d(tile, sbase + (size_t)blk * kRun, kRunBytes, &full[b]);
+                        tma_load_run(tile, &tmap, row0 + (int)blk * (kRun / 8), &full[b]);
 #pragma unroll
                         for (int r = 1; r < 8; ++r) tma_load_1d(tile + r * kRun, zero_page, kRunBytes, &full[b]);
                     } else {
 #pragma unroll
-                        for (int r = 0; r < 8; ++r)
-                            tma_load_1d(tile + r * kRun, ((P.in_runs >> r) & 1) ? sbase + run_off[r] : zero_page, kRunBytes,
-                                        &full[b]);
+                        for (int r = 0; r < 8; ++r) {
+                            if ((P.in_runs >> r) & 1) tma_load_run(tile + r * kRun, &tmap, row0 + (int)(run_off[r] >> 3), &full[b]);
+                            else tma_load_1d(tile + r * kRun, zero_page, kRunBytes, &full[b]);      // zeros in any layout
+                        }
                     }
                 } else {
                     mbar_expect_tx(&full[b], kEvBytes + kAuxBytes);
@@ -365,10 +407,10 @@ k_layer2(double2 *__restrict__ state, const __grid_constant__ LayerArg2 P, const
                 const uint32_t shot = act_list[item >> P.tile_shift];
                 uint32_t base, run_off[8];
                 tile_coords(P.A, P.tile_ids[item & tile_mask], base, run_off);
-                double2 *sbase = state + (size_t)shot * kDim;
+                const int row0 = (int)(shot * (uint32_t)(kDim / 8));
                 const double2 *tile = tiles + (size_t)b * kTile;
 #pragma unroll
-                for (int r = 0; r < 8; ++r) tma_store_1d(sbase + run_off[r], tile + r * kRun, kRunBytes);
+                for (int r = 0; r < 8; ++r) tma_store_run(&tmap, row0 + (int)(run_off[r] >> 3), tile + r * kRun);
                 tma_store_commit_and_wait_read();
                 mbar_arrive(&free_[b]);
             }
@@ -406,7 +448,7 @@ k_layer2(double2 *__restrict__ state, const __grid_constant__ LayerArg2 P, const
 #pragma unroll 4
             for (int i = 0; i < kTile / kGroupThreads; ++i) tile[tg + kGroupThreads * i] = make_double2(0.0, 0.0);
             group_barrier(grp);
-            if (tile_id == 0 && tg == 0) tile[init_basis] = make_double2(1.0, 0.0);
+            if (tile_id == 0 && tg == 0) tile[swz(init_basis)] = make_double2(1.0, 0.0);
             group_barrier(grp);
         }
 
@@ -454,13 +496,13 @@ k_layer2(double2 *__restrict__ state, const __grid_constant__ LayerArg2 P, const
                 const FastC f1 = fast_coeffs(c1), f2 = fast_coeffs(c2);
 #pragma unroll 1
                 for (int it = 0; it < kTile / 16 / kGroupThreads; ++it) {
-                    if (ps.kind == 1) fast_item<1>(tile, g, tg + kGroupThreads * it, f1, f2, sc);
-                    else fast_item<0>(tile, g, tg + kGroupThreads * it, f1, f2, sc);
+                    if (ps.kind == 1) fast_item_swz<1>(tile, g, ps, tg + kGroupThreads * it, f1, f2, sc);
+                    else fast_item_swz<0>(tile, g, ps, tg + kGroupThreads * it, f1, f2, sc);
                 }
             } else {
 #pragma unroll 1
                 for (int it = 0; it < kTile / 16 / kGroupThreads; ++it)
-                    slow_item(tile, &P, ps, g, tg + kGroupThreads * it, w1, w2, zm, lm, c0, sc);
+                    slow_item(tile, &P, ps, g, tg + kGroupThreads * it, w1, w2, zm, lm, c0, sc, true);
             }
             group_barrier(grp);
         }

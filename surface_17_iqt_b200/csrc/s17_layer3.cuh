@@ -17,20 +17,6 @@ constexpr int kL3Threads = 128;
 constexpr int kL3CtasPerSm = 3;
 constexpr size_t kL3Smem = (size_t)kTile * 16 + 2 * (kEvBytes + kAuxBytes) + 64;
 
-// 2-D tensor-map TMA of one 8 KiB run (64 rows x 128 B) with the hardware 128-byte swizzle
-__device__ __forceinline__ void tma_load_run(void *dst_smem, const CUtensorMap *tm, int row, uint64_t *bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-            smem_u32(dst_smem)),
-        "l"(tm), "r"(0), "r"(row), "r"(smem_u32(bar))
-        : "memory");
-}
-__device__ __forceinline__ void tma_store_run(const CUtensorMap *tm, int row, const void *src_smem) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tm), "r"(0),
-                 "r"(row), "r"(smem_u32(src_smem))
-                 : "memory");
-}
-
 // x-type operations (timesteps 1-4) have no Ry: two gate slots instead of four
 template <bool OP2>
 __device__ __forceinline__ void apply_fast_x(double2 (&a)[16], double s, double sx) {

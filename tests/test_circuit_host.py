@@ -169,3 +169,19 @@ def test_host_lowering_selects_the_whole_cycle_kernel(error_models):
     assert [i["k_cycle1"] for i in info] == [True, False, False] and not any(i["coherent"] for i in info)
     late = circuit.compile_program(error_models["PDD_model"], [12, 18, 24, 78, 24], fusion=2, early_measure=False)
     assert not any(i["k_half"] or i["k_cycle"] for i in backend.describe_program(late))
+
+
+def test_allreduce_counts_sums_contexts():
+    """s17_allreduce_counts: the host-side sum over the contexts of one process (no device needed)."""
+    import ctypes as C
+    from surface_17_iqt_b200 import _lib as L
+    lib = L.load()
+    parts = (L.Counts * 3)()
+    for i, c in enumerate(parts):
+        c.shots, c.failed, c.not0, c.counted, c.errors, c.sweeps, c.rounds, c.sweep_bytes = (
+            100 + i, 3 * i, 7 + i, 90 + i, 0, 200 * (i + 1), i, 1 << (20 + i))
+    out = L.Counts()
+    assert lib.s17_allreduce_counts(parts, 3, C.byref(out)) == 0
+    assert (out.shots, out.failed, out.not0, out.counted, out.sweeps, out.rounds) == (303, 9, 24, 273, 1200, 3)
+    assert out.sweep_bytes == (1 << 20) + (1 << 21) + (1 << 22)
+    assert lib.s17_allreduce_counts(parts, 0, C.byref(out)) != 0

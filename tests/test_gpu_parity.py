@@ -470,25 +470,31 @@ def test_dense_ring_kernel_stress(error_models, correction_table, bitflip_table,
 
 
 def test_depolarising_true_probability_statistics(error_models, correction_table, bitflip_table):
-    """BASELINE config 1 (depolarising_model, Bernoulli per slot, single round): failure rate within binomial 3 sigma
-    of the oracle's own sampling, and every device-sampled shot replays bit-exactly through the oracle."""
+    """BASELINE config 1 (depolarising_model, Bernoulli per slot, single round) at p = 0.02: failure rate and detection
+    rate of 2^17 device shots (geometric skipping, memoised event-free cycles) within 3.5 binomial sigma of 480 oracle
+    shots."""
     import surface_17_iqt_b200.calc_log_e_rate_arbitrary_error_model as drv
     p = 0.02
     p_set = [30 * [p / 3], 30 * [p / 3], 30 * [p / 3], 24 * [p]]
     drv.VERBOSE = False
-    drv.BATCH_SHOTS = 8192
-    rate, failed, counted, _ = drv.calculate_log_e_rate_true_probability(8192, correction_table, "depolarising_model",
-                                                                          p_set, bitflip_table)
+    drv.BATCH_SHOTS = 1 << 17
+    n = 1 << 17
+    rate, failed, counted, not0 = drv.calculate_log_e_rate_true_probability(n, correction_table, "depolarising_model",
+                                                                           p_set, bitflip_table)
     drv.release()
-    assert counted == 8192
+    assert counted == n
     orc = so.ShotOracle(error_models, correction_table, bitflip_table)
     rnd, mr = random.Random(5), random.Random(6)
-    m, ofail = 160, 0
+    m, ofail, onot0 = 480, 0, 0
     for _ in range(m):
-        ofail += orc.run_shot("depolarising_model", p_set, "single", rnd=rnd, meas=so.SampledMeasure(mr))["fail"]
-    pooled = (failed + ofail) / (counted + m)
-    assert abs(rate - ofail / m) < 3 * np.sqrt(pooled * (1 - pooled) * (1 / counted + 1 / m)) + 1e-9
-    assert 0.02 < rate < 0.6
+        r = orc.run_shot("depolarising_model", p_set, "single", rnd=rnd, meas=so.SampledMeasure(mr))
+        ofail += r["fail"]
+        onot0 += r["not0"]
+    # failure rate and detection rate (syndrome changed in the noisy cycle): 480 oracle shots resolve a factor-two error
+    # in either (sigma of the detection rate ~ 2.3 %, of the failure rate ~ 1.2 %)
+    for got, ref in ((rate, ofail / m), (not0 / n, onot0 / m)):
+        assert abs(got - ref) < 3.5 * np.sqrt(got * (1 - got) / m) + 1e-9, (got, ref)
+    assert 0.02 < rate < 0.6 and 0.2 < not0 / n < 0.95
 
 
 def test_run_til_fail_sweep_example():
