@@ -33,6 +33,7 @@ VERBOSE = True                                            # print the reference'
 _SIMS = {}
 _BATCH_OF = {}          # program key -> batch that fits (set when BATCH_SHOTS full-size states did not)
 LAST_TIMING = {}
+LAST_RESULTS = {}       # calculate_log_e_rate, rank 0: the per-run arrays of the last call (numpy; the JSON holds them as lists)
 
 
 def _log(*a):
@@ -328,42 +329,51 @@ def calculate_log_e_rate(num_runs, filename, correction_table, e_model, e_probs,
         span_ms = sim.backend.timing()["span_ms"]
     else:
         my_rounds, my_syndb, my_total, my_errors, span_ms = np.zeros(0, np.int64), np.zeros(0, np.int64), 0, 0, 0.0
-    rounds_arr = distributed.gather_lists(my_rounds)
-    syndb_arr = distributed.gather_lists(my_syndb)
+    # the per-run lists go to rank 0 only (it writes the file and fits); every rank gets the fit and the totals
+    rounds_arr = distributed.gather_to_root(my_rounds)
+    syndb_arr = distributed.gather_to_root(my_syndb)
     total_rounds, errors = distributed.allreduce_counts([my_total, my_errors])
     if errors:
         raise L.S17Error("{} rounds hit a zero-probability outcome".format(errors))
     total_time_taken = time.perf_counter() - t_begin
     _log('total time taken {}'.format(total_time_taken))
-    cens = rounds_arr == 0                                                    # cut short by round_budget
-    if max_rounds:
-        cens |= rounds_arr >= max_rounds
-    censored = np.nonzero(cens)[0].tolist()
-    round_count_list, syndrome_b_list = rounds_arr.tolist(), syndb_arr.tolist()
-    results = {
-        'total_time_taken_{}_runs'.format(num_runs): total_time_taken,
-        'probability_set': e_probs,
-        'rounds_til_fail_list': round_count_list,
-        'syndrome_b_measured_list': syndrome_b_list,
-        'rounds_til_fail_list_X0': [], 'rounds_til_fail_list_X1': [],
-        'rounds_til_fail_list_Z0': round_count_list, 'rounds_til_fail_list_Z1': [],
-        'error_model': e_model,
-    }
-    if censored:
-        results['censored_runs'] = censored
-    results['total_rounds'] = int(total_rounds)
     LAST_TIMING.update(rounds=int(total_rounds), span_ms=span_ms)
-    if save and rank == 0:
-        os.makedirs("data", exist_ok=True)
-        with open(os.path.join("data", filename + '.json'), 'w') as file:
-            json.dump(results, file)
+    log_e_rate, fit_error = None, ""
+    if rank == 0:
+        cens = rounds_arr == 0                                                # cut short by round_budget
+        if max_rounds:
+            cens |= rounds_arr >= max_rounds
+        LAST_RESULTS.clear()
+        LAST_RESULTS.update(rounds_til_fail=rounds_arr, syndrome_b_measured=syndb_arr, censored=cens,
+                            total_rounds=int(total_rounds))
+        if save:
+            round_count_list, syndrome_b_list = rounds_arr.tolist(), syndb_arr.tolist()
+            results = {
+                'total_time_taken_{}_runs'.format(num_runs): total_time_taken,
+                'probability_set': e_probs,
+                'rounds_til_fail_list': round_count_list,
+                'syndrome_b_measured_list': syndrome_b_list,
+                'rounds_til_fail_list_X0': [], 'rounds_til_fail_list_X1': [],
+                'rounds_til_fail_list_Z0': round_count_list, 'rounds_til_fail_list_Z1': [],
+                'error_model': e_model,
+            }
+            if cens.any():
+                results['censored_runs'] = np.nonzero(cens)[0].tolist()
+            results['total_rounds'] = int(total_rounds)
+            os.makedirs("data", exist_ok=True)
+            with open(os.path.join("data", filename + '.json'), 'w') as file:
+                json.dump(results, file)
+        if fit:
+            done = {'rounds_til_fail_list': rounds_arr[~cens], 'syndrome_b_measured_list': syndb_arr[~cens]}
+            try:
+                log_e_rate = float(fit_log_e_rate(done, num_bins)[0])
+            except RuntimeError as exc:            # scipy: "Optimal parameters not found" -- every rank must hear of it
+                log_e_rate, fit_error = float('nan'), str(exc)
     if not fit:
         return None
-    done = dict(results)
-    if censored:
-        done['rounds_til_fail_list'] = rounds_arr[~cens].tolist()
-        done['syndrome_b_measured_list'] = syndb_arr[~cens].tolist()
-    log_e_rate, _A, _vals, _bins = fit_log_e_rate(done, num_bins)
+    log_e_rate = distributed.broadcast_float(log_e_rate)
+    if log_e_rate != log_e_rate:
+        raise RuntimeError("exponential fit of the rounds-til-fail histogram failed" + (": " + fit_error if fit_error else ""))
     return log_e_rate
 
 

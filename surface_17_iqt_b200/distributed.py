@@ -102,3 +102,45 @@ def gather_lists(values):
     dist.all_gather(parts, mine)
     out = np.concatenate([part[:sz].cpu().numpy() for sz, part in zip(sizes, parts)]) if sizes else np.zeros(0, np.int64)
     return out if as_array else [int(v) for v in out]
+
+
+def gather_to_root(values):
+    """Rank 0 receives the concatenation (rank order) of one int64 array per rank; the other ranks get an empty array."""
+    import numpy as np
+    values = np.asarray(values, dtype=np.int64)
+    try:
+        import torch
+        import torch.distributed as dist
+    except ImportError:
+        return values
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return values
+    dev = _group_device(dist)
+    rank, world = dist.get_rank(), dist.get_world_size()
+    n = torch.tensor([len(values)], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(sizes, n)
+    sizes = [int(v.item()) for v in sizes]
+    pad = max(sizes) if sizes else 0
+    mine = torch.zeros(pad, dtype=torch.int64, device=dev)
+    if len(values):
+        mine[:len(values)] = torch.as_tensor(values, device=dev)
+    parts = [torch.zeros(pad, dtype=torch.int64, device=dev) for _ in sizes] if rank == 0 else None
+    dist.gather(mine, parts, dst=0)
+    if rank != 0:
+        return np.zeros(0, np.int64)
+    return np.concatenate([part[:sz].cpu().numpy() for sz, part in zip(sizes, parts)])
+
+
+def broadcast_float(value):
+    """Rank 0's float (None allowed on the others) on every rank."""
+    try:
+        import torch
+        import torch.distributed as dist
+    except ImportError:
+        return value
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return value
+    t = torch.tensor([float(value) if value is not None else 0.0], dtype=torch.float64, device=_group_device(dist))
+    dist.broadcast(t, src=0)
+    return float(t.item())

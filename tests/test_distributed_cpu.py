@@ -55,7 +55,12 @@ WORKER = textwrap.dedent("""
     seed = distributed.broadcast_seed(0xFEDCBA9876543210 + rank)
     runs_first, runs = distributed.shard_range(7, rank, world)
     lists = distributed.gather_lists([100 * rank + i for i in range(runs)])
+    root = distributed.gather_to_root([100 * rank + i for i in range(runs)]).tolist()
+    assert (rank == 0) == (len(root) == 7)
+    fit = distributed.broadcast_float(0.25 if rank == 0 else None)
+    assert fit == 0.25
     if rank == 0:
+        assert root == lists
         print(json.dumps(total + [seed] + lists))
     dist.destroy_process_group()
 """)
