@@ -133,8 +133,29 @@ def _run_subset(*args):
     return _with_batch_retry(lambda: _run_subset_once(*args))
 
 
+def subset_sweep(protocol, num_runs, correction_table, model, esets, locations, bitflip_table, prob_lists,
+                 cooling=False):
+    """Every error subset of `esets` through the loop of the s1 / s2 / single driver (CL:261-353, 355-457, 183-259) with
+    ONE exchange for the whole sweep: the ranks' int64[n_subsets x 4] counter array (failed, not0, counted, errors) is
+    all-reduced once at the end (SURVEY 5) instead of once per subset.  Returns one (failed, not0, counted) per subset;
+    the rates are the callers' (failed / (runs - not0) for s1, failed / not0 for s2, failed / runs for single)."""
+    local = []
+    for eset in esets:
+        local.extend(_with_batch_retry(lambda e=eset: _run_subset_once(
+            protocol, num_runs, correction_table, model, list(e), locations, bitflip_table, prob_lists, False, cooling,
+            False)))
+    total = distributed.allreduce_counts(local)
+    out = []
+    for k in range(len(esets)):
+        failed, not0, counted, errors = total[4 * k:4 * k + 4]
+        if errors:
+            raise L.S17Error("{} shots of subset {} hit a zero-probability outcome".format(errors, list(esets[k])))
+        out.append((failed, not0, counted))
+    return out
+
+
 def _run_subset_once(protocol, num_runs, correction_table, model, eset, locations, bitflip_table, prob_lists, cz_comp,
-                     cooling):
+                     cooling, reduce=True):
     if cz_comp:
         raise NotImplementedError("the experimental CZ compilation is outside the accelerated path (SURVEY C-9)")
     if len(eset) != len(locations) or len(prob_lists) != len(eset):
@@ -158,6 +179,10 @@ def _run_subset_once(protocol, num_runs, correction_table, model, eset, location
         sweeps, launches = sweeps + c.sweeps, launches + t["launches"]
         sweep_bytes += c.sweep_bytes
         done += n
+    if not reduce:                       # subset_sweep: the caller reduces the counters of the whole sweep at once
+        LAST_TIMING.update(gate_ms=gate_ms, span_ms=span_ms, sweeps=sweeps, sweep_bytes=sweep_bytes, launches=launches,
+                           shots=count)
+        return [failed, not0, counted, errors]
     # the error count rides in the reduced vector: every rank leaves the collective before any of them raises
     failed, not0, counted, errors = distributed.allreduce_counts([failed, not0, counted, errors])
     if errors:

@@ -268,3 +268,21 @@ def test_cycle_kernel_block_equals_reference_block(error_models, correction_tabl
             checked += 1
         sim.close()
     assert checked == len(reps) >= 36
+
+
+def test_subset_sweep_equals_the_per_subset_drivers(error_models, correction_table, bitflip_table):
+    """subset_sweep (one counter exchange for a whole sweep of subsets) returns, subset by subset, what the s2 driver
+    returns for the same seeds."""
+    import surface_17_iqt_b200.calc_log_e_rate_arbitrary_error_model as drv
+    drv.VERBOSE = False
+    locs = [24, 36, 48, 156, 48]
+    probs = [[1e-4], [1e-4], [5e-3], [1e-3], [5e-3]]
+    esets = [[0, 0, 1, 0, 0], [0, 0, 2, 0, 0], [1, 1, 1, 1, 0]]
+    random.seed(2026)
+    sweep = drv.subset_sweep("s2", 20000, correction_table, "PDD_model", esets, locs, bitflip_table, probs)
+    random.seed(2026)
+    single = [drv.s2_calculate_log_e_rate_error_subset(20000, correction_table, "PDD_model", e, locs, bitflip_table, probs)
+              for e in esets]
+    drv.release()
+    assert [(f, n0) for f, n0, _c in sweep] == [(r[2], r[3]) for r in single]
+    assert all(c == n0 for _f, n0, c in sweep) and sweep[0][0] == 0           # s2 counts the shots that went on; distance 3
