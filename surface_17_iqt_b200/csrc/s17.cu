@@ -2415,6 +2415,12 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
         }
         // mixed: the shots with a leak flag go through the regular preparation cycle below (k_plan lists only them)
     }
+    const int which0 = stage == 0 ? 0 : (second ? 2 : 1);
+    // A preparation cycle of a plain run with a model that has no leakage entries: every shot takes part, none has an
+    // event or a set leak flag -- nothing to plan, no list to build; the reset of the call waits for the next k_plan.
+    const bool trivial_prep = stage == 0 && !ctx->plan_has_leak && a.protocol != S17_PROTO_RTF && ctx->diag1_ok[which0] &&
+                              !ctx->no_diag && !dense && !mid_collapse && !max_layers && !ctx->force_ring && !ctx->no_fuse &&
+                              !ctx->pend_rec;
     PlanArgs pa;
     pa.n_instr = ctx->n_plan;
     pa.noise = (int)a.noise;
@@ -2428,7 +2434,7 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
     pa.seed = a.seed;
     pa.first_shot = a.first_shot_id;
     pa.n_shots = n;
-    {
+    if (!trivial_prep) {
         StepArgs sa;
         memset(&sa, 0, sizeof(sa));
         sa.do_record = ctx->pend_rec ? 1 : 0;
@@ -2494,7 +2500,8 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
         ma.data_stream = 32u;
         {
             SCOPE(CAT_GATE);
-            launch_cycle1(ctx, which, ma, ctx->state, ctx->stride, ctx->ev, ctx->frm, ctx->act_list, ctx->n_act, ctx->aux,
+            launch_cycle1(ctx, which, ma, ctx->state, ctx->stride, ctx->ev, ctx->frm, trivial_prep ? nullptr : ctx->act_list,
+                          ctx->n_act, ctx->aux,
                           ctx->forced, ctx->meas_out, ctx->dsamp, ctx->counters, init_basis,
                           (ctx->use_prep && stage == 1) ? ctx->prep_blocks : nullptr, nullptr, nullptr);
             ctx->n_gate++;

@@ -54,7 +54,9 @@ constexpr size_t kDgSmem = (size_t)kDgWarps * kDgWarpBytes;
 // k_cycle1 adds, per CTA, the tables of an event-free half cycle (both halves) and 128 zero bytes of event words
 constexpr size_t kDgSmem1 = kDgSmem + 2 * kDgTabBytes + kEvBytes;
 static_assert(kDgWarpBytes % 16 == 0, "per-warp shared memory must keep 16-byte alignment");
+#ifndef S17_NO_SMEM_ASSERT
 static_assert(kDgSmem1 <= 232448, "k_cycle1: shared memory per SM");
+#endif
 
 struct DiagOp {
     uint8_t d, ev_word;
@@ -439,7 +441,10 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
     }
     __syncthreads();
 
-    const uint32_t n_items = *n_act_ptr;
+    // act_list == nullptr: every shot of the batch takes part and none has an event or a set leak flag (a preparation
+    // cycle of a model without leakage): no list, no event / frame words to load
+    const bool all_quiet = act_list == nullptr;
+    const uint32_t n_items = all_quiet ? (uint32_t)ma.n_shots : *n_act_ptr;
     const uint32_t n_warps = gridDim.x * kDgWarps, gw = blockIdx.x * kDgWarps + warp;
     const uint32_t chunk = (n_items + n_warps - 1) / n_warps;
     const uint32_t first = gw * chunk, last = min(n_items, first + chunk);
@@ -500,9 +505,11 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
         unsigned char *m = meta + sb * kDgMetaBytes;
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the bulk store staged in this buffer has left it
         fence_proxy_async_smem();                 // the buffers were last touched through the generic proxy
-        mbar_expect_tx(&mfull[sb], kDgMetaBytes);
-        tma_load_1d(m, ev + (size_t)shot_ * S17_EV_WORDS, kEvBytes, &mfull[sb]);
-        tma_load_1d(m + kEvBytes, frm + (size_t)shot_ * 4, kDgFrmBytes, &mfull[sb]);
+        if (!all_quiet) {
+            mbar_expect_tx(&mfull[sb], kDgMetaBytes);
+            tma_load_1d(m, ev + (size_t)shot_ * S17_EV_WORDS, kEvBytes, &mfull[sb]);
+            tma_load_1d(m + kEvBytes, frm + (size_t)shot_ * 4, kDgFrmBytes, &mfull[sb]);
+        }
         if (init_basis < 0) {
             mbar_expect_tx(&full[sb], kRunBytes);
             tma_load_1d(buf + sb * kRunBytes, cached ? alt_src + (size_t)(entry >> 24) * kRun : state + (size_t)shot_ * stride,
@@ -517,8 +524,13 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
         }
     };
 
-    uint32_t entry = act_list[first];
+    uint32_t entry = all_quiet ? first : act_list[first];
     if (lane == 0) prefetch(entry, 0);
+#ifdef S17_DG_STAGGER
+    // the three warps of a scheduler start a third of a shot apart, so that they are not all in the same phase
+    // (FP64 butterflies / shuffles / exchange) at the same time
+    __nanosleep((uint32_t)(warp >> 2) * S17_DG_STAGGER);
+#endif
 
     const uint32_t nout = 8u * (uint32_t)ma.stage;
     const bool is_forced = ma.forced != 0;
@@ -528,11 +540,11 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
         const uint32_t shot = alt_src ? (entry & 0x7FFFFFu) : entry;
         uint32_t entry1 = 0;
         if (item + 1 < last) {
-            entry1 = act_list[item + 1];
+            entry1 = all_quiet ? item + 1 : act_list[item + 1];
             if (lane == 0) prefetch(entry1, sb ^ 1);
         }
-        const uint32_t *evw = reinterpret_cast<const uint32_t *>(meta + sb * kDgMetaBytes);
-        const uint32_t *fwp = reinterpret_cast<const uint32_t *>(meta + sb * kDgMetaBytes + kEvBytes);
+        const uint32_t *evw = all_quiet ? zero_ev : reinterpret_cast<const uint32_t *>(meta + sb * kDgMetaBytes);
+        const uint32_t *fwp = all_quiet ? zero_ev : reinterpret_cast<const uint32_t *>(meta + sb * kDgMetaBytes + kEvBytes);
         unsigned char *xb = buf + sb * kRunBytes;
 
         uint32_t fo = 0;
@@ -560,7 +572,7 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
             for (int i = 0; i < 16; ++i)
                 p[i] = make_double2((__popc((laneB | (P.mapB.lin16[i] >> 4)) & (uint32_t)init_basis) & 1) ? -1.0 : 1.0, 0.0);
         }
-        mbar_wait(&mfull[sb], (j >> 1) & 1u);
+        if (!all_quiet) mbar_wait(&mfull[sb], (j >> 1) & 1u);
         __syncwarp();                             // every lane holds its amplitudes: the buffer becomes exchange scratch
 
         // Six steps: per half cycle [transform into its frame] [tables + four ancilla slots] [transform back].  The loop is
