@@ -286,3 +286,23 @@ def test_subset_sweep_equals_the_per_subset_drivers(error_models, correction_tab
     drv.release()
     assert [(f, n0) for f, n0, _c in sweep] == [(r[2], r[3]) for r in single]
     assert all(c == n0 for _f, n0, c in sweep) and sweep[0][0] == 0           # s2 counts the shots that went on; distance 3
+
+
+def test_per_kernel_class_timing(error_models, correction_table, bitflip_table, monkeypatch):
+    """s17_last_timing_detail: the full-state mode materialises one collapse per shot after the preparation cycle and one
+    per shot that goes on to a second cycle, samples three All(Measure)s, and the classes' device times are part of the
+    measurement time of s17_last_timing."""
+    monkeypatch.setenv("S17_DENSE", "1")
+    locs = [24, 36, 48, 156, 48]
+    n = 64
+    sim = api.Simulation("PDD_model", locs, max_shots=n, fusion=1, correction_table=correction_table,
+                         bitflip_table=bitflip_table, error_models=error_models, early_measure=False)
+    sim.backend.set_subset([0, 0, 2, 1, 1], locs)
+    c = sim.backend.run("s2", n, L.NOISE_SUBSET, seed=3)
+    t = sim.backend.timing()
+    cl = t["classes"]
+    assert cl["collapse"]["launches"] == 2 and cl["collapse"]["units"] == n + c.not0
+    assert cl["sample"]["launches"] == 3 and cl["plan"]["launches"] == 3
+    assert 0 < cl["collapse"]["ms"] + cl["sample"]["ms"] <= t["measure_ms"] + 1e-6
+    assert t["gate_launches"] == 24 and c.sweeps == 8 * (2 * n + c.not0)
+    sim.close()
