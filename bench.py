@@ -460,7 +460,9 @@ def run_gpu(args):
                 "traffic": traffic,
                 "traffic_source": counts.get("source"),
                 "binding_unit": "fp64 pipe", "fp64": fp64,
-                "note": "one launch = one stabiliser cycle of every active shot: 8 KiB read (none in the preparation "
+                "note": "round 2 removed FP64 work (1810 -> 1168 warp instructions per shot-cycle) faster than it removed time, "
+                        "so the pipe fraction is lower than round 1's 0.48 while the kernel is 23 % faster per shot-cycle.  "
+                        "One launch = one stabiliser cycle of every active shot: 8 KiB read (none in the preparation "
                         "cycle) + 8 KiB written per shot, everything else in registers / shared memory, so the HBM "
                         "fraction is low by construction; the unit that binds is the FP64 pipe (`fp64`: counted FP64 warp "
                         "instructions x 0.5 clock / kernel time).  SURVEY 8(d)'s per-layer bytes (4 194 304 per gate layer, "
