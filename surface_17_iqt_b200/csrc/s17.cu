@@ -1076,6 +1076,7 @@ struct s17_ctx {
     DiagCoh diag_coh[3];              // coherent over-rotations of a cycle that runs on k_cycle1<true>
     bool coh_ok[3] = {false, false, false};
     bool no_coh = false;              // S17_COH=0: coherent models keep the sweep kernels
+    bool no_trivial_prep = false;     // S17_TRIVIAL_PREP=0: plan the preparation cycle of a leak-free model like any other
     bool no_diag = false;
     bool last_collapsed = true;       // the previous cycle left every active shot collapsed to ancilla block 0
     uint32_t *frm = nullptr;          // per shot: frame words of the two half cycles (k_plan -> k_cycle)
@@ -1277,6 +1278,8 @@ extern "C" int s17_create(s17_ctx **out, int device, uint64_t max_shots) {
         ctx->quiet_copy = qcp && qcp[0] == '1';
         const char *r = getenv("S17_RING");
         ctx->force_ring = r && r[0] == '1';
+        const char *tp = getenv("S17_TRIVIAL_PREP");
+        ctx->no_trivial_prep = tp && tp[0] == '0';
         const char *ge = getenv("S17_GEO");               // 0: one Bernoulli draw per entry instead of geometric skipping
         ctx->no_geo = ge && ge[0] == '0';
     }
@@ -2420,7 +2423,7 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
     // event or a set leak flag -- nothing to plan, no list to build; the reset of the call waits for the next k_plan.
     const bool trivial_prep = stage == 0 && !ctx->plan_has_leak && a.protocol != S17_PROTO_RTF && ctx->diag1_ok[which0] &&
                               !ctx->no_diag && !dense && !mid_collapse && !max_layers && !ctx->force_ring && !ctx->no_fuse &&
-                              !ctx->pend_rec;
+                              !ctx->pend_rec && !ctx->no_trivial_prep;
     PlanArgs pa;
     pa.n_instr = ctx->n_plan;
     pa.noise = (int)a.noise;
