@@ -19,7 +19,10 @@
 namespace s17 {
 
 constexpr int kMathThreads = S17_MATH_THREADS;
-constexpr int kGroups = 2;                          // independent math groups, each on its own tile
+#ifndef S17_MATH_GROUPS
+#define S17_MATH_GROUPS 2
+#endif
+constexpr int kGroups = S17_MATH_GROUPS;            // independent math groups, each on its own tile
 constexpr int kGroupThreads = kMathThreads / kGroups;
 constexpr int kL2Threads = kMathThreads + 64;      // + loader warp + storer warp
 constexpr int kRing = 3;
