@@ -2236,6 +2236,17 @@ static void launch_cycle1(s17_ctx *ctx, int which, const MeasArgs &ma, double2 *
                                                                             dsamp, counters, init_basis, alt_src, pp_out, cdf_out);
 }
 
+// device scratch of a host-side set-up step: released when the scope ends, whichever way it ends
+struct DevScratch {
+    std::vector<void *> ptrs;
+    ~DevScratch() { for (void *q : ptrs) cudaFree(q); }
+    template <class T> cudaError_t alloc(T **out, size_t bytes) {
+        const cudaError_t e = cudaMalloc(out, bytes);
+        if (e == cudaSuccess) ptrs.push_back(*out);
+        return e;
+    }
+};
+
 // Build the memoised preparation cycle for `basis`: run the production kernel once per outcome pattern (256 forced shots
 // on private buffers), keep the collapsed blocks and the probability pair of every Measure along the way.
 static int build_prep_cache(s17_ctx *ctx, int basis) {
@@ -2247,16 +2258,17 @@ static int build_prep_cache(s17_ctx *ctx, int basis) {
     ShotAux *aux = nullptr;
     double *pp = nullptr;
     unsigned long long *cnt = nullptr;
-    CK(cudaMalloc(&ev, N * S17_EV_WORDS * 4));
-    CK(cudaMalloc(&frm, N * 16));
-    CK(cudaMalloc(&list, N * 4));
-    CK(cudaMalloc(&nact, 4));
-    CK(cudaMalloc(&mo, N * 8));
-    CK(cudaMalloc(&ds, N * 4));
-    CK(cudaMalloc(&forced, N * S17_MAX_OUTCOMES));
-    CK(cudaMalloc(&aux, N * sizeof(ShotAux)));
-    CK(cudaMalloc(&pp, N * 16 * sizeof(double)));
-    CK(cudaMalloc(&cnt, C_N * sizeof(unsigned long long)));
+    DevScratch scratch;                               // freed on every exit path (CK returns early on a CUDA error)
+    CK(scratch.alloc(&ev, N * S17_EV_WORDS * 4));
+    CK(scratch.alloc(&frm, N * 16));
+    CK(scratch.alloc(&list, N * 4));
+    CK(scratch.alloc(&nact, 4));
+    CK(scratch.alloc(&mo, N * 8));
+    CK(scratch.alloc(&ds, N * 4));
+    CK(scratch.alloc(&forced, N * S17_MAX_OUTCOMES));
+    CK(scratch.alloc(&aux, N * sizeof(ShotAux)));
+    CK(scratch.alloc(&pp, N * 16 * sizeof(double)));
+    CK(scratch.alloc(&cnt, C_N * sizeof(unsigned long long)));
     CK(cudaMemset(ev, 0, N * S17_EV_WORDS * 4));
     CK(cudaMemset(frm, 0, N * 16));
     CK(cudaMemset(cnt, 0, C_N * sizeof(unsigned long long)));
@@ -2359,9 +2371,6 @@ static int build_prep_cache(s17_ctx *ctx, int basis) {
         }
     }
     CK(cudaMemcpy(ctx->quiet_ok, quiet_ok.data(), N, cudaMemcpyHostToDevice));
-    for (void *q : {(void *)ev, (void *)frm, (void *)list, (void *)nact, (void *)mo, (void *)ds, (void *)forced, (void *)aux,
-                    (void *)pp, (void *)cnt})
-        cudaFree(q);
     ctx->prep_basis = basis;
     return S17_OK;
 }
