@@ -306,3 +306,42 @@ def test_per_kernel_class_timing(error_models, correction_table, bitflip_table, 
     assert 0 < cl["collapse"]["ms"] + cl["sample"]["ms"] <= t["measure_ms"] + 1e-6
     assert t["gate_launches"] == 24 and c.sweeps == 8 * (2 * n + c.not0)
     sim.close()
+
+
+@pytest.mark.parametrize("switch", ["S17_TRIVIAL_PREP", "S17_GEO"])
+def test_launch_shortcuts_do_not_change_results(error_models, correction_table, bitflip_table, switch, monkeypatch):
+    """S17_TRIVIAL_PREP (no planning launch and no shot list for the preparation cycle of a leak-free model; the call's
+    reset rides in the next k_plan) gives bit-identical counters, records, masks and stored blocks with every cycle
+    computed per shot.  S17_GEO (geometric skipping over the survival products instead of one Bernoulli draw per entry)
+    draws other uniforms, so the trajectories differ: the rates of 2^18 true-probability shots agree within 4 sigma."""
+    monkeypatch.setenv("S17_PREP_CACHE", "0")
+    locs = [24, 36, 48, 156, 48]
+    out = {}
+    for val in ("1", "0"):
+        monkeypatch.setenv(switch, val)
+        if switch == "S17_TRIVIAL_PREP":
+            n = 4096
+            sim = make_sim(error_models, correction_table, bitflip_table, "PDD_model", locs, n)
+            sim.backend.set_subset([0, 1, 2, 1, 1], locs)
+            c = sim.backend.run("s2", n, L.NOISE_SUBSET, seed=31, first_shot_id=777)
+            out[val] = ((c.failed, c.not0, c.counted, c.errors, c.sweeps), sim.backend.records(n),
+                        sim.backend.masks_packed(n)[:, :L.MASK_WORDS].copy(),
+                        np.stack([sim.backend.state(i)[:512] for i in range(0, n, 128)]),
+                        sim.backend.timing()["launches"])
+        else:
+            n = 1 << 18
+            per_round = [12, 18, 24, 78, 24]
+            sim = make_sim(error_models, correction_table, bitflip_table, "PDD_model", per_round, n)
+            sim.backend.set_slot_probs([[2e-3] * 12, [2e-3] * 18, [2e-2] * 24, [2e-3] * 78, [2e-3] * 24])
+            c = sim.backend.run("s1", n, L.NOISE_PROB, seed=31)
+            out[val] = (c.failed, c.not0, c.counted)
+        sim.close()
+    if switch == "S17_TRIVIAL_PREP":
+        assert out["1"][0] == out["0"][0] and out["1"][1] == out["0"][1]
+        assert np.array_equal(out["1"][2], out["0"][2]) and np.array_equal(out["1"][3], out["0"][3])
+        assert out["1"][4] == out["0"][4] - 1                     # one launch less
+    else:
+        for k in (0, 1):
+            a, b = out["1"][k] / n, out["0"][k] / n
+            assert abs(a - b) < 4 * np.sqrt((a * (1 - a) + b * (1 - b)) / n) + 1e-9, (k, a, b)
+        assert 0.05 < out["1"][1] / n < 0.95
