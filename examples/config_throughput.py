@@ -6,7 +6,7 @@ host arguments in, host results out), one JSON line per shape.  Needs a B200.
 
 1  depolarising_model, true-probability noise p = 1e-3, single round            (config 1; the reference's CPU case)
 2  PDD_model, fixed-weight subset [0,0,2,1,1], s2 protocol, uniform placement     (config 2; the bench workload)
-3  coherent_model: over-rotations eps = 0.02 on every gate + stochastic XX        (config 3; general amplitude kernels)
+3  coherent_model: over-rotations eps = 0.02 on every gate + stochastic XX        (config 3; coherent form of the cycle kernel)
 4a PDD_model with linear motional heating, non-uniform placement, s2              (config 4, importance_sampling_...py:20-36)
 4b Dress_cooling with sympathetic cooling (119 idle slots per round), s2          (config 4, ..._cooling_...py:19-21)
 5  Dress_model (leakage), run-til-fail, p = 1e-2                                   (config 5, vary_p.py)
