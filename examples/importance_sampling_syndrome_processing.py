@@ -64,6 +64,9 @@ def run_pipeline(model="PDD_model", runs=10000, cutoff=1e-6, out="imp_samp", ver
                                                                       time.perf_counter() - t0))
     # stage: one round per significant subset (IS:78-92)
     s1_rate, s2_rate, failcount, s2count = {}, {}, {}, {}
+    # (one small untimed call first: library load, CUDA context, program upload -- seconds, once per process)
+    CL.s1_calculate_log_e_rate_error_subset(64, correction_table, model, subsets_s1["error_subset_list"][0], locations,
+                                            bitflip_table, pl_s1, cooling=cooling)
     t0 = time.perf_counter()
     for eset in subsets_s1["error_subset_list"]:
         r = CL.s1_calculate_log_e_rate_error_subset(runs, correction_table, model, eset, locations, bitflip_table, pl_s1,
