@@ -248,11 +248,13 @@ int s17_last_timing(s17_ctx *ctx, double *gate_ms, double *measure_ms, double *o
  * precedes the Measure) */
 enum { S17_T_COLLAPSE = 0,   /* k_collapse: ProjectQ's collapse + renormalise + reset, materialised */
        S17_T_SAMPLE = 1,     /* k_measure: the Measure gates of one All(Measure) from the joint weights */
-       S17_T_PLAN = 2,       /* k_plan: error insertion (insert_errors / insert_error) -> per-operation events */
-       S17_T_COMPACT = 3,    /* k_compact */
-       S17_T_RECORD = 4,     /* k_record: leak override, protocol branch, lookup decode */
+       S17_T_PLAN = 2,       /* k_plan: error insertion (insert_errors / insert_error) -> per-operation events; in the
+                                whole-cycle path also the previous cycle's bookkeeping, the shot list, the call's
+                                reset and the fixed-weight placement (one launch between two cycle kernels) */
+       S17_T_COMPACT = 3,    /* (unused since the shot list is built inside k_plan) */
+       S17_T_RECORD = 4,     /* k_record: leak override, protocol branch, lookup decode -- only where it runs on its own */
        S17_T_READOUT = 5,    /* k_readout / k_readout_s: logical_measurement */
-       S17_T_PLACE = 6,      /* k_reset + k_place: generate_error_locations(_non_uniform) */
+       S17_T_PLACE = 6,      /* k_reset: per-shot reset (+ generate_error_locations(_non_uniform) for a run-til-fail job) */
        S17_T_N = 8 };
 int s17_last_timing_detail(s17_ctx *ctx, double *ms, uint64_t *launches,
                            uint64_t *units /* NULL, or [S17_T_COLLAPSE] = shots whose collapse was materialised */);
