@@ -259,3 +259,164 @@ def diag_half(psi512, ops, words, frame_x, idle=None):
             out[a] = o
     factor = SQ ** n_factors / (512.0 if frame_x else 1.0)
     return out, factor
+
+
+# ---- coherent over-rotations (the `*_over` entries; k_cycle1<true>) -----------------------------------------------------
+def rot(name, theta):
+    c, s = np.cos(0.5 * theta), np.sin(0.5 * theta)
+    if name == "x":
+        return np.array([[c, -1j * s], [-1j * s, c]], dtype=complex)
+    return np.array([[c, -s], [s, c]], dtype=complex)          # "y"
+
+
+def apply_xx_angle(psi, bd, ba, theta):
+    idx = np.arange(psi.size)
+    flipped = psi[idx ^ ((1 << bd) | (1 << ba))]
+    psi[:] = np.cos(0.5 * theta) * psi - 1j * np.sin(0.5 * theta) * flipped
+
+
+def brute_half_coh(psi512, ops, words, eps):
+    """Gate by gate with over-rotations: every gate is followed by the same-axis rotation eps[i][gate] (gate in
+    'ry1', 'rxx', 'rx', 'ry2'), then by its event field -- the order of the `*_over` entries and the stochastic entries in
+    an error model (coherent first).  A leak-skipped Rxx skips its over-rotation and its field too."""
+    psi = np.zeros(1 << 13, dtype=complex)
+    psi[:512] = psi512
+    for op, w, e in zip(ops, words, eps):
+        bd, ba, s, shape = op["d"], 9 + op["slot"], op["s"], op["shape"]
+        skip = (w >> 24) & 1
+        if shape & 1:
+            apply_1q(psi, bd, ry(+1))
+            apply_1q(psi, bd, rot("y", e["ry1"]))
+            apply_field(psi, w & 63, bd, ba)
+        if not skip:
+            apply_xx(psi, bd, ba, s)
+            apply_xx_angle(psi, bd, ba, e["rxx"])
+            apply_field(psi, (w >> 6) & 63, bd, ba)
+        if shape & 2:
+            apply_1q(psi, bd, rx(-s))
+            apply_1q(psi, bd, rot("x", e["rx"]))
+            apply_field(psi, (w >> 12) & 63, bd, ba)
+        if shape & 4:
+            apply_1q(psi, bd, ry(-1))
+            apply_1q(psi, bd, rot("y", e["ry2"]))
+            apply_field(psi, (w >> 18) & 63, bd, ba)
+    return psi
+
+
+def diag_half_coh(psi512, ops, words, frame_x, eps):
+    """The diagonal-frame half cycle with over-rotations and Pauli events of ANY kind, every event treated where it acts
+    (no conjugation to the end of the operation: a Pauli pushed through a non-Clifford rotation is not a Pauli):
+
+    * a frame-diagonal data part (sign type) commutes with every gate of the half: collected in the sign mask;
+    * a frame-flip data part relabels the basis for every LATER gate on that qubit (per-gate flip state) and ends in the
+      flip mask; a sign met after a flip costs a factor -1;
+    * an ancilla part acts on the ancilla's (u, v) pair where it occurs;
+    * Ry(eps) after Ry(+pi/2) / Ry(-pi/2): a real rotation of the data qubit before / after its bracket; flips that
+      happened inside the bracket invert the angle of the one after it (X Ry(e) X = Ry(-e)), and the signs of events that
+      come after it are applied after it.
+
+    Returns out[a] and the factor to the brute-force projection, as diag_half."""
+    nq = 9
+    first = {}
+    last = {}
+    for i, op in enumerate(ops):
+        first.setdefault(op["d"], i)
+        last[op["d"]] = i
+    S = psi512.astype(complex).copy()
+    if frame_x:
+        S = wht(S)
+    else:
+        for q in range(nq):                                   # pre-layer: Ry(eps_a) of the operation that opens the bracket
+            if q in first and ops[first[q]]["shape"] & 1:
+                apply_1q(S, q, rot("y", eps[first[q]]["ry1"]))
+    Fm = ZACC = g = 0
+    zacc_out = 0                                              # signs of events after a closed bracket (after its Ry(eps))
+    flip_in = 0                                               # flips that happened inside a (still open or closed) bracket
+    per_op = []
+    for i, (op, w) in enumerate(zip(ops, words)):
+        d, shape = op["d"], op["shape"]
+        skip = (w >> 24) & 1
+        rec = dict(pre=(0, 0), post=[], fl_rxx=0, fl_rx=0)
+        inside = True                                         # x-type half, or inside the Ry bracket
+
+        def take(field, inside_bracket):
+            nonlocal Fm, ZACC, g, flip_in, zacc_out
+            x, z, xa, za, k = field & 1, (field >> 1) & 1, (field >> 2) & 1, (field >> 3) & 1, (field >> 4) & 3
+            F = frame_pauli(field & 0x33, frame_x, 0 if inside_bracket else 4)
+            xf, zf, kf = F & 1, (F >> 1) & 1, (F >> 4) & 3
+            if zf:
+                if inside_bracket:
+                    ZACC ^= 1 << d
+                else:
+                    zacc_out ^= 1 << d
+                g += 2 * ((Fm >> d) & 1)
+            if xf:
+                Fm ^= 1 << d
+                if inside_bracket:
+                    flip_in ^= 1 << d
+            g += kf
+            return xa, za
+        if shape & 1:
+            rec["pre"] = take(w & 63, True)
+        rec["fl_rxx"] = (Fm >> d) & 1
+        if not skip:
+            rec["post"].append(take((w >> 6) & 63, True))
+        rec["fl_rx"] = (Fm >> d) & 1
+        if shape & 2:
+            rec["post"].append(take((w >> 12) & 63, True))
+        if shape & 4:
+            rec["post"].append(take((w >> 18) & 63, False))
+        per_op.append(rec)
+    p = np.arange(512)
+    amp = {a: S.copy() for a in range(16)}
+    for k in range(4):
+        mine = [i for i, op in enumerate(ops) if op["slot"] == k]
+        T = np.zeros((1 << len(mine), 2), dtype=complex)
+        for idx in range(1 << len(mine)):
+            u, v, ph = 1.0 + 0j, 0j, 1.0 + 0j
+            for j, i in enumerate(mine):
+                op, w, rec, e = ops[i], words[i], per_op[i], eps[i]
+                bit = (idx >> j) & 1
+                xa, za = rec["pre"]
+                if za:
+                    v = -v
+                if xa:
+                    u, v = v, u
+                if not ((w >> 24) & 1):
+                    lam = (-1) ** (bit ^ rec["fl_rxx"])
+                    th = 0.5 * (op["s"] * 0.5 * np.pi + e["rxx"])
+                    c, sn = np.cos(th), lam * np.sin(th)
+                    u, v = c * u - 1j * sn * v, c * v - 1j * sn * u
+                if op["shape"] & 2:
+                    lam = (-1) ** (bit ^ rec["fl_rx"])
+                    th = 0.5 * (-op["s"] * 0.5 * np.pi + e["rx"])
+                    ph *= np.cos(th) - 1j * lam * np.sin(th)
+                for xa, za in rec["post"]:
+                    if za:
+                        v = -v
+                    if xa:
+                        u, v = v, u
+            T[idx] = (ph * u, ph * v)
+        idx_of_p = np.zeros(512, dtype=int)
+        for j, i in enumerate(mine):
+            idx_of_p |= ((p >> ops[i]["d"]) & 1) << j
+        for a in range(16):
+            amp[a] = amp[a] * T[idx_of_p, (a >> k) & 1]
+    sign = (-1.0) ** np.array([bin(int(q) & ZACC).count("1") for q in p])
+    out = {}
+    for a in range(16):
+        Sa = amp[a] * sign * (1j ** (g & 3))
+        if frame_x:
+            W = wht(Sa)
+            fix = (-1.0) ** np.array([bin(int(z) & Fm).count("1") for z in p])
+            out[a] = W * fix
+        else:
+            for q in range(nq):                               # post-layer, before the relabelling by the flips
+                if q in last and ops[last[q]]["shape"] & 4:
+                    e = eps[last[q]]["ry2"]
+                    apply_1q(Sa, q, rot("y", -e if (flip_in >> q) & 1 else e))
+            Sa = Sa * (-1.0) ** np.array([bin(int(q) & zacc_out).count("1") for q in p])
+            o = np.zeros(512, dtype=complex)
+            o[p ^ Fm] = Sa
+            out[a] = o
+    return out, (1.0 / 512.0 if frame_x else 1.0)

@@ -69,3 +69,27 @@ def test_diag_half_with_idle_z_events(density):
             out, factor = dm.diag_half(psi, ops, words, frame_x, idle)
             for a in range(16):
                 np.testing.assert_allclose(out[a] * factor, brute[512 * a:512 * (a + 1)], atol=1e-12, rtol=0)
+
+
+def random_eps(rng, ops, scale):
+    return [dict(ry1=rng.uniform(-scale, scale), rxx=rng.uniform(-scale, scale), rx=rng.uniform(-scale, scale),
+                 ry2=rng.uniform(-scale, scale)) for _ in ops]
+
+
+@pytest.mark.parametrize("density,skips", [(0.0, False), (0.3, False), (0.6, True)])
+def test_coherent_half_with_any_pauli_event_equals_brute_force(density, skips):
+    """Over-rotations of +-0.3 rad after every gate, Pauli events of every kind between the gates, leak skips: the
+    diagonal-frame algorithm with every event treated where it acts (per-gate flip state, signs collected, ancilla
+    parts on the (u, v) pair, the rotation after a bracket inverted by the flips inside it) against the gate-by-gate
+    simulation, every joint outcome, 1e-12."""
+    rng = np.random.default_rng(40 + int(density * 10) + skips)
+    for ops, frame_x in halves():
+        for _ in range(4):
+            psi = rng.normal(size=512) + 1j * rng.normal(size=512)
+            psi /= np.linalg.norm(psi)
+            words = random_words(rng, ops, density, skips)
+            eps = random_eps(rng, ops, 0.3)
+            brute = dm.brute_half_coh(psi, ops, words, eps)
+            out, factor = dm.diag_half_coh(psi, ops, words, frame_x, eps)
+            for a in range(16):
+                np.testing.assert_allclose(out[a] * factor, brute[512 * a:512 * (a + 1)], atol=1e-12, rtol=0)
