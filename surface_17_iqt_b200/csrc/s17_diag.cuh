@@ -49,13 +49,21 @@ constexpr int kDgFrmBytes = 16;                                // per-shot frame
 constexpr int kDgMetaBytes = kEvBytes + kDgFrmBytes;
 constexpr int kDgTabEntries = 40;                              // table entries of one half cycle (sum over slots of 2^n_ops)
 constexpr int kDgTabBytes = 3 * kDgTabEntries * 16;            // A0 | A1 | Q
-constexpr int kDgWarpBytes = 2 * kRunBytes + kDgTabBytes + 2 * kDgMetaBytes + 64;
+constexpr int kDgSmallBytes = kDgTabBytes + 2 * kDgMetaBytes + 64;       // per warp: tables | metadata [2] | mbarriers
+constexpr int kDgWarpBytes = 2 * kRunBytes + kDgSmallBytes;
 constexpr size_t kDgSmem = (size_t)kDgWarps * kDgWarpBytes;
 // k_cycle1 adds, per CTA, the tables of an event-free half cycle (both halves) and 128 zero bytes of event words
-constexpr size_t kDgSmem1 = kDgSmem + 2 * kDgTabBytes + kEvBytes;
-static_assert(kDgWarpBytes % 16 == 0, "per-warp shared memory must keep 16-byte alignment");
+constexpr int kDgCleanBytes = 2 * kDgTabBytes + kEvBytes;
+static_assert(kDgSmallBytes % 16 == 0, "per-warp shared memory must keep 16-byte alignment");
+// The 8 KiB block buffers are aligned to their own size IN THE SHARED WINDOW, so that a lane's address is
+// (buffer | lane part) ^ register part: one LOP3 with a constant-bank operand per access.  The dynamic segment starts
+// wherever the driver puts it (1 KiB into the window today), so the kernel skips `gap` < 8 KiB bytes and uses the gap for
+// the per-CTA tables when they fit; the launch always asks for the maximum.
+constexpr size_t kDgSmem1 = 232448;
 #ifndef S17_NO_SMEM_ASSERT
-static_assert(kDgSmem1 <= 232448, "k_cycle1: shared memory per SM");
+static_assert(kDgSmem + kDgCleanBytes + (kDgCleanBytes - 1) <= kDgSmem1 && kDgSmem + (kRunBytes - 1) <= kDgSmem1,
+              "k_cycle1: shared memory per SM (either placement of the per-CTA tables)");
+static_assert((kRunBytes & (kRunBytes - 1)) == 0, "block buffers are aligned to their size");
 #endif
 
 struct DiagOp {
@@ -117,6 +125,15 @@ struct DiagCoh {
 
 __device__ __forceinline__ double2 dg_cmul(const double2 a, const double2 b) {
     return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
+}
+// shared-memory accesses by 32-bit window address (k_cycle1 forms them with one XOR, see kDgSmem1)
+__device__ __forceinline__ double2 dg_lds(uint32_t a) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void dg_sts(uint32_t a, const double2 v) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory");
 }
 __device__ __forceinline__ void dg_wht16(double2 (&p)[16]) {
 #pragma unroll
@@ -342,10 +359,12 @@ __device__ __forceinline__ void dg_half1(double2 (&p)[16], const unsigned char *
             oa = (fo >> aj[KA]) & 1u;
             ob = (fo >> aj[KB]) & 1u;
         } else {
-            oa = (__shfl_sync(0xffffffffu, uu, u_lane0 + KA) * (a0 + a1) < a1) ? 1u : 0u;   // Measure: P(1) against one uniform
+            // Measure: P(1) against one uniform.  Every lane holds the same (a0, a1); the lane that drew the uniform of
+            // this Measure decides, the others read its bit from the ballot
+            oa = (__ballot_sync(0xffffffffu, uu * (a0 + a1) < a1) >> (u_lane0 + KA)) & 1u;
         }
         const double b0 = oa ? J[1] : J[0], b1 = oa ? J[3] : J[2];            // P(o_a, o_b = 0), P(o_a, o_b = 1)
-        if (!forced) ob = (__shfl_sync(0xffffffffu, uu, u_lane0 + KB) * (b0 + b1) < b1) ? 1u : 0u;
+        if (!forced) ob = (__ballot_sync(0xffffffffu, uu * (b0 + b1) < b1) >> (u_lane0 + KB)) & 1u;
         if (forced && ((oa ? a1 : a0) <= 0.0 || (ob ? b1 : b0) <= 0.0)) bad = true;
         if (pp) { pp[2 * KA] = a0; pp[2 * KA + 1] = a1; pp[2 * KB] = b0; pp[2 * KB + 1] = b1; }   // every lane holds the same pairs
         csel[KA][0] = oa ? qa0.y : qa0.x;
@@ -414,14 +433,18 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
     // build those caches)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned char *wb = smem_raw + (size_t)warp * kDgWarpBytes;
-    unsigned char *buf = wb;                                                         // [2][8 KiB]
-    unsigned char *tab = wb + 2 * kRunBytes;                                         // A0 | A1 | Q
-    unsigned char *meta = wb + 2 * kRunBytes + kDgTabBytes;                          // [2][kDgMetaBytes]
+    // [gap][block buffers: warp x 2 x 8 KiB, 8 KiB aligned in the window][per-warp small blocks][per-CTA tables, if not in the gap]
+    const uint32_t gap = (0u - smem_u32(smem_raw)) & (uint32_t)(kRunBytes - 1);
+    unsigned char *buf = smem_raw + gap + (size_t)warp * 2 * kRunBytes;              // [2][8 KiB]
+    unsigned char *wb = smem_raw + gap + (size_t)kDgWarps * 2 * kRunBytes + (size_t)warp * kDgSmallBytes;
+    unsigned char *tab = wb;                                                         // A0 | A1 | Q
+    unsigned char *meta = wb + kDgTabBytes;                                          // [2][kDgMetaBytes]
     uint64_t *full = reinterpret_cast<uint64_t *>(meta + 2 * kDgMetaBytes);          // [2]
     uint64_t *mfull = full + 2;                                                      // [2]
     // per CTA: the tables of a half cycle without events (most slots of most shots), built once
-    unsigned char *clean = smem_raw + kDgSmem;                                       // [2][kDgTabBytes]
+    unsigned char *clean = gap >= (uint32_t)kDgCleanBytes ? smem_raw                 // [2][kDgTabBytes]
+                                                          : smem_raw + gap + kDgSmem;
+    const uint32_t buf32 = smem_u32(buf);
     uint32_t *zero_ev = reinterpret_cast<uint32_t *>(clean + 2 * kDgTabBytes);       // [S17_EV_WORDS]
     if (warp == 0) {
         zero_ev[lane] = 0u;
@@ -517,11 +540,24 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
         }
     };
     auto lane_stage = [&](double2 (&q)[16]) {
+#ifdef S17_DG_LS_GROUP
+#pragma unroll
+        for (int g0 = 0; g0 < 16; g0 += S17_DG_LS_GROUP) {
+            double2 o[S17_DG_LS_GROUP];
+#pragma unroll
+            for (int i = 0; i < S17_DG_LS_GROUP; ++i)
+                o[i] = make_double2(__shfl_xor_sync(0xffffffffu, q[g0 + i].x, sh_mask), __shfl_xor_sync(0xffffffffu, q[g0 + i].y, sh_mask));
+#pragma unroll
+            for (int i = 0; i < S17_DG_LS_GROUP; ++i)
+                q[g0 + i] = make_double2(fma(sh_sign, q[g0 + i].x, o[i].x), fma(sh_sign, q[g0 + i].y, o[i].y));
+        }
+#else
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             const double ox = __shfl_xor_sync(0xffffffffu, q[i].x, sh_mask), oy = __shfl_xor_sync(0xffffffffu, q[i].y, sh_mask);
             q[i] = make_double2(fma(sh_sign, q[i].x, ox), fma(sh_sign, q[i].y, oy));
         }
+#endif
     };
 
     uint32_t entry = all_quiet ? first : act_list[first];
@@ -546,6 +582,8 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
         const uint32_t *evw = all_quiet ? zero_ev : reinterpret_cast<const uint32_t *>(meta + sb * kDgMetaBytes);
         const uint32_t *fwp = all_quiet ? zero_ev : reinterpret_cast<const uint32_t *>(meta + sb * kDgMetaBytes + kEvBytes);
         unsigned char *xb = buf + sb * kRunBytes;
+        const uint32_t xb32 = buf32 + (uint32_t)sb * kRunBytes;                    // aligned to 8 KiB: | and ^ with offsets < 8 KiB
+        const uint32_t la32 = xb32 | linA;
 
         uint32_t fo = 0;
         double uu = 0.0;
@@ -564,7 +602,7 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
         if (init_basis < 0) {
             mbar_wait(&full[sb], (j >> 1) & 1u);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) p[i] = *reinterpret_cast<const double2 *>(xb + (linA ^ P.mapA.lin16[i]));
+            for (int i = 0; i < 16; ++i) p[i] = dg_lds(la32 ^ P.mapA.lin16[i]);
         } else {
             // first cycle of a shot: the (unnormalised) Walsh-Hadamard transform of the basis state |b> is the sign
             // pattern (-1)^{y.b} -- exactly what the transform below would compute from it -- written in map B
@@ -605,8 +643,7 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
                 // Walsh-Hadamard transform of the data register: the register bits of the current map, the exchange to the
                 // other map, its register bits; the one remaining label bit is a lane bit of map A (shuffle stage)
                 const int dir = r >> 1;                           // 0: map A -> B (into the frame), 1: map B -> A
-                const uint32_t wl = dir ? swzB : swzA, rl = dir ? swzA : swzB;
-                const uint32_t *wr = dir ? P.mapB.swz16 : P.mapA.swz16, *rr = dir ? P.mapA.swz16 : P.mapB.swz16;
+                const uint32_t xa32 = xb32 | swzA, xc32 = xb32 | swzB;
 #pragma unroll kDgHpUnroll
                 for (int half_pass = 0; half_pass < 2; ++half_pass) {
                     if (COH && dir) {
@@ -627,12 +664,21 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
                     dg_wht16(p);
                     }
                     if (half_pass == 0) {
+                        // the exchange, once per direction: the register parts are constant-bank operands of the XOR
                         __syncwarp();
+                        if (dir) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) *reinterpret_cast<double2 *>(xb + (wl ^ wr[i])) = p[i];
-                        __syncwarp();
+                            for (int i = 0; i < 16; ++i) dg_sts(xc32 ^ P.mapB.swz16[i], p[i]);
+                            __syncwarp();
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) p[i] = *reinterpret_cast<const double2 *>(xb + (rl ^ rr[i]));
+                            for (int i = 0; i < 16; ++i) p[i] = dg_lds(xa32 ^ P.mapA.swz16[i]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) dg_sts(xa32 ^ P.mapA.swz16[i], p[i]);
+                            __syncwarp();
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) p[i] = dg_lds(xc32 ^ P.mapB.swz16[i]);
+                        }
                     }
                 }
                 if (dir) carry = fw & 511u;                       // its data flips are signs now: next half's sign mask
@@ -719,17 +765,18 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
             // the list, then the last state of positive weight is taken.
             double cum = __shfl_up_sync(0xffffffffu, incl, 1);
             if (lane == 0) cum = 0.0;
-            int pick = 0, last_pos = 0;
+            int pick = 0;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 cum += wsum[i];
                 pick += (cum <= target) ? 1 : 0;
-                last_pos = wsum[i] > 0.0 ? i : last_pos;
             }
-            pick = pick > 15 ? last_pos : pick;
-            uint32_t lab = 0;
+            if (pick > 15) {                      // (rounding only: rare, and only the selected lane's value is used)
+                pick = 0;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) lab = (i == pick) ? ((linA ^ P.mapA.lin16[i]) >> 4) : lab;
+                for (int i = 0; i < 16; ++i) pick = wsum[i] > 0.0 ? i : pick;
+            }
+            uint32_t lab = (linA ^ P.mapA.lin16[pick]) >> 4;
             lab = __shfl_sync(0xffffffffu, lab, sel);
             if (lane == 0) dsamp[shot] = (lab ^ perm) & 511u;
         }
@@ -737,8 +784,11 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
         // stage the (already renormalised) block in label order (data flips of the computational-frame half relabel it)
         // and hand it to one bulk store
         __syncwarp();
+        {
+            const uint32_t ls32 = la32 ^ (perm << 4);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) *reinterpret_cast<double2 *>(xb + ((linA ^ P.mapA.lin16[i]) ^ (perm << 4))) = p[i];
+            for (int i = 0; i < 16; ++i) dg_sts(ls32 ^ P.mapA.lin16[i], p[i]);
+        }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
