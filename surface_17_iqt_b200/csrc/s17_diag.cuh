@@ -435,15 +435,22 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // [gap][block buffers: warp x 2 x 8 KiB, 8 KiB aligned in the window][per-warp small blocks][per-CTA tables, if not in the gap]
     const uint32_t gap = (0u - smem_u32(smem_raw)) & (uint32_t)(kRunBytes - 1);
-    unsigned char *buf = smem_raw + gap + (size_t)warp * 2 * kRunBytes;              // [2][8 KiB]
-    unsigned char *wb = smem_raw + gap + (size_t)kDgWarps * 2 * kRunBytes + (size_t)warp * kDgSmallBytes;
+    uint32_t buf_off = gap + (uint32_t)warp * 2 * kRunBytes;
+    uint32_t wb_off = gap + (uint32_t)kDgWarps * 2 * kRunBytes + (uint32_t)warp * kDgSmallBytes;
+    uint32_t clean_off = gap >= (uint32_t)kDgCleanBytes ? 0u : gap + (uint32_t)kDgSmem;
+#ifndef S17_DG_NO_PIN
+    // keep the per-warp offsets in registers: under register pressure the compiler otherwise rebuilds them from the thread
+    // index at every use (a dozen instructions each, several times per cycle)
+    asm volatile("" : "+r"(buf_off), "+r"(wb_off), "+r"(clean_off));
+#endif
+    unsigned char *buf = smem_raw + buf_off;                                         // [2][8 KiB]
+    unsigned char *wb = smem_raw + wb_off;
     unsigned char *tab = wb;                                                         // A0 | A1 | Q
     unsigned char *meta = wb + kDgTabBytes;                                          // [2][kDgMetaBytes]
     uint64_t *full = reinterpret_cast<uint64_t *>(meta + 2 * kDgMetaBytes);          // [2]
     uint64_t *mfull = full + 2;                                                      // [2]
     // per CTA: the tables of a half cycle without events (most slots of most shots), built once
-    unsigned char *clean = gap >= (uint32_t)kDgCleanBytes ? smem_raw                 // [2][kDgTabBytes]
-                                                          : smem_raw + gap + kDgSmem;
+    unsigned char *clean = smem_raw + clean_off;                                     // [2][kDgTabBytes]
     const uint32_t buf32 = smem_u32(buf);
     uint32_t *zero_ev = reinterpret_cast<uint32_t *>(clean + 2 * kDgTabBytes);       // [S17_EV_WORDS]
     if (warp == 0) {
@@ -504,6 +511,11 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
         return label ^ c;
     };
     const uint32_t linA = laneA << 4, swzA = swz(laneA) << 4, swzB = swz(laneB) << 4;
+    // this lane's three access bases in buffer 0 (linear, exchange through map A / map B); buffer 1 is 8 KiB further
+    uint32_t la0 = buf32 | linA, xa0 = buf32 | swzA, xc0 = buf32 | swzB;
+#ifndef S17_DG_NO_PIN
+    asm volatile("" : "+r"(la0), "+r"(xa0), "+r"(xc0));
+#endif
     const double sh_sign = ((lane >> P.sh_lane_bit) & 1) ? -1.0 : 1.0;
     const int sh_mask = 1 << P.sh_lane_bit;
     // lane part of this lane's table index per slot (4 bits each; the register-fed index bit stays 0)
@@ -582,8 +594,8 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
         const uint32_t *evw = all_quiet ? zero_ev : reinterpret_cast<const uint32_t *>(meta + sb * kDgMetaBytes);
         const uint32_t *fwp = all_quiet ? zero_ev : reinterpret_cast<const uint32_t *>(meta + sb * kDgMetaBytes + kEvBytes);
         unsigned char *xb = buf + sb * kRunBytes;
-        const uint32_t xb32 = buf32 + (uint32_t)sb * kRunBytes;                    // aligned to 8 KiB: | and ^ with offsets < 8 KiB
-        const uint32_t la32 = xb32 | linA;
+        const uint32_t sboff = (uint32_t)sb * kRunBytes;                            // buffers are aligned to 8 KiB: the lane parts stay below
+        const uint32_t la32 = la0 + sboff;
 
         uint32_t fo = 0;
         double uu = 0.0;
@@ -643,7 +655,7 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
                 // Walsh-Hadamard transform of the data register: the register bits of the current map, the exchange to the
                 // other map, its register bits; the one remaining label bit is a lane bit of map A (shuffle stage)
                 const int dir = r >> 1;                           // 0: map A -> B (into the frame), 1: map B -> A
-                const uint32_t xa32 = xb32 | swzA, xc32 = xb32 | swzB;
+                const uint32_t xa32 = xa0 + sboff, xc32 = xc0 + sboff;
 #pragma unroll kDgHpUnroll
                 for (int half_pass = 0; half_pass < 2; ++half_pass) {
                     if (COH && dir) {
