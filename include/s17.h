@@ -208,6 +208,13 @@ typedef struct {
 } s17_program_info;
 int s17_describe_program(const s17_layer *layers, const uint32_t n_layers[3], const double *params_cos_sin,
                          uint32_t n_params, const s17_pinstr *plan, uint32_t n_plan, s17_program_info *out);
+/* Host-side check hook (no device): the closed form the whole-cycle kernel uses for one private table entry of an ancilla
+ * slot (s17_diag.cuh: dg_slot_entry) -- the amplitudes (A0, A1) the ancilla ends in for outcome 0 / 1 after the operations
+ * of the slot (x_type_entangling / z_type_entangling, CS:291-344, with the events insert_error put there, CS:188-234).
+ * Every mask has operation j at bit 8 j: W = event word >> 24 (bit 7 data flip seen by the operation, 4 / 3 net Z / X on the
+ * ancilla after it, 0 leak skip), f1 = Rxx sign is -1, f2 = an Rx follows, idx = table index bits, cz = idle Z after the
+ * operation, mm = operations in use.  out = {Re A0, Im A0, Re A1, Im A1} (Gaussian integers). */
+int s17_diag_slot_entry(uint32_t W, uint32_t f1, uint32_t f2, uint32_t idx, uint32_t cz, uint32_t mm, int32_t out[4]);
 /* decoder tables: lookup (CS:886-892) and return_weight_classical_lookup (CS:895-898) */
 int s17_load_tables(s17_ctx *ctx, const uint32_t *lut256, const uint8_t *classical_weight16);
 /* true-probability mode: the lists instantiate_error_model binds (CS:31-49) */

@@ -82,6 +82,7 @@ assert C.sizeof(Uop) == 8 and C.sizeof(Op) == 72 and C.sizeof(Layer) == 1160
 assert C.sizeof(PInstr) == 12 and C.sizeof(Record) == 60 and C.sizeof(RunArgs) == 88
 
 EXPORTS = ("s17_create", "s17_destroy", "s17_last_error", "s17_device_count", "s17_load_program", "s17_describe_program",
+           "s17_diag_slot_entry",
            "s17_load_tables", "s17_set_slot_probs", "s17_set_subset", "s17_set_replay", "s17_run",
            "s17_read_records", "s17_read_masks", "s17_read_events", "s17_read_state", "s17_read_rtf", "s17_last_timing",
            "s17_last_timing_detail", "s17_allreduce_counts",
@@ -118,6 +119,7 @@ def load():
                                    C.POINTER(PInstr), u32, C.POINTER(Lists)]
     L.s17_describe_program.argtypes = [C.POINTER(Layer), C.POINTER(u32), C.POINTER(C.c_double), u32, C.POINTER(PInstr), u32,
                                        C.POINTER(ProgramInfo)]
+    L.s17_diag_slot_entry.argtypes = [u32, u32, u32, u32, u32, u32, C.POINTER(C.c_int32)]
     L.s17_load_tables.argtypes = [vp, C.POINTER(u32), C.POINTER(C.c_uint8)]
     L.s17_set_slot_probs.argtypes = [vp, u32, C.POINTER(C.c_double), u32]
     L.s17_set_subset.argtypes = [vp, u32, C.POINTER(u32), C.POINTER(u32), C.POINTER(C.POINTER(C.c_double))]

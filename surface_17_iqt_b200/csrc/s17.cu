@@ -1759,6 +1759,16 @@ static bool make_diag1(const DiagProg &G, DiagProg1 &P1) {
                 }
             for (int m = 0; m < 5; ++m)
                 if (laneA[m] == sh) P1.sh_lane_bit = (uint8_t)m;
+            for (int h = 0; h < 2; ++h)
+                for (int k = 0; k < 4; ++k)
+                    for (int j = 0; j < P1.h[h].n_ops[k]; ++j) {             // packed per-slot words of dg_slot_entry
+                        const DiagOp &op = P1.h[h].ops[k][j];
+                        P1.ev4[h][k] |= (uint32_t)op.ev_word << (8 * j);
+                        P1.pad4[h][k] |= (uint32_t)op.pad << (8 * j);
+                        P1.f1s[h][k] |= (uint32_t)(op.flags & 1u) << (8 * j);
+                        P1.f2s[h][k] |= (uint32_t)((op.flags >> 1) & 1u) << (8 * j);
+                        P1.mm4[h][k] |= 1u << (8 * j);
+                    }
             return true;
         }
     }
@@ -2089,6 +2099,14 @@ extern "C" int s17_describe_program(const s17_layer *layers, const uint32_t n_la
         }
     }
     delete ctx;
+    return S17_OK;
+}
+
+extern "C" int s17_diag_slot_entry(uint32_t W, uint32_t f1, uint32_t f2, uint32_t idx, uint32_t cz, uint32_t mm, int32_t out[4]) {
+    if (!out) return fail(nullptr, S17_E_ARG, "s17_diag_slot_entry: bad arguments");
+    int a0r, a0i, a1r, a1i;
+    dg_slot_entry(W, f1, f2, idx, cz, mm, a0r, a0i, a1r, a1i);
+    out[0] = a0r; out[1] = a0i; out[2] = a1r; out[3] = a1i;
     return S17_OK;
 }
 

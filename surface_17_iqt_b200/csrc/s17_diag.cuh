@@ -104,6 +104,12 @@ struct DiagProg1 {
     uint16_t own[2][4];        // label bits whose sign slot k carries (DiagOp flag bit 2), per half
     uint32_t off1[2][4];       // slot k's table index takes register index bit k: byte offset from the entry for that
                                // bit = 0 to the one for bit = 1 (0: the slot does not depend on a register bit)
+    // per half and slot, for the private entries of a shot (dg_slot_entry): operation j at byte j
+    uint32_t ev4[2][4];        // event word index of operation j (0 beyond n_ops)
+    uint32_t pad4[2][4];       // its index within the half cycle, in time order
+    uint32_t f1s[2][4];        // 0x01 where the Rxx sign is -1 (DiagOp flag bit 0)
+    uint32_t f2s[2][4];        // 0x01 where an Rx follows (flag bit 1)
+    uint32_t mm4[2][4];        // 0x01 per operation in use
 };
 
 // Coherent over-rotations of a noisy cycle (k_cycle1<true>; the `*_over` entries of an error model, SURVEY C-10).
@@ -225,29 +231,73 @@ __device__ __forceinline__ double2 dg_times_i_pow(const double2 a, uint32_t g) {
     return dg_neg_if(r, (g >> 1) & 1u);
 }
 
-// private entries of ONE slot (k) for one shot: lanes with idx < 2^n_ops[k] compute entry idx.  Events: bit 31 data flip
+// Private entries of ONE slot (k) for one shot: lanes with idx < 2^n_ops[k] compute entry idx.  Events: bit 31 data flip
 // seen by the operation, bit 24 leak skip, bits 27 / 28 net X / Z on the ancilla after the operation, ancz idle Z after
 // it.  Signs and the global phase are NOT part of the entries (the caller applies them to the selected factors).
-__device__ __forceinline__ void dg_build_slot(const DiagHalf &H, const uint32_t *evw, double2 *tab, int k, int idx,
+//
+// Closed form of the recursion  (u, v) -> (u - i s v, v - i s u) [unless skipped],  ph *= (1 + i s) [Rx],  Z, X, Z  per
+// operation: in the X_a eigenbasis a = u + v, b = u - v an Rxx multiplies a by (1 - i s) and b by (1 + i s), Z swaps a and
+// b, X negates b.  With T_j = parity of the Z's before operation j the two accumulators are
+//     A = +-(1 - i)^(n+ - n-) 2^min(n+, n-),   B = +-conj(.),   n+- = live operations with s_j (-1)^T_j = +-1,
+// each X_j negating the one that is `b` at its time; a final swap if the number of Z's is odd; ph = (1 + i)^p+ (1 - i)^p-.
+// Exact Gaussian-integer arithmetic, identical to the recursion on all 2 x 10^8 event patterns (tests/test_slot_entry.py).
+__host__ __device__ __forceinline__ int dg_popc(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+// (1 - i)^d: real and imaginary part for |d| = 0..4 as signed nibbles (d < 0: the conjugate)
+__host__ __device__ __forceinline__ void dg_pow1mi(int d, int &re, int &im) {
+    const int ad = d < 0 ? -d : d;
+    re = (int)(0x00CE011u << (28 - 4 * ad)) >> 28;          // 1, 1, 0, -2, -4
+    im = (int)(0x00EEF0u << (28 - 4 * ad)) >> 28;           // 0, -1, -2, -2, 0
+    im = d < 0 ? -im : im;
+}
+// W: byte j = event word of operation j >> 24; f1s / f2s / mm: DiagProg1; idxs: table index bits, cs: idle Z after the
+// operation -- every mask with operation j at bit 8 j
+__host__ __device__ __forceinline__ void dg_slot_entry(uint32_t W, uint32_t f1s, uint32_t f2s, uint32_t idxs, uint32_t cs,
+                                                       uint32_t mm, int &a0r, int &a0i, int &a1r, int &a1i) {
+    const uint32_t Fm = (W >> 7) & mm, Bm = (W >> 4) & mm, Xm = (W >> 3) & mm, Km = W & mm;
+    const uint32_t S = (f1s ^ idxs ^ Fm) & mm;                               // sigma_j = -1
+    const uint32_t Zm = (Bm ^ cs) & mm;
+    const uint32_t T = ((Zm << 8) ^ (Zm << 16) ^ (Zm << 24)) & mm;           // parity of the ancilla Z's before operation j
+    const uint32_t Sp = S ^ T, live = mm & ~Km;
+    const int nminus = dg_popc(Sp & live), nplus = dg_popc(~Sp & live);
+    const uint32_t tx = T ^ Bm;                                              // which accumulator is `b` when X_j acts
+    const int sA = dg_popc(Xm & tx) & 1, sB = dg_popc(Xm & ~tx) & 1;
+    int x, y;
+    dg_pow1mi(nplus - nminus, x, y);
+    const int mn = nplus < nminus ? nplus : nminus;
+    x *= 1 << mn;
+    y *= 1 << mn;
+    int Ar = sA ? -x : x, Ai = sA ? -y : y, Br = sB ? -x : x, Bi = sB ? y : -y;
+    if (dg_popc(Zm) & 1) { int t = Ar; Ar = Br; Br = t; t = Ai; Ai = Bi; Bi = t; }
+    const int ur = (Ar + Br) >> 1, ui = (Ai + Bi) >> 1, vr = (Ar - Br) >> 1, vi = (Ai - Bi) >> 1;
+    const int pp = dg_popc(~S & f2s & mm), pm = dg_popc(S & f2s & mm);
+    int pr, pi;
+    dg_pow1mi(pm - pp, pr, pi);
+    const int mp = pp < pm ? pp : pm;
+    pr *= 1 << mp;
+    pi *= 1 << mp;
+    a0r = pr * ur - pi * ui; a0i = pr * ui + pi * ur;
+    a1r = pr * vr - pi * vi; a1i = pr * vi + pi * vr;
+}
+__device__ __forceinline__ void dg_build_slot(const DiagProg1 &P, int h, const uint32_t *evw, double2 *tab, int k, int idx,
                                               uint32_t ancz) {
-    int ur = 1, ui = 0, vr = 0, vi = 0, pr = 1, pi = 0;
-    const int n = H.n_ops[k];
-    for (int j = 0; j < n; ++j) {
-        const DiagOp op = H.ops[k][j];
-        const uint32_t w = evw[op.ev_word];
-        const uint32_t neg = (uint32_t)(op.flags & 1u) ^ ((uint32_t)(idx >> j) & 1u) ^ (w >> 31);
-        const int sg = neg ? -1 : 1;
-        if (!((w >> 24) & 1u)) {                              // Rxx unless leak-skipped: (u, v) -> (u - i sg v, v - i sg u)
-            const int nur = ur + sg * vi, nui = ui - sg * vr, nvr = vr + sg * ui, nvi = vi - sg * ur;
-            ur = nur; ui = nui; vr = nvr; vi = nvi;
-        }
-        if (op.flags & 2u) { const int npr = pr - sg * pi, npi = pi + sg * pr; pr = npr; pi = npi; }   // (1 + i sg) ph
-        if ((w >> 28) & 1u) { vr = -vr; vi = -vi; }                                                   // net event: Z on the ancilla
-        if ((w >> 27) & 1u) { int t = ur; ur = vr; vr = t; t = ui; ui = vi; vi = t; }                 //            X on the ancilla
-        if ((ancz >> op.pad) & 1u) { vr = -vr; vi = -vi; }                                            // idle Z after the operation
+    const uint32_t e4 = P.ev4[h][k];
+    const uint32_t w0 = evw[e4 & 0xFFu], w1 = evw[(e4 >> 8) & 0xFFu], w2 = evw[(e4 >> 16) & 0xFFu], w3 = evw[e4 >> 24];
+    const uint32_t W = __byte_perm(__byte_perm(w0, w1, 0x0073), __byte_perm(w2, w3, 0x0073), 0x5410);
+    uint32_t cs = 0;
+    if (ancz) {
+        const uint32_t p4 = P.pad4[h][k];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cs |= ((ancz >> ((p4 >> (8 * j)) & 0xFFu)) & 1u) << (8 * j);
     }
-    const int a0r = pr * ur - pi * ui, a0i = pr * ui + pi * ur, a1r = pr * vr - pi * vi, a1i = pr * vi + pi * vr;
-    const int e = H.tbase[k] + idx;
+    int a0r, a0i, a1r, a1i;
+    dg_slot_entry(W, P.f1s[h][k], P.f2s[h][k], ((uint32_t)idx * 0x00204081u) & 0x01010101u, cs, P.mm4[h][k], a0r, a0i, a1r, a1i);
+    const int e = P.h[h].tbase[k] + idx;
     tab[e] = make_double2((double)a0r, (double)a0i);
     tab[e + kDgTabEntries] = make_double2((double)a1r, (double)a1i);
     tab[e + 2 * kDgTabEntries] = make_double2((double)(a0r * a0r + a0i * a0i), (double)(a1r * a1r + a1i * a1i));
@@ -720,7 +770,7 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
                     const int k = lane < 16 ? k0 : k1, idx = lane & 15;
                     if (k >= 0 && idx < (1 << H.n_ops[k])) {
                         if (COH) dg_build_entry_coh(H, C.rxx[h], C.rx[h], evw, reinterpret_cast<double2 *>(tab), k, idx, fw >> 20);
-                        else dg_build_slot(H, evw, reinterpret_cast<double2 *>(tab), k, idx, fw >> 20);
+                        else dg_build_slot(P, h, evw, reinterpret_cast<double2 *>(tab), k, idx, fw >> 20);
                     }
                 }
                 __syncwarp();

@@ -1,0 +1,77 @@
+"""The closed form k_cycle1 uses for the private table entries of an ancilla slot (s17_diag.cuh: dg_slot_entry, reached
+through the host-only hook s17_diag_slot_entry) against the gate-by-gate recursion it replaces: per operation of the slot
+Rxx(s pi/2) unless leak-skipped (CS:293, 322), the Rx phase, then the net Z / X event on the ancilla (insert_error,
+CS:188-234) and an idle Z (sympathetic_cooling, CS:762-772).  Exact integer arithmetic: equality, not a tolerance."""
+import ctypes as C
+import itertools
+import random
+
+from surface_17_iqt_b200 import _lib
+
+
+def spread(m):
+    return (m * 0x00204081) & 0x01010101
+
+
+def recursion(n, f1, idx, flip, skip, zb, xb, zc, f2):
+    u, v, ph = 1 + 0j, 0j, 1 + 0j
+    for j in range(n):
+        sg = -1 if ((f1 >> j) ^ (idx >> j) ^ (flip >> j)) & 1 else 1
+        if not (skip >> j) & 1:
+            u, v = u - 1j * sg * v, v - 1j * sg * u
+        if (f2 >> j) & 1:
+            ph *= 1 + 1j * sg
+        if (zb >> j) & 1:
+            v = -v
+        if (xb >> j) & 1:
+            u, v = v, u
+        if (zc >> j) & 1:
+            v = -v
+    return ph * u, ph * v
+
+
+def closed(L, n, f1, idx, flip, skip, zb, xb, zc, f2, junk=0):
+    W = 0
+    for j in range(4):
+        if j < n:
+            t = (junk & 0x66) | (((flip >> j) & 1) << 7) | (((zb >> j) & 1) << 4) | (((xb >> j) & 1) << 3) | ((skip >> j) & 1)
+        else:
+            t = 0xFF                      # bytes beyond the slot's operations must not matter
+        W |= t << (8 * j)
+    mm = spread((1 << n) - 1)
+    out = (C.c_int32 * 4)()
+    # bits beyond the slot's operations are set in f1 / idx / cz as well
+    extra = 0x01010101 & ~mm
+    assert L.s17_diag_slot_entry(W, spread(f1) | extra, spread(f2), spread(idx) | extra, spread(zc) | extra, mm, out) == 0
+    return complex(out[0], out[1]), complex(out[2], out[3])
+
+
+def test_slot_entry_closed_form_equals_the_recursion():
+    L = _lib.load()
+    rnd = random.Random(17)
+    n_cases = 0
+    # every event pattern of slots with one to three operations, all sign / index / phase patterns
+    for n in (1, 2, 3):
+        R = range(1 << n)
+        for f1, idx, flip, skip, zb, xb, zc in itertools.product(R, R, R, R, R, R, R):
+            if n == 3 and (f1 & 2 or zc & 5):
+                continue                  # (keeps the run in seconds; the four-operation sample below covers the rest)
+            f2 = rnd.randrange(1 << n)
+            assert closed(L, n, f1, idx, flip, skip, zb, xb, zc, f2, rnd.randrange(256)) == \
+                recursion(n, f1, idx, flip, skip, zb, xb, zc, f2), (n, f1, idx, flip, skip, zb, xb, zc, f2)
+            n_cases += 1
+    for _ in range(60000):
+        a = [rnd.randrange(16) for _ in range(8)]
+        assert closed(L, 4, *a, rnd.randrange(256)) == recursion(4, *a), a
+        n_cases += 1
+    assert n_cases > 100000
+
+
+def test_slot_entry_without_events_is_the_clean_table():
+    """No event: (A0, A1) = ph (u, v) of the plain product of (1 - i s X_a) factors -- e.g. two operations of opposite sign
+    cancel to 2 |0>, four equal ones give -4 |0>."""
+    L = _lib.load()
+    assert closed(L, 2, 0b01, 0, 0, 0, 0, 0, 0, 0) == (2 + 0j, 0j)
+    assert closed(L, 4, 0, 0, 0, 0, 0, 0, 0, 0) == (-4 + 0j, 0j)
+    assert closed(L, 1, 0, 0, 0, 0, 0, 0, 0, 0) == (1 + 0j, -1j)
+    assert closed(L, 1, 0, 0, 0, 1, 0, 0, 0, 0) == (1 + 0j, 0j)          # leak-skipped: identity
