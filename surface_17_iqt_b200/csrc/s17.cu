@@ -1757,8 +1757,18 @@ static bool make_diag1(const DiagProg &G, DiagProg1 &P1) {
                     for (int j = 0; j < P1.h[h].n_ops[k]; ++j)
                         if (P1.h[h].ops[k][j].flags & 4) P1.own[h][k] |= (uint16_t)(1u << P1.h[h].ops[k][j].d);
                 }
-            for (int m = 0; m < 5; ++m)
+            for (int m = 0; m < 5; ++m) {
                 if (laneA[m] == sh) P1.sh_lane_bit = (uint8_t)m;
+                if (laneB[m] == sh) P1.sh_lane_bit_b = (uint8_t)m;
+            }
+            {
+                // the partner lane of the exchange load: the one whose label differs in bit sh
+                const uint32_t k = (((1u << sh) ^ (sh >= 3 ? (uint32_t)gvec[sh] : 0u)) << 4);
+                for (int i = 0; i < 16; ++i) {
+                    P1.mapA.swzp16[i] = P1.mapA.swz16[i] ^ k;
+                    P1.mapB.swzp16[i] = P1.mapB.swz16[i] ^ k;
+                }
+            }
             for (int h = 0; h < 2; ++h)
                 for (int k = 0; k < 4; ++k)
                     for (int j = 0; j < P1.h[h].n_ops[k]; ++j) {             // packed per-slot words of dg_slot_entry
@@ -2244,6 +2254,15 @@ static void launch_cycle1(s17_ctx *ctx, int which, const MeasArgs &ma, double2 *
                           const uint32_t *frm, const uint32_t *list, const uint32_t *n_act, ShotAux *aux, const uint8_t *forced,
                           uint32_t *meas_out, uint32_t *dsamp, unsigned long long *counters, int init_basis,
                           const double2 *alt_src, double *pp_out, double *cdf_out) {
+    if (init_basis >= 0) {
+        // a cycle that starts from a basis state: the kernel writes its Walsh-Hadamard transform (a sign pattern) straight
+        // into map B; the register part of every sign rides in bits 9-24
+        const DiagMap &B = ctx->diag_prog1[which].mapB;
+        uint32_t regpar = 0;
+        for (int i = 0; i < 16; ++i)
+            regpar |= (uint32_t)(__builtin_popcount((B.lin16[i] >> 4) & (uint32_t)init_basis) & 1) << i;
+        init_basis = (init_basis & 511) | (int)(regpar << 9);
+    }
     if (ctx->coh_ok[which])
         k_cycle1<true><<<ctx->num_sms, kDgThreads, kDgSmem1, ctx->stream>>>(ctx->diag_prog1[which], ctx->diag_coh[which], ma, state,
                                                                            stride, ev, frm, list, n_act, aux, forced, meas_out,

@@ -42,7 +42,11 @@ namespace s17 {
 #ifndef S17_DG_HP_UNROLL
 #define S17_DG_HP_UNROLL 1      // the two passes of a transform
 #endif
+#ifndef S17_DG_XLANE
+#define S17_DG_XLANE 1          // 1: the one lane-carried label bit of a transform rides in the exchange load (no shuffles)
+#endif
 constexpr int kDgStUnroll = S17_DG_ST_UNROLL, kDgHpUnroll = S17_DG_HP_UNROLL;
+constexpr bool kDgXlane = S17_DG_XLANE != 0;
 constexpr int kDgWarps = S17_DG_WARPS;                         // warps (= shots in flight) per SM
 constexpr int kDgThreads = kDgWarps * 32;
 constexpr int kDgFrmBytes = 16;                                // per-shot frame words (4 x u32, two used)
@@ -94,13 +98,15 @@ struct DiagMap {
     uint8_t pad[3];
     uint32_t lin16[16];        // label part of register i, as a byte offset into a linear 512-amplitude buffer
     uint32_t swz16[16];        // the same through the exchange swizzle
+    uint32_t swzp16[16];       // swz16 of the partner lane: the lane that differs in the label bit neither map keeps in registers
 };
 struct DiagProg1 {
     DiagHalf h[2];             // lane_bit refers to the map of the half (B for the Hadamard frame, A otherwise)
     DiagMap mapA, mapB;        // A: load / store and the computational-frame half; B: the Hadamard-frame half
     uint8_t sh_lane_bit;       // lane bit (map A) of the one label bit transformed by the shuffle stage
     uint8_t gvec[9];           // exchange swizzle: 16-byte column ^= gvec[b] for every set label bit b >= 3
-    uint8_t pad[2];
+    uint8_t sh_lane_bit_b;     // the same label bit as a lane bit of map B
+    uint8_t pad[1];
     uint16_t own[2][4];        // label bits whose sign slot k carries (DiagOp flag bit 2), per half
     uint32_t off1[2][4];       // slot k's table index takes register index bit k: byte offset from the entry for that
                                // bit = 0 to the one for bit = 1 (0: the slot does not depend on a register bit)
@@ -383,8 +389,8 @@ __device__ __forceinline__ void dg_reduce4(double (&v)[4], int lane) {
 // P(o_a) = J[o_a][0] + J[o_a][1], P(o_b | o_a) = J[o_a][o_b] / P(o_a) are the sequential Measures' own probabilities.
 __device__ __forceinline__ void dg_half1(double2 (&p)[16], const unsigned char *(&tk0)[4], const unsigned char *(&tk1)[4],
                                          const uint8_t (&aj)[4], bool forced, uint32_t fo, double uu, int u_lane0,
-                                         uint32_t lane_neg, uint32_t reg_neg, uint32_t g, bool scale_out, uint32_t &a_out,
-                                         bool &bad, double &pfin, double *pp, int lane) {
+                                         uint32_t lane_neg, uint32_t reg_neg, uint32_t g, bool scale_out, uint32_t xs,
+                                         uint32_t &a_out, bool &bad, double &pfin, double *pp, int lane) {
     double w[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) w[i] = fma(p[i].x, p[i].x, p[i].y * p[i].y);
@@ -403,7 +409,11 @@ __device__ __forceinline__ void dg_half1(double2 (&p)[16], const unsigned char *
         double J[4] = {fma(t00, qb0.x, t10 * qb1.x), fma(t01, qb0.x, t11 * qb1.x),
                        fma(t00, qb0.y, t10 * qb1.y), fma(t01, qb0.y, t11 * qb1.y)};
         dg_reduce4(J, lane);
-        const double a0 = J[0] + J[2], a1 = J[1] + J[3];                     // P(o_a = 0), P(o_a = 1) (unnormalised)
+        // J is indexed by table COLUMN (A0 / A1); a slot with an odd number of X events on its ancilla (xs) reports the
+        // other column's outcome: X_a commutes with every gate of the slot, so it acts as if right before the Measure
+        const bool xa = (xs >> KA) & 1u, xb = (xs >> KB) & 1u;
+        const double c0 = J[0] + J[2], c1 = J[1] + J[3];
+        const double a0 = xa ? c1 : c0, a1 = xa ? c0 : c1;                   // P(o_a = 0), P(o_a = 1) (unnormalised)
         uint32_t oa, ob;
         if (forced) {
             oa = (fo >> aj[KA]) & 1u;
@@ -413,15 +423,18 @@ __device__ __forceinline__ void dg_half1(double2 (&p)[16], const unsigned char *
             // this Measure decides, the others read its bit from the ballot
             oa = (__ballot_sync(0xffffffffu, uu * (a0 + a1) < a1) >> (u_lane0 + KA)) & 1u;
         }
-        const double b0 = oa ? J[1] : J[0], b1 = oa ? J[3] : J[2];            // P(o_a, o_b = 0), P(o_a, o_b = 1)
+        const uint32_t ca = oa ^ (xa ? 1u : 0u);                              // the column that outcome selects
+        const double d0 = ca ? J[1] : J[0], d1 = ca ? J[3] : J[2];
+        const double b0 = xb ? d1 : d0, b1 = xb ? d0 : d1;                    // P(o_a, o_b = 0), P(o_a, o_b = 1)
         if (!forced) ob = (__ballot_sync(0xffffffffu, uu * (b0 + b1) < b1) >> (u_lane0 + KB)) & 1u;
+        const uint32_t cb = ob ^ (xb ? 1u : 0u);
         if (forced && ((oa ? a1 : a0) <= 0.0 || (ob ? b1 : b0) <= 0.0)) bad = true;
         if (pp) { pp[2 * KA] = a0; pp[2 * KA + 1] = a1; pp[2 * KB] = b0; pp[2 * KB + 1] = b1; }   // every lane holds the same pairs
-        csel[KA][0] = oa ? qa0.y : qa0.x;
-        csel[KA][1] = oa ? qa1.y : qa1.x;
-        csel[KB][0] = ob ? qb0.y : qb0.x;
-        csel[KB][1] = ob ? qb1.y : qb1.x;
-        outs |= (oa << KA) | (ob << KB);
+        csel[KA][0] = ca ? qa0.y : qa0.x;
+        csel[KA][1] = ca ? qa1.y : qa1.x;
+        csel[KB][0] = cb ? qb0.y : qb0.x;
+        csel[KB][1] = cb ? qb1.y : qb1.x;
+        outs |= (ca << KA) | (cb << KB);
         a_out |= (oa << aj[KA]) | (ob << aj[KB]);
         pfin = ob ? b1 : b0;
     };
@@ -668,9 +681,13 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
         } else {
             // first cycle of a shot: the (unnormalised) Walsh-Hadamard transform of the basis state |b> is the sign
             // pattern (-1)^{y.b} -- exactly what the transform below would compute from it -- written in map B
+            // (bits 9-24 of init_basis: the parity of the basis state over the label part of register i, from the host)
+            uint32_t lb = laneB;
+            asm volatile("" : "+r"(lb));          // keeps the pattern inside this branch (the compiler otherwise builds it for every cycle and discards it)
+            const uint32_t sg = ((uint32_t)init_basis >> 9) ^ ((__popc(lb & (uint32_t)init_basis & 511u) & 1) ? 0xFFFFu : 0u);
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-                p[i] = make_double2((__popc((laneB | (P.mapB.lin16[i] >> 4)) & (uint32_t)init_basis) & 1) ? -1.0 : 1.0, 0.0);
+                p[i] = make_double2(__hiloint2double((int)(0x3ff00000u | (((sg >> i) & 1u) << 31)), 0), 0.0);
         }
         if (!all_quiet) mbar_wait(&mfull[sb], (j >> 1) & 1u);
         __syncwarp();                             // every lane holds its amplitudes: the buffer becomes exchange scratch
@@ -722,24 +739,45 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
                             dg_rot16(p, C.preB);
                         }
                     } else {
-                    if (half_pass == dir) lane_stage(p);          // in map A: before the first pass / before the last one
+                    if (!kDgXlane && half_pass == dir) lane_stage(p);          // in map A: before the first pass / before the last one
                     dg_wht16(p);
                     }
                     if (half_pass == 0) {
-                        // the exchange, once per direction: the register parts are constant-bank operands of the XOR
+                        // the exchange, once per direction: the register parts are constant-bank operands of the XOR.
+                        // The one label bit that is a lane bit under both maps is transformed on the way in (kDgXlane): a
+                        // lane also loads the sixteen amplitudes of the lane that differs in that bit (the same addresses,
+                        // permuted over the warp: as conflict-free as its own) -- no shuffles, no 64-bit repacking
+                        const bool xl = kDgXlane && !(COH && dir);
                         __syncwarp();
                         if (dir) {
 #pragma unroll
                             for (int i = 0; i < 16; ++i) dg_sts(xc32 ^ P.mapB.swz16[i], p[i]);
                             __syncwarp();
+                            if (xl) {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) p[i] = dg_lds(xa32 ^ P.mapA.swz16[i]);
+                                for (int i = 0; i < 16; ++i) {
+                                    const double2 u = dg_lds(xa32 ^ P.mapA.swz16[i]), v = dg_lds(xa32 ^ P.mapA.swzp16[i]);
+                                    p[i] = make_double2(fma(sh_sign, u.x, v.x), fma(sh_sign, u.y, v.y));
+                                }
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) p[i] = dg_lds(xa32 ^ P.mapA.swz16[i]);
+                            }
                         } else {
 #pragma unroll
                             for (int i = 0; i < 16; ++i) dg_sts(xa32 ^ P.mapA.swz16[i], p[i]);
                             __syncwarp();
+                            if (xl) {
+                                const double sgb = ((lane >> P.sh_lane_bit_b) & 1) ? -1.0 : 1.0;
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) p[i] = dg_lds(xc32 ^ P.mapB.swz16[i]);
+                                for (int i = 0; i < 16; ++i) {
+                                    const double2 u = dg_lds(xc32 ^ P.mapB.swz16[i]), v = dg_lds(xc32 ^ P.mapB.swzp16[i]);
+                                    p[i] = make_double2(fma(sgb, u.x, v.x), fma(sgb, u.y, v.y));
+                                }
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) p[i] = dg_lds(xc32 ^ P.mapB.swz16[i]);
+                            }
                         }
                     }
                 }
@@ -754,12 +792,18 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
             const uint32_t zmask = ((fw >> 9) ^ carry) & 511u, g = (fw >> 18) & 3u;
             const uint32_t cw = h ? chk_word[1] : chk_word[0];
             const uint32_t wv = cw != 0xFFu ? evw[cw & 0xFFu] : 0u;
-            const uint32_t evd = __ballot_sync(0xffffffffu, cw != 0xFFu && ((wv & 0x7FFFFFFFu) != 0u || ((fw >> (20 + (cw >> 8))) & 1u)));
+            // (bit 24: leak skip, bit 28: net Z on the ancilla, frame bits 20+: idle Z after the operation; a net X on the
+            //  ancilla alone -- bit 27, e.g. an XX error -- commutes with every gate of its slot and only swaps the two
+            //  outcomes of that slot's Measure: xs, no private entries)
+            const uint32_t evd = __ballot_sync(0xffffffffu, cw != 0xFFu && ((wv & 0x11000000u) != 0u || ((fw >> (20 + (cw >> 8))) & 1u)));
             uint32_t flipb = __ballot_sync(0xffffffffu, (wv >> 31) != 0u);
-            uint32_t dirty = 0;
+            const uint32_t xev = __ballot_sync(0xffffffffu, ((wv >> 27) & 1u) != 0u);
+            uint32_t dirty = 0, xs = 0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if ((evd >> (4 * k)) & 15u) { dirty |= 1u << k; flipb &= ~(15u << (4 * k)); }     // flips are part of private entries
+            for (int k = 0; k < 4; ++k) {
+                if ((evd >> (4 * k)) & 15u) { dirty |= 1u << k; flipb &= ~(15u << (4 * k)); }     // flips and X's are part of private entries
+                else xs |= (uint32_t)(__popc((xev >> (4 * k)) & 15u) & 1) << k;
+            }
             if (dirty) {
                 uint32_t d = dirty;
                 while (d) {                                    // two slots per pass: lanes 0-15 / 16-31
@@ -792,7 +836,7 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
             const uint32_t lane_neg = __popc((H.frame_x ? laneB : laneA) & zmask) & 1u;
             uint32_t a_out = 0;
             bool bad = false;
-            dg_half1(p, tk0, tk1, H.aj, is_forced, fo, uu, 4 * h, lane_neg, reg_neg, g, h == 1, a_out, bad, pfin,
+            dg_half1(p, tk0, tk1, H.aj, is_forced, fo, uu, 4 * h, lane_neg, reg_neg, g, h == 1, xs, a_out, bad, pfin,
                      pp_out ? pp_out + ((size_t)shot * 8 + 4 * h) * 2 : nullptr, lane);
             if (!H.frame_x) {
                 carry = 0;
