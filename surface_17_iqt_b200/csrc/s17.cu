@@ -1708,6 +1708,7 @@ static bool order_and_apply_map1(DiagHalf &H, std::vector<int> &reg, const std::
 static bool make_diag1(const DiagProg &G, DiagProg1 &P1) {
     memset(&P1, 0, sizeof(P1));
     const DiagHalf &hx = G.h[0], &hz = G.h[1];
+    if (!hx.frame_x || hz.frame_x) return false;            // k_cycle1: Hadamard-frame half first, computational-frame half second
     auto count_ok = [](const DiagHalf &H, uint32_t regmask) {
         for (int k = 0; k < 4; ++k) {
             int n = 0;

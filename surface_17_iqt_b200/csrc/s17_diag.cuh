@@ -144,6 +144,11 @@ __device__ __forceinline__ double2 dg_lds(uint32_t a) {
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a) : "memory");
     return v;
 }
+__device__ __forceinline__ uint32_t dg_lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
 __device__ __forceinline__ void dg_sts(uint32_t a, const double2 v) {
     asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory");
 }
@@ -412,31 +417,33 @@ __device__ __forceinline__ void dg_half1(double2 (&p)[16], const unsigned char *
         // J is indexed by table COLUMN (A0 / A1); a slot with an odd number of X events on its ancilla (xs) reports the
         // other column's outcome: X_a commutes with every gate of the slot, so it acts as if right before the Measure
         const bool xa = (xs >> KA) & 1u, xb = (xs >> KB) & 1u;
-        const double c0 = J[0] + J[2], c1 = J[1] + J[3];
-        const double a0 = xa ? c1 : c0, a1 = xa ? c0 : c1;                   // P(o_a = 0), P(o_a = 1) (unnormalised)
+        const double c0 = J[0] + J[2], c1 = J[1] + J[3];                     // weight of column 0 / 1 of slot KA (unnormalised)
         uint32_t oa, ob;
         if (forced) {
             oa = (fo >> aj[KA]) & 1u;
             ob = (fo >> aj[KB]) & 1u;
         } else {
-            // Measure: P(1) against one uniform.  Every lane holds the same (a0, a1); the lane that drew the uniform of
+            // Measure: P(1) against one uniform.  Every lane holds the same weights; the lane that drew the uniform of
             // this Measure decides, the others read its bit from the ballot
-            oa = (__ballot_sync(0xffffffffu, uu * (a0 + a1) < a1) >> (u_lane0 + KA)) & 1u;
+            oa = (__ballot_sync(0xffffffffu, uu * (c0 + c1) < (xa ? c0 : c1)) >> (u_lane0 + KA)) & 1u;
         }
         const uint32_t ca = oa ^ (xa ? 1u : 0u);                              // the column that outcome selects
-        const double d0 = ca ? J[1] : J[0], d1 = ca ? J[3] : J[2];
-        const double b0 = xb ? d1 : d0, b1 = xb ? d0 : d1;                    // P(o_a, o_b = 0), P(o_a, o_b = 1)
-        if (!forced) ob = (__ballot_sync(0xffffffffu, uu * (b0 + b1) < b1) >> (u_lane0 + KB)) & 1u;
+        const double d0 = ca ? J[1] : J[0], d1 = ca ? J[3] : J[2];            // joint weight with column 0 / 1 of slot KB
+        if (!forced) ob = (__ballot_sync(0xffffffffu, uu * (d0 + d1) < (xb ? d0 : d1)) >> (u_lane0 + KB)) & 1u;
         const uint32_t cb = ob ^ (xb ? 1u : 0u);
-        if (forced && ((oa ? a1 : a0) <= 0.0 || (ob ? b1 : b0) <= 0.0)) bad = true;
-        if (pp) { pp[2 * KA] = a0; pp[2 * KA + 1] = a1; pp[2 * KB] = b0; pp[2 * KB + 1] = b1; }   // every lane holds the same pairs
+        const double wsel = cb ? d1 : d0;                                     // weight of the two outcomes taken
+        if (forced && ((ca ? c1 : c0) <= 0.0 || wsel <= 0.0)) bad = true;
+        if (pp) {                                                             // (P(0), P(1)) per Measure; every lane holds the same pairs
+            pp[2 * KA] = xa ? c1 : c0; pp[2 * KA + 1] = xa ? c0 : c1;
+            pp[2 * KB] = xb ? d1 : d0; pp[2 * KB + 1] = xb ? d0 : d1;
+        }
         csel[KA][0] = ca ? qa0.y : qa0.x;
         csel[KA][1] = ca ? qa1.y : qa1.x;
         csel[KB][0] = cb ? qb0.y : qb0.x;
         csel[KB][1] = cb ? qb1.y : qb1.x;
         outs |= (ca << KA) | (cb << KB);
         a_out |= (oa << aj[KA]) | (ob << aj[KB]);
-        pfin = ob ? b1 : b0;
+        pfin = wsel;
     };
     {
         double m[4];                                                          // sum over register bits 2, 3
@@ -515,7 +522,9 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
     // per CTA: the tables of a half cycle without events (most slots of most shots), built once
     unsigned char *clean = smem_raw + clean_off;                                     // [2][kDgTabBytes]
     const uint32_t buf32 = smem_u32(buf);
-    uint32_t *zero_ev = reinterpret_cast<uint32_t *>(clean + 2 * kDgTabBytes);       // [S17_EV_WORDS]
+    const uint32_t meta32_0 = smem_u32(meta);
+    uint32_t *zero_ev = reinterpret_cast<uint32_t *>(clean + 2 * kDgTabBytes);       // [S17_EV_WORDS]: the event words of a shot without events
+    const uint32_t zero32 = smem_u32(zero_ev);
     if (warp == 0) {
         zero_ev[lane] = 0u;
         __syncwarp();
@@ -654,8 +663,8 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
             entry1 = all_quiet ? item + 1 : act_list[item + 1];
             if (lane == 0) prefetch(entry1, sb ^ 1);
         }
-        const uint32_t *evw = all_quiet ? zero_ev : reinterpret_cast<const uint32_t *>(meta + sb * kDgMetaBytes);
-        const uint32_t *fwp = all_quiet ? zero_ev : reinterpret_cast<const uint32_t *>(meta + sb * kDgMetaBytes + kEvBytes);
+        // this shot's event words [S17_EV_WORDS] and frame words [4] by shared-window address (zeros for a cycle without a list)
+        const uint32_t meta32 = all_quiet ? zero32 : meta32_0 + (uint32_t)sb * kDgMetaBytes;
         unsigned char *xb = buf + sb * kRunBytes;
         const uint32_t sboff = (uint32_t)sb * kRunBytes;                            // buffers are aligned to 8 KiB: the lane parts stay below
         const uint32_t la32 = la0 + sboff;
@@ -692,36 +701,21 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
         if (!all_quiet) mbar_wait(&mfull[sb], (j >> 1) & 1u);
         __syncwarp();                             // every lane holds its amplitudes: the buffer becomes exchange scratch
 
-        // Six steps: per half cycle [transform into its frame] [tables + four ancilla slots] [transform back].  The loop is
-        // not unrolled, so the transform and the slot code exist once in the instruction stream (the working set of
-        // twelve warps at different points of it has to stay inside the instruction cache).
+        // Two steps, one per half cycle: [Walsh-Hadamard transform] [tables + four ancilla slots].  Half 0 works in the
+        // Hadamard frame, half 1 in the computational frame (make_diag1 checks that), so the transform before half 0 goes
+        // into the frame and the one before half 1 comes back.  The loop is not unrolled: the transform and the slot code
+        // exist once in the instruction stream (the working set of twelve warps at different points of it has to stay
+        // inside the instruction cache).
         uint32_t carry = 0, perm = 0;
         double pfin = 1.0;
-#pragma unroll kDgStUnroll
-        for (int st = 0; st < 6; ++st) {
-            const int h = st >= 3 ? 1 : 0, r = st - 3 * h;
-            const DiagHalf &H = P.h[h];
-            const uint32_t fw = fwp[h];
-            if (r != 1) {
-                if (COH && st == 5) {
-                    // Ry(eps_b) on every data qubit after its bracket: register bits in place, lane bits by shuffle
-                    dg_ry16(p, C.postR);
 #pragma unroll 1
-                    for (int m = 0; m < 5; ++m) {
-                        const double c = C.postL[m].x, sn = ((lane >> m) & 1) ? C.postL[m].y : -C.postL[m].y;
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const double ox = __shfl_xor_sync(0xffffffffu, p[i].x, 1 << m), oy = __shfl_xor_sync(0xffffffffu, p[i].y, 1 << m);
-                            p[i] = make_double2(fma(sn, ox, c * p[i].x), fma(sn, oy, c * p[i].y));
-                        }
-                    }
-                    continue;
-                }
-                if (!H.frame_x) continue;
-                if (st == 0 && init_basis >= 0) continue;         // already in the frame (see above)
+        for (int h = 0; h < 2; ++h) {
+            const DiagHalf &H = P.h[h];
+            const uint32_t fw = all_quiet ? 0u : dg_lds32(meta32 + (uint32_t)kEvBytes + 4u * (uint32_t)h);
+            if (h == 1 || init_basis < 0) {                       // (a cycle that starts from a basis state is in the frame already)
                 // Walsh-Hadamard transform of the data register: the register bits of the current map, the exchange to the
-                // other map, its register bits; the one remaining label bit is a lane bit of map A (shuffle stage)
-                const int dir = r >> 1;                           // 0: map A -> B (into the frame), 1: map B -> A
+                // other map, its register bits; the one remaining label bit is a lane bit of both maps (exchange load)
+                const int dir = h;                                // 0: map A -> B (into the frame), 1: map B -> A
                 const uint32_t xa32 = xa0 + sboff, xc32 = xc0 + sboff;
 #pragma unroll kDgHpUnroll
                 for (int half_pass = 0; half_pass < 2; ++half_pass) {
@@ -781,8 +775,6 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
                         }
                     }
                 }
-                if (dir) carry = fw & 511u;                       // its data flips are signs now: next half's sign mask
-                continue;
             }
             __syncwarp();
             // This shot's events in this half cycle.  Data flips upstream of an operation (bit 31 of its event word) are
@@ -791,20 +783,23 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
             // leak skip or an idle Z get private entries.
             const uint32_t zmask = ((fw >> 9) ^ carry) & 511u, g = (fw >> 18) & 3u;
             const uint32_t cw = h ? chk_word[1] : chk_word[0];
-            const uint32_t wv = cw != 0xFFu ? evw[cw & 0xFFu] : 0u;
+            const uint32_t wv = (!all_quiet && cw != 0xFFu) ? dg_lds32(meta32 + 4u * (cw & 0xFFu)) : 0u;
             // (bit 24: leak skip, bit 28: net Z on the ancilla, frame bits 20+: idle Z after the operation; a net X on the
             //  ancilla alone -- bit 27, e.g. an XX error -- commutes with every gate of its slot and only swaps the two
             //  outcomes of that slot's Measure: xs, no private entries)
-            const uint32_t evd = __ballot_sync(0xffffffffu, cw != 0xFFu && ((wv & 0x11000000u) != 0u || ((fw >> (20 + (cw >> 8))) & 1u)));
-            uint32_t flipb = __ballot_sync(0xffffffffu, (wv >> 31) != 0u);
-            const uint32_t xev = __ballot_sync(0xffffffffu, ((wv >> 27) & 1u) != 0u);
-            uint32_t dirty = 0, xs = 0;
+            uint32_t flipb = 0, dirty = 0, xs = 0;
+            if (!all_quiet) {                       // (a cycle without a list has no events: nothing to look at)
+                const uint32_t evd = __ballot_sync(0xffffffffu, cw != 0xFFu && ((wv & 0x11000000u) != 0u || ((fw >> (20 + (cw >> 8))) & 1u)));
+                flipb = __ballot_sync(0xffffffffu, (wv >> 31) != 0u);
+                const uint32_t xev = __ballot_sync(0xffffffffu, ((wv >> 27) & 1u) != 0u);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if ((evd >> (4 * k)) & 15u) { dirty |= 1u << k; flipb &= ~(15u << (4 * k)); }     // flips and X's are part of private entries
-                else xs |= (uint32_t)(__popc((xev >> (4 * k)) & 15u) & 1) << k;
+                for (int k = 0; k < 4; ++k) {
+                    if ((evd >> (4 * k)) & 15u) { dirty |= 1u << k; flipb &= ~(15u << (4 * k)); }     // flips and X's are part of private entries
+                    else xs |= (uint32_t)(__popc((xev >> (4 * k)) & 15u) & 1) << k;
+                }
             }
             if (dirty) {
+                const uint32_t *evw = reinterpret_cast<const uint32_t *>(meta + sb * kDgMetaBytes);    // (dirty: not all_quiet)
                 uint32_t d = dirty;
                 while (d) {                                    // two slots per pass: lanes 0-15 / 16-31
                     const int k0 = __ffs(d) - 1;
@@ -823,7 +818,7 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
             const uint32_t li = (h ? lidx[1] : lidx[0]) ^ flipb;
             const unsigned char *tk0[4], *tk1[4];
             uint32_t reg_neg = 0;
-            const DiagMap &M = H.frame_x ? P.mapB : P.mapA;
+            const DiagMap &M = h == 0 ? P.mapB : P.mapA;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const uint32_t rmask = P.off1[h][k] >> 4;                          // index bit fed by register bit k (or 0)
@@ -833,16 +828,27 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
                 tk1[k] = base + ((ix ^ rmask) << 4);
                 reg_neg |= ((zmask >> M.reg[k]) & 1u) << k;
             }
-            const uint32_t lane_neg = __popc((H.frame_x ? laneB : laneA) & zmask) & 1u;
+            const uint32_t lane_neg = __popc((h == 0 ? laneB : laneA) & zmask) & 1u;
             uint32_t a_out = 0;
             bool bad = false;
             dg_half1(p, tk0, tk1, H.aj, is_forced, fo, uu, 4 * h, lane_neg, reg_neg, g, h == 1, xs, a_out, bad, pfin,
                      pp_out ? pp_out + ((size_t)shot * 8 + 4 * h) * 2 : nullptr, lane);
-            if (!H.frame_x) {
-                carry = 0;
-                perm = fw & 511u;                                 // data flips of a computational-frame half relabel the store
-            }
+            if (h == 0) carry = fw & 511u;                        // data flips of the Hadamard-frame half are signs afterwards: half 1's sign mask
+            else perm = fw & 511u;                                // data flips of the computational-frame half relabel the store
             if (lane == 0) meas_out[2 * shot + H.final_part] = a_out | (bad ? 0x100u : 0u);
+        }
+        if (COH) {
+            // Ry(eps_b) on every data qubit after its bracket: register bits in place, lane bits by shuffle
+            dg_ry16(p, C.postR);
+#pragma unroll 1
+            for (int m = 0; m < 5; ++m) {
+                const double c = C.postL[m].x, sn = ((lane >> m) & 1) ? C.postL[m].y : -C.postL[m].y;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const double ox = __shfl_xor_sync(0xffffffffu, p[i].x, 1 << m), oy = __shfl_xor_sync(0xffffffffu, p[i].y, 1 << m);
+                    p[i] = make_double2(fma(sn, ox, c * p[i].x), fma(sn, oy, c * p[i].y));
+                }
+            }
         }
 
         // All(Measure) | data of a read-out that may follow (CS:56): one basis state drawn from |psi|^2 -- one uniform
