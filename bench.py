@@ -502,6 +502,13 @@ def run_gpu(args):
                 "floor_ms": floor_ms, "kernel_ms": gate_ms, "frac": floor_ms / gate_ms,
                 "peak": "64 FP64 lanes per SM and clock x {} SMs x {:.0f} MHz".format(n_sms, sm_hz / 1e6),
                 "source": counts.get("source")}
+    issue = None
+    if counts.get("warp_instr_per_shot_cycle") and gate_ms > 0:
+        # four schedulers per SM, one warp instruction each per clock
+        i_floor_ms = 1e3 * counts["warp_instr_per_shot_cycle"] * sweeps / (n_sms * 4 * sm_hz)
+        issue = {"warp_instr_per_shot_cycle": counts["warp_instr_per_shot_cycle"], "floor_ms": i_floor_ms,
+                 "kernel_ms": gate_ms, "frac": i_floor_ms / gate_ms,
+                 "peak": "4 warp instructions per SM and clock x {} SMs x {:.0f} MHz".format(n_sms, sm_hz / 1e6)}
     traffic = None
     if counts.get("dram_bytes_per_shot_cycle") and gate_launches:
         traffic = counts["dram_bytes_per_shot_cycle"] * sweeps / gate_launches
@@ -509,14 +516,16 @@ def run_gpu(args):
                 "frac": achieved / peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                 "traffic": traffic,
                 "traffic_source": counts.get("source"),
-                "binding_unit": "fp64 pipe", "fp64": fp64,
-                "note": "round 2 removed FP64 work (1810 -> 1168 warp instructions per shot-cycle) faster than it removed time, "
-                        "so the pipe fraction is lower than round 1's 0.48 while the kernel is 23 % faster per shot-cycle.  "
-                        "One launch = one stabiliser cycle of every active shot: 8 KiB read (none in the preparation "
+                "binding_unit": "fp64 pipe / instruction issue", "fp64": fp64, "issue": issue,
+                "note": "One launch = one stabiliser cycle of every active shot: 8 KiB read (none in the preparation "
                         "cycle) + 8 KiB written per shot, everything else in registers / shared memory, so the HBM "
-                        "fraction is low by construction; the unit that binds is the FP64 pipe (`fp64`: counted FP64 warp "
-                        "instructions x 0.5 clock / kernel time).  SURVEY 8(d)'s per-layer bytes (4 194 304 per gate layer, "
-                        "6 291 456 per measurement layer) apply to the full-state configuration: `roofline_dense`",
+                        "fraction is low by construction.  What binds is the SM: `fp64` = counted FP64 warp instructions "
+                        "x 0.5 clock over the kernel time (the floor of the arithmetic), `issue` = all counted warp "
+                        "instructions over four issue slots per SM and clock (the floor of the instruction stream as "
+                        "written: 1172 of its instructions are FP64, the rest is addressing, selects, shuffles and "
+                        "control).  Round 1: 4280 instructions per shot-cycle (1810 FP64); counts of the committed ncu "
+                        "capture in `profiles/k_cycle1_counts.json`.  SURVEY 8(d)'s per-layer bytes (4 194 304 per gate "
+                        "layer, 6 291 456 per measurement layer) apply to the full-state configuration: `roofline_dense`",
                 "launches": int(gate_launches), "sweeps": int(sweeps),
                 "sweeps_per_shot": sweeps / (B * args.steps),
                 "bytes_per_shot": sweep_bytes / (B * args.steps), "dense_bytes_per_sweep": SWEEP_BYTES,

@@ -394,7 +394,7 @@ __device__ __forceinline__ void dg_reduce4(double (&v)[4], int lane) {
 // P(o_a) = J[o_a][0] + J[o_a][1], P(o_b | o_a) = J[o_a][o_b] / P(o_a) are the sequential Measures' own probabilities.
 __device__ __forceinline__ void dg_half1(double2 (&p)[16], const unsigned char *(&tk0)[4], const unsigned char *(&tk1)[4],
                                          const uint8_t (&aj)[4], bool forced, uint32_t fo, double uu, int u_lane0,
-                                         uint32_t lane_neg, uint32_t reg_neg, uint32_t g, bool scale_out, uint32_t xs,
+                                         uint32_t lane_neg, uint32_t reg_neg, uint32_t g, bool scale_out, uint32_t xs4,
                                          uint32_t &a_out, bool &bad, double &pfin, double *pp, int lane) {
     double w[16];
 #pragma unroll
@@ -416,7 +416,7 @@ __device__ __forceinline__ void dg_half1(double2 (&p)[16], const unsigned char *
         dg_reduce4(J, lane);
         // J is indexed by table COLUMN (A0 / A1); a slot with an odd number of X events on its ancilla (xs) reports the
         // other column's outcome: X_a commutes with every gate of the slot, so it acts as if right before the Measure
-        const bool xa = (xs >> KA) & 1u, xb = (xs >> KB) & 1u;
+        const bool xa = (xs4 >> (4 * KA)) & 1u, xb = (xs4 >> (4 * KB)) & 1u;
         const double c0 = J[0] + J[2], c1 = J[1] + J[3];                     // weight of column 0 / 1 of slot KA (unnormalised)
         uint32_t oa, ob;
         if (forced) {
@@ -502,7 +502,11 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
     // the (P(0), P(1)) pair of every Measure, cdf_out != nullptr: the read-out's cumulative weights (used once, to
     // build those caches)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    int lane = threadIdx.x & 31;
+#ifndef S17_DG_NO_PIN
+    asm volatile("" : "+r"(lane));                // (otherwise re-read from the special register, with its latency, inside the cycle)
+#endif
     // [gap][block buffers: warp x 2 x 8 KiB, 8 KiB aligned in the window][per-warp small blocks][per-CTA tables, if not in the gap]
     const uint32_t gap = (0u - smem_u32(smem_raw)) & (uint32_t)(kRunBytes - 1);
     uint32_t buf_off = gap + (uint32_t)warp * 2 * kRunBytes;
@@ -644,7 +648,10 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
 #endif
     };
 
+    // list entries are read two shots ahead: the entry of shot j + 1 is needed at the top of shot j (its prefetch), a
+    // global load issued there would be waited for at once
     uint32_t entry = all_quiet ? first : act_list[first];
+    uint32_t entry1 = (first + 1 < last) ? (all_quiet ? first + 1 : act_list[first + 1]) : 0u;
     if (lane == 0) prefetch(entry, 0);
 #ifdef S17_DG_STAGGER
     // the three warps of a scheduler start a third of a shot apart, so that they are not all in the same phase
@@ -658,11 +665,9 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
     for (uint32_t item = first; item < last; ++item, ++j) {
         const int sb = (int)(j & 1u);
         const uint32_t shot = alt_src ? (entry & 0x7FFFFFu) : entry;
-        uint32_t entry1 = 0;
-        if (item + 1 < last) {
-            entry1 = all_quiet ? item + 1 : act_list[item + 1];
-            if (lane == 0) prefetch(entry1, sb ^ 1);
-        }
+        uint32_t entry2 = 0;
+        if (item + 2 < last) entry2 = all_quiet ? item + 2 : act_list[item + 2];
+        if (item + 1 < last && lane == 0) prefetch(entry1, sb ^ 1);
         // this shot's event words [S17_EV_WORDS] and frame words [4] by shared-window address (zeros for a cycle without a list)
         const uint32_t meta32 = all_quiet ? zero32 : meta32_0 + (uint32_t)sb * kDgMetaBytes;
         unsigned char *xb = buf + sb * kRunBytes;
@@ -787,24 +792,25 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
             // (bit 24: leak skip, bit 28: net Z on the ancilla, frame bits 20+: idle Z after the operation; a net X on the
             //  ancilla alone -- bit 27, e.g. an XX error -- commutes with every gate of its slot and only swaps the two
             //  outcomes of that slot's Measure: xs, no private entries)
-            uint32_t flipb = 0, dirty = 0, xs = 0;
+            // one nibble per slot (lanes 4 k .. 4 k + 3 look at the operations of slot k); dirty4 / xs4: bit 4 k = slot k
+            uint32_t flipb = 0, dirty4 = 0, xs4 = 0;
             if (!all_quiet) {                       // (a cycle without a list has no events: nothing to look at)
                 const uint32_t evd = __ballot_sync(0xffffffffu, cw != 0xFFu && ((wv & 0x11000000u) != 0u || ((fw >> (20 + (cw >> 8))) & 1u)));
                 flipb = __ballot_sync(0xffffffffu, (wv >> 31) != 0u);
                 const uint32_t xev = __ballot_sync(0xffffffffu, ((wv >> 27) & 1u) != 0u);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if ((evd >> (4 * k)) & 15u) { dirty |= 1u << k; flipb &= ~(15u << (4 * k)); }     // flips and X's are part of private entries
-                    else xs |= (uint32_t)(__popc((xev >> (4 * k)) & 15u) & 1) << k;
-                }
+                uint32_t t = evd | (evd >> 1);
+                dirty4 = (t | (t >> 2)) & 0x1111u;                                   // any event bit in the nibble
+                flipb &= ~(dirty4 * 15u);                                            // flips and X's are part of private entries
+                t = xev ^ (xev >> 1);
+                xs4 = (t ^ (t >> 2)) & 0x1111u & ~dirty4;                            // parity of the nibble
             }
-            if (dirty) {
+            if (dirty4) {
                 const uint32_t *evw = reinterpret_cast<const uint32_t *>(meta + sb * kDgMetaBytes);    // (dirty: not all_quiet)
-                uint32_t d = dirty;
+                uint32_t d = dirty4;
                 while (d) {                                    // two slots per pass: lanes 0-15 / 16-31
-                    const int k0 = __ffs(d) - 1;
+                    const int k0 = (__ffs(d) - 1) >> 2;
                     d &= d - 1;
-                    const int k1 = d ? __ffs(d) - 1 : -1;
+                    const int k1 = d ? (__ffs(d) - 1) >> 2 : -1;
                     d &= d - 1;
                     const int k = lane < 16 ? k0 : k1, idx = lane & 15;
                     if (k >= 0 && idx < (1 << H.n_ops[k])) {
@@ -823,7 +829,7 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
             for (int k = 0; k < 4; ++k) {
                 const uint32_t rmask = P.off1[h][k] >> 4;                          // index bit fed by register bit k (or 0)
                 const uint32_t ix = (li >> (4 * k)) & 15u;
-                const unsigned char *base = (((dirty >> k) & 1u) ? tab : clean_h) + ((uint32_t)H.tbase[k] << 4);
+                const unsigned char *base = (((dirty4 >> (4 * k)) & 1u) ? tab : clean_h) + ((uint32_t)H.tbase[k] << 4);
                 tk0[k] = base + (ix << 4);                                         // (ix & rmask: that operation sees its bit flipped)
                 tk1[k] = base + ((ix ^ rmask) << 4);
                 reg_neg |= ((zmask >> M.reg[k]) & 1u) << k;
@@ -831,7 +837,7 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
             const uint32_t lane_neg = __popc((h == 0 ? laneB : laneA) & zmask) & 1u;
             uint32_t a_out = 0;
             bool bad = false;
-            dg_half1(p, tk0, tk1, H.aj, is_forced, fo, uu, 4 * h, lane_neg, reg_neg, g, h == 1, xs, a_out, bad, pfin,
+            dg_half1(p, tk0, tk1, H.aj, is_forced, fo, uu, 4 * h, lane_neg, reg_neg, g, h == 1, xs4, a_out, bad, pfin,
                      pp_out ? pp_out + ((size_t)shot * 8 + 4 * h) * 2 : nullptr, lane);
             if (h == 0) carry = fw & 511u;                        // data flips of the Hadamard-frame half are signs afterwards: half 1's sign mask
             else perm = fw & 511u;                                // data flips of the computational-frame half relabel the store
@@ -914,6 +920,7 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
         }
         __syncwarp();                             // tables and the metadata slot are reused
         entry = entry1;
+        entry1 = entry2;
     }
     if (lane == 0) {
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
