@@ -61,7 +61,7 @@ def main():
     half = find("dg_half1(p, tk0, tk1")
     marks = [("kernel prologue + prefetch lambda", kstart),
              ("per shot: list, uniforms, load", find("for (uint32_t item = first")),
-             ("loop over the halves", find("for (int h = 0; h < 2; ++h) {", kstart)),
+             ("loop over the halves", find("for (int h = 0; h < 2; ++h) {", find("for (uint32_t item = first"))),
              ("transform", find("// Walsh-Hadamard transform of the data register: the register bits")),
              ("event scan", find("// This shot's events in this half cycle")),
              ("private entries", find("if (dirty4) {")),

@@ -37,7 +37,7 @@ namespace s17 {
 #define S17_DG_WARPS 12
 #endif
 #ifndef S17_DG_ST_UNROLL
-#define S17_DG_ST_UNROLL 1      // the six-step loop of a cycle (1: the transform and the half-cycle code exist once)
+#define S17_DG_ST_UNROLL 1      // the two-step loop of a cycle (1: the transform and the half-cycle code exist once)
 #endif
 #ifndef S17_DG_HP_UNROLL
 #define S17_DG_HP_UNROLL 1      // the two passes of a transform
@@ -713,7 +713,7 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
         // inside the instruction cache).
         uint32_t carry = 0, perm = 0;
         double pfin = 1.0;
-#pragma unroll 1
+#pragma unroll kDgStUnroll
         for (int h = 0; h < 2; ++h) {
             const DiagHalf &H = P.h[h];
             const uint32_t fw = all_quiet ? 0u : dg_lds32(meta32 + (uint32_t)kEvBytes + 4u * (uint32_t)h);
