@@ -205,6 +205,8 @@ typedef struct {
     uint8_t slot_ancilla[3][2][4];  /* ancilla index measured by slot k of half h */
     uint8_t coherent[3];            /* 1: the cycle carries coherent over-rotations and runs on the whole-cycle kernel's
                                        coherent form (its Clifford skeleton fixed the maps above) */
+    uint8_t prep_rides_in_cycle1;   /* 1: the preparation cycle and the first noisy cycle lower to the same whole-cycle
+                                       program, so an un-memoised run computes both in one launch per shot */
 } s17_program_info;
 int s17_describe_program(const s17_layer *layers, const uint32_t n_layers[3], const double *params_cos_sin,
                          uint32_t n_params, const s17_pinstr *plan, uint32_t n_plan, s17_program_info *out);

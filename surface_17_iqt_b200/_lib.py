@@ -75,7 +75,8 @@ class ProgramInfo(C.Structure):
     _fields_ = [("n_sweeps", C.c_uint32 * 3), ("half_kernel", C.c_uint8 * 3), ("cycle_kernel", C.c_uint8 * 3),
                 ("cycle_kernel_maps", C.c_uint8 * 3), ("shuffle_bit", C.c_uint8 * 3), ("reg_bits_z", (C.c_uint8 * 4) * 3),
                 ("reg_bits_x", (C.c_uint8 * 4) * 3), ("table_entries", (C.c_uint8 * 2) * 3),
-                ("slot_ancilla", ((C.c_uint8 * 4) * 2) * 3), ("coherent", C.c_uint8 * 3)]
+                ("slot_ancilla", ((C.c_uint8 * 4) * 2) * 3), ("coherent", C.c_uint8 * 3),
+                ("prep_rides_in_cycle1", C.c_uint8)]
 
 
 assert C.sizeof(Uop) == 8 and C.sizeof(Op) == 72 and C.sizeof(Layer) == 1160

@@ -62,7 +62,10 @@ def describe_program(prog):
             "shuffle_bit": int(info.shuffle_bit[c]),
             "reg_bits_z": [int(v) for v in info.reg_bits_z[c]], "reg_bits_x": [int(v) for v in info.reg_bits_x[c]],
             "table_entries": [int(v) for v in info.table_entries[c]],
-            "slot_ancilla": [[int(v) for v in info.slot_ancilla[c][h]] for h in range(2)]})
+            "slot_ancilla": [[int(v) for v in info.slot_ancilla[c][h]] for h in range(2)],
+            # (stab_ind=0 entry) the preparation cycle lowers to the same whole-cycle program: an un-memoised run
+            # computes it inside the launch of the first noisy cycle
+            "prep_rides_along": bool(info.prep_rides_in_cycle1) if c == 1 else False})
     return out
 
 

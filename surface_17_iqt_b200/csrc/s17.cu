@@ -142,6 +142,8 @@ struct MeasArgs {
     uint32_t stream;
     uint64_t seed, first_shot;
     int n_shots;
+    int with_prep;    // k_cycle1 ran the noiseless preparation cycle of every shot in the same launch, ahead of this cycle: its
+                      // outcomes ride in bits 16-23 (zero-probability flag: bit 24) of the shot's meas_out words
 };
 
 __device__ __forceinline__ void reset_shot(int shot, uint8_t *__restrict__ active, uint8_t *__restrict__ ready,
@@ -204,6 +206,22 @@ __device__ void record_measurement(const MeasArgs &ma, int shot, uint32_t a, uin
         ready[shot] = 1;
     }
     rec[shot] = r;
+}
+
+// the bookkeeping of a whole cycle from the two meas_out words of a shot (k_half / k_cycle1 / k_prep write them); with
+// ma.with_prep the preparation cycle's first
+__device__ __forceinline__ void record_cycle(const MeasArgs &ma, int shot, const uint32_t *__restrict__ meas_out,
+                                             const uint32_t *__restrict__ lut, uint32_t *__restrict__ leak,
+                                             uint8_t *__restrict__ active, uint8_t *__restrict__ ready,
+                                             s17_record *__restrict__ rec, unsigned long long *__restrict__ counters)
+{
+    const uint32_t xz = meas_out[2 * shot] | meas_out[2 * shot + 1];
+    if (ma.with_prep) {
+        MeasArgs m0 = ma;
+        m0.stage = 0;
+        record_measurement(m0, shot, (xz >> 16) & 0xFFu, 0u, ((xz >> 24) & 1u) != 0, lut, leak, active, ready, rec, counters);
+    }
+    record_measurement(ma, shot, xz & 0xFFu, 8u * (uint32_t)ma.stage, (xz & 0x100u) != 0, lut, leak, active, ready, rec, counters);
 }
 
 // one warp per shot: sample the ancillas in `mask` from the joint histogram, then (on the final part of a
@@ -272,9 +290,7 @@ __global__ void k_record(MeasArgs ma, const uint32_t *__restrict__ meas_out, con
 {
     const int shot = blockIdx.x * blockDim.x + threadIdx.x;
     if (shot >= ma.n_shots || !active[shot]) return;
-    const uint32_t x = meas_out[2 * shot], z = meas_out[2 * shot + 1];
-    record_measurement(ma, shot, (x | z) & 0xFFu, 8u * (uint32_t)ma.stage, ((x | z) & 0x100u) != 0, lut, leak, active, ready,
-                       rec, counters);
+    record_cycle(ma, shot, meas_out, lut, leak, active, ready, rec, counters);
 }
 
 // =================================================================================================
@@ -407,9 +423,7 @@ k_plan(const s17_pinstr *__restrict__ prog, PlanArgs pa, const __grid_constant__
     }
     bool act = shot < pa.n_shots && (sa.do_reset || active[shot]);
     if (sa.do_record && act) {
-        const uint32_t x = sa.meas_out[2 * shot], z = sa.meas_out[2 * shot + 1];
-        record_measurement(sa.rec_ma, shot, (x | z) & 0xFFu, 8u * (uint32_t)sa.rec_ma.stage, ((x | z) & 0x100u) != 0, sa.lut, leak,
-                           active, sa.ready, sa.rec, sa.counters);
+        record_cycle(sa.rec_ma, shot, sa.meas_out, sa.lut, leak, active, sa.ready, sa.rec, sa.counters);
         act = active[shot] != 0;                       // the protocol may have retired the shot (CL:321, 416, 86)
     }
     // preparation stage next to the memoised one (k_prep): only the shots it left (a set leak flag) run a cycle
@@ -833,9 +847,7 @@ k_readout_s(ReadArgs ra, const uint32_t *__restrict__ dsamp, const uint8_t *__re
 {
     const int shot = blockIdx.x * blockDim.x + threadIdx.x;
     if (do_record && shot < ra.n_shots && active[shot]) {
-        const uint32_t x = meas_out[2 * shot], z = meas_out[2 * shot + 1];
-        record_measurement(rec_ma, shot, (x | z) & 0xFFu, 8u * (uint32_t)rec_ma.stage, ((x | z) & 0x100u) != 0, lut, leak, active,
-                           ready, rec, counters);
+        record_cycle(rec_ma, shot, meas_out, lut, leak, active, ready, rec, counters);
     }
     const bool live = shot < ra.n_shots && ready[shot];
     bool fail = false;
@@ -1076,6 +1088,9 @@ struct s17_ctx {
     DiagCoh diag_coh[3];              // coherent over-rotations of a cycle that runs on k_cycle1<true>
     bool coh_ok[3] = {false, false, false};
     bool no_coh = false;              // S17_COH=0: coherent models keep the sweep kernels
+    bool no_fuse_prep = false;        // S17_FUSE_PREP=0: the preparation cycle of an un-memoised run keeps its own launch
+    bool fuse_prep = false;           // this call: the first noisy cycle's launch runs the preparation cycle of its shots first
+    int fuse_basis = 0;               //            from this basis state
     bool no_trivial_prep = false;     // S17_TRIVIAL_PREP=0: plan the preparation cycle of a leak-free model like any other
     bool no_diag = false;
     bool last_collapsed = true;       // the previous cycle left every active shot collapsed to ancilla block 0
@@ -1280,6 +1295,8 @@ extern "C" int s17_create(s17_ctx **out, int device, uint64_t max_shots) {
         ctx->force_ring = r && r[0] == '1';
         const char *tp = getenv("S17_TRIVIAL_PREP");
         ctx->no_trivial_prep = tp && tp[0] == '0';
+        const char *fp = getenv("S17_FUSE_PREP");
+        ctx->no_fuse_prep = fp && fp[0] == '0';
         const char *ge = getenv("S17_GEO");               // 0: one Bernoulli draw per entry instead of geometric skipping
         ctx->no_geo = ge && ge[0] == '0';
     }
@@ -1786,6 +1803,28 @@ static bool make_diag1(const DiagProg &G, DiagProg1 &P1) {
     return false;
 }
 
+// Two cycle kinds lower to the same whole-cycle program apart from where their events live (event words, ev4): then the
+// launch of the first noisy cycle can run the noiseless preparation cycle of its shots first (k_cycle1, MeasArgs::with_prep).
+static bool diag1_same_circuit(const DiagProg1 &A, const DiagProg1 &B) {
+    for (int h = 0; h < 2; ++h) {
+        const DiagHalf &a = A.h[h], &b = B.h[h];
+        if (a.frame_x != b.frame_x || a.final_part != b.final_part || a.n_entries != b.n_entries) return false;
+        if (memcmp(a.n_ops, b.n_ops, 4) || memcmp(a.aj, b.aj, 4) || memcmp(a.tbase, b.tbase, 4) ||
+            memcmp(a.lane_bit, b.lane_bit, sizeof(a.lane_bit)))
+            return false;
+        for (int k = 0; k < 4; ++k)
+            for (int j = 0; j < a.n_ops[k]; ++j)
+                if (a.ops[k][j].d != b.ops[k][j].d || a.ops[k][j].flags != b.ops[k][j].flags || a.ops[k][j].pad != b.ops[k][j].pad)
+                    return false;
+        if (memcmp(A.own[h], B.own[h], sizeof(A.own[h])) || memcmp(A.off1[h], B.off1[h], sizeof(A.off1[h])) ||
+            memcmp(A.pad4[h], B.pad4[h], sizeof(A.pad4[h])) || memcmp(A.f1s[h], B.f1s[h], sizeof(A.f1s[h])) ||
+            memcmp(A.f2s[h], B.f2s[h], sizeof(A.f2s[h])) || memcmp(A.mm4[h], B.mm4[h], sizeof(A.mm4[h])))
+            return false;
+    }
+    return !memcmp(&A.mapA, &B.mapA, sizeof(DiagMap)) && !memcmp(&A.mapB, &B.mapB, sizeof(DiagMap)) &&
+           A.sh_lane_bit == B.sh_lane_bit && A.sh_lane_bit_b == B.sh_lane_bit_b && !memcmp(A.gvec, B.gvec, 9);
+}
+
 // ---- coherent over-rotations on the whole-cycle kernel ------------------------------------------------------------------
 // With the over-rotation micro-ops taken out a coherent cycle is the Clifford cycle; its diagonal-frame form and label
 // maps carry over (the rotations are functions of the same X_d X_a / X_d, or real rotations of one data qubit around its
@@ -2100,6 +2139,9 @@ extern "C" int s17_describe_program(const s17_layer *layers, const uint32_t n_la
         out->cycle_kernel[c] = ctx->diag_ok[c] ? 1 : 0;
         out->cycle_kernel_maps[c] = ctx->diag1_ok[c] ? 1 : 0;
         out->coherent[c] = ctx->coh_ok[c] ? 1 : 0;
+        if (c == 1)
+            out->prep_rides_in_cycle1 = (ctx->diag1_ok[0] && ctx->diag1_ok[1] && !ctx->coh_ok[0] && !ctx->coh_ok[1] &&
+                                         diag1_same_circuit(ctx->diag_prog1[0], ctx->diag_prog1[1])) ? 1 : 0;
         if (!ctx->diag1_ok[c]) continue;
         const DiagProg1 &P = ctx->diag_prog1[c];
         for (int j = 0; j < 4; ++j) { out->reg_bits_z[c][j] = P.mapA.reg[j]; out->reg_bits_x[c][j] = P.mapB.reg[j]; }
@@ -2471,6 +2513,18 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
     const bool trivial_prep = stage == 0 && !ctx->plan_has_leak && a.protocol != S17_PROTO_RTF && ctx->diag1_ok[which0] &&
                               !ctx->no_diag && !dense && !mid_collapse && !max_layers && !ctx->force_ring && !ctx->no_fuse &&
                               !ctx->pend_rec && !ctx->no_trivial_prep;
+    if (stage == 0) {
+        // Un-memoised run: the preparation cycle needs no launch of its own -- the launch of the first noisy cycle starts every
+        // shot from the basis state and runs the noiseless cycle first, block in registers (no 8 KiB store + load, no
+        // second pass over the per-shot prologue); its outcomes reach the bookkeeping through the same meas_out words.
+        ctx->fuse_prep = trivial_prep && !ctx->no_fuse_prep && !ctx->use_prep && !a.forced && !a.materialize &&
+                         a.stop_stage == S17_STOP_NONE && ctx->diag1_ok[1] && !ctx->coh_ok[0] && !ctx->coh_ok[1] &&
+                         diag1_same_circuit(ctx->diag_prog1[0], ctx->diag_prog1[1]);
+        if (ctx->fuse_prep) {
+            ctx->fuse_basis = init_basis;
+            return S17_OK;
+        }
+    }
     PlanArgs pa;
     pa.n_instr = ctx->n_plan;
     pa.noise = (int)a.noise;
@@ -2536,8 +2590,12 @@ static int run_cycle(s17_ctx *ctx, const s17_run_args &a, int stage, int second,
     ma.n_shots = n;
     const bool fused_ok = !dense && !mid_collapse && !max_layers && !ctx->force_ring && !ctx->no_fuse;
     if (ctx->diag1_ok[which] && fused_ok && !ctx->no_diag) {
+        const bool with_prep = stage == 1 && ctx->fuse_prep;
+        ctx->fuse_prep = false;
+        if (with_prep) init_basis = ctx->fuse_basis;
         if (init_basis < 0 && !ctx->last_collapsed) collapse(ctx, n, ctx->active);     // k_cycle reads the block at ancilla value 0
         ctx->last_collapsed = true;
+        ma.with_prep = with_prep ? 1 : 0;
         // production path for Clifford cycles with Pauli / leakage noise: the whole cycle in the frame where it is
         // diagonal, one warp per shot, the state in registers (s17_diag.cuh)
         ma.mask = 0xFFu;
@@ -2654,6 +2712,7 @@ static int run_round(s17_ctx *ctx, const s17_run_args &a) {
     // an event-free first cycle of a shot that sits in a memoised preparation leaf is replayed from the cache as well
     ctx->use_quiet = ctx->use_prep && !ctx->no_quiet && ctx->any_quiet_leaf;
     ctx->pend_rec = false;
+    ctx->fuse_prep = false;
     {
         Nvtx r("s17: preparation cycle");
         if (int rc = run_cycle(ctx, a, 0, 0, basis_index, 0, dense, explicit_collapse)) return rc;

@@ -674,19 +674,6 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
         const uint32_t sboff = (uint32_t)sb * kRunBytes;                            // buffers are aligned to 8 KiB: the lane parts stay below
         const uint32_t la32 = la0 + sboff;
 
-        uint32_t fo = 0;
-        double uu = 0.0;
-        if (is_forced) {
-            const uint32_t b = lane < 8 ? (uint32_t)forced[(size_t)shot * S17_MAX_OUTCOMES + nout + lane] : 0u;
-            fo = __ballot_sync(0xffffffffu, (b & 1u) != 0u) & 0xFFu;
-        } else if (lane < 9) {
-            // lanes 0-7: the uniforms of the eight Measure gates (stream per half, counter block = slot); lane 8: the
-            // read-out's uniform (k_readout's stream)
-            Philox rng(ma.seed, ma.first_shot + shot, lane == 8 ? ma.data_stream : ma.stream + ((lane >> 2) ? 0u : 1u));
-            rng.c3 = lane == 8 ? 0u : (uint32_t)(lane & 3);
-            uu = rng.next();
-        }
-
         double2 p[16];
         if (init_basis < 0) {
             mbar_wait(&full[sb], (j >> 1) & 1u);
@@ -711,13 +698,36 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
         // into the frame and the one before half 1 comes back.  The loop is not unrolled: the transform and the slot code
         // exist once in the instruction stream (the working set of twelve warps at different points of it has to stay
         // inside the instruction cache).
-        uint32_t carry = 0, perm = 0;
+        //
+        // ma.with_prep: two cycles per shot in this launch -- first the noiseless preparation cycle from the basis state
+        // (no events, the streams and the outcome slots of stage 0), then the launch's own cycle on the block in registers.
+        uint32_t perm = 0, prep_bits = 0, fo = 0;
+        double uu = 0.0;
+        const int n_stg = ma.with_prep ? 2 : 1;
+#pragma unroll 1
+        for (int stg = 0; stg < n_stg; ++stg) {
+        const bool prep_stg = ma.with_prep && stg == 0;
+        const bool quiet = all_quiet || prep_stg;
+        const bool from_basis = init_basis >= 0 && stg == 0;
+        if (is_forced) {
+            const uint32_t b = lane < 8 ? (uint32_t)forced[(size_t)shot * S17_MAX_OUTCOMES + (prep_stg ? 0u : nout) + lane] : 0u;
+            fo = __ballot_sync(0xffffffffu, (b & 1u) != 0u) & 0xFFu;
+        } else if (lane < 9) {
+            // lanes 0-7: the uniforms of the eight Measure gates (stream per half, counter block = slot); lane 8: the
+            // read-out's uniform (k_readout's stream)
+            const uint32_t strm = prep_stg ? ma.stream - 4u * (uint32_t)ma.stage : ma.stream;      // stage s draws from 16 + 4 s (+ 1)
+            Philox rng(ma.seed, ma.first_shot + shot, lane == 8 ? ma.data_stream : strm + ((lane >> 2) ? 0u : 1u));
+            rng.c3 = lane == 8 ? 0u : (uint32_t)(lane & 3);
+            uu = rng.next();
+        }
+        uint32_t carry = 0;
         double pfin = 1.0;
+        perm = 0;
 #pragma unroll kDgStUnroll
         for (int h = 0; h < 2; ++h) {
             const DiagHalf &H = P.h[h];
-            const uint32_t fw = all_quiet ? 0u : dg_lds32(meta32 + (uint32_t)kEvBytes + 4u * (uint32_t)h);
-            if (h == 1 || init_basis < 0) {                       // (a cycle that starts from a basis state is in the frame already)
+            const uint32_t fw = quiet ? 0u : dg_lds32(meta32 + (uint32_t)kEvBytes + 4u * (uint32_t)h);
+            if (h == 1 || !from_basis) {                          // (a cycle that starts from a basis state is in the frame already)
                 // Walsh-Hadamard transform of the data register: the register bits of the current map, the exchange to the
                 // other map, its register bits; the one remaining label bit is a lane bit of both maps (exchange load)
                 const int dir = h;                                // 0: map A -> B (into the frame), 1: map B -> A
@@ -788,13 +798,13 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
             // leak skip or an idle Z get private entries.
             const uint32_t zmask = ((fw >> 9) ^ carry) & 511u, g = (fw >> 18) & 3u;
             const uint32_t cw = h ? chk_word[1] : chk_word[0];
-            const uint32_t wv = (!all_quiet && cw != 0xFFu) ? dg_lds32(meta32 + 4u * (cw & 0xFFu)) : 0u;
+            const uint32_t wv = (!quiet && cw != 0xFFu) ? dg_lds32(meta32 + 4u * (cw & 0xFFu)) : 0u;
             // (bit 24: leak skip, bit 28: net Z on the ancilla, frame bits 20+: idle Z after the operation; a net X on the
             //  ancilla alone -- bit 27, e.g. an XX error -- commutes with every gate of its slot and only swaps the two
             //  outcomes of that slot's Measure: xs, no private entries)
             // one nibble per slot (lanes 4 k .. 4 k + 3 look at the operations of slot k); dirty4 / xs4: bit 4 k = slot k
             uint32_t flipb = 0, dirty4 = 0, xs4 = 0;
-            if (!all_quiet) {                       // (a cycle without a list has no events: nothing to look at)
+            if (!quiet) {                           // (a cycle without a list, a preparation cycle: no events, nothing to look at)
                 const uint32_t evd = __ballot_sync(0xffffffffu, cw != 0xFFu && ((wv & 0x11000000u) != 0u || ((fw >> (20 + (cw >> 8))) & 1u)));
                 flipb = __ballot_sync(0xffffffffu, (wv >> 31) != 0u);
                 const uint32_t xev = __ballot_sync(0xffffffffu, ((wv >> 27) & 1u) != 0u);
@@ -841,7 +851,9 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
                      pp_out ? pp_out + ((size_t)shot * 8 + 4 * h) * 2 : nullptr, lane);
             if (h == 0) carry = fw & 511u;                        // data flips of the Hadamard-frame half are signs afterwards: half 1's sign mask
             else perm = fw & 511u;                                // data flips of the computational-frame half relabel the store
-            if (lane == 0) meas_out[2 * shot + H.final_part] = a_out | (bad ? 0x100u : 0u);
+            // (the outcomes of a preparation cycle run ahead of this one: bits 16-24 of the same words, record_cycle)
+            if (prep_stg) prep_bits |= a_out | (bad ? 0x100u : 0u);
+            else if (lane == 0) meas_out[2 * shot + H.final_part] = a_out | (bad ? 0x100u : 0u) | (prep_bits << 16);
         }
         if (COH) {
             // Ry(eps_b) on every data qubit after its bracket: register bits in place, lane bits by shuffle
@@ -856,6 +868,7 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
                 }
             }
         }
+        }   // stage
 
         // All(Measure) | data of a read-out that may follow (CS:56): one basis state drawn from |psi|^2 -- one uniform
         // against the cumulative weights in (lane, register) order.  The decoder's X correction relabels it later.
@@ -924,7 +937,7 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
     }
     if (lane == 0) {
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        atomicAdd(&counters[4], (unsigned long long)(last - first));                                     // C_SWEEPS
+        atomicAdd(&counters[4], (unsigned long long)(last - first) * (ma.with_prep ? 2ull : 1ull));     // C_SWEEPS (cycles)
         atomicAdd(&counters[8], (unsigned long long)(last - first) * ((init_basis < 0 && !alt_src) ? 2ull : 1ull));   // 8 KiB runs moved (HBM)
     }
 }

@@ -137,7 +137,10 @@ def test_host_lowering_selects_the_whole_cycle_kernel(error_models):
                            ("PDD_cooling", True), ("Dress_cooling", True)):
         prog = circuit.compile_program(error_models[model], circuit.list_lengths(error_models[model]), fusion=2,
                                        cooling=cooling, early_measure=True)
-        for info in backend.describe_program(prog):
+        infos = backend.describe_program(prog)
+        # the noiseless preparation cycle is the same whole-cycle program as the first noisy cycle (events aside)
+        assert infos[1]["prep_rides_along"], model
+        for info in infos:
             assert info["k_half"] and info["k_cycle"] and info["k_cycle1"], (model, info)
             assert sorted(info["reg_bits_z"]) == [0, 3, 5, 8] and sorted(info["reg_bits_x"]) == [1, 2, 6, 7]
             assert info["shuffle_bit"] == 4 and info["table_entries"] == [40, 40]
@@ -152,7 +155,7 @@ def test_host_lowering_selects_the_whole_cycle_kernel(error_models):
     # coherent over-rotations: the noisy cycles keep the maps of their Clifford skeleton and run on the coherent form of the
     # whole-cycle kernel (k_half / the generic-map k_cycle do not apply); the preparation cycle is the plain one
     assert [i["k_cycle1"] for i in info] == [True, True, True]
-    assert [i["coherent"] for i in info] == [False, True, True]
+    assert [i["coherent"] for i in info] == [False, True, True] and not info[1]["prep_rides_along"]
     assert [i["k_cycle"] for i in info] == [True, False, False] and [i["k_half"] for i in info] == [True, False, False]
     plain = backend.describe_program(circuit.compile_program(error_models["PDD_model"], [12, 18, 24, 78, 24], fusion=2,
                                                             early_measure=True))

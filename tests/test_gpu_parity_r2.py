@@ -308,18 +308,19 @@ def test_per_kernel_class_timing(error_models, correction_table, bitflip_table, 
     sim.close()
 
 
-@pytest.mark.parametrize("switch", ["S17_TRIVIAL_PREP", "S17_GEO"])
+@pytest.mark.parametrize("switch", ["S17_TRIVIAL_PREP", "S17_FUSE_PREP", "S17_GEO"])
 def test_launch_shortcuts_do_not_change_results(error_models, correction_table, bitflip_table, switch, monkeypatch):
     """S17_TRIVIAL_PREP (no planning launch and no shot list for the preparation cycle of a leak-free model; the call's
-    reset rides in the next k_plan) gives bit-identical counters, records, masks and stored blocks with every cycle
-    computed per shot.  S17_GEO (geometric skipping over the survival products instead of one Bernoulli draw per entry)
+    reset rides in the next k_plan) and S17_FUSE_PREP (the preparation cycle of an un-memoised run computed inside the
+    launch of the first noisy cycle, block in registers, its outcomes handed to the bookkeeping through the same words)
+    give bit-identical counters, records, masks and stored blocks with every cycle computed per shot.  S17_GEO (geometric skipping over the survival products instead of one Bernoulli draw per entry)
     draws other uniforms, so the trajectories differ: the rates of 2^18 true-probability shots agree within 4 sigma."""
     monkeypatch.setenv("S17_PREP_CACHE", "0")
     locs = [24, 36, 48, 156, 48]
     out = {}
     for val in ("1", "0"):
         monkeypatch.setenv(switch, val)
-        if switch == "S17_TRIVIAL_PREP":
+        if switch != "S17_GEO":
             n = 4096
             sim = make_sim(error_models, correction_table, bitflip_table, "PDD_model", locs, n)
             sim.backend.set_subset([0, 1, 2, 1, 1], locs)
@@ -336,10 +337,12 @@ def test_launch_shortcuts_do_not_change_results(error_models, correction_table, 
             c = sim.backend.run("s1", n, L.NOISE_PROB, seed=31)
             out[val] = (c.failed, c.not0, c.counted)
         sim.close()
-    if switch == "S17_TRIVIAL_PREP":
+    if switch != "S17_GEO":
         assert out["1"][0] == out["0"][0] and out["1"][1] == out["0"][1]
         assert np.array_equal(out["1"][2], out["0"][2]) and np.array_equal(out["1"][3], out["0"][3])
-        assert out["1"][4] == out["0"][4] - 1                     # one launch less
+        # launches of an s2 call: plan, cycle (preparation + first), plan, cycle, read-out = 5; without the fused
+        # preparation cycle one more (its own cycle launch), planned like any other cycle one more again
+        assert out["1"][4] == out["0"][4] - (2 if switch == "S17_TRIVIAL_PREP" else 1)
     else:
         for k in (0, 1):
             a, b = out["1"][k] / n, out["0"][k] / n
