@@ -75,3 +75,20 @@ def test_slot_entry_without_events_is_the_clean_table():
     assert closed(L, 4, 0, 0, 0, 0, 0, 0, 0, 0) == (-4 + 0j, 0j)
     assert closed(L, 1, 0, 0, 0, 0, 0, 0, 0, 0) == (1 + 0j, -1j)
     assert closed(L, 1, 0, 0, 0, 1, 0, 0, 0, 0) == (1 + 0j, 0j)          # leak-skipped: identity
+
+
+def test_ancilla_x_events_only_swap_the_outcomes():
+    """What k_cycle1 does instead of building private entries for a slot whose only events are net X's on its ancilla (an
+    XX error, say): X_a commutes with every Rxx of the slot, so with an odd number of them the two outcome amplitudes of
+    EVERY table entry swap -- data flips seen by the operations (bit 31: an XOR on the table index in the kernel) included --
+    and with an even number nothing changes.  Checked on the recursion (the reference's gate order) and on the closed form."""
+    L = _lib.load()
+    rnd = random.Random(5)
+    for n in (1, 2, 3, 4):
+        R = range(1 << n)
+        for f1, idx, xb in itertools.product(R, R, R):
+            flip, f2 = rnd.randrange(1 << n), rnd.randrange(1 << n)
+            clean = recursion(n, f1, idx ^ flip, 0, 0, 0, 0, 0, f2)          # the clean table at the flipped index
+            want = clean[::-1] if bin(xb).count("1") & 1 else clean
+            assert recursion(n, f1, idx, flip, 0, 0, xb, 0, f2) == want, (n, f1, idx, flip, xb, f2)
+            assert closed(L, n, f1, idx, flip, 0, 0, xb, 0, f2) == want, (n, f1, idx, flip, xb, f2)
