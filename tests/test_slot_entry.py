@@ -92,3 +92,21 @@ def test_ancilla_x_events_only_swap_the_outcomes():
             want = clean[::-1] if bin(xb).count("1") & 1 else clean
             assert recursion(n, f1, idx, flip, 0, 0, xb, 0, f2) == want, (n, f1, idx, flip, xb, f2)
             assert closed(L, n, f1, idx, flip, 0, 0, xb, 0, f2) == want, (n, f1, idx, flip, xb, f2)
+
+
+def test_ancilla_z_event_is_an_index_flip_and_a_phase():
+    """The next shortcut (not in the kernel yet): one net Z on the ancilla after operation j of a slot swaps the two
+    X_a eigen-components, which later operations then rotate the other way -- the entry equals the CLEAN entry at the index
+    with the bits of the later operations flipped, the outcome-1 amplitude negated, times i s_k lambda_k for every later
+    operation k that carries an Rx."""
+    for n in (2, 3, 4):
+        R = range(1 << n)
+        for f1, idx, f2 in itertools.product(R, R, R):
+            for j in range(n):
+                later = ((1 << n) - 1) & ~((1 << (j + 1)) - 1)
+                u, v = recursion(n, f1, idx ^ later, 0, 0, 0, 0, 0, f2)
+                ph = 1 + 0j
+                for k in range(j + 1, n):
+                    if (f2 >> k) & 1:
+                        ph *= 1j * (-1 if ((f1 >> k) ^ (idx >> k)) & 1 else 1)
+                assert recursion(n, f1, idx, 0, 0, 1 << j, 0, 0, f2) == (ph * u, -ph * v), (n, f1, idx, f2, j)
