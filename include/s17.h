@@ -198,7 +198,8 @@ typedef struct {
     uint8_t half_kernel[3];         /* 1: the fused half-cycle kernel (k_half) applies */
     uint8_t cycle_kernel[3];        /* 1: the cycle has the Clifford diagonal-frame form (tables of Gaussian integers) */
     uint8_t cycle_kernel_maps[3];   /* 1: label maps with one register bit per ancilla slot exist (k_cycle1) */
-    uint8_t shuffle_bit[3];         /* data bit transformed by the shuffle stage of the Walsh-Hadamard transform */
+    uint8_t shuffle_bit[3];         /* data bit that is a lane bit under both label maps: transformed between lanes (in
+                                       the exchange load of the Walsh-Hadamard transform; a shuffle stage before round 2) */
     uint8_t reg_bits_z[3][4];       /* data bits carried by the register index in the computational frame; slot k uses [k] */
     uint8_t reg_bits_x[3][4];       /* ... in the Hadamard frame */
     uint8_t table_entries[3][2];    /* table entries per half cycle */

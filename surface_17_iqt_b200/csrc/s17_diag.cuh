@@ -737,11 +737,13 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
                     if (COH && dir) {
                         // back to the computational frame, with Ry(eps_a) of every data qubit merged into its butterfly
                         if (half_pass) {
-                            const double al = ((lane >> P.sh_lane_bit) & 1) ? -C.preSh.x : C.preSh.x, be = C.preSh.y;
+                            if (!kDgXlane) {
+                                const double al = ((lane >> P.sh_lane_bit) & 1) ? -C.preSh.x : C.preSh.x, be = C.preSh.y;
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                const double ox = __shfl_xor_sync(0xffffffffu, p[i].x, sh_mask), oy = __shfl_xor_sync(0xffffffffu, p[i].y, sh_mask);
-                                p[i] = make_double2(fma(al, p[i].x, be * ox), fma(al, p[i].y, be * oy));
+                                for (int i = 0; i < 16; ++i) {
+                                    const double ox = __shfl_xor_sync(0xffffffffu, p[i].x, sh_mask), oy = __shfl_xor_sync(0xffffffffu, p[i].y, sh_mask);
+                                    p[i] = make_double2(fma(al, p[i].x, be * ox), fma(al, p[i].y, be * oy));
+                                }
                             }
                             dg_rot16(p, C.preA);
                         } else {
@@ -756,17 +758,21 @@ k_cycle1(const __grid_constant__ DiagProg1 P, const __grid_constant__ DiagCoh C,
                         // The one label bit that is a lane bit under both maps is transformed on the way in (kDgXlane): a
                         // lane also loads the sixteen amplitudes of the lane that differs in that bit (the same addresses,
                         // permuted over the warp: as conflict-free as its own) -- no shuffles, no 64-bit repacking
-                        const bool xl = kDgXlane && !(COH && dir);
+                        // (coherent form, on the way back: the butterfly of that bit carries Ry(eps_a), [[a, b], [b, -a]])
+                        const bool xl = kDgXlane;
                         __syncwarp();
                         if (dir) {
 #pragma unroll
                             for (int i = 0; i < 16; ++i) dg_sts(xc32 ^ P.mapB.swz16[i], p[i]);
                             __syncwarp();
                             if (xl) {
+                                const double al = COH ? (((lane >> P.sh_lane_bit) & 1) ? -C.preSh.x : C.preSh.x) : sh_sign;
+                                const double be = COH ? C.preSh.y : 1.0;
 #pragma unroll
                                 for (int i = 0; i < 16; ++i) {
                                     const double2 u = dg_lds(xa32 ^ P.mapA.swz16[i]), v = dg_lds(xa32 ^ P.mapA.swzp16[i]);
-                                    p[i] = make_double2(fma(sh_sign, u.x, v.x), fma(sh_sign, u.y, v.y));
+                                    p[i] = COH ? make_double2(fma(al, u.x, be * v.x), fma(al, u.y, be * v.y))
+                                               : make_double2(fma(al, u.x, v.x), fma(al, u.y, v.y));
                                 }
                             } else {
 #pragma unroll
